@@ -1,0 +1,182 @@
+/* lpc.h — C-ABI of the B200-native propagation engine (drop-in for the fixpoint hot path of lala-pc).
+ *
+ * Everything here is `extern "C"`, plain pointers and sizes. No torch / C++ types cross this boundary.
+ * Each entry point cites the reference interface it replaces (paths relative to the lala-pc repository).
+ *
+ * Conventions
+ *   - every function returns an `int` status (LPC_OK == 0); `lpc_last_error()` gives a message (thread-local).
+ *   - a *store* is an array of `nvars` intervals, laid out as interleaved int32 pairs {lb, ub} (8 B per
+ *     variable), i.e. the memory image of `VStore<Interval<ZLB>>::data` (used at pir.hpp:724-726, 813-815).
+ *     top = [INT32_MIN, INT32_MAX]; an interval with lb > ub is empty (bot).
+ *   - a *table* is the immutable propagator table `battery::vector<bytecode_type>` (pir.hpp:104, 115-118).
+ *   - arithmetic is 32-bit two's-complement with wrap-around (the reference has UB on overflow,
+ *     pir.hpp:759-772; generators keep magnitudes small so that the question never arises).
+ *   - one in-flight call per handle; distinct handles are independent. Handles live on the CUDA device that
+ *     was current when they were created.
+ */
+#ifndef LPC_H
+#define LPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPC_OK 0
+#define LPC_ERR_INVALID 1   /* bad argument */
+#define LPC_ERR_CUDA 2      /* CUDA runtime error, see lpc_last_error() */
+#define LPC_ERR_NOMEM 3
+#define LPC_ERR_UNSUPPORTED 4
+#define LPC_ERR_NO_DEVICE 5 /* no CUDA device: the product has no CPU fallback */
+
+/* Operator codes of `bytecode_type::op`. Numeric values follow lala-core's `Sig` enumeration (v1.2.8,
+ * un-vendored: recalled, to be static_assert-ed on the reference side). Only the ten
+ * operators PIR accepts (pir.hpp:270-273) are valid. */
+enum lpc_sig {
+  LPC_ADD = 2, LPC_MUL = 4, LPC_MIN = 6, LPC_MAX = 7,
+  LPC_TDIV = 25, LPC_FDIV = 27, LPC_CDIV = 29, LPC_EDIV = 31,
+  LPC_EQ = 46, LPC_LEQ = 48
+};
+
+/* The constraint `x = y op z`. Mirrors `struct bytecode_type {Sig op; AVar x, y, z;}` (pir.hpp:37-47; 16 B,
+ * size asserts pir.hpp:112-113). x, y, z are plain variable indices into the store (`AVar::vid()`). */
+typedef struct lpc_bytecode {
+  int32_t op;
+  int32_t x, y, z;
+} lpc_bytecode;
+
+typedef struct lpc_table lpc_table;
+typedef struct lpc_store lpc_store;
+typedef struct lpc_batch lpc_batch;
+typedef struct lpc_pc_table lpc_pc_table;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+const char* lpc_version(void);
+const char* lpc_last_error(void);
+/* Select the CUDA device for subsequent handle creation on this thread. Fails with LPC_ERR_NO_DEVICE when no
+ * GPU is present (there is deliberately no CPU path in the product). */
+int lpc_device_init(int device);
+int lpc_device_count(int* out);
+/* Number of kernels of this library launched by the calling process so far (bench.py's `gpu_launches`). */
+int64_t lpc_launch_count(void);
+
+/* ---- propagator table (PIR::deduce(tell) build step, pir.hpp:326-352) ------------------------------------ */
+/* Upload `n` records (host AoS, the order the caller wants `deduce(i)` / `ask(i)` to index — the façade
+ * sorts by (op, y, x, z) like pir.hpp:343-347 before calling). The device keeps an opcode-byte + x/y/z SoA
+ * (13 B per record) read with 128-bit loads, plus a var->records CSR for the change-driven worklist.
+ * Validates op codes and 0 <= x,y,z < nvars. The EQ/LEQ result clamp to [0,1] (pir.hpp:333-335) is a store
+ * operation and is applied by lpc_table_clamp_reified(). */
+int lpc_table_create(const lpc_bytecode* records, int64_t n, int32_t nvars, lpc_table** out);
+int lpc_table_destroy(lpc_table* t);
+/* PIR::num_deductions (pir.hpp:382-384). */
+int64_t lpc_table_size(const lpc_table* t);
+int32_t lpc_table_nvars(const lpc_table* t);
+/* PIR::load_deduce (pir.hpp:358-366): record i, from the host mirror. */
+int lpc_table_load(const lpc_table* t, int64_t i, lpc_bytecode* out);
+/* pir.hpp:333-335: for every EQ/LEQ record, meet store[x] with [0,1]. */
+int lpc_table_clamp_reified(const lpc_table* t, lpc_store* s);
+
+/* ---- interval store (VStore<Interval<ZLB>>) -------------------------------------------------------------- */
+int lpc_store_create(int32_t nvars, lpc_store** out);      /* every variable at top */
+/* Non-owning view over caller-provided device memory of nvars*8 bytes (e.g. a torch tensor's data_ptr). */
+int lpc_store_wrap_device(void* device_ptr, int32_t nvars, lpc_store** out);
+int lpc_store_destroy(lpc_store* s);
+int32_t lpc_store_nvars(const lpc_store* s);               /* PIR::vars, pir.hpp:853-855 */
+void* lpc_store_device_ptr(lpc_store* s);
+/* Plain assignment of variables [first, first+n) from host pairs {lb,ub}. */
+int lpc_store_write(lpc_store* s, int32_t first, int32_t n, const int32_t* lbub);
+/* PIR::operator[] / project (pir.hpp:840-851): copy variables [first, first+n) to host. */
+int lpc_store_read(const lpc_store* s, int32_t first, int32_t n, int32_t* lbub);
+/* PIR::embed (pir.hpp:354-356): store[var] := store[var] meet [lb,ub]; *changed as VStore::embed. */
+int lpc_store_embed(lpc_store* s, int32_t var, int32_t lb, int32_t ub, int* changed);
+/* snapshot/restore of the store part (pir.hpp:857-870): device-to-device copy. */
+int lpc_store_copy(lpc_store* dst, const lpc_store* src);
+/* PIR::is_bot (pir.hpp:831-833): 1 iff some variable is empty. PIR::is_top's store half (pir.hpp:836-838). */
+int lpc_store_is_bot(const lpc_store* s, int* out);
+int lpc_store_is_top(const lpc_store* s, int* out);
+
+/* ---- the hot path: one fixpoint (GaussSeidelIteration::fixpoint(n, deduce) call sites:
+ *      tests/pir_test.cpp:60-62, 82-86; bound_consistency_test.hpp:36-39) ---------------------------------- */
+#define LPC_MODE_AUTO 0      /* dense sweeps, switching to the change-driven worklist when few vars change */
+#define LPC_MODE_SWEEP 1     /* dense: every sweep evaluates every propagator */
+#define LPC_MODE_WORKLIST 2  /* change-driven from the first iteration on */
+
+typedef struct lpc_fixpoint_opts {
+  int32_t mode;          /* LPC_MODE_* */
+  int32_t max_sweeps;    /* 0 = unlimited */
+  int32_t stop_on_bot;   /* 1 (default contract): stop at the first sweep that observes an empty variable */
+  int32_t reserved;
+  uint64_t stream;       /* cudaStream_t to enqueue on (0 = the default stream) */
+} lpc_fixpoint_opts;
+
+typedef struct lpc_fixpoint_result {
+  int32_t has_changed;   /* the `has_changed` out-parameter of fixpoint(n, f, has_changed) */
+  int32_t is_bot;        /* store is at bot (contents then unspecified, like the reference's failed stores) */
+  int32_t sweeps;        /* iterations of the outer loop (informational: schedule dependent) */
+  int32_t dense_sweeps;  /* how many of them were dense */
+  int64_t deductions;    /* deduce() evaluations executed (informational: schedule dependent) */
+  float device_ms;       /* device time of the fixpoint kernel(s), CUDA events on `stream` */
+  int32_t reserved;
+} lpc_fixpoint_result;
+
+void lpc_fixpoint_default_opts(lpc_fixpoint_opts* o);
+/* Run deduce(i) for all i until no bound changes. Store resident on the device. Synchronous. */
+int lpc_fixpoint(const lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r);
+/* Enqueue only (no host synchronisation); collect later with lpc_fixpoint_collect on the same store. */
+int lpc_fixpoint_async(const lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o);
+int lpc_fixpoint_collect(lpc_store* s, lpc_fixpoint_result* r);
+/* Same with HOST buffers: copies `lbub` (nvars pairs) to the device, runs the fixpoint, copies it back. */
+int lpc_fixpoint_host(const lpc_table* t, int32_t* lbub, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r);
+
+/* PIR::deduce(int i) (pir.hpp:387-390, 721-817): a single propagator step, for façade parity. */
+int lpc_deduce_one(const lpc_table* t, lpc_store* s, int64_t i, int* changed);
+/* PIR::ask(int i) (pir.hpp:368-370, 417-438). */
+int lpc_ask_one(const lpc_table* t, const lpc_store* s, int64_t i, int* entailed);
+/* The ask loop of PIR::is_extractable (pir.hpp:873-884): number of entailed records; all = (n == size). */
+int lpc_ask_all(const lpc_table* t, const lpc_store* s, int64_t* n_entailed);
+/* Per-record entailment bits (one byte per record) to host. */
+int lpc_ask_bits(const lpc_table* t, const lpc_store* s, uint8_t* out);
+
+/* ---- batched mode: one store per subproblem, one thread block per store ---------------------------------- */
+/* The table is shared by all stores (the `deps.is_shared_copy()` design of pir.hpp:182-195). */
+int lpc_batch_create(const lpc_table* t, int32_t n_stores, lpc_batch** out);
+int lpc_batch_destroy(lpc_batch* b);
+void* lpc_batch_device_ptr(lpc_batch* b);                 /* [n_stores][nvars] pairs */
+int lpc_batch_write(lpc_batch* b, int32_t first_store, int32_t n, const int32_t* lbub);
+int lpc_batch_read(const lpc_batch* b, int32_t first_store, int32_t n, int32_t* lbub);
+/* EPS decomposition on the device: store k := base, then for decision j (bit j of first_id + k):
+ * var d_j keeps its lower half [lb, mid] (bit 0) or upper half [mid+1, ub] (bit 1), mid = lb + (ub-lb)/2
+ * taken on the base domain. */
+int lpc_batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                         int64_t first_id);
+
+typedef struct lpc_batch_result {
+  int64_t n_bot;         /* stores that failed */
+  int64_t n_solution;    /* non-failed stores on which every propagator is entailed (is_extractable) */
+  int64_t n_unknown;     /* the rest */
+  int32_t best_bound;    /* min over non-failed stores of lb(objective_var); INT32_MAX if none */
+  int32_t max_sweeps_seen;
+  int64_t sweeps_total;  /* sum over stores */
+  int64_t deductions;    /* deduce() evaluations executed over the whole batch */
+  float device_ms;
+  int32_t reserved;
+} lpc_batch_result;
+
+/* Fixpoint of every store of the batch. objective_var < 0: no objective. */
+int lpc_batch_fixpoint(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var, lpc_batch_result* r);
+int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var);
+int lpc_batch_collect(lpc_batch* b, lpc_batch_result* r);
+/* Same with HOST buffers ([n_stores][nvars] pairs in, fixpoints out). */
+int lpc_batch_fixpoint_host(lpc_batch* b, int32_t* lbub, const lpc_fixpoint_opts* o, int32_t objective_var,
+                            lpc_batch_result* r);
+/* Per-store flags to host: bit0 = bot, bit1 = all propagators entailed. */
+int lpc_batch_flags(const lpc_batch* b, uint8_t* out);
+/* Device address of the 4 x int64 reduction record {n_solution, n_bot, n_unknown, best_bound} of the last
+ * lpc_batch_fixpoint: the payload of the one NCCL all-reduce of the multi-GPU driver. */
+void* lpc_batch_reduction_device_ptr(lpc_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPC_H */

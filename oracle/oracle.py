@@ -1,0 +1,165 @@
+"""ctypes binding of the CPU checker (oracle/pir_oracle.cpp, oracle/pc_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs. The product package never imports this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liblpc_oracle.so")
+
+
+def build(force=False):
+    """Compile the checker with the committed Makefile (g++ only, no dependencies)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".cpp")]
+    stale = force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liblpc_oracle.so"], check=True, capture_output=True)
+    return _LIB
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("has_changed", ctypes.c_int32), ("is_bot", ctypes.c_int32), ("sweeps", ctypes.c_int64),
+                ("deductions", ctypes.c_int64), ("seconds", ctypes.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB)
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        L.lpco_pir_deduce.argtypes = [i32p, ctypes.c_int32, i32p, i32p]
+        L.lpco_pir_deduce.restype = ctypes.c_int
+        L.lpco_pir_ask.argtypes = [i32p, ctypes.c_int32, i32p]
+        L.lpco_pir_ask.restype = ctypes.c_int
+        L.lpco_pir_clamp_reified.argtypes = [i32p, ctypes.c_int32, i32p, ctypes.c_int64, i32p]
+        L.lpco_pir_clamp_reified.restype = None
+        L.lpco_pir_fixpoint.argtypes = [i32p, ctypes.c_int32, i32p, ctypes.c_int64, ctypes.c_int32,
+                                        ctypes.c_int64, ctypes.POINTER(Stats)]
+        L.lpco_pir_fixpoint.restype = None
+        L.lpco_pir_fixpoint_perm.argtypes = [i32p, ctypes.c_int32, i32p, ctypes.c_int64, i64p, ctypes.c_int32,
+                                             ctypes.c_int64, ctypes.POINTER(Stats)]
+        L.lpco_pir_fixpoint_perm.restype = None
+        L.lpco_pir_ask_all.argtypes = [i32p, ctypes.c_int32, i32p, ctypes.c_int64, u8p]
+        L.lpco_pir_ask_all.restype = ctypes.c_int64
+        L.lpco_pir_batch_fixpoint.argtypes = [i32p, ctypes.c_int32, ctypes.c_int32, i32p, ctypes.c_int64,
+                                              ctypes.c_int32, u8p, i32p, i64p]
+        L.lpco_pir_batch_fixpoint.restype = ctypes.c_double
+        L.lpco_pir_exhaustive_count.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.lpco_pir_exhaustive_count.restype = ctypes.c_int64
+        L.lpco_pir_exhaustive.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          i64p, i32p]
+        L.lpco_pir_exhaustive.restype = None
+        L.lpco_div.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+        L.lpco_div.restype = ctypes.c_int32
+        _lib = L
+    return _lib
+
+
+def _p32(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+def _store(store):
+    s = np.ascontiguousarray(store, dtype=np.int32)
+    assert s.ndim == 2 and s.shape[1] == 2, "store must be [nvars, 2] int32 {lb, ub}"
+    return s
+
+
+def _recs(records):
+    r = np.ascontiguousarray(records, dtype=np.int32)
+    assert r.ndim == 2 and r.shape[1] == 4, "records must be [n, 4] int32 {op, x, y, z}"
+    return r
+
+
+def pir_deduce(store, rec, is_bot=False):
+    """One PIR::deduce(bytecode) step (pir.hpp:721-817). Returns (store', changed, is_bot)."""
+    s = _store(store).copy()
+    r = np.asarray(rec, dtype=np.int32).copy()
+    b = ctypes.c_int32(int(is_bot))
+    c = lib().lpco_pir_deduce(_p32(s), s.shape[0], _p32(r), ctypes.byref(b))
+    return s, bool(c), bool(b.value)
+
+
+def pir_ask(store, rec):
+    s = _store(store)
+    r = np.asarray(rec, dtype=np.int32).copy()
+    return bool(lib().lpco_pir_ask(_p32(s), s.shape[0], _p32(r)))
+
+
+def pir_clamp_reified(store, records):
+    s = _store(store).copy()
+    r = _recs(records)
+    b = ctypes.c_int32(0)
+    lib().lpco_pir_clamp_reified(_p32(s), s.shape[0], _p32(r), r.shape[0], ctypes.byref(b))
+    return s
+
+
+def pir_fixpoint(store, records, stop_on_bot=True, max_sweeps=0, perm=None):
+    """Gauss-Seidel fixpoint (or a fixed-permutation chaotic iteration). Returns (store', Stats)."""
+    s = _store(store).copy()
+    r = _recs(records)
+    st = Stats()
+    if perm is None:
+        lib().lpco_pir_fixpoint(_p32(s), s.shape[0], _p32(r), r.shape[0], int(stop_on_bot), max_sweeps,
+                                ctypes.byref(st))
+    else:
+        p = np.ascontiguousarray(perm, dtype=np.int64)
+        lib().lpco_pir_fixpoint_perm(_p32(s), s.shape[0], _p32(r), r.shape[0],
+                                     p.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), int(stop_on_bot),
+                                     max_sweeps, ctypes.byref(st))
+    return s, st
+
+
+def pir_ask_all(store, records, want_bits=False):
+    s = _store(store)
+    r = _recs(records)
+    bits = np.zeros(r.shape[0], dtype=np.uint8) if want_bits else None
+    n = lib().lpco_pir_ask_all(_p32(s), s.shape[0], _p32(r), r.shape[0],
+                               bits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if want_bits else None)
+    return (int(n), bits) if want_bits else int(n)
+
+
+def pir_batch_fixpoint(stores, records, threads=1):
+    """stores [n_stores, nvars, 2]. Returns (stores', flags u8, sweeps i32, deductions, seconds)."""
+    s = np.ascontiguousarray(stores, dtype=np.int32).copy()
+    assert s.ndim == 3 and s.shape[2] == 2
+    r = _recs(records)
+    flags = np.zeros(s.shape[0], dtype=np.uint8)
+    sweeps = np.zeros(s.shape[0], dtype=np.int32)
+    ded = ctypes.c_int64(0)
+    sec = lib().lpco_pir_batch_fixpoint(_p32(s), s.shape[0], s.shape[1], _p32(r), r.shape[0], threads,
+                                        flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _p32(sweeps),
+                                        ctypes.byref(ded))
+    return s, flags, sweeps, int(ded.value), float(sec)
+
+
+def div(a, op, b):
+    return int(lib().lpco_div(a, op, b))
+
+
+EXH_KEYS = ("cases", "bot_cases", "unsound", "incomplete", "spurious_bot", "bad_entail", "entailed_cases",
+            "not_converged")
+
+
+def pir_exhaustive(op, minval, maxval, complete, threads=0, want_fixpoints=False):
+    """The exhaustive bounds-consistency property (bound_consistency_test.hpp:155-225) on the oracle.
+    Returns (dict of counters, fixpoints [cases, 7] or None)."""
+    threads = threads or (os.cpu_count() or 1)
+    n = lib().lpco_pir_exhaustive_count(minval, maxval)
+    out = np.zeros(8, dtype=np.int64)
+    fix = np.zeros((n, 7), dtype=np.int32) if want_fixpoints else None
+    lib().lpco_pir_exhaustive(op, minval, maxval, int(complete), threads,
+                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                              _p32(fix) if want_fixpoints else None)
+    return dict(zip(EXH_KEYS, (int(v) for v in out))), fix
