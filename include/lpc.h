@@ -49,7 +49,6 @@ typedef struct lpc_bytecode {
 typedef struct lpc_table lpc_table;
 typedef struct lpc_store lpc_store;
 typedef struct lpc_batch lpc_batch;
-typedef struct lpc_pc_table lpc_pc_table;
 
 /* ---- library ------------------------------------------------------------------------------------------ */
 const char* lpc_version(void);

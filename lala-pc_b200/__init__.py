@@ -1,0 +1,419 @@
+"""lala-pc_b200 — host-side binding of the B200 propagation engine (the C-ABI of include/lpc.h).
+
+Thin ctypes layer, no compute of its own: every call goes to liblpc.so (hand-written CUDA for sm_100a). There is
+no CPU fallback: importing works without a GPU (so that symbols can be inspected), but creating a table, a store
+or a batch raises `LpcError` when no CUDA device is present, and a missing liblpc.so raises at import time.
+
+Mirrors the reference's PIR interface (lala-pc include/lala/pir.hpp): `PIR.num_deductions`, `load_deduce`,
+`deduce(i)`, `ask(i)`, `embed`, `is_bot`, `is_top`, `__getitem__`, `vars`, `snapshot/restore`,
+`is_extractable`, `extract`, plus `fixpoint()` for the GaussSeidelIteration loop the tests drive by hand.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblpc.so")
+
+# lala-core Sig values of the operators PIR accepts (include/lpc.h: enum lpc_sig)
+ADD, MUL, MIN, MAX, TDIV, FDIV, CDIV, EDIV, EQ, LEQ = 2, 4, 6, 7, 25, 27, 29, 31, 46, 48
+SIG_NAMES = {ADD: "ADD", MUL: "MUL", MIN: "MIN", MAX: "MAX", TDIV: "TDIV", FDIV: "FDIV", CDIV: "CDIV",
+             EDIV: "EDIV", EQ: "EQ", LEQ: "LEQ"}
+MODE_AUTO, MODE_SWEEP, MODE_WORKLIST = 0, 1, 2
+INT_MIN, INT_MAX = -2**31, 2**31 - 1
+
+
+class LpcError(RuntimeError):
+    pass
+
+
+class FixpointOpts(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("max_sweeps", ctypes.c_int32), ("stop_on_bot", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("stream", ctypes.c_uint64)]
+
+
+class FixpointResult(ctypes.Structure):
+    _fields_ = [("has_changed", ctypes.c_int32), ("is_bot", ctypes.c_int32), ("sweeps", ctypes.c_int32),
+                ("dense_sweeps", ctypes.c_int32), ("deductions", ctypes.c_int64), ("device_ms", ctypes.c_float),
+                ("reserved", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class BatchResult(ctypes.Structure):
+    _fields_ = [("n_bot", ctypes.c_int64), ("n_solution", ctypes.c_int64), ("n_unknown", ctypes.c_int64),
+                ("best_bound", ctypes.c_int32), ("max_sweeps_seen", ctypes.c_int32),
+                ("sweeps_total", ctypes.c_int64), ("deductions", ctypes.c_int64), ("device_ms", ctypes.c_float),
+                ("reserved", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(nvcc, sm_100a). There is no CPU fallback.")
+
+_L = ctypes.CDLL(LIB_PATH)
+_vp, _i32, _i64, _u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+_pi32 = ctypes.POINTER(ctypes.c_int32)
+_pint = ctypes.POINTER(ctypes.c_int)
+_pu8 = ctypes.POINTER(ctypes.c_uint8)
+_pvp = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); also the list the symbol-export test checks against include/lpc.h
+SIGNATURES = {
+    "lpc_version": (ctypes.c_char_p, []),
+    "lpc_last_error": (ctypes.c_char_p, []),
+    "lpc_device_init": (ctypes.c_int, [ctypes.c_int]),
+    "lpc_device_count": (ctypes.c_int, [_pint]),
+    "lpc_launch_count": (_i64, []),
+    "lpc_table_create": (ctypes.c_int, [_vp, _i64, _i32, _pvp]),
+    "lpc_table_destroy": (ctypes.c_int, [_vp]),
+    "lpc_table_size": (_i64, [_vp]),
+    "lpc_table_nvars": (_i32, [_vp]),
+    "lpc_table_load": (ctypes.c_int, [_vp, _i64, _pi32]),
+    "lpc_table_clamp_reified": (ctypes.c_int, [_vp, _vp]),
+    "lpc_store_create": (ctypes.c_int, [_i32, _pvp]),
+    "lpc_store_wrap_device": (ctypes.c_int, [_vp, _i32, _pvp]),
+    "lpc_store_destroy": (ctypes.c_int, [_vp]),
+    "lpc_store_nvars": (_i32, [_vp]),
+    "lpc_store_device_ptr": (_vp, [_vp]),
+    "lpc_store_write": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
+    "lpc_store_read": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
+    "lpc_store_embed": (ctypes.c_int, [_vp, _i32, _i32, _i32, _pint]),
+    "lpc_store_copy": (ctypes.c_int, [_vp, _vp]),
+    "lpc_store_is_bot": (ctypes.c_int, [_vp, _pint]),
+    "lpc_store_is_top": (ctypes.c_int, [_vp, _pint]),
+    "lpc_fixpoint_default_opts": (None, [ctypes.POINTER(FixpointOpts)]),
+    "lpc_fixpoint": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
+    "lpc_fixpoint_async": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts)]),
+    "lpc_fixpoint_collect": (ctypes.c_int, [_vp, ctypes.POINTER(FixpointResult)]),
+    "lpc_fixpoint_host": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
+    "lpc_deduce_one": (ctypes.c_int, [_vp, _vp, _i64, _pint]),
+    "lpc_ask_one": (ctypes.c_int, [_vp, _vp, _i64, _pint]),
+    "lpc_ask_all": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_int64)]),
+    "lpc_ask_bits": (ctypes.c_int, [_vp, _vp, _pu8]),
+    "lpc_batch_create": (ctypes.c_int, [_vp, _i32, _pvp]),
+    "lpc_batch_destroy": (ctypes.c_int, [_vp]),
+    "lpc_batch_device_ptr": (_vp, [_vp]),
+    "lpc_batch_write": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
+    "lpc_batch_read": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
+    "lpc_batch_init_split": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64]),
+    "lpc_batch_fixpoint": (ctypes.c_int, [_vp, ctypes.POINTER(FixpointOpts), _i32, ctypes.POINTER(BatchResult)]),
+    "lpc_batch_fixpoint_async": (ctypes.c_int, [_vp, ctypes.POINTER(FixpointOpts), _i32]),
+    "lpc_batch_collect": (ctypes.c_int, [_vp, ctypes.POINTER(BatchResult)]),
+    "lpc_batch_fixpoint_host": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), _i32,
+                                               ctypes.POINTER(BatchResult)]),
+    "lpc_batch_flags": (ctypes.c_int, [_vp, _pu8]),
+    "lpc_batch_reduction_device_ptr": (_vp, [_vp]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _f = getattr(_L, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+lib = _L
+
+
+def _check(rc):
+    if rc != 0:
+        raise LpcError(f"lpc error {rc}: {_L.lpc_last_error().decode()}")
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    _L.lpc_device_count(ctypes.byref(n))
+    return n.value
+
+
+def device_init(device=0):
+    _check(_L.lpc_device_init(device))
+
+
+def launch_count():
+    return int(_L.lpc_launch_count())
+
+
+def sort_records(records):
+    """The host-side ordering of PIR::deduce(tell) (pir.hpp:343-347): stable sort by (op, y, x, z)."""
+    r = np.ascontiguousarray(records, dtype=np.int32)
+    order = np.lexsort((r[:, 3], r[:, 1], r[:, 2], r[:, 0]))   # last key is primary
+    return r[order]
+
+
+def _opts(mode=MODE_AUTO, max_sweeps=0, stop_on_bot=True, stream=0, switch_div=0):
+    o = FixpointOpts()
+    _L.lpc_fixpoint_default_opts(ctypes.byref(o))
+    o.mode, o.max_sweeps, o.stop_on_bot, o.stream, o.reserved = mode, max_sweeps, int(stop_on_bot), stream, switch_div
+    return o
+
+
+class Table:
+    """Immutable device propagator table (battery::vector<bytecode_type>, pir.hpp:104,115-118)."""
+
+    def __init__(self, records, nvars):
+        r = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, 4)
+        self._h = ctypes.c_void_p()
+        _check(_L.lpc_table_create(r.ctypes.data, r.shape[0], nvars, ctypes.byref(self._h)))
+        self.nvars = nvars
+
+    def __len__(self):
+        return int(_L.lpc_table_size(self._h))
+
+    def load(self, i):
+        out = (ctypes.c_int32 * 4)()
+        _check(_L.lpc_table_load(self._h, i, out))
+        return tuple(out)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _L.lpc_table_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Store:
+    """Device interval store (VStore<Interval<ZLB>>): nvars pairs {lb, ub}."""
+
+    def __init__(self, nvars=None, values=None, device_ptr=None):
+        self._h = ctypes.c_void_p()
+        if device_ptr is not None:
+            _check(_L.lpc_store_wrap_device(device_ptr, nvars, ctypes.byref(self._h)))
+        else:
+            if values is not None:
+                values = np.ascontiguousarray(values, dtype=np.int32).reshape(-1, 2)
+                nvars = values.shape[0]
+            _check(_L.lpc_store_create(nvars, ctypes.byref(self._h)))
+            if values is not None:
+                self.write(values)
+        self.nvars = nvars
+
+    def write(self, values, first=0):
+        v = np.ascontiguousarray(values, dtype=np.int32).reshape(-1, 2)
+        _check(_L.lpc_store_write(self._h, first, v.shape[0], v.ctypes.data))
+
+    def read(self, first=0, n=None):
+        n = self.nvars - first if n is None else n
+        out = np.empty((n, 2), dtype=np.int32)
+        _check(_L.lpc_store_read(self._h, first, n, out.ctypes.data))
+        return out
+
+    def embed(self, var, lb, ub):
+        c = ctypes.c_int(0)
+        _check(_L.lpc_store_embed(self._h, var, lb, ub, ctypes.byref(c)))
+        return bool(c.value)
+
+    def copy_from(self, other):
+        _check(_L.lpc_store_copy(self._h, other._h))
+
+    def is_bot(self):
+        c = ctypes.c_int(0)
+        _check(_L.lpc_store_is_bot(self._h, ctypes.byref(c)))
+        return bool(c.value)
+
+    def is_top(self):
+        c = ctypes.c_int(0)
+        _check(_L.lpc_store_is_top(self._h, ctypes.byref(c)))
+        return bool(c.value)
+
+    @property
+    def device_ptr(self):
+        return _L.lpc_store_device_ptr(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _L.lpc_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def fixpoint(table, store, **kw):
+    """GaussSeidelIteration{}.fixpoint(n, deduce) on the device (tests/pir_test.cpp:60-62)."""
+    o, r = _opts(**kw), FixpointResult()
+    _check(_L.lpc_fixpoint(table._h, store._h, ctypes.byref(o), ctypes.byref(r)))
+    return r
+
+
+def fixpoint_async(table, store, **kw):
+    o = _opts(**kw)
+    _check(_L.lpc_fixpoint_async(table._h, store._h, ctypes.byref(o)))
+
+
+def fixpoint_collect(store):
+    r = FixpointResult()
+    _check(_L.lpc_fixpoint_collect(store._h, ctypes.byref(r)))
+    return r
+
+
+def fixpoint_host(table, values, **kw):
+    """Host-buffer entry point: values ([nvars,2] int32, or a raw address) is updated in place."""
+    o, r = _opts(**kw), FixpointResult()
+    ptr = values if isinstance(values, int) else values.ctypes.data
+    _check(_L.lpc_fixpoint_host(table._h, ptr, ctypes.byref(o), ctypes.byref(r)))
+    return r
+
+
+class Batch:
+    """n_stores independent stores over one shared table (one thread block per store)."""
+
+    def __init__(self, table, n_stores):
+        self._h = ctypes.c_void_p()
+        self.table, self.n_stores, self.nvars = table, n_stores, table.nvars
+        _check(_L.lpc_batch_create(table._h, n_stores, ctypes.byref(self._h)))
+
+    def write(self, values, first=0):
+        v = np.ascontiguousarray(values, dtype=np.int32).reshape(-1, self.nvars, 2)
+        _check(_L.lpc_batch_write(self._h, first, v.shape[0], v.ctypes.data))
+
+    def read(self, first=0, n=None):
+        n = self.n_stores - first if n is None else n
+        out = np.empty((n, self.nvars, 2), dtype=np.int32)
+        _check(_L.lpc_batch_read(self._h, first, n, out.ctypes.data))
+        return out
+
+    def init_split(self, base, decision_vars, first_id=0):
+        b = np.ascontiguousarray(base, dtype=np.int32).reshape(-1, 2)
+        d = np.ascontiguousarray(decision_vars, dtype=np.int32)
+        _check(_L.lpc_batch_init_split(self._h, b.ctypes.data, d.ctypes.data, d.shape[0], first_id))
+
+    def fixpoint(self, objective_var=-1, **kw):
+        o, r = _opts(**kw), BatchResult()
+        _check(_L.lpc_batch_fixpoint(self._h, ctypes.byref(o), objective_var, ctypes.byref(r)))
+        return r
+
+    def fixpoint_async(self, objective_var=-1, **kw):
+        o = _opts(**kw)
+        _check(_L.lpc_batch_fixpoint_async(self._h, ctypes.byref(o), objective_var))
+
+    def collect(self):
+        r = BatchResult()
+        _check(_L.lpc_batch_collect(self._h, ctypes.byref(r)))
+        return r
+
+    def fixpoint_host(self, values, objective_var=-1, **kw):
+        o, r = _opts(**kw), BatchResult()
+        ptr = values if isinstance(values, int) else values.ctypes.data
+        _check(_L.lpc_batch_fixpoint_host(self._h, ptr, ctypes.byref(o), objective_var, ctypes.byref(r)))
+        return r
+
+    def flags(self):
+        out = np.empty(self.n_stores, dtype=np.uint8)
+        _check(_L.lpc_batch_flags(self._h, out.ctypes.data_as(_pu8)))
+        return out
+
+    @property
+    def device_ptr(self):
+        return _L.lpc_batch_device_ptr(self._h)
+
+    @property
+    def reduction_device_ptr(self):
+        return _L.lpc_batch_reduction_device_ptr(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _L.lpc_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class PIR:
+    """Python mirror of `PIR<VStore<Interval<ZLB>>>` over the C-ABI (same member names as pir.hpp)."""
+
+    name = "PIR"
+
+    def __init__(self, nvars):
+        self._records = np.zeros((0, 4), dtype=np.int32)
+        self.store = Store(nvars)
+        self._table = None
+
+    # -- build step: PIR::deduce(const tell_type&) (pir.hpp:326-352) --
+    def tell(self, records=(), domains=()):
+        """records: iterable of (op, x, y, z); domains: iterable of (var, lb, ub) store tells."""
+        changed = False
+        for v, lb, ub in domains:
+            changed |= self.store.embed(v, lb, ub)
+        recs = np.asarray(list(records), dtype=np.int32).reshape(-1, 4)
+        if len(recs):
+            self._records = sort_records(np.concatenate([self._records, recs]))
+            self._rebuild()
+            _check(_L.lpc_table_clamp_reified(self._table._h, self.store._h))
+            changed = True
+        return changed
+
+    def _rebuild(self):
+        if self._table is not None:
+            self._table.close()
+        self._table = Table(self._records, self.store.nvars)
+
+    @property
+    def table(self):
+        if self._table is None:
+            self._rebuild()
+        return self._table
+
+    def num_deductions(self):
+        return len(self._records)
+
+    def load_deduce(self, i):
+        return self.table.load(i)
+
+    load_deductions = load_deduce   # spelling used by BASELINE.json's north_star
+
+    def deduce(self, i):
+        c = ctypes.c_int(0)
+        _check(_L.lpc_deduce_one(self.table._h, self.store._h, i, ctypes.byref(c)))
+        return bool(c.value)
+
+    def ask(self, i):
+        c = ctypes.c_int(0)
+        _check(_L.lpc_ask_one(self.table._h, self.store._h, i, ctypes.byref(c)))
+        return bool(c.value)
+
+    def embed(self, var, lb, ub):
+        return self.store.embed(var, lb, ub)
+
+    def fixpoint(self, **kw):
+        return fixpoint(self.table, self.store, **kw)
+
+    def is_bot(self):
+        return self.store.is_bot()
+
+    def is_top(self):
+        return self.store.is_top() and self.num_deductions() == 0
+
+    def __getitem__(self, v):
+        lb, ub = self.store.read(v, 1)[0]
+        return int(lb), int(ub)
+
+    project = __getitem__
+
+    def vars(self):
+        return self.store.nvars
+
+    def snapshot(self):
+        return len(self._records), self.store.read()
+
+    def restore(self, snap):
+        n, values = snap
+        if n != len(self._records):
+            raise LpcError("restore across a table change needs the records told since the snapshot")
+        self.store.write(values)
+
+    def is_extractable(self):
+        if self.is_bot():
+            return False
+        n = ctypes.c_int64(0)
+        _check(_L.lpc_ask_all(self.table._h, self.store._h, ctypes.byref(n)))
+        return n.value == self.num_deductions()
+
+    def extract(self):
+        return self.store.read()

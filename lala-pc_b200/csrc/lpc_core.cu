@@ -1,0 +1,335 @@
+// lpc_core.cu — library plumbing: errors, device selection, propagator table upload, interval store.
+#include "lpc_internal.cuh"
+
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include <climits>
+
+namespace lpc {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return e == cudaErrorMemoryAllocation ? LPC_ERR_NOMEM : LPC_ERR_CUDA;
+}
+
+// lala-core Sig -> dense device opcode.
+static int to_dev_op(int sig) {
+  switch(sig) {
+    case LPC_ADD: return D_ADD; case LPC_MUL: return D_MUL; case LPC_MIN: return D_MIN; case LPC_MAX: return D_MAX;
+    case LPC_TDIV: return D_TDIV; case LPC_FDIV: return D_FDIV; case LPC_CDIV: return D_CDIV; case LPC_EDIV: return D_EDIV;
+    case LPC_EQ: return D_EQ; case LPC_LEQ: return D_LEQ;
+    default: return -1;
+  }
+}
+
+// ---- small store kernels -------------------------------------------------------------------------------------------
+__global__ void k_store_fill_top(int2* s, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) s[i] = make_int2(LPC_MINF, LPC_INF);
+}
+
+// out[0] |= any empty, out[1] |= any non-top
+__global__ void k_store_scan(const int2* s, int n, int* out) {
+  int bot = 0, nontop = 0;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int2 v = s[i];
+    bot |= v.x > v.y;
+    nontop |= (v.x != LPC_MINF) | (v.y != LPC_INF);
+  }
+  bot = __syncthreads_or(bot);
+  nontop = __syncthreads_or(nontop);
+  if(threadIdx.x == 0) {
+    if(bot) atomicOr(&out[0], 1);
+    if(nontop) atomicOr(&out[1], 1);
+  }
+}
+
+// VStore::embed: meet + changed
+__global__ void k_store_embed(int2* s, int var, int lb, int ub, int* changed) {
+  int2 v = s[var];
+  int c = 0;
+  if(lb > v.x) { v.x = lb; c = 1; }
+  if(ub < v.y) { v.y = ub; c = 1; }
+  if(c) s[var] = v;
+  *changed = c;
+}
+
+// pir.hpp:333-335
+__global__ void k_clamp_reified(TableDev t, int2* s) {
+  for(long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {
+    int op = t.op[i];
+    if(op == D_EQ || op == D_LEQ) {
+      int x = t.x[i];
+      atomicMax(&s[x].x, 0);
+      atomicMin(&s[x].y, 1);
+    }
+  }
+}
+
+} // namespace lpc
+
+using namespace lpc;
+
+extern "C" {
+
+const char* lpc_version(void) { return "lpc-b200 0.1 (sm_100a)"; }
+const char* lpc_last_error(void) { return g_err; }
+int64_t lpc_launch_count(void) { return g_launches.load(); }
+
+int lpc_device_count(int* out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if(e != cudaSuccess) { n = 0; cudaGetLastError(); }
+  if(out) *out = n;
+  return LPC_OK;
+}
+
+int lpc_device_init(int device) {
+  int n = 0;
+  lpc_device_count(&n);
+  if(n == 0) {
+    set_error("no CUDA device: this library has no CPU path");
+    return LPC_ERR_NO_DEVICE;
+  }
+  LPC_REQUIRE(device >= 0 && device < n, "device index out of range");
+  LPC_CUDA(cudaSetDevice(device));
+  LPC_CUDA(cudaFree(0));
+  return LPC_OK;
+}
+
+// ---- table ---------------------------------------------------------------------------------------------------------
+int lpc_table_create(const lpc_bytecode* records, int64_t n, int32_t nvars, lpc_table** out) {
+  LPC_REQUIRE(out != nullptr, "null out");
+  LPC_REQUIRE(n >= 0 && (n == 0 || records != nullptr), "bad records");
+  LPC_REQUIRE(nvars >= 0, "bad nvars");
+  LPC_REQUIRE(n < (1ll << 31) - 8, "too many records");
+  int dev = 0;
+  {
+    int cnt = 0;
+    lpc_device_count(&cnt);
+    if(cnt == 0) { set_error("no CUDA device: this library has no CPU path"); return LPC_ERR_NO_DEVICE; }
+  }
+  LPC_CUDA(cudaGetDevice(&dev));
+  // padded with NOP records to a multiple of 16: quads for the 128-bit loads, 16-B granules for the bulk copies
+  long long n_pad = (n + 15) / 16 * 16;
+  if(n_pad == 0) n_pad = 16;
+  std::vector<uint8_t> op(n_pad, (uint8_t)D_NOP);
+  std::vector<int> x(n_pad, 0), y(n_pad, 0), z(n_pad, 0);
+  lpc_table* t = new lpc_table();
+  t->device = dev;
+  for(int64_t i = 0; i < n; ++i) {
+    const lpc_bytecode& b = records[i];
+    int d = to_dev_op(b.op);
+    if(d < 0) { delete t; set_error("lpc_table_create: record %lld has unsupported op %d", (long long)i, b.op); return LPC_ERR_UNSUPPORTED; }
+    if(b.x < 0 || b.x >= nvars || b.y < 0 || b.y >= nvars || b.z < 0 || b.z >= nvars) {
+      delete t; set_error("lpc_table_create: record %lld has a variable out of range", (long long)i); return LPC_ERR_INVALID;
+    }
+    op[i] = (uint8_t)d; x[i] = b.x; y[i] = b.y; z[i] = b.z;
+    t->op_count[d]++;
+    if(d >= D_TDIV && d <= D_EDIV) t->has_div = true;
+  }
+  t->host.assign(records, records + n);
+  // var -> records incidence (counting sort)
+  std::vector<int> off((size_t)nvars + 1, 0);
+  auto each_var = [&](int64_t i, auto f) {
+    f(x[i]);
+    if(y[i] != x[i]) f(y[i]);
+    if(z[i] != x[i] && z[i] != y[i]) f(z[i]);
+  };
+  for(int64_t i = 0; i < n; ++i) each_var(i, [&](int v) { off[v + 1]++; });
+  for(int v = 0; v < nvars; ++v) off[v + 1] += off[v];
+  std::vector<int> idx((size_t)std::max(1, off[nvars]));
+  {
+    std::vector<int> cur(off.begin(), off.end() - 1);
+    for(int64_t i = 0; i < n; ++i) each_var(i, [&](int v) { idx[cur[v]++] = (int)i; });
+  }
+  auto up = [&](void** d, const void* h, size_t bytes) -> int {
+    LPC_CUDA(cudaMalloc(d, std::max<size_t>(bytes, 16)));
+    if(bytes) LPC_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+    return LPC_OK;
+  };
+  int rc;
+  if((rc = up(&t->d_op, op.data(), n_pad)) || (rc = up(&t->d_x, x.data(), n_pad * 4)) ||
+     (rc = up(&t->d_y, y.data(), n_pad * 4)) || (rc = up(&t->d_z, z.data(), n_pad * 4)) ||
+     (rc = up(&t->d_inc_off, off.data(), off.size() * 4)) || (rc = up(&t->d_inc_idx, idx.data(), idx.size() * 4))) {
+    lpc_table_destroy(t);
+    return rc;
+  }
+  t->dev.op = (const uint8_t*)t->d_op; t->dev.x = (const int*)t->d_x; t->dev.y = (const int*)t->d_y; t->dev.z = (const int*)t->d_z;
+  t->dev.n = n; t->dev.n_pad = n_pad; t->dev.nvars = nvars;
+  t->dev.inc_off = (const int*)t->d_inc_off; t->dev.inc_idx = (const int*)t->d_inc_idx;
+  cudaDeviceProp prop;
+  LPC_CUDA(cudaGetDeviceProperties(&prop, dev));
+  t->sm_count = prop.multiProcessorCount;
+  *out = t;
+  return LPC_OK;
+}
+
+int lpc_table_destroy(lpc_table* t) {
+  if(!t) return LPC_OK;
+  cudaFree(t->d_op); cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z);
+  cudaFree(t->d_inc_off); cudaFree(t->d_inc_idx); cudaFree(t->d_chunk);
+  if(t->host_store) lpc_store_destroy(t->host_store);
+  delete t;
+  return LPC_OK;
+}
+
+int64_t lpc_table_size(const lpc_table* t) { return t ? (int64_t)t->dev.n : 0; }
+int32_t lpc_table_nvars(const lpc_table* t) { return t ? t->dev.nvars : 0; }
+
+int lpc_table_load(const lpc_table* t, int64_t i, lpc_bytecode* out) {
+  LPC_REQUIRE(t && out, "null argument");
+  LPC_REQUIRE(i >= 0 && i < (int64_t)t->host.size(), "record index out of range");
+  *out = t->host[i];
+  return LPC_OK;
+}
+
+int lpc_table_clamp_reified(const lpc_table* t, lpc_store* s) {
+  LPC_REQUIRE(t && s, "null argument");
+  LPC_REQUIRE(s->nvars >= t->dev.nvars, "store smaller than the table's variable range");
+  if(t->dev.n == 0) return LPC_OK;
+  int blocks = std::min<long long>(ceil_div(t->dev.n, 256), 148 * 8);
+  k_clamp_reified<<<blocks, 256>>>(t->dev, s->d);
+  g_launches++;
+  LPC_CUDA(cudaGetLastError());
+  LPC_CUDA(cudaDeviceSynchronize());
+  return LPC_OK;
+}
+
+// ---- store ---------------------------------------------------------------------------------------------------------
+static int store_init_common(lpc_store* s) {
+  LPC_CUDA(cudaMalloc((void**)&s->d_ctl, sizeof(FixCtl)));
+  LPC_CUDA(cudaMemset(s->d_ctl, 0, sizeof(FixCtl)));
+  LPC_CUDA(cudaHostAlloc((void**)&s->h_ctl, sizeof(FixCtl), cudaHostAllocDefault));
+  memset(s->h_ctl, 0, sizeof(FixCtl));
+  LPC_CUDA(cudaEventCreate(&s->ev0));
+  LPC_CUDA(cudaEventCreate(&s->ev1));
+  return LPC_OK;
+}
+
+int lpc_store_create(int32_t nvars, lpc_store** out) {
+  LPC_REQUIRE(out != nullptr && nvars >= 0, "bad argument");
+  int cnt = 0;
+  lpc_device_count(&cnt);
+  if(cnt == 0) { set_error("no CUDA device: this library has no CPU path"); return LPC_ERR_NO_DEVICE; }
+  lpc_store* s = new lpc_store();
+  LPC_CUDA(cudaGetDevice(&s->device));
+  s->nvars = nvars;
+  s->owning = true;
+  cudaError_t e = cudaMalloc((void**)&s->d, std::max<size_t>((size_t)nvars * 8, 16));
+  if(e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(store)", __FILE__, __LINE__); }
+  if(nvars) {
+    k_store_fill_top<<<ceil_div(nvars, 256), 256>>>(s->d, nvars);
+    g_launches++;
+  }
+  int rc = store_init_common(s);
+  if(rc) { lpc_store_destroy(s); return rc; }
+  LPC_CUDA(cudaDeviceSynchronize());
+  *out = s;
+  return LPC_OK;
+}
+
+int lpc_store_wrap_device(void* device_ptr, int32_t nvars, lpc_store** out) {
+  LPC_REQUIRE(out != nullptr && nvars >= 0 && device_ptr != nullptr, "bad argument");
+  LPC_REQUIRE(((uintptr_t)device_ptr & 7) == 0, "device pointer must be 8-byte aligned");
+  lpc_store* s = new lpc_store();
+  LPC_CUDA(cudaGetDevice(&s->device));
+  s->nvars = nvars;
+  s->owning = false;
+  s->d = (int2*)device_ptr;
+  int rc = store_init_common(s);
+  if(rc) { lpc_store_destroy(s); return rc; }
+  *out = s;
+  return LPC_OK;
+}
+
+int lpc_store_destroy(lpc_store* s) {
+  if(!s) return LPC_OK;
+  if(s->owning) cudaFree(s->d);
+  cudaFree(s->wl_stamp); cudaFree(s->wl_q0); cudaFree(s->wl_q1); cudaFree(s->wl_vmark);
+  cudaFree(s->d_ctl);
+  if(s->h_ctl) cudaFreeHost(s->h_ctl);
+  if(s->ev0) cudaEventDestroy(s->ev0);
+  if(s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+  return LPC_OK;
+}
+
+int32_t lpc_store_nvars(const lpc_store* s) { return s ? s->nvars : 0; }
+void* lpc_store_device_ptr(lpc_store* s) { return s ? (void*)s->d : nullptr; }
+
+int lpc_store_write(lpc_store* s, int32_t first, int32_t n, const int32_t* lbub) {
+  LPC_REQUIRE(s && (n == 0 || lbub), "null argument");
+  LPC_REQUIRE(first >= 0 && n >= 0 && (long long)first + n <= s->nvars, "range out of bounds");
+  if(n) LPC_CUDA(cudaMemcpy(s->d + first, lbub, (size_t)n * 8, cudaMemcpyHostToDevice));
+  return LPC_OK;
+}
+
+int lpc_store_read(const lpc_store* s, int32_t first, int32_t n, int32_t* lbub) {
+  LPC_REQUIRE(s && (n == 0 || lbub), "null argument");
+  LPC_REQUIRE(first >= 0 && n >= 0 && (long long)first + n <= s->nvars, "range out of bounds");
+  if(n) LPC_CUDA(cudaMemcpy(lbub, s->d + first, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return LPC_OK;
+}
+
+int lpc_store_embed(lpc_store* s, int32_t var, int32_t lb, int32_t ub, int* changed) {
+  LPC_REQUIRE(s != nullptr, "null store");
+  LPC_REQUIRE(var >= 0 && var < s->nvars, "variable out of range");
+  k_store_embed<<<1, 1>>>(s->d, var, lb, ub, &s->d_ctl->scratch[0]);
+  g_launches++;
+  LPC_CUDA(cudaGetLastError());
+  int c = 0;
+  LPC_CUDA(cudaMemcpy(&c, &s->d_ctl->scratch[0], sizeof(int), cudaMemcpyDeviceToHost));
+  if(changed) *changed = c;
+  return LPC_OK;
+}
+
+int lpc_store_copy(lpc_store* dst, const lpc_store* src) {
+  LPC_REQUIRE(dst && src, "null argument");
+  LPC_REQUIRE(dst->nvars == src->nvars, "stores differ in size");
+  if(src->nvars) LPC_CUDA(cudaMemcpy(dst->d, src->d, (size_t)src->nvars * 8, cudaMemcpyDeviceToDevice));
+  return LPC_OK;
+}
+
+static int store_scan(const lpc_store* s, int out[2]) {
+  out[0] = out[1] = 0;
+  if(s->nvars == 0) return LPC_OK;
+  LPC_CUDA(cudaMemset(&s->d_ctl->scratch[0], 0, 2 * sizeof(int)));
+  int blocks = std::min(ceil_div(s->nvars, 256), 148 * 8);
+  k_store_scan<<<blocks, 256>>>(s->d, s->nvars, &s->d_ctl->scratch[0]);
+  g_launches++;
+  LPC_CUDA(cudaGetLastError());
+  LPC_CUDA(cudaMemcpy(out, &s->d_ctl->scratch[0], 2 * sizeof(int), cudaMemcpyDeviceToHost));
+  return LPC_OK;
+}
+
+int lpc_store_is_bot(const lpc_store* s, int* out) {
+  LPC_REQUIRE(s && out, "null argument");
+  int r[2];
+  int rc = store_scan(s, r);
+  if(rc) return rc;
+  *out = r[0];
+  return LPC_OK;
+}
+
+int lpc_store_is_top(const lpc_store* s, int* out) {
+  LPC_REQUIRE(s && out, "null argument");
+  int r[2];
+  int rc = store_scan(s, r);
+  if(rc) return rc;
+  *out = !r[1];
+  return LPC_OK;
+}
+
+} // extern "C"

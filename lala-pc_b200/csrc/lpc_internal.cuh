@@ -1,0 +1,94 @@
+// lpc_internal.cuh — handle layouts and helpers shared by the translation units of liblpc.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <atomic>
+
+#include "../../include/lpc.h"
+#include "pir_device.cuh"
+
+namespace lpc {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+extern std::atomic<int64_t> g_launches;
+
+#define LPC_CUDA(call)                                                            \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if(e__ != cudaSuccess) return lpc::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while(0)
+
+#define LPC_REQUIRE(cond, msg)                  \
+  do {                                          \
+    if(!(cond)) {                               \
+      lpc::set_error("%s: %s", __func__, msg);  \
+      return LPC_ERR_INVALID;                   \
+    }                                           \
+  } while(0)
+
+// Device image of the propagator table: opcode bytes + x/y/z index arrays (SoA, 13 B per record), padded with
+// D_NOP records to a multiple of 4 so that a thread fetches 4 records with one 32-bit and three 128-bit loads.
+struct TableDev {
+  const uint8_t* op;
+  const int* x;
+  const int* y;
+  const int* z;
+  long long n;       // records
+  long long n_pad;   // multiple of 4
+  int nvars;
+  // var -> records incidence (CSR), for the change-driven worklist
+  const int* inc_off;   // [nvars + 1]
+  const int* inc_idx;   // [3 n] (duplicates removed per record)
+};
+
+// Control block of one fixpoint run (device memory, one per store handle).
+struct FixCtl {
+  int flags[4];         // rotating per-iteration flag words: bit0 = changed, bit1 = bot
+  int sweeps;
+  int dense_sweeps;
+  int has_changed;
+  int is_bot;
+  unsigned long long deductions;
+  // worklist state
+  int q_len[4];         // rotating queue-length words (3 in use)
+  int scratch[4];
+};
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+} // namespace lpc
+
+struct lpc_store;
+struct lpc_table {
+  int device = 0;
+  std::vector<lpc_bytecode> host;   // the caller's records, caller's order (load_deduce)
+  lpc::TableDev dev{};
+  void* d_op = nullptr; void* d_x = nullptr; void* d_y = nullptr; void* d_z = nullptr;
+  void* d_inc_off = nullptr; void* d_inc_idx = nullptr;
+  bool has_div = false;
+  long long op_count[10] = {0};
+  // cost-balanced contiguous chunks of quads (4 records) for the dense sweep, one per resident block
+  int grid = 0, block = 0;
+  void* d_chunk = nullptr;          // int[grid + 1]
+  int sm_count = 0;
+  lpc_store* host_store = nullptr;  // device staging store of lpc_fixpoint_host
+};
+
+struct lpc_store {
+  int device = 0;
+  int nvars = 0;
+  int2* d = nullptr;
+  bool owning = true;
+  lpc::FixCtl* d_ctl = nullptr;
+  lpc::FixCtl* h_ctl = nullptr;     // pinned mirror
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool pending = false;
+  // worklist scratch (allocated on first use): enqueue stamps, two record queues, changed-variable marks
+  int* wl_stamp = nullptr; int* wl_q0 = nullptr; int* wl_q1 = nullptr; int* wl_vmark = nullptr;
+  long long wl_n = 0; int wl_nvars = 0;
+};

@@ -1,0 +1,477 @@
+// pir_fixpoint.cu — the single-store fixpoint: a persistent cooperative kernel for sm_100a.
+//
+// Replaces the loop  GaussSeidelIteration{}.fixpoint(pir.num_deductions(), [&](size_t i){ return pir.deduce(i); })
+// (call sites tests/pir_test.cpp:60-62, 82-86) with chaotic parallel iteration. Because every propagator is
+// monotone, the least fixpoint does not depend on the schedule; only sweep and deduction counts do.
+//
+// One launch = one fixpoint:
+//   dense sweeps   every resident block owns a contiguous, cost-balanced chunk of the table (contiguous so that
+//                  the (op, y, x, z) sort order of pir.hpp:343-347 turns into L1 locality of the gathers). A thread
+//                  fetches 4 records with one 32-bit + three 128-bit loads, gathers their 12 intervals, evaluates
+//                  the rules in registers and joins tightened bounds with atomicMax / atomicMin (RED at L2).
+//   worklist       once few variables change per sweep, the kernel switches to change-driven iterations: changed
+//                  variables enqueue their incident propagators (var -> records CSR, warp-cooperative, de-duplicated
+//                  by an iteration stamp) and only those are re-run.
+//   termination    a grid barrier per iteration; the barrier's fence invalidates L1, so the last (quiescent)
+//                  iteration reads the final store. has_changed / bot flags are formed by __syncthreads_or and one
+//                  atomic per block.
+#include "lpc_internal.cuh"
+
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstring>
+
+namespace cg = cooperative_groups;
+
+namespace lpc {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ int2 ld_itv(const int2* p) { return *p; }
+
+// Join the new domain into the store. Returns bit0 = changed, bit1 = became empty.
+template <bool TRACK>
+__device__ __forceinline__ int commit(int2* p, int2 old, const Itv& nw, int* vmark, int v, int mark) {
+  int f = 0;
+  if(nw.lb > old.x) { atomicMax(&p->x, nw.lb); f = 1; }
+  if(nw.ub < old.y) { atomicMin(&p->y, nw.ub); f = 1; }
+  if(f) {
+    if(nw.lb > nw.ub) f |= 2;
+    if(TRACK) vmark[v] = mark;
+  }
+  return f;
+}
+
+template <bool HAS_DIV, bool TRACK>
+__device__ __forceinline__ int run_record(int op, int xi, int yi, int zi, int2 a, int2 b, int2 c, int2* store,
+                                          int* vmark, int mark) {
+  Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
+  int f = (r1.is_bot() | r2.is_bot() | r3.is_bot()) ? 2 : 0;
+  deduce_regs<HAS_DIV>(op, r1, r2, r3);
+  f |= commit<TRACK>(store + xi, a, r1, vmark, xi, mark);
+  f |= commit<TRACK>(store + yi, b, r2, vmark, yi, mark);
+  f |= commit<TRACK>(store + zi, c, r3, vmark, zi, mark);
+  return f;
+}
+
+struct WlState {
+  int* stamp;      // [n] iteration id at which a record was last enqueued
+  int* queue[2];   // [n] each
+  int* vmark;      // [nvars] sweep id at which a variable last changed
+};
+
+// Enqueue every propagator incident to variable v (warp-cooperative, warp-aggregated append).
+__device__ __forceinline__ void expand_var(int v, int lane, int stampval, const TableDev& t, const WlState& w,
+                                           int* qnext, int* qlen_next) {
+  const int b = t.inc_off[v], e = t.inc_off[v + 1];
+  for(int base = b; base < e; base += 32) {
+    int j = base + lane;
+    int r = j < e ? t.inc_idx[j] : -1;
+    bool push = r >= 0 && atomicExch(&w.stamp[r], stampval) != stampval;
+    unsigned m = __ballot_sync(0xffffffffu, push);
+    if(m) {
+      int leader = __ffs(m) - 1, pos = 0;
+      if(lane == leader) pos = atomicAdd(qlen_next, __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if(push) qnext[pos + __popc(m & ((1u << lane) - 1))] = r;
+    }
+  }
+}
+
+// mode thresholds: switch_at = number of change events per sweep at or below which the worklist takes over
+// (0: never, INT_MAX: after the first sweep).
+template <bool HAS_DIV, bool TRACK>
+__global__ void __launch_bounds__(TPB) k_pir_fixpoint(TableDev t, int2* store, const int* __restrict__ chunk_q,
+                                                      FixCtl* ctl, WlState w, int max_sweeps, int stop_on_bot,
+                                                      unsigned switch_at) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const long long gtid = blockIdx.x * (long long)TPB + tid;
+  const long long gthreads = (long long)gridDim.x * TPB;
+  volatile int* vflags = ctl->flags;
+  volatile int* vbot = &ctl->is_bot;
+  volatile int* vqlen = ctl->q_len;   // 3 rotating queue-length words
+
+  // ---- prologue: a store created with an empty variable is at bot before the first sweep ----
+  {
+    int f = 0;
+    for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = store[i]; f |= v.x > v.y; }
+    if(__syncthreads_or(f) && tid == 0) atomicOr(&ctl->is_bot, 1);
+  }
+  grid.sync();
+  int sweeps = 0, dense = 0;
+  bool any_changed = false;
+  bool bot = *vbot != 0;
+  unsigned long long deductions = 0;
+  const uchar4* op4 = reinterpret_cast<const uchar4*>(t.op);
+  const int4* x4 = reinterpret_cast<const int4*>(t.x);
+  const int4* y4 = reinterpret_cast<const int4*>(t.y);
+  const int4* z4 = reinterpret_cast<const int4*>(t.z);
+  const int q0 = chunk_q[blockIdx.x], q1 = chunk_q[blockIdx.x + 1];
+  bool done = (bot && stop_on_bot) || t.n == 0;
+  bool worklist = false;
+
+  // ---- dense sweeps ----
+  while(!done) {
+    const int slot = sweeps % 3;
+    if(blockIdx.x == 0 && tid == 0) vflags[(sweeps + 1) % 3] = 0;
+    const int mark = sweeps + 1;
+    int f = 0, nchg = 0;
+    for(int q = q0 + tid; q < q1; q += TPB) {
+      const uchar4 o = op4[q];
+      const int4 X = x4[q], Y = y4[q], Z = z4[q];
+      int2 a0 = ld_itv(store + X.x), b0 = ld_itv(store + Y.x), c0 = ld_itv(store + Z.x);
+      int2 a1 = ld_itv(store + X.y), b1 = ld_itv(store + Y.y), c1 = ld_itv(store + Z.y);
+      int2 a2 = ld_itv(store + X.z), b2 = ld_itv(store + Y.z), c2 = ld_itv(store + Z.z);
+      int2 a3 = ld_itv(store + X.w), b3 = ld_itv(store + Y.w), c3 = ld_itv(store + Z.w);
+      int g0 = run_record<HAS_DIV, TRACK>(o.x, X.x, Y.x, Z.x, a0, b0, c0, store, w.vmark, mark);
+      int g1 = run_record<HAS_DIV, TRACK>(o.y, X.y, Y.y, Z.y, a1, b1, c1, store, w.vmark, mark);
+      int g2 = run_record<HAS_DIV, TRACK>(o.z, X.z, Y.z, Z.z, a2, b2, c2, store, w.vmark, mark);
+      int g3 = run_record<HAS_DIV, TRACK>(o.w, X.w, Y.w, Z.w, a3, b3, c3, store, w.vmark, mark);
+      f |= g0 | g1 | g2 | g3;
+      nchg += (g0 & 1) + (g1 & 1) + (g2 & 1) + (g3 & 1);
+    }
+    // block-level flags: one atomic per block
+    if(__syncthreads_or(f & 2) && tid == 0) atomicOr(&ctl->is_bot, 1);
+    if(TRACK) {
+      nchg = __reduce_add_sync(0xffffffffu, nchg);
+      if(lane == 0 && nchg) atomicAdd(&ctl->flags[slot], nchg);
+    }
+    else {
+      if(__syncthreads_or(f & 1) && tid == 0) atomicOr(&ctl->flags[slot], 1);
+    }
+    grid.sync();
+    ++sweeps; ++dense;
+    deductions += (unsigned long long)t.n;
+    const unsigned c = (unsigned)vflags[slot];
+    bot = *vbot != 0;
+    any_changed |= c != 0;
+    if(c == 0 || (bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) done = true;
+    else if(TRACK && c <= switch_at) { worklist = true; break; }
+  }
+
+  if(TRACK && worklist && !done) {
+    // ---- frontier expansion: variables marked in the last dense sweep enqueue their propagators ----
+    const int mark = sweeps;        // marks written by the last dense sweep
+    int it = sweeps + 1;            // stamp value == iteration id, strictly increasing
+    // queue-length words rotate over 3 slots; slot (it % 3) is the one being filled for iteration `it`
+    {
+      const long long warps = gthreads >> 5, wid = gtid >> 5;
+      for(long long base = wid * 32; base < t.nvars; base += warps * 32) {
+        long long v = base + lane;
+        bool hit = v < t.nvars && w.vmark[v] == mark;
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while(m) {
+          int src = __ffs(m) - 1;
+          m &= m - 1;
+          expand_var((int)(base + src), lane, it, t, w, w.queue[it & 1], (int*)&vqlen[it % 3]);
+        }
+      }
+    }
+    grid.sync();
+    // ---- change-driven iterations ----
+    while(true) {
+      const int len = vqlen[it % 3];
+      if(len == 0) break;
+      if(blockIdx.x == 0 && tid == 0) vqlen[(it + 2) % 3] = 0;   // last read in iteration it-1
+      const int* qcur = w.queue[it & 1];
+      int* qnext = w.queue[(it + 1) & 1];
+      int* qlen_next = (int*)&vqlen[(it + 1) % 3];
+      int f = 0;
+      const long long warps = gthreads >> 5, wid = gtid >> 5;
+      for(long long base = wid * 32; base < len; base += warps * 32) {
+        long long i = base + lane;
+        int cv0 = -1, cv1 = -1, cv2 = -1;
+        if(i < len) {
+          const int r = qcur[i];
+          const int op = t.op[r], xi = t.x[r], yi = t.y[r], zi = t.z[r];
+          int2 a = ld_itv(store + xi), b = ld_itv(store + yi), c = ld_itv(store + zi);
+          Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
+          if(r1.is_bot() | r2.is_bot() | r3.is_bot()) f |= 2;
+          deduce_regs<HAS_DIV>(op, r1, r2, r3);
+          int g0 = commit<false>(store + xi, a, r1, nullptr, 0, 0);
+          int g1 = commit<false>(store + yi, b, r2, nullptr, 0, 0);
+          int g2 = commit<false>(store + zi, c, r3, nullptr, 0, 0);
+          if(g0 & 1) cv0 = xi;
+          if(g1 & 1) cv1 = yi;
+          if(g2 & 1) cv2 = zi;
+          f |= g0 | g1 | g2;
+        }
+#pragma unroll
+        for(int k = 0; k < 3; ++k) {
+          int cv = k == 0 ? cv0 : k == 1 ? cv1 : cv2;
+          unsigned m = __ballot_sync(0xffffffffu, cv >= 0);
+          while(m) {
+            int src = __ffs(m) - 1;
+            m &= m - 1;
+            int v = __shfl_sync(0xffffffffu, cv, src);
+            expand_var(v, lane, it + 1, t, w, qnext, qlen_next);
+          }
+        }
+      }
+      if(__syncthreads_or(f & 2) && tid == 0) atomicOr(&ctl->is_bot, 1);
+      grid.sync();
+      ++sweeps;
+      deductions += (unsigned long long)len;
+      ++it;
+      bot = *vbot != 0;
+      if((bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) break;
+    }
+  }
+
+  if(blockIdx.x == 0 && tid == 0) {
+    ctl->sweeps = sweeps;
+    ctl->dense_sweeps = dense;
+    ctl->has_changed = any_changed;
+    ctl->is_bot = bot;
+    ctl->deductions = deductions;
+  }
+}
+
+// ---- single-step and entailment kernels ----------------------------------------------------------------------------
+__global__ void k_deduce_one(TableDev t, int2* store, long long i, int* out) {
+  const int op = t.op[i], xi = t.x[i], yi = t.y[i], zi = t.z[i];
+  int2 a = store[xi], b = store[yi], c = store[zi];
+  int f = run_record<true, false>(op, xi, yi, zi, a, b, c, store, nullptr, 0);
+  out[0] = f & 1;
+}
+
+__global__ void k_ask_all(TableDev t, const int2* store, unsigned long long* count, uint8_t* bits) {
+  unsigned cnt = 0;
+  for(long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {
+    const int op = t.op[i];
+    int2 a = store[t.x[i]], b = store[t.y[i]], c = store[t.z[i]];
+    bool e = ask_regs(op, Itv(a.x, a.y), Itv(b.x, b.y), Itv(c.x, c.y));
+    if(bits) bits[i] = e;
+    cnt += e;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if((threadIdx.x & 31) == 0 && cnt) atomicAdd(count, (unsigned long long)cnt);
+}
+
+typedef void (*fix_kernel_t)(TableDev, int2*, const int*, FixCtl*, WlState, int, int, unsigned);
+
+static fix_kernel_t pick_kernel(bool has_div, bool track) {
+  if(has_div) return track ? k_pir_fixpoint<true, true> : k_pir_fixpoint<true, false>;
+  return track ? k_pir_fixpoint<false, true> : k_pir_fixpoint<false, false>;
+}
+
+// Relative cost of one record per device opcode (used to balance the contiguous chunks of the dense sweep).
+static const int kOpCost[10] = {4, 10, 4, 4, 24, 24, 24, 24, 4, 4};
+
+// Partition the quads into `grid` contiguous chunks of equal estimated cost.
+static int build_chunks(lpc_table* t, int grid) {
+  if(t->d_chunk && t->grid == grid) return LPC_OK;
+  const long long nq = t->dev.n_pad / 4;
+  std::vector<uint8_t> op(t->dev.n_pad, (uint8_t)D_NOP);
+  for(size_t i = 0; i < t->host.size(); ++i) {
+    int s = t->host[i].op, d;
+    switch(s) {
+      case LPC_ADD: d = D_ADD; break; case LPC_MUL: d = D_MUL; break; case LPC_MIN: d = D_MIN; break;
+      case LPC_MAX: d = D_MAX; break; case LPC_TDIV: d = D_TDIV; break; case LPC_FDIV: d = D_FDIV; break;
+      case LPC_CDIV: d = D_CDIV; break; case LPC_EDIV: d = D_EDIV; break; case LPC_EQ: d = D_EQ; break;
+      default: d = D_LEQ; break;
+    }
+    op[i] = (uint8_t)d;
+  }
+  std::vector<long long> pre(nq + 1, 0);
+  for(long long q = 0; q < nq; ++q) {
+    int c = 0;
+    for(int k = 0; k < 4; ++k) { int o = op[q * 4 + k]; c += o < 10 ? kOpCost[o] : 1; }
+    pre[q + 1] = pre[q] + c;
+  }
+  std::vector<int> chunk(grid + 1, 0);
+  const long long total = pre[nq];
+  long long q = 0;
+  for(int b = 1; b < grid; ++b) {
+    long long target = total * b / grid;
+    while(q < nq && pre[q] < target) ++q;
+    chunk[b] = (int)q;
+  }
+  chunk[grid] = (int)nq;
+  if(t->d_chunk) { cudaFree(t->d_chunk); t->d_chunk = nullptr; }
+  LPC_CUDA(cudaMalloc(&t->d_chunk, (grid + 1) * sizeof(int)));
+  LPC_CUDA(cudaMemcpy(t->d_chunk, chunk.data(), (grid + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  t->grid = grid;
+  return LPC_OK;
+}
+
+} // namespace lpc
+
+using namespace lpc;
+
+// worklist scratch lives with the store (one in-flight call per store handle)
+static int get_scratch(lpc_store* s, const lpc_table* t, WlState* w) {
+  long long n = std::max<long long>(t->dev.n, 1);
+  if(s->wl_n < n || s->wl_nvars < s->nvars) {
+    cudaFree(s->wl_stamp); cudaFree(s->wl_q0); cudaFree(s->wl_q1); cudaFree(s->wl_vmark);
+    s->wl_stamp = s->wl_q0 = s->wl_q1 = s->wl_vmark = nullptr;
+    s->wl_n = 0; s->wl_nvars = 0;
+    LPC_CUDA(cudaMalloc((void**)&s->wl_stamp, n * 4));
+    LPC_CUDA(cudaMalloc((void**)&s->wl_q0, n * 4));
+    LPC_CUDA(cudaMalloc((void**)&s->wl_q1, n * 4));
+    LPC_CUDA(cudaMalloc((void**)&s->wl_vmark, (size_t)std::max(1, s->nvars) * 4));
+    s->wl_n = n; s->wl_nvars = s->nvars;
+  }
+  w->stamp = s->wl_stamp; w->queue[0] = s->wl_q0; w->queue[1] = s->wl_q1; w->vmark = s->wl_vmark;
+  return LPC_OK;
+}
+
+extern "C" {
+
+void lpc_fixpoint_default_opts(lpc_fixpoint_opts* o) {
+  if(!o) return;
+  memset(o, 0, sizeof(*o));
+  o->mode = LPC_MODE_AUTO;
+  o->max_sweeps = 0;
+  o->stop_on_bot = 1;
+}
+
+int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opts* o) {
+  LPC_REQUIRE(tc && s, "null argument");
+  lpc_table* t = const_cast<lpc_table*>(tc);
+  LPC_REQUIRE(s->nvars >= t->dev.nvars, "store smaller than the table's variable range");
+  lpc_fixpoint_opts def;
+  if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
+  LPC_REQUIRE(o->mode >= LPC_MODE_AUTO && o->mode <= LPC_MODE_WORKLIST, "bad mode");
+  cudaStream_t st = (cudaStream_t)o->stream;
+  const bool track = o->mode != LPC_MODE_SWEEP;
+  fix_kernel_t k = pick_kernel(t->has_div, track);
+  int per_sm = 0;
+  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TPB, 0));
+  LPC_REQUIRE(per_sm > 0, "kernel does not fit on an SM");
+  // enough blocks to fill the chip, no more than there are quads to hand out
+  long long nq = t->dev.n_pad / 4;
+  int grid = t->sm_count * per_sm;
+  long long want = std::max<long long>(1, (nq + TPB - 1) / TPB);
+  if(want < grid) grid = (int)std::max<long long>(want, 1);
+  int rc = build_chunks(t, grid);
+  if(rc) return rc;
+  WlState w{};
+  unsigned switch_at = 0;
+  if(track) {
+    rc = get_scratch(s, t, &w);
+    if(rc) return rc;
+    LPC_CUDA(cudaMemsetAsync(w.stamp, 0, std::max<long long>(t->dev.n, 1) * 4, st));
+    LPC_CUDA(cudaMemsetAsync(w.vmark, 0, std::max(1, s->nvars) * 4, st));
+    if(o->mode == LPC_MODE_WORKLIST) switch_at = 0xffffffffu;
+    else {
+      int div = o->reserved > 0 ? o->reserved : 128;
+      switch_at = (unsigned)std::max<long long>(1, t->dev.n / div);
+    }
+  }
+  LPC_CUDA(cudaMemsetAsync(s->d_ctl, 0, sizeof(FixCtl), st));
+  LPC_CUDA(cudaEventRecord(s->ev0, st));
+  TableDev td = t->dev;
+  int2* store = s->d;
+  const int* chunk = (const int*)t->d_chunk;
+  FixCtl* ctl = s->d_ctl;
+  int max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
+  void* args[] = {&td, &store, &chunk, &ctl, &w, &max_sweeps, &stop, &switch_at};
+  LPC_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(grid), dim3(TPB), args, 0, st));
+  g_launches++;
+  LPC_CUDA(cudaEventRecord(s->ev1, st));
+  LPC_CUDA(cudaMemcpyAsync(s->h_ctl, s->d_ctl, sizeof(FixCtl), cudaMemcpyDeviceToHost, st));
+  s->last_stream = st;
+  s->pending = true;
+  return LPC_OK;
+}
+
+int lpc_fixpoint_collect(lpc_store* s, lpc_fixpoint_result* r) {
+  LPC_REQUIRE(s != nullptr, "null store");
+  LPC_REQUIRE(s->pending, "no fixpoint in flight on this store");
+  LPC_CUDA(cudaStreamSynchronize(s->last_stream));
+  s->pending = false;
+  if(r) {
+    memset(r, 0, sizeof(*r));
+    r->has_changed = s->h_ctl->has_changed;
+    r->is_bot = s->h_ctl->is_bot;
+    r->sweeps = s->h_ctl->sweeps;
+    r->dense_sweeps = s->h_ctl->dense_sweeps;
+    r->deductions = (int64_t)s->h_ctl->deductions;
+    float ms = 0;
+    LPC_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    r->device_ms = ms;
+  }
+  return LPC_OK;
+}
+
+int lpc_fixpoint(const lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r) {
+  int rc = lpc_fixpoint_async(t, s, o);
+  if(rc) return rc;
+  return lpc_fixpoint_collect(s, r);
+}
+
+int lpc_fixpoint_host(const lpc_table* t, int32_t* lbub, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r) {
+  LPC_REQUIRE(t && lbub, "null argument");
+  // one cached device store per table for the host-buffer entry point
+  lpc_table* tm = const_cast<lpc_table*>(t);
+  if(!tm->host_store) {
+    int rc = lpc_store_create(t->dev.nvars, &tm->host_store);
+    if(rc) return rc;
+  }
+  lpc_store* s = tm->host_store;
+  cudaStream_t st = o ? (cudaStream_t)o->stream : nullptr;
+  size_t bytes = (size_t)t->dev.nvars * 8;
+  if(bytes) LPC_CUDA(cudaMemcpyAsync(s->d, lbub, bytes, cudaMemcpyHostToDevice, st));
+  int rc = lpc_fixpoint_async(t, s, o);
+  if(rc) return rc;
+  if(bytes) LPC_CUDA(cudaMemcpyAsync(lbub, s->d, bytes, cudaMemcpyDeviceToHost, st));
+  return lpc_fixpoint_collect(s, r);
+}
+
+int lpc_deduce_one(const lpc_table* t, lpc_store* s, int64_t i, int* changed) {
+  LPC_REQUIRE(t && s, "null argument");
+  LPC_REQUIRE(i >= 0 && i < t->dev.n, "record index out of range");   // assert at pir.hpp:388
+  LPC_REQUIRE(s->nvars >= t->dev.nvars, "store smaller than the table's variable range");
+  k_deduce_one<<<1, 1>>>(t->dev, s->d, i, &s->d_ctl->scratch[0]);
+  g_launches++;
+  LPC_CUDA(cudaGetLastError());
+  int c = 0;
+  LPC_CUDA(cudaMemcpy(&c, &s->d_ctl->scratch[0], sizeof(int), cudaMemcpyDeviceToHost));
+  if(changed) *changed = c;
+  return LPC_OK;
+}
+
+static int ask_impl(const lpc_table* t, const lpc_store* s, int64_t* n_entailed, uint8_t* host_bits) {
+  LPC_REQUIRE(t && s, "null argument");
+  LPC_REQUIRE(s->nvars >= t->dev.nvars, "store smaller than the table's variable range");
+  unsigned long long* d_cnt = nullptr;
+  uint8_t* d_bits = nullptr;
+  LPC_CUDA(cudaMalloc((void**)&d_cnt, 8));
+  LPC_CUDA(cudaMemset(d_cnt, 0, 8));
+  if(host_bits && t->dev.n) LPC_CUDA(cudaMalloc((void**)&d_bits, t->dev.n));
+  if(t->dev.n) {
+    int blocks = (int)std::min<long long>(ceil_div(t->dev.n, 256), 148 * 8);
+    k_ask_all<<<blocks, 256>>>(t->dev, s->d, d_cnt, d_bits);
+    g_launches++;
+    LPC_CUDA(cudaGetLastError());
+  }
+  unsigned long long c = 0;
+  LPC_CUDA(cudaMemcpy(&c, d_cnt, 8, cudaMemcpyDeviceToHost));
+  if(host_bits && t->dev.n) LPC_CUDA(cudaMemcpy(host_bits, d_bits, t->dev.n, cudaMemcpyDeviceToHost));
+  cudaFree(d_cnt);
+  cudaFree(d_bits);
+  if(n_entailed) *n_entailed = (int64_t)c;
+  return LPC_OK;
+}
+
+int lpc_ask_all(const lpc_table* t, const lpc_store* s, int64_t* n_entailed) { return ask_impl(t, s, n_entailed, nullptr); }
+
+int lpc_ask_bits(const lpc_table* t, const lpc_store* s, uint8_t* out) {
+  LPC_REQUIRE(out != nullptr || (t && t->dev.n == 0), "null output");
+  return ask_impl(t, s, nullptr, out);
+}
+
+int lpc_ask_one(const lpc_table* t, const lpc_store* s, int64_t i, int* entailed) {
+  LPC_REQUIRE(t && s && entailed, "null argument");
+  LPC_REQUIRE(i >= 0 && i < t->dev.n, "record index out of range");
+  std::vector<uint8_t> bits(t->dev.n);
+  int rc = ask_impl(t, s, nullptr, bits.data());
+  if(rc) return rc;
+  *entailed = bits[i];
+  return LPC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,247 @@
+"""Synthetic propagator networks of the shapes named in BASELINE.json.
+
+Pure numpy, deterministic (counter-based splitmix64; seed = 0xB2000000 + config id). Every network has a
+*planted solution*: a hidden value s[v] per variable, only records that hold under s are emitted, and every domain
+contains s[v], so propagation happens but the network can never fail. `failing_twin` moves one domain off its
+planted value so that the bot flag can be checked too. Magnitudes are bounded (|s| <= 4096, MUL operands
+|s| <= 64) so that no int32 intermediate overflows (the reference has UB there, pir.hpp:759-772).
+
+Variable classes (kept apart so that the network does not solve itself in one sweep — see `pir_network`):
+  A  addition population: x, y, z of `x = y + z`
+  M  small multiplication operands, P  products: `x = y * z` with y, z in M and x in P
+  B  0/1 variables: results of the reified `b = (y <= z)` / `b = (y == z)` over A, M and P
+
+Records are returned sorted by (op, y, x, z), the order PIR::deduce(tell) establishes (pir.hpp:343-347).
+"""
+import numpy as np
+
+ADD, MUL, MIN, MAX, TDIV, FDIV, CDIV, EDIV, EQ, LEQ = 2, 4, 6, 7, 25, 27, 29, 31, 46, 48
+SEED_BASE = 0xB2000000
+CLS_A, CLS_M, CLS_P, CLS_B = 0, 1, 2, 3
+
+
+def splitmix64(seed, stream, n):
+    """n uint64 values of stream `stream`: counter-based, so any slice is reproducible independently."""
+    with np.errstate(over="ignore"):
+        x = (np.uint64(seed) + np.uint64(stream) * np.uint64(0xD1342543DE82EF95)
+             + (np.arange(1, n + 1, dtype=np.uint64)) * np.uint64(0x9E3779B97F4A7C15))
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+class _Rng:
+    def __init__(self, seed):
+        self.seed, self.stream = seed, 0
+
+    def u64(self, n):
+        self.stream += 1
+        return splitmix64(self.seed, self.stream, n)
+
+    def below(self, n, bound):
+        """n integers in [0, bound) (bound may be an array)."""
+        return (self.u64(n) % np.asarray(bound, dtype=np.uint64)).astype(np.int64)
+
+    def between(self, n, lo, hi):
+        """n integers in [lo, hi] inclusive (arrays allowed)."""
+        lo = np.asarray(lo, dtype=np.int64)
+        hi = np.asarray(hi, dtype=np.int64)
+        return lo + self.below(n, hi - lo + 1)
+
+
+def sort_records(recs):
+    order = np.lexsort((recs[:, 3], recs[:, 1], recs[:, 2], recs[:, 0]))
+    return np.ascontiguousarray(recs[order])
+
+
+class Network:
+    """records [n,4] int32 {op,x,y,z}; store [nvars,2] int32 {lb,ub}; solution [nvars] planted values."""
+
+    def __init__(self, records, store, solution, meta):
+        self.records, self.store, self.solution, self.meta = records, store, solution, meta
+        self.nvars = store.shape[0]
+
+    def failing_twin(self):
+        """Same network with the result variable of the first ADD record pinned one off the value that its
+        (pinned) operands force: the fixpoint must end at bot."""
+        st = self.store.copy()
+        i = int(np.flatnonzero(self.records[:, 0] == ADD)[0])
+        _, x, y, z = self.records[i]
+        for v in (y, z):
+            st[v] = (self.solution[v], self.solution[v])
+        st[x] = (self.solution[x] + 1, self.solution[x] + 1)
+        return Network(self.records, st, self.solution, dict(self.meta, failing=True))
+
+
+class _ValueIndex:
+    """Variables of one class indexed by planted value: lookup of a variable with a given value near a position."""
+
+    def __init__(self, members, s, nvars, base):
+        self.nvars, self.base = nvars, base
+        key = (s[members] + base) * nvars + members
+        o = np.argsort(key, kind="stable")
+        self.keys, self.idx = key[o], members[o]
+
+    def find(self, value, pos):
+        want = value + self.base
+        q = want * self.nvars + pos
+        j = np.clip(np.searchsorted(self.keys, q), 0, len(self.keys) - 1)
+        jm = np.clip(j - 1, 0, len(self.keys) - 1)
+        ok_j = self.keys[j] // self.nvars == want
+        ok_m = self.keys[jm] // self.nvars == want
+        dj = np.abs(self.keys[j] % self.nvars - pos)
+        dm = np.abs(self.keys[jm] % self.nvars - pos)
+        use_m = ok_m & (~ok_j | (dm < dj))
+        out = np.where(use_m, self.idx[jm], self.idx[j])
+        return np.where(ok_j | ok_m, out, -1)
+
+
+def pir_network(nvars, nrec, seed, mix=((ADD, 0.5), (MUL, 0.25), (LEQ, 0.25)), window=4096, local_frac=0.8, width=16,
+                singleton_frac=0.01, class_frac=(0.60, 0.20, 0.15, 0.05), bool_fixed_frac=0.30, value_range=None):
+    """Planted-solution PIR network (configs 1, 2, 4 of BASELINE.json).
+
+    window/local_frac: the locality knob — that fraction of a record's other operands lies within +-window of y.
+
+    Why classes and slack >= 1: `x = y + z` copies tightness (slack(x) <= slack(y) + slack(z)); with ~15 incidences
+    per variable a zero-slack fraction above ~1/60 percolates and a single Gauss-Seidel sweep solves the whole
+    network (measured: 10 % singletons -> 99.9 % singletons after one sweep). Multiplication pins its small operands
+    almost immediately, so it gets its own operand / product populations; what remains is an addition network
+    whose bounds tighten over ~10 sweeps, coupled to the rest through the reified comparisons.
+    """
+    rng = _Rng(seed)
+    R = int(value_range or min(4096, max(16, nvars // 64)))        # |s| <= R
+    r_small = int(np.floor(np.sqrt(R)))             # MUL operands
+    cum = np.cumsum(np.asarray(class_frac, dtype=np.float64))
+    u = rng.below(nvars, 1 << 20) / float(1 << 20)
+    cls = np.searchsorted(cum / cum[-1], u, side="right").clip(0, 3)
+    allv = np.arange(nvars, dtype=np.int64)
+    members = [allv[cls == c] for c in range(4)]
+    for c in range(4):
+        assert len(members[c]) >= 4, "network too small for four variable classes"
+    s = rng.between(nvars, -R, R)
+    s = np.where(cls == CLS_M, rng.between(nvars, -r_small, r_small), s)
+    s = np.where(cls == CLS_P, rng.between(nvars, -r_small, r_small) * rng.between(nvars, -r_small, r_small), s)
+    s = np.where(cls == CLS_B, rng.below(nvars, 2), s)
+    idx_a = _ValueIndex(members[CLS_A], s, nvars, R)
+    idx_p = _ValueIndex(members[CLS_P], s, nvars, R)
+    idx_b = _ValueIndex(members[CLS_B], s, nvars, 0)
+    ints = allv[cls != CLS_B]
+
+    def near(pos, n):
+        """n positions near `pos`: within +-window with probability local_frac, anywhere otherwise."""
+        loc = rng.below(n, 1000) < int(local_frac * 1000)
+        off = rng.between(n, -window, window)
+        return np.where(loc, np.clip(pos + off, 0, nvars - 1), rng.below(n, nvars))
+
+    def member_at(m, pos):
+        """The member of the sorted index list `m` at or after position `pos`."""
+        return m[np.clip(np.searchsorted(m, pos), 0, len(m) - 1)]
+
+    parts = []
+    for op, frac in mix:
+        want = int(round(nrec * frac))
+        got, have = [], 0
+        while have < want:
+            n = int((want - have) * 1.6) + 64
+            if op == ADD:        # x = y + z over class A: pick y and x, look z up by value
+                y = member_at(members[CLS_A], rng.below(n, nvars))
+                x = member_at(members[CLS_A], near(y, n))
+                d = s[x] - s[y]
+                z = idx_a.find(d, near(y, n))
+                ok = (np.abs(d) <= R) & (z >= 0)
+            elif op == MUL:      # x = y * z: operands from class M, product looked up in class P
+                y = member_at(members[CLS_M], rng.below(n, nvars))
+                z = member_at(members[CLS_M], near(y, n))
+                p = s[y] * s[z]
+                x = idx_p.find(p, near(y, n))
+                ok = (np.abs(p) <= R) & (x >= 0)
+            elif op in (LEQ, EQ):    # b = (y <= z) / b = (y == z), b from the 0/1 pool
+                y = member_at(ints, rng.below(n, nvars))
+                z = member_at(ints, near(y, n))
+                truth = (s[y] <= s[z]) if op == LEQ else (s[y] == s[z])
+                x = idx_b.find(truth.astype(np.int64), near(y, n))
+                ok = x >= 0
+            elif op in (MIN, MAX):
+                y = member_at(members[CLS_A], rng.below(n, nvars))
+                z = member_at(members[CLS_A], near(y, n))
+                val = np.minimum(s[y], s[z]) if op == MIN else np.maximum(s[y], s[z])
+                x = idx_a.find(val, near(y, n))
+                ok = x >= 0
+            else:
+                raise ValueError(f"op {op} not supported by this generator")
+            ok &= (x != y) & (x != z) & (y != z)
+            rec = np.stack([np.full(n, op, dtype=np.int64), x, y, z], axis=1)[ok]
+            got.append(rec[: want - have])
+            have += len(got[-1])
+        parts.append(np.concatenate(got))
+    recs = np.concatenate(parts).astype(np.int32)
+    a = rng.between(nvars, 1, width)
+    b = rng.between(nvars, 1, width)
+    single = rng.below(nvars, 10000) < int(singleton_frac * 10000)
+    lb = np.where(single, s, s - a)
+    ub = np.where(single, s, s + b)
+    bfix = rng.below(nvars, 1000) < int(bool_fixed_frac * 1000)
+    lb = np.where(cls == CLS_B, np.where(bfix, s, 0), lb)
+    ub = np.where(cls == CLS_B, np.where(bfix, s, 1), ub)
+    store = np.stack([lb, ub], axis=1).astype(np.int32)
+    recs = sort_records(recs)
+    assert check_solution(recs, s)
+    return Network(recs, store, s.astype(np.int32), dict(nvars=nvars, nrec=len(recs), seed=seed, R=R))
+
+
+def check_solution(recs, s):
+    """Every record holds under the planted assignment."""
+    op, x, y, z = (recs[:, i].astype(np.int64) for i in range(4))
+    sx, sy, sz = s[x], s[y], s[z]
+    ok = np.ones(len(recs), dtype=bool)
+    ok &= np.where(op == ADD, sx == sy + sz, True)
+    ok &= np.where(op == MUL, sx == sy * sz, True)
+    ok &= np.where(op == LEQ, sx == (sy <= sz), True)
+    ok &= np.where(op == EQ, sx == (sy == sz), True)
+    ok &= np.where(op == MIN, sx == np.minimum(sy, sz), True)
+    ok &= np.where(op == MAX, sx == np.maximum(sy, sz), True)
+    return bool(ok.all())
+
+
+def config1():
+    """10k vars, 50k ternary propagators (x=y+z, x=y*z, x=(y<=z)) — the reference's CPU-runnable case."""
+    return pir_network(10_000, 50_000, SEED_BASE + 1)
+
+
+def config2(scale=1.0):
+    """1M vars, 5M ternary propagators; `scale` shrinks it for parity tests."""
+    return pir_network(int(1_000_000 * scale), int(5_000_000 * scale), SEED_BASE + 2)
+
+
+def config4_base():
+    """Base model of the batched EPS config: 2k vars / 10k propagators + 16 decision variables + objective.
+    Decision variables are the widest addition-class variables of the propagated base model."""
+    return pir_network(2_000, 10_000, SEED_BASE + 4, window=256, value_range=1024)
+
+
+def eps_decisions(records, root_store, n=16, min_degree=8):
+    """n decision variables — the widest domains of the root fixpoint among variables with at least `min_degree`
+    incident propagators (ties by index) — and an objective variable (the next one in that order)."""
+    nvars = len(root_store)
+    w = root_store[:, 1].astype(np.int64) - root_store[:, 0]
+    deg = np.bincount(np.asarray(records)[:, 1:].ravel(), minlength=nvars)
+    cand = np.flatnonzero(deg >= min_degree)
+    order = cand[np.lexsort((cand, -w[cand]))]
+    assert len(order) > n
+    return sorted(int(v) for v in order[:n]), int(order[n])
+
+
+def eps_stores(base_store, decision_vars, first_id, n):
+    """Host restatement of lpc_batch_init_split (include/lpc.h): subproblem id bit j halves variable d_j."""
+    out = np.repeat(base_store[None, :, :], n, axis=0).copy()
+    ids = first_id + np.arange(n, dtype=np.int64)
+    for j, v in enumerate(decision_vars):
+        lb, ub = int(base_store[v, 0]), int(base_store[v, 1])
+        mid = lb + ((ub - lb) >> 1)
+        bit = (ids >> j) & 1
+        out[:, v, 0] = np.where(bit == 1, mid + 1, lb)
+        out[:, v, 1] = np.where(bit == 1, ub, mid)
+    return out

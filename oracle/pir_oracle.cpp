@@ -23,7 +23,9 @@
 // exhaustive bounds-consistency property of tests/bound_consistency_test.hpp (see tests/test_oracle_pir.py).
 //
 // Arithmetic is int32 two's complement with explicit wrap-around (the reference's `yl + zl` etc. are UB on
-// overflow); division is made total (b == 0 -> 0, INT_MIN / -1 -> INT_MIN) where the reference would trap.
+// overflow); division is made total (b == 0 -> 0, INT_MIN / -1 -> INT_MIN) where the reference would trap. The two
+// guards `xu + 1 < 0` (pir.hpp:522) and `xl - 1 > 0` (pir.hpp:579) are read as `xu < -1` / `xl > 1`, which is what
+// an optimising compiler makes of them under the no-overflow assumption.
 
 #include <cstdint>
 #include <cstring>
@@ -200,7 +202,7 @@ Itv num_ediv(const Itv& r1, const Itv& r3) {
 
 // pir.hpp:520-574
 Itv den_fdiv(const Itv& r1, const Itv& r2) {
-  if(xl > 0 || wadd(xu, 1) < 0) {
+  if(xl > 0 || xu < -1) {   // `xu + 1 < 0` read without overflow
     if(yl > 0) {
       return Itv(wadd(vmin(fdiv(yl, wadd(xu, 1)), fdiv(yu, wadd(xu, 1))), 1),
                  vmax(fdiv(yl, xl), fdiv(yu, xl)));
@@ -243,7 +245,7 @@ Itv den_fdiv(const Itv& r1, const Itv& r2) {
 
 // pir.hpp:577-630
 Itv den_cdiv(const Itv& r1, const Itv& r2) {
-  if(wsub(xl, 1) > 0 || xu < 0) {
+  if(xl > 1 || xu < 0) {   // `xl - 1 > 0` read without overflow
     if(yl > 0) {
       return Itv(vmin(cdiv(yl, xu), cdiv(yu, xu)),
                  wsub(vmax(cdiv(yl, wsub(xl, 1)), cdiv(yu, wsub(xl, 1))), 1));

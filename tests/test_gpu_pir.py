@@ -1,0 +1,280 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle and the reference's
+golden vectors. Bar: bit-exact stores on non-failed stores, identical bot / entailment flags."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+ADD, MUL, MIN, MAX, TDIV, FDIV, CDIV, EDIV, EQ, LEQ = 2, 4, 6, 7, 25, 27, 29, 31, 46, 48
+OPS = dict(ADD=ADD, MUL=MUL, MIN=MIN, MAX=MAX, TDIV=TDIV, FDIV=FDIV, CDIV=CDIV, EDIV=EDIV, EQ=EQ, LEQ=LEQ)
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lala_pc_b200 as L
+    L.device_init(0)
+    return L
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def W():
+    from lala_pc_b200 import workloads
+    return workloads
+
+
+def modes(L):
+    return [("sweep", L.MODE_SWEEP), ("auto", L.MODE_AUTO), ("worklist", L.MODE_WORKLIST)]
+
+
+def gpu_fixpoint(L, records, store, mode, **kw):
+    t = L.Table(records, len(store))
+    s = L.Store(values=store)
+    r = L.fixpoint(t, s, mode=mode, **kw)
+    return s.read(), r, t, s
+
+
+def check_parity(L, O, records, store, mode, label=""):
+    want, st = O.pir_fixpoint(store, records)
+    got, r, t, s = gpu_fixpoint(L, records, store, mode)
+    assert bool(r.is_bot) == bool(st.is_bot), (label, "bot flag")
+    if not st.is_bot:
+        assert np.array_equal(got, want), (label, "store", int((got != want).any(1).sum()))
+        n_ent, bits = O.pir_ask_all(want, records, want_bits=True)
+        gbits = np.empty(len(records), dtype=np.uint8)
+        L._check(L.lib.lpc_ask_bits(t._h, s._h, gbits.ctypes.data_as(L._pu8)))
+        assert np.array_equal(gbits, bits), (label, "ask bits")
+        assert bool(r.has_changed) == bool(st.has_changed), (label, "has_changed")
+    return got, r, st
+
+
+def test_golden_vectors_through_the_facade(L, O, pir_kats):
+    """tests/pir_test.cpp goldens (record form) through the PIR mirror: tell, fixpoint in every mode, extract."""
+    for name, mode in modes(L):
+        for k in pir_kats:
+            pir = L.PIR(len(k["store"]))
+            pir.tell(domains=[(v, lb, ub) for v, (lb, ub) in enumerate(k["store"])])
+            pir.tell(records=k["records"])
+            assert pir.num_deductions() == len(k["records"])
+            r = pir.fixpoint(mode=mode)
+            if k["bot"]:
+                assert r.is_bot and r.has_changed and pir.is_bot(), (k["name"], name)
+                continue
+            assert not r.is_bot and not pir.is_bot(), (k["name"], name)
+            got = pir.extract()
+            after = np.array(k["after"], dtype=np.int32)
+            assert np.array_equal(got[:len(after)], after), (k["name"], name, got[:len(after)].tolist())
+            if k["ua"] is not None:
+                assert pir.is_extractable() == k["ua"], (k["name"], name)
+
+
+def test_deduce_one_matches_oracle_step_by_step(L, O, pir_kats):
+    """PIR::deduce(i) one record at a time in index order == one Gauss-Seidel sweep of the oracle."""
+    for k in pir_kats:
+        store = np.array(k["store"], dtype=np.int32)
+        recs = L.sort_records(np.array(k["records"], dtype=np.int32))
+        store = O.pir_clamp_reified(store, recs)
+        pir = L.PIR(len(store))
+        pir.store.write(store)
+        pir.tell(records=recs)
+        bot = False
+        for i in range(len(recs)):
+            assert tuple(recs[i]) == pir.load_deduce(i)
+            store, changed, bot = O.pir_deduce(store, recs[i], bot)
+            assert pir.deduce(i) == changed, (k["name"], i)
+            if not bot:
+                assert np.array_equal(pir.extract(), store), (k["name"], i)
+        for i in range(len(recs)):
+            if not bot:
+                assert pir.ask(i) == O.pir_ask(store, recs[i]), (k["name"], i)
+
+
+@pytest.mark.parametrize("mode_name", ["sweep", "auto", "worklist"])
+def test_config1_parity(L, O, W, mode_name):
+    """BASELINE.json config 1: 10k vars / 50k propagators, one fixpoint."""
+    mode = dict(modes(L))[mode_name]
+    net = W.config1()
+    got, r, st = check_parity(L, O, net.records, net.store, mode, "config1")
+    assert ((got[:, 0] <= net.solution) & (net.solution <= got[:, 1])).all()
+    twin = net.failing_twin()
+    check_parity(L, O, twin.records, twin.store, mode, "config1 failing twin")
+
+
+@pytest.mark.parametrize("mode_name", ["sweep", "auto", "worklist"])
+def test_config2_parity_tenth(L, O, W, mode_name):
+    mode = dict(modes(L))[mode_name]
+    net = W.config2(0.1)
+    check_parity(L, O, net.records, net.store, mode, "config2@0.1")
+    twin = net.failing_twin()
+    check_parity(L, O, twin.records, twin.store, mode, "config2@0.1 twin")
+
+
+def test_config2_full_size(L, O, W):
+    """BASELINE.json config 2 at full size (1M vars / 5M propagators): bit-exact against the oracle, and
+    idempotence (a second fixpoint changes nothing and costs one iteration)."""
+    net = W.config2()
+    want, st = O.pir_fixpoint(net.store, net.records)
+    t = L.Table(net.records, net.nvars)
+    for name, mode in modes(L):
+        s = L.Store(values=net.store)
+        r = L.fixpoint(t, s, mode=mode)
+        assert not r.is_bot
+        assert np.array_equal(s.read(), want), name
+        r2 = L.fixpoint(t, s, mode=mode)
+        assert not r2.has_changed and r2.sweeps == 1 and np.array_equal(s.read(), want), name
+
+
+def test_fixpoint_host_buffers(L, O, W):
+    net = W.config1()
+    want, st = O.pir_fixpoint(net.store, net.records)
+    t = L.Table(net.records, net.nvars)
+    buf = net.store.copy()
+    r = L.fixpoint_host(t, buf)
+    assert np.array_equal(buf, want) and not r.is_bot and r.deductions > 0
+
+
+def random_soup(rng, nvars, nrec, ops, lo=-30, hi=30):
+    recs = np.stack([rng.choice(ops, nrec), rng.integers(0, nvars, nrec), rng.integers(0, nvars, nrec),
+                     rng.integers(0, nvars, nrec)], axis=1).astype(np.int32)
+    a = rng.integers(lo, hi + 1, (nvars, 2))
+    store = np.stack([a.min(1), a.max(1)], axis=1).astype(np.int32)
+    wide = rng.random(nvars) < 0.3
+    store[wide] = (lo * 4, hi * 4)
+    return recs, store
+
+
+def test_random_networks_all_ops(L, O):
+    """Small random networks over all ten operators (divisions included, repeated variables allowed):
+    most fail, some do not; flags and non-failed stores must match in every mode."""
+    rng = np.random.default_rng(2026)
+    ops = list(OPS.values())
+    n_ok = 0
+    for trial in range(150):
+        nvars = int(rng.integers(3, 12))
+        recs, store = random_soup(rng, nvars, int(rng.integers(1, 10)), ops)
+        recs = L.sort_records(recs)
+        store = O.pir_clamp_reified(store, recs)
+        for name, mode in modes(L):
+            _, r, st = check_parity(L, O, recs, store, mode, f"soup {trial} {name}")
+        n_ok += not st.is_bot
+    assert n_ok >= 10
+
+
+def test_edge_cases(L, O):
+    # empty table: zero sweeps, nothing changes
+    store = np.array([[0, 5], [1, 2]], dtype=np.int32)
+    got, r, t, s = gpu_fixpoint(L, np.zeros((0, 4), dtype=np.int32), store, L.MODE_AUTO)
+    assert np.array_equal(got, store) and r.sweeps == 0 and not r.has_changed and not r.is_bot
+    # a store that is empty before the first sweep is bot with zero sweeps (bound_consistency_test.hpp:22-25)
+    store = np.array([[1, 0], [0, 5], [0, 5], [0, 0]], dtype=np.int32)
+    got, r, t, s = gpu_fixpoint(L, np.array([[ADD, 1, 2, 3]], dtype=np.int32), store, L.MODE_SWEEP)
+    assert r.is_bot and r.sweeps == 0 and not r.has_changed
+    # max_sweeps bounds the iteration
+    recs = np.array([[ADD, 3, 0, 1], [ADD, 4, 3, 2]], dtype=np.int32)
+    store = np.array([[3, 10], [3, 10], [3, 10], [-2**31, 2**31 - 1], [-2**31, 9]], dtype=np.int32)
+    got, r, t, s = gpu_fixpoint(L, recs, store, L.MODE_SWEEP, max_sweeps=1)
+    assert r.sweeps == 1
+    # error behaviour: out-of-range variable, unsupported op, store smaller than the table
+    with pytest.raises(L.LpcError):
+        L.Table(np.array([[ADD, 0, 1, 9]], dtype=np.int32), 3)
+    with pytest.raises(L.LpcError):
+        L.Table(np.array([[3, 0, 1, 2]], dtype=np.int32), 3)
+    t = L.Table(np.array([[ADD, 0, 1, 2]], dtype=np.int32), 3)
+    with pytest.raises(L.LpcError):
+        L.fixpoint(t, L.Store(2))
+    # store primitives: top, embed (meet + changed), snapshot/restore
+    s = L.Store(4)
+    assert s.is_top() and not s.is_bot()
+    assert s.embed(1, 0, 10) and not s.embed(1, -5, 20) and s.embed(1, 3, 20)
+    assert s.read(1, 1).tolist() == [[3, 10]] and not s.is_top()
+    snap = L.Store(4)
+    snap.copy_from(s)
+    assert s.embed(1, 11, 12) and s.is_bot()
+    s.copy_from(snap)
+    assert not s.is_bot() and s.read(1, 1).tolist() == [[3, 10]]
+
+
+@pytest.mark.parametrize("name", list(OPS))
+def test_exhaustive_triples_batched(L, O, name):
+    """The exhaustive bounds-consistency stores (bound_consistency_test.hpp:155-225) as one batch: every interval
+    triple in [-5,5]^3 is one 4-variable store (3 + 1 pad), one block each; results must equal the oracle's."""
+    op = OPS[name]
+    lo, hi = -5, 5
+    stats, fix = O.pir_exhaustive(op, lo, hi, name in ("EQ", "LEQ", "ADD", "MIN", "MAX"), want_fixpoints=True)
+    n = len(fix)
+    vals = [(a, b) for a in range(lo, hi + 1) for b in range(a, hi + 1)]
+    v = np.array(vals, dtype=np.int32)
+    m = len(v)
+    stores = np.zeros((n, 4, 2), dtype=np.int32)
+    idx = np.arange(n)
+    stores[:, 0] = v[idx // (m * m)]
+    stores[:, 1] = v[(idx // m) % m]
+    stores[:, 2] = v[idx % m]
+    if name in ("EQ", "LEQ"):
+        stores[:, 0, 0] = np.maximum(stores[:, 0, 0], 0)
+        stores[:, 0, 1] = np.minimum(stores[:, 0, 1], 1)
+    t = L.Table(np.array([[op, 0, 1, 2]], dtype=np.int32), 4)
+    b = L.Batch(t, n)
+    b.write(stores)
+    res = b.fixpoint()
+    got = b.read()
+    flags = b.flags()
+    want_bot = fix[:, 6].astype(bool)
+    assert np.array_equal((flags & 1).astype(bool), want_bot)
+    ok = ~want_bot
+    assert np.array_equal(got[ok, :3].reshape(-1, 6), fix[ok, :6])
+    assert res.n_bot == int(want_bot.sum()) == stats["bot_cases"]
+    assert res.n_solution == stats["entailed_cases"]
+
+
+def test_config4_batched_parity(L, O, W):
+    """BASELINE.json config 4 shape: EPS subproblems of a 2k-var / 10k-propagator model, one block per store."""
+    net = W.config4_base()
+    root, st = O.pir_fixpoint(net.store, net.records)
+    assert not st.is_bot
+    dec, obj = W.eps_decisions(net.records, root)
+    n = 2048
+    first_id = 12345
+    stores = W.eps_stores(root, dec, first_id, n)
+    want, wflags, wsweeps, _, _ = O.pir_batch_fixpoint(stores, net.records, threads=8)
+    t = L.Table(net.records, net.nvars)
+    b = L.Batch(t, n)
+    b.init_split(root, dec, first_id)
+    assert np.array_equal(b.read(), stores), "device EPS split differs from the host restatement"
+    res = b.fixpoint(objective_var=obj)
+    got, flags = b.read(), b.flags()
+    assert np.array_equal(flags, wflags)
+    ok = (wflags & 1) == 0
+    assert ok.any() and (~ok).any()
+    assert np.array_equal(got[ok], want[ok])
+    assert res.n_bot == int((~ok).sum()) and res.n_solution == int(((wflags & 2) != 0).sum())
+    assert res.n_unknown == n - res.n_bot - res.n_solution
+    assert res.best_bound == int(want[ok][:, obj, 0].min())
+    # host-buffer entry point
+    buf = stores.copy()
+    res2 = b.fixpoint_host(buf, objective_var=obj)
+    assert np.array_equal(buf[ok], want[ok]) and res2.n_bot == res.n_bot
+
+
+def test_batch_tables_larger_than_shared_memory(L, O, W):
+    """A table that does not fit next to the store ring in shared memory is read through L1/L2 instead."""
+    net = W.pir_network(4_000, 30_000, W.SEED_BASE + 41, window=512, value_range=1024)
+    root, st = O.pir_fixpoint(net.store, net.records)
+    dec, obj = W.eps_decisions(net.records, root, n=6)
+    stores = W.eps_stores(root, dec, 0, 64)
+    want, wflags, _, _, _ = O.pir_batch_fixpoint(stores, net.records, threads=8)
+    t = L.Table(net.records, net.nvars)
+    b = L.Batch(t, 64)
+    b.write(stores)
+    b.fixpoint(objective_var=obj)
+    got, flags = b.read(), b.flags()
+    assert np.array_equal(flags, wflags)
+    ok = (wflags & 1) == 0
+    assert np.array_equal(got[ok], want[ok])
