@@ -278,3 +278,34 @@ def test_batch_tables_larger_than_shared_memory(L, O, W):
     assert np.array_equal(flags, wflags)
     ok = (wflags & 1) == 0
     assert np.array_equal(got[ok], want[ok])
+
+
+@pytest.mark.parametrize("name", list(OPS))
+def test_exhaustive_triples_as_one_network(L, O, name):
+    """Every NON-failing interval triple of [-5,5]^3 as a disjoint component of one big network (3 variables and one
+    record per triple): a single launch of the single-store kernel (dense and worklist) must reproduce all of the
+    oracle's fixpoints. Covers every rule path of the dense / worklist kernels' inlined code."""
+    op = OPS[name]
+    lo, hi = -5, 5
+    _, fix = O.pir_exhaustive(op, lo, hi, False, want_fixpoints=True)
+    keep = np.flatnonzero(fix[:, 6] == 0)
+    vals = np.array([(a, b) for a in range(lo, hi + 1) for b in range(a, hi + 1)], dtype=np.int32)
+    m = len(vals)
+    n = len(keep)
+    store = np.zeros((n, 3, 2), dtype=np.int32)
+    store[:, 0] = vals[keep // (m * m)]
+    store[:, 1] = vals[(keep // m) % m]
+    store[:, 2] = vals[keep % m]
+    if name in ("EQ", "LEQ"):
+        store[:, 0, 0] = np.maximum(store[:, 0, 0], 0)
+        store[:, 0, 1] = np.minimum(store[:, 0, 1], 1)
+    store = store.reshape(-1, 2)
+    base = 3 * np.arange(n, dtype=np.int32)
+    recs = np.stack([np.full(n, op, dtype=np.int32), base, base + 1, base + 2], axis=1)
+    want = fix[keep, :6].reshape(-1, 2)
+    t = L.Table(recs, 3 * n)
+    for mname, mode in modes(L):
+        s = L.Store(values=store)
+        r = L.fixpoint(t, s, mode=mode)
+        assert not r.is_bot, (name, mname)
+        assert np.array_equal(s.read(), want), (name, mname)
