@@ -65,10 +65,31 @@ __device__ __forceinline__ void bulk_g2s_chunked(char* dst, const char* src, uns
   for(unsigned o = 0; o < bytes; o += 32768u) bulk_g2s(dst + o, src + o, min(32768u, bytes - o), bar);
 }
 
-__device__ __forceinline__ int commit_smem(int2* p, int2 old, const Itv& nw) {
+// Shared-state-space accessors with 32-bit addresses: the ring slot is selected at run time, so through generic
+// pointers the compiler falls back to generic LD / ATOM and 64-bit address arithmetic.
+__device__ __forceinline__ int2 lds_itv(unsigned addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_u8(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void reds_max(unsigned addr, int v) { asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_min(unsigned addr, int v) { asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// Join into the shared-memory store (only called when something tightened or an operand was empty).
+__device__ __forceinline__ int commit_smem(unsigned addr, int2 old, const Itv& nw) {
   int f = 0;
-  if(nw.lb > old.x) { atomicMax(&p->x, nw.lb); f = 1; }
-  if(nw.ub < old.y) { atomicMin(&p->y, nw.ub); f = 1; }
+  if(nw.lb > old.x) { reds_max(addr, nw.lb); f = 1; }
+  if(nw.ub < old.y) { reds_min(addr + 4, nw.ub); f = 1; }
   if(f && nw.lb > nw.ub) f |= 2;
   return f;
 }
@@ -115,6 +136,7 @@ __global__ void k_pir_batch(TableDev t, int2* stores, int n_stores, int sbytes, 
     sop = reinterpret_cast<const uint8_t*>(tb + (size_t)npad * 12);
     mbar_wait(&bars[2], 0);
   }
+  const unsigned a_x = smem_u32(sx), a_y = smem_u32(sy), a_z = smem_u32(sz), a_op = smem_u32(sop);   // valid iff TABLE_SMEM
 
   // block-level accumulators (thread 0)
   long long a_sol = 0, a_bot = 0, a_unk = 0, a_sweeps = 0, a_ded = 0;
@@ -136,6 +158,7 @@ __global__ void k_pir_batch(TableDev t, int2* stores, int n_stores, int sbytes, 
     mbar_wait(&bars[b], phase[b]);
     phase[b] ^= 1;
     int2* S = ring[b];
+    const unsigned a_S = smem_u32(S);
 
     // bot before the first sweep?
     if(tid == 0) *s_bot = 0;
@@ -147,12 +170,19 @@ __global__ void k_pir_batch(TableDev t, int2* stores, int n_stores, int sbytes, 
     while(changed) {
       int f = 0;
       for(int i = tid; i < npad; i += nthr) {
-        const int op = sop[i], xi = sx[i], yi = sy[i], zi = sz[i];
-        const int2 a = S[xi], bb = S[yi], c = S[zi];
+        int op, xi, yi, zi;
+        if(TABLE_SMEM) { op = lds_u8(a_op + i); xi = lds_s32(a_x + 4 * i); yi = lds_s32(a_y + 4 * i); zi = lds_s32(a_z + 4 * i); }
+        else { op = sop[i]; xi = sx[i]; yi = sy[i]; zi = sz[i]; }
+        const unsigned ax = a_S + 8u * xi, ay = a_S + 8u * yi, az = a_S + 8u * zi;
+        const int2 a = lds_itv(ax), bb = lds_itv(ay), c = lds_itv(az);
         Itv r1(a.x, a.y), r2(bb.x, bb.y), r3(c.x, c.y);
-        if(r1.is_bot() | r2.is_bot() | r3.is_bot()) f |= 2;
         deduce_regs<HAS_DIV>(op, r1, r2, r3);
-        f |= commit_smem(S + xi, a, r1) | commit_smem(S + yi, bb, r2) | commit_smem(S + zi, c, r3);
+        const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > bb.x) | (r2.ub < bb.y) | (r3.lb > c.x) | (r3.ub < c.y)
+                        | (a.x > a.y) | (bb.x > bb.y) | (c.x > c.y);
+        if(slow) {
+          if((a.x > a.y) | (bb.x > bb.y) | (c.x > c.y)) f |= 2;
+          f |= commit_smem(ax, a, r1) | commit_smem(ay, bb, r2) | commit_smem(az, c, r3);
+        }
       }
       ++sweeps;
       if(f & 2) *s_bot = 1;

@@ -115,12 +115,25 @@ template <bool HAS_DIV>
 LPC_HD void deduce_regs(int op, Itv& r1, Itv& r2, Itv& r3) {
   switch(op) {
     case D_ADD: {
-      r1.lb = (yl == LPC_MINF || zl == LPC_MINF) ? xl : max(xl, wadd(yl, zl));
-      r1.ub = (yu == LPC_INF || zu == LPC_INF) ? xu : min(xu, wadd(yu, zu));
-      r2.lb = (xl == LPC_MINF || zu == LPC_INF) ? yl : max(yl, wsub(xl, zu));
-      r2.ub = (xu == LPC_INF || zl == LPC_MINF) ? yu : min(yu, wsub(xu, zl));
-      r3.lb = (xl == LPC_MINF || yu == LPC_INF) ? zl : max(zl, wsub(xl, yu));
-      r3.ub = (xu == LPC_INF || yl == LPC_MINF) ? zu : min(zu, wsub(xu, yl));
+      // fast path: no infinite bound anywhere -> six fused add+min/max, no guards (identical results: the guards
+      // of pir.hpp:759-764 only fire on exact INT_MIN / INT_MAX bounds)
+      const int lo = min(min(xl, yl), zl), hi = max(max(xu, yu), zu);
+      if(lo != LPC_MINF && hi != LPC_INF) {
+        r1.lb = max(xl, wadd(yl, zl));
+        r1.ub = min(xu, wadd(yu, zu));
+        r2.lb = max(yl, wsub(xl, zu));
+        r2.ub = min(yu, wsub(xu, zl));
+        r3.lb = max(zl, wsub(xl, yu));
+        r3.ub = min(zu, wsub(xu, yl));
+      }
+      else {
+        r1.lb = (yl == LPC_MINF || zl == LPC_MINF) ? xl : max(xl, wadd(yl, zl));
+        r1.ub = (yu == LPC_INF || zu == LPC_INF) ? xu : min(xu, wadd(yu, zu));
+        r2.lb = (xl == LPC_MINF || zu == LPC_INF) ? yl : max(yl, wsub(xl, zu));
+        r2.ub = (xu == LPC_INF || zl == LPC_MINF) ? yu : min(yu, wsub(xu, zl));
+        r3.lb = (xl == LPC_MINF || yu == LPC_INF) ? zl : max(zl, wsub(xl, yu));
+        r3.ub = (xu == LPC_INF || yl == LPC_MINF) ? zu : min(zu, wsub(xu, yl));
+      }
       break;
     }
     case D_MUL: {

@@ -5,10 +5,12 @@
 // monotone, the least fixpoint does not depend on the schedule; only sweep and deduction counts do.
 //
 // One launch = one fixpoint:
-//   dense sweeps   every resident block owns a contiguous, cost-balanced chunk of the table (contiguous so that
-//                  the (op, y, x, z) sort order of pir.hpp:343-347 turns into L1 locality of the gathers). A thread
-//                  fetches 4 records with one 32-bit + three 128-bit loads, gathers their 12 intervals, evaluates
-//                  the rules in registers and joins tightened bounds with atomicMax / atomicMin (RED at L2).
+//   dense sweeps   the table is cut into its opcode segments (it is sorted by (op, y, x, z), pir.hpp:343-347) and
+//                  every resident block owns the same contiguous fraction of EVERY segment: contiguous so that the
+//                  sort order turns into L1 locality of the gathers, per segment so that all blocks see the same
+//                  operator mix and reach the grid barrier together. A thread fetches RPT records with vector loads
+//                  (RPT = 4: one 32-bit + three 128-bit loads), gathers their intervals, evaluates the rules in
+//                  registers and joins tightened bounds with atomicMax / atomicMin (RED at L2).
 //   worklist       once few variables change per sweep, the kernel switches to change-driven iterations: changed
 //                  variables enqueue their incident propagators (var -> records CSR, warp-cooperative, de-duplicated
 //                  by an iteration stamp) and only those are re-run.
@@ -19,6 +21,7 @@
 
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace cg = cooperative_groups;
@@ -26,8 +29,14 @@ namespace cg = cooperative_groups;
 namespace lpc {
 
 constexpr int TPB = 256;
+constexpr int MAX_SEG = 16;
 
-__device__ __forceinline__ int2 ld_itv(const int2* p) { return *p; }
+// Opcode segments of the padded table, in quads (4 records). nseg == 0 never happens (an empty table has one
+// all-padding segment).
+struct SegTable {
+  int nseg;
+  int q[MAX_SEG + 1];
+};
 
 // Join the new domain into the store. Returns bit0 = changed, bit1 = became empty.
 template <bool TRACK>
@@ -42,15 +51,22 @@ __device__ __forceinline__ int commit(int2* p, int2 old, const Itv& nw, int* vma
   return f;
 }
 
+// One propagator evaluation: rules in registers, then (rarely) the joins. The common case - nothing tightens, no
+// operand empty - is nine compares folded into one predicate and a single not-taken branch.
 template <bool HAS_DIV, bool TRACK>
 __device__ __forceinline__ int run_record(int op, int xi, int yi, int zi, int2 a, int2 b, int2 c, int2* store,
                                           int* vmark, int mark) {
   Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
-  int f = (r1.is_bot() | r2.is_bot() | r3.is_bot()) ? 2 : 0;
   deduce_regs<HAS_DIV>(op, r1, r2, r3);
-  f |= commit<TRACK>(store + xi, a, r1, vmark, xi, mark);
-  f |= commit<TRACK>(store + yi, b, r2, vmark, yi, mark);
-  f |= commit<TRACK>(store + zi, c, r3, vmark, zi, mark);
+  const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > b.x) | (r2.ub < b.y) | (r3.lb > c.x) | (r3.ub < c.y)
+                  | (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
+  int f = 0;
+  if(slow) {
+    f = ((a.x > a.y) | (b.x > b.y) | (c.x > c.y)) ? 2 : 0;
+    f |= commit<TRACK>(store + xi, a, r1, vmark, xi, mark);
+    f |= commit<TRACK>(store + yi, b, r2, vmark, yi, mark);
+    f |= commit<TRACK>(store + zi, c, r3, vmark, zi, mark);
+  }
   return f;
 }
 
@@ -78,12 +94,43 @@ __device__ __forceinline__ void expand_var(int v, int lane, int stampval, const 
   }
 }
 
-// mode thresholds: switch_at = number of change events per sweep at or below which the worklist takes over
-// (0: never, INT_MAX: after the first sweep).
-template <bool HAS_DIV, bool TRACK>
-__global__ void __launch_bounds__(TPB) k_pir_fixpoint(TableDev t, int2* store, const int* __restrict__ chunk_q,
-                                                      FixCtl* ctl, WlState w, int max_sweeps, int stop_on_bot,
-                                                      unsigned switch_at) {
+// RPT records of unit u: opcode bytes and x / y / z indices with one vector load each.
+template <int RPT> struct Unit;
+template <> struct Unit<4> {
+  int op[4], x[4], y[4], z[4];
+  __device__ __forceinline__ void load(const TableDev& t, int u) {
+    const uchar4 o = reinterpret_cast<const uchar4*>(t.op)[u];
+    const int4 X = reinterpret_cast<const int4*>(t.x)[u], Y = reinterpret_cast<const int4*>(t.y)[u],
+               Z = reinterpret_cast<const int4*>(t.z)[u];
+    op[0] = o.x; op[1] = o.y; op[2] = o.z; op[3] = o.w;
+    x[0] = X.x; x[1] = X.y; x[2] = X.z; x[3] = X.w;
+    y[0] = Y.x; y[1] = Y.y; y[2] = Y.z; y[3] = Y.w;
+    z[0] = Z.x; z[1] = Z.y; z[2] = Z.z; z[3] = Z.w;
+  }
+};
+template <> struct Unit<2> {
+  int op[2], x[2], y[2], z[2];
+  __device__ __forceinline__ void load(const TableDev& t, int u) {
+    const uchar2 o = reinterpret_cast<const uchar2*>(t.op)[u];
+    const int2 X = reinterpret_cast<const int2*>(t.x)[u], Y = reinterpret_cast<const int2*>(t.y)[u],
+               Z = reinterpret_cast<const int2*>(t.z)[u];
+    op[0] = o.x; op[1] = o.y;
+    x[0] = X.x; x[1] = X.y; y[0] = Y.x; y[1] = Y.y; z[0] = Z.x; z[1] = Z.y;
+  }
+};
+template <> struct Unit<1> {
+  int op[1], x[1], y[1], z[1];
+  __device__ __forceinline__ void load(const TableDev& t, int u) {
+    op[0] = t.op[u]; x[0] = t.x[u]; y[0] = t.y[u]; z[0] = t.z[u];
+  }
+};
+
+// switch_at = number of change events per sweep at or below which the worklist takes over
+// (0: never, UINT_MAX: after the first sweep).
+template <bool HAS_DIV, bool TRACK, int RPT, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_pir_fixpoint(TableDev t, int2* store, SegTable seg, FixCtl* ctl,
+                                                            WlState w, int max_sweeps, int stop_on_bot,
+                                                            unsigned switch_at) {
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -104,13 +151,9 @@ __global__ void __launch_bounds__(TPB) k_pir_fixpoint(TableDev t, int2* store, c
   bool any_changed = false;
   bool bot = *vbot != 0;
   unsigned long long deductions = 0;
-  const uchar4* op4 = reinterpret_cast<const uchar4*>(t.op);
-  const int4* x4 = reinterpret_cast<const int4*>(t.x);
-  const int4* y4 = reinterpret_cast<const int4*>(t.y);
-  const int4* z4 = reinterpret_cast<const int4*>(t.z);
-  const int q0 = chunk_q[blockIdx.x], q1 = chunk_q[blockIdx.x + 1];
   bool done = (bot && stop_on_bot) || t.n == 0;
   bool worklist = false;
+  constexpr int UPQ = 4 / RPT;   // units per quad
 
   // ---- dense sweeps ----
   while(!done) {
@@ -118,19 +161,23 @@ __global__ void __launch_bounds__(TPB) k_pir_fixpoint(TableDev t, int2* store, c
     if(blockIdx.x == 0 && tid == 0) vflags[(sweeps + 1) % 3] = 0;
     const int mark = sweeps + 1;
     int f = 0, nchg = 0;
-    for(int q = q0 + tid; q < q1; q += TPB) {
-      const uchar4 o = op4[q];
-      const int4 X = x4[q], Y = y4[q], Z = z4[q];
-      int2 a0 = ld_itv(store + X.x), b0 = ld_itv(store + Y.x), c0 = ld_itv(store + Z.x);
-      int2 a1 = ld_itv(store + X.y), b1 = ld_itv(store + Y.y), c1 = ld_itv(store + Z.y);
-      int2 a2 = ld_itv(store + X.z), b2 = ld_itv(store + Y.z), c2 = ld_itv(store + Z.z);
-      int2 a3 = ld_itv(store + X.w), b3 = ld_itv(store + Y.w), c3 = ld_itv(store + Z.w);
-      int g0 = run_record<HAS_DIV, TRACK>(o.x, X.x, Y.x, Z.x, a0, b0, c0, store, w.vmark, mark);
-      int g1 = run_record<HAS_DIV, TRACK>(o.y, X.y, Y.y, Z.y, a1, b1, c1, store, w.vmark, mark);
-      int g2 = run_record<HAS_DIV, TRACK>(o.z, X.z, Y.z, Z.z, a2, b2, c2, store, w.vmark, mark);
-      int g3 = run_record<HAS_DIV, TRACK>(o.w, X.w, Y.w, Z.w, a3, b3, c3, store, w.vmark, mark);
-      f |= g0 | g1 | g2 | g3;
-      nchg += (g0 & 1) + (g1 & 1) + (g2 & 1) + (g3 & 1);
+    for(int s = 0; s < seg.nseg; ++s) {
+      const long long sq0 = seg.q[s], len = seg.q[s + 1] - sq0;
+      const int u0 = (int)((sq0 + len * blockIdx.x / gridDim.x) * UPQ);
+      const int u1 = (int)((sq0 + len * (blockIdx.x + 1) / gridDim.x) * UPQ);
+      for(int u = u0 + tid; u < u1; u += TPB) {
+        Unit<RPT> r;
+        r.load(t, u);
+        int2 a[RPT], b[RPT], c[RPT];
+#pragma unroll
+        for(int k = 0; k < RPT; ++k) { a[k] = store[r.x[k]]; b[k] = store[r.y[k]]; c[k] = store[r.z[k]]; }
+#pragma unroll
+        for(int k = 0; k < RPT; ++k) {
+          const int g = run_record<HAS_DIV, TRACK>(r.op[k], r.x[k], r.y[k], r.z[k], a[k], b[k], c[k], store, w.vmark, mark);
+          f |= g;
+          nchg += g & 1;
+        }
+      }
     }
     // block-level flags: one atomic per block
     if(__syncthreads_or(f & 2) && tid == 0) atomicOr(&ctl->is_bot, 1);
@@ -186,7 +233,7 @@ __global__ void __launch_bounds__(TPB) k_pir_fixpoint(TableDev t, int2* store, c
         if(i < len) {
           const int r = qcur[i];
           const int op = t.op[r], xi = t.x[r], yi = t.y[r], zi = t.z[r];
-          int2 a = ld_itv(store + xi), b = ld_itv(store + yi), c = ld_itv(store + zi);
+          const int2 a = store[xi], b = store[yi], c = store[zi];
           Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
           if(r1.is_bot() | r2.is_bot() | r3.is_bot()) f |= 2;
           deduce_regs<HAS_DIV>(op, r1, r2, r3);
@@ -250,51 +297,56 @@ __global__ void k_ask_all(TableDev t, const int2* store, unsigned long long* cou
   if((threadIdx.x & 31) == 0 && cnt) atomicAdd(count, (unsigned long long)cnt);
 }
 
-typedef void (*fix_kernel_t)(TableDev, int2*, const int*, FixCtl*, WlState, int, int, unsigned);
+typedef void (*fix_kernel_t)(TableDev, int2*, SegTable, FixCtl*, WlState, int, int, unsigned);
 
-static fix_kernel_t pick_kernel(bool has_div, bool track) {
-  if(has_div) return track ? k_pir_fixpoint<true, true> : k_pir_fixpoint<true, false>;
-  return track ? k_pir_fixpoint<false, true> : k_pir_fixpoint<false, false>;
+// The (records per thread, min blocks per SM) variants that are built; LPC_RPT / LPC_MINB select one for tuning.
+struct Variant { int rpt, minb; fix_kernel_t k[2][2]; };
+#define LPC_VARIANT(R, M) { R, M, { { k_pir_fixpoint<false, false, R, M>, k_pir_fixpoint<false, true, R, M> }, \
+                                    { k_pir_fixpoint<true, false, R, M>, k_pir_fixpoint<true, true, R, M> } } }
+static const Variant kVariants[] = { LPC_VARIANT(4, 2), LPC_VARIANT(4, 3), LPC_VARIANT(2, 3), LPC_VARIANT(2, 4),
+                                     LPC_VARIANT(1, 4) };
+static const int kDefaultVariant = 2;   // RPT 2, 3 blocks / SM: fastest on config 2 (profiles/r01_variants.md)
+
+static const Variant& pick_variant() {
+  static int chosen = -1;
+  if(chosen < 0) {
+    chosen = kDefaultVariant;
+    const char* r = getenv("LPC_RPT");
+    const char* m = getenv("LPC_MINB");
+    if(r && m) {
+      for(size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
+        if(kVariants[i].rpt == atoi(r) && kVariants[i].minb == atoi(m)) chosen = (int)i;
+    }
+  }
+  return kVariants[chosen];
 }
 
-// Relative cost of one record per device opcode (used to balance the contiguous chunks of the dense sweep).
-static const int kOpCost[10] = {4, 10, 4, 4, 24, 24, 24, 24, 4, 4};
-
-// Partition the quads into `grid` contiguous chunks of equal estimated cost.
-static int build_chunks(lpc_table* t, int grid) {
-  if(t->d_chunk && t->grid == grid) return LPC_OK;
+// Opcode segments of the padded table in quads. A table that is not sorted by opcode (more than MAX_SEG runs) is
+// treated as one segment.
+static SegTable build_segments(const lpc_table* t) {
+  SegTable s;
   const long long nq = t->dev.n_pad / 4;
-  std::vector<uint8_t> op(t->dev.n_pad, (uint8_t)D_NOP);
-  for(size_t i = 0; i < t->host.size(); ++i) {
-    int s = t->host[i].op, d;
-    switch(s) {
-      case LPC_ADD: d = D_ADD; break; case LPC_MUL: d = D_MUL; break; case LPC_MIN: d = D_MIN; break;
-      case LPC_MAX: d = D_MAX; break; case LPC_TDIV: d = D_TDIV; break; case LPC_FDIV: d = D_FDIV; break;
-      case LPC_CDIV: d = D_CDIV; break; case LPC_EDIV: d = D_EDIV; break; case LPC_EQ: d = D_EQ; break;
-      default: d = D_LEQ; break;
+  auto dev_op = [&](long long i) -> int {
+    if(i >= (long long)t->host.size()) return D_NOP;
+    switch(t->host[i].op) {
+      case LPC_ADD: return D_ADD; case LPC_MUL: return D_MUL; case LPC_MIN: return D_MIN; case LPC_MAX: return D_MAX;
+      case LPC_TDIV: return D_TDIV; case LPC_FDIV: return D_FDIV; case LPC_CDIV: return D_CDIV;
+      case LPC_EDIV: return D_EDIV; case LPC_EQ: return D_EQ; default: return D_LEQ;
     }
-    op[i] = (uint8_t)d;
+  };
+  s.nseg = 0;
+  s.q[0] = 0;
+  int prev = dev_op(0);
+  for(long long q = 1; q < nq; ++q) {
+    int o = dev_op(q * 4);
+    if(o != prev) {
+      if(s.nseg + 1 >= MAX_SEG) { s.nseg = 0; break; }
+      s.q[++s.nseg] = (int)q;
+      prev = o;
+    }
   }
-  std::vector<long long> pre(nq + 1, 0);
-  for(long long q = 0; q < nq; ++q) {
-    int c = 0;
-    for(int k = 0; k < 4; ++k) { int o = op[q * 4 + k]; c += o < 10 ? kOpCost[o] : 1; }
-    pre[q + 1] = pre[q] + c;
-  }
-  std::vector<int> chunk(grid + 1, 0);
-  const long long total = pre[nq];
-  long long q = 0;
-  for(int b = 1; b < grid; ++b) {
-    long long target = total * b / grid;
-    while(q < nq && pre[q] < target) ++q;
-    chunk[b] = (int)q;
-  }
-  chunk[grid] = (int)nq;
-  if(t->d_chunk) { cudaFree(t->d_chunk); t->d_chunk = nullptr; }
-  LPC_CUDA(cudaMalloc(&t->d_chunk, (grid + 1) * sizeof(int)));
-  LPC_CUDA(cudaMemcpy(t->d_chunk, chunk.data(), (grid + 1) * sizeof(int), cudaMemcpyHostToDevice));
-  t->grid = grid;
-  return LPC_OK;
+  s.q[++s.nseg] = (int)nq;
+  return s;
 }
 
 } // namespace lpc
@@ -336,25 +388,29 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   LPC_REQUIRE(o->mode >= LPC_MODE_AUTO && o->mode <= LPC_MODE_WORKLIST, "bad mode");
   cudaStream_t st = (cudaStream_t)o->stream;
-  const bool track = o->mode != LPC_MODE_SWEEP;
-  fix_kernel_t k = pick_kernel(t->has_div, track);
+  // AUTO currently resolves to dense sweeps unless the caller gives a switch divisor (opts.reserved = d: hand over
+  // to the worklist once a sweep changes <= n/d bounds): measured on config 2 the change-driven iterations do 4x
+  // fewer deductions but are latency-bound (profiles/r01_summary.md), so dense is the faster default for now.
+  const bool track = o->mode == LPC_MODE_WORKLIST || (o->mode == LPC_MODE_AUTO && o->reserved > 0);
+  const Variant& var = pick_variant();
+  fix_kernel_t k = var.k[t->has_div ? 1 : 0][track ? 1 : 0];
   int per_sm = 0;
   LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TPB, 0));
   LPC_REQUIRE(per_sm > 0, "kernel does not fit on an SM");
-  // enough blocks to fill the chip, no more than there are quads to hand out
-  long long nq = t->dev.n_pad / 4;
+  // enough blocks to fill the chip, no more than there are thread-loads of work
+  const long long units = t->dev.n_pad / var.rpt;
   int grid = t->sm_count * per_sm;
-  long long want = std::max<long long>(1, (nq + TPB - 1) / TPB);
-  if(want < grid) grid = (int)std::max<long long>(want, 1);
-  int rc = build_chunks(t, grid);
-  if(rc) return rc;
+  long long want = std::max<long long>(1, (units + TPB - 1) / TPB);
+  if(want < grid) grid = (int)want;
+  SegTable seg = build_segments(t);
   WlState w{};
   unsigned switch_at = 0;
+  LPC_CUDA(cudaEventRecord(s->ev0, st));   // device_ms covers the scratch clears as well as the kernel
   if(track) {
-    rc = get_scratch(s, t, &w);
+    int rc = get_scratch(s, t, &w);
     if(rc) return rc;
     LPC_CUDA(cudaMemsetAsync(w.stamp, 0, std::max<long long>(t->dev.n, 1) * 4, st));
-    LPC_CUDA(cudaMemsetAsync(w.vmark, 0, std::max(1, s->nvars) * 4, st));
+    LPC_CUDA(cudaMemsetAsync(w.vmark, 0, (size_t)std::max(1, s->nvars) * 4, st));
     if(o->mode == LPC_MODE_WORKLIST) switch_at = 0xffffffffu;
     else {
       int div = o->reserved > 0 ? o->reserved : 128;
@@ -362,13 +418,11 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
     }
   }
   LPC_CUDA(cudaMemsetAsync(s->d_ctl, 0, sizeof(FixCtl), st));
-  LPC_CUDA(cudaEventRecord(s->ev0, st));
   TableDev td = t->dev;
   int2* store = s->d;
-  const int* chunk = (const int*)t->d_chunk;
   FixCtl* ctl = s->d_ctl;
   int max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
-  void* args[] = {&td, &store, &chunk, &ctl, &w, &max_sweeps, &stop, &switch_at};
+  void* args[] = {&td, &store, &seg, &ctl, &w, &max_sweeps, &stop, &switch_at};
   LPC_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(grid), dim3(TPB), args, 0, st));
   g_launches++;
   LPC_CUDA(cudaEventRecord(s->ev1, st));

@@ -31,13 +31,15 @@ def W():
 
 
 def modes(L):
-    return [("sweep", L.MODE_SWEEP), ("auto", L.MODE_AUTO), ("worklist", L.MODE_WORKLIST)]
+    """Fixpoint options under test: dense sweeps, dense -> worklist hand-over, worklist after the first sweep."""
+    return [("sweep", dict(mode=L.MODE_SWEEP)), ("auto", dict(mode=L.MODE_AUTO, switch_div=8)),
+            ("worklist", dict(mode=L.MODE_WORKLIST))]
 
 
 def gpu_fixpoint(L, records, store, mode, **kw):
     t = L.Table(records, len(store))
     s = L.Store(values=store)
-    r = L.fixpoint(t, s, mode=mode, **kw)
+    r = L.fixpoint(t, s, **mode, **kw)
     return s.read(), r, t, s
 
 
@@ -63,7 +65,7 @@ def test_golden_vectors_through_the_facade(L, O, pir_kats):
             pir.tell(domains=[(v, lb, ub) for v, (lb, ub) in enumerate(k["store"])])
             pir.tell(records=k["records"])
             assert pir.num_deductions() == len(k["records"])
-            r = pir.fixpoint(mode=mode)
+            r = pir.fixpoint(**mode)
             if k["bot"]:
                 assert r.is_bot and r.has_changed and pir.is_bot(), (k["name"], name)
                 continue
@@ -124,10 +126,10 @@ def test_config2_full_size(L, O, W):
     t = L.Table(net.records, net.nvars)
     for name, mode in modes(L):
         s = L.Store(values=net.store)
-        r = L.fixpoint(t, s, mode=mode)
+        r = L.fixpoint(t, s, **mode)
         assert not r.is_bot
         assert np.array_equal(s.read(), want), name
-        r2 = L.fixpoint(t, s, mode=mode)
+        r2 = L.fixpoint(t, s, **mode)
         assert not r2.has_changed and r2.sweeps == 1 and np.array_equal(s.read(), want), name
 
 
@@ -170,16 +172,16 @@ def test_random_networks_all_ops(L, O):
 def test_edge_cases(L, O):
     # empty table: zero sweeps, nothing changes
     store = np.array([[0, 5], [1, 2]], dtype=np.int32)
-    got, r, t, s = gpu_fixpoint(L, np.zeros((0, 4), dtype=np.int32), store, L.MODE_AUTO)
+    got, r, t, s = gpu_fixpoint(L, np.zeros((0, 4), dtype=np.int32), store, dict(mode=L.MODE_AUTO))
     assert np.array_equal(got, store) and r.sweeps == 0 and not r.has_changed and not r.is_bot
     # a store that is empty before the first sweep is bot with zero sweeps (bound_consistency_test.hpp:22-25)
     store = np.array([[1, 0], [0, 5], [0, 5], [0, 0]], dtype=np.int32)
-    got, r, t, s = gpu_fixpoint(L, np.array([[ADD, 1, 2, 3]], dtype=np.int32), store, L.MODE_SWEEP)
+    got, r, t, s = gpu_fixpoint(L, np.array([[ADD, 1, 2, 3]], dtype=np.int32), store, dict(mode=L.MODE_SWEEP))
     assert r.is_bot and r.sweeps == 0 and not r.has_changed
     # max_sweeps bounds the iteration
     recs = np.array([[ADD, 3, 0, 1], [ADD, 4, 3, 2]], dtype=np.int32)
     store = np.array([[3, 10], [3, 10], [3, 10], [-2**31, 2**31 - 1], [-2**31, 9]], dtype=np.int32)
-    got, r, t, s = gpu_fixpoint(L, recs, store, L.MODE_SWEEP, max_sweeps=1)
+    got, r, t, s = gpu_fixpoint(L, recs, store, dict(mode=L.MODE_SWEEP), max_sweeps=1)
     assert r.sweeps == 1
     # error behaviour: out-of-range variable, unsupported op, store smaller than the table
     with pytest.raises(L.LpcError):
@@ -306,6 +308,6 @@ def test_exhaustive_triples_as_one_network(L, O, name):
     t = L.Table(recs, 3 * n)
     for mname, mode in modes(L):
         s = L.Store(values=store)
-        r = L.fixpoint(t, s, mode=mode)
+        r = L.fixpoint(t, s, **mode)
         assert not r.is_bot, (name, mname)
         assert np.array_equal(s.read(), want), (name, mname)
