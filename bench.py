@@ -211,10 +211,11 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
     import lala_pc_b200 as L
     steps = args.steps if steps is None else steps
     warmup = args.warmup if warmup is None else warmup
+    from lala_pc_b200 import sharding
     net, table, root, dec, obj = build_c4()
-    nbits = 16 + max(0, (world - 1).bit_length())
+    nbits = sharding.decision_bits(world)
     dec = dec[:nbits]
-    first_id = rank * n_stores if first_id is None else first_id
+    first_id = sharding.shard_first_id(rank, n_stores) if first_id is None else first_id
     batch = L.Batch(table, n_stores)
 
     class _Red:   # the 4 x int64 reduction record of the library, viewed as a torch tensor (no copy)
@@ -239,9 +240,7 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
             if i >= warmup:
                 ev[i - warmup][0].record()
             batch.fixpoint_async(objective_var=obj)
-            if dist is not None:
-                dist.all_reduce(red[:3], op=dist.ReduceOp.SUM)
-                dist.all_reduce(red[3:], op=dist.ReduceOp.MIN)
+            sharding.allreduce_record(red, dist)
             if i >= warmup:
                 ev[i - warmup][1].record()
             res = batch.collect()
@@ -290,8 +289,7 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
             t0 = time.perf_counter()
             r = batch.fixpoint_host(pinned.data_ptr(), objective_var=obj)
             if dist is not None:
-                dist.all_reduce(red[:3], op=dist.ReduceOp.SUM)
-                dist.all_reduce(red[3:], op=dist.ReduceOp.MIN)
+                sharding.allreduce_record(red, dist)
                 torch.cuda.synchronize()
             t1 = time.perf_counter()
             if i >= 1:
@@ -347,7 +345,8 @@ def reference_arm(args, rank, world):
     else:
         net = W.config4_base()
         root, st = O.pir_fixpoint(net.store, net.records)
-        nbits = 16 + max(0, (world - 1).bit_length())
+        from lala_pc_b200 import sharding
+        nbits = sharding.decision_bits(world)
         dec, obj = W.eps_decisions(net.records, root, n=24)
         sample = 4096
         secs, ded = [], []

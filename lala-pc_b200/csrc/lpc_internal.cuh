@@ -71,10 +71,14 @@ struct lpc_table {
   void* d_inc_off = nullptr; void* d_inc_idx = nullptr;
   bool has_div = false;
   long long op_count[10] = {0};
-  // cost-balanced contiguous chunks of quads (4 records) for the dense sweep, one per resident block
-  int grid = 0, block = 0;
-  void* d_chunk = nullptr;          // int[grid + 1]
+  // launch plan of the dense sweep, computed once on first use (opcode segments in quads, blocks per SM)
+  bool plan_ready = false;
+  int seg_n = 0;
+  int seg_q[17] = {0};
+  int blocks_per_sm[2] = {0, 0};    // [track]
+  void* d_chunk = nullptr;          // unused (kept for ABI stability of the handle)
   int sm_count = 0;
+  size_t smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin
   lpc_store* host_store = nullptr;  // device staging store of lpc_fixpoint_host
 };
 

@@ -268,6 +268,10 @@ struct lpc_batch {
   cudaStream_t last_stream = nullptr;
   bool pending = false;
   int sbytes = 0;
+  bool plan_ready = false, table_smem = false;
+  size_t smem = 0;
+  int threads = 0, grid = 0;
+  lpc::BatchCtl* h_init = nullptr;   // pinned initial control block
 };
 
 typedef void (*batch_kernel_t)(TableDev, int2*, int, int, uint8_t*, int*, int*, BatchCtl*, int, int, int);
@@ -303,6 +307,7 @@ int lpc_batch_create(const lpc_table* t, int32_t n_stores, lpc_batch** out) {
   LPC_CUDA(cudaMemset(b->d_flags, 0, std::max(n_stores, 16)));
   LPC_CUDA(cudaHostAlloc((void**)&b->h_ctl, sizeof(BatchCtl), cudaHostAllocDefault));
   memset(b->h_ctl, 0, sizeof(BatchCtl));
+  LPC_CUDA(cudaHostAlloc((void**)&b->h_init, sizeof(BatchCtl), cudaHostAllocDefault));
   LPC_CUDA(cudaEventCreate(&b->ev0));
   LPC_CUDA(cudaEventCreate(&b->ev1));
   *out = b;
@@ -313,6 +318,7 @@ int lpc_batch_destroy(lpc_batch* b) {
   if(!b) return LPC_OK;
   cudaFree(b->d); cudaFree(b->d_flags); cudaFree(b->d_sweeps); cudaFree(b->d_obj); cudaFree(b->d_ctl);
   if(b->h_ctl) cudaFreeHost(b->h_ctl);
+  if(b->h_init) cudaFreeHost(b->h_init);
   if(b->ev0) cudaEventDestroy(b->ev0);
   if(b->ev1) cudaEventDestroy(b->ev1);
   delete b;
@@ -364,38 +370,43 @@ int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t o
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   const lpc_table* t = b->table;
   cudaStream_t st = (cudaStream_t)o->stream;
-  cudaDeviceProp prop;
-  int dev = 0;
-  LPC_CUDA(cudaGetDevice(&dev));
-  LPC_CUDA(cudaGetDeviceProperties(&prop, dev));
-  const size_t max_smem = prop.sharedMemPerBlockOptin;
-  const size_t ring = 64 + 2 * (size_t)b->sbytes;
-  const size_t tbl = (size_t)t->dev.n_pad * 13;
-  if(ring > max_smem) {
-    set_error("lpc_batch_fixpoint: a store of %d variables does not fit the shared-memory ring (%zu > %zu B); use lpc_fixpoint per store", b->nvars, ring, max_smem);
-    return LPC_ERR_UNSUPPORTED;
+  // launch plan: computed once per batch handle (device attribute / occupancy queries are slow driver calls)
+  if(!b->plan_ready) {
+    int dev = 0, sms = 0, optin = 0;
+    LPC_CUDA(cudaGetDevice(&dev));
+    LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    LPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t max_smem = (size_t)optin;
+    const size_t ring = 64 + 2 * (size_t)b->sbytes;
+    const size_t tbl = (size_t)t->dev.n_pad * 13;
+    if(ring > max_smem) {
+      set_error("lpc_batch_fixpoint: a store of %d variables does not fit the shared-memory ring (%zu > %zu B); use lpc_fixpoint per store", b->nvars, ring, max_smem);
+      return LPC_ERR_UNSUPPORTED;
+    }
+    // bulk copies need every sub-array 16-B aligned and sized: n_pad is a multiple of 16 (lpc_table_create)
+    b->table_smem = ring + tbl <= max_smem;
+    b->smem = b->table_smem ? ring + tbl : ring;
+    batch_kernel_t kk = pick_batch_kernel(t->has_div, b->table_smem);
+    LPC_CUDA(cudaFuncSetAttribute((const void*)kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    b->threads = (int)std::min<long long>(1024, std::max<long long>(32, (t->dev.n_pad + 31) / 32 * 32));
+    int per_sm = 0;
+    LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kk, b->threads, b->smem));
+    if(per_sm < 1 && b->threads > 256) {
+      b->threads = 256;
+      LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kk, b->threads, b->smem));
+    }
+    LPC_REQUIRE(per_sm > 0, "batch kernel does not fit on an SM");
+    b->grid = std::max(1, std::min(b->n_stores, sms * per_sm));
+    b->plan_ready = true;
   }
-  // bulk copies need every sub-array 16-B aligned and sized: n_pad is a multiple of 16 (lpc_table_create)
-  const bool table_smem = ring + tbl <= max_smem;
-  const size_t smem = table_smem ? ring + tbl : ring;
-  batch_kernel_t k = pick_batch_kernel(t->has_div, table_smem);
-  LPC_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int threads = (int)std::min<long long>(1024, std::max<long long>(32, (t->dev.n_pad + 31) / 32 * 32));
-  int per_sm = 0;
-  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
-  if(per_sm < 1 && threads > 256) {
-    threads = 256;
-    LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
-  }
-  LPC_REQUIRE(per_sm > 0, "batch kernel does not fit on an SM");
-  int grid = std::max(1, std::min(b->n_stores, prop.multiProcessorCount * per_sm));
-  LPC_CUDA(cudaMemsetAsync(b->d_ctl, 0, sizeof(BatchCtl), st));
-  BatchCtl init;
-  memset(&init, 0, sizeof(init));
-  init.red[3] = LPC_INF;
-  init.next_store = grid;
-  LPC_CUDA(cudaMemcpyAsync(b->d_ctl, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  batch_kernel_t k = pick_batch_kernel(t->has_div, b->table_smem);
+  const int grid = b->grid, threads = b->threads;
+  const size_t smem = b->smem;
+  memset(b->h_init, 0, sizeof(BatchCtl));
+  b->h_init->red[3] = LPC_INF;
+  b->h_init->next_store = grid;
   LPC_CUDA(cudaEventRecord(b->ev0, st));
+  LPC_CUDA(cudaMemcpyAsync(b->d_ctl, b->h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
   if(b->n_stores > 0) {
     k<<<grid, threads, smem, st>>>(t->dev, b->d, b->n_stores, b->sbytes, b->d_flags, b->d_sweeps, b->d_obj, b->d_ctl,
                                   objective_var, o->max_sweeps, o->stop_on_bot);

@@ -394,15 +394,25 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
   const bool track = o->mode == LPC_MODE_WORKLIST || (o->mode == LPC_MODE_AUTO && o->reserved > 0);
   const Variant& var = pick_variant();
   fix_kernel_t k = var.k[t->has_div ? 1 : 0][track ? 1 : 0];
-  int per_sm = 0;
-  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TPB, 0));
+  // launch plan: computed once per table (the segment scan is O(n) on the host, the occupancy query is a driver call)
+  if(!t->plan_ready) {
+    SegTable sg = build_segments(t);
+    t->seg_n = sg.nseg;
+    for(int i = 0; i <= sg.nseg; ++i) t->seg_q[i] = sg.q[i];
+    for(int tr = 0; tr < 2; ++tr)
+      LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[tr], var.k[t->has_div ? 1 : 0][tr], TPB, 0));
+    t->plan_ready = true;
+  }
+  const int per_sm = t->blocks_per_sm[track ? 1 : 0];
   LPC_REQUIRE(per_sm > 0, "kernel does not fit on an SM");
   // enough blocks to fill the chip, no more than there are thread-loads of work
   const long long units = t->dev.n_pad / var.rpt;
   int grid = t->sm_count * per_sm;
   long long want = std::max<long long>(1, (units + TPB - 1) / TPB);
   if(want < grid) grid = (int)want;
-  SegTable seg = build_segments(t);
+  SegTable seg;
+  seg.nseg = t->seg_n;
+  for(int i = 0; i <= seg.nseg; ++i) seg.q[i] = t->seg_q[i];
   WlState w{};
   unsigned switch_at = 0;
   LPC_CUDA(cudaEventRecord(s->ev0, st));   // device_ms covers the scratch clears as well as the kernel
