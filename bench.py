@@ -379,6 +379,10 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink config 2 (development only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # exactly ONE line on stdout: keep a private handle to it and point fd 1 at stderr, so that anything a C library
+    # prints (e.g. NCCL's version banner) cannot end up in front of the JSON line
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -389,7 +393,8 @@ def main():
     if args.impl == "reference":
         line = reference_arm(args, rank, world)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            real_stdout.write(json.dumps(line) + "\n")
+            real_stdout.flush()
         return 0
 
     import torch
@@ -425,7 +430,8 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     return 0
 
 

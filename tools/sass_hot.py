@@ -4,7 +4,13 @@ from collections import defaultdict
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]
 ia, isrc, isamp, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-ins = [(i, r[isrc].strip(), int(r[isamp] or 0), int(r[iex] or 0)) for i, r in enumerate(rows[2:]) if len(r) > iex]
+ins = []
+for i, r in enumerate(rows[2:]):
+    if len(r) <= iex:
+        if ins: break          # next kernel's header: keep the first captured launch only
+        continue
+    if not (r[isamp] or '0').isdigit(): break
+    ins.append((i, r[isrc].strip(), int(r[isamp] or 0), int(r[iex] or 0)))
 tot_s = sum(x[2] for x in ins); tot_e = sum(x[3] for x in ins)
 byop_e, byop_s = defaultdict(int), defaultdict(int)
 for i, s, sm, ex in ins:
