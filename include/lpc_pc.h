@@ -1,0 +1,72 @@
+/* lpc_pc.h — C-ABI for the PC (propagator completion) hot path: n-ary terms and formulas over the interval store.
+ *
+ * The reference keeps each PC propagator as a heap-allocated variant tree (pc::Formula / pc::Term,
+ * include/lala/formula.hpp, include/lala/terms.hpp) and walks it in PC::deduce(int) (include/lala/pc.hpp:671-680).
+ * Here the in-scope shapes are flattened into one 16-byte header + a run of {coef, var} terms, so that a sweep is a
+ * streaming read instead of a pointer chase. Each flat kind names the reference tree it stands for; the result of
+ * `deduce` on it is bit-identical to walking that tree (tests/test_gpu_pc.py against oracle/pc_oracle.cpp).
+ *
+ * Same conventions as lpc.h (status codes, stores as {lb,ub} int32 pairs, one in-flight call per handle).
+ */
+#ifndef LPC_PC_H
+#define LPC_PC_H
+
+#include "lpc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum lpc_pc_kind {
+  /* Inequality(Nary<Add>(t_1..t_n), Constant rhs), t_i = Variable (coef 1) or Binary<Mul>(Constant coef, Variable):
+   * sum_i coef_i * x_i <= rhs          formula.hpp:796-805, terms.hpp:465-499, 231-262 */
+  LPC_PC_LIN_LE = 1,
+  /* Biconditional(VariableLiteral(bvar), <the LIN_LE above>):  bvar <=> (sum <= rhs)      formula.hpp:421-427 */
+  LPC_PC_REIF_LIN_LE = 2,
+  /* Equality(Variable x, Variable y): terms = {x, y}                                       formula.hpp:672-681 */
+  LPC_PC_EQ = 3,
+  /* Equality<neg>(Variable x, Variable y) (2 terms) or (Variable x, Constant rhs) (1 term) formula.hpp:636-670 */
+  LPC_PC_NEQ = 4,
+  /* right-nested Disjunction of VariableLiterals l_1 \/ (l_2 \/ (... \/ l_n)); term coef +1 = x, -1 = not x
+   * (bool_clause, pc.hpp:542-544)                                                          formula.hpp:346-350 */
+  LPC_PC_CLAUSE = 5,
+  /* Equality(Unary<Abs>(Variable x), Variable y): terms = {x, y}                           terms.hpp:104-119 */
+  LPC_PC_ABS_EQ = 6
+};
+
+typedef struct lpc_pc_prop {
+  int32_t kind;        /* lpc_pc_kind */
+  int32_t first_term;  /* index of the first term in the term array */
+  int32_t n_terms;
+  int32_t rhs;         /* constant right-hand side (LIN_LE, REIF_LIN_LE, NEQ with a constant) */
+  int32_t bvar;        /* reification variable (REIF_LIN_LE), else -1 */
+} lpc_pc_prop;
+
+typedef struct lpc_pc_term {
+  int32_t coef;        /* coefficient (LIN kinds, non-zero) or literal sign (+1 / -1, CLAUSE); 1 otherwise */
+  int32_t var;
+} lpc_pc_term;
+
+typedef struct lpc_pc_table lpc_pc_table;
+
+/* PC::deduce(const tell_type&) (pc.hpp:625-645): upload the flattened propagators, in the caller's order. */
+int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_term* terms, int64_t n_terms,
+                        int32_t nvars, lpc_pc_table** out);
+int lpc_pc_table_destroy(lpc_pc_table* t);
+/* PC::num_deductions (pc.hpp:665-667) */
+int64_t lpc_pc_table_size(const lpc_pc_table* t);
+int64_t lpc_pc_table_terms(const lpc_pc_table* t);
+
+/* GaussSeidelIteration::fixpoint(n, PC::deduce(i)) (tests/pc_test.cpp:91-94) as one persistent kernel. */
+int lpc_pc_fixpoint(const lpc_pc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r);
+/* Same with HOST buffers. */
+int lpc_pc_fixpoint_host(const lpc_pc_table* t, int32_t* lbub, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r);
+/* PC::deduce(int i) (pc.hpp:671-680), one launch. */
+int lpc_pc_deduce_one(const lpc_pc_table* t, lpc_store* s, int64_t i, int* changed);
+/* PC::ask(int i) over all i (pc.hpp:661-663; the loop of is_extractable, pc.hpp:726-738); bits may be NULL. */
+int lpc_pc_ask_all(const lpc_pc_table* t, const lpc_store* s, int64_t* n_entailed, uint8_t* bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPC_PC_H */

@@ -109,6 +109,15 @@ SIGNATURES = {
                                                ctypes.POINTER(BatchResult)]),
     "lpc_batch_flags": (ctypes.c_int, [_vp, _pu8]),
     "lpc_batch_reduction_device_ptr": (_vp, [_vp]),
+    # include/lpc_pc.h
+    "lpc_pc_table_create": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _pvp]),
+    "lpc_pc_table_destroy": (ctypes.c_int, [_vp]),
+    "lpc_pc_table_size": (_i64, [_vp]),
+    "lpc_pc_table_terms": (_i64, [_vp]),
+    "lpc_pc_fixpoint": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
+    "lpc_pc_fixpoint_host": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
+    "lpc_pc_deduce_one": (ctypes.c_int, [_vp, _vp, _i64, _pint]),
+    "lpc_pc_ask_all": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_int64), _pu8]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(_L, _name)
@@ -258,6 +267,57 @@ def fixpoint_host(table, values, **kw):
     ptr = values if isinstance(values, int) else values.ctypes.data
     _check(_L.lpc_fixpoint_host(table._h, ptr, ctypes.byref(o), ctypes.byref(r)))
     return r
+
+
+PC_LIN_LE, PC_REIF_LIN_LE, PC_EQ, PC_NEQ, PC_CLAUSE, PC_ABS_EQ = 1, 2, 3, 4, 5, 6
+
+
+class PcTable:
+    """Flattened PC propagators (include/lpc_pc.h): props [n,5] int32 {kind, first_term, n_terms, rhs, bvar},
+    terms [m,2] int32 {coef, var}."""
+
+    def __init__(self, props, terms, nvars):
+        p = np.ascontiguousarray(props, dtype=np.int32).reshape(-1, 5)
+        t = np.ascontiguousarray(terms, dtype=np.int32).reshape(-1, 2)
+        self._h = ctypes.c_void_p()
+        self.nvars = nvars
+        _check(_L.lpc_pc_table_create(p.ctypes.data, p.shape[0], t.ctypes.data, t.shape[0], nvars, ctypes.byref(self._h)))
+
+    def __len__(self):
+        return int(_L.lpc_pc_table_size(self._h))
+
+    def num_terms(self):
+        return int(_L.lpc_pc_table_terms(self._h))
+
+    def fixpoint(self, store, **kw):
+        o, r = _opts(**kw), FixpointResult()
+        _check(_L.lpc_pc_fixpoint(self._h, store._h, ctypes.byref(o), ctypes.byref(r)))
+        return r
+
+    def fixpoint_host(self, values, **kw):
+        o, r = _opts(**kw), FixpointResult()
+        ptr = values if isinstance(values, int) else values.ctypes.data
+        _check(_L.lpc_pc_fixpoint_host(self._h, ptr, ctypes.byref(o), ctypes.byref(r)))
+        return r
+
+    def deduce(self, store, i):
+        c = ctypes.c_int(0)
+        _check(_L.lpc_pc_deduce_one(self._h, store._h, i, ctypes.byref(c)))
+        return bool(c.value)
+
+    def ask_all(self, store, want_bits=False):
+        n = ctypes.c_int64(0)
+        bits = np.zeros(max(1, len(self)), dtype=np.uint8) if want_bits else None
+        _check(_L.lpc_pc_ask_all(self._h, store._h, ctypes.byref(n), bits.ctypes.data_as(_pu8) if want_bits else None))
+        return (int(n.value), bits[:len(self)]) if want_bits else int(n.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _L.lpc_pc_table_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 class Batch:

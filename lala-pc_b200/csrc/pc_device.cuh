@@ -1,0 +1,221 @@
+// pc_device.cuh — the flat PC propagators (include/lpc_pc.h) on registers, for sm_100a.
+//
+// Device counterpart of PC::deduce(int) -> pc::Formula::deduce -> pc::Term::{project, embed}
+// (lala-pc include/lala/pc.hpp:671-680, formula.hpp, terms.hpp) for the tree shapes named in lpc_pc.h. Every routine
+// cites the tree walk it replaces. Bound arithmetic follows lala-core's Interval::project as restated by the oracle
+// (oracle/pc_oracle.cpp): ADD / SUB componentwise on the bounds, an infinite operand bound gives an infinite result
+// bound, MUL / EDIV by a constant as the hull of the corner results. `Acc` abstracts the store: `load(v)` returns the
+// current domain, `embed(v, itv)` joins (VStore::embed) and returns bit0 = changed, bit1 = became empty.
+#pragma once
+#include "pir_device.cuh"
+
+namespace lpc {
+
+enum PcKind : int { PC_LIN_LE = 1, PC_REIF_LIN_LE = 2, PC_EQ = 3, PC_NEQ = 4, PC_CLAUSE = 5, PC_ABS_EQ = 6 };
+
+struct PcTableDev {
+  const int4* hdr;     // {kind | n_terms << 8, first_term, rhs, bvar}
+  const int2* terms;   // {coef, var}
+  long long n;
+  long long n_terms;
+  int nvars;
+};
+
+LPC_HD bool b_inf(int x) { return x == LPC_INF || x == LPC_MINF; }
+LPC_HD int b_clamp(long long x) { return x >= LPC_INF ? LPC_INF : (x <= LPC_MINF ? LPC_MINF : (int)x); }
+LPC_HD int b_add(int a, int b) { if(b_inf(a)) return a; if(b_inf(b)) return b; return b_clamp((long long)a + b); }
+LPC_HD int b_neg(int a) { return a == LPC_INF ? LPC_MINF : (a == LPC_MINF ? LPC_INF : -a); }
+LPC_HD int b_sub(int a, int b) { return b_add(a, b_neg(b)); }
+LPC_HD int b_mul(int a, int b) {
+  if(a == 0 || b == 0) return 0;
+  if(b_inf(a) || b_inf(b)) return ((a < 0) != (b < 0)) ? LPC_MINF : LPC_INF;
+  return b_clamp((long long)a * b);
+}
+LPC_HD int b_ediv(int a, int b) {   // Euclidean, b != 0 and finite
+  if(b_inf(a)) return (b > 0) ? a : b_neg(a);
+  long long q = (long long)a / b, r = (long long)a % b;
+  if(r < 0) q += (b > 0) ? -1 : 1;
+  return b_clamp(q);
+}
+LPC_HD bool contains0(const Itv& a) { return a.lb <= 0 && 0 <= a.ub; }            // a >= eq_zero
+LPC_HD bool sub_of_zero(const Itv& a) { return a.is_bot() || (a.lb >= 0 && a.ub <= 0); }   // a <= eq_zero
+
+// Binary<GroupMul>(Constant c, Variable x)::project / Variable::project (terms.hpp:399-405, 69-71)
+LPC_HD Itv term_project(int c, const Itv& x) {
+  if(c == 1) return x;
+  if(x.is_bot()) return itv_bot();
+  const int p = b_mul(c, x.lb), q = b_mul(c, x.ub);
+  return Itv(min(p, q), max(p, q));
+}
+// ...::embed: the variable's residual for `c * x <= u` in the lattice sense (terms.hpp:384-396, 249-253)
+LPC_HD Itv term_residual(int c, const Itv& u) {
+  if(c == 1) return u;
+  if(u.is_bot()) return itv_bot();
+  const int p = b_ediv(u.lb, c), q = b_ediv(u.ub, c);
+  return Itv(min(p, q), max(p, q));
+}
+
+// Nary<Add>::project (terms.hpp:465-478)
+template <class Acc>
+LPC_HD Itv lin_project(const Acc& a, const int2* terms, int n) {
+  int2 t0 = terms[0];
+  Itv accu = term_project(t0.x, a.load(t0.y));
+  for(int i = 1; i < n; ++i) {
+    const int2 t = terms[i];
+    const Itv ti = term_project(t.x, a.load(t.y));
+    accu = Itv(b_add(accu.lb, ti.lb), b_add(accu.ub, ti.ub));
+  }
+  return accu;
+}
+
+// Nary<Add>::embed(u) (terms.hpp:480-499): all = sum once; per term the others' sum through additive_inverse
+// (GroupAdd::rev_op, :190-194), residual = u - others (left_residual, :196-198), then the term's own embed.
+// The interpreter builds a lone term as itself, two terms as Binary<GroupAdd> and three or more as Nary<Add>
+// (pc.hpp:277-296), and the three differ once infinite bounds are involved, so each arity keeps its own walk.
+template <class Acc>
+LPC_HD int lin_embed(Acc& a, const int2* terms, int n, const Itv& u, const Itv& all) {
+  int f = 0;
+  if(n == 1) return a.embed(terms[0].y, term_residual(terms[0].x, u));   // Variable / Binary<Mul>::embed
+  if(n == 2) {   // Binary<GroupAdd>::embed (terms.hpp:376-397): x <- u - y, then y <- u - x with x re-read
+    const int2 t0 = terms[0], t1 = terms[1];
+    const Itv yt = term_project(t1.x, a.load(t1.y));
+    f |= a.embed(t0.y, term_residual(t0.x, Itv(b_sub(u.lb, yt.ub), b_sub(u.ub, yt.lb))));
+    const Itv xt = term_project(t0.x, a.load(t0.y));
+    f |= a.embed(t1.y, term_residual(t1.x, Itv(b_sub(u.lb, xt.ub), b_sub(u.ub, xt.lb))));
+    return f;
+  }
+  for(int i = 0; i < n; ++i) {
+    const int2 t = terms[i];
+    const Itv ti = term_project(t.x, a.load(t.y));
+    const Itv others(b_add(all.lb, b_neg(ti.lb)), b_add(all.ub, b_neg(ti.ub)));
+    const Itv res(b_sub(u.lb, others.ub), b_sub(u.ub, others.lb));
+    f |= a.embed(t.y, term_residual(t.x, res));
+  }
+  return f;
+}
+
+// VariableLiteral (formula.hpp:97-120): ask / nask / deduce / contradeduce with `neg` folded in.
+LPC_HD bool lit_ask(bool neg, const Itv& b) { return neg ? sub_of_zero(b) : !contains0(b); }
+template <class Acc> LPC_HD int lit_deduce(Acc& a, bool neg, int v) { return a.embed(v, neg ? Itv(0, 0) : Itv(1, 1)); }
+
+// PC::deduce(i) for one flat propagator. Returns bit0 = changed, bit1 = some variable became empty.
+template <class Acc>
+LPC_HD int pc_deduce(Acc& a, const int4 h, const int2* terms) {
+  const int kind = h.x & 0xff, n = h.x >> 8, rhs = h.z, bvar = h.w;
+  switch(kind) {
+    case PC_LIN_LE: {   // Inequality<false>::deduce, right side constant (formula.hpp:796-800)
+      const Itv all = lin_project(a, terms, n);
+      return lin_embed(a, terms, n, Itv(LPC_MINF, rhs), all);
+    }
+    case PC_REIF_LIN_LE: {   // Biconditional::deduce (formula.hpp:421-427)
+      const Itv b = a.load(bvar);
+      const Itv all = lin_project(a, terms, n);
+      if(lit_ask(false, b)) return lin_embed(a, terms, n, Itv(LPC_MINF, rhs), all);                 // g.deduce
+      else if(lit_ask(true, b)) return lin_embed(a, terms, n, Itv(b_add(rhs, 1), LPC_INF), all);    // g.contradeduce: l > r (:779-785)
+      else if(all.ub <= rhs) return lit_deduce(a, false, bvar);                                      // g.ask (:769)
+      else if(all.lb > rhs) return lit_deduce(a, true, bvar);                                        // g.nask (:766)
+      return 0;
+    }
+    case PC_EQ: {   // Equality<false>::deduce (formula.hpp:672-681)
+      const int x = terms[0].y, y = terms[1].y;
+      int f = a.embed(y, a.load(x));
+      f |= a.embed(x, a.load(y));
+      return f;
+    }
+    case PC_NEQ: {   // Equality<true>::deduce (formula.hpp:636-670)
+      const int x = terms[0].y;
+      if(n == 2) {
+        const int y = terms[1].y;
+        const Itv l = a.load(x);
+        if(l.lb == l.ub) {
+          Itv r = a.load(y), lo = r, hi = r;
+          lo.meet(Itv(b_add(l.lb, 1), LPC_INF));
+          hi.meet(Itv(LPC_MINF, b_sub(l.ub, 1)));
+          return a.embed(y, fjoin(lo, hi));
+        }
+        const Itv r = a.load(y);
+        if(r.lb == r.ub) {
+          Itv l2 = a.load(x), lo = l2, hi = l2;
+          lo.meet(Itv(b_add(r.lb, 1), LPC_INF));
+          hi.meet(Itv(LPC_MINF, b_sub(r.ub, 1)));
+          return a.embed(x, fjoin(lo, hi));
+        }
+        return 0;
+      }
+      // x != constant: only the left side can move
+      Itv l2 = a.load(x), lo = l2, hi = l2;
+      lo.meet(Itv(b_add(rhs, 1), LPC_INF));
+      hi.meet(Itv(LPC_MINF, b_sub(rhs, 1)));
+      return a.embed(x, fjoin(lo, hi));
+    }
+    case PC_CLAUSE: {   // nested Disjunction::deduce = unit propagation (formula.hpp:346-350)
+      int first = -1;
+      bool rest_refuted = true;
+      for(int i = 0; i < n; ++i) {
+        const int2 t = terms[i];
+        const bool refuted = lit_ask(t.x > 0, a.load(t.y));   // nask of a literal = ask of its negation
+        if(first < 0) { if(!refuted) first = i; }
+        else rest_refuted &= refuted;
+      }
+      if(first < 0) first = n - 1;   // every literal refuted: the innermost level deduces the last one -> bot
+      else if(!rest_refuted) return 0;
+      return lit_deduce(a, terms[first].x < 0, terms[first].y);
+    }
+    case PC_ABS_EQ: {   // Equality(Abs(x), y): y <- |x| (terms.hpp:107-110), then x <- hull(y, -y) (:112-114)
+      const int x = terms[0].y, y = terms[1].y;
+      const Itv xv = a.load(x);
+      Itv ax = xv;
+      if(!xv.is_bot()) {
+        if(xv.lb >= 0) ax = xv;
+        else if(xv.ub <= 0) ax = Itv(b_neg(xv.ub), b_neg(xv.lb));
+        else ax = Itv(0, max(b_neg(xv.lb), xv.ub));
+      }
+      int f = a.embed(y, ax);
+      const Itv r = a.load(y);
+      f |= a.embed(x, fjoin(r, Itv(b_neg(r.ub), b_neg(r.lb))));
+      return f;
+    }
+    default: return 0;
+  }
+}
+
+// PC::ask(i) (pc.hpp:661-663) for one flat propagator.
+template <class Acc>
+LPC_HD bool pc_ask(const Acc& a, const int4 h, const int2* terms) {
+  const int kind = h.x & 0xff, n = h.x >> 8, rhs = h.z, bvar = h.w;
+  switch(kind) {
+    case PC_LIN_LE: return lin_project(a, terms, n).ub <= rhs;                       // formula.hpp:769
+    case PC_REIF_LIN_LE: {                                                           // formula.hpp:408-412
+      const Itv b = a.load(bvar), all = lin_project(a, terms, n);
+      return (lit_ask(false, b) && all.ub <= rhs) || (lit_ask(true, b) && all.lb > rhs);
+    }
+    case PC_EQ: {                                                                    // formula.hpp:629
+      const Itv l = a.load(terms[0].y), r = a.load(terms[1].y);
+      return ((l.is_bot() && r.is_bot()) || (l.lb == r.lb && l.ub == r.ub)) && l.lb == l.ub;
+    }
+    case PC_NEQ: {                                                                   // formula.hpp:626
+      Itv l = a.load(terms[0].y);
+      const Itv r = n == 2 ? a.load(terms[1].y) : Itv(rhs, rhs);
+      l.meet(r);
+      return l.is_bot();
+    }
+    case PC_CLAUSE: {                                                                // formula.hpp:338-340
+      bool any = false;
+      for(int i = 0; i < n; ++i) any |= lit_ask(terms[i].x < 0, a.load(terms[i].y));
+      return any;
+    }
+    case PC_ABS_EQ: {
+      const Itv xv = a.load(terms[0].y), r = a.load(terms[1].y);
+      Itv ax = xv;
+      if(!xv.is_bot()) {
+        if(xv.lb >= 0) ax = xv;
+        else if(xv.ub <= 0) ax = Itv(b_neg(xv.ub), b_neg(xv.lb));
+        else ax = Itv(0, max(b_neg(xv.lb), xv.ub));
+      }
+      return ((ax.is_bot() && r.is_bot()) || (ax.lb == r.lb && ax.ub == r.ub)) && ax.lb == ax.ub;
+    }
+    default: return true;
+  }
+}
+
+} // namespace lpc

@@ -1,0 +1,118 @@
+"""Host-side flattening of PC formulas into the device encoding of include/lpc_pc.h — the counterpart of
+PC::interpret_formula / interpret_term (lala-pc include/lala/pc.hpp:217-604) for the in-scope shapes.
+
+Formulas are nested tuples (a plain Python stand-in for lala-core's TFormula):
+  terms     ('var', v) ('const', k) ('mul', ('const', c), ('var', v)) ('add', t1, t2) ('sum', t1, ..., tn >= 3)
+            ('abs', ('var', v))
+  formulas  ('le', term, ('const', k))  ('equiv', ('lit', b), ('le', term, ('const', k)))
+            ('eq', ('var', x), ('var', y))  ('ne', ('var', x), ('var', y) | ('const', k))
+            ('or', lit, ('or', lit, ...)) with lit = ('lit', v) | ('nlit', v)   ('eq', ('abs', ('var', x)), ('var', y))
+Anything else raises `Unsupported` (the reference's "shape of this formula is not supported" interpretation error);
+such formulas stay on the reference's tree-walking path.
+"""
+import numpy as np
+
+PC_LIN_LE, PC_REIF_LIN_LE, PC_EQ, PC_NEQ, PC_CLAUSE, PC_ABS_EQ = 1, 2, 3, 4, 5, 6
+
+
+class Unsupported(ValueError):
+    pass
+
+
+def _linear_terms(t):
+    """A term that is a variable, coef * variable, or an n-ary sum of those -> [(coef, var)]."""
+    op = t[0]
+    if op == "var":
+        return [(1, int(t[1]))]
+    if op == "mul" and t[1][0] == "const" and t[2][0] == "var" and int(t[1][1]) != 0:
+        return [(int(t[1][1]), int(t[2][1]))]
+    if op == "add":   # Binary<GroupAdd> of two leaf terms
+        a, b = _linear_terms(t[1]), _linear_terms(t[2])
+        if len(a) != 1 or len(b) != 1 or t[1][0] in ("add", "sum") or t[2][0] in ("add", "sum"):
+            raise Unsupported("nested binary sums are not flattened (their residuals differ from a flat sum)")
+        return a + b
+    if op == "sum":
+        if len(t) - 1 < 3:
+            raise Unsupported("an n-ary sum has at least three operands (pc.hpp:277-296)")
+        out = []
+        for s in t[1:]:
+            if s[0] in ("sum", "add"):
+                raise Unsupported("nested n-ary sums are not flattened (their residuals differ from a flat sum)")
+            out += _linear_terms(s)
+        return out
+    raise Unsupported(f"term {op} is not linear")
+
+
+def _lin_le(f):
+    if f[0] == "le" and f[2][0] == "const":
+        return _linear_terms(f[1]), int(f[2][1])
+    raise Unsupported("not a linear inequality with a constant right-hand side")
+
+
+def _clause_literals(f):
+    lits = []
+    while True:
+        if f[0] == "or" and f[1][0] in ("lit", "nlit"):
+            lits.append((1 if f[1][0] == "lit" else -1, int(f[1][1])))
+            f = f[2]
+        elif f[0] in ("lit", "nlit"):
+            lits.append((1 if f[0] == "lit" else -1, int(f[1])))
+            return lits
+        else:
+            raise Unsupported("not a right-nested clause of literals")
+
+
+def flatten_one(f):
+    """-> (kind, [(coef, var)], rhs, bvar)"""
+    op = f[0]
+    if op == "le":
+        terms, k = _lin_le(f)
+        return PC_LIN_LE, terms, k, -1
+    if op == "equiv" and f[1][0] == "lit" and f[2][0] == "le":
+        terms, k = _lin_le(f[2])
+        return PC_REIF_LIN_LE, terms, k, int(f[1][1])
+    if op == "eq" and f[1][0] == "var" and f[2][0] == "var":
+        return PC_EQ, [(1, int(f[1][1])), (1, int(f[2][1]))], 0, -1
+    if op == "eq" and f[1][0] == "abs" and f[1][1][0] == "var" and f[2][0] == "var":
+        return PC_ABS_EQ, [(1, int(f[1][1][1])), (1, int(f[2][1]))], 0, -1
+    if op == "ne" and f[1][0] == "var" and f[2][0] == "var":
+        return PC_NEQ, [(1, int(f[1][1])), (1, int(f[2][1]))], 0, -1
+    if op == "ne" and f[1][0] == "var" and f[2][0] == "const":
+        return PC_NEQ, [(1, int(f[1][1]))], int(f[2][1]), -1
+    if op in ("or", "lit", "nlit"):   # a lone VariableLiteral is a one-literal clause
+        return PC_CLAUSE, _clause_literals(f), 0, -1
+    raise Unsupported(f"formula {op} has no flat kind")
+
+
+def flatten(formulas):
+    """List of formula trees -> (props [n,5] int32, terms [m,2] int32)."""
+    props, terms = [], []
+    for f in formulas:
+        kind, ts, rhs, bvar = flatten_one(f)
+        props.append((kind, len(terms), len(ts), rhs, bvar))
+        terms += ts
+    return (np.asarray(props, dtype=np.int32).reshape(-1, 5), np.asarray(terms, dtype=np.int32).reshape(-1, 2))
+
+
+def to_tree(kind, ts, rhs, bvar):
+    """The formula tree a flat propagator stands for (inverse of flatten_one; used by generators and tests)."""
+    def term(c, v):
+        return ("var", v) if c == 1 else ("mul", ("const", c), ("var", v))
+    if kind in (PC_LIN_LE, PC_REIF_LIN_LE):
+        lhs = (term(*ts[0]) if len(ts) == 1 else ("add", term(*ts[0]), term(*ts[1])) if len(ts) == 2
+               else ("sum",) + tuple(term(c, v) for c, v in ts))
+        le = ("le", lhs, ("const", rhs))
+        return le if kind == PC_LIN_LE else ("equiv", ("lit", bvar), le)
+    if kind == PC_EQ:
+        return ("eq", ("var", ts[0][1]), ("var", ts[1][1]))
+    if kind == PC_ABS_EQ:
+        return ("eq", ("abs", ("var", ts[0][1])), ("var", ts[1][1]))
+    if kind == PC_NEQ:
+        return ("ne", ("var", ts[0][1]), ("var", ts[1][1]) if len(ts) == 2 else ("const", rhs))
+    if kind == PC_CLAUSE:
+        lits = [("lit", v) if c > 0 else ("nlit", v) for c, v in ts]
+        f = lits[-1]
+        for l in reversed(lits[:-1]):
+            f = ("or", l, f)
+        return f
+    raise Unsupported(kind)

@@ -234,6 +234,145 @@ def eps_decisions(records, root_store, n=16, min_degree=8):
     return sorted(int(v) for v in order[:n]), int(order[n])
 
 
+class PcNetwork:
+    """props [n,5] int32 {kind, first_term, n_terms, rhs, bvar}, terms [m,2] int32 {coef, var} (include/lpc_pc.h),
+    store [nvars,2], solution [nvars]."""
+
+    def __init__(self, props, terms, store, solution, meta):
+        self.props, self.terms, self.store, self.solution, self.meta = props, terms, store, solution, meta
+        self.nvars = store.shape[0]
+
+    def formulas(self):
+        """The formula trees the flat propagators stand for (for the tree-walking checker)."""
+        from . import pcflat
+        out = []
+        for kind, first, n, rhs, bvar in self.props.tolist():
+            ts = [tuple(t) for t in self.terms[first:first + n].tolist()]
+            out.append(pcflat.to_tree(kind, ts, rhs, bvar))
+        return out
+
+
+def config3(scale=1.0, seed=SEED_BASE + 3, reified_frac=0.30):
+    """PC with n-ary linear sums and reified sums (BASELINE.json configs[2]): 200k vars, constraints
+    sum c_i x_i <= k and b <=> (sum c_i x_i <= k), arity U{2..8}, c_i in {1,2,3,5}, until 1M terms are emitted."""
+    nvars = int(200_000 * scale)
+    want_terms = int(1_000_000 * scale)
+    rng = _Rng(seed)
+    nbool = max(16, nvars // 20)
+    is_bool = np.zeros(nvars, dtype=bool)
+    is_bool[rng.below(nbool, nvars)] = True
+    ints = np.flatnonzero(~is_bool)
+    bools = np.flatnonzero(is_bool)
+    s = np.where(is_bool, rng.below(nvars, 2), rng.between(nvars, 0, 100))
+    ncons = int(want_terms / 5.0 * 1.05) + 8
+    arity = rng.between(ncons, 2, 8)
+    cum = np.cumsum(arity)
+    ncons = int(np.searchsorted(cum, want_terms)) + 1
+    arity = arity[:ncons]
+    first = np.concatenate([[0], np.cumsum(arity)[:-1]])
+    m = int(arity.sum())
+    # variables of a constraint: a random anchor, then distinct neighbours (anchor + a strictly increasing offset)
+    anchor = np.repeat(rng.below(ncons, len(ints)), arity)
+    pos_in = np.arange(m) - np.repeat(first, arity)
+    step = rng.between(m, 1, 64)
+    csum = np.cumsum(step)
+    off = np.where(pos_in == 0, 0, csum - np.repeat(csum[first], arity))   # strictly increasing inside a constraint
+    var = ints[(anchor + off) % len(ints)]
+    coef = np.array([1, 2, 3, 5], dtype=np.int64)[rng.below(m, 4)]
+    lhs = np.add.reduceat(coef * s[var], first)
+    reified = rng.below(ncons, 1000) < int(reified_frac * 1000)
+    # right-hand sides: non-reified constraints hold with a small slack; reified ones sit around the planted sum
+    slack = rng.between(ncons, 0, 12)
+    rhs = np.where(reified, lhs + rng.between(ncons, -10, 10), lhs + slack)
+    truth = lhs <= rhs
+    bvar = np.full(ncons, -1, dtype=np.int64)
+    # reification variable with the right planted value, near the anchor
+    idx_b = _ValueIndex(bools.astype(np.int64), s, nvars, 0)
+    pick = idx_b.find(truth.astype(np.int64), var[first])
+    bvar = np.where(reified, pick, -1)
+    assert (bvar[reified] >= 0).all()
+    kind = np.where(reified, 2, 1)
+    props = np.stack([kind, first, arity, rhs, bvar], axis=1).astype(np.int32)
+    terms = np.stack([coef, var], axis=1).astype(np.int32)
+    a = rng.between(nvars, 1, 16)
+    b = rng.between(nvars, 1, 16)
+    lb = np.maximum(0, s - a)
+    ub = s + b
+    bfix = rng.below(nvars, 1000) < 300
+    lb = np.where(is_bool, np.where(bfix, s, 0), lb)
+    ub = np.where(is_bool, np.where(bfix, s, 1), ub)
+    store = np.stack([lb, ub], axis=1).astype(np.int32)
+    # sort by (kind, length) like PC::deduce(tell) (pc.hpp:636-643): stable, so equal keys keep emission order
+    order = np.lexsort((props[:, 2], props[:, 0]))
+    props = np.ascontiguousarray(props[order])
+    return PcNetwork(props, terms, store, s.astype(np.int32), dict(nvars=nvars, nprops=len(props), nterms=m, seed=seed))
+
+
+def config5(scale=1.0, seed=SEED_BASE + 5):
+    """Bitset-domain PC shapes (tests/pc_bitset_test.cpp) scaled up (BASELINE.json configs[4]): 100k vars with domains
+    inside [0, 61], 500k propagators: 40 % x != y, 30 % x = y, 25 % 4-literal clauses, 5 % y = |x|."""
+    nvars = int(100_000 * scale)
+    nprops = int(500_000 * scale)
+    rng = _Rng(seed)
+    nbool = max(16, nvars // 10)
+    is_bool = np.zeros(nvars, dtype=bool)
+    is_bool[rng.below(nbool, nvars)] = True
+    ints = np.flatnonzero(~is_bool).astype(np.int64)
+    bools = np.flatnonzero(is_bool).astype(np.int64)
+    s = np.where(is_bool, rng.below(nvars, 2), rng.between(nvars, 0, 61))
+    idx_i = _ValueIndex(ints, s, nvars, 0)
+    n_ne, n_eq, n_cl = int(nprops * 0.40), int(nprops * 0.30), int(nprops * 0.25)
+    n_abs = nprops - n_ne - n_eq - n_cl
+    props, terms = [], []
+
+    def pairs(n, same):
+        out_x, out_y = [], []
+        have = 0
+        while have < n:
+            k = int((n - have) * 1.3) + 64
+            x = ints[rng.below(k, len(ints))]
+            if same:
+                y = idx_i.find(s[x], np.clip(x + rng.between(k, -2048, 2048), 0, nvars - 1))
+                ok = (y >= 0) & (y != x)
+            else:
+                y = ints[np.clip(np.searchsorted(ints, np.clip(x + rng.between(k, -2048, 2048), 0, nvars - 1)), 0, len(ints) - 1)]
+                ok = s[x] != s[y]
+            out_x.append(x[ok][: n - have]); out_y.append(y[ok][: n - have])
+            have += len(out_x[-1])
+        return np.concatenate(out_x), np.concatenate(out_y)
+
+    t0 = 0
+    for kind, n, same in ((4, n_ne, False), (3, n_eq, True), (6, n_abs, True)):
+        x, y = pairs(n, same)
+        first = t0 + 2 * np.arange(n)
+        props.append(np.stack([np.full(n, kind), first, np.full(n, 2), np.zeros(n, dtype=np.int64), np.full(n, -1)], axis=1))
+        terms.append(np.stack([np.ones(2 * n, dtype=np.int64), np.stack([x, y], axis=1).ravel()], axis=1))
+        t0 += 2 * n
+    # clauses: 4 literals over 0/1 variables, at least one true under the planted assignment
+    v = bools[rng.below(4 * n_cl, len(bools))].reshape(n_cl, 4)
+    sign = np.where(rng.below(4 * n_cl, 2).reshape(n_cl, 4) == 1, 1, -1)
+    true_lit = (sign > 0) == (s[v] == 1)
+    none = ~true_lit.any(axis=1)
+    sign[none, 0] = np.where(s[v[none, 0]] == 1, 1, -1)     # make the first literal true
+    first = t0 + 4 * np.arange(n_cl)
+    props.append(np.stack([np.full(n_cl, 5), first, np.full(n_cl, 4), np.zeros(n_cl, dtype=np.int64), np.full(n_cl, -1)], axis=1))
+    terms.append(np.stack([sign.ravel(), v.ravel()], axis=1))
+    props = np.concatenate(props).astype(np.int32)
+    terms = np.concatenate(terms).astype(np.int32)
+    a = rng.between(nvars, 1, 12)
+    b = rng.between(nvars, 1, 12)
+    single = rng.below(nvars, 1000) < 50
+    lb = np.where(single, s, np.maximum(0, s - a))
+    ub = np.where(single, s, np.minimum(61, s + b))
+    bfix = rng.below(nvars, 1000) < 300
+    lb = np.where(is_bool, np.where(bfix, s, 0), lb)
+    ub = np.where(is_bool, np.where(bfix, s, 1), ub)
+    store = np.stack([lb, ub], axis=1).astype(np.int32)
+    order = np.lexsort((props[:, 2], props[:, 0]))
+    props = np.ascontiguousarray(props[order])
+    return PcNetwork(props, terms, store, s.astype(np.int32), dict(nvars=nvars, nprops=len(props), nterms=len(terms), seed=seed))
+
+
 def eps_stores(base_store, decision_vars, first_id, n):
     """Host restatement of lpc_batch_init_split (include/lpc.h): subproblem id bit j halves variable d_j."""
     out = np.repeat(base_store[None, :, :], n, axis=0).copy()

@@ -163,3 +163,121 @@ def pir_exhaustive(op, minval, maxval, complete, threads=0, want_fixpoints=False
                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                               _p32(fix) if want_fixpoints else None)
     return dict(zip(EXH_KEYS, (int(v) for v in out))), fix
+
+
+# ---- PC (oracle/pc_oracle.cpp) -------------------------------------------------------------------------------------
+# prefix token codes of the formula stream (enum Tok in pc_oracle.cpp)
+T_CONST, T_VAR, T_NEG, T_ABS, T_ADD, T_SUB, T_MUL, T_NARY_ADD = 1, 2, 3, 4, 5, 6, 7, 8
+F_VARLIT, F_NVARLIT, F_LEQ, F_GT, F_EQ, F_NEQ, F_AND, F_OR, F_EQUIV = 20, 21, 22, 23, 24, 25, 26, 27, 28
+
+_pc_bound = False
+
+
+def _pc_lib():
+    global _pc_bound
+    L = lib()
+    if not _pc_bound:
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        L.lpco_pc_parse.argtypes = [i32p, ctypes.c_int32]
+        L.lpco_pc_parse.restype = ctypes.c_void_p
+        L.lpco_pc_free.argtypes = [ctypes.c_void_p]
+        L.lpco_pc_free.restype = None
+        L.lpco_pc_deduce.argtypes = [ctypes.c_void_p, ctypes.c_int32, i32p, ctypes.c_int32, i32p]
+        L.lpco_pc_deduce.restype = ctypes.c_int
+        L.lpco_pc_ask.argtypes = [ctypes.c_void_p, ctypes.c_int32, i32p, ctypes.c_int32]
+        L.lpco_pc_ask.restype = ctypes.c_int
+        L.lpco_pc_term_project.argtypes = [i32p, i32p, ctypes.c_int32, i32p]
+        L.lpco_pc_term_project.restype = None
+        L.lpco_pc_term_embed.argtypes = [i32p, i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+        L.lpco_pc_term_embed.restype = ctypes.c_int
+        L.lpco_pc_fixpoint.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                       ctypes.POINTER(Stats)]
+        L.lpco_pc_fixpoint.restype = None
+        L.lpco_pc_ask_all.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint8)]
+        L.lpco_pc_ask_all.restype = ctypes.c_int64
+        _pc_bound = True
+    return L
+
+
+def flatten(tree):
+    """Nested tuples -> prefix int list. ('var', v), ('const', k), ('neg', t), ('abs', t), ('add'|'sub'|'mul', a, b),
+    ('sum', t1, ..., tn); formulas ('lit', v), ('nlit', v), ('le'|'gt'|'eq'|'ne', a, b), ('and'|'or'|'equiv', f, g)."""
+    op = tree[0]
+    unary = {"neg": T_NEG, "abs": T_ABS}
+    binary = {"add": T_ADD, "sub": T_SUB, "mul": T_MUL, "le": F_LEQ, "gt": F_GT, "eq": F_EQ, "ne": F_NEQ,
+              "and": F_AND, "or": F_OR, "equiv": F_EQUIV}
+    if op == "var":
+        return [T_VAR, int(tree[1])]
+    if op == "const":
+        return [T_CONST, int(tree[1])]
+    if op == "lit":
+        return [F_VARLIT, int(tree[1])]
+    if op == "nlit":
+        return [F_NVARLIT, int(tree[1])]
+    if op in unary:
+        return [unary[op]] + flatten(tree[1])
+    if op in binary:
+        return [binary[op]] + flatten(tree[1]) + flatten(tree[2])
+    if op == "sum":
+        out = [T_NARY_ADD, len(tree) - 1]
+        for t in tree[1:]:
+            out += flatten(t)
+        return out
+    raise ValueError(f"unknown node {op}")
+
+
+class PCModel:
+    """A list of PC propagators (formula trees) held by the CPU checker."""
+
+    def __init__(self, formulas):
+        self.formulas = list(formulas)
+        stream = []
+        for f in self.formulas:
+            stream += flatten(f)
+        self._stream = np.asarray(stream if stream else [0], dtype=np.int32)
+        self._h = _pc_lib().lpco_pc_parse(_p32(self._stream), len(self.formulas))
+
+    def __len__(self):
+        return len(self.formulas)
+
+    def deduce(self, i, store, is_bot=False):
+        s = _store(store).copy()
+        b = ctypes.c_int32(int(is_bot))
+        c = _pc_lib().lpco_pc_deduce(self._h, i, _p32(s), s.shape[0], ctypes.byref(b))
+        return s, bool(c), bool(b.value)
+
+    def ask(self, i, store):
+        s = _store(store)
+        return bool(_pc_lib().lpco_pc_ask(self._h, i, _p32(s), s.shape[0]))
+
+    def fixpoint(self, store, stop_on_bot=True, max_sweeps=0):
+        s = _store(store).copy()
+        st = Stats()
+        _pc_lib().lpco_pc_fixpoint(self._h, _p32(s), s.shape[0], int(stop_on_bot), max_sweeps, ctypes.byref(st))
+        return s, st
+
+    def ask_all(self, store, want_bits=False):
+        s = _store(store)
+        bits = np.zeros(max(1, len(self)), dtype=np.uint8)
+        n = _pc_lib().lpco_pc_ask_all(self._h, _p32(s), s.shape[0], bits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return (int(n), bits[:len(self)]) if want_bits else int(n)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _pc_lib().lpco_pc_free(self._h)
+            self._h = None
+
+
+def pc_term_project(term, store):
+    s = _store(store)
+    stream = np.asarray(flatten(term), dtype=np.int32)
+    out = np.zeros(2, dtype=np.int32)
+    _pc_lib().lpco_pc_term_project(_p32(stream), _p32(s), s.shape[0], _p32(out))
+    return int(out[0]), int(out[1])
+
+
+def pc_term_embed(term, store, lb, ub):
+    s = _store(store).copy()
+    stream = np.asarray(flatten(term), dtype=np.int32)
+    c = _pc_lib().lpco_pc_term_embed(_p32(stream), _p32(s), s.shape[0], lb, ub)
+    return s, bool(c)

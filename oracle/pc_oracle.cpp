@@ -1,0 +1,394 @@
+// pc_oracle.cpp — TEST INFRASTRUCTURE ONLY (see pir_oracle.cpp). CPU restatement of the PC hot path of lala-pc:
+// PC::deduce(i) -> pc::Formula::deduce -> pc::Term::{project, embed} over a VStore<Interval<ZLB>>.
+//
+// What it restates (paths relative to the lala-pc repository):
+//   PC::deduce(int) / ask(int) / num_deductions       include/lala/pc.hpp:661-680
+//   Formula as term: embed / project                  include/lala/formula.hpp:1090-1102
+//   VariableLiteral<neg>                              include/lala/formula.hpp:80-167
+//   Conjunction / Disjunction / Biconditional         include/lala/formula.hpp:241-451
+//   Equality<neg> (=, !=)                             include/lala/formula.hpp:589-724
+//   Inequality<neg> (<=, >)                           include/lala/formula.hpp:727-851
+//   Constant, Variable, Unary<Neg|Abs>                include/lala/terms.hpp:18-175
+//   Binary<GroupAdd|GroupSub|GroupMul<EDIV>>          include/lala/terms.hpp:177-262, 333-434
+//   Nary<Add>                                         include/lala/terms.hpp:436-526
+// The leaf arithmetic, Interval::project(Sig, ...), additive_inverse, fjoin, LB::prev / UB::prev, lives in
+// lala-core v1.2.8 (un-vendored, CMakeLists.txt:33-37) and is restated from its published behaviour:
+//   ADD/SUB componentwise on the bounds (no bot check: Nary<Add>::embed feeds it the crossed interval produced by
+//   additive_inverse, terms.hpp:190-194), NEG = [-ub,-lb], ABS, MUL / EDIV = hull of the corner results,
+//   an infinite operand bound gives an infinite result bound.
+//
+// Parity status: PINNED by tests/pc_test.cpp for what its goldens exercise (TermTest.AddTermBinary/AddTermNary,
+// <=, >, =, != on sums and differences, NEG, ABS, positive coefficients under <=, reification, clauses, infinite
+// domains on a single variable). PARITY UNPINNED for: lower-bound rounding of `u ediv c` (reified sums with b = 0),
+// negative coefficients, infinite bounds inside sums (tests/test_oracle_pc.py lists the pinned goldens).
+//
+// Formulas come in as a prefix-encoded int32 stream (see enum Tok); the same stream is what the tests flatten into
+// the device encoding of include/lpc_pc.h.
+
+#include <cstdint>
+#include <climits>
+#include <memory>
+#include <vector>
+#include <chrono>
+
+namespace {
+
+typedef int32_t v_t;
+const v_t INF = INT32_MAX, MINF = INT32_MIN;
+
+struct Itv {
+  v_t lb, ub;
+  Itv() : lb(MINF), ub(INF) {}
+  Itv(v_t l, v_t u) : lb(l), ub(u) {}
+  bool is_bot() const { return lb > ub; }
+  bool meet(const Itv& o) { bool c = false; if(o.lb > lb) { lb = o.lb; c = true; } if(o.ub < ub) { ub = o.ub; c = true; } return c; }
+  bool contains0() const { return lb <= 0 && 0 <= ub; }          // `*this >= eq_zero` in the lattice order
+  bool sub_of(v_t l, v_t u) const { return is_bot() || (lb >= l && ub <= u); }   // `*this <= [l,u]`
+};
+inline Itv fjoin(const Itv& a, const Itv& b) {
+  if(a.is_bot()) return b;
+  if(b.is_bot()) return a;
+  return Itv(a.lb < b.lb ? a.lb : b.lb, a.ub > b.ub ? a.ub : b.ub);
+}
+inline bool inf(v_t x) { return x == INF || x == MINF; }
+inline v_t clamp64(long long x) { return x >= INF ? INF : (x <= MINF ? MINF : (v_t)x); }
+// bound arithmetic: an infinite operand gives an infinite result of the natural sign
+inline v_t badd(v_t a, v_t b) { if(inf(a)) return a; if(inf(b)) return b; return clamp64((long long)a + b); }
+inline v_t bneg(v_t a) { return a == INF ? MINF : (a == MINF ? INF : -a); }
+inline v_t bsub(v_t a, v_t b) { return badd(a, bneg(b)); }
+inline v_t bmul(v_t a, v_t b) {
+  if(a == 0 || b == 0) return 0;
+  if(inf(a) || inf(b)) return ((a < 0) != (b < 0)) ? MINF : INF;
+  return clamp64((long long)a * b);
+}
+inline v_t bediv(v_t a, v_t b) {   // Euclidean division, b != 0
+  if(inf(a)) return (b > 0) ? a : bneg(a);
+  if(inf(b)) return 0;
+  long long q = (long long)a / b, r = (long long)a % b;
+  if(r < 0) q += (b > 0) ? -1 : 1;
+  return clamp64(q);
+}
+inline Itv p_add(const Itv& a, const Itv& b) { return Itv(badd(a.lb, b.lb), badd(a.ub, b.ub)); }
+inline Itv p_sub(const Itv& a, const Itv& b) { return Itv(bsub(a.lb, b.ub), bsub(a.ub, b.lb)); }
+inline Itv p_neg(const Itv& a) { return Itv(bneg(a.ub), bneg(a.lb)); }
+inline Itv additive_inverse(const Itv& a) { return Itv(bneg(a.lb), bneg(a.ub)); }
+inline Itv p_abs(const Itv& a) {
+  if(a.is_bot()) return a;
+  if(a.lb >= 0) return a;
+  if(a.ub <= 0) return p_neg(a);
+  v_t m = bneg(a.lb) > a.ub ? bneg(a.lb) : a.ub;
+  return Itv(0, m);
+}
+inline Itv hull4(v_t t1, v_t t2, v_t t3, v_t t4) {
+  v_t lo = t1, hi = t1;
+  for(v_t t : {t2, t3, t4}) { if(t < lo) lo = t; if(t > hi) hi = t; }
+  return Itv(lo, hi);
+}
+inline Itv p_mul(const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return Itv(INF, MINF);
+  return hull4(bmul(a.lb, b.lb), bmul(a.lb, b.ub), bmul(a.ub, b.lb), bmul(a.ub, b.ub));
+}
+inline Itv p_ediv(const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return Itv(INF, MINF);
+  if(b.contains0()) return Itv();   // unpinned: not exercised by the in-scope shapes (constant non-zero divisors)
+  return hull4(bediv(a.lb, b.lb), bediv(a.lb, b.ub), bediv(a.ub, b.lb), bediv(a.ub, b.ub));
+}
+
+struct Store {
+  v_t* d; int n; bool bot;
+  Itv get(int v) const { return Itv(d[2 * v], d[2 * v + 1]); }
+  void project(int v, Itv& r) const { r.meet(get(v)); }
+  bool embed(int v, const Itv& u) {
+    Itv c = get(v);
+    if(c.meet(u)) { d[2 * v] = c.lb; d[2 * v + 1] = c.ub; if(c.is_bot()) bot = true; return true; }
+    return false;
+  }
+};
+
+enum Tok { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8,
+           F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27, F_EQUIV = 28 };
+
+struct Term {
+  int kind = 0; v_t k = 0; int var = -1;
+  std::vector<std::unique_ptr<Term>> sub;
+  bool is_const() const { return kind == T_CONST; }
+
+  void project(const Store& a, Itv& r) const {
+    switch(kind) {
+      case T_CONST: r.meet(Itv(k, k)); break;                        // terms.hpp:34
+      case T_VAR: a.project(var, r); break;                          // terms.hpp:69-71
+      case T_NEG: { Itv t; sub[0]->project(a, t); r.meet(p_neg(t)); break; }   // terms.hpp:148-152, 91-93
+      case T_ABS: { Itv t; sub[0]->project(a, t); r.meet(p_abs(t)); break; }
+      case T_ADD: case T_SUB: case T_MUL: {                          // terms.hpp:399-405
+        Itv x, y; sub[0]->project(a, x); sub[1]->project(a, y);
+        r.meet(kind == T_ADD ? p_add(x, y) : kind == T_SUB ? p_sub(x, y) : p_mul(x, y));
+        break;
+      }
+      case T_NARY_ADD: {                                             // terms.hpp:465-478
+        Itv accu; sub[0]->project(a, accu);
+        for(size_t i = 1; i < sub.size(); ++i) { Itv t; sub[i]->project(a, t); accu = p_add(accu, t); }
+        r.meet(accu);
+        break;
+      }
+    }
+  }
+
+  bool embed(Store& a, const Itv& u) const {
+    switch(kind) {
+      case T_CONST: return false;                                    // terms.hpp:33
+      case T_VAR: return a.embed(var, u);                            // terms.hpp:65-67
+      case T_NEG: { Itv t; t.meet(p_neg(u)); return sub[0]->embed(a, t); }     // terms.hpp:142-146, 95-97
+      case T_ABS: { Itv t; t.meet(fjoin(u, p_neg(u))); return sub[0]->embed(a, t); }   // terms.hpp:112-114
+      case T_ADD: case T_SUB: case T_MUL: {                          // terms.hpp:376-397
+        bool ch = false;
+        if(!sub[0]->is_const()) {
+          Itv yt, res; sub[1]->project(a, yt);
+          left_residual(u, yt, res);
+          ch |= sub[0]->embed(a, res);
+        }
+        if(!sub[1]->is_const()) {
+          Itv xt, res; sub[0]->project(a, xt);
+          right_residual(u, xt, res);
+          ch |= sub[1]->embed(a, res);
+        }
+        return ch;
+      }
+      case T_NARY_ADD: {                                             // terms.hpp:480-499
+        Itv all; project(a, all);
+        bool ch = false;
+        for(size_t i = 0; i < sub.size(); ++i) {
+          Itv tmp; sub[i]->project(a, tmp);
+          Itv tmp2; tmp2.meet(p_add(all, additive_inverse(tmp)));    // GroupAdd::rev_op, terms.hpp:190-194
+          Itv res; res.meet(p_sub(u, tmp2));                         // GroupAdd::left_residual, :196-198
+          ch |= sub[i]->embed(a, res);
+        }
+        return ch;
+      }
+    }
+    return false;
+  }
+
+  void left_residual(const Itv& u, const Itv& b, Itv& r) const {
+    if(kind == T_ADD) r.meet(p_sub(u, b));                           // terms.hpp:196-198
+    else if(kind == T_SUB) r.meet(p_add(u, b));                      // terms.hpp:218-220
+    else if(!(u.contains0() && b.contains0())) r.meet(p_ediv(u, b)); // GroupMul, terms.hpp:249-253
+  }
+  void right_residual(const Itv& u, const Itv& b, Itv& r) const {
+    if(kind == T_SUB) r.meet(p_sub(b, u));                           // terms.hpp:222-224
+    else left_residual(u, b, r);
+  }
+};
+
+struct Formula {
+  int kind = 0; int var = -1;
+  std::unique_ptr<Term> l, r;
+  std::unique_ptr<Formula> f, g;
+
+  bool ask(const Store& a) const { return ask_impl(a, false); }
+  bool nask(const Store& a) const { return ask_impl(a, true); }
+  bool deduce(Store& a) const { return deduce_impl(a, false); }
+  bool contradeduce(Store& a) const { return deduce_impl(a, true); }
+
+  // `negated` selects the dual operation (nask / contradeduce); literal and comparison kinds fold it into `neg`.
+  bool ask_impl(const Store& a, bool negated) const {
+    switch(kind) {
+      case F_VARLIT: case F_NVARLIT: {                               // formula.hpp:97-110, 126-135
+        bool neg = (kind == F_NVARLIT) != negated;
+        Itv t; a.project(var, t);
+        return neg ? t.sub_of(0, 0) : !t.contains0();
+      }
+      case F_LEQ: case F_GT: {                                       // formula.hpp:757-771
+        bool neg = (kind == F_GT) != negated;
+        Itv x, y; l->project(a, x); r->project(a, y);
+        return neg ? x.lb > y.ub : x.ub <= y.lb;
+      }
+      case F_EQ: case F_NEQ: {                                       // formula.hpp:616-631
+        bool neg = (kind == F_NEQ) != negated;
+        Itv x, y; l->project(a, x); r->project(a, y);
+        if(neg) { Itv m = x; m.meet(y); return m.is_bot(); }
+        return ((x.is_bot() && y.is_bot()) || (x.lb == y.lb && x.ub == y.ub)) && x.lb == x.ub;
+      }
+      case F_AND: return negated ? (f->nask(a) || g->nask(a)) : (f->ask(a) && g->ask(a));       // formula.hpp:268-274
+      case F_OR: return negated ? (f->nask(a) && g->nask(a)) : (f->ask(a) || g->ask(a));        // formula.hpp:338-344
+      case F_EQUIV:                                                  // formula.hpp:408-419
+        return negated ? ((f->ask(a) && g->nask(a)) || (f->nask(a) && g->ask(a)))
+                       : ((f->ask(a) && g->ask(a)) || (f->nask(a) && g->nask(a)));
+    }
+    return false;
+  }
+
+  bool deduce_impl(Store& a, bool negated) const {
+    switch(kind) {
+      case F_VARLIT: case F_NVARLIT: {                               // formula.hpp:112-120, 140-149
+        bool neg = (kind == F_NVARLIT) != negated;
+        return a.embed(var, neg ? Itv(0, 0) : Itv(1, 1));
+      }
+      case F_LEQ: case F_GT: {                                       // formula.hpp:773-807
+        bool neg = (kind == F_GT) != negated;
+        bool ch = false;
+        Itv x, y;
+        if(neg) {   // l > r
+          if(!l->is_const()) { r->project(a, y); y.meet(Itv(badd(y.lb, 1), INF)); ch = l->embed(a, Itv(y.lb, INF)); }
+          if(!r->is_const()) { l->project(a, x); x.meet(Itv(MINF, bsub(x.ub, 1))); ch |= r->embed(a, Itv(MINF, x.ub)); }
+        }
+        else {      // l <= r
+          if(!l->is_const()) { r->project(a, y); ch |= l->embed(a, Itv(MINF, y.ub)); }
+          if(!r->is_const()) { l->project(a, x); ch = r->embed(a, Itv(x.lb, INF)); }   // `=` as in formula.hpp:803
+        }
+        return ch;
+      }
+      case F_EQ: case F_NEQ: {                                       // formula.hpp:633-683
+        bool neg = (kind == F_NEQ) != negated;
+        Itv x, y;
+        if(neg) {
+          if(!r->is_const()) {
+            l->project(a, x);
+            if(x.lb == x.ub) {
+              r->project(a, y);
+              Itv lo = y, hi = y;
+              lo.meet(Itv(badd(x.lb, 1), INF));
+              hi.meet(Itv(MINF, bsub(x.ub, 1)));
+              return r->embed(a, fjoin(lo, hi));
+            }
+          }
+          if(!l->is_const()) {
+            r->project(a, y);
+            if(y.lb == y.ub) {
+              Itv x2; l->project(a, x2);
+              Itv lo = x2, hi = x2;
+              lo.meet(Itv(badd(y.lb, 1), INF));
+              hi.meet(Itv(MINF, bsub(y.ub, 1)));
+              return l->embed(a, fjoin(lo, hi));
+            }
+          }
+          return false;
+        }
+        bool ch = false;
+        if(!r->is_const()) { l->project(a, x); ch = r->embed(a, x); }
+        if(!l->is_const()) { r->project(a, y); ch |= l->embed(a, y); }
+        return ch;
+      }
+      case F_AND:                                                    // formula.hpp:276-286
+        if(!negated) { bool c = f->deduce(a); c |= g->deduce(a); return c; }
+        if(f->ask(a)) return g->contradeduce(a);
+        else if(g->ask(a)) return f->contradeduce(a);
+        return false;
+      case F_OR:                                                     // formula.hpp:346-356
+        if(negated) { bool c = f->contradeduce(a); c |= g->contradeduce(a); return c; }
+        if(f->nask(a)) return g->deduce(a);
+        else if(g->nask(a)) return f->deduce(a);
+        return false;
+      case F_EQUIV:                                                  // formula.hpp:421-435
+        if(!negated) {
+          if(f->ask(a)) return g->deduce(a);
+          else if(f->nask(a)) return g->contradeduce(a);
+          else if(g->ask(a)) return f->deduce(a);
+          else if(g->nask(a)) return f->contradeduce(a);
+          return false;
+        }
+        if(f->ask(a)) return g->contradeduce(a);
+        else if(f->nask(a)) return g->deduce(a);
+        else if(g->ask(a)) return f->contradeduce(a);
+        else if(g->nask(a)) return f->deduce(a);
+        return false;
+    }
+    return false;
+  }
+};
+
+std::unique_ptr<Term> parse_term(const int32_t*& p) {
+  std::unique_ptr<Term> t(new Term());
+  t->kind = *p++;
+  switch(t->kind) {
+    case T_CONST: t->k = *p++; break;
+    case T_VAR: t->var = *p++; break;
+    case T_NEG: case T_ABS: t->sub.push_back(parse_term(p)); break;
+    case T_ADD: case T_SUB: case T_MUL: t->sub.push_back(parse_term(p)); t->sub.push_back(parse_term(p)); break;
+    case T_NARY_ADD: { int n = *p++; for(int i = 0; i < n; ++i) t->sub.push_back(parse_term(p)); break; }
+  }
+  return t;
+}
+std::unique_ptr<Formula> parse_formula(const int32_t*& p) {
+  std::unique_ptr<Formula> f(new Formula());
+  f->kind = *p++;
+  switch(f->kind) {
+    case F_VARLIT: case F_NVARLIT: f->var = *p++; break;
+    case F_LEQ: case F_GT: case F_EQ: case F_NEQ: f->l = parse_term(p); f->r = parse_term(p); break;
+    default: f->f = parse_formula(p); f->g = parse_formula(p); break;
+  }
+  return f;
+}
+
+struct Model { std::vector<std::unique_ptr<Formula>> props; };
+
+bool scan_bot(const v_t* d, int n) { for(int i = 0; i < n; ++i) if(d[2 * i] > d[2 * i + 1]) return true; return false; }
+
+} // namespace
+
+extern "C" {
+
+struct lpco_stats { int32_t has_changed, is_bot; int64_t sweeps, deductions; double seconds; };
+
+// stream: n_props formulas, prefix encoded back to back. Returns an opaque model.
+void* lpco_pc_parse(const int32_t* stream, int32_t n_props) {
+  Model* m = new Model();
+  const int32_t* p = stream;
+  for(int i = 0; i < n_props; ++i) m->props.push_back(parse_formula(p));
+  return m;
+}
+void lpco_pc_free(void* m) { delete static_cast<Model*>(m); }
+
+// PC::deduce(i) (pc.hpp:671-680) on an interleaved {lb,ub} store.
+int lpco_pc_deduce(void* m, int32_t i, int32_t* lbub, int32_t nvars, int32_t* is_bot) {
+  Store s{lbub, nvars, is_bot && *is_bot};
+  bool c = static_cast<Model*>(m)->props[i]->deduce(s);
+  if(is_bot) *is_bot = s.bot;
+  return c;
+}
+int lpco_pc_ask(void* m, int32_t i, const int32_t* lbub, int32_t nvars) {
+  Store s{const_cast<int32_t*>(lbub), nvars, false};
+  return static_cast<Model*>(m)->props[i]->ask(s);
+}
+// Term-level entry points for TermTest.* (pc_test.cpp:31-67): project / embed of ONE term stream.
+void lpco_pc_term_project(const int32_t* stream, const int32_t* lbub, int32_t nvars, int32_t* out2) {
+  const int32_t* p = stream;
+  auto t = parse_term(p);
+  Store s{const_cast<int32_t*>(lbub), nvars, false};
+  Itv r; t->project(s, r);
+  out2[0] = r.lb; out2[1] = r.ub;
+}
+int lpco_pc_term_embed(const int32_t* stream, int32_t* lbub, int32_t nvars, int32_t lb, int32_t ub) {
+  const int32_t* p = stream;
+  auto t = parse_term(p);
+  Store s{lbub, nvars, false};
+  return t->embed(s, Itv(lb, ub));
+}
+
+// GaussSeidelIteration::fixpoint over PC::deduce(i) (tests/pc_test.cpp:91-94); stop_on_bot as in pir_oracle.cpp.
+void lpco_pc_fixpoint(void* mp, int32_t* lbub, int32_t nvars, int32_t stop_on_bot, int64_t max_sweeps, lpco_stats* out) {
+  Model* m = static_cast<Model*>(mp);
+  Store s{lbub, nvars, scan_bot(lbub, nvars)};
+  auto t0 = std::chrono::steady_clock::now();
+  bool changed = true, any = false;
+  int64_t sweeps = 0;
+  const size_t n = m->props.size();
+  while(changed && !(stop_on_bot && s.bot) && (max_sweeps <= 0 || sweeps < max_sweeps)) {
+    changed = false;
+    for(size_t i = 0; i < n; ++i) changed |= m->props[i]->deduce(s);
+    any |= changed;
+    ++sweeps;
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  if(out) { out->has_changed = any; out->is_bot = s.bot; out->sweeps = sweeps; out->deductions = sweeps * (int64_t)n;
+            out->seconds = std::chrono::duration<double>(t1 - t0).count(); }
+}
+
+int64_t lpco_pc_ask_all(void* mp, const int32_t* lbub, int32_t nvars, uint8_t* bits) {
+  Model* m = static_cast<Model*>(mp);
+  Store s{const_cast<int32_t*>(lbub), nvars, false};
+  int64_t c = 0;
+  for(size_t i = 0; i < m->props.size(); ++i) { bool e = m->props[i]->ask(s); if(bits) bits[i] = e; c += e; }
+  return c;
+}
+
+} // extern "C"

@@ -1,0 +1,118 @@
+"""Writes tests/golden/pc_kat.json: the reference's PC golden vectors (tests/pc_test.cpp) as formula trees.
+
+The reference builds its propagators from FlatZinc through an un-vendored parser; here each case is the formula tree
+the PC interpreter produces for it (pc.hpp:217-604): `int_ge(t, k)` is the flipped `k <= t` (pc.hpp:565),
+`int_plus(x, y, k)` is `x + y = k`, `bool_clause([x1,x2],[y1,y2])` is the binarised disjunction
+`x1 \\/ (x2 \\/ (not y1 \\/ not y2))` (pc.hpp:542-544), `b = (phi)` is the biconditional `b <=> phi`, a Boolean
+variable used as a formula is a VariableLiteral. Expected intervals are the reference's own. `bot: true` means the
+reference expects every listed variable to be bot and `is_bot()`.
+
+Run:  python tests/golden/make_pc_kat.py
+"""
+import json
+import os
+
+NI, PI = -2**31, 2**31 - 1
+TOP = [NI, PI]
+K = []
+
+
+def v(i):
+    return ["var", i]
+
+
+def c(k):
+    return ["const", k]
+
+
+def kat(name, source, store, props, after=None, bot=False, ua=None, changed=None):
+    K.append(dict(name=name, source=source, store=store, props=props, after=after, bot=bot, ua=ua, changed=changed))
+
+
+D10 = [0, 10]
+kat("AddEquality", "pc_test.cpp:114-120", [D10, D10], [["eq", ["add", v(0), v(1)], c(5)]], [[0, 5], [0, 5]], ua=False, changed=True)
+kat("TemporalConstraint1Flat", "pc_test.cpp:123-129", [D10, D10, [NI, 5]], [["eq", ["add", v(0), v(1)], v(2)]],
+    [[0, 5], [0, 5], [0, 5]], ua=False, changed=True)
+kat("TemporalConstraint1", "pc_test.cpp:132-138", [D10, D10], [["le", ["add", v(0), v(1)], c(5)]], [[0, 5], [0, 5]], ua=False, changed=True)
+kat("TemporalConstraint2", "pc_test.cpp:141-147", [D10, D10], [["gt", ["add", v(0), v(1)], c(5)]], [D10, D10], ua=False, changed=False)
+kat("TemporalConstraint3", "pc_test.cpp:150-156", [[0, 3], [0, 3]], [["gt", ["add", v(0), v(1)], c(5)]], [[3, 3], [3, 3]], ua=True, changed=True)
+kat("TemporalConstraint4", "pc_test.cpp:159-165", [[0, 3], [0, 3]], [["le", c(5), ["add", v(0), v(1)]]], [[2, 3], [2, 3]], ua=False, changed=True)
+kat("TemporalConstraint5", "pc_test.cpp:168-174", [[0, 4], [0, 4]], [["eq", ["add", v(0), v(1)], c(5)]], [[1, 4], [1, 4]], ua=False, changed=True)
+kat("TemporalConstraint6", "pc_test.cpp:177-183", [D10, D10], [["le", ["sub", v(0), v(1)], c(5)]], [D10, D10], ua=False, changed=False)
+kat("TemporalConstraint7", "pc_test.cpp:186-192", [D10, D10], [["le", ["sub", v(0), v(1)], c(-10)]], [[0, 0], [10, 10]], ua=True, changed=True)
+kat("TemporalConstraint8", "pc_test.cpp:195-201", [D10, D10], [["le", c(5), ["sub", v(0), v(1)]]], [[5, 10], [0, 5]], ua=False, changed=True)
+kat("TemporalConstraint9", "pc_test.cpp:204-210", [D10, D10], [["le", ["sub", v(0), v(1)], c(-5)]], [[0, 5], [5, 10]], ua=False, changed=True)
+kat("TemporalConstraint10", "pc_test.cpp:213-219", [D10, D10], [["le", v(0), ["add", c(-5), v(1)]]], [[0, 5], [5, 10]], ua=False, changed=True)
+for nm, src, dom, k, after, bot, ua in [
+    ("TopProp", "pc_test.cpp:222-230", [3, 10], 8, None, True, None),
+    ("TernaryAdd2", "pc_test.cpp:233-240", [3, 10], 9, [[3, 3]] * 3, False, True),
+    ("TernaryAdd3", "pc_test.cpp:243-250", [3, 10], 10, [[3, 4]] * 3, False, False),
+    ("TernaryAdd4", "pc_test.cpp:253-260", [-2, 2], -5, [[-2, -1]] * 3, False, False),
+]:
+    kat(nm, src, [dom, dom, dom], [["le", ["add", ["add", v(0), v(1)], v(2)], c(k)]], after, bot=bot, ua=ua, changed=True)
+    # the same constraint as ONE n-ary sum (the shape config 3 uses); same expected result
+    kat(nm + ".nary", src, [dom, dom, dom], [["le", ["sum", v(0), v(1), v(2)], c(k)]], after, bot=bot, ua=ua, changed=True)
+B = [0, 1]
+for nm, src, terms, after, ua, chg in [
+    ("PseudoBoolean1", "pc_test.cpp:263-270", (["mul", c(2), v(0)], v(1), ["mul", c(3), v(2)]), [B, B, [0, 0]], False, True),
+    ("PseudoBoolean2", "pc_test.cpp:273-280", (["mul", c(2), v(0)], ["mul", c(5), v(1)], ["mul", c(3), v(2)]), [B, [0, 0], [0, 0]], True, True),
+    ("PseudoBoolean3", "pc_test.cpp:283-290", (["mul", c(3), v(0)], ["mul", c(5), v(1)], ["mul", c(3), v(2)]), [[0, 0]] * 3, True, True),
+    ("PseudoBoolean4", "pc_test.cpp:293-300", (["neg", v(0)], v(1), ["mul", c(3), v(2)]), [B, B, B], False, False),
+]:
+    kat(nm, src, [B, B, B], [["le", ["add", ["add", terms[0], terms[1]], terms[2]], c(2)]], after, ua=ua, changed=chg)
+    kat(nm + ".nary", src, [B, B, B], [["le", ["sum", terms[0], terms[1], terms[2]], c(2)]], after, ua=ua, changed=chg)
+for nm, src, dom, prop, after, bot, ua in [
+    ("NegationOp1", "pc_test.cpp:303-308", [-4, 3], ["le", ["neg", v(0)], c(2)], [[-2, 3]], False, True),
+    ("NegationOp2", "pc_test.cpp:311-316", [-4, 3], ["le", ["neg", v(0)], c(-2)], [[2, 3]], False, True),
+    ("NegationOp3", "pc_test.cpp:319-324", [0, 3], ["le", ["neg", v(0)], c(-2)], [[2, 3]], False, True),
+    ("NegationOp4", "pc_test.cpp:327-332", [-4, -3], ["le", ["neg", v(0)], c(4)], [[-4, -3]], False, True),
+    ("NegationOp5", "pc_test.cpp:335-340", [-4, 3], ["le", c(-2), ["neg", v(0)]], [[-4, 2]], False, True),
+    ("NegationOp6", "pc_test.cpp:343-348", [-4, 3], ["gt", ["neg", v(0)], c(2)], [[-4, -3]], False, True),
+    ("NegationOp7", "pc_test.cpp:351-357", [-4, 3], ["le", c(5), ["neg", v(0)]], None, True, None),
+]:
+    kat(nm, src, [dom], [prop], after, bot=bot, ua=ua)
+
+
+def resource(k1, k2):
+    return ["equiv", ["lit", 2], ["and", ["le", ["sub", v(0), v(1)], c(k1)], ["le", ["sub", v(1), v(0)], c(k2)]]]
+
+
+kat("ResourceConstraint1.a", "pc_test.cpp:360-368", [[5, 10], [9, 15], B], [resource(0, 2)], [[5, 10], [9, 15], B], ua=False, changed=False)
+kat("ResourceConstraint1.b", "pc_test.cpp:370-371", [[5, 10], [9, 15], [1, 1]], [resource(0, 2)], [[7, 10], [9, 12], [1, 1]], ua=False, changed=True)
+kat("ResourceConstraint2.a", "pc_test.cpp:374-381", [[1, 2], [0, 2], B], [resource(2, -1)], [[1, 2], [0, 2], B], ua=False, changed=False)
+kat("ResourceConstraint2.b", "pc_test.cpp:383-384", [[1, 2], [0, 2], [0, 0]], [resource(2, -1)], [[1, 2], [1, 2], [0, 0]], ua=False, changed=True)
+kat("NotEqualConstraint1", "pc_test.cpp:386-390", [[1, 10]], [["ne", v(0), c(10)]], [[1, 9]], ua=True, changed=True)
+kat("NotEqualConstraint2", "pc_test.cpp:392-396", [[1, 10], [10, 10]], [["ne", v(0), v(1)]], [[1, 9], [10, 10]], ua=True, changed=True)
+kat("NotEqualConstraint3", "pc_test.cpp:398-402", [[1, 10]], [["ne", v(0), c(10)]], [[1, 9]], ua=True, changed=True)
+
+
+def clause():
+    return ["or", ["lit", 0], ["or", ["lit", 1], ["or", ["nlit", 2], ["nlit", 3]]]]
+
+
+kat("BooleanClause1", "pc_test.cpp:564-572", [[1, 1], B, B, B], [clause()], [[1, 1], B, B, B], ua=True, changed=False)
+kat("BooleanClause2", "pc_test.cpp:574-582", [B, B, [0, 0], B], [clause()], [B, B, [0, 0], B], ua=True, changed=False)
+kat("BooleanClause3.c", "pc_test.cpp:584-596", [[0, 0], [0, 0], [1, 1], B], [clause()], [[0, 0], [0, 0], [1, 1], [0, 0]], ua=True, changed=True)
+kat("BooleanClause4.c", "pc_test.cpp:598-610", [[0, 0], B, [1, 1], [1, 1]], [clause()], [[0, 0], [1, 1], [1, 1], [1, 1]], ua=True, changed=True)
+kat("BooleanClause3.a", "pc_test.cpp:591-592", [[0, 0], B, B, B], [clause()], [[0, 0], B, B, B], ua=False, changed=False)
+kat("IntAbs1", "pc_test.cpp:700-707", [[-15, 5], [-10, 10]], [["eq", ["abs", v(0)], v(1)]], [[-10, 5], [0, 10]], ua=False, changed=True)
+kat("InfiniteDomain1.a", "pc_test.cpp:766-772", [TOP, B], [["equiv", ["lit", 1], ["le", v(0), c(5)]]], [TOP, B], ua=False, changed=False)
+kat("InfiniteDomain1.b", "pc_test.cpp:773-775", [TOP, [1, 1]], [["equiv", ["lit", 1], ["le", v(0), c(5)]]], [[NI, 5], [1, 1]], ua=True, changed=True)
+kat("InfiniteDomain2.b", "pc_test.cpp:785-787", [TOP, [0, 0]], [["equiv", ["lit", 1], ["le", v(0), c(5)]]], [[6, PI], [0, 0]], ua=True, changed=True)
+# x = 5 xor y = 5  ==  (x = 5) <=> not (y = 5)  ==  (x = 5) <=> (y != 5)
+xor = ["equiv", ["eq", v(0), c(5)], ["ne", v(1), c(5)]]
+kat("XorConstraint1.b", "pc_test.cpp:434-435", [[1, 1], TOP], [xor], [[1, 1], [5, 5]], ua=True, changed=True)
+kat("XorConstraint2.b", "pc_test.cpp:445-446", [[1, 5], [5, 5]], [xor], [[1, 4], [5, 5]], ua=True, changed=True)
+
+TERM_KATS = [
+    dict(name="TermTest.AddTermBinary", source="pc_test.cpp:31-47", store=[D10, D10], term=["add", v(0), v(1)],
+         project=[0, 20], embed=[NI, 5], changed=True, project_after=[0, 10]),
+    dict(name="TermTest.AddTermNary", source="pc_test.cpp:49-67", store=[D10, D10, D10], term=["sum", v(0), v(1), v(2)],
+         project=[0, 30], embed=[NI, 5], changed=True, project_after=[0, 15]),
+]
+
+if __name__ == "__main__":
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pc_kat.json")
+    with open(out, "w") as f:
+        json.dump(dict(props=K, terms=TERM_KATS), f, indent=0)
+    print(f"wrote {len(K)} + {len(TERM_KATS)} cases to {out}")

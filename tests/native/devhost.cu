@@ -3,6 +3,7 @@
 // machine without a GPU. Built by tests/test_devhost.py with nvcc; never part of the product.
 #define LPC_HOST_HARNESS
 #include "../../lala-pc_b200/csrc/pir_div.cuh"
+#include "../../lala-pc_b200/csrc/pc_device.cuh"
 namespace lpc { LPC_HD void deduce_div(int op, Itv& r1, Itv& r2, Itv& r3) { deduce_div_rules(op, r1, r2, r3); } }
 using namespace lpc;
 
@@ -62,5 +63,45 @@ void devhost_exhaustive(int sig, int lo, int hi, int* out) {
     for(int k = 0; k < 6; ++k) out[idx * 7 + k] = s[k];
     out[idx * 7 + 6] = bot;
   }
+}
+
+// ---- PC: the flat propagators of pc_device.cuh on the host --------------------------------------------------------
+struct HostAcc {
+  int* d;
+  mutable int seen_bot;
+  Itv load(int v) const { if(d[2 * v] > d[2 * v + 1]) seen_bot = 1; return Itv(d[2 * v], d[2 * v + 1]); }
+  int embed(int v, const Itv& u) {
+    int f = 0;
+    if(u.lb > d[2 * v]) { d[2 * v] = u.lb; f = 1; }
+    if(u.ub < d[2 * v + 1]) { d[2 * v + 1] = u.ub; f = 1; }
+    if(f && d[2 * v] > d[2 * v + 1]) f |= 2;
+    return f;
+  }
+};
+// props: n x 5 {kind, first_term, n_terms, rhs, bvar}; terms: m x 2 {coef, var}. Gauss-Seidel, stop at bot.
+int devhost_pc_fixpoint(const int* props, long long n, const int* terms, int* lbub, int nvars, int* is_bot, int* has_changed) {
+  int bot = 0, any = 0;
+  for(int v = 0; v < nvars; ++v) bot |= lbub[2 * v] > lbub[2 * v + 1];
+  int sweeps = 0, changed = 1;
+  while(changed && !bot && sweeps < 100000) {
+    changed = 0;
+    for(long long i = 0; i < n; ++i) {
+      const int* p = props + 5 * i;
+      int4 h = make_int4(p[0] | (p[2] << 8), p[1], p[3], p[4]);
+      HostAcc acc{lbub, 0};
+      int f = pc_deduce(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
+      changed |= f & 1; bot |= ((f >> 1) & 1) | acc.seen_bot;
+    }
+    any |= changed;
+    ++sweeps;
+  }
+  *is_bot = bot; *has_changed = any;
+  return sweeps;
+}
+int devhost_pc_ask(const int* props, long long i, const int* terms, const int* lbub) {
+  const int* p = props + 5 * i;
+  int4 h = make_int4(p[0] | (p[2] << 8), p[1], p[3], p[4]);
+  HostAcc acc{const_cast<int*>(lbub), 0};
+  return pc_ask(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
 }
 }

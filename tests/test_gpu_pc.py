@@ -1,0 +1,184 @@
+"""Parity tests of the PC path (-m gpu): flat propagators on the device (include/lpc_pc.h) against the tree-walking
+oracle (oracle/pc_oracle.cpp) and the reference's golden vectors (tests/pc_test.cpp)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lala_pc_b200 as L
+    L.device_init(0)
+    return L
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def W():
+    from lala_pc_b200 import workloads
+    return workloads
+
+
+def to_tree(x):
+    return tuple(to_tree(e) if isinstance(e, list) else e for e in x)
+
+
+def flattenable(formulas):
+    from lala_pc_b200 import pcflat
+    try:
+        return pcflat.flatten(formulas)
+    except pcflat.Unsupported:
+        return None
+
+
+def check_parity(L, O, formulas, store, label=""):
+    from lala_pc_b200 import pcflat
+    props, terms = pcflat.flatten(formulas)
+    m = O.PCModel(formulas)
+    want, st = m.fixpoint(store)
+    t = L.PcTable(props, terms, len(store))
+    s = L.Store(values=store)
+    r = t.fixpoint(s)
+    got = s.read()
+    assert bool(r.is_bot) == bool(st.is_bot), (label, "bot flag")
+    if not st.is_bot:
+        assert np.array_equal(got, want), (label, "store", np.flatnonzero((got != want).any(1))[:5].tolist())
+        n_ent, bits = m.ask_all(want, want_bits=True)
+        g_ent, gbits = t.ask_all(s, want_bits=True)
+        assert np.array_equal(gbits, bits) and g_ent == n_ent, (label, "ask bits")
+        assert bool(r.has_changed) == bool(st.has_changed), (label, "has_changed")
+    return got, r, st
+
+
+def test_golden_vectors(L, O):
+    """Every pc_test.cpp golden whose tree has a flat kind, through the device path."""
+    kats = load_golden("pc_kat.json")["props"]
+    ran = 0
+    for k in kats:
+        formulas = [to_tree(p) for p in k["props"]]
+        if flattenable(formulas) is None:
+            continue
+        ran += 1
+        store = np.array(k["store"], dtype=np.int32)
+        got, r, st = check_parity(L, O, formulas, store, k["name"])
+        if k["bot"]:
+            assert r.is_bot, k["name"]
+            continue
+        after = np.array(k["after"], dtype=np.int32)
+        assert np.array_equal(got[:len(after)], after), (k["name"], got.tolist())
+    assert ran >= 18, ran
+
+
+def test_deduce_one_step_by_step(L, O):
+    """PC::deduce(i) one propagator at a time in index order == one Gauss-Seidel sweep of the tree walker."""
+    from lala_pc_b200 import pcflat
+    for k in load_golden("pc_kat.json")["props"]:
+        formulas = [to_tree(p) for p in k["props"]]
+        flat = flattenable(formulas)
+        if flat is None:
+            continue
+        m = O.PCModel(formulas)
+        store = np.array(k["store"], dtype=np.int32)
+        t = L.PcTable(flat[0], flat[1], len(store))
+        s = L.Store(values=store)
+        bot = False
+        for sweep in range(3):
+            for i in range(len(formulas)):
+                store, changed, bot = m.deduce(i, store, bot)
+                assert t.deduce(s, i) == changed, (k["name"], sweep, i)
+                if not bot:
+                    assert np.array_equal(s.read(), store), (k["name"], sweep, i)
+
+
+@pytest.mark.parametrize("cfg", ["config3", "config5"])
+def test_config_shapes_parity_small(L, O, W, cfg):
+    net = getattr(W, cfg)(0.05)
+    formulas = net.formulas()
+    got, r, st = check_parity(L, O, formulas, net.store, cfg)
+    assert not st.is_bot and st.sweeps >= 3
+    assert ((got[:, 0] <= net.solution) & (net.solution <= got[:, 1])).all()
+    # failing twin: push one variable of the first propagator far above its planted value
+    twin = net.store.copy()
+    v = int(net.terms[net.props[0, 1], 1])
+    twin[v] = (net.solution[v] + 1000, net.solution[v] + 1001)
+    _, r2, st2 = check_parity(L, O, formulas, twin, cfg + " twin")
+    assert st2.is_bot and r2.is_bot
+
+
+def test_config3_full_size(L, O, W):
+    """BASELINE.json config 3 at full size (200k vars, 1M terms): bit-exact against the tree walker; idempotent."""
+    net = W.config3()
+    assert net.meta["nterms"] >= 1_000_000
+    m = O.PCModel(net.formulas())
+    want, st = m.fixpoint(net.store)
+    t = L.PcTable(net.props, net.terms, net.nvars)
+    s = L.Store(values=net.store)
+    r = t.fixpoint(s)
+    assert not r.is_bot and np.array_equal(s.read(), want)
+    r2 = t.fixpoint(s)
+    assert not r2.has_changed and r2.sweeps == 1
+    buf = net.store.copy()
+    t.fixpoint_host(buf)
+    assert np.array_equal(buf, want)
+
+
+def random_pc(rng, nvars):
+    from lala_pc_b200 import pcflat
+    forms = []
+    for _ in range(int(rng.integers(1, 8))):
+        kind = int(rng.integers(1, 7))
+        vs = rng.permutation(nvars)
+        if kind in (1, 2):
+            n = int(rng.integers(1, min(6, nvars - 1)))
+            ts = [(int(rng.choice([1, 1, 2, 3, 5, -1, -2])), int(v)) for v in vs[:n]]
+            forms.append(pcflat.to_tree(kind, ts, int(rng.integers(-10, 40)), int(vs[n]) if kind == 2 else -1))
+        elif kind == 4 and rng.random() < 0.4:
+            forms.append(pcflat.to_tree(4, [(1, int(vs[0]))], int(rng.integers(-3, 8)), -1))
+        elif kind == 5:
+            n = int(rng.integers(1, min(5, nvars)))
+            forms.append(pcflat.to_tree(5, [(int(rng.choice([1, -1])), int(v)) for v in vs[:n]], 0, -1))
+        else:
+            forms.append(pcflat.to_tree(kind, [(1, int(vs[0])), (1, int(vs[1]))], 0, -1))
+    return forms
+
+
+def test_random_networks(L, O):
+    """Small random networks over all flat kinds (negative coefficients, 0/1 and wide domains, a few infinite
+    bounds): bot flags and non-failed stores must match the tree walker."""
+    rng = np.random.default_rng(33)
+    n_ok = 0
+    for trial in range(200):
+        nvars = int(rng.integers(4, 10))
+        forms = random_pc(rng, nvars)
+        a = rng.integers(-6, 12, (nvars, 2))
+        store = np.stack([a.min(1), a.max(1)], axis=1).astype(np.int32)
+        boolish = rng.random(nvars) < 0.4
+        store[boolish] = (0, 1)
+        if rng.random() < 0.2:
+            store[int(rng.integers(0, nvars))] = (-2**31, 2**31 - 1)
+        _, r, st = check_parity(L, O, forms, store, f"random {trial}")
+        n_ok += not st.is_bot
+    assert n_ok >= 40
+
+
+def test_errors(L):
+    with pytest.raises(L.LpcError):
+        L.PcTable(np.array([[9, 0, 1, 0, -1]], dtype=np.int32), np.array([[1, 0]], dtype=np.int32), 2)      # bad kind
+    with pytest.raises(L.LpcError):
+        L.PcTable(np.array([[1, 0, 2, 0, -1]], dtype=np.int32), np.array([[1, 0]], dtype=np.int32), 2)      # term range
+    with pytest.raises(L.LpcError):
+        L.PcTable(np.array([[1, 0, 1, 0, -1]], dtype=np.int32), np.array([[1, 5]], dtype=np.int32), 2)      # variable
+    with pytest.raises(L.LpcError):
+        L.PcTable(np.array([[2, 0, 1, 0, -1]], dtype=np.int32), np.array([[1, 0]], dtype=np.int32), 2)      # no bvar
+    t = L.PcTable(np.zeros((0, 5), dtype=np.int32), np.zeros((0, 2), dtype=np.int32), 2)
+    s = L.Store(values=np.array([[0, 5], [1, 2]], dtype=np.int32))
+    r = t.fixpoint(s)
+    assert r.sweeps == 0 and not r.has_changed and not r.is_bot
