@@ -2,8 +2,8 @@
 //
 // Device counterpart of PC::deduce(int) -> pc::Formula::deduce -> pc::Term::{project, embed}
 // (lala-pc include/lala/pc.hpp:671-680, formula.hpp, terms.hpp) for the tree shapes named in lpc_pc.h. Every routine
-// cites the tree walk it replaces. Bound arithmetic follows lala-core's Interval::project as restated by the oracle
-// (oracle/pc_oracle.cpp): ADD / SUB componentwise on the bounds, an infinite operand bound gives an infinite result
+// cites the tree walk it replaces. Bound arithmetic follows lala-core's Interval::project (un-vendored; the same
+// restatement the CPU checker of the test-suite uses): ADD / SUB componentwise on the bounds, an infinite operand bound gives an infinite result
 // bound, MUL / EDIV by a constant as the hull of the corner results. `Acc` abstracts the store: `load(v)` returns the
 // current domain, `embed(v, itv)` joins (VStore::embed) and returns bit0 = changed, bit1 = became empty.
 #pragma once
