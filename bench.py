@@ -308,6 +308,54 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
     return out
 
 
+def own_pc(args, cpu=True):
+    """PC configs (BASELINE.json configs[2] and [4]): one fixpoint of the flattened n-ary propagators per step, on an
+    interval store and (config 5) on an NBitset<64> store. Algorithmic bytes per deduction = 16 B header + per term
+    8 B {coef, var} + 8 B domain."""
+    import torch
+    import lala_pc_b200 as L
+    from lala_pc_b200 import workloads as W
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    peak, _ = measured_peak()
+    out = {}
+    for name, net, bitset in (("c3_interval", W.config3(), False), ("c5_interval", W.config5(), False),
+                              ("c5_bitset", None, True)):
+        if net is None:
+            net = prev
+        prev = net
+        t = L.PcTable(net.props, net.terms, net.nvars)
+        cells = L.nbit_from_intervals(net.store) if bitset else None
+        ms, res = [], None
+        n_steps = max(3, min(args.steps, 10))
+        for i in range(3 + n_steps):
+            s = L.Store(values=net.store)
+            if bitset:
+                s.write_bits(cells)
+            flush.zero_()
+            torch.cuda.synchronize()
+            res = t.fixpoint(s, bitset=bitset)
+            if i >= 3:
+                ms.append(res.device_ms)
+        P, T = len(net.props), len(net.terms)
+        bytes_per_sweep = 16 * P + 16 * T + (8 * int((net.props[:, 0] == 2).sum()))
+        m = float(np.mean(ms))
+        achieved = bytes_per_sweep * res.sweeps / (m * 1e-3) / 1e9
+        e = {"ms_per_fixpoint": m, "sweeps": int(res.sweeps), "propagators": P, "terms": T, "vars": net.nvars,
+             "value": res.deductions / (m * 1e-3), "unit": UNIT,
+             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                          "kernel": "k_pc_fixpoint<%s>" % ("true" if bitset else "false"),
+                          "algorithmic_bytes_per_launch": bytes_per_sweep * res.sweeps}}
+        if cpu:
+            from oracle import oracle as O
+            mdl = O.PCModel(net.formulas())
+            _, st = mdl.fixpoint_bits(cells) if bitset else mdl.fixpoint(net.store)
+            e["cpu_baseline"] = {"value": st.deductions / st.seconds, "unit": UNIT, "cores": 1, "kind": "port",
+                                 "fixpoint_ms": st.seconds * 1e3, "sweeps": int(st.sweeps),
+                                 "sample": "the whole workload: one Gauss-Seidel fixpoint of the tree-walking restatement"}
+        out[name] = e
+    return out
+
+
 def cpu_baseline_single(net, max_seconds=30.0):
     """The oracle's Gauss-Seidel fixpoint (restated reference CPU path) on the same network, 1 thread."""
     from oracle import oracle as O
@@ -378,6 +426,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c4"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink config 2 (development only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pc", action="store_true", help="skip the PC configs (3 and 5) section")
     args = ap.parse_args()
     # exactly ONE line on stdout: keep a private handle to it and point fd 1 at stderr, so that anything a C library
     # prints (e.g. NCCL's version banner) cannot end up in front of the JSON line
@@ -417,6 +466,10 @@ def main():
         line["batched"] = {k: b[k] for k in ("value", "ms_per_step", "config", "batch_result", "roofline", "e2e") if k in b}
         line["batched"]["unit"] = UNIT
         line["gpu_launches"] += b["gpu_launches"]
+        if args.workload == "c2" and args.scale == 1.0 and not args.no_pc:
+            l0 = L.launch_count()
+            line["pc"] = own_pc(args, cpu=not args.no_cpu_baseline)
+            line["gpu_launches"] += L.launch_count() - l0
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(net)
     else:

@@ -66,6 +66,22 @@ int lpc_pc_deduce_one(const lpc_pc_table* t, lpc_store* s, int64_t i, int* chang
 /* PC::ask(int i) over all i (pc.hpp:661-663; the loop of is_extractable, pc.hpp:726-738); bits may be NULL. */
 int lpc_pc_ask_all(const lpc_pc_table* t, const lpc_store* s, int64_t* n_entailed, uint8_t* bits);
 
+/* ---- bitset stores: VStore<NBitset<64, local_memory, unsigned long long>> (tests/pc_bitset_test.cpp:23-25) ----------
+ * The same 8-byte cells of an lpc_store read as ONE uint64 per variable: bit 0 = "some value <= -1", bit i (1..62) =
+ * value i - 1, bit 63 = "some value >= 62" (so [0, 61] is exact); meet = AND, bot = 0, top = all ones. A store handle
+ * carries no domain tag: the caller picks the `_bits` entry points for stores it filled with lpc_store_write_bits.
+ * Kinds with a bitset rule: EQ, NEQ (by complement, formula.hpp:642-644), CLAUSE, ABS_EQ - the shapes the reference
+ * pins in tests/pc_bitset_test.cpp. Tables holding LIN_LE / REIF_LIN_LE return LPC_ERR_UNSUPPORTED from the `_bits`
+ * calls: NBitset arithmetic on sums lives in lala-core (un-vendored) and no reference test pins it. */
+int lpc_store_write_bits(lpc_store* s, int32_t first, int32_t n, const uint64_t* cells);
+int lpc_store_read_bits(const lpc_store* s, int32_t first, int32_t n, uint64_t* cells);
+/* NBitset(lb, ub): the cell holding the integer range [lb, ub] (empty if lb > ub). Pure host helper. */
+uint64_t lpc_nbit_range(int32_t lb, int32_t ub);
+int lpc_pc_fixpoint_bits(const lpc_pc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r);
+int lpc_pc_fixpoint_bits_host(const lpc_pc_table* t, uint64_t* cells, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r);
+int lpc_pc_deduce_one_bits(const lpc_pc_table* t, lpc_store* s, int64_t i, int* changed);
+int lpc_pc_ask_all_bits(const lpc_pc_table* t, const lpc_store* s, int64_t* n_entailed, uint8_t* bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,13 @@ SIGNATURES = {
     "lpc_pc_fixpoint_host": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
     "lpc_pc_deduce_one": (ctypes.c_int, [_vp, _vp, _i64, _pint]),
     "lpc_pc_ask_all": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_int64), _pu8]),
+    "lpc_store_write_bits": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
+    "lpc_store_read_bits": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
+    "lpc_nbit_range": (_u64, [_i32, _i32]),
+    "lpc_pc_fixpoint_bits": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
+    "lpc_pc_fixpoint_bits_host": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
+    "lpc_pc_deduce_one_bits": (ctypes.c_int, [_vp, _vp, _i64, _pint]),
+    "lpc_pc_ask_all_bits": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_int64), _pu8]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(_L, _name)
@@ -212,6 +219,17 @@ class Store:
         _check(_L.lpc_store_read(self._h, first, n, out.ctypes.data))
         return out
 
+    def write_bits(self, cells, first=0):
+        """The same cells as one uint64 NBitset<64> per variable (include/lpc_pc.h)."""
+        v = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1)
+        _check(_L.lpc_store_write_bits(self._h, first, v.shape[0], v.ctypes.data))
+
+    def read_bits(self, first=0, n=None):
+        n = self.nvars - first if n is None else n
+        out = np.empty(n, dtype=np.uint64)
+        _check(_L.lpc_store_read_bits(self._h, first, n, out.ctypes.data))
+        return out
+
     def embed(self, var, lb, ub):
         c = ctypes.c_int(0)
         _check(_L.lpc_store_embed(self._h, var, lb, ub, ctypes.byref(c)))
@@ -272,6 +290,22 @@ def fixpoint_host(table, values, **kw):
 PC_LIN_LE, PC_REIF_LIN_LE, PC_EQ, PC_NEQ, PC_CLAUSE, PC_ABS_EQ = 1, 2, 3, 4, 5, 6
 
 
+def nbit_range(lb, ub):
+    """NBitset<64>(lb, ub) as a uint64 cell (scalar or arrays)."""
+    lb, ub = np.asarray(lb, dtype=np.int64), np.asarray(ub, dtype=np.int64)
+    frm = np.where(lb < 0, 0, np.where(lb >= 62, 63, lb + 1)).astype(np.uint64)
+    to = np.where(ub < 0, 0, np.where(ub >= 62, 63, ub + 1)).astype(np.uint64)
+    ones = np.uint64(0xFFFFFFFFFFFFFFFF)
+    cells = (ones << frm) & (ones >> (np.uint64(63) - to))
+    return np.where(lb > ub, np.uint64(0), cells).astype(np.uint64)
+
+
+def nbit_from_intervals(store):
+    """An interval store [n,2] as NBitset<64> cells (exact for domains inside [0, 61])."""
+    s = np.asarray(store).reshape(-1, 2)
+    return nbit_range(s[:, 0], s[:, 1])
+
+
 class PcTable:
     """Flattened PC propagators (include/lpc_pc.h): props [n,5] int32 {kind, first_term, n_terms, rhs, bvar},
     terms [m,2] int32 {coef, var}."""
@@ -289,26 +323,31 @@ class PcTable:
     def num_terms(self):
         return int(_L.lpc_pc_table_terms(self._h))
 
-    def fixpoint(self, store, **kw):
+    def fixpoint(self, store, bitset=False, **kw):
+        """`bitset=True`: the store holds NBitset<64> cells (Store.write_bits), see include/lpc_pc.h."""
         o, r = _opts(**kw), FixpointResult()
-        _check(_L.lpc_pc_fixpoint(self._h, store._h, ctypes.byref(o), ctypes.byref(r)))
+        f = _L.lpc_pc_fixpoint_bits if bitset else _L.lpc_pc_fixpoint
+        _check(f(self._h, store._h, ctypes.byref(o), ctypes.byref(r)))
         return r
 
-    def fixpoint_host(self, values, **kw):
+    def fixpoint_host(self, values, bitset=False, **kw):
         o, r = _opts(**kw), FixpointResult()
         ptr = values if isinstance(values, int) else values.ctypes.data
-        _check(_L.lpc_pc_fixpoint_host(self._h, ptr, ctypes.byref(o), ctypes.byref(r)))
+        f = _L.lpc_pc_fixpoint_bits_host if bitset else _L.lpc_pc_fixpoint_host
+        _check(f(self._h, ptr, ctypes.byref(o), ctypes.byref(r)))
         return r
 
-    def deduce(self, store, i):
+    def deduce(self, store, i, bitset=False):
         c = ctypes.c_int(0)
-        _check(_L.lpc_pc_deduce_one(self._h, store._h, i, ctypes.byref(c)))
+        f = _L.lpc_pc_deduce_one_bits if bitset else _L.lpc_pc_deduce_one
+        _check(f(self._h, store._h, i, ctypes.byref(c)))
         return bool(c.value)
 
-    def ask_all(self, store, want_bits=False):
+    def ask_all(self, store, want_bits=False, bitset=False):
         n = ctypes.c_int64(0)
         bits = np.zeros(max(1, len(self)), dtype=np.uint8) if want_bits else None
-        _check(_L.lpc_pc_ask_all(self._h, store._h, ctypes.byref(n), bits.ctypes.data_as(_pu8) if want_bits else None))
+        f = _L.lpc_pc_ask_all_bits if bitset else _L.lpc_pc_ask_all
+        _check(f(self._h, store._h, ctypes.byref(n), bits.ctypes.data_as(_pu8) if want_bits else None))
         return (int(n.value), bits[:len(self)]) if want_bits else int(n.value)
 
     def close(self):

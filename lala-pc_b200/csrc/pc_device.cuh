@@ -218,4 +218,115 @@ LPC_HD bool pc_ask(const Acc& a, const int4 h, const int2* terms) {
   }
 }
 
+// ---- the same propagators over a VStore<NBitset<64>> (tests/pc_bitset_test.cpp:23-25) ----------------------------
+// One uint64 per variable: bit 0 = "some value <= -1", bit i (1..62) = value i - 1, bit 63 = "some value >= 62"; meet =
+// AND, join = OR, bot = 0, complement = NOT (lala-core nbitset.hpp, un-vendored; pinned by pc_bitset_test.cpp). Only the
+// four shapes those tests pin have a bitset rule (EQ, NEQ, CLAUSE, ABS_EQ); the table builder refuses the linear kinds
+// on a bitset store because NBitset's arithmetic is unpinned. `BAcc`: `load(v)` -> bits, `embed(v, bits)` -> bit0 =
+// changed, bit1 = became empty.
+typedef unsigned long long u64;
+LPC_HD int nb_ctz(u64 b) {
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long)b) - 1;
+#else
+  return __builtin_ctzll(b);
+#endif
+}
+LPC_HD int nb_clz(u64 b) {
+#ifdef __CUDA_ARCH__
+  return __clzll((long long)b);
+#else
+  return __builtin_clzll(b);
+#endif
+}
+// NBitset(lb, ub)
+LPC_HD u64 nb_range(int l, int u) {
+  if(l > u) return 0;
+  const int from = l < 0 ? 0 : (l >= 62 ? 63 : l + 1), to = u < 0 ? 0 : (u >= 62 ? 63 : u + 1);
+  return (~0ull << from) & (~0ull >> (63 - to));
+}
+// [lb(), ub()] of a non-empty set; the empty set gives the empty interval
+LPC_HD Itv nb_itv(u64 b) {
+  if(b == 0) return itv_bot();
+  return Itv((b & 1) ? LPC_MINF : nb_ctz(b) - 1, (b >> 63) ? LPC_INF : 62 - nb_clz(b));
+}
+LPC_HD bool nb_singleton(u64 b) { return b != 0 && (b & (b - 1)) == 0 && !(b & 1) && !(b >> 63); }   // lb() == ub()
+LPC_HD u64 nb_abs(u64 b) {   // project(ABS) through the interval (terms.hpp:107-110)
+  if(b == 0) return 0;
+  const Itv x = nb_itv(b);
+  if(x.lb >= 0) return nb_range(x.lb, x.ub);
+  if(x.ub <= 0) return nb_range(b_neg(x.ub), b_neg(x.lb));
+  return nb_range(0, max(b_neg(x.lb), x.ub));
+}
+LPC_HD u64 nb_neg(u64 b) {   // project_fun(NEG)
+  if(b == 0) return 0;
+  const Itv x = nb_itv(b);
+  return nb_range(b_neg(x.ub), b_neg(x.lb));
+}
+LPC_HD bool nb_lit_ask(bool neg, u64 b) { return neg ? (b & ~2ull) == 0 : !((b >> 1) & 1); }   // formula.hpp:100-110
+
+template <class BAcc>
+LPC_HD int pc_deduce_bits(BAcc& a, const int4 h, const int2* terms) {
+  const int kind = h.x & 0xff, n = h.x >> 8, rhs = h.z;
+  switch(kind) {
+    case PC_EQ: {   // Equality<false>::deduce (formula.hpp:672-681)
+      const int x = terms[0].y, y = terms[1].y;
+      int f = a.embed(y, a.load(x));
+      f |= a.embed(x, a.load(y));
+      return f;
+    }
+    case PC_NEQ: {   // Equality<true>::deduce, complemented universe (formula.hpp:640-644, 656-660)
+      const int x = terms[0].y;
+      if(n == 2) {
+        const int y = terms[1].y;
+        const u64 l = a.load(x);
+        if(nb_singleton(l)) return a.embed(y, ~l);
+        const u64 r = a.load(y);
+        if(nb_singleton(r)) return a.embed(x, ~r);
+        return 0;
+      }
+      const u64 r = nb_range(rhs, rhs);            // Constant::project into the universe
+      if(nb_singleton(r)) return a.embed(x, ~r);
+      return 0;
+    }
+    case PC_CLAUSE: {   // nested Disjunction::deduce = unit propagation (formula.hpp:346-350)
+      int first = -1;
+      bool rest_refuted = true;
+      for(int i = 0; i < n; ++i) {
+        const int2 t = terms[i];
+        const bool refuted = nb_lit_ask(t.x > 0, a.load(t.y));
+        if(first < 0) { if(!refuted) first = i; }
+        else rest_refuted &= refuted;
+      }
+      if(first < 0) first = n - 1;
+      else if(!rest_refuted) return 0;
+      return a.embed(terms[first].y, terms[first].x < 0 ? 2ull : 4ull);   // eq_zero = {0}, eq_one = {1}
+    }
+    case PC_ABS_EQ: {   // Equality(Abs(x), y) (terms.hpp:104-119)
+      const int x = terms[0].y, y = terms[1].y;
+      int f = a.embed(y, nb_abs(a.load(x)));
+      const u64 r = a.load(y);
+      f |= a.embed(x, r | nb_neg(r));
+      return f;
+    }
+    default: return 0;
+  }
+}
+
+template <class BAcc>
+LPC_HD bool pc_ask_bits(const BAcc& a, const int4 h, const int2* terms) {
+  const int kind = h.x & 0xff, n = h.x >> 8, rhs = h.z;
+  switch(kind) {
+    case PC_EQ: { const u64 l = a.load(terms[0].y), r = a.load(terms[1].y); return l == r && nb_singleton(l); }   // formula.hpp:629
+    case PC_NEQ: { const u64 l = a.load(terms[0].y), r = n == 2 ? a.load(terms[1].y) : nb_range(rhs, rhs); return (l & r) == 0; }
+    case PC_CLAUSE: {
+      bool any = false;
+      for(int i = 0; i < n; ++i) any |= nb_lit_ask(terms[i].x < 0, a.load(terms[i].y));
+      return any;
+    }
+    case PC_ABS_EQ: { const u64 ax = nb_abs(a.load(terms[0].y)), r = a.load(terms[1].y); return ax == r && nb_singleton(ax); }
+    default: return true;
+  }
+}
+
 } // namespace lpc

@@ -195,8 +195,51 @@ def _pc_lib():
         L.lpco_pc_fixpoint.restype = None
         L.lpco_pc_ask_all.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint8)]
         L.lpco_pc_ask_all.restype = ctypes.c_int64
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+        L.lpco_pc_deduce_bits.argtypes = [ctypes.c_void_p, ctypes.c_int32, u64p, ctypes.c_int32, i32p]
+        L.lpco_pc_deduce_bits.restype = ctypes.c_int
+        L.lpco_pc_ask_bits.argtypes = [ctypes.c_void_p, ctypes.c_int32, u64p, ctypes.c_int32]
+        L.lpco_pc_ask_bits.restype = ctypes.c_int
+        L.lpco_pc_fixpoint_bits.argtypes = [ctypes.c_void_p, u64p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                            ctypes.POINTER(Stats)]
+        L.lpco_pc_fixpoint_bits.restype = None
+        L.lpco_pc_ask_all_bits.argtypes = [ctypes.c_void_p, u64p, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint8)]
+        L.lpco_pc_ask_all_bits.restype = ctypes.c_int64
+        L.lpco_nbit.argtypes = [ctypes.c_int32, ctypes.c_int32]
+        L.lpco_nbit.restype = ctypes.c_uint64
+        L.lpco_nbit_bounds.argtypes = [ctypes.c_uint64, i32p]
+        L.lpco_nbit_bounds.restype = None
         _pc_bound = True
     return L
+
+
+def _p64(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+
+def nbit(lb, ub):
+    """NBitset<64>(lb, ub) (pc_bitset_test.cpp: NBit(1, 9))."""
+    return int(_pc_lib().lpco_nbit(int(lb), int(ub)))
+
+
+def nbit_from_set(values):
+    """NBitset<64>::from_set (pc_bitset_test.cpp:81)."""
+    b = 0
+    for v in values:
+        b |= nbit(v, v)
+    return b
+
+
+def nbit_bounds(bits):
+    out = np.zeros(2, dtype=np.int32)
+    _pc_lib().lpco_nbit_bounds(int(bits), _p32(out))
+    return int(out[0]), int(out[1])
+
+
+def nbit_store(store):
+    """Interval store [n,2] -> uint64 cells."""
+    s = _store(store)
+    return np.array([nbit(l, u) for l, u in s.tolist()], dtype=np.uint64)
 
 
 def flatten(tree):
@@ -260,6 +303,25 @@ class PCModel:
         s = _store(store)
         bits = np.zeros(max(1, len(self)), dtype=np.uint8)
         n = _pc_lib().lpco_pc_ask_all(self._h, _p32(s), s.shape[0], bits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return (int(n), bits[:len(self)]) if want_bits else int(n)
+
+    # the same model over a VStore<NBitset<64>>: cells = uint64 [nvars]
+    def deduce_bits(self, i, cells, is_bot=False):
+        s = np.ascontiguousarray(cells, dtype=np.uint64).copy()
+        b = ctypes.c_int32(int(is_bot))
+        c = _pc_lib().lpco_pc_deduce_bits(self._h, i, _p64(s), s.shape[0], ctypes.byref(b))
+        return s, bool(c), bool(b.value)
+
+    def fixpoint_bits(self, cells, stop_on_bot=True, max_sweeps=0):
+        s = np.ascontiguousarray(cells, dtype=np.uint64).copy()
+        st = Stats()
+        _pc_lib().lpco_pc_fixpoint_bits(self._h, _p64(s), s.shape[0], int(stop_on_bot), max_sweeps, ctypes.byref(st))
+        return s, st
+
+    def ask_all_bits(self, cells, want_bits=False):
+        s = np.ascontiguousarray(cells, dtype=np.uint64)
+        bits = np.zeros(max(1, len(self)), dtype=np.uint8)
+        n = _pc_lib().lpco_pc_ask_all_bits(self._h, _p64(s), s.shape[0], bits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
         return (int(n), bits[:len(self)]) if want_bits else int(n)
 
     def __del__(self):

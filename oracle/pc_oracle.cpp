@@ -22,6 +22,15 @@
 // domains on a single variable). PARITY UNPINNED for: lower-bound rounding of `u ediv c` (reified sums with b = 0),
 // negative coefficients, infinite bounds inside sums (tests/test_oracle_pc.py lists the pinned goldens).
 //
+// The walker is a template over the universe: Interval<ZLB> (Itv, tests/pc_test.cpp) and NBitset<64> (NBit,
+// tests/pc_bitset_test.cpp:23-25). NBitset lives in lala-core too; restated: bit 0 = "some value <= -1", bit i (1..62) =
+// value i-1, bit 63 = "some value >= 62" (pinned by `var -15..5` == NBit(-1,5), pc_bitset_test.cpp:152-156), meet = AND,
+// join = OR, complement = NOT (`complemented`, formula.hpp:642-644), lb()/ub() = lowest / highest member with the end
+// bits read as -inf / +inf, arithmetic (NEG, ABS, ADD, ...) through the interval [lb(), ub()] and back.
+// Parity status of NBit: PINNED by the 10 goldens of pc_bitset_test.cpp (!=, =, clauses, int_abs);
+// PARITY UNPINNED for NBitset arithmetic beyond IntAbs1 (the device path therefore only accepts the four pinned shapes
+// on bitset stores, see include/lpc_pc.h).
+//
 // Formulas come in as a prefix-encoded int32 stream (see enum Tok); the same stream is what the tests flatten into
 // the device encoding of include/lpc_pc.h.
 
@@ -38,12 +47,17 @@ const v_t INF = INT32_MAX, MINF = INT32_MIN;
 
 struct Itv {
   v_t lb, ub;
+  static constexpr bool complemented = false;
   Itv() : lb(MINF), ub(INF) {}
   Itv(v_t l, v_t u) : lb(l), ub(u) {}
   bool is_bot() const { return lb > ub; }
+  v_t lo() const { return lb; }
+  v_t hi() const { return ub; }
   bool meet(const Itv& o) { bool c = false; if(o.lb > lb) { lb = o.lb; c = true; } if(o.ub < ub) { ub = o.ub; c = true; } return c; }
   bool contains0() const { return lb <= 0 && 0 <= ub; }          // `*this >= eq_zero` in the lattice order
   bool sub_of(v_t l, v_t u) const { return is_bot() || (lb >= l && ub <= u); }   // `*this <= [l,u]`
+  bool same(const Itv& o) const { return (is_bot() && o.is_bot()) || (lb == o.lb && ub == o.ub); }
+  Itv complement() const { return Itv(); }                        // never called (complemented == false)
 };
 inline Itv fjoin(const Itv& a, const Itv& b) {
   if(a.is_bot()) return b;
@@ -94,72 +108,105 @@ inline Itv p_ediv(const Itv& a, const Itv& b) {
   return hull4(bediv(a.lb, b.lb), bediv(a.lb, b.ub), bediv(a.ub, b.lb), bediv(a.ub, b.ub));
 }
 
+// NBitset<64, local_memory, unsigned long long> (lala-core, un-vendored; see the header).
+struct NBit {
+  uint64_t bits;
+  static constexpr bool complemented = true;
+  NBit() : bits(~0ull) {}
+  NBit(v_t l, v_t u) : bits(0) {
+    if(l > u) return;
+    const int from = l < 0 ? 0 : (l >= 62 ? 63 : l + 1), to = u < 0 ? 0 : (u >= 62 ? 63 : u + 1);
+    bits = (~0ull << from) & (~0ull >> (63 - to));
+  }
+  static NBit raw(uint64_t b) { NBit r; r.bits = b; return r; }
+  bool is_bot() const { return bits == 0; }
+  v_t lo() const { return (bits & 1) ? MINF : (bits ? (v_t)__builtin_ctzll(bits) - 1 : INF); }
+  v_t hi() const { return (bits >> 63) ? INF : (bits ? 62 - (v_t)__builtin_clzll(bits) : MINF); }
+  bool meet(const NBit& o) { const uint64_t n = bits & o.bits; const bool c = n != bits; bits = n; return c; }
+  bool contains0() const { return (bits >> 1) & 1; }              // superset of eq_zero = {0}
+  bool sub_of(v_t l, v_t u) const { return (bits & ~NBit(l, u).bits) == 0; }
+  bool same(const NBit& o) const { return bits == o.bits; }
+  NBit complement() const { return raw(~bits); }
+  Itv itv() const { return Itv(lo(), hi()); }
+};
+inline NBit from_itv(const Itv& i) { return NBit(i.lb, i.ub); }
+inline NBit fjoin(const NBit& a, const NBit& b) { return NBit::raw(a.bits | b.bits); }
+inline NBit p_add(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_add(a.itv(), b.itv())); }
+inline NBit p_sub(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_sub(a.itv(), b.itv())); }
+inline NBit p_neg(const NBit& a) { return a.is_bot() ? a : from_itv(p_neg(a.itv())); }
+inline NBit additive_inverse(const NBit& a) { return p_neg(a); }   // unpinned; a set has no crossed form
+inline NBit p_abs(const NBit& a) { return a.is_bot() ? a : from_itv(p_abs(a.itv())); }
+inline NBit p_mul(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_mul(a.itv(), b.itv())); }
+inline NBit p_ediv(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_ediv(a.itv(), b.itv())); }
+
+template <class U>
 struct Store {
-  v_t* d; int n; bool bot;
-  Itv get(int v) const { return Itv(d[2 * v], d[2 * v + 1]); }
-  void project(int v, Itv& r) const { r.meet(get(v)); }
-  bool embed(int v, const Itv& u) {
-    Itv c = get(v);
-    if(c.meet(u)) { d[2 * v] = c.lb; d[2 * v + 1] = c.ub; if(c.is_bot()) bot = true; return true; }
+  U* d; int n; bool bot;     // 8-byte cells: {int32 lb, int32 ub} or one uint64 bitset
+  const U& get(int v) const { return d[v]; }
+  void project(int v, U& r) const { r.meet(d[v]); }
+  bool embed(int v, const U& u) {                                    // VStore::embed
+    if(d[v].meet(u)) { if(d[v].is_bot()) bot = true; return true; }
     return false;
   }
 };
+static_assert(sizeof(Itv) == 8 && sizeof(NBit) == 8, "8-byte cells");
 
 enum Tok { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8,
            F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27, F_EQUIV = 28 };
 
+template <class U>
 struct Term {
   int kind = 0; v_t k = 0; int var = -1;
   std::vector<std::unique_ptr<Term>> sub;
   bool is_const() const { return kind == T_CONST; }
 
-  void project(const Store& a, Itv& r) const {
+  void project(const Store<U>& a, U& r) const {
     switch(kind) {
-      case T_CONST: r.meet(Itv(k, k)); break;                        // terms.hpp:34
+      case T_CONST: r.meet(U(k, k)); break;                          // terms.hpp:34
       case T_VAR: a.project(var, r); break;                          // terms.hpp:69-71
-      case T_NEG: { Itv t; sub[0]->project(a, t); r.meet(p_neg(t)); break; }   // terms.hpp:148-152, 91-93
-      case T_ABS: { Itv t; sub[0]->project(a, t); r.meet(p_abs(t)); break; }
+      case T_NEG: { U t; sub[0]->project(a, t); r.meet(p_neg(t)); break; }   // terms.hpp:148-152, 91-93
+      case T_ABS: { U t; sub[0]->project(a, t); r.meet(p_abs(t)); break; }
       case T_ADD: case T_SUB: case T_MUL: {                          // terms.hpp:399-405
-        Itv x, y; sub[0]->project(a, x); sub[1]->project(a, y);
+        U x, y; sub[0]->project(a, x); sub[1]->project(a, y);
         r.meet(kind == T_ADD ? p_add(x, y) : kind == T_SUB ? p_sub(x, y) : p_mul(x, y));
         break;
       }
       case T_NARY_ADD: {                                             // terms.hpp:465-478
-        Itv accu; sub[0]->project(a, accu);
-        for(size_t i = 1; i < sub.size(); ++i) { Itv t; sub[i]->project(a, t); accu = p_add(accu, t); }
+        U accu; sub[0]->project(a, accu);
+        for(size_t i = 1; i < sub.size(); ++i) { U t; sub[i]->project(a, t); accu = p_add(accu, t); }
         r.meet(accu);
         break;
       }
     }
   }
 
-  bool embed(Store& a, const Itv& u) const {
+  bool embed(Store<U>& a, const U& u) const {
     switch(kind) {
       case T_CONST: return false;                                    // terms.hpp:33
       case T_VAR: return a.embed(var, u);                            // terms.hpp:65-67
-      case T_NEG: { Itv t; t.meet(p_neg(u)); return sub[0]->embed(a, t); }     // terms.hpp:142-146, 95-97
-      case T_ABS: { Itv t; t.meet(fjoin(u, p_neg(u))); return sub[0]->embed(a, t); }   // terms.hpp:112-114
+      case T_NEG: { U t; t.meet(p_neg(u)); return sub[0]->embed(a, t); }     // terms.hpp:142-146, 95-97
+      case T_ABS: { U t; t.meet(fjoin(u, p_neg(u))); return sub[0]->embed(a, t); }   // terms.hpp:112-114
       case T_ADD: case T_SUB: case T_MUL: {                          // terms.hpp:376-397
         bool ch = false;
         if(!sub[0]->is_const()) {
-          Itv yt, res; sub[1]->project(a, yt);
+          U yt, res; sub[1]->project(a, yt);
           left_residual(u, yt, res);
           ch |= sub[0]->embed(a, res);
         }
         if(!sub[1]->is_const()) {
-          Itv xt, res; sub[0]->project(a, xt);
+          U xt, res; sub[0]->project(a, xt);
           right_residual(u, xt, res);
           ch |= sub[1]->embed(a, res);
         }
         return ch;
       }
       case T_NARY_ADD: {                                             // terms.hpp:480-499
-        Itv all; project(a, all);
+        U all; project(a, all);
         bool ch = false;
         for(size_t i = 0; i < sub.size(); ++i) {
-          Itv tmp; sub[i]->project(a, tmp);
-          Itv tmp2; tmp2.meet(p_add(all, additive_inverse(tmp)));    // GroupAdd::rev_op, terms.hpp:190-194
-          Itv res; res.meet(p_sub(u, tmp2));                         // GroupAdd::left_residual, :196-198
+          U tmp; sub[i]->project(a, tmp);
+          U tmp2; tmp2.meet(p_add(all, additive_inverse(tmp)));      // GroupAdd::rev_op, terms.hpp:190-194
+          U res; res.meet(p_sub(u, tmp2));                           // GroupAdd::left_residual, :196-198
           ch |= sub[i]->embed(a, res);
         }
         return ch;
@@ -168,45 +215,46 @@ struct Term {
     return false;
   }
 
-  void left_residual(const Itv& u, const Itv& b, Itv& r) const {
+  void left_residual(const U& u, const U& b, U& r) const {
     if(kind == T_ADD) r.meet(p_sub(u, b));                           // terms.hpp:196-198
     else if(kind == T_SUB) r.meet(p_add(u, b));                      // terms.hpp:218-220
     else if(!(u.contains0() && b.contains0())) r.meet(p_ediv(u, b)); // GroupMul, terms.hpp:249-253
   }
-  void right_residual(const Itv& u, const Itv& b, Itv& r) const {
+  void right_residual(const U& u, const U& b, U& r) const {
     if(kind == T_SUB) r.meet(p_sub(b, u));                           // terms.hpp:222-224
     else left_residual(u, b, r);
   }
 };
 
+template <class U>
 struct Formula {
   int kind = 0; int var = -1;
-  std::unique_ptr<Term> l, r;
+  std::unique_ptr<Term<U>> l, r;
   std::unique_ptr<Formula> f, g;
 
-  bool ask(const Store& a) const { return ask_impl(a, false); }
-  bool nask(const Store& a) const { return ask_impl(a, true); }
-  bool deduce(Store& a) const { return deduce_impl(a, false); }
-  bool contradeduce(Store& a) const { return deduce_impl(a, true); }
+  bool ask(const Store<U>& a) const { return ask_impl(a, false); }
+  bool nask(const Store<U>& a) const { return ask_impl(a, true); }
+  bool deduce(Store<U>& a) const { return deduce_impl(a, false); }
+  bool contradeduce(Store<U>& a) const { return deduce_impl(a, true); }
 
   // `negated` selects the dual operation (nask / contradeduce); literal and comparison kinds fold it into `neg`.
-  bool ask_impl(const Store& a, bool negated) const {
+  bool ask_impl(const Store<U>& a, bool negated) const {
     switch(kind) {
       case F_VARLIT: case F_NVARLIT: {                               // formula.hpp:97-110, 126-135
         bool neg = (kind == F_NVARLIT) != negated;
-        Itv t; a.project(var, t);
+        U t; a.project(var, t);
         return neg ? t.sub_of(0, 0) : !t.contains0();
       }
       case F_LEQ: case F_GT: {                                       // formula.hpp:757-771
         bool neg = (kind == F_GT) != negated;
-        Itv x, y; l->project(a, x); r->project(a, y);
-        return neg ? x.lb > y.ub : x.ub <= y.lb;
+        U x, y; l->project(a, x); r->project(a, y);
+        return neg ? x.lo() > y.hi() : x.hi() <= y.lo();
       }
       case F_EQ: case F_NEQ: {                                       // formula.hpp:616-631
         bool neg = (kind == F_NEQ) != negated;
-        Itv x, y; l->project(a, x); r->project(a, y);
-        if(neg) { Itv m = x; m.meet(y); return m.is_bot(); }
-        return ((x.is_bot() && y.is_bot()) || (x.lb == y.lb && x.ub == y.ub)) && x.lb == x.ub;
+        U x, y; l->project(a, x); r->project(a, y);
+        if(neg) { U m = x; m.meet(y); return m.is_bot(); }
+        return x.same(y) && x.lo() == x.hi();
       }
       case F_AND: return negated ? (f->nask(a) || g->nask(a)) : (f->ask(a) && g->ask(a));       // formula.hpp:268-274
       case F_OR: return negated ? (f->nask(a) && g->nask(a)) : (f->ask(a) || g->ask(a));        // formula.hpp:338-344
@@ -217,49 +265,47 @@ struct Formula {
     return false;
   }
 
-  bool deduce_impl(Store& a, bool negated) const {
+  // Equality<true>::deduce for one direction: `other` loses the singleton `single` (formula.hpp:640-653, 656-669)
+  static bool shave(Store<U>& a, const Term<U>& other, const U& single) {
+    if(U::complemented) return other.embed(a, single.complement());
+    U o; other.project(a, o);
+    U lo = o, hi = o;
+    lo.meet(U(badd(single.lo(), 1), INF));
+    hi.meet(U(MINF, bsub(single.hi(), 1)));
+    return other.embed(a, fjoin(lo, hi));
+  }
+
+  bool deduce_impl(Store<U>& a, bool negated) const {
     switch(kind) {
       case F_VARLIT: case F_NVARLIT: {                               // formula.hpp:112-120, 140-149
         bool neg = (kind == F_NVARLIT) != negated;
-        return a.embed(var, neg ? Itv(0, 0) : Itv(1, 1));
+        return a.embed(var, neg ? U(0, 0) : U(1, 1));
       }
       case F_LEQ: case F_GT: {                                       // formula.hpp:773-807
         bool neg = (kind == F_GT) != negated;
         bool ch = false;
-        Itv x, y;
+        U x, y;
         if(neg) {   // l > r
-          if(!l->is_const()) { r->project(a, y); y.meet(Itv(badd(y.lb, 1), INF)); ch = l->embed(a, Itv(y.lb, INF)); }
-          if(!r->is_const()) { l->project(a, x); x.meet(Itv(MINF, bsub(x.ub, 1))); ch |= r->embed(a, Itv(MINF, x.ub)); }
+          if(!l->is_const()) { r->project(a, y); y.meet(U(badd(y.lo(), 1), INF)); ch = l->embed(a, U(y.lo(), INF)); }
+          if(!r->is_const()) { l->project(a, x); x.meet(U(MINF, bsub(x.hi(), 1))); ch |= r->embed(a, U(MINF, x.hi())); }
         }
         else {      // l <= r
-          if(!l->is_const()) { r->project(a, y); ch |= l->embed(a, Itv(MINF, y.ub)); }
-          if(!r->is_const()) { l->project(a, x); ch = r->embed(a, Itv(x.lb, INF)); }   // `=` as in formula.hpp:803
+          if(!l->is_const()) { r->project(a, y); ch |= l->embed(a, U(MINF, y.hi())); }
+          if(!r->is_const()) { l->project(a, x); ch = r->embed(a, U(x.lo(), INF)); }   // `=` as in formula.hpp:803
         }
         return ch;
       }
       case F_EQ: case F_NEQ: {                                       // formula.hpp:633-683
         bool neg = (kind == F_NEQ) != negated;
-        Itv x, y;
+        U x, y;
         if(neg) {
           if(!r->is_const()) {
             l->project(a, x);
-            if(x.lb == x.ub) {
-              r->project(a, y);
-              Itv lo = y, hi = y;
-              lo.meet(Itv(badd(x.lb, 1), INF));
-              hi.meet(Itv(MINF, bsub(x.ub, 1)));
-              return r->embed(a, fjoin(lo, hi));
-            }
+            if(x.lo() == x.hi()) return shave(a, *r, x);
           }
           if(!l->is_const()) {
             r->project(a, y);
-            if(y.lb == y.ub) {
-              Itv x2; l->project(a, x2);
-              Itv lo = x2, hi = x2;
-              lo.meet(Itv(badd(y.lb, 1), INF));
-              hi.meet(Itv(MINF, bsub(y.ub, 1)));
-              return l->embed(a, fjoin(lo, hi));
-            }
+            if(y.lo() == y.hi()) return shave(a, *l, y);
           }
           return false;
         }
@@ -296,85 +342,53 @@ struct Formula {
   }
 };
 
-std::unique_ptr<Term> parse_term(const int32_t*& p) {
-  std::unique_ptr<Term> t(new Term());
+template <class U>
+std::unique_ptr<Term<U>> parse_term(const int32_t*& p) {
+  std::unique_ptr<Term<U>> t(new Term<U>());
   t->kind = *p++;
   switch(t->kind) {
     case T_CONST: t->k = *p++; break;
     case T_VAR: t->var = *p++; break;
-    case T_NEG: case T_ABS: t->sub.push_back(parse_term(p)); break;
-    case T_ADD: case T_SUB: case T_MUL: t->sub.push_back(parse_term(p)); t->sub.push_back(parse_term(p)); break;
-    case T_NARY_ADD: { int n = *p++; for(int i = 0; i < n; ++i) t->sub.push_back(parse_term(p)); break; }
+    case T_NEG: case T_ABS: t->sub.push_back(parse_term<U>(p)); break;
+    case T_ADD: case T_SUB: case T_MUL: t->sub.push_back(parse_term<U>(p)); t->sub.push_back(parse_term<U>(p)); break;
+    case T_NARY_ADD: { int n = *p++; for(int i = 0; i < n; ++i) t->sub.push_back(parse_term<U>(p)); break; }
   }
   return t;
 }
-std::unique_ptr<Formula> parse_formula(const int32_t*& p) {
-  std::unique_ptr<Formula> f(new Formula());
+template <class U>
+std::unique_ptr<Formula<U>> parse_formula(const int32_t*& p) {
+  std::unique_ptr<Formula<U>> f(new Formula<U>());
   f->kind = *p++;
   switch(f->kind) {
     case F_VARLIT: case F_NVARLIT: f->var = *p++; break;
-    case F_LEQ: case F_GT: case F_EQ: case F_NEQ: f->l = parse_term(p); f->r = parse_term(p); break;
-    default: f->f = parse_formula(p); f->g = parse_formula(p); break;
+    case F_LEQ: case F_GT: case F_EQ: case F_NEQ: f->l = parse_term<U>(p); f->r = parse_term<U>(p); break;
+    default: f->f = parse_formula<U>(p); f->g = parse_formula<U>(p); break;
   }
   return f;
 }
 
-struct Model { std::vector<std::unique_ptr<Formula>> props; };
+// One model keeps both instantiations of its propagators; `bits` selects the universe of the store it is run on.
+struct Model {
+  std::vector<std::unique_ptr<Formula<Itv>>> props;
+  std::vector<std::unique_ptr<Formula<NBit>>> bprops;
+};
 
-bool scan_bot(const v_t* d, int n) { for(int i = 0; i < n; ++i) if(d[2 * i] > d[2 * i + 1]) return true; return false; }
+template <class U> bool scan_bot(const U* d, int n) { for(int i = 0; i < n; ++i) if(d[i].is_bot()) return true; return false; }
 
-} // namespace
+struct lpco_stats_ { int32_t has_changed, is_bot; int64_t sweeps, deductions; double seconds; };
 
-extern "C" {
-
-struct lpco_stats { int32_t has_changed, is_bot; int64_t sweeps, deductions; double seconds; };
-
-// stream: n_props formulas, prefix encoded back to back. Returns an opaque model.
-void* lpco_pc_parse(const int32_t* stream, int32_t n_props) {
-  Model* m = new Model();
-  const int32_t* p = stream;
-  for(int i = 0; i < n_props; ++i) m->props.push_back(parse_formula(p));
-  return m;
-}
-void lpco_pc_free(void* m) { delete static_cast<Model*>(m); }
-
-// PC::deduce(i) (pc.hpp:671-680) on an interleaved {lb,ub} store.
-int lpco_pc_deduce(void* m, int32_t i, int32_t* lbub, int32_t nvars, int32_t* is_bot) {
-  Store s{lbub, nvars, is_bot && *is_bot};
-  bool c = static_cast<Model*>(m)->props[i]->deduce(s);
-  if(is_bot) *is_bot = s.bot;
-  return c;
-}
-int lpco_pc_ask(void* m, int32_t i, const int32_t* lbub, int32_t nvars) {
-  Store s{const_cast<int32_t*>(lbub), nvars, false};
-  return static_cast<Model*>(m)->props[i]->ask(s);
-}
-// Term-level entry points for TermTest.* (pc_test.cpp:31-67): project / embed of ONE term stream.
-void lpco_pc_term_project(const int32_t* stream, const int32_t* lbub, int32_t nvars, int32_t* out2) {
-  const int32_t* p = stream;
-  auto t = parse_term(p);
-  Store s{const_cast<int32_t*>(lbub), nvars, false};
-  Itv r; t->project(s, r);
-  out2[0] = r.lb; out2[1] = r.ub;
-}
-int lpco_pc_term_embed(const int32_t* stream, int32_t* lbub, int32_t nvars, int32_t lb, int32_t ub) {
-  const int32_t* p = stream;
-  auto t = parse_term(p);
-  Store s{lbub, nvars, false};
-  return t->embed(s, Itv(lb, ub));
-}
-
-// GaussSeidelIteration::fixpoint over PC::deduce(i) (tests/pc_test.cpp:91-94); stop_on_bot as in pir_oracle.cpp.
-void lpco_pc_fixpoint(void* mp, int32_t* lbub, int32_t nvars, int32_t stop_on_bot, int64_t max_sweeps, lpco_stats* out) {
-  Model* m = static_cast<Model*>(mp);
-  Store s{lbub, nvars, scan_bot(lbub, nvars)};
+// GaussSeidelIteration::fixpoint over PC::deduce(i) (tests/pc_test.cpp:91-94, pc_bitset_test.cpp:52-55).
+template <class U>
+void fixpoint(const std::vector<std::unique_ptr<Formula<U>>>& props, U* cells, int nvars, int stop_on_bot,
+              int64_t max_sweeps, lpco_stats_* out) {
+  Store<U> s{cells, nvars, scan_bot(cells, nvars)};
   auto t0 = std::chrono::steady_clock::now();
   bool changed = true, any = false;
   int64_t sweeps = 0;
-  const size_t n = m->props.size();
+  const size_t n = props.size();
   while(changed && !(stop_on_bot && s.bot) && (max_sweeps <= 0 || sweeps < max_sweeps)) {
     changed = false;
-    for(size_t i = 0; i < n; ++i) changed |= m->props[i]->deduce(s);
+    for(size_t i = 0; i < n; ++i) changed |= props[i]->deduce(s);
     any |= changed;
     ++sweeps;
   }
@@ -383,12 +397,85 @@ void lpco_pc_fixpoint(void* mp, int32_t* lbub, int32_t nvars, int32_t stop_on_bo
             out->seconds = std::chrono::duration<double>(t1 - t0).count(); }
 }
 
-int64_t lpco_pc_ask_all(void* mp, const int32_t* lbub, int32_t nvars, uint8_t* bits) {
-  Model* m = static_cast<Model*>(mp);
-  Store s{const_cast<int32_t*>(lbub), nvars, false};
+template <class U>
+int64_t ask_all(const std::vector<std::unique_ptr<Formula<U>>>& props, const U* cells, int nvars, uint8_t* bits) {
+  Store<U> s{const_cast<U*>(cells), nvars, false};
   int64_t c = 0;
-  for(size_t i = 0; i < m->props.size(); ++i) { bool e = m->props[i]->ask(s); if(bits) bits[i] = e; c += e; }
+  for(size_t i = 0; i < props.size(); ++i) { bool e = props[i]->ask(s); if(bits) bits[i] = e; c += e; }
   return c;
 }
+
+} // namespace
+
+extern "C" {
+
+typedef lpco_stats_ lpco_stats;
+
+// stream: n_props formulas, prefix encoded back to back. Returns an opaque model.
+void* lpco_pc_parse(const int32_t* stream, int32_t n_props) {
+  Model* m = new Model();
+  const int32_t* p = stream;
+  for(int i = 0; i < n_props; ++i) m->props.push_back(parse_formula<Itv>(p));
+  p = stream;
+  for(int i = 0; i < n_props; ++i) m->bprops.push_back(parse_formula<NBit>(p));
+  return m;
+}
+void lpco_pc_free(void* m) { delete static_cast<Model*>(m); }
+
+// PC::deduce(i) (pc.hpp:671-680) on an interleaved {lb,ub} store.
+int lpco_pc_deduce(void* m, int32_t i, int32_t* lbub, int32_t nvars, int32_t* is_bot) {
+  Store<Itv> s{reinterpret_cast<Itv*>(lbub), nvars, is_bot && *is_bot};
+  bool c = static_cast<Model*>(m)->props[i]->deduce(s);
+  if(is_bot) *is_bot = s.bot;
+  return c;
+}
+int lpco_pc_ask(void* m, int32_t i, const int32_t* lbub, int32_t nvars) {
+  Store<Itv> s{reinterpret_cast<Itv*>(const_cast<int32_t*>(lbub)), nvars, false};
+  return static_cast<Model*>(m)->props[i]->ask(s);
+}
+// The same two on a VStore<NBitset<64>> (one uint64 per variable).
+int lpco_pc_deduce_bits(void* m, int32_t i, uint64_t* cells, int32_t nvars, int32_t* is_bot) {
+  Store<NBit> s{reinterpret_cast<NBit*>(cells), nvars, is_bot && *is_bot};
+  bool c = static_cast<Model*>(m)->bprops[i]->deduce(s);
+  if(is_bot) *is_bot = s.bot;
+  return c;
+}
+int lpco_pc_ask_bits(void* m, int32_t i, const uint64_t* cells, int32_t nvars) {
+  Store<NBit> s{reinterpret_cast<NBit*>(const_cast<uint64_t*>(cells)), nvars, false};
+  return static_cast<Model*>(m)->bprops[i]->ask(s);
+}
+// Term-level entry points for TermTest.* (pc_test.cpp:31-67): project / embed of ONE term stream.
+void lpco_pc_term_project(const int32_t* stream, const int32_t* lbub, int32_t nvars, int32_t* out2) {
+  const int32_t* p = stream;
+  auto t = parse_term<Itv>(p);
+  Store<Itv> s{reinterpret_cast<Itv*>(const_cast<int32_t*>(lbub)), nvars, false};
+  Itv r; t->project(s, r);
+  out2[0] = r.lb; out2[1] = r.ub;
+}
+int lpco_pc_term_embed(const int32_t* stream, int32_t* lbub, int32_t nvars, int32_t lb, int32_t ub) {
+  const int32_t* p = stream;
+  auto t = parse_term<Itv>(p);
+  Store<Itv> s{reinterpret_cast<Itv*>(lbub), nvars, false};
+  return t->embed(s, Itv(lb, ub));
+}
+
+// GaussSeidelIteration::fixpoint over PC::deduce(i); stop_on_bot as in pir_oracle.cpp.
+void lpco_pc_fixpoint(void* mp, int32_t* lbub, int32_t nvars, int32_t stop_on_bot, int64_t max_sweeps, lpco_stats* out) {
+  fixpoint(static_cast<Model*>(mp)->props, reinterpret_cast<Itv*>(lbub), nvars, stop_on_bot, max_sweeps, out);
+}
+void lpco_pc_fixpoint_bits(void* mp, uint64_t* cells, int32_t nvars, int32_t stop_on_bot, int64_t max_sweeps, lpco_stats* out) {
+  fixpoint(static_cast<Model*>(mp)->bprops, reinterpret_cast<NBit*>(cells), nvars, stop_on_bot, max_sweeps, out);
+}
+
+int64_t lpco_pc_ask_all(void* mp, const int32_t* lbub, int32_t nvars, uint8_t* bits) {
+  return ask_all(static_cast<Model*>(mp)->props, reinterpret_cast<const Itv*>(lbub), nvars, bits);
+}
+int64_t lpco_pc_ask_all_bits(void* mp, const uint64_t* cells, int32_t nvars, uint8_t* bits) {
+  return ask_all(static_cast<Model*>(mp)->bprops, reinterpret_cast<const NBit*>(cells), nvars, bits);
+}
+
+// NBitset(lb, ub) constructor and lb()/ub() for the tests' conversions (pc_bitset_test.cpp: NBit(1,9), from_set).
+uint64_t lpco_nbit(int32_t lb, int32_t ub) { return NBit(lb, ub).bits; }
+void lpco_nbit_bounds(uint64_t bits, int32_t* out2) { NBit b = NBit::raw(bits); out2[0] = b.lo(); out2[1] = b.hi(); }
 
 } // extern "C"

@@ -104,4 +104,45 @@ int devhost_pc_ask(const int* props, long long i, const int* terms, const int* l
   HostAcc acc{const_cast<int*>(lbub), 0};
   return pc_ask(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
 }
+
+// ---- the same over NBitset<64> cells ---------------------------------------------------------------------------------
+struct HostBitAcc {
+  unsigned long long* d;
+  mutable int seen_bot;
+  u64 load(int v) const { if(d[v] == 0) seen_bot = 1; return d[v]; }
+  int embed(int v, u64 u) {
+    const u64 old = d[v];
+    if(old == 0) return 2;
+    const u64 nw = old & u;
+    if(nw == old) return 0;
+    d[v] = nw;
+    return nw == 0 ? 3 : 1;
+  }
+};
+int devhost_pc_fixpoint_bits(const int* props, long long n, const int* terms, unsigned long long* cells, int nvars, int* is_bot,
+                             int* has_changed) {
+  int bot = 0, any = 0;
+  for(int v = 0; v < nvars; ++v) bot |= cells[v] == 0;
+  int sweeps = 0, changed = 1;
+  while(changed && !bot && sweeps < 100000) {
+    changed = 0;
+    for(long long i = 0; i < n; ++i) {
+      const int* p = props + 5 * i;
+      int4 h = make_int4(p[0] | (p[2] << 8), p[1], p[3], p[4]);
+      HostBitAcc acc{cells, 0};
+      int f = pc_deduce_bits(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
+      changed |= f & 1; bot |= ((f >> 1) & 1) | acc.seen_bot;
+    }
+    any |= changed;
+    ++sweeps;
+  }
+  *is_bot = bot; *has_changed = any;
+  return sweeps;
+}
+int devhost_pc_ask_bits(const int* props, long long i, const int* terms, const unsigned long long* cells) {
+  const int* p = props + 5 * i;
+  int4 h = make_int4(p[0] | (p[2] << 8), p[1], p[3], p[4]);
+  HostBitAcc acc{const_cast<unsigned long long*>(cells), 0};
+  return pc_ask_bits(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
+}
 }

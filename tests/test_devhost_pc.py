@@ -86,3 +86,84 @@ def test_random_networks(devhost):
         st = compare(devhost, forms, store, f"random {trial}")
         n_ok += not st.is_bot
     assert n_ok >= 60
+
+
+# ---- the bitset rules (NBitset<64> cells) ---------------------------------------------------------------------------
+def host_fixpoint_bits(D, props, terms, cells):
+    s = np.ascontiguousarray(cells, dtype=np.uint64).copy()
+    p = np.ascontiguousarray(props if len(props) else np.zeros((1, 5)), dtype=np.int32)
+    t = np.ascontiguousarray(terms if len(terms) else np.zeros((1, 2)), dtype=np.int32)
+    bot, ch = ctypes.c_int(0), ctypes.c_int(0)
+    D.devhost_pc_fixpoint_bits(p.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(len(props)), t.ctypes.data_as(ctypes.c_void_p),
+                               s.ctypes.data_as(ctypes.c_void_p), len(s), ctypes.byref(bot), ctypes.byref(ch))
+    return s, bool(bot.value), bool(ch.value)
+
+
+def compare_bits(D, formulas, cells, label):
+    from lala_pc_b200 import pcflat
+    props, terms = pcflat.flatten(formulas)
+    m = O.PCModel(formulas)
+    want, st = m.fixpoint_bits(cells)
+    got, bot, ch = host_fixpoint_bits(D, props, terms, cells)
+    assert bot == bool(st.is_bot), label
+    if not bot:
+        assert np.array_equal(got, want), (label, got.tolist(), want.tolist())
+        assert ch == bool(st.has_changed), label
+        _, bits = m.ask_all_bits(want, want_bits=True)
+        p = np.ascontiguousarray(props, dtype=np.int32)
+        t = np.ascontiguousarray(terms if len(terms) else np.zeros((1, 2)), dtype=np.int32)
+        w = np.ascontiguousarray(want)
+        gb = [D.devhost_pc_ask_bits(p.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(i), t.ctypes.data_as(ctypes.c_void_p),
+                                    w.ctypes.data_as(ctypes.c_void_p)) for i in range(len(p))]
+        assert gb == bits.tolist(), label
+    return got, st
+
+
+def random_bits_pc(rng, nvars):
+    from lala_pc_b200 import pcflat
+    forms = []
+    for _ in range(int(rng.integers(1, 8))):
+        kind = int(rng.integers(3, 7))
+        vs = rng.permutation(nvars)
+        if kind == 4 and rng.random() < 0.4:
+            forms.append(pcflat.to_tree(4, [(1, int(vs[0]))], int(rng.integers(-3, 70)), -1))
+        elif kind == 5:
+            n = int(rng.integers(1, min(5, nvars)))
+            forms.append(pcflat.to_tree(5, [(int(rng.choice([1, -1])), int(v)) for v in vs[:n]], 0, -1))
+        else:
+            forms.append(pcflat.to_tree(kind, [(1, int(vs[0])), (1, int(vs[1]))], 0, -1))
+    return forms
+
+
+def random_cells(rng, nvars):
+    cells = np.zeros(nvars, dtype=np.uint64)
+    for i in range(nvars):
+        r = rng.random()
+        if r < 0.35:
+            cells[i] = O.nbit(0, 1) if rng.random() < 0.7 else O.nbit(int(rng.integers(0, 2)), 1)
+        elif r < 0.7:
+            a, b = sorted(int(x) for x in rng.integers(-3, 66, 2))
+            cells[i] = O.nbit(a, b)
+        else:
+            cells[i] = O.nbit_from_set(int(x) for x in rng.integers(-2, 64, int(rng.integers(1, 5))))
+    return cells
+
+
+def test_bitset_goldens(devhost):
+    for k in load_golden("pc_bitset_kat.json")["props"]:
+        got, st = compare_bits(devhost, [to_tree(p) for p in k["props"]], np.array(k["before_bits"], dtype=np.uint64), k["name"])
+        assert got.tolist() == k["after_bits"], k["name"]
+
+
+def test_bitset_config5_and_random(devhost):
+    from lala_pc_b200 import workloads as W
+    net = W.config5(0.05)
+    _, st = compare_bits(devhost, net.formulas(), O.nbit_store(net.store), "config5 bits")
+    assert not st.is_bot and st.sweeps >= 3
+    rng = np.random.default_rng(11)
+    n_ok = 0
+    for trial in range(400):
+        nvars = int(rng.integers(3, 9))
+        _, st = compare_bits(devhost, random_bits_pc(rng, nvars), random_cells(rng, nvars), f"random bits {trial}")
+        n_ok += not st.is_bot
+    assert n_ok >= 100

@@ -182,3 +182,104 @@ def test_errors(L):
     s = L.Store(values=np.array([[0, 5], [1, 2]], dtype=np.int32))
     r = t.fixpoint(s)
     assert r.sweeps == 0 and not r.has_changed and not r.is_bot
+
+
+# ---- bitset stores (VStore<NBitset<64>>, tests/pc_bitset_test.cpp) -------------------------------------------------
+def check_parity_bits(L, O, formulas, cells, nvars, label=""):
+    from lala_pc_b200 import pcflat
+    props, terms = pcflat.flatten(formulas)
+    m = O.PCModel(formulas)
+    want, st = m.fixpoint_bits(cells)
+    t = L.PcTable(props, terms, nvars)
+    s = L.Store(nvars=nvars)
+    s.write_bits(cells)
+    r = t.fixpoint(s, bitset=True)
+    got = s.read_bits()
+    assert bool(r.is_bot) == bool(st.is_bot), (label, "bot flag")
+    if not st.is_bot:
+        assert np.array_equal(got, want), (label, "cells", np.flatnonzero(got != want)[:5].tolist())
+        n_ent, bits = m.ask_all_bits(want, want_bits=True)
+        g_ent, gbits = t.ask_all(s, want_bits=True, bitset=True)
+        assert np.array_equal(gbits, bits) and g_ent == n_ent, (label, "ask bits")
+        assert bool(r.has_changed) == bool(st.has_changed), (label, "has_changed")
+    return got, r, st
+
+
+def test_bitset_golden_vectors(L, O):
+    for k in load_golden("pc_bitset_kat.json")["props"]:
+        cells = np.array(k["before_bits"], dtype=np.uint64)
+        got, r, st = check_parity_bits(L, O, [to_tree(p) for p in k["props"]], cells, len(cells), k["name"])
+        assert got.tolist() == k["after_bits"], k["name"]
+        assert bool(r.has_changed) == k["changed"], k["name"]
+
+
+def test_bitset_deduce_one_and_random(L, O):
+    from lala_pc_b200 import pcflat
+    from test_devhost_pc import random_bits_pc, random_cells
+    rng = np.random.default_rng(5)
+    n_ok = 0
+    for trial in range(150):
+        nvars = int(rng.integers(3, 9))
+        forms, cells = random_bits_pc(rng, nvars), random_cells(rng, nvars)
+        _, r, st = check_parity_bits(L, O, forms, cells, nvars, f"random bits {trial}")
+        n_ok += not st.is_bot
+        if trial < 25:   # PC::deduce(i) step by step
+            props, terms = pcflat.flatten(forms)
+            m = O.PCModel(forms)
+            t = L.PcTable(props, terms, nvars)
+            s = L.Store(nvars=nvars)
+            s.write_bits(cells)
+            cur, bot = cells, False
+            for i in range(len(forms)):
+                cur, changed, bot = m.deduce_bits(i, cur, bot)
+                assert t.deduce(s, i, bitset=True) == changed, (trial, i)
+                if not bot:
+                    assert np.array_equal(s.read_bits(), cur), (trial, i)
+    assert n_ok >= 25
+
+
+@pytest.mark.parametrize("scale", [0.05, 1.0])
+def test_config5_interval_vs_bitset(L, O, W, scale):
+    """BASELINE.json config 5 (100k vars / 500k propagators at scale 1): both stores bit-exact against the tree walker,
+    the bitset fixpoint refines the interval one, the planted solution survives, and the fixpoint is idempotent."""
+    net = W.config5(scale)
+    formulas = net.formulas()
+    m = O.PCModel(formulas)
+    t = L.PcTable(net.props, net.terms, net.nvars)
+    want_i, st_i = m.fixpoint(net.store)
+    si = L.Store(values=net.store)
+    ri = t.fixpoint(si)
+    assert not ri.is_bot and np.array_equal(si.read(), want_i)
+    cells = L.nbit_from_intervals(net.store)
+    assert np.array_equal(cells, O.nbit_store(net.store))
+    want_b, st_b = m.fixpoint_bits(cells)
+    sb = L.Store(nvars=net.nvars)
+    sb.write_bits(cells)
+    rb = t.fixpoint(sb, bitset=True)
+    got_b = sb.read_bits()
+    assert not rb.is_bot and not st_b.is_bot and np.array_equal(got_b, want_b)
+    assert ((got_b & ~L.nbit_from_intervals(want_i)) == 0).all()
+    sol = L.nbit_range(net.solution, net.solution)
+    assert ((got_b & sol) == sol).all()
+    r2 = t.fixpoint(sb, bitset=True)
+    assert not r2.has_changed and r2.sweeps == 1
+    buf = cells.copy()
+    t.fixpoint_host(buf, bitset=True)
+    assert np.array_equal(buf, want_b)
+    # failing twin: a variable of an equality pushed off its planted value
+    eq = np.flatnonzero(net.props[:, 0] == 3)[0]
+    v = int(net.terms[net.props[eq, 1], 1])
+    twin = cells.copy()
+    twin[v] = L.nbit_range((int(net.solution[v]) + 30) % 62, (int(net.solution[v]) + 30) % 62)
+    _, stt = m.fixpoint_bits(twin)
+    sb.write_bits(twin)
+    rt = t.fixpoint(sb, bitset=True)
+    assert bool(rt.is_bot) == bool(stt.is_bot)
+
+
+def test_bitset_refuses_linear_kinds(L):
+    t = L.PcTable(np.array([[1, 0, 2, 5, -1]], dtype=np.int32), np.array([[1, 0], [1, 1]], dtype=np.int32), 2)
+    s = L.Store(nvars=2)
+    s.write_bits(np.array([7, 7], dtype=np.uint64))
+    with pytest.raises(L.LpcError):
+        t.fixpoint(s, bitset=True)

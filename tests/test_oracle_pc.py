@@ -44,3 +44,47 @@ def test_formula_goldens():
         # stop-on-bot contract gives the same store on non-failed inputs
         s2, st2 = m.fixpoint(store)
         assert np.array_equal(s2, s) and not st2.is_bot
+
+
+def test_bitset_goldens():
+    """BitPCTest.* (pc_bitset_test.cpp:68-157): the tree walker over NBitset<64> cells."""
+    kats = load_golden("pc_bitset_kat.json")["props"]
+    assert len(kats) == 15
+    for k in kats:
+        m = O.PCModel([to_tree(p) for p in k["props"]])
+        before = np.array(k["before_bits"], dtype=np.uint64)
+        s, st = m.fixpoint_bits(before, stop_on_bot=False, max_sweeps=100)
+        assert not st.is_bot and st.sweeps < 100, k["name"]
+        assert s.tolist() == k["after_bits"], (k["name"], [hex(int(x)) for x in s])
+        assert bool(st.has_changed) == k["changed"], k["name"]
+        assert (m.ask_all_bits(s) == len(m)) == k["ua"], k["name"]
+
+
+def test_nbit_layout():
+    """NBit(lb, ub), from_set, lb()/ub(): the layout pinned by `var -15..5` == NBit(-1, 5) (pc_bitset_test.cpp:152-156)."""
+    assert O.nbit(-15, 5) == O.nbit(-1, 5) == 0b1111111
+    assert O.nbit(0, 61) == ((1 << 63) - 2) and O.nbit(-2**31, 2**31 - 1) == 2**64 - 1
+    assert O.nbit(62, 100) == 1 << 63 and O.nbit(5, 4) == 0
+    assert O.nbit_from_set([1, 3]) == 0b10100
+    assert O.nbit_bounds(O.nbit(3, 9)) == (3, 9)
+    assert O.nbit_bounds(O.nbit(-5, 70)) == (-2**31, 2**31 - 1)
+    assert O.nbit_bounds(1 << 63) == (62, 2**31 - 1) and O.nbit_bounds(1) == (-2**31, -1)
+    import lala_pc_b200 as L     # the product's host helper builds the same cells
+    lo = np.array([-15, 0, 62, 5, 3, -2**31])
+    hi = np.array([5, 61, 100, 4, 9, 2**31 - 1])
+    assert L.nbit_range(lo, hi).tolist() == [O.nbit(a, b) for a, b in zip(lo.tolist(), hi.tolist())]
+
+
+def test_bitset_refines_interval():
+    """On domains inside [0, 61] the bitset fixpoint is at least as tight as the interval one (config-5 shapes)."""
+    from lala_pc_b200 import workloads as W
+    net = W.config5(0.02)
+    m = O.PCModel(net.formulas())
+    si, sti = m.fixpoint(net.store)
+    sb, stb = m.fixpoint_bits(O.nbit_store(net.store))
+    assert not sti.is_bot and not stb.is_bot
+    hull = O.nbit_store(si)
+    assert ((sb & ~hull) == 0).all()
+    assert (sb != hull).any()        # != punches holes an interval cannot hold
+    sol = np.array([O.nbit(v, v) for v in net.solution.tolist()], dtype=np.uint64)
+    assert ((sb & sol) == sol).all()  # the planted solution survives
