@@ -75,6 +75,10 @@ int lpc_pc_ask_all(const lpc_pc_table* t, const lpc_store* s, int64_t* n_entaile
  * calls: NBitset arithmetic on sums lives in lala-core (un-vendored) and no reference test pins it. */
 int lpc_store_write_bits(lpc_store* s, int32_t first, int32_t n, const uint64_t* cells);
 int lpc_store_read_bits(const lpc_store* s, int32_t first, int32_t n, uint64_t* cells);
+/* VStore::embed / is_bot / is_top on bitset cells (pc.hpp:647-649, 685-692). */
+int lpc_store_embed_bits(lpc_store* s, int32_t var, uint64_t cell, int* changed);
+int lpc_store_is_bot_bits(const lpc_store* s, int* out);
+int lpc_store_is_top_bits(const lpc_store* s, int* out);
 /* NBitset(lb, ub): the cell holding the integer range [lb, ub] (empty if lb > ub). Pure host helper. */
 uint64_t lpc_nbit_range(int32_t lb, int32_t ub);
 int lpc_pc_fixpoint_bits(const lpc_pc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, lpc_fixpoint_result* r);

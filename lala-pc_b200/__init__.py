@@ -121,6 +121,9 @@ SIGNATURES = {
     "lpc_store_write_bits": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "lpc_store_read_bits": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "lpc_nbit_range": (_u64, [_i32, _i32]),
+    "lpc_store_embed_bits": (ctypes.c_int, [_vp, _i32, _u64, _pint]),
+    "lpc_store_is_bot_bits": (ctypes.c_int, [_vp, _pint]),
+    "lpc_store_is_top_bits": (ctypes.c_int, [_vp, _pint]),
     "lpc_pc_fixpoint_bits": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
     "lpc_pc_fixpoint_bits_host": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(FixpointOpts), ctypes.POINTER(FixpointResult)]),
     "lpc_pc_deduce_one_bits": (ctypes.c_int, [_vp, _vp, _i64, _pint]),

@@ -1,5 +1,6 @@
 // lpc_core.cu — library plumbing: errors, device selection, propagator table upload, interval store.
 #include "lpc_internal.cuh"
+#include "../../include/lpc_pc.h"
 
 #include <cstdarg>
 #include <cstring>
@@ -53,6 +54,27 @@ __global__ void k_store_scan(const int2* s, int n, int* out) {
     if(bot) atomicOr(&out[0], 1);
     if(nontop) atomicOr(&out[1], 1);
   }
+}
+
+// the same over NBitset<64> cells: empty = 0, top = all ones
+__global__ void k_store_scan_bits(const unsigned long long* s, int n, int* out) {
+  int bot = 0, nontop = 0;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long v = s[i];
+    bot |= v == 0;
+    nontop |= v != ~0ull;
+  }
+  bot = __syncthreads_or(bot);
+  nontop = __syncthreads_or(nontop);
+  if(threadIdx.x == 0) {
+    if(bot) atomicOr(&out[0], 1);
+    if(nontop) atomicOr(&out[1], 1);
+  }
+}
+__global__ void k_store_embed_bits(unsigned long long* s, int var, unsigned long long cell, int* changed) {
+  const unsigned long long v = s[var], n = v & cell;
+  if(n != v) s[var] = n;
+  *changed = n != v;
 }
 
 // VStore::embed: meet + changed
@@ -302,12 +324,13 @@ int lpc_store_copy(lpc_store* dst, const lpc_store* src) {
   return LPC_OK;
 }
 
-static int store_scan(const lpc_store* s, int out[2]) {
+static int store_scan(const lpc_store* s, int out[2], bool bits = false) {
   out[0] = out[1] = 0;
   if(s->nvars == 0) return LPC_OK;
   LPC_CUDA(cudaMemset(&s->d_ctl->scratch[0], 0, 2 * sizeof(int)));
   int blocks = std::min(ceil_div(s->nvars, 256), 148 * 8);
-  k_store_scan<<<blocks, 256>>>(s->d, s->nvars, &s->d_ctl->scratch[0]);
+  if(bits) k_store_scan_bits<<<blocks, 256>>>(reinterpret_cast<const unsigned long long*>(s->d), s->nvars, &s->d_ctl->scratch[0]);
+  else k_store_scan<<<blocks, 256>>>(s->d, s->nvars, &s->d_ctl->scratch[0]);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   LPC_CUDA(cudaMemcpy(out, &s->d_ctl->scratch[0], 2 * sizeof(int), cudaMemcpyDeviceToHost));
@@ -327,6 +350,37 @@ int lpc_store_is_top(const lpc_store* s, int* out) {
   LPC_REQUIRE(s && out, "null argument");
   int r[2];
   int rc = store_scan(s, r);
+  if(rc) return rc;
+  *out = !r[1];
+  return LPC_OK;
+}
+
+/* ---- NBitset<64> cells (include/lpc_pc.h) ---- */
+int lpc_store_embed_bits(lpc_store* s, int32_t var, uint64_t cell, int* changed) {
+  LPC_REQUIRE(s != nullptr, "null store");
+  LPC_REQUIRE(var >= 0 && var < s->nvars, "variable out of range");
+  k_store_embed_bits<<<1, 1>>>(reinterpret_cast<unsigned long long*>(s->d), var, cell, &s->d_ctl->scratch[0]);
+  g_launches++;
+  LPC_CUDA(cudaGetLastError());
+  int c = 0;
+  LPC_CUDA(cudaMemcpy(&c, &s->d_ctl->scratch[0], sizeof(int), cudaMemcpyDeviceToHost));
+  if(changed) *changed = c;
+  return LPC_OK;
+}
+
+int lpc_store_is_bot_bits(const lpc_store* s, int* out) {
+  LPC_REQUIRE(s && out, "null argument");
+  int r[2];
+  int rc = store_scan(s, r, true);
+  if(rc) return rc;
+  *out = r[0];
+  return LPC_OK;
+}
+
+int lpc_store_is_top_bits(const lpc_store* s, int* out) {
+  LPC_REQUIRE(s && out, "null argument");
+  int r[2];
+  int rc = store_scan(s, r, true);
   if(rc) return rc;
   *out = !r[1];
   return LPC_OK;
