@@ -194,6 +194,7 @@ int lpc_table_create(const lpc_bytecode* records, int64_t n, int32_t nvars, lpc_
   cudaDeviceProp prop;
   LPC_CUDA(cudaGetDeviceProperties(&prop, dev));
   t->sm_count = prop.multiProcessorCount;
+  t->smem_optin = prop.sharedMemPerBlockOptin;
   *out = t;
   return LPC_OK;
 }
@@ -203,6 +204,7 @@ int lpc_table_destroy(lpc_table* t) {
   cudaFree(t->d_op); cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z);
   cudaFree(t->d_inc_off); cudaFree(t->d_inc_idx); cudaFree(t->d_chunk);
   if(t->host_store) lpc_store_destroy(t->host_store);
+  lpc_win_plan_free(t->win_plan);
   delete t;
   return LPC_OK;
 }

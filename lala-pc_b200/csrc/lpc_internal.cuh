@@ -56,6 +56,7 @@ struct FixCtl {
   // worklist state
   int q_len[4];         // rotating queue-length words (3 in use)
   int scratch[4];
+  unsigned long long bar[4];   // rotating vote-carrying barrier words (grid_barrier.cuh; 3 in use)
 };
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -63,6 +64,9 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 } // namespace lpc
 
 struct lpc_store;
+struct lpc_win_plan;                                   // pir_window.cu
+void lpc_win_plan_free(lpc_win_plan* p);
+int lpc_win_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, int* used);
 struct lpc_table {
   int device = 0;
   std::vector<lpc_bytecode> host;   // the caller's records, caller's order (load_deduce)
@@ -80,6 +84,8 @@ struct lpc_table {
   int sm_count = 0;
   size_t smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin
   lpc_store* host_store = nullptr;  // device staging store of lpc_fixpoint_host
+  bool win_plan_tried = false;      // shared-memory window plan of pir_window.cu (built on first dense launch)
+  lpc_win_plan* win_plan = nullptr;
 };
 
 struct lpc_store {

@@ -19,7 +19,17 @@ struct PcTableDev {
   long long n;
   long long n_terms;
   int nvars;
+  // lane tiles of the fixpoint kernel (pc_fixpoint.cu): 32 x {coef, var, meta, rhs} per tile
+  const int4* tiles;
+  const int* tile_prop0;   // index of the first propagator of each tile
+  long long n_tiles;
+  const int* big;          // propagators with more than 32 lanes
+  int n_big;
 };
+
+// lane meta word: bits 0-4 first lane of the propagator, 5-10 its lane count (1..32), 11-13 kind (0 = padding),
+// bit 14 = this lane is the Boolean of a reified sum
+#define PC_META(start, len, kind, isb) ((start) | ((len) << 5) | ((kind) << 11) | ((isb) << 14))
 
 LPC_HD bool b_inf(int x) { return x == LPC_INF || x == LPC_MINF; }
 LPC_HD int b_clamp(long long x) { return x >= LPC_INF ? LPC_INF : (x <= LPC_MINF ? LPC_MINF : (int)x); }

@@ -2,35 +2,45 @@
 //
 // Replaces  GaussSeidelIteration{}.fixpoint(pc.num_deductions(), [&](size_t i){ return pc.deduce(i); }, has_changed)
 // (tests/pc_test.cpp:91-94) where pc.deduce(i) walks a heap-allocated formula / term tree (pc.hpp:671-680). The flat
-// table is streamed instead: one 16-byte header per propagator + 8 bytes per term, one thread per propagator, bounds
-// gathered from the L2-resident store, joins by atomicMax / atomicMin. Same persistent cooperative skeleton as the
-// PIR kernel: dense chaotic sweeps, block-voted has_changed / bot, a grid barrier per sweep.
+// table is streamed instead, ONE LANE PER TERM: the builder packs whole propagators into 32-lane tiles (a 16-byte
+// {coef, var, meta, rhs} record per lane, a reified sum gets one more lane for its Boolean), a warp fetches a tile with
+// one coalesced 512-byte load, every lane gathers its own domain from the L2-resident store, the lanes of a propagator
+// combine through segmented shuffles (sum of the term bounds, partner domain, ballot of refuted literals) and each lane
+// joins its own variable by atomicMax / atomicMin (atomicAnd on bitset stores). Two dependent memory round trips per
+// propagator whatever its arity, where a thread walking its terms one after the other pays two per term.
+// Propagators whose arithmetic could leave int32 (an infinite or empty operand, |term bound| >= 2^26) and propagators
+// with more than 32 lanes are evaluated by the term-by-term routine of pc_device.cuh (`pc_deduce`), which is also what
+// PC::deduce(i) uses; both compute the same monotone operator, so the fixpoint is the same.
+// Same persistent cooperative skeleton as the PIR kernel: dense chaotic sweeps, block-voted has_changed / bot, a grid
+// barrier per sweep.
 #include "lpc_internal.cuh"
 #include "pc_device.cuh"
+#include "grid_barrier.cuh"
 
-#include <cooperative_groups.h>
 #include <algorithm>
 #include <cstring>
 
 #include "../../include/lpc_pc.h"
 
-namespace cg = cooperative_groups;
-
 namespace lpc {
 
 constexpr int PC_TPB = 256;
+// kernel variants <tiles whose loads a warp keeps in flight together (0 = software pipeline), min blocks per SM>; LPC_PC_VARIANT picks one for
+// tuning runs (tools/pc_probe.py), the default is the fastest measured on config 3 / config 5
+constexpr int PC_NVAR = 5;
+constexpr int PC_VAR_DEFAULT = 0;
 
 // VStore<Interval<ZLB>> in global memory: gathers + lattice joins at L2.
 struct GlobalAcc {
   int2* s;
   mutable int seen_bot;
   __device__ __forceinline__ Itv load(int v) const {
-    const int2 d = s[v];
+    const int2 d = __ldcg(&s[v]);
     seen_bot |= d.x > d.y;
     return Itv(d.x, d.y);
   }
   __device__ __forceinline__ int embed(int v, const Itv& u) {
-    const int2 old = s[v];
+    const int2 old = __ldcg(&s[v]);
     int f = 0;
     if(u.lb > old.x) { atomicMax(&s[v].x, u.lb); f = 1; }
     if(u.ub < old.y) { atomicMin(&s[v].y, u.ub); f = 1; }
@@ -44,12 +54,12 @@ struct GlobalBitAcc {
   u64* s;
   mutable int seen_bot;
   __device__ __forceinline__ u64 load(int v) const {
-    const u64 d = s[v];
+    const u64 d = __ldcg(&s[v]);
     seen_bot |= d == 0;
     return d;
   }
   __device__ __forceinline__ int embed(int v, u64 u) {
-    const u64 old = s[v];
+    const u64 old = __ldcg(&s[v]);
     if(old == 0) return 2;
     const u64 nw = old & u;
     if(nw == old) return 0;
@@ -60,51 +70,239 @@ struct GlobalBitAcc {
 
 template <bool BITS> struct PcAcc { typedef GlobalAcc type; };
 template <> struct PcAcc<true> { typedef GlobalBitAcc type; };
-template <bool BITS, class Acc> __device__ __forceinline__ int pc_step(Acc& acc, const int4 h, const int2* terms) {
+template <bool BITS, class Acc> __device__ __noinline__ int pc_step(Acc& acc, const int4 h, const int2* terms) {
   if constexpr(BITS) return pc_deduce_bits(acc, h, terms);
   else return pc_deduce(acc, h, terms);
 }
 __device__ __forceinline__ GlobalAcc make_acc(int2* store, GlobalAcc*) { return GlobalAcc{store, 0}; }
 __device__ __forceinline__ GlobalBitAcc make_acc(int2* store, GlobalBitAcc*) { return GlobalBitAcc{reinterpret_cast<u64*>(store), 0}; }
 
-template <bool BITS>
-__global__ void __launch_bounds__(PC_TPB) k_pc_fixpoint(PcTableDev t, int2* store, FixCtl* ctl, int max_sweeps,
+// ---- one tile = one warp step ------------------------------------------------------------------------------------------
+// Join of one variable given the domain this lane read (VStore::embed): bit0 = tightened, bit1 = became empty.
+__device__ __forceinline__ int lane_embed(int2* s, int v, const Itv& old, const Itv& u) {
+  int f = 0;
+  if(u.lb > old.lb) { atomicMax(&s[v].x, u.lb); f = 1; }
+  if(u.ub < old.ub) { atomicMin(&s[v].y, u.ub); f = 1; }
+  if(f && max(u.lb, old.lb) > min(u.ub, old.ub)) f |= 2;
+  return f;
+}
+__device__ __forceinline__ int lane_embed_bits(u64* s, int v, u64 old, u64 u) {
+  const u64 nw = old & u;
+  if(nw == old) return 0;
+  atomicAnd(&s[v], u);
+  return nw == 0 ? 3 : 1;
+}
+// x with the value p removed (Equality<true>::deduce, formula.hpp:645-652)
+__device__ __forceinline__ Itv itv_shave(const Itv& x, int p) {
+  Itv lo = x, hi = x;
+  lo.meet(Itv(b_add(p, 1), LPC_INF));
+  hi.meet(Itv(LPC_MINF, b_sub(p, 1)));
+  return fjoin(lo, hi);
+}
+
+// the rare path of a tile: one propagator evaluated term by term (kept out of line: it would otherwise set the register
+// count of the whole kernel)
+template <class Acc>
+__device__ __forceinline__ int tile_fallback(const PcTableDev& t, Acc& acc, int p) {
+  const int4 h = t.hdr[p];
+  return pc_step<false>(acc, h, t.terms + h.y);
+}
+
+// `L` = this lane's record of the tile, `raw` = the 8-byte cell of its variable (already loaded by the caller so that
+// several tiles' loads are in flight together).
+template <bool BITS, class Acc>
+__device__ __forceinline__ int tile_step(const PcTableDev& t, Acc& acc, int2* store, long long tile, int lane, const int4 L,
+                                         const int2 raw) {
+  const unsigned FULL = 0xffffffffu;
+  const int coef = L.x, var = L.y, meta = L.z, rhs = L.w;
+  const int kind = (meta >> 11) & 7, seg0 = meta & 31, len = (meta >> 5) & 63, pos = lane - seg0;
+  const bool active = kind != 0, isb = (meta >> 14) & 1;
+  const int last = seg0 + len - 1;
+  const unsigned segmask = (len >= 32 ? FULL : ((1u << len) - 1u)) << seg0;
+  // the lane whose domain this lane needs: the Boolean of a reified sum, else the other side of a binary propagator
+  const int partner = (kind == PC_LIN_LE || kind == PC_REIF_LIN_LE) ? last : (len == 2 ? seg0 + 1 - pos : lane);
+  int f = 0;
+  if constexpr(BITS) {
+    u64* cells = reinterpret_cast<u64*>(store);
+    const u64 dom = active ? ((u64)(unsigned)raw.x | ((u64)(unsigned)raw.y << 32)) : ~0ull;
+    const u64 pd = __shfl_sync(FULL, dom, partner);
+    const bool refuted = kind == PC_CLAUSE && nb_lit_ask(coef > 0, dom);
+    const unsigned open = __ballot_sync(FULL, kind == PC_CLAUSE && !refuted) & segmask;
+    if(!active) return 0;
+    if(dom == 0) f |= 2;
+    switch(kind) {
+      case PC_EQ: f |= lane_embed_bits(cells, var, dom, pd); break;
+      case PC_NEQ:
+        if(len == 2) { if(nb_singleton(pd)) f |= lane_embed_bits(cells, var, dom, ~pd); }
+        else { const u64 r = nb_range(rhs, rhs); if(nb_singleton(r)) f |= lane_embed_bits(cells, var, dom, ~r); }
+        break;
+      case PC_CLAUSE: {
+        const int n_open = __popc(open);
+        if((n_open == 1 && !refuted) || (n_open == 0 && lane == last)) f |= lane_embed_bits(cells, var, dom, coef < 0 ? 2ull : 4ull);
+        break;
+      }
+      case PC_ABS_EQ:
+        if(pos == 0) f |= lane_embed_bits(cells, var, dom, pd | nb_neg(pd));   // x <- y join -y
+        else f |= lane_embed_bits(cells, var, dom, nb_abs(pd));                // y <- |x|
+        break;
+      default: break;
+    }
+    return f;
+  }
+  else {
+    const Itv dom = active ? Itv(raw.x, raw.y) : Itv(0, 0);
+    const bool lin = kind == PC_LIN_LE || kind == PC_REIF_LIN_LE;
+    const bool term_lane = lin && !isb;
+    // c * x as the hull of the two products (terms.hpp:399-405). A propagator is "tame" when every operand is non-empty
+    // and every term bound is below 2^24 in magnitude: with at most 32 lanes and |rhs| < 2^30 (checked by the table
+    // builder) nothing below can leave int32, so plain integer arithmetic gives what the saturating bound arithmetic
+    // of pc_device.cuh gives. Infinite bounds fail the test by their size.
+    const long long p0 = (long long)coef * dom.lb, p1 = (long long)coef * dom.ub;
+    const long long tlo = min(p0, p1), thi = max(p0, p1);
+    const bool tame = dom.lb <= dom.ub && (!term_lane || (tlo > -(1 << 24) && thi < (1 << 24)));
+    const int ti_lb = term_lane ? (int)tlo : 0, ti_ub = term_lane ? (int)thi : 0;
+    const unsigned wildm = __ballot_sync(FULL, active && lin && !tame);
+    const unsigned heads = __ballot_sync(FULL, active && pos == 0);
+    const int maxlen = __reduce_max_sync(FULL, lin ? len : 0);
+    // segmented inclusive sums of the term bounds, then the propagator's total from its last lane
+    int slb = ti_lb, sub_ = ti_ub;
+    for(int off = 1; off < maxlen; off <<= 1) {
+      const int a = __shfl_up_sync(FULL, slb, off), b = __shfl_up_sync(FULL, sub_, off);
+      if(pos >= off) { slb = wadd(slb, a); sub_ = wadd(sub_, b); }
+    }
+    const int all_lb = __shfl_sync(FULL, slb, last), all_ub = __shfl_sync(FULL, sub_, last);
+    const Itv pd(__shfl_sync(FULL, dom.lb, partner), __shfl_sync(FULL, dom.ub, partner));
+    const bool refuted = kind == PC_CLAUSE && lit_ask(coef > 0, dom);
+    const unsigned open = __ballot_sync(FULL, kind == PC_CLAUSE && !refuted) & segmask;
+    if(!active) return 0;
+    if(dom.lb > dom.ub) f |= 2;
+    if(lin) {
+      if(wildm & segmask) {   // rare: the term-by-term routine, by the first lane of the propagator
+        if(pos == 0) f |= tile_fallback(t, acc, t.tile_prop0[tile] + __popc(heads & ((1u << lane) - 1u)));
+        return f;
+      }
+      // Inequality::deduce / Biconditional::deduce (formula.hpp:796-805, 421-427); pd = the Boolean's domain
+      int dir = 1;   // 1: sum <= rhs, -1: sum >= rhs + 1, 0: the terms stay
+      if(kind == PC_REIF_LIN_LE) {
+        if(pd.lb > 0 || pd.ub < 0) dir = 1;              // b true (b does not contain 0)
+        else if(pd.lb == 0 && pd.ub == 0) dir = -1;      // b false
+        else {
+          dir = 0;
+          if(isb) {
+            if(all_ub <= rhs) f |= lane_embed(store, var, dom, Itv(1, 1));
+            else if(all_lb > rhs) f |= lane_embed(store, var, dom, Itv(0, 0));
+          }
+        }
+      }
+      if(dir != 0 && !isb) {
+        // Nary<Add>::embed (terms.hpp:480-499): c * x <= rhs - (all.lb - t.lb), resp. c * x >= rhs + 1 - (all.ub - t.ub);
+        // then x's side by Euclidean division (GroupMul::left_residual, terms.hpp:249-253)
+        const int bound = dir > 0 ? rhs - (all_lb - ti_lb) : rhs + 1 - (all_ub - ti_ub);
+        int q = bound;
+        if(coef != 1) {
+          q = bound / coef;
+          const int r = bound - q * coef;
+          if(r < 0) q += coef > 0 ? -1 : 1;
+        }
+        // sum <= rhs bounds x above for a positive coefficient and below for a negative one; sum >= rhs + 1 the reverse.
+        // The Euclidean quotient is a floor for c > 0 and a ceiling for c < 0, which is the wanted rounding when the
+        // bounded side is "above" (dir * c > 0); for the other side the hull of the reference's residual is the same
+        // quotient (both ends of u ediv c, one of them infinite).
+        if((dir > 0) == (coef > 0)) { if(q < dom.ub) { atomicMin(&store[var].y, q); f |= q < dom.lb ? 3 : 1; } }
+        else { if(q > dom.lb) { atomicMax(&store[var].x, q); f |= q > dom.ub ? 3 : 1; } }
+      }
+      return f;
+    }
+    switch(kind) {
+      case PC_EQ: f |= lane_embed(store, var, dom, pd); break;
+      case PC_NEQ:
+        if(len == 2) { if(pd.lb == pd.ub) f |= lane_embed(store, var, dom, itv_shave(dom, pd.lb)); }
+        else f |= lane_embed(store, var, dom, itv_shave(dom, rhs));
+        break;
+      case PC_CLAUSE: {
+        const int n_open = __popc(open);
+        if((n_open == 1 && !refuted) || (n_open == 0 && lane == last)) f |= lane_embed(store, var, dom, coef < 0 ? Itv(0, 0) : Itv(1, 1));
+        break;
+      }
+      case PC_ABS_EQ:
+        if(pos == 0) f |= lane_embed(store, var, dom, fjoin(pd, Itv(b_neg(pd.ub), b_neg(pd.lb))));   // x <- hull(y, -y)
+        else {                                                                                       // y <- |x|
+          Itv ax = pd;
+          if(!pd.is_bot()) {
+            if(pd.lb >= 0) ax = pd;
+            else if(pd.ub <= 0) ax = Itv(b_neg(pd.ub), b_neg(pd.lb));
+            else ax = Itv(0, max(b_neg(pd.lb), pd.ub));
+          }
+          f |= lane_embed(store, var, dom, ax);
+        }
+        break;
+      default: break;
+    }
+    return f;
+  }
+}
+
+template <bool BITS, int PC_UNROLL, int PC_MIN_BLOCKS>
+__global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDev t, int2* store, FixCtl* ctl, int max_sweeps,
                                                         int stop_on_bot) {
   typedef typename PcAcc<BITS>::type Acc;
-  cg::grid_group grid = cg::this_grid();
+  __shared__ unsigned long long s_vote;
   const int tid = threadIdx.x;
   const long long gtid = blockIdx.x * (long long)PC_TPB + tid;
   const long long gthreads = (long long)gridDim.x * PC_TPB;
-  volatile int* vflags = ctl->flags;
-  volatile int* vbot = &ctl->is_bot;
-  {
+  const int lane = tid & 31;
+  const long long gwarp = gtid >> 5, gwarps = gthreads >> 5;
+  int nbar = 0;
+  bool bot;
+  {   // a store that is already at bot stops before the first sweep
     int f = 0;
-    for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = store[i]; f |= BITS ? (v.x | v.y) == 0 : v.x > v.y; }
-    if(__syncthreads_or(f) && tid == 0) atomicOr(&ctl->is_bot, 1);
+    for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = __ldcg(&store[i]); f |= BITS ? (v.x | v.y) == 0 : v.x > v.y; }
+    bot = grid_vote_barrier(ctl->bar, nbar++, false, f != 0, &s_vote).bot;
   }
-  grid.sync();
   int sweeps = 0;
   bool any_changed = false;
-  bool bot = *vbot != 0;
   bool done = (bot && stop_on_bot) || t.n == 0;
   while(!done) {
-    const int slot = sweeps % 3;
-    if(blockIdx.x == 0 && tid == 0) vflags[(sweeps + 1) % 3] = 0;
     Acc acc = make_acc(store, (Acc*)nullptr);
     int f = 0;
-    for(long long p = gtid; p < t.n; p += gthreads) {
-      const int4 h = t.hdr[p];
+    if constexpr(PC_UNROLL == 0) {
+      // two-stage software pipeline: while tile i is evaluated, the domains of tile i + 1 and the records of tile i + 2
+      // are in flight, so a warp waits for memory once per sweep instead of twice per tile
+      const int4 Z = make_int4(0, 0, 0, 0);
+      long long cur = gwarp;
+      int4 L0 = cur < t.n_tiles ? __ldg(&t.tiles[cur * 32 + lane]) : Z;
+      int4 L1 = cur + gwarps < t.n_tiles ? __ldg(&t.tiles[(cur + gwarps) * 32 + lane]) : Z;
+      int2 r0 = (L0.z >> 11) & 7 ? __ldcg(&store[L0.y]) : make_int2(0, 0);
+      while(cur < t.n_tiles) {
+        const int4 L2 = cur + 2 * gwarps < t.n_tiles ? __ldg(&t.tiles[(cur + 2 * gwarps) * 32 + lane]) : Z;
+        const int2 r1 = (L1.z >> 11) & 7 ? __ldcg(&store[L1.y]) : make_int2(0, 0);
+        f |= tile_step<BITS>(t, acc, store, cur, lane, L0, r0);
+        L0 = L1; L1 = L2; r0 = r1;
+        cur += gwarps;
+      }
+    }
+    else
+    for(long long base = gwarp * PC_UNROLL; base < t.n_tiles; base += gwarps * PC_UNROLL) {
+      int4 L[PC_UNROLL ? PC_UNROLL : 1];
+      int2 raw[PC_UNROLL ? PC_UNROLL : 1];
+#pragma unroll
+      for(int u = 0; u < PC_UNROLL; ++u)
+        L[u] = base + u < t.n_tiles ? __ldg(&t.tiles[(base + u) * 32 + lane]) : make_int4(0, 0, 0, 0);
+#pragma unroll
+      for(int u = 0; u < PC_UNROLL; ++u) raw[u] = (L[u].z >> 11) & 7 ? __ldcg(&store[L[u].y]) : make_int2(0, 0);
+#pragma unroll
+      for(int u = 0; u < PC_UNROLL; ++u) f |= tile_step<BITS>(t, acc, store, base + u, lane, L[u], raw[u]);
+    }
+    for(long long b = gtid; b < t.n_big; b += gthreads) {
+      const int4 h = t.hdr[t.big[b]];
       f |= pc_step<BITS>(acc, h, t.terms + h.y);
     }
     if(acc.seen_bot) f |= 2;
-    if(__syncthreads_or(f & 2) && tid == 0) atomicOr(&ctl->is_bot, 1);
-    if(__syncthreads_or(f & 1) && tid == 0) atomicOr(&ctl->flags[slot], 1);
-    grid.sync();
+    const GridVote v = grid_vote_barrier(ctl->bar, nbar++, f & 1, f & 2, &s_vote);
     ++sweeps;
-    const int c = vflags[slot];
-    bot = *vbot != 0;
-    any_changed |= c != 0;
-    if(c == 0 || (bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) done = true;
+    bot |= v.bot;
+    any_changed |= v.changed;
+    if(!v.changed || (bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) done = true;
   }
   if(blockIdx.x == 0 && tid == 0) {
     ctl->sweeps = sweeps;
@@ -148,11 +346,24 @@ struct lpc_pc_table {
   PcTableDev dev{};
   void* d_hdr = nullptr;
   void* d_terms = nullptr;
+  void* d_tiles = nullptr;
+  void* d_tile_prop0 = nullptr;
+  void* d_big = nullptr;
   int sm_count = 0;
   int blocks_per_sm[2] = {0, 0};   // [interval store, bitset store]
+  int variant = 0;
   bool has_linear = false;          // LIN_LE / REIF_LIN_LE present: no bitset rule (see lpc_pc.h)
   lpc_store* host_store = nullptr;
 };
+
+static const void* pc_kernel(bool bits, int variant) {
+  static const void* k[2][PC_NVAR] = {
+    {(const void*)k_pc_fixpoint<false, 1, 4>, (const void*)k_pc_fixpoint<false, 2, 4>, (const void*)k_pc_fixpoint<false, 0, 3>,
+     (const void*)k_pc_fixpoint<false, 0, 4>, (const void*)k_pc_fixpoint<false, 0, 2>},
+    {(const void*)k_pc_fixpoint<true, 1, 4>, (const void*)k_pc_fixpoint<true, 2, 4>, (const void*)k_pc_fixpoint<true, 0, 3>,
+     (const void*)k_pc_fixpoint<true, 0, 4>, (const void*)k_pc_fixpoint<true, 0, 2>}};
+  return k[bits][variant];
+}
 
 extern "C" {
 
@@ -187,20 +398,59 @@ int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_
   LPC_CUDA(cudaMalloc(&t->d_terms, std::max<size_t>((size_t)n_terms * sizeof(int2), 16)));
   if(n_props) LPC_CUDA(cudaMemcpy(t->d_hdr, hdr.data(), (size_t)n_props * sizeof(int4), cudaMemcpyHostToDevice));
   if(n_terms) LPC_CUDA(cudaMemcpy(t->d_terms, terms, (size_t)n_terms * sizeof(int2), cudaMemcpyHostToDevice));
+  // lane tiles: whole propagators packed into 32-lane tiles, in table order (see the header of this file)
+  {
+    std::vector<int4> tiles;
+    std::vector<int> prop0, big;
+    int cur = 32;   // lanes used in the open tile (32 = none open)
+    for(int64_t i = 0; i < n_props; ++i) {
+      const lpc_pc_prop& p = props[i];
+      const int lanes = p.n_terms + (p.kind == LPC_PC_REIF_LIN_LE ? 1 : 0);
+      const bool lin_kind = p.kind == LPC_PC_LIN_LE || p.kind == LPC_PC_REIF_LIN_LE;
+      if(lanes > 32 || (lin_kind && (p.rhs >= (1 << 30) || p.rhs <= -(1 << 30)))) {   // see tile_step: keeps the tile arithmetic in int32
+        big.push_back((int)i);
+        cur = 32;   // close the tile so that tile_prop0 + rank stays a contiguous propagator range
+        continue;
+      }
+      if(cur + lanes > 32) {
+        tiles.resize(tiles.size() + 32, make_int4(0, 0, 0, 0));
+        prop0.push_back((int)i);
+        cur = 0;
+      }
+      int4* lane = tiles.data() + tiles.size() - 32 + cur;
+      for(int k = 0; k < p.n_terms; ++k) {
+        const lpc_pc_term& tm = terms[p.first_term + k];
+        lane[k] = make_int4(tm.coef, tm.var, PC_META(cur, lanes, p.kind, 0), p.rhs);
+      }
+      if(lanes > p.n_terms) lane[p.n_terms] = make_int4(0, p.bvar, PC_META(cur, lanes, p.kind, 1), p.rhs);
+      cur += lanes;
+    }
+    t->dev.n_tiles = (long long)prop0.size();
+    t->dev.n_big = (int)big.size();
+    LPC_CUDA(cudaMalloc(&t->d_tiles, std::max<size_t>(tiles.size() * sizeof(int4), 16)));
+    LPC_CUDA(cudaMalloc(&t->d_tile_prop0, std::max<size_t>(prop0.size() * sizeof(int), 16)));
+    LPC_CUDA(cudaMalloc(&t->d_big, std::max<size_t>(big.size() * sizeof(int), 16)));
+    if(!tiles.empty()) LPC_CUDA(cudaMemcpy(t->d_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    if(!prop0.empty()) LPC_CUDA(cudaMemcpy(t->d_tile_prop0, prop0.data(), prop0.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if(!big.empty()) LPC_CUDA(cudaMemcpy(t->d_big, big.data(), big.size() * sizeof(int), cudaMemcpyHostToDevice));
+    t->dev.tiles = (const int4*)t->d_tiles; t->dev.tile_prop0 = (const int*)t->d_tile_prop0; t->dev.big = (const int*)t->d_big;
+  }
   t->dev.hdr = (const int4*)t->d_hdr; t->dev.terms = (const int2*)t->d_terms;
   t->dev.n = n_props; t->dev.n_terms = n_terms; t->dev.nvars = nvars;
   int dev = 0;
   LPC_CUDA(cudaGetDevice(&dev));
   LPC_CUDA(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
-  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[0], k_pc_fixpoint<false>, PC_TPB, 0));
-  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[1], k_pc_fixpoint<true>, PC_TPB, 0));
+  t->variant = PC_VAR_DEFAULT;
+  if(const char* e = getenv("LPC_PC_VARIANT")) { int v = atoi(e); if(v >= 0 && v < PC_NVAR) t->variant = v; }
+  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[0], pc_kernel(false, t->variant), PC_TPB, 0));
+  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[1], pc_kernel(true, t->variant), PC_TPB, 0));
   *out = t;
   return LPC_OK;
 }
 
 int lpc_pc_table_destroy(lpc_pc_table* t) {
   if(!t) return LPC_OK;
-  cudaFree(t->d_hdr); cudaFree(t->d_terms);
+  cudaFree(t->d_hdr); cudaFree(t->d_terms); cudaFree(t->d_tiles); cudaFree(t->d_tile_prop0); cudaFree(t->d_big);
   if(t->host_store) lpc_store_destroy(t->host_store);
   delete t;
   return LPC_OK;
@@ -226,7 +476,7 @@ static int pc_fixpoint_async(const lpc_pc_table* t, lpc_store* s, const lpc_fixp
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   cudaStream_t st = (cudaStream_t)o->stream;
   int grid = t->sm_count * t->blocks_per_sm[bits];
-  long long want = std::max<long long>(1, (t->dev.n + PC_TPB - 1) / PC_TPB);
+  long long want = std::max<long long>(1, std::max<long long>((t->dev.n_tiles * 32 + PC_TPB - 1) / PC_TPB, (t->dev.n_big + PC_TPB - 1) / PC_TPB));
   if(want < grid) grid = (int)want;
   LPC_CUDA(cudaEventRecord(s->ev0, st));
   LPC_CUDA(cudaMemsetAsync(s->d_ctl, 0, sizeof(FixCtl), st));
@@ -235,8 +485,7 @@ static int pc_fixpoint_async(const lpc_pc_table* t, lpc_store* s, const lpc_fixp
   FixCtl* ctl = s->d_ctl;
   int max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
   void* args[] = {&td, &store, &ctl, &max_sweeps, &stop};
-  LPC_CUDA(cudaLaunchCooperativeKernel(bits ? (void*)k_pc_fixpoint<true> : (void*)k_pc_fixpoint<false>, dim3(grid),
-                                       dim3(PC_TPB), args, 0, st));
+  LPC_CUDA(cudaLaunchCooperativeKernel(pc_kernel(bits, t->variant), dim3(grid), dim3(PC_TPB), args, 0, st));
   g_launches++;
   LPC_CUDA(cudaEventRecord(s->ev1, st));
   LPC_CUDA(cudaMemcpyAsync(s->h_ctl, s->d_ctl, sizeof(FixCtl), cudaMemcpyDeviceToHost, st));

@@ -18,6 +18,7 @@
 //                  iteration reads the final store. has_changed / bot flags are formed by __syncthreads_or and one
 //                  atomic per block.
 #include "lpc_internal.cuh"
+#include "grid_barrier.cuh"
 
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -127,11 +128,12 @@ template <> struct Unit<1> {
 
 // switch_at = number of change events per sweep at or below which the worklist takes over
 // (0: never, UINT_MAX: after the first sweep).
-template <bool HAS_DIV, bool TRACK, int RPT, int MINB>
+template <bool HAS_DIV, bool TRACK, int RPT, int MINB, bool PIPE>
 __global__ void __launch_bounds__(TPB, MINB) k_pir_fixpoint(TableDev t, int2* store, SegTable seg, FixCtl* ctl,
                                                             WlState w, int max_sweeps, int stop_on_bot,
-                                                            unsigned switch_at) {
+                                                            unsigned switch_at, int use_vote) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ unsigned long long s_vote;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const long long gtid = blockIdx.x * (long long)TPB + tid;
@@ -165,6 +167,40 @@ __global__ void __launch_bounds__(TPB, MINB) k_pir_fixpoint(TableDev t, int2* st
       const long long sq0 = seg.q[s], len = seg.q[s + 1] - sq0;
       const int u0 = (int)((sq0 + len * blockIdx.x / gridDim.x) * UPQ);
       const int u1 = (int)((sq0 + len * (blockIdx.x + 1) / gridDim.x) * UPQ);
+      if constexpr(PIPE) {
+        // two-stage software pipeline: while unit i is evaluated, the bounds of unit i + 1 and the records of unit
+        // i + 2 are in flight, so a thread waits for memory once per segment instead of twice per unit. Indices past
+        // the end are clamped to the last unit of the range (a redundant load, never evaluated).
+        int u = u0 + tid;
+        if(u < u1) {
+          const int ulast = u1 - 1;
+          Unit<RPT> cur, nxt;
+          cur.load(t, u);
+          nxt.load(t, min(u + TPB, ulast));
+          int2 a[RPT], b[RPT], c[RPT];
+#pragma unroll
+          for(int k = 0; k < RPT; ++k) { a[k] = store[cur.x[k]]; b[k] = store[cur.y[k]]; c[k] = store[cur.z[k]]; }
+          while(true) {
+            Unit<RPT> nn;
+            nn.load(t, min(u + 2 * TPB, ulast));
+            int2 a2[RPT], b2[RPT], c2[RPT];
+#pragma unroll
+            for(int k = 0; k < RPT; ++k) { a2[k] = store[nxt.x[k]]; b2[k] = store[nxt.y[k]]; c2[k] = store[nxt.z[k]]; }
+#pragma unroll
+            for(int k = 0; k < RPT; ++k) {
+              const int g = run_record<HAS_DIV, TRACK>(cur.op[k], cur.x[k], cur.y[k], cur.z[k], a[k], b[k], c[k], store, w.vmark, mark);
+              f |= g;
+              nchg += g & 1;
+            }
+            u += TPB;
+            if(u >= u1) break;
+            cur = nxt; nxt = nn;
+#pragma unroll
+            for(int k = 0; k < RPT; ++k) { a[k] = a2[k]; b[k] = b2[k]; c[k] = c2[k]; }
+          }
+        }
+      }
+      else
       for(int u = u0 + tid; u < u1; u += TPB) {
         Unit<RPT> r;
         r.load(t, u);
@@ -179,23 +215,32 @@ __global__ void __launch_bounds__(TPB, MINB) k_pir_fixpoint(TableDev t, int2* st
         }
       }
     }
-    // block-level flags: one atomic per block
-    if(__syncthreads_or(f & 2) && tid == 0) atomicOr(&ctl->is_bot, 1);
-    if(TRACK) {
-      nchg = __reduce_add_sync(0xffffffffu, nchg);
-      if(lane == 0 && nchg) atomicAdd(&ctl->flags[slot], nchg);
+    if(!TRACK && use_vote) {
+      // the arrival at the grid barrier carries the block's votes (grid_barrier.cuh): one L2 round trip instead of four
+      const GridVote v = grid_vote_barrier(ctl->bar, sweeps, f & 1, f & 2, &s_vote);
+      ++sweeps; ++dense;
+      deductions += (unsigned long long)t.n;
+      bot |= v.bot;
+      any_changed |= v.changed;
+      if(!v.changed || (bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) done = true;
     }
     else {
-      if(__syncthreads_or(f & 1) && tid == 0) atomicOr(&ctl->flags[slot], 1);
+      // block-level flags: one atomic per block
+      if(__syncthreads_or(f & 2) && tid == 0) atomicOr(&ctl->is_bot, 1);
+      if(TRACK) {
+        nchg = __reduce_add_sync(0xffffffffu, nchg);
+        if(lane == 0 && nchg) atomicAdd(&ctl->flags[slot], nchg);
+      }
+      else if(__syncthreads_or(f & 1) && tid == 0) atomicOr(&ctl->flags[slot], 1);
+      grid.sync();
+      ++sweeps; ++dense;
+      deductions += (unsigned long long)t.n;
+      const unsigned c = (unsigned)vflags[slot];
+      bot = *vbot != 0;
+      any_changed |= c != 0;
+      if(c == 0 || (bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) done = true;
+      else if(TRACK && c <= switch_at) { worklist = true; break; }
     }
-    grid.sync();
-    ++sweeps; ++dense;
-    deductions += (unsigned long long)t.n;
-    const unsigned c = (unsigned)vflags[slot];
-    bot = *vbot != 0;
-    any_changed |= c != 0;
-    if(c == 0 || (bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) done = true;
-    else if(TRACK && c <= switch_at) { worklist = true; break; }
   }
 
   if(TRACK && worklist && !done) {
@@ -297,14 +342,16 @@ __global__ void k_ask_all(TableDev t, const int2* store, unsigned long long* cou
   if((threadIdx.x & 31) == 0 && cnt) atomicAdd(count, (unsigned long long)cnt);
 }
 
-typedef void (*fix_kernel_t)(TableDev, int2*, SegTable, FixCtl*, WlState, int, int, unsigned);
+typedef void (*fix_kernel_t)(TableDev, int2*, SegTable, FixCtl*, WlState, int, int, unsigned, int);
 
 // The (records per thread, min blocks per SM) variants that are built; LPC_RPT / LPC_MINB select one for tuning.
 struct Variant { int rpt, minb; fix_kernel_t k[2][2]; };
-#define LPC_VARIANT(R, M) { R, M, { { k_pir_fixpoint<false, false, R, M>, k_pir_fixpoint<false, true, R, M> }, \
-                                    { k_pir_fixpoint<true, false, R, M>, k_pir_fixpoint<true, true, R, M> } } }
-static const Variant kVariants[] = { LPC_VARIANT(4, 2), LPC_VARIANT(4, 3), LPC_VARIANT(2, 3), LPC_VARIANT(2, 4),
-                                     LPC_VARIANT(1, 4) };
+#define LPC_VARIANT(R, M, P) { R + 10 * P, M, { { k_pir_fixpoint<false, false, R, M, P>, k_pir_fixpoint<false, true, R, M, P> }, \
+                                    { k_pir_fixpoint<true, false, R, M, P>, k_pir_fixpoint<true, true, R, M, P> } } }
+// LPC_RPT = records per thread (+ 10 for the software-pipelined loop)
+static const Variant kVariants[] = { LPC_VARIANT(4, 2, false), LPC_VARIANT(4, 3, false), LPC_VARIANT(2, 3, false), LPC_VARIANT(2, 4, false),
+                                     LPC_VARIANT(1, 4, false), LPC_VARIANT(1, 4, true), LPC_VARIANT(1, 3, true), LPC_VARIANT(2, 3, true),
+                                     LPC_VARIANT(2, 2, true) };
 static const int kDefaultVariant = 2;   // RPT 2, 3 blocks / SM: fastest on config 2 (profiles/r01_variants.md)
 
 static const Variant& pick_variant() {
@@ -403,6 +450,11 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
       LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[tr], var.k[t->has_div ? 1 : 0][tr], TPB, 0));
     t->plan_ready = true;
   }
+  if(!track) {   // dense sweeps: shared-memory windows when the table has the locality for it (pir_window.cu)
+    int used = 0;
+    int rc = lpc_win_fixpoint_launch(t, s, o, &used);
+    if(rc || used) return rc;
+  }
   const int per_sm = t->blocks_per_sm[track ? 1 : 0];
   LPC_REQUIRE(per_sm > 0, "kernel does not fit on an SM");
   // enough blocks to fill the chip, no more than there are thread-loads of work
@@ -432,7 +484,12 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
   int2* store = s->d;
   FixCtl* ctl = s->d_ctl;
   int max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
-  void* args[] = {&td, &store, &seg, &ctl, &w, &max_sweeps, &stop, &switch_at};
+  int use_vote = 1;   // LPC_VOTE=0: flag words + cooperative_groups grid.sync() (kept for A/B runs, profiles/r01_summary.md)
+  if(const char* e = getenv("LPC_VOTE")) use_vote = atoi(e);
+  // a table with at most a couple of units per thread is swept as ONE segment: with a handful of records per block the
+  // per-segment passes only add dependent memory round trips (config 1: 3 segments x 2 round trips per sweep)
+  if(units <= 2LL * grid * TPB) { seg.nseg = 1; seg.q[0] = 0; seg.q[1] = (int)(t->dev.n_pad / 4); }
+  void* args[] = {&td, &store, &seg, &ctl, &w, &max_sweeps, &stop, &switch_at, &use_vote};
   LPC_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(grid), dim3(TPB), args, 0, st));
   g_launches++;
   LPC_CUDA(cudaEventRecord(s->ev1, st));

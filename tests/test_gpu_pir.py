@@ -118,6 +118,34 @@ def test_config2_parity_tenth(L, O, W, mode_name):
     check_parity(L, O, twin.records, twin.store, mode, "config2@0.1 twin")
 
 
+@pytest.mark.parametrize("env", [{"LPC_WINDOW": "1"}, {"LPC_VOTE": "0"}, {"LPC_RPT": "12", "LPC_MINB": "3"}])
+def test_alternative_dense_kernels_parity(L, O, W, env):
+    """The dense-sweep alternatives that are built but not the default - shared-memory store windows (pir_window.cu),
+    the flag-word + grid.sync barrier, the software-pipelined record loop - reach the same fixpoints."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, '.')\n"
+        "import lala_pc_b200 as L\n"
+        "from lala_pc_b200 import workloads as W\n"
+        "from oracle import oracle as O\n"
+        "L.device_init(0)\n"
+        "for net in (W.config1(), W.config2(0.1), W.config2(0.1).failing_twin()):\n"
+        "    want, st = O.pir_fixpoint(net.store, net.records)\n"
+        "    t = L.Table(net.records, net.nvars)\n"
+        "    s = L.Store(values=net.store)\n"
+        "    r = L.fixpoint(t, s, mode=L.MODE_SWEEP)\n"
+        "    assert bool(r.is_bot) == bool(st.is_bot)\n"
+        "    assert st.is_bot or np.array_equal(s.read(), want)\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_config2_full_size(L, O, W):
     """BASELINE.json config 2 at full size (1M vars / 5M propagators): bit-exact against the oracle, and
     idempotence (a second fixpoint changes nothing and costs one iteration)."""

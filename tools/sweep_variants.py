@@ -22,7 +22,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         out[name] = dict(ms=float(np.mean(ms)), sweeps=r.sweeps, gded=r.deductions / np.mean(ms) / 1e6)
     print(json.dumps(out))
 else:
-    for rpt, minb in ((4, 2), (4, 3), (2, 3), (2, 4), (1, 4)):
+    for rpt, minb in ((2, 3), (1, 4), (11, 4), (11, 3), (12, 3), (12, 2)):
         env = dict(os.environ, LPC_RPT=str(rpt), LPC_MINB=str(minb))
         r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         print(rpt, minb, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:], flush=True)
