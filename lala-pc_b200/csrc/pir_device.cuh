@@ -70,20 +70,6 @@ LPC_HD int divop(int a, int op, int b) {
   return op == D_TDIV ? d.q : op == D_FDIV ? fdiv_of(d, b) : op == D_CDIV ? cdiv_of(d, b) : ediv_of(d, b);
 }
 
-// floor and ceiling of a / b through one float reciprocal, exact for |a|, |b| < 2^22 and b != 0: the estimate a * (1/b)
-// is within 1 of the quotient, the remainder test below corrects it. `rb` = 1.0f / b is shared by the caller between the
-// quotients that have the same divisor. An integer division costs ~25 instructions on the device, this ~10.
-struct FC { int f, c; };
-LPC_HD FC fcdiv_small(int a, int b, float rb) {
-  int q = (int)floorf((float)a * rb);
-  int r = a - q * b;
-  if(b > 0) { if(r < 0) { --q; r += b; } else if(r >= b) { ++q; r -= b; } }
-  else { if(r > 0) { --q; r += b; } else if(r <= b) { ++q; r -= b; } }
-  FC o; o.f = q; o.c = q + (r != 0);
-  return o;
-}
-LPC_HD bool small22(int v) { return v > -(1 << 22) && v < (1 << 22); }
-
 #define xl r1.lb
 #define xu r1.ub
 #define yl r2.lb
@@ -105,20 +91,6 @@ LPC_HD void mul_inv(const Itv& r1, Itv& r2, Itv& r3) {
   else if(xnz || zl > 0 || zu < 0) {
     if(xl == LPC_MINF || xu == LPC_INF || zl == LPC_MINF || zu == LPC_INF) return;
     if(r3.is_bot()) return;
-    if(small22(xl) && small22(xu) && small22(zl) && small22(zu) && zl != 0 && zu != 0) {   // the common case, see fcdiv_small
-      const float rl = 1.0f / (float)zl;
-      const FC a = fcdiv_small(xl, zl, rl), c = fcdiv_small(xu, zl, rl);
-      int lo = min(a.c, c.c), hi = max(a.f, c.f);
-      if(zu != zl) {
-        const float ru = 1.0f / (float)zu;
-        const FC b = fcdiv_small(xl, zu, ru), d = fcdiv_small(xu, zu, ru);
-        lo = min(lo, min(b.c, d.c));
-        hi = max(hi, max(b.f, d.f));
-      }
-      r2.lb = max(yl, lo);
-      r2.ub = min(yu, hi);
-      return;
-    }
     QR a = divqr(xl, zl), c = divqr(xu, zl);
     int lo = min(cdiv_of(a, zl), cdiv_of(c, zl));
     int hi = max(fdiv_of(a, zl), fdiv_of(c, zl));

@@ -65,32 +65,6 @@ void devhost_exhaustive(int sig, int lo, int hi, int* out) {
   }
 }
 
-// fcdiv_small against the integer division it replaces; returns the number of mismatches over n random pairs plus the
-// exhaustive square [-lim, lim]^2.
-long long devhost_fcdiv_check(unsigned long long seed, long long n, int lim) {
-  long long bad = 0;
-  auto chk = [&](int a, int b) {
-    if(b == 0) return;
-    FC g = fcdiv_small(a, b, 1.0f / (float)b);
-    QR d = divqr(a, b);
-    if(g.f != fdiv_of(d, b) || g.c != cdiv_of(d, b)) ++bad;
-  };
-  for(int a = -lim; a <= lim; ++a) for(int b = -lim; b <= lim; ++b) chk(a, b);
-  unsigned long long s = seed;
-  auto rnd = [&]() { s += 0x9E3779B97F4A7C15ull; unsigned long long z = s; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-                     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
-  const int M = (1 << 22) - 1;
-  for(long long i = 0; i < n; ++i) {
-    int a = (int)(rnd() % (2ull * M + 1)) - M, b = (int)(rnd() % (2ull * M + 1)) - M;
-    if(i & 1) b = (int)(rnd() % 2001) - 1000;          // small divisors
-    if((i & 7) == 3) a = b * ((int)(rnd() % 4001) - 2000) + ((int)(rnd() % 3) - 1);   // near exact multiples
-    if(!small22(a)) continue;
-    chk(a, b);
-  }
-  for(int a : {-M, -M + 1, -1, 0, 1, M - 1, M}) for(int b : {-M, -M + 1, -2, -1, 1, 2, M - 1, M}) chk(a, b);
-  return bad;
-}
-
 // ---- PC: the flat propagators of pc_device.cuh on the host --------------------------------------------------------
 struct HostAcc {
   int* d;

@@ -49,10 +49,3 @@ def test_device_ask_on_host_matches_oracle(devhost):
             got = devhost.devhost_ask(store.ctypes.data_as(ctypes.c_void_p), rec.ctypes.data_as(ctypes.c_void_p))
             assert bool(got) == O.pir_ask(store, rec), (name, store.tolist())
 
-
-def test_fast_division_matches_integer_division(devhost):
-    """mul_inv's float-reciprocal floor / ceiling division (pir_device.cuh: fcdiv_small) against the integer division it
-    replaces: every pair of [-300, 300]^2, 20M random pairs below 2^22 (small divisors, near-exact multiples), extremes."""
-    devhost.devhost_fcdiv_check.restype = ctypes.c_longlong
-    bad = devhost.devhost_fcdiv_check(ctypes.c_ulonglong(12345), ctypes.c_longlong(20_000_000), 300)
-    assert bad == 0
