@@ -175,6 +175,40 @@ int lpc_batch_flags(const lpc_batch* b, uint8_t* out);
  * lpc_batch_fixpoint: the payload of the one NCCL all-reduce of the multi-GPU driver. */
 void* lpc_batch_reduction_device_ptr(lpc_batch* b);
 
+/* ---- in-kernel search over the batch (snapshot / restore + branching next to the fixpoint) ---------
+ * Every store of the batch is the root of a depth-first search run by ONE thread block: propagate (the fixpoint above),
+ * then branch on the first non-singleton variable of `branch_vars` (input order) by bisection, lower half first; the
+ * right branch is a store snapshot (PIR::snapshot, pir.hpp:857-861) pushed on a per-block stack in device memory and
+ * restored (pir.hpp:863-870) on backtrack. A leaf (all branching variables fixed) is a solution iff every propagator is
+ * entailed (is_extractable, pir.hpp:873-884). The stores of the batch are the roots and are left untouched. Counts are
+ * schedule independent. A subproblem that would exceed max_depth snapshots or max_nodes nodes is abandoned and counted
+ * in n_incomplete. */
+typedef struct lpc_search_opts {
+  int64_t max_nodes;      /* per subproblem, 0 = unlimited */
+  int32_t max_depth;      /* snapshots per block stack (default 64) */
+  int32_t objective_var;  /* < 0: none; else best_bound = min over solutions of lb(objective_var) */
+  uint64_t stream;
+} lpc_search_opts;
+
+typedef struct lpc_search_result {
+  int64_t n_solutions;
+  int64_t n_nodes;          /* fixpoints computed */
+  int64_t n_fails;          /* nodes whose fixpoint is bot */
+  int64_t n_unknown_leaves; /* leaves with a propagator that is not entailed (branch_vars does not cover the model) */
+  int64_t n_incomplete;     /* subproblems abandoned at a limit */
+  int64_t sweeps_total;
+  int64_t deductions;
+  int32_t best_bound;       /* INT32_MAX if there is no solution or no objective */
+  int32_t max_depth_seen;
+  float device_ms;
+  int32_t reserved;
+} lpc_search_result;
+
+void lpc_search_default_opts(lpc_search_opts* o);
+/* per_store (may be NULL): n_stores x 6 int64 {solutions, nodes, fails, best, incomplete, unknown_leaves}. Synchronous. */
+int lpc_batch_search(lpc_batch* b, const int32_t* branch_vars, int32_t n_branch, const lpc_search_opts* o,
+                     lpc_search_result* r, int64_t* per_store);
+
 #ifdef __cplusplus
 }
 #endif

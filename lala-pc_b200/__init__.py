@@ -42,6 +42,21 @@ class FixpointResult(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class SearchOpts(ctypes.Structure):
+    _fields_ = [("max_nodes", ctypes.c_int64), ("max_depth", ctypes.c_int32), ("objective_var", ctypes.c_int32),
+                ("stream", ctypes.c_uint64)]
+
+
+class SearchResult(ctypes.Structure):
+    _fields_ = [("n_solutions", ctypes.c_int64), ("n_nodes", ctypes.c_int64), ("n_fails", ctypes.c_int64),
+                ("n_unknown_leaves", ctypes.c_int64), ("n_incomplete", ctypes.c_int64), ("sweeps_total", ctypes.c_int64),
+                ("deductions", ctypes.c_int64), ("best_bound", ctypes.c_int32), ("max_depth_seen", ctypes.c_int32),
+                ("device_ms", ctypes.c_float), ("reserved", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 class BatchResult(ctypes.Structure):
     _fields_ = [("n_bot", ctypes.c_int64), ("n_solution", ctypes.c_int64), ("n_unknown", ctypes.c_int64),
                 ("best_bound", ctypes.c_int32), ("max_sweeps_seen", ctypes.c_int32),
@@ -109,6 +124,8 @@ SIGNATURES = {
                                                ctypes.POINTER(BatchResult)]),
     "lpc_batch_flags": (ctypes.c_int, [_vp, _pu8]),
     "lpc_batch_reduction_device_ptr": (_vp, [_vp]),
+    "lpc_search_default_opts": (None, [ctypes.POINTER(SearchOpts)]),
+    "lpc_batch_search": (ctypes.c_int, [_vp, _vp, _i32, ctypes.POINTER(SearchOpts), ctypes.POINTER(SearchResult), _vp]),
     # include/lpc_pc.h
     "lpc_pc_table_create": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _pvp]),
     "lpc_pc_table_destroy": (ctypes.c_int, [_vp]),
@@ -417,6 +434,18 @@ class Batch:
     @property
     def reduction_device_ptr(self):
         return _L.lpc_batch_reduction_device_ptr(self._h)
+
+    def search(self, branch_vars, objective_var=-1, max_nodes=0, max_depth=64, stream=0, want_per_store=True):
+        """Depth-first search from every store of the batch (include/lpc.h: lpc_batch_search).
+        Returns (SearchResult, int64 [n_stores, 6] {solutions, nodes, fails, best, incomplete, unknown_leaves} or None)."""
+        bv = np.ascontiguousarray(branch_vars, dtype=np.int32)
+        o, r = SearchOpts(), SearchResult()
+        _L.lpc_search_default_opts(ctypes.byref(o))
+        o.max_nodes, o.max_depth, o.objective_var, o.stream = max_nodes, max_depth, objective_var, stream
+        per = np.zeros((self.n_stores, 6), dtype=np.int64) if want_per_store else None
+        _check(_L.lpc_batch_search(self._h, bv.ctypes.data, bv.shape[0], ctypes.byref(o), ctypes.byref(r),
+                                   per.ctypes.data if want_per_store else None))
+        return r, per
 
     def close(self):
         if getattr(self, "_h", None):

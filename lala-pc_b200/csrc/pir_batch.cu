@@ -13,6 +13,7 @@
 //   * per store: bot flag, all-entailed flag (the ask loop of is_extractable, pir.hpp:873-884), lb(objective);
 //     per batch: 4 x int64 reduction record, the payload of the single NCCL all-reduce of the multi-GPU driver.
 #include "lpc_internal.cuh"
+#include "smem_tma.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -26,73 +27,6 @@ struct BatchCtl {
   int max_sweeps_seen;
   int next_store;              // dynamic scheduler
 };
-
-// ---- PTX helpers: mbarrier + bulk async copies (TMA, 1-D) --------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-    "{\n\t.reg .pred p;\n\t"
-    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-    "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  while(!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// Issue a large global->shared copy as <= 32 KB bulk pieces (sizes are multiples of 16 by construction).
-__device__ __forceinline__ void bulk_g2s_chunked(char* dst, const char* src, unsigned bytes, unsigned long long* bar) {
-  for(unsigned o = 0; o < bytes; o += 32768u) bulk_g2s(dst + o, src + o, min(32768u, bytes - o), bar);
-}
-
-// Shared-state-space accessors with 32-bit addresses: the ring slot is selected at run time, so through generic
-// pointers the compiler falls back to generic LD / ATOM and 64-bit address arithmetic.
-__device__ __forceinline__ int2 lds_itv(unsigned addr) {
-  int2 v;
-  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ int lds_s32(unsigned addr) {
-  int v;
-  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ int lds_u8(unsigned addr) {
-  int v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void reds_max(unsigned addr, int v) { asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void reds_min(unsigned addr, int v) { asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-
-// Join into the shared-memory store (only called when something tightened or an operand was empty).
-__device__ __forceinline__ int commit_smem(unsigned addr, int2 old, const Itv& nw) {
-  int f = 0;
-  if(nw.lb > old.x) { reds_max(addr, nw.lb); f = 1; }
-  if(nw.ub < old.y) { reds_min(addr + 4, nw.ub); f = 1; }
-  if(f && nw.lb > nw.ub) f |= 2;
-  return f;
-}
 
 // Shared memory carve-up (dynamic): [mbarriers 64 B][store ring 2 x sbytes][table: x | y | z | op]
 template <bool HAS_DIV, bool TABLE_SMEM>
@@ -230,6 +164,193 @@ __global__ void k_pir_batch(TableDev t, int2* stores, int n_stores, int sbytes, 
     atomicAdd((unsigned long long*)&ctl->sweeps_total, (unsigned long long)a_sweeps);
     atomicAdd((unsigned long long*)&ctl->deductions, (unsigned long long)a_ded);
     atomicMax(&ctl->max_sweeps_seen, a_maxsw);
+  }
+}
+
+// ---- in-kernel search: propagate + branch on one store per block ------------------------------------------------------
+// snapshot / restore (pir.hpp:857-870) and branching moved next to the fixpoint, so that a
+// subproblem is SOLVED by its block instead of only propagated once. Depth-first, deterministic: the variable is the
+// first non-singleton of `bvars` (FlatZinc input_order), the value split is a bisection, lower half first
+// (indomain_split); a leaf is a store whose branching variables are all fixed - a solution iff every propagator is
+// entailed (is_extractable, pir.hpp:873-884). The right branch of every decision is a full store image pushed on a
+// per-block stack in global memory by one bulk copy (the device counterpart of snapshot()), popped back by another
+// (restore()). Node, failure and solution counts do not depend on the schedule because each node's fixpoint does not.
+struct SearchCtl {
+  long long n_solutions, n_nodes, n_fails, n_unknown_leaves, n_incomplete, sweeps_total, deductions;
+  long long best;      // min over solutions of lb(objective)
+  int max_depth_seen;
+  int next_store;
+};
+
+// One fixpoint of the store at shared address a_S (the loop of k_pir_batch). Returns bot; adds to sweeps.
+template <bool HAS_DIV, bool TABLE_SMEM>
+__device__ __forceinline__ bool block_fixpoint(const TableDev& t, const int2* S, unsigned a_S, const int* sx, const int* sy,
+                                               const int* sz, const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z,
+                                               unsigned a_op, volatile int* s_bot, long long& sweeps_acc) {
+  const int tid = threadIdx.x, nthr = blockDim.x, npad = (int)t.n_pad;
+  if(tid == 0) *s_bot = 0;
+  int f0 = 0;
+  for(int v = tid; v < t.nvars; v += nthr) { int2 d = S[v]; f0 |= d.x > d.y; }
+  bool bot = __syncthreads_or(f0) != 0;
+  bool changed = !bot && t.n > 0;
+  int sweeps = 0;
+  while(changed) {
+    int f = 0;
+    for(int i = tid; i < npad; i += nthr) {
+      int op, xi, yi, zi;
+      if(TABLE_SMEM) { op = lds_u8(a_op + i); xi = lds_s32(a_x + 4 * i); yi = lds_s32(a_y + 4 * i); zi = lds_s32(a_z + 4 * i); }
+      else { op = sop[i]; xi = sx[i]; yi = sy[i]; zi = sz[i]; }
+      const unsigned ax = a_S + 8u * xi, ay = a_S + 8u * yi, az = a_S + 8u * zi;
+      const int2 a = lds_itv(ax), bb = lds_itv(ay), c = lds_itv(az);
+      Itv r1(a.x, a.y), r2(bb.x, bb.y), r3(c.x, c.y);
+      deduce_regs<HAS_DIV>(op, r1, r2, r3);
+      const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > bb.x) | (r2.ub < bb.y) | (r3.lb > c.x) | (r3.ub < c.y)
+                      | (a.x > a.y) | (bb.x > bb.y) | (c.x > c.y);
+      if(slow) {
+        if((a.x > a.y) | (bb.x > bb.y) | (c.x > c.y)) f |= 2;
+        f |= commit_smem(ax, a, r1) | commit_smem(ay, bb, r2) | commit_smem(az, c, r3);
+      }
+    }
+    ++sweeps;
+    if(f & 2) *s_bot = 1;
+    const int any_chg = __syncthreads_or(f & 1);
+    bot |= *s_bot != 0;
+    changed = any_chg && !bot;
+  }
+  sweeps_acc += sweeps;
+  return bot;
+}
+
+// Shared memory carve-up (dynamic): [mbarriers + scalars 64 B][store sbytes][table: x | y | z | op]
+template <bool HAS_DIV, bool TABLE_SMEM>
+__global__ void k_pir_search(TableDev t, const int2* roots, int n_stores, int sbytes, int2* stack, int max_depth,
+                             const int* bvars, int nb, int objective_var, long long max_nodes, long long* per_store,
+                             SearchCtl* ctl) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);   // [0]: store, [2]: table
+  int* s_next = reinterpret_cast<int*>(smem + 32);
+  volatile int* s_bot = reinterpret_cast<volatile int*>(smem + 36);
+  int* s_idx = reinterpret_cast<int*>(smem + 40);
+  int2* S = reinterpret_cast<int2*>(smem + 64);
+  const int* sx = t.x; const int* sy = t.y; const int* sz = t.z; const uint8_t* sop = t.op;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int npad = (int)t.n_pad;
+  const size_t store_stride = (size_t)t.nvars;
+  int2* my_stack = stack + (size_t)blockIdx.x * max_depth * store_stride;
+  if(tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
+  __syncthreads();
+  if(TABLE_SMEM) {
+    char* tb = reinterpret_cast<char*>(smem + 64 + (size_t)sbytes);
+    if(tid == 0) {
+      mbar_expect_tx(&bars[2], (unsigned)(npad * 13));
+      bulk_g2s_chunked(tb, (const char*)t.x, npad * 4, &bars[2]);
+      bulk_g2s_chunked(tb + (size_t)npad * 4, (const char*)t.y, npad * 4, &bars[2]);
+      bulk_g2s_chunked(tb + (size_t)npad * 8, (const char*)t.z, npad * 4, &bars[2]);
+      bulk_g2s_chunked(tb + (size_t)npad * 12, (const char*)t.op, npad, &bars[2]);
+    }
+    sx = reinterpret_cast<const int*>(tb);
+    sy = reinterpret_cast<const int*>(tb + (size_t)npad * 4);
+    sz = reinterpret_cast<const int*>(tb + (size_t)npad * 8);
+    sop = reinterpret_cast<const uint8_t*>(tb + (size_t)npad * 12);
+    mbar_wait(&bars[2], 0);
+  }
+  const unsigned a_x = smem_u32(sx), a_y = smem_u32(sy), a_z = smem_u32(sz), a_op = smem_u32(sop);
+  const unsigned a_S = smem_u32(S);
+  unsigned phase = 0;
+  long long a_sol = 0, a_nodes = 0, a_fails = 0, a_unk = 0, a_inc = 0, a_sweeps = 0, a_best = LPC_INF;
+  int a_maxd = 0;
+  int cur = blockIdx.x < n_stores ? blockIdx.x : -1;
+  while(cur >= 0) {
+    // restore(root): the subproblem's store
+    fence_async_smem();
+    __syncthreads();
+    if(tid == 0) {
+      mbar_expect_tx(&bars[0], (unsigned)sbytes);
+      bulk_g2s_chunked((char*)S, (const char*)(roots + cur * store_stride), sbytes, &bars[0]);
+    }
+    mbar_wait(&bars[0], phase); phase ^= 1;
+    long long sol = 0, nodes = 0, fails = 0, unk = 0, sweeps = 0, best = LPC_INF;
+    int depth = 0, incomplete = 0;
+    while(true) {
+      const bool bot = block_fixpoint<HAS_DIV, TABLE_SMEM>(t, S, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, s_bot, sweeps);
+      ++nodes;
+      bool backtrack = false;
+      if(bot) { ++fails; backtrack = true; }
+      else {
+        // first non-singleton branching variable
+        if(tid == 0) *s_idx = 0x7fffffff;
+        __syncthreads();
+        for(int i = tid; i < nb; i += nthr) { const int2 d = S[bvars[i]]; if(d.x < d.y) { atomicMin(s_idx, i); break; } }
+        __syncthreads();
+        const int idx = *s_idx;
+        if(idx == 0x7fffffff) {   // leaf: is_extractable
+          int ok = 1;
+          for(int i = tid; i < npad && ok; i += nthr) {
+            const int2 a = S[sx[i]], bb = S[sy[i]], c = S[sz[i]];
+            ok = ask_regs(sop[i], Itv(a.x, a.y), Itv(bb.x, bb.y), Itv(c.x, c.y));
+          }
+          if(__syncthreads_and(ok)) { ++sol; if(objective_var >= 0) best = min(best, (long long)S[objective_var].x); }
+          else ++unk;
+          backtrack = true;
+        }
+        else if(depth >= max_depth || (max_nodes > 0 && nodes >= max_nodes)) { incomplete = 1; break; }
+        else {
+          // snapshot of the right branch [mid + 1, ub] goes on the stack, the block continues with [lb, mid]
+          const int v = bvars[idx];
+          const int2 d = S[v];
+          const int mid = (int)((long long)d.x + (((long long)d.y - (long long)d.x) >> 1));
+          __syncthreads();                       // everyone has read d
+          if(tid == 0) S[v] = make_int2(mid + 1, d.y);
+          fence_async_smem();
+          __syncthreads();
+          if(tid == 0) {
+            char* dst = (char*)(my_stack + (size_t)depth * store_stride);
+            for(int o = 0; o < sbytes; o += 32768) bulk_s2g(dst + o, (char*)S + o, min(32768, sbytes - o));
+            bulk_commit();
+            bulk_wait_read0();                   // the copy engine has read the image; it may change again
+            S[v] = make_int2(d.x, mid);
+          }
+          ++depth;
+          a_maxd = max(a_maxd, depth);
+          __syncthreads();
+        }
+      }
+      if(backtrack) {
+        if(depth == 0) break;
+        --depth;
+        fence_async_smem();                      // order this block's reads of S before the copy engine overwrites it
+        __syncthreads();
+        if(tid == 0) {                           // restore(): pop the most recent right branch
+          bulk_wait0();                          // its write has completed
+          mbar_expect_tx(&bars[0], (unsigned)sbytes);
+          bulk_g2s_chunked((char*)S, (const char*)(my_stack + (size_t)depth * store_stride), sbytes, &bars[0]);
+        }
+        mbar_wait(&bars[0], phase); phase ^= 1;
+      }
+    }
+    if(tid == 0) {
+      long long* ps = per_store + (size_t)cur * 6;
+      ps[0] = sol; ps[1] = nodes; ps[2] = fails; ps[3] = best; ps[4] = incomplete; ps[5] = unk;
+      a_sol += sol; a_nodes += nodes; a_fails += fails; a_unk += unk; a_inc += incomplete; a_sweeps += sweeps;
+      a_best = min(a_best, best);
+      int nx = atomicAdd(&ctl->next_store, 1);
+      *s_next = nx < n_stores ? nx : -1;
+    }
+    __syncthreads();
+    cur = *s_next;
+    __syncthreads();
+  }
+  if(tid == 0) {
+    bulk_wait0();
+    atomicAdd((unsigned long long*)&ctl->n_solutions, (unsigned long long)a_sol);
+    atomicAdd((unsigned long long*)&ctl->n_nodes, (unsigned long long)a_nodes);
+    atomicAdd((unsigned long long*)&ctl->n_fails, (unsigned long long)a_fails);
+    atomicAdd((unsigned long long*)&ctl->n_unknown_leaves, (unsigned long long)a_unk);
+    atomicAdd((unsigned long long*)&ctl->n_incomplete, (unsigned long long)a_inc);
+    atomicAdd((unsigned long long*)&ctl->sweeps_total, (unsigned long long)a_sweeps);
+    atomicAdd((unsigned long long*)&ctl->deductions, (unsigned long long)(a_sweeps * t.n));
+    atomicMin(&ctl->best, a_best);
+    atomicMax(&ctl->max_depth_seen, a_maxd);
   }
 }
 
@@ -463,6 +584,76 @@ int lpc_batch_flags(const lpc_batch* b, uint8_t* out) {
   LPC_REQUIRE(b && (out || b->n_stores == 0), "null argument");
   if(b->n_stores) LPC_CUDA(cudaMemcpy(out, b->d_flags, b->n_stores, cudaMemcpyDeviceToHost));
   return LPC_OK;
+}
+
+int lpc_batch_search(lpc_batch* b, const int32_t* branch_vars, int32_t n_branch, const lpc_search_opts* o,
+                     lpc_search_result* r, int64_t* per_store) {
+  LPC_REQUIRE(b && (branch_vars || n_branch == 0) && n_branch >= 0, "bad argument");
+  lpc_search_opts def;
+  if(!o) { lpc_search_default_opts(&def); o = &def; }
+  LPC_REQUIRE(o->objective_var < b->nvars, "objective variable out of range");
+  LPC_REQUIRE(o->max_depth >= 1, "max_depth must be at least 1");
+  for(int i = 0; i < n_branch; ++i) LPC_REQUIRE(branch_vars[i] >= 0 && branch_vars[i] < b->nvars, "branching variable out of range");
+  const lpc_table* t = b->table;
+  cudaStream_t st = (cudaStream_t)o->stream;
+  int dev = 0, sms = 0, optin = 0;
+  LPC_CUDA(cudaGetDevice(&dev));
+  LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  LPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t base = 64 + (size_t)b->sbytes, tbl = (size_t)t->dev.n_pad * 13;
+  if(base > (size_t)optin) { set_error("lpc_batch_search: a store of %d variables does not fit shared memory", b->nvars); return LPC_ERR_UNSUPPORTED; }
+  const bool table_smem = base + tbl <= (size_t)optin;
+  const size_t smem = table_smem ? base + tbl : base;
+  typedef void (*search_kernel_t)(TableDev, const int2*, int, int, int2*, int, const int*, int, int, long long, long long*, SearchCtl*);
+  search_kernel_t k = t->has_div ? (table_smem ? k_pir_search<true, true> : k_pir_search<true, false>)
+                                 : (table_smem ? k_pir_search<false, true> : k_pir_search<false, false>);
+  LPC_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int threads = (int)std::min<long long>(1024, std::max<long long>(32, (t->dev.n_pad + 31) / 32 * 32));
+  int per_sm = 0;
+  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
+  if(per_sm < 1 && threads > 256) { threads = 256; LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem)); }
+  LPC_REQUIRE(per_sm > 0, "search kernel does not fit on an SM");
+  const int grid = std::max(1, std::min(b->n_stores, sms * per_sm));
+  // scratch: snapshot stacks, branching order, per-store records, control block
+  int2* d_stack = nullptr; int* d_bv = nullptr; long long* d_ps = nullptr; SearchCtl* d_ctl = nullptr;
+  LPC_CUDA(cudaMalloc((void**)&d_stack, std::max<size_t>((size_t)grid * o->max_depth * b->nvars * 8, 16)));
+  LPC_CUDA(cudaMalloc((void**)&d_bv, std::max<size_t>((size_t)n_branch * 4, 16)));
+  LPC_CUDA(cudaMalloc((void**)&d_ps, std::max<size_t>((size_t)b->n_stores * 6 * 8, 16)));
+  LPC_CUDA(cudaMalloc((void**)&d_ctl, sizeof(SearchCtl)));
+  SearchCtl h;
+  memset(&h, 0, sizeof(h));
+  h.best = LPC_INF; h.next_store = grid;
+  if(n_branch) LPC_CUDA(cudaMemcpyAsync(d_bv, branch_vars, (size_t)n_branch * 4, cudaMemcpyHostToDevice, st));
+  LPC_CUDA(cudaMemcpyAsync(d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  LPC_CUDA(cudaEventRecord(b->ev0, st));
+  if(b->n_stores > 0) {
+    k<<<grid, threads, smem, st>>>(t->dev, b->d, b->n_stores, b->sbytes, d_stack, o->max_depth, d_bv, n_branch, o->objective_var,
+                                  (long long)o->max_nodes, d_ps, d_ctl);
+    g_launches++;
+    LPC_CUDA(cudaGetLastError());
+  }
+  LPC_CUDA(cudaEventRecord(b->ev1, st));
+  LPC_CUDA(cudaMemcpyAsync(&h, d_ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+  if(per_store && b->n_stores) LPC_CUDA(cudaMemcpyAsync(per_store, d_ps, (size_t)b->n_stores * 6 * 8, cudaMemcpyDeviceToHost, st));
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d_stack); cudaFree(d_bv); cudaFree(d_ps); cudaFree(d_ctl);
+  LPC_CUDA(e);
+  if(r) {
+    memset(r, 0, sizeof(*r));
+    r->n_solutions = h.n_solutions; r->n_nodes = h.n_nodes; r->n_fails = h.n_fails; r->n_unknown_leaves = h.n_unknown_leaves;
+    r->n_incomplete = h.n_incomplete; r->sweeps_total = h.sweeps_total; r->deductions = h.deductions;
+    r->best_bound = (int32_t)h.best; r->max_depth_seen = h.max_depth_seen;
+    float ms = 0;
+    LPC_CUDA(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    r->device_ms = ms;
+  }
+  return LPC_OK;
+}
+
+void lpc_search_default_opts(lpc_search_opts* o) {
+  if(!o) return;
+  memset(o, 0, sizeof(*o));
+  o->max_nodes = 0; o->max_depth = 64; o->objective_var = -1;
 }
 
 } // extern "C"

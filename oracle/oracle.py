@@ -144,6 +144,26 @@ def pir_batch_fixpoint(stores, records, threads=1):
     return s, flags, sweeps, int(ded.value), float(sec)
 
 
+SEARCH_COLS = ("solutions", "nodes", "fails", "best", "incomplete", "unknown_leaves")
+
+
+def pir_search(roots, records, branch_vars, objective_var=-1, max_nodes=0, max_depth=64, threads=1):
+    """Depth-first search (input order, bisection) around the Gauss-Seidel fixpoint, one tree per root store
+    [n_stores, nvars, 2]. Returns int64 [n_stores, 6] with the columns SEARCH_COLS."""
+    s = np.ascontiguousarray(roots, dtype=np.int32)
+    assert s.ndim == 3 and s.shape[2] == 2
+    r = _recs(records)
+    bv = np.ascontiguousarray(branch_vars, dtype=np.int32)
+    out = np.zeros((s.shape[0], 6), dtype=np.int64)
+    f = lib().lpco_pir_search
+    f.restype = None
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                  ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+    f(s.ctypes.data, s.shape[0], s.shape[1], r.ctypes.data, r.shape[0], bv.ctypes.data, bv.shape[0], objective_var,
+      max_nodes, max_depth, threads, out.ctypes.data)
+    return out
+
+
 def div(a, op, b):
     return int(lib().lpco_div(a, op, b))
 

@@ -588,6 +588,67 @@ double lpco_pir_batch_fixpoint(int32_t* lbub, int32_t n_stores, int32_t nvars, c
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Depth-first search around the fixpoint with snapshot / restore (pir.hpp:857-870): the checker of lpc_batch_search.
+// Variable = first non-singleton of `bvars` (input order), split = bisection with the lower half first, leaf = all
+// branching variables fixed, solution = leaf on which every propagator is entailed (is_extractable, pir.hpp:873-884).
+// The search strategy itself is lala-core's (un-vendored SearchTree / split strategies): PARITY UNPINNED for the order of
+// exploration; the counts checked here do not depend on it as long as the tree is explored completely.
+// out: n_stores x 6 int64 {solutions, nodes, fails, best, incomplete, unknown_leaves}. roots are not modified.
+void lpco_pir_search(const int32_t* roots, int32_t n_stores, int32_t nvars, const int32_t* recs, int64_t n,
+                     const int32_t* bvars, int32_t nb, int32_t objective_var, int64_t max_nodes, int32_t max_depth,
+                     int32_t threads, int64_t* out) {
+  const Rec* r = reinterpret_cast<const Rec*>(recs);
+  if(threads < 1) threads = 1;
+  auto work = [&](int tid) {
+    std::vector<int32_t> cur(2 * (size_t)nvars);
+    std::vector<std::vector<int32_t>> stack;
+    for(int64_t k = tid; k < n_stores; k += threads) {
+      std::copy(roots + k * 2 * (int64_t)nvars, roots + (k + 1) * 2 * (int64_t)nvars, cur.begin());
+      stack.clear();
+      int64_t sol = 0, nodes = 0, fails = 0, unk = 0, best = INT32_MAX, incomplete = 0;
+      while(true) {
+        Store s{cur.data(), nvars, scan_bot(cur.data(), nvars)};
+        Stats st;
+        gauss_seidel(s, r, n, 1, 0, &st);
+        ++nodes;
+        bool backtrack = false;
+        if(s.bot) { ++fails; backtrack = true; }
+        else {
+          int idx = -1;
+          for(int i = 0; i < nb; ++i) if(cur[2 * bvars[i]] < cur[2 * bvars[i] + 1]) { idx = i; break; }
+          if(idx < 0) {
+            bool all = true;
+            for(int64_t i = 0; i < n && all; ++i) all = ask(s, r[i]);
+            if(all) { ++sol; if(objective_var >= 0 && cur[2 * objective_var] < best) best = cur[2 * objective_var]; }
+            else ++unk;
+            backtrack = true;
+          }
+          else if((int)stack.size() >= max_depth || (max_nodes > 0 && nodes >= max_nodes)) { incomplete = 1; break; }
+          else {
+            const int v = bvars[idx];
+            const int64_t lb = cur[2 * v], ub = cur[2 * v + 1];
+            const int32_t mid = (int32_t)(lb + ((ub - lb) >> 1));
+            stack.push_back(cur);                       // snapshot of the right branch
+            stack.back()[2 * v] = mid + 1;
+            cur[2 * v + 1] = mid;
+          }
+        }
+        if(backtrack) {
+          if(stack.empty()) break;
+          cur = stack.back();                           // restore
+          stack.pop_back();
+        }
+      }
+      int64_t* o = out + k * 6;
+      o[0] = sol; o[1] = nodes; o[2] = fails; o[3] = best; o[4] = incomplete; o[5] = unk;
+    }
+  };
+  std::vector<std::thread> th;
+  for(int t = 1; t < threads; ++t) th.emplace_back(work, t);
+  work(0);
+  for(auto& t : th) t.join();
+}
+
 // battery division helpers, exported for the division known-answer tests.
 int32_t lpco_div(int32_t a, int32_t op, int32_t b) { return divop(a, op, b); }
 
