@@ -162,7 +162,7 @@ def own_single(args, rank):
     value = float(np.sum(ded)) / (total_ms * 1e-3)
     # latency of the other modes (same input, untimed warm-up then best of 3)
     latency = {"sweep_ms": float(np.mean(dev_ms)), "sweeps": results[0]["sweeps"]}
-    for mname, m in (("handover", dict(mode=L.MODE_AUTO, switch_div=128)), ("worklist", dict(mode=L.MODE_WORKLIST))):
+    for mname, m in (("auto", dict(mode=L.MODE_AUTO)), ("worklist", dict(mode=L.MODE_WORKLIST))):
         best = None
         for _ in range(4):
             s = L.Store(values=net.store)
@@ -356,6 +356,39 @@ def own_pc(args, cpu=True):
     return out
 
 
+def own_search(args, cpu=True, n_stores=4096, max_nodes=64):
+    """the config-4 model, every EPS subproblem searched depth-first in its block (propagate,
+    branch by bisection on the widest variables, snapshot / restore on the device) under a node budget."""
+    import lala_pc_b200 as L
+    from lala_pc_b200 import workloads as W
+    from lala_pc_b200 import sharding
+    net, table, root, dec, obj = build_c4()
+    dec = dec[:sharding.decision_bits(1)]
+    width = root[:, 1].astype(np.int64) - root[:, 0]
+    bv = [int(v) for v in np.argsort(-width, kind="stable")[:64]]
+    batch = L.Batch(table, n_stores)
+    batch.init_split(root, dec, 0)
+    best = None
+    for _ in range(4):
+        r, _ = batch.search(bv, objective_var=obj, max_nodes=max_nodes, max_depth=48, want_per_store=False)
+        best = r if best is None or r.device_ms < best.device_ms else best
+    out = {"workload": "config-4 model, %d EPS subproblems, DFS with a budget of %d nodes each" % (n_stores, max_nodes),
+           "ms": best.device_ms, "nodes": int(best.n_nodes), "solutions": int(best.n_solutions), "fails": int(best.n_fails),
+           "nodes_per_s": best.n_nodes / (best.device_ms * 1e-3), "value": best.deductions / (best.device_ms * 1e-3), "unit": UNIT}
+    if cpu:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        sample = 256
+        stores = batch.read(0, sample)
+        t0 = time.perf_counter()
+        want = O.pir_search(stores, net.records, bv, objective_var=obj, max_nodes=max_nodes, max_depth=48, threads=cores)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"nodes_per_s": float(want[:, 1].sum()) / dt, "cores": cores, "kind": "port",
+                               "sample": "%d of the %d subproblems" % (sample, n_stores)}
+    batch.close()
+    return out
+
+
 def cpu_baseline_single(net, max_seconds=30.0):
     """The oracle's Gauss-Seidel fixpoint (restated reference CPU path) on the same network, 1 thread."""
     from oracle import oracle as O
@@ -469,6 +502,7 @@ def main():
         if args.workload == "c2" and args.scale == 1.0 and not args.no_pc:
             l0 = L.launch_count()
             line["pc"] = own_pc(args, cpu=not args.no_cpu_baseline)
+            line["search"] = own_search(args, cpu=not args.no_cpu_baseline)
             line["gpu_launches"] += L.launch_count() - l0
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(net)

@@ -97,15 +97,16 @@ int lpc_store_is_top(const lpc_store* s, int* out);
 
 /* ---- the hot path: one fixpoint (GaussSeidelIteration::fixpoint(n, deduce) call sites:
  *      tests/pir_test.cpp:60-62, 82-86; bound_consistency_test.hpp:36-39) ---------------------------------- */
-#define LPC_MODE_AUTO 0      /* dense sweeps, switching to the change-driven worklist when few vars change */
+#define LPC_MODE_AUTO 0      /* change-driven: dense sweeps that skip 64-record groups none of whose variables changed, once
+                                a sweep changes at most 1/d of the groups (d = opts.reserved, default 8) */
 #define LPC_MODE_SWEEP 1     /* dense: every sweep evaluates every propagator */
-#define LPC_MODE_WORKLIST 2  /* change-driven from the first iteration on */
+#define LPC_MODE_WORKLIST 2  /* record-granular worklist from the second iteration on */
 
 typedef struct lpc_fixpoint_opts {
   int32_t mode;          /* LPC_MODE_* */
   int32_t max_sweeps;    /* 0 = unlimited */
   int32_t stop_on_bot;   /* 1 (default contract): stop at the first sweep that observes an empty variable */
-  int32_t reserved;
+  int32_t reserved;      /* LPC_MODE_AUTO: hand-over divisor d (0 = default) */
   uint64_t stream;       /* cudaStream_t to enqueue on (0 = the default stream) */
 } lpc_fixpoint_opts;
 

@@ -3,15 +3,16 @@
 // A sweep of the fixpoint ends with "did any block tighten a bound / see an empty variable" and a barrier. Doing that
 // with a flag word plus cooperative_groups' grid.sync() costs four dependent L2 round trips per sweep (flag atomic,
 // barrier atomic, barrier poll, flag read); small networks then spend most of a sweep there. Here the arrival IS the
-// vote: one 64-bit atomicAdd per block adds 1 to the arrival count (bits 0-19) and, if the block voted so, 1 to the
-// `changed` count (bits 20-39) and to the `bot` count (bits 40-59); the value polled for the barrier already holds the
+// vote: one 64-bit atomicAdd per block adds 1 to the arrival count (bits 0-15), the block's `changed` count to bits
+// 16-43 (1 per block for a plain vote; the number of record groups it changed for the change-driven kernel) and, if the
+// block saw an empty variable, 1 to the `bot` count (bits 44-63); the value polled for the barrier already holds the
 // grid's verdict. Three words rotate: while barrier k is in use, block 0 clears the word of barrier k + 1, which nobody
 // can touch before block 0 itself has arrived at barrier k. Requires all blocks co-resident (cooperative launch).
 #pragma once
 
 namespace lpc {
 
-struct GridVote { bool changed, bot; };
+struct GridVote { bool changed, bot; unsigned long long n_changed; };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
   unsigned long long v;
@@ -20,27 +21,35 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 }
 
 // words: 3 x u64 in global memory, zero at launch. `sweep` counts barriers from 0. Every thread of every block calls it.
-__device__ __forceinline__ GridVote grid_vote_barrier(unsigned long long* words, int sweep, bool changed, bool bot,
-                                                      unsigned long long* smem_slot) {
+// `block_changed` is block-uniform (already reduced over the block): how much this block adds to the changed count.
+__device__ __forceinline__ GridVote grid_count_barrier(unsigned long long* words, int sweep, unsigned block_changed,
+                                                       bool any_bot, unsigned long long* smem_slot) {
   const int slot = sweep % 3;
-  const bool any_changed = __syncthreads_or(changed);   // also orders this block's joins before the arrival below
-  const bool any_bot = __syncthreads_or(bot);
+  __syncthreads();                                       // orders this block's joins before the arrival below
   if(threadIdx.x == 0) {
     if(blockIdx.x == 0) words[(sweep + 1) % 3] = 0ull;
     __threadfence();
-    const unsigned long long add = 1ull | (any_changed ? 1ull << 20 : 0ull) | (any_bot ? 1ull << 40 : 0ull);
+    const unsigned long long add = 1ull | ((unsigned long long)block_changed << 16) | (any_bot ? 1ull << 44 : 0ull);
     unsigned long long v = atomicAdd(&words[slot], add) + add;
     const volatile unsigned long long* w = &words[slot];
-    while((v & 0xfffffull) != gridDim.x) v = *w;   // plain polling; the fence below is the acquire (and drops stale L1 lines)
+    while((v & 0xffffull) != gridDim.x) v = *w;   // plain polling; the fence below is the acquire (and drops stale L1 lines)
     __threadfence();
     *smem_slot = v;
   }
   __syncthreads();
   const unsigned long long v = *smem_slot;
   GridVote r;
-  r.changed = ((v >> 20) & 0xfffffull) != 0;
-  r.bot = (v >> 40) != 0;
+  r.n_changed = (v >> 16) & 0xfffffffull;
+  r.changed = r.n_changed != 0;
+  r.bot = (v >> 44) != 0;
   return r;
+}
+
+__device__ __forceinline__ GridVote grid_vote_barrier(unsigned long long* words, int sweep, bool changed, bool bot,
+                                                      unsigned long long* smem_slot) {
+  const bool any_changed = __syncthreads_or(changed);
+  const bool any_bot = __syncthreads_or(bot);
+  return grid_count_barrier(words, sweep, any_changed ? 1u : 0u, any_bot, smem_slot);
 }
 
 } // namespace lpc

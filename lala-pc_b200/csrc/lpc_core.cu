@@ -281,7 +281,7 @@ int lpc_store_wrap_device(void* device_ptr, int32_t nvars, lpc_store** out) {
 int lpc_store_destroy(lpc_store* s) {
   if(!s) return LPC_OK;
   if(s->owning) cudaFree(s->d);
-  cudaFree(s->wl_stamp); cudaFree(s->wl_q0); cudaFree(s->wl_q1); cudaFree(s->wl_vmark);
+  cudaFree(s->wl_stamp); cudaFree(s->wl_q0); cudaFree(s->wl_q1); cudaFree(s->wl_vmark); cudaFree(s->d_dirty);
   cudaFree(s->d_ctl);
   if(s->h_ctl) cudaFreeHost(s->h_ctl);
   if(s->ev0) cudaEventDestroy(s->ev0);

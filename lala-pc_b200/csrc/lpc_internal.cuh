@@ -67,6 +67,7 @@ struct lpc_store;
 struct lpc_win_plan;                                   // pir_window.cu
 void lpc_win_plan_free(lpc_win_plan* p);
 int lpc_win_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, int* used);
+int lpc_dirty_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o);   // pir_dirty.cu
 struct lpc_table {
   int device = 0;
   std::vector<lpc_bytecode> host;   // the caller's records, caller's order (load_deduce)
@@ -84,6 +85,8 @@ struct lpc_table {
   int sm_count = 0;
   size_t smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin
   lpc_store* host_store = nullptr;  // device staging store of lpc_fixpoint_host
+  bool dirty_ready = false;         // occupancy of the change-driven kernel (pir_dirty.cu)
+  int dirty_blocks_per_sm[2] = {0, 0};
   bool win_plan_tried = false;      // shared-memory window plan of pir_window.cu (built on first dense launch)
   lpc_win_plan* win_plan = nullptr;
 };
@@ -101,4 +104,6 @@ struct lpc_store {
   // worklist scratch (allocated on first use): enqueue stamps, two record queues, changed-variable marks
   int* wl_stamp = nullptr; int* wl_q0 = nullptr; int* wl_q1 = nullptr; int* wl_vmark = nullptr;
   long long wl_n = 0; int wl_nvars = 0;
+  // group byte maps of the change-driven kernel (pir_dirty.cu)
+  unsigned char* d_dirty = nullptr; long long dirty_cap = 0;
 };

@@ -1,0 +1,214 @@
+// pir_dirty.cu — the change-driven single-store fixpoint (LPC_MODE_AUTO): dense sweeps that learn to skip (sm_100a).
+//
+// BASELINE.json's north_star asks for "an optional change-driven worklist so only propagators touching changed
+// variables are re-run". A record-granular queue (LPC_MODE_WORKLIST, pir_fixpoint.cu) pays an atomicExch per enqueued
+// record and gives up the streaming table scan; on config 2 it runs 4x fewer deductions and is still slower than dense
+// sweeps. This kernel keeps the dense sweep's shape - same partition, same coalesced record loads, same rules - and
+// makes whole 64-record GROUPS skippable:
+//   * while many groups change per sweep (the first sweeps) it is the dense kernel: no bookkeeping at all;
+//   * once a sweep changes at most 1/8 of the groups, the next sweep still evaluates everything but every tightening of
+//     a variable v also marks the groups of v's incident records (var -> records CSR, built by lpc_table_create) in a
+//     byte map for the following sweep;
+//   * from then on a warp first reads the flags of its groups (one coalesced byte load per 32 iterations) and only
+//     evaluates flagged groups, marking as it tightens. Three byte maps rotate: read, write, being cleared.
+// Invariant: a change of v after the last evaluation of a record on v always flags that record's group for the next
+// sweep (also when the evaluation read a stale L1 copy), so at the sweep that changes nothing every record has been
+// evaluated on the final value of its variables: the store is the common fixpoint, the same as Gauss-Seidel's
+// (DESIGN.md §2). Sweeps end in the count-carrying grid barrier of grid_barrier.cuh.
+#include "lpc_internal.cuh"
+#include "grid_barrier.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace lpc {
+
+constexpr int DTPB = 256;
+constexpr int D_MAX_SEG = 16;
+struct DSeg { int nseg; int u[D_MAX_SEG + 1]; };   // opcode segments in units of 2 records
+
+template <bool HAS_DIV>
+__global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, DSeg seg, FixCtl* ctl, unsigned char* dmap,
+                                                       int n_groups, int map_stride, unsigned switch_groups, int max_sweeps,
+                                                       int stop_on_bot) {
+  __shared__ unsigned long long s_vote;
+  __shared__ unsigned s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long gtid = blockIdx.x * (long long)DTPB + tid;
+  const long long gthreads = (long long)gridDim.x * DTPB;
+  int nbar = 0;
+  bool bot;
+  {
+    int f = 0;
+    for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = store[i]; f |= v.x > v.y; }
+    for(long long i = gtid; i < 3LL * map_stride; i += gthreads) dmap[i] = 0;
+    bot = grid_vote_barrier(ctl->bar, nbar++, false, f != 0, &s_vote).bot;
+  }
+  int sweeps = 0, dense = 0;
+  bool any_changed = false;
+  unsigned long long deductions = 0;
+  bool done = (bot && stop_on_bot) || t.n == 0;
+  int phase = 0;   // 0: dense, no marking; 1: dense + marking; 2: flagged groups only + marking
+  while(!done) {
+    const unsigned char* dcur = dmap + (size_t)(sweeps % 3) * map_stride;
+    unsigned char* dnext = phase ? dmap + (size_t)((sweeps + 1) % 3) * map_stride : nullptr;
+    if(phase) {   // the map of the sweep after next: nobody reads or writes it during this sweep
+      unsigned char* dclr = dmap + (size_t)((sweeps + 2) % 3) * map_stride;
+      for(long long i = gtid * 16; i < map_stride; i += gthreads * 16) *reinterpret_cast<uint4*>(dclr + i) = make_uint4(0, 0, 0, 0);
+    }
+    if(tid == 0) s_cnt = 0;
+    __syncthreads();
+    int f = 0;
+    unsigned my_groups = 0, my_evals = 0;
+    for(int s = 0; s < seg.nseg; ++s) {
+      // this block's contiguous share of the segment, cut at group boundaries (32 units = 64 records)
+      const long long s0 = seg.u[s], s1 = seg.u[s + 1], len = s1 - s0;
+      long long b0 = s0 + len * blockIdx.x / gridDim.x, b1 = s0 + len * (blockIdx.x + 1) / gridDim.x;
+      b0 = blockIdx.x == 0 ? s0 : max(s0, b0 & ~31LL);
+      b1 = blockIdx.x == gridDim.x - 1 ? s1 : max(s0, b1 & ~31LL);
+      const int u0 = (int)b0, u1 = (int)b1;
+      if(u0 >= u1) continue;
+      const int a0 = u0 & ~31;
+      const int niter = (u1 - a0 + DTPB - 1) / DTPB;
+      for(int kb = 0; kb < niter; kb += 32) {
+        unsigned need = 0xffffffffu;
+        if(phase == 2) {
+          const int k = kb + lane;
+          const int g = (a0 + warp * 32 + k * DTPB) >> 5;
+          const int fl = (k < niter && g < n_groups) ? dcur[g] : 0;
+          need = __ballot_sync(0xffffffffu, fl != 0);
+        }
+        const int kend = min(niter, kb + 32);
+        for(int k = kb; k < kend; ++k) {
+          if(!((need >> (k - kb)) & 1u)) continue;
+          const int u = a0 + tid + k * DTPB;
+          int g1 = 0;
+          int cv[6] = {-1, -1, -1, -1, -1, -1};   // variables this lane tightened (2 records x 3 operands)
+          if(u >= u0 && u < u1) {
+            const uchar2 o = reinterpret_cast<const uchar2*>(t.op)[u];
+            const int2 X = reinterpret_cast<const int2*>(t.x)[u], Y = reinterpret_cast<const int2*>(t.y)[u],
+                       Z = reinterpret_cast<const int2*>(t.z)[u];
+            const int2 a0v = store[X.x], b0v = store[Y.x], c0v = store[Z.x];
+            const int2 a1v = store[X.y], b1v = store[Y.y], c1v = store[Z.y];
+#pragma unroll
+            for(int h = 0; h < 2; ++h) {
+              const int op = h ? o.y : o.x, xi = h ? X.y : X.x, yi = h ? Y.y : Y.x, zi = h ? Z.y : Z.x;
+              const int2 a = h ? a1v : a0v, b = h ? b1v : b0v, c = h ? c1v : c0v;
+              Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
+              deduce_regs<HAS_DIV>(op, r1, r2, r3);
+              const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > b.x) | (r2.ub < b.y) | (r3.lb > c.x) | (r3.ub < c.y)
+                              | (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
+              if(slow) {
+                if((a.x > a.y) | (b.x > b.y) | (c.x > c.y)) g1 |= 2;
+#pragma unroll
+                for(int w = 0; w < 3; ++w) {
+                  const int v = w == 0 ? xi : w == 1 ? yi : zi;
+                  const int2 old = w == 0 ? a : w == 1 ? b : c;
+                  const Itv nw = w == 0 ? r1 : w == 1 ? r2 : r3;
+                  int ch = 0;
+                  if(nw.lb > old.x) { atomicMax(&store[v].x, nw.lb); ch = 1; }
+                  if(nw.ub < old.y) { atomicMin(&store[v].y, nw.ub); ch = 1; }
+                  if(ch) {
+                    g1 |= nw.lb > nw.ub ? 3 : 1;
+                    cv[h * 3 + w] = v;
+                  }
+                }
+              }
+            }
+          }
+          f |= g1;
+          const bool grp_changed = __any_sync(0xffffffffu, g1 & 1);
+          if(grp_changed && dnext) {
+            // flag the groups of the records incident to every tightened variable: the warp walks each variable's CSR
+            // row together (one coalesced load of up to 32 record indices) instead of one lane chasing it alone
+#pragma unroll
+            for(int q = 0; q < 6; ++q) {
+              unsigned m = __ballot_sync(0xffffffffu, cv[q] >= 0);
+              if(!m) continue;
+              int rb = 0, re = 0;
+              if(cv[q] >= 0) { rb = t.inc_off[cv[q]]; re = t.inc_off[cv[q] + 1]; }
+              while(m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int bb = __shfl_sync(0xffffffffu, rb, src), ee = __shfl_sync(0xffffffffu, re, src);
+                for(int j = bb + lane; j < ee; j += 32) dnext[t.inc_idx[j] >> 6] = 1;
+              }
+            }
+          }
+          if(grp_changed) ++my_groups;
+          ++my_evals;
+        }
+      }
+    }
+    // changed groups of the block -> the barrier's count; evaluated groups -> the deduction counter
+    if(lane == 0 && my_groups) atomicAdd(&s_cnt, my_groups);
+    const bool any_bot = __syncthreads_or(f & 2);
+    const GridVote v = grid_count_barrier(ctl->bar, nbar++, s_cnt, any_bot, &s_vote);
+    ++sweeps;
+    if(phase < 2) { ++dense; deductions += (unsigned long long)t.n; }
+    else if(lane == 0 && my_evals) atomicAdd(&ctl->deductions, 64ull * my_evals);
+    bot |= v.bot;
+    any_changed |= v.changed;
+    if(!v.changed || (bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) done = true;
+    else if(phase == 0) { if(v.n_changed <= switch_groups) phase = 1; }
+    else phase = 2;
+  }
+  if(blockIdx.x == 0 && tid == 0) {
+    ctl->sweeps = sweeps;
+    ctl->dense_sweeps = dense;
+    ctl->has_changed = any_changed;
+    ctl->is_bot = bot;
+    atomicAdd(&ctl->deductions, deductions);
+  }
+}
+
+} // namespace lpc
+
+using namespace lpc;
+
+// Called by lpc_fixpoint_async for LPC_MODE_AUTO. The three byte maps live with the store handle.
+int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o) {
+  cudaStream_t st = (cudaStream_t)o->stream;
+  const long long n_pad = t->dev.n_pad;
+  const int n_groups = (int)((n_pad + 63) / 64);
+  const int map_stride = (n_groups + 15) / 16 * 16;
+  if(s->dirty_cap < 3LL * map_stride) {
+    cudaFree(s->d_dirty);
+    s->d_dirty = nullptr; s->dirty_cap = 0;
+    LPC_CUDA(cudaMalloc((void**)&s->d_dirty, 3 * (size_t)map_stride));
+    s->dirty_cap = 3LL * map_stride;
+  }
+  if(!t->dirty_ready) {
+    for(int d = 0; d < 2; ++d)
+      LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->dirty_blocks_per_sm[d], d ? k_pir_dirty<true> : k_pir_dirty<false>, DTPB, 0));
+    t->dirty_ready = true;
+  }
+  const int per_sm = t->dirty_blocks_per_sm[t->has_div ? 1 : 0];
+  LPC_REQUIRE(per_sm > 0, "kernel does not fit on an SM");
+  int grid = t->sm_count * per_sm;
+  const long long units = n_pad / 2;
+  grid = (int)std::max<long long>(1, std::min<long long>(grid, (units + DTPB - 1) / DTPB));
+  DSeg seg;
+  seg.nseg = t->seg_n;
+  for(int i = 0; i <= t->seg_n; ++i) seg.u[i] = t->seg_q[i] * 2;
+  if(units <= 2LL * grid * DTPB) { seg.nseg = 1; seg.u[0] = 0; seg.u[1] = (int)units; }   // small table: one pass (see pir_fixpoint.cu)
+  // hand over to flagged sweeps once a sweep changes at most 1/d of the groups (opts.reserved = d, default 8)
+  const int div = o->reserved > 0 ? o->reserved : 8;
+  unsigned switch_groups = (unsigned)std::max(1, n_groups / div);
+  LPC_CUDA(cudaEventRecord(s->ev0, st));
+  LPC_CUDA(cudaMemsetAsync(s->d_ctl, 0, sizeof(FixCtl), st));
+  TableDev td = t->dev;
+  int2* store = s->d;
+  FixCtl* ctl = s->d_ctl;
+  unsigned char* dmap = s->d_dirty;
+  int ng = n_groups, ms = map_stride, max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
+  void* args[] = {&td, &store, &seg, &ctl, &dmap, &ng, &ms, &switch_groups, &max_sweeps, &stop};
+  void* k = t->has_div ? (void*)k_pir_dirty<true> : (void*)k_pir_dirty<false>;
+  LPC_CUDA(cudaLaunchCooperativeKernel(k, dim3(grid), dim3(DTPB), args, 0, st));
+  g_launches++;
+  LPC_CUDA(cudaEventRecord(s->ev1, st));
+  LPC_CUDA(cudaMemcpyAsync(s->h_ctl, s->d_ctl, sizeof(FixCtl), cudaMemcpyDeviceToHost, st));
+  s->last_stream = st;
+  s->pending = true;
+  return LPC_OK;
+}

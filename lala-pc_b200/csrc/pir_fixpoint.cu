@@ -435,10 +435,9 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   LPC_REQUIRE(o->mode >= LPC_MODE_AUTO && o->mode <= LPC_MODE_WORKLIST, "bad mode");
   cudaStream_t st = (cudaStream_t)o->stream;
-  // AUTO currently resolves to dense sweeps unless the caller gives a switch divisor (opts.reserved = d: hand over
-  // to the worklist once a sweep changes <= n/d bounds): measured on config 2 the change-driven iterations do 4x
-  // fewer deductions but are latency-bound (profiles/r01_summary.md), so dense is the faster default for now.
-  const bool track = o->mode == LPC_MODE_WORKLIST || (o->mode == LPC_MODE_AUTO && o->reserved > 0);
+  // LPC_MODE_AUTO is the change-driven kernel of pir_dirty.cu (dense sweeps that skip unflagged 64-record groups once
+  // few groups change); LPC_MODE_WORKLIST keeps the record-granular queues of this file; LPC_MODE_SWEEP is purely dense.
+  const bool track = o->mode == LPC_MODE_WORKLIST;
   const Variant& var = pick_variant();
   fix_kernel_t k = var.k[t->has_div ? 1 : 0][track ? 1 : 0];
   // launch plan: computed once per table (the segment scan is O(n) on the host, the occupancy query is a driver call)
@@ -450,6 +449,7 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
       LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[tr], var.k[t->has_div ? 1 : 0][tr], TPB, 0));
     t->plan_ready = true;
   }
+  if(o->mode == LPC_MODE_AUTO) return lpc_dirty_fixpoint_launch(t, s, o);
   if(!track) {   // dense sweeps: shared-memory windows when the table has the locality for it (pir_window.cu)
     int used = 0;
     int rc = lpc_win_fixpoint_launch(t, s, o, &used);

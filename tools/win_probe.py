@@ -19,6 +19,15 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             if i >= 3: ms.append(r.device_ms)
         out[name] = dict(ms=round(float(np.mean(ms)), 4), sweeps=r.sweeps, gded=round(r.deductions / np.mean(ms) / 1e6, 1),
                          us_per_sweep=round(float(np.mean(ms)) * 1e3 / r.sweeps, 2))
+        for div in (0, 4, 16, 64):
+            ms = []
+            for i in range(6):
+                s = L.Store(values=net.store)
+                flush.zero_()
+                r = L.fixpoint(t, s, mode=L.MODE_AUTO, switch_div=div)
+                if i >= 2: ms.append(r.device_ms)
+            out[name + ".auto%d" % div] = dict(ms=round(float(np.mean(ms)), 4), sweeps=r.sweeps, dense=r.dense_sweeps,
+                                               mded=round(r.deductions / 1e6, 2))
     print(json.dumps(out))
 else:
     for win in sys.argv[1:] or ("0", "1"):
