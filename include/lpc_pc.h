@@ -31,7 +31,16 @@ enum lpc_pc_kind {
    * (bool_clause, pc.hpp:542-544)                                                          formula.hpp:346-350 */
   LPC_PC_CLAUSE = 5,
   /* Equality(Unary<Abs>(Variable x), Variable y): terms = {x, y}                           terms.hpp:104-119 */
-  LPC_PC_ABS_EQ = 6
+  LPC_PC_ABS_EQ = 6,
+  /* The other comparisons of a linear term with a constant, same term encoding as LIN_LE:
+   * Inequality(Constant rhs, sum):      rhs <= sum                                          formula.hpp:801-804 */
+  LPC_PC_LIN_GE = 7,
+  /* Inequality<neg>(sum, Constant rhs): sum > rhs                                           formula.hpp:779-785 */
+  LPC_PC_LIN_GT = 8,
+  /* Equality(sum, Constant rhs):        sum = rhs                                           formula.hpp:676-680 */
+  LPC_PC_LIN_EQ = 9,
+  /* Equality(sum, Variable bvar):       sum = z, z in `bvar`                                formula.hpp:672-681 */
+  LPC_PC_LIN_EQ_VAR = 10
 };
 
 typedef struct lpc_pc_prop {
@@ -39,11 +48,13 @@ typedef struct lpc_pc_prop {
   int32_t first_term;  /* index of the first term in the term array */
   int32_t n_terms;
   int32_t rhs;         /* constant right-hand side (LIN_LE, REIF_LIN_LE, NEQ with a constant) */
-  int32_t bvar;        /* reification variable (REIF_LIN_LE), else -1 */
+  int32_t bvar;        /* reification variable (REIF_LIN_LE) or the variable equal to the sum (LIN_EQ_VAR), else -1 */
 } lpc_pc_prop;
 
 typedef struct lpc_pc_term {
-  int32_t coef;        /* coefficient (LIN kinds, non-zero) or literal sign (+1 / -1, CLAUSE); 1 otherwise */
+  int32_t coef;        /* coefficient (LIN kinds, non-zero) or literal sign (+1 / -1, CLAUSE); 1 otherwise. A coefficient
+                          of -1 also stands for Unary<Neg>(Variable) and for the right operand of Binary<Sub>
+                          (terms.hpp:87-102, 209-229): same bounds as Binary<Mul>(Constant -1, Variable). */
   int32_t var;
 } lpc_pc_term;
 

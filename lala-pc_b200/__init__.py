@@ -308,6 +308,7 @@ def fixpoint_host(table, values, **kw):
 
 
 PC_LIN_LE, PC_REIF_LIN_LE, PC_EQ, PC_NEQ, PC_CLAUSE, PC_ABS_EQ = 1, 2, 3, 4, 5, 6
+PC_LIN_GE, PC_LIN_GT, PC_LIN_EQ, PC_LIN_EQ_VAR = 7, 8, 9, 10
 
 
 def nbit_range(lb, ub):

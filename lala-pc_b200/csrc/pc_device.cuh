@@ -11,7 +11,10 @@
 
 namespace lpc {
 
-enum PcKind : int { PC_LIN_LE = 1, PC_REIF_LIN_LE = 2, PC_EQ = 3, PC_NEQ = 4, PC_CLAUSE = 5, PC_ABS_EQ = 6 };
+enum PcKind : int { PC_LIN_LE = 1, PC_REIF_LIN_LE = 2, PC_EQ = 3, PC_NEQ = 4, PC_CLAUSE = 5, PC_ABS_EQ = 6,
+                    PC_LIN_GE = 7, PC_LIN_GT = 8, PC_LIN_EQ = 9, PC_LIN_EQ_VAR = 10 };
+__host__ __device__ __forceinline__ bool pc_is_linear(int kind) { return kind == PC_LIN_LE || kind == PC_REIF_LIN_LE || kind >= PC_LIN_GE; }
+__host__ __device__ __forceinline__ bool pc_has_extra_lane(int kind) { return kind == PC_REIF_LIN_LE || kind == PC_LIN_EQ_VAR; }
 
 struct PcTableDev {
   const int4* hdr;     // {kind | n_terms << 8, first_term, rhs, bvar}
@@ -27,9 +30,11 @@ struct PcTableDev {
   int n_big;
 };
 
-// lane meta word: bits 0-4 first lane of the propagator, 5-10 its lane count (1..32), 11-13 kind (0 = padding),
-// bit 14 = this lane is the Boolean of a reified sum
-#define PC_META(start, len, kind, isb) ((start) | ((len) << 5) | ((kind) << 11) | ((isb) << 14))
+// lane meta word: bits 0-4 first lane of the propagator, 5-10 its lane count (1..32), 11-14 kind (0 = padding),
+// bit 15 = this lane is the extra variable of the propagator (the Boolean of a reified sum, the z of sum = z)
+#define PC_META(start, len, kind, isb) ((start) | ((len) << 5) | ((kind) << 11) | ((isb) << 15))
+#define PC_META_KIND(m) (((m) >> 11) & 15)
+#define PC_META_EXTRA(m) (((m) >> 15) & 1)
 
 LPC_HD bool b_inf(int x) { return x == LPC_INF || x == LPC_MINF; }
 LPC_HD int b_clamp(long long x) { return x >= LPC_INF ? LPC_INF : (x <= LPC_MINF ? LPC_MINF : (int)x); }
@@ -126,6 +131,25 @@ LPC_HD int pc_deduce(Acc& a, const int4 h, const int2* terms) {
       else if(all.lb > rhs) return lit_deduce(a, true, bvar);                                        // g.nask (:766)
       return 0;
     }
+    case PC_LIN_GE: {   // Inequality<false>::deduce, left side constant (formula.hpp:801-804)
+      const Itv all = lin_project(a, terms, n);
+      return lin_embed(a, terms, n, Itv(rhs, LPC_INF), all);
+    }
+    case PC_LIN_GT: {   // Inequality<true>::deduce, right side constant (formula.hpp:779-785)
+      const Itv all = lin_project(a, terms, n);
+      return lin_embed(a, terms, n, Itv(b_add(rhs, 1), LPC_INF), all);
+    }
+    case PC_LIN_EQ: {   // Equality<false>::deduce, right side constant (formula.hpp:676-680)
+      const Itv all = lin_project(a, terms, n);
+      return lin_embed(a, terms, n, Itv(rhs, rhs), all);
+    }
+    case PC_LIN_EQ_VAR: {   // Equality<false>::deduce (formula.hpp:672-681): z <- sum, then sum <- z
+      int f = a.embed(bvar, lin_project(a, terms, n));
+      const Itv z = a.load(bvar);
+      const Itv all = lin_project(a, terms, n);
+      f |= lin_embed(a, terms, n, z, all);
+      return f;
+    }
     case PC_EQ: {   // Equality<false>::deduce (formula.hpp:672-681)
       const int x = terms[0].y, y = terms[1].y;
       int f = a.embed(y, a.load(x));
@@ -198,6 +222,13 @@ LPC_HD bool pc_ask(const Acc& a, const int4 h, const int2* terms) {
     case PC_REIF_LIN_LE: {                                                           // formula.hpp:408-412
       const Itv b = a.load(bvar), all = lin_project(a, terms, n);
       return (lit_ask(false, b) && all.ub <= rhs) || (lit_ask(true, b) && all.lb > rhs);
+    }
+    case PC_LIN_GE: return rhs <= lin_project(a, terms, n).lb;                       // formula.hpp:769
+    case PC_LIN_GT: return lin_project(a, terms, n).lb > rhs;                        // formula.hpp:766
+    case PC_LIN_EQ: { const Itv all = lin_project(a, terms, n); return all.lb == rhs && all.ub == rhs; }   // formula.hpp:629
+    case PC_LIN_EQ_VAR: {
+      const Itv all = lin_project(a, terms, n), z = a.load(bvar);
+      return ((all.is_bot() && z.is_bot()) || (all.lb == z.lb && all.ub == z.ub)) && all.lb == all.ub;
     }
     case PC_EQ: {                                                                    // formula.hpp:629
       const Itv l = a.load(terms[0].y), r = a.load(terms[1].y);

@@ -92,6 +92,14 @@ __device__ __forceinline__ int lane_embed_bits(u64* s, int v, u64 old, u64 u) {
   atomicAnd(&s[v], u);
   return nw == 0 ? 3 : 1;
 }
+// Euclidean quotient of int32 operands that cannot overflow (|a| < 2^31, b != 0 finite)
+__device__ __forceinline__ int ediv_small(int a, int b) {
+  if(b == 1) return a;
+  int q = a / b;
+  const int r = a - q * b;
+  if(r < 0) q += b > 0 ? -1 : 1;
+  return q;
+}
 // x with the value p removed (Equality<true>::deduce, formula.hpp:645-652)
 __device__ __forceinline__ Itv itv_shave(const Itv& x, int p) {
   Itv lo = x, hi = x;
@@ -115,12 +123,12 @@ __device__ __forceinline__ int tile_step(const PcTableDev& t, Acc& acc, int2* st
                                          const int2 raw) {
   const unsigned FULL = 0xffffffffu;
   const int coef = L.x, var = L.y, meta = L.z, rhs = L.w;
-  const int kind = (meta >> 11) & 7, seg0 = meta & 31, len = (meta >> 5) & 63, pos = lane - seg0;
-  const bool active = kind != 0, isb = (meta >> 14) & 1;
+  const int kind = PC_META_KIND(meta), seg0 = meta & 31, len = (meta >> 5) & 63, pos = lane - seg0;
+  const bool active = kind != 0, isb = PC_META_EXTRA(meta);
   const int last = seg0 + len - 1;
   const unsigned segmask = (len >= 32 ? FULL : ((1u << len) - 1u)) << seg0;
   // the lane whose domain this lane needs: the Boolean of a reified sum, else the other side of a binary propagator
-  const int partner = (kind == PC_LIN_LE || kind == PC_REIF_LIN_LE) ? last : (len == 2 ? seg0 + 1 - pos : lane);
+  const int partner = pc_is_linear(kind) ? last : (len == 2 ? seg0 + 1 - pos : lane);
   int f = 0;
   if constexpr(BITS) {
     u64* cells = reinterpret_cast<u64*>(store);
@@ -151,7 +159,7 @@ __device__ __forceinline__ int tile_step(const PcTableDev& t, Acc& acc, int2* st
   }
   else {
     const Itv dom = active ? Itv(raw.x, raw.y) : Itv(0, 0);
-    const bool lin = kind == PC_LIN_LE || kind == PC_REIF_LIN_LE;
+    const bool lin = pc_is_linear(kind);
     const bool term_lane = lin && !isb;
     // c * x as the hull of the two products (terms.hpp:399-405). A propagator is "tame" when every operand is non-empty
     // and every term bound is below 2^24 in magnitude: with at most 32 lanes and |rhs| < 2^30 (checked by the table
@@ -159,7 +167,8 @@ __device__ __forceinline__ int tile_step(const PcTableDev& t, Acc& acc, int2* st
     // of pc_device.cuh gives. Infinite bounds fail the test by their size.
     const long long p0 = (long long)coef * dom.lb, p1 = (long long)coef * dom.ub;
     const long long tlo = min(p0, p1), thi = max(p0, p1);
-    const bool tame = dom.lb <= dom.ub && (!term_lane || (tlo > -(1 << 24) && thi < (1 << 24)));
+    const bool small_or_inf = (dom.lb == LPC_MINF || dom.lb > -(1 << 30)) && (dom.ub == LPC_INF || dom.ub < (1 << 30));
+    const bool tame = dom.lb <= dom.ub && (term_lane ? (tlo > -(1 << 24) && thi < (1 << 24)) : small_or_inf);
     const int ti_lb = term_lane ? (int)tlo : 0, ti_ub = term_lane ? (int)thi : 0;
     const unsigned wildm = __ballot_sync(FULL, active && lin && !tame);
     const unsigned heads = __ballot_sync(FULL, active && pos == 0);
@@ -181,35 +190,39 @@ __device__ __forceinline__ int tile_step(const PcTableDev& t, Acc& acc, int2* st
         if(pos == 0) f |= tile_fallback(t, acc, t.tile_prop0[tile] + __popc(heads & ((1u << lane) - 1u)));
         return f;
       }
-      // Inequality::deduce / Biconditional::deduce (formula.hpp:796-805, 421-427); pd = the Boolean's domain
-      int dir = 1;   // 1: sum <= rhs, -1: sum >= rhs + 1, 0: the terms stay
-      if(kind == PC_REIF_LIN_LE) {
-        if(pd.lb > 0 || pd.ub < 0) dir = 1;              // b true (b does not contain 0)
-        else if(pd.lb == 0 && pd.ub == 0) dir = -1;      // b false
-        else {
-          dir = 0;
-          if(isb) {
-            if(all_ub <= rhs) f |= lane_embed(store, var, dom, Itv(1, 1));
-            else if(all_lb > rhs) f |= lane_embed(store, var, dom, Itv(0, 0));
+      // The interval u the sum is met with (Inequality / Equality / Biconditional::deduce, formula.hpp:796-805,
+      // 672-681, 421-427); pd = the domain of the extra lane (Boolean / z). An infinite end of u constrains nothing.
+      int ulb = LPC_MINF, uub = LPC_INF;
+      bool to_terms = true;
+      switch(kind) {
+        case PC_LIN_LE: uub = rhs; break;
+        case PC_LIN_GE: ulb = rhs; break;
+        case PC_LIN_GT: ulb = rhs + 1; break;
+        case PC_LIN_EQ: ulb = rhs; uub = rhs; break;
+        case PC_LIN_EQ_VAR:   // z <- sum first (its own lane), then the sum is met with the new z
+          ulb = max(pd.lb, all_lb); uub = min(pd.ub, all_ub);
+          if(isb) f |= lane_embed(store, var, dom, Itv(all_lb, all_ub));
+          break;
+        default:   // PC_REIF_LIN_LE
+          if(pd.lb > 0 || pd.ub < 0) uub = rhs;                  // b true (b does not contain 0)
+          else if(pd.lb == 0 && pd.ub == 0) ulb = rhs + 1;       // b false
+          else {
+            to_terms = false;
+            if(isb) {
+              if(all_ub <= rhs) f |= lane_embed(store, var, dom, Itv(1, 1));
+              else if(all_lb > rhs) f |= lane_embed(store, var, dom, Itv(0, 0));
+            }
           }
-        }
       }
-      if(dir != 0 && !isb) {
-        // Nary<Add>::embed (terms.hpp:480-499): c * x <= rhs - (all.lb - t.lb), resp. c * x >= rhs + 1 - (all.ub - t.ub);
-        // then x's side by Euclidean division (GroupMul::left_residual, terms.hpp:249-253)
-        const int bound = dir > 0 ? rhs - (all_lb - ti_lb) : rhs + 1 - (all_ub - ti_ub);
-        int q = bound;
-        if(coef != 1) {
-          q = bound / coef;
-          const int r = bound - q * coef;
-          if(r < 0) q += coef > 0 ? -1 : 1;
-        }
-        // sum <= rhs bounds x above for a positive coefficient and below for a negative one; sum >= rhs + 1 the reverse.
-        // The Euclidean quotient is a floor for c > 0 and a ceiling for c < 0, which is the wanted rounding when the
-        // bounded side is "above" (dir * c > 0); for the other side the hull of the reference's residual is the same
-        // quotient (both ends of u ediv c, one of them infinite).
-        if((dir > 0) == (coef > 0)) { if(q < dom.ub) { atomicMin(&store[var].y, q); f |= q < dom.lb ? 3 : 1; } }
-        else { if(q > dom.lb) { atomicMax(&store[var].x, q); f |= q > dom.ub ? 3 : 1; } }
+      if(to_terms && !isb) {
+        // Nary<Add>::embed (terms.hpp:480-499): c * x in [ulb - (all.ub - t.ub), uub - (all.lb - t.lb)], then x's side
+        // by Euclidean division, as the hull of both ends (GroupMul::left_residual, terms.hpp:249-253): a floor for
+        // c > 0, a ceiling for c < 0, an infinite end staying infinite with the sign of c.
+        const bool has_lo = ulb != LPC_MINF, has_hi = uub != LPC_INF;
+        int p = coef > 0 ? LPC_MINF : LPC_INF, q = coef > 0 ? LPC_INF : LPC_MINF;
+        if(has_lo) p = ediv_small(ulb - (all_ub - ti_ub), coef);
+        if(has_hi) q = ediv_small(uub - (all_lb - ti_lb), coef);
+        f |= lane_embed(store, var, dom, Itv(min(p, q), max(p, q)));
       }
       return f;
     }
@@ -272,10 +285,10 @@ __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDe
       long long cur = gwarp;
       int4 L0 = cur < t.n_tiles ? __ldg(&t.tiles[cur * 32 + lane]) : Z;
       int4 L1 = cur + gwarps < t.n_tiles ? __ldg(&t.tiles[(cur + gwarps) * 32 + lane]) : Z;
-      int2 r0 = (L0.z >> 11) & 7 ? __ldcg(&store[L0.y]) : make_int2(0, 0);
+      int2 r0 = PC_META_KIND(L0.z) ? __ldcg(&store[L0.y]) : make_int2(0, 0);
       while(cur < t.n_tiles) {
         const int4 L2 = cur + 2 * gwarps < t.n_tiles ? __ldg(&t.tiles[(cur + 2 * gwarps) * 32 + lane]) : Z;
-        const int2 r1 = (L1.z >> 11) & 7 ? __ldcg(&store[L1.y]) : make_int2(0, 0);
+        const int2 r1 = PC_META_KIND(L1.z) ? __ldcg(&store[L1.y]) : make_int2(0, 0);
         f |= tile_step<BITS>(t, acc, store, cur, lane, L0, r0);
         L0 = L1; L1 = L2; r0 = r1;
         cur += gwarps;
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDe
       for(int u = 0; u < PC_UNROLL; ++u)
         L[u] = base + u < t.n_tiles ? __ldg(&t.tiles[(base + u) * 32 + lane]) : make_int4(0, 0, 0, 0);
 #pragma unroll
-      for(int u = 0; u < PC_UNROLL; ++u) raw[u] = (L[u].z >> 11) & 7 ? __ldcg(&store[L[u].y]) : make_int2(0, 0);
+      for(int u = 0; u < PC_UNROLL; ++u) raw[u] = PC_META_KIND(L[u].z) ? __ldcg(&store[L[u].y]) : make_int2(0, 0);
 #pragma unroll
       for(int u = 0; u < PC_UNROLL; ++u) f |= tile_step<BITS>(t, acc, store, base + u, lane, L[u], raw[u]);
     }
@@ -379,18 +392,19 @@ int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_
   bool has_linear = false;
   for(int64_t i = 0; i < n_props; ++i) {
     const lpc_pc_prop& p = props[i];
-    if(p.kind < LPC_PC_LIN_LE || p.kind > LPC_PC_ABS_EQ) { set_error("lpc_pc_table_create: propagator %lld has unsupported kind %d", (long long)i, p.kind); return LPC_ERR_UNSUPPORTED; }
+    if(p.kind < LPC_PC_LIN_LE || p.kind > LPC_PC_LIN_EQ_VAR) { set_error("lpc_pc_table_create: propagator %lld has unsupported kind %d", (long long)i, p.kind); return LPC_ERR_UNSUPPORTED; }
     if(p.n_terms < 1 || p.n_terms >= (1 << 23) || p.first_term < 0 || (int64_t)p.first_term + p.n_terms > n_terms) { set_error("lpc_pc_table_create: propagator %lld has a bad term range", (long long)i); return LPC_ERR_INVALID; }
     const bool two = p.kind == LPC_PC_EQ || p.kind == LPC_PC_ABS_EQ;
     if((two && p.n_terms != 2) || (p.kind == LPC_PC_NEQ && p.n_terms > 2)) { set_error("lpc_pc_table_create: propagator %lld has the wrong arity for its kind", (long long)i); return LPC_ERR_INVALID; }
-    if(p.kind == LPC_PC_REIF_LIN_LE && (p.bvar < 0 || p.bvar >= nvars)) { set_error("lpc_pc_table_create: propagator %lld has a bad reification variable", (long long)i); return LPC_ERR_INVALID; }
+    const bool lin_kind = p.kind == LPC_PC_LIN_LE || p.kind == LPC_PC_REIF_LIN_LE || p.kind >= LPC_PC_LIN_GE;
+    if((p.kind == LPC_PC_REIF_LIN_LE || p.kind == LPC_PC_LIN_EQ_VAR) && (p.bvar < 0 || p.bvar >= nvars)) { set_error("lpc_pc_table_create: propagator %lld has a bad reification / result variable", (long long)i); return LPC_ERR_INVALID; }
     for(int k = 0; k < p.n_terms; ++k) {
       const lpc_pc_term& t = terms[p.first_term + k];
       if(t.var < 0 || t.var >= nvars) { set_error("lpc_pc_table_create: propagator %lld has a variable out of range", (long long)i); return LPC_ERR_INVALID; }
-      if((p.kind == LPC_PC_LIN_LE || p.kind == LPC_PC_REIF_LIN_LE || p.kind == LPC_PC_CLAUSE) && t.coef == 0) { set_error("lpc_pc_table_create: propagator %lld has a zero coefficient", (long long)i); return LPC_ERR_INVALID; }
+      if((lin_kind || p.kind == LPC_PC_CLAUSE) && t.coef == 0) { set_error("lpc_pc_table_create: propagator %lld has a zero coefficient", (long long)i); return LPC_ERR_INVALID; }
     }
     hdr[i] = make_int4(p.kind | (p.n_terms << 8), p.first_term, p.rhs, p.bvar);
-    has_linear |= p.kind == LPC_PC_LIN_LE || p.kind == LPC_PC_REIF_LIN_LE;
+    has_linear |= lin_kind;
   }
   lpc_pc_table* t = new lpc_pc_table();
   t->has_linear = has_linear;
@@ -405,8 +419,8 @@ int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_
     int cur = 32;   // lanes used in the open tile (32 = none open)
     for(int64_t i = 0; i < n_props; ++i) {
       const lpc_pc_prop& p = props[i];
-      const int lanes = p.n_terms + (p.kind == LPC_PC_REIF_LIN_LE ? 1 : 0);
-      const bool lin_kind = p.kind == LPC_PC_LIN_LE || p.kind == LPC_PC_REIF_LIN_LE;
+      const int lanes = p.n_terms + (pc_has_extra_lane(p.kind) ? 1 : 0);
+      const bool lin_kind = pc_is_linear(p.kind);
       if(lanes > 32 || (lin_kind && (p.rhs >= (1 << 30) || p.rhs <= -(1 << 30)))) {   // see tile_step: keeps the tile arithmetic in int32
         big.push_back((int)i);
         cur = 32;   // close the tile so that tile_prop0 + rank stays a contiguous propagator range

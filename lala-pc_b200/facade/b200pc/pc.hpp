@@ -298,6 +298,10 @@ private:
       if(!env.interpret(F::var(t.seq(1).name), v)) return false;
       out = lpc_pc_term{t.seq(0).k, v.vid()}; len = 3; return true;
     }
+    if(t.is_seq() && t.sig() == NEG && t.args.size() == 1 && t.seq(0).is_variable()) {   // Unary<Neg>: the bounds of -1 * x
+      if(!env.interpret(F::var(t.seq(0).name), v)) return false;
+      out = lpc_pc_term{-1, v.vid()}; len = 2; return true;
+    }
     return false;
   }
   static bool linear(const TF& t, const VarEnv& env, std::vector<lpc_pc_term>& out, int& len) {
@@ -308,20 +312,40 @@ private:
       for(auto& a : t.args) { if(!linear_leaf(a, env, leaf, l)) return false; out.push_back(leaf); len += l; }
       return true;
     }
+    if(t.is_binary() && t.sig() == SUB && t.seq(1).is_variable()) {   // Binary<GroupSub>(leaf, Variable) == leaf + (-1) * y
+      AVar v;
+      if(!linear_leaf(t.seq(0), env, leaf, l) || !env.interpret(F::var(t.seq(1).name), v)) return false;
+      out.push_back(leaf); out.push_back(lpc_pc_term{-1, v.vid()});
+      len = 1 + l + 1;
+      return true;
+    }
     return false;
   }
-  // l <= k with a linear left side; `k >= l` and `l <= k` both arrive here (pc.hpp:563-565)
-  static bool lin_le(const TF& f, const VarEnv& env, prop_type& p) {
+  // A comparison of a linear term with a constant. `>=` and `<` are the flipped `<=` and `>` (pc.hpp:563-566).
+  static bool lin_cmp(const TF& f, const VarEnv& env, prop_type& p) {
     if(!f.is_binary()) return false;
-    const TF* l = nullptr; const TF* r = nullptr;
-    if(f.sig() == LEQ) { l = &f.seq(0); r = &f.seq(1); }
-    else if(f.sig() == GEQ) { l = &f.seq(1); r = &f.seq(0); }
-    else return false;
-    if(!r->is_constant()) return false;
+    int sig = f.sig();
+    const TF* l = &f.seq(0); const TF* r = &f.seq(1);
+    if(sig == GEQ) { sig = LEQ; std::swap(l, r); }
+    else if(sig == LT) { sig = GT; std::swap(l, r); }
+    if(sig != LEQ && sig != GT) return false;
+    const bool const_left = l->is_constant();
+    const TF* term = const_left ? r : l;
+    const TF* cst = const_left ? l : r;
+    if(!cst->is_constant() || term->is_constant()) return false;
     int len = 0;
-    if(!linear(*l, env, p.terms, len)) return false;
-    p.kind = LPC_PC_LIN_LE; p.rhs = r->k; p.ref_kind = 4 /* ILeq */; p.length = 1 + len + 1;
+    if(!linear(*term, env, p.terms, len)) return false;
+    p.length = 1 + len + 1;
+    if(sig == LEQ) { p.kind = const_left ? LPC_PC_LIN_GE : LPC_PC_LIN_LE; p.rhs = cst->k; p.ref_kind = 4 /* ILeq */; }
+    else if(!const_left) { p.kind = LPC_PC_LIN_GT; p.rhs = cst->k; p.ref_kind = 5 /* IGt */; }
+    else {   // k > term: Inequality<neg>(Constant, term) embeds [-inf, k - 1] (formula.hpp:786-792)
+      if(cst->k == INT_MIN) return false;
+      p.kind = LPC_PC_LIN_LE; p.rhs = cst->k - 1; p.ref_kind = 5;
+    }
     return true;
+  }
+  static bool lin_le(const TF& f, const VarEnv& env, prop_type& p) {   // the shape a reification accepts
+    return lin_cmp(f, env, p) && p.kind == LPC_PC_LIN_LE && p.ref_kind == 4;
   }
   static bool literal(const TF& f, const VarEnv& env, lpc_pc_term& out) {
     AVar v;
@@ -360,7 +384,7 @@ private:
     if(f.sig() == EQUIV || (f.sig() == EQ && (a.is_predicate() || b.is_predicate() || a.is_logical() || b.is_logical()))) {
       const TF* lhs = &a; const TF* rhs = &b;
       if(!lhs->is_variable() && rhs->is_variable()) std::swap(lhs, rhs);
-      if(lhs->is_variable() && env.interpret(F::var(lhs->name), x) && lin_le(*rhs, env, p)) {
+      if(lhs->is_variable() && !bitset && env.interpret(F::var(lhs->name), x) && lin_le(*rhs, env, p)) {
         p.kind = LPC_PC_REIF_LIN_LE; p.bvar = x.vid(); p.ref_kind = 10 /* IBicond */; p.length = 1 + 1 + p.length;
         out.props.push_back(p); return true;
       }
@@ -381,9 +405,16 @@ private:
         p.kind = LPC_PC_ABS_EQ; p.terms = {{1, x.vid()}, {1, y.vid()}}; p.ref_kind = 6; p.length = 4;
         out.props.push_back(p); return true;
       }
+      int len = 0;
+      if(!ne && !bitset && a.is_seq() && linear(a, env, p.terms, len)) {   // sum = k, sum = z
+        if(b.is_constant()) { p.kind = LPC_PC_LIN_EQ; p.rhs = b.k; p.ref_kind = 6; p.length = 1 + len + 1; out.props.push_back(p); return true; }
+        if(b.is_variable() && env.interpret(F::var(b.name), y)) {
+          p.kind = LPC_PC_LIN_EQ_VAR; p.bvar = y.vid(); p.ref_kind = 6; p.length = 1 + len + 1; out.props.push_back(p); return true;
+        }
+      }
       return fail(why, "The shape of this formula is not supported.");
     }
-    if(lin_le(f, env, p)) {
+    if(lin_cmp(f, env, p)) {
       if(bitset) return fail(why, "Linear sums over a bitset store are not supported (NBitset arithmetic is unpinned).");
       out.props.push_back(p); return true;
     }

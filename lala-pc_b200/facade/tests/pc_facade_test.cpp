@@ -116,6 +116,47 @@ static void TemporalConstraint1() {   // pc_test.cpp:132-138: x + y <= 5
   deduce_and_test(ipc, 1, {Itv(0, 10), Itv(0, 10)}, {Itv(0, 5), Itv(0, 5)}, false);
 }
 
+static void TemporalConstraints() {   // pc_test.cpp:114-210
+  struct { TF c; std::vector<Itv> dom, after; bool ua, changed; } cases[] = {
+    {bin(bin(V("x"), ADD, V("y")), EQ, K(5)), {Itv(0, 10), Itv(0, 10)}, {Itv(0, 5), Itv(0, 5)}, false, true},          // AddEquality
+    {bin(bin(V("x"), ADD, V("y")), GT, K(5)), {Itv(0, 10), Itv(0, 10)}, {Itv(0, 10), Itv(0, 10)}, false, false},       // 2
+    {bin(bin(V("x"), ADD, V("y")), GT, K(5)), {Itv(0, 3), Itv(0, 3)}, {Itv(3, 3), Itv(3, 3)}, true, true},             // 3
+    {bin(bin(V("x"), ADD, V("y")), GEQ, K(5)), {Itv(0, 3), Itv(0, 3)}, {Itv(2, 3), Itv(2, 3)}, false, true},           // 4
+    {bin(bin(V("x"), ADD, V("y")), EQ, K(5)), {Itv(0, 4), Itv(0, 4)}, {Itv(1, 4), Itv(1, 4)}, false, true},            // 5
+    {bin(bin(V("x"), SUB, V("y")), LEQ, K(5)), {Itv(0, 10), Itv(0, 10)}, {Itv(0, 10), Itv(0, 10)}, false, false},      // 6
+    {bin(bin(V("x"), SUB, V("y")), LEQ, K(-10)), {Itv(0, 10), Itv(0, 10)}, {Itv(0, 0), Itv(10, 10)}, true, true},      // 7
+    {bin(bin(V("x"), SUB, V("y")), GEQ, K(5)), {Itv(0, 10), Itv(0, 10)}, {Itv(5, 10), Itv(0, 5)}, false, true},        // 8
+    {bin(bin(V("x"), SUB, V("y")), LEQ, K(-5)), {Itv(0, 10), Itv(0, 10)}, {Itv(0, 5), Itv(5, 10)}, false, true}};      // 9
+  for(auto& cs : cases) {
+    Model<IPC> m;
+    m.var("x", cs.dom[0]).var("y", cs.dom[1]).c(cs.c);
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, cs.dom, cs.after, cs.ua, cs.changed);
+  }
+  {   // pc_test.cpp:123-129: x + y = z, z <= 5
+    Model<IPC> m;
+    m.var("x", Itv(0, 10)).var("y", Itv(0, 10)).var("z").c(bin(V("z"), LEQ, K(5))).c(bin(bin(V("x"), ADD, V("y")), EQ, V("z")));
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, {Itv(0, 10), Itv(0, 10), Itv(INT_MIN, 5)}, {Itv(0, 5), Itv(0, 5), Itv(0, 5)}, false);
+  }
+}
+
+static void NegationOps() {   // pc_test.cpp:303-357
+  TF nx = TF::make_unary(NEG, V("x"));
+  struct { Itv dom; TF c; Itv after; bool bot; } cases[] = {
+    {Itv(-4, 3), bin(nx, LEQ, K(2)), Itv(-2, 3), false}, {Itv(-4, 3), bin(nx, LEQ, K(-2)), Itv(2, 3), false},
+    {Itv(0, 3), bin(nx, LEQ, K(-2)), Itv(2, 3), false}, {Itv(-4, -3), bin(nx, LEQ, K(4)), Itv(-4, -3), false},
+    {Itv(-4, 3), bin(nx, GEQ, K(-2)), Itv(-4, 2), false}, {Itv(-4, 3), bin(nx, GT, K(2)), Itv(-4, -3), false},
+    {Itv(-4, 3), bin(nx, GEQ, K(5)), Itv(), true}};
+  for(auto& cs : cases) {
+    Model<IPC> m;
+    m.var("x", cs.dom).c(cs.c);
+    IPC ipc = create_and_interpret_and_tell(m);
+    if(cs.bot) deduce_and_test_bot(ipc, 1, {cs.dom});
+    else deduce_and_test(ipc, 1, {cs.dom}, {cs.after}, true, !(cs.after == cs.dom));
+  }
+}
+
 static void TernarySums() {   // pc_test.cpp:222-260 as one n-ary sum x + y + z <= k (the shape config 3 uses)
   struct { Itv d; int k; bool bot; Itv after; bool ua; } cases[] = {
     {Itv(3, 10), 8, true, Itv(), false}, {Itv(3, 10), 9, false, Itv(3, 3), true},
@@ -306,6 +347,8 @@ static void BitIntAbs1() {   // pc_bitset_test.cpp:150-157
 int main() {
   if(lpc_device_init(0) != LPC_OK) { printf("no CUDA device: %s\n", lpc_last_error()); return 2; }
   TemporalConstraint1();
+  TemporalConstraints();
+  NegationOps();
   TernarySums();
   PseudoBoolean();
   NotEqual();

@@ -2,9 +2,11 @@
 PC::interpret_formula / interpret_term (lala-pc include/lala/pc.hpp:217-604) for the in-scope shapes.
 
 Formulas are nested tuples (a plain Python stand-in for lala-core's TFormula):
-  terms     ('var', v) ('const', k) ('mul', ('const', c), ('var', v)) ('add', t1, t2) ('sum', t1, ..., tn >= 3)
-            ('abs', ('var', v))
-  formulas  ('le', term, ('const', k))  ('equiv', ('lit', b), ('le', term, ('const', k)))
+  terms     ('var', v) ('const', k) ('neg', ('var', v)) ('mul', ('const', c), ('var', v)) ('add', t1, t2)
+            ('sub', t1, ('var', v)) ('sum', t1, ..., tn >= 3) ('abs', ('var', v))
+  formulas  ('le', term, ('const', k))  ('le', ('const', k), term)  ('gt', term, ('const', k))
+            ('eq', term, ('const', k))  ('eq', sum-term, ('var', z))
+            ('equiv', ('lit', b), ('le', term, ('const', k)))
             ('eq', ('var', x), ('var', y))  ('ne', ('var', x), ('var', y) | ('const', k))
             ('or', lit, ('or', lit, ...)) with lit = ('lit', v) | ('nlit', v)   ('eq', ('abs', ('var', x)), ('var', y))
 Anything else raises `Unsupported` (the reference's "shape of this formula is not supported" interpretation error);
@@ -13,6 +15,7 @@ such formulas stay on the reference's tree-walking path.
 import numpy as np
 
 PC_LIN_LE, PC_REIF_LIN_LE, PC_EQ, PC_NEQ, PC_CLAUSE, PC_ABS_EQ = 1, 2, 3, 4, 5, 6
+PC_LIN_GE, PC_LIN_GT, PC_LIN_EQ, PC_LIN_EQ_VAR = 7, 8, 9, 10
 
 
 class Unsupported(ValueError):
@@ -24,11 +27,18 @@ def _linear_terms(t):
     op = t[0]
     if op == "var":
         return [(1, int(t[1]))]
+    if op == "neg" and t[1][0] == "var":   # Unary<Neg>(Variable): the bounds of -1 * x (terms.hpp:87-102)
+        return [(-1, int(t[1][1]))]
     if op == "mul" and t[1][0] == "const" and t[2][0] == "var" and int(t[1][1]) != 0:
         return [(int(t[1][1]), int(t[2][1]))]
+    if op == "sub":   # Binary<GroupSub>(leaf, Variable): same residuals as leaf + (-1) * y (terms.hpp:209-229)
+        a = _linear_terms(t[1])
+        if len(a) != 1 or t[1][0] in ("add", "sum", "sub") or t[2][0] != "var":
+            raise Unsupported("only leaf - variable differences are flattened (a scaled right operand rounds differently)")
+        return a + [(-1, int(t[2][1]))]
     if op == "add":   # Binary<GroupAdd> of two leaf terms
         a, b = _linear_terms(t[1]), _linear_terms(t[2])
-        if len(a) != 1 or len(b) != 1 or t[1][0] in ("add", "sum") or t[2][0] in ("add", "sum"):
+        if len(a) != 1 or len(b) != 1 or t[1][0] in ("add", "sum", "sub") or t[2][0] in ("add", "sum", "sub"):
             raise Unsupported("nested binary sums are not flattened (their residuals differ from a flat sum)")
         return a + b
     if op == "sum":
@@ -36,7 +46,7 @@ def _linear_terms(t):
             raise Unsupported("an n-ary sum has at least three operands (pc.hpp:277-296)")
         out = []
         for s in t[1:]:
-            if s[0] in ("sum", "add"):
+            if s[0] in ("sum", "add", "sub"):
                 raise Unsupported("nested n-ary sums are not flattened (their residuals differ from a flat sum)")
             out += _linear_terms(s)
         return out
@@ -65,9 +75,17 @@ def _clause_literals(f):
 def flatten_one(f):
     """-> (kind, [(coef, var)], rhs, bvar)"""
     op = f[0]
+    if op == "le" and f[1][0] == "const" and f[2][0] != "const":   # k <= term
+        return PC_LIN_GE, _linear_terms(f[2]), int(f[1][1]), -1
     if op == "le":
         terms, k = _lin_le(f)
         return PC_LIN_LE, terms, k, -1
+    if op == "gt" and f[2][0] == "const":
+        return PC_LIN_GT, _linear_terms(f[1]), int(f[2][1]), -1
+    if op == "eq" and f[2][0] == "const" and f[1][0] != "abs":
+        return PC_LIN_EQ, _linear_terms(f[1]), int(f[2][1]), -1
+    if op == "eq" and f[2][0] == "var" and f[1][0] in ("add", "sub", "sum", "mul", "neg"):
+        return PC_LIN_EQ_VAR, _linear_terms(f[1]), 0, int(f[2][1])
     if op == "equiv" and f[1][0] == "lit" and f[2][0] == "le":
         terms, k = _lin_le(f[2])
         return PC_REIF_LIN_LE, terms, k, int(f[1][1])
@@ -98,9 +116,19 @@ def to_tree(kind, ts, rhs, bvar):
     """The formula tree a flat propagator stands for (inverse of flatten_one; used by generators and tests)."""
     def term(c, v):
         return ("var", v) if c == 1 else ("mul", ("const", c), ("var", v))
-    if kind in (PC_LIN_LE, PC_REIF_LIN_LE):
+    if kind in (PC_LIN_LE, PC_REIF_LIN_LE, PC_LIN_GE, PC_LIN_GT, PC_LIN_EQ, PC_LIN_EQ_VAR):
         lhs = (term(*ts[0]) if len(ts) == 1 else ("add", term(*ts[0]), term(*ts[1])) if len(ts) == 2
                else ("sum",) + tuple(term(c, v) for c, v in ts))
+        if kind == PC_LIN_GE:
+            return ("le", ("const", rhs), lhs)
+        if kind == PC_LIN_GT:
+            return ("gt", lhs, ("const", rhs))
+        if kind == PC_LIN_EQ:
+            return ("eq", lhs, ("const", rhs))
+        if kind == PC_LIN_EQ_VAR:
+            if len(ts) == 1 and ts[0][0] == 1:
+                raise Unsupported("x = z is the EQ kind")
+            return ("eq", lhs, ("var", bvar))
         le = ("le", lhs, ("const", rhs))
         return le if kind == PC_LIN_LE else ("equiv", ("lit", bvar), le)
     if kind == PC_EQ:

@@ -55,10 +55,11 @@ def test_goldens_and_flattener(devhost):
             continue
         ran += 1
         compare(devhost, formulas, np.array(k["store"], dtype=np.int32), k["name"])
-    assert ran >= 18
+    assert ran >= 38
     # shapes without a flat kind are refused, not approximated
     for f in (("le", ("add", ("add", ("var", 0), ("var", 1)), ("var", 2)), ("const", 3)),
-              ("le", ("var", 0), ("var", 1)), ("gt", ("var", 0), ("const", 1)),
+              ("le", ("var", 0), ("var", 1)), ("gt", ("var", 0), ("var", 1)), ("le", ("var", 0), ("add", ("const", -5), ("var", 1))),
+              ("le", ("sub", ("var", 0), ("mul", ("const", 3), ("var", 1))), ("const", 2)),
               ("equiv", ("lit", 0), ("and", ("lit", 1), ("lit", 2)))):
         with pytest.raises(pcflat.Unsupported):
             pcflat.flatten([f])

@@ -74,7 +74,7 @@ def test_golden_vectors(L, O):
             continue
         after = np.array(k["after"], dtype=np.int32)
         assert np.array_equal(got[:len(after)], after), (k["name"], got.tolist())
-    assert ran >= 18, ran
+    assert ran >= 38, ran
 
 
 def test_deduce_one_step_by_step(L, O):
@@ -134,12 +134,23 @@ def random_pc(rng, nvars):
     from lala_pc_b200 import pcflat
     forms = []
     for _ in range(int(rng.integers(1, 8))):
-        kind = int(rng.integers(1, 7))
+        kind = int(rng.integers(1, 11))
         vs = rng.permutation(nvars)
-        if kind in (1, 2):
+        if kind in (1, 2, 7, 8, 9, 10):
             n = int(rng.integers(1, min(6, nvars - 1)))
             ts = [(int(rng.choice([1, 1, 2, 3, 5, -1, -2])), int(v)) for v in vs[:n]]
-            forms.append(pcflat.to_tree(kind, ts, int(rng.integers(-10, 40)), int(vs[n]) if kind == 2 else -1))
+            if kind == 10 and n == 1 and ts[0][0] == 1:
+                ts = [(2, ts[0][1])]
+            tree = pcflat.to_tree(kind, ts, int(rng.integers(-10, 40)), int(vs[n]) if kind in (2, 10) else -1)
+            if n == 2 and ts[1][0] == -1 and kind != 2 and rng.random() < 0.5:
+                # the same constraint written with Unary<Neg> / Binary<Sub> (terms.hpp:87-102, 209-229)
+                c0, v0 = ts[0]
+                leaf = ("var", v0) if c0 == 1 else ("neg", ("var", v0)) if c0 == -1 else ("mul", ("const", c0), ("var", v0))
+                sub = ("sub", leaf, ("var", ts[1][1]))
+                tree = tuple(sub if isinstance(e, tuple) and e[0] == "add" else e for e in tree)
+            elif n == 1 and ts[0][0] == -1 and kind != 2 and rng.random() < 0.5:
+                tree = tuple(("neg", ("var", ts[0][1])) if isinstance(e, tuple) and e[0] == "mul" else e for e in tree)
+            forms.append(tree)
         elif kind == 4 and rng.random() < 0.4:
             forms.append(pcflat.to_tree(4, [(1, int(vs[0]))], int(rng.integers(-3, 8)), -1))
         elif kind == 5:
@@ -171,7 +182,7 @@ def test_random_networks(L, O):
 
 def test_errors(L):
     with pytest.raises(L.LpcError):
-        L.PcTable(np.array([[9, 0, 1, 0, -1]], dtype=np.int32), np.array([[1, 0]], dtype=np.int32), 2)      # bad kind
+        L.PcTable(np.array([[99, 0, 1, 0, -1]], dtype=np.int32), np.array([[1, 0]], dtype=np.int32), 2)     # bad kind
     with pytest.raises(L.LpcError):
         L.PcTable(np.array([[1, 0, 2, 0, -1]], dtype=np.int32), np.array([[1, 0]], dtype=np.int32), 2)      # term range
     with pytest.raises(L.LpcError):
