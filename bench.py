@@ -356,35 +356,42 @@ def own_pc(args, cpu=True):
     return out
 
 
-def own_search(args, cpu=True, n_stores=4096, max_nodes=64):
-    """the config-4 model, every EPS subproblem searched depth-first in its block (propagate,
-    branch by bisection on the widest variables, snapshot / restore on the device) under a node budget."""
+def own_search(args, cpu=True, n_split=16384, max_nodes=64):
+    """the config-4 model; the EPS subproblems that survive their root fixpoint are searched
+    depth-first, each in its block (propagate, branch by bisection on the widest variables, snapshot / restore on the
+    device), under a node budget."""
     import lala_pc_b200 as L
-    from lala_pc_b200 import workloads as W
     from lala_pc_b200 import sharding
     net, table, root, dec, obj = build_c4()
     dec = dec[:sharding.decision_bits(1)]
     width = root[:, 1].astype(np.int64) - root[:, 0]
     bv = [int(v) for v in np.argsort(-width, kind="stable")[:64]]
-    batch = L.Batch(table, n_stores)
-    batch.init_split(root, dec, 0)
+    split = L.Batch(table, n_split)
+    split.init_split(root, dec, 0)
+    split.fixpoint(objective_var=obj)
+    alive = np.flatnonzero((split.flags() & 1) == 0)
+    roots = np.ascontiguousarray(split.read()[alive])
+    split.close()
+    batch = L.Batch(table, len(alive))
+    batch.write(roots)
     best = None
     for _ in range(4):
         r, _ = batch.search(bv, objective_var=obj, max_nodes=max_nodes, max_depth=48, want_per_store=False)
         best = r if best is None or r.device_ms < best.device_ms else best
-    out = {"workload": "config-4 model, %d EPS subproblems, DFS with a budget of %d nodes each" % (n_stores, max_nodes),
+    out = {"workload": "config-4 model: the %d of %d EPS subproblems alive after their root fixpoint, DFS with a budget of "
+                       "%d nodes each" % (len(alive), n_split, max_nodes),
            "ms": best.device_ms, "nodes": int(best.n_nodes), "solutions": int(best.n_solutions), "fails": int(best.n_fails),
+           "incomplete": int(best.n_incomplete), "max_depth": int(best.max_depth_seen),
            "nodes_per_s": best.n_nodes / (best.device_ms * 1e-3), "value": best.deductions / (best.device_ms * 1e-3), "unit": UNIT}
     if cpu:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
-        sample = 256
-        stores = batch.read(0, sample)
+        sample = min(len(alive), 4 * cores)
         t0 = time.perf_counter()
-        want = O.pir_search(stores, net.records, bv, objective_var=obj, max_nodes=max_nodes, max_depth=48, threads=cores)
+        want = O.pir_search(roots[:sample], net.records, bv, objective_var=obj, max_nodes=max_nodes, max_depth=48, threads=cores)
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"nodes_per_s": float(want[:, 1].sum()) / dt, "cores": cores, "kind": "port",
-                               "sample": "%d of the %d subproblems" % (sample, n_stores)}
+                               "sample": "%d of the %d subproblems" % (sample, len(alive))}
     batch.close()
     return out
 
