@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblpc.so")
+LIB_PATH = os.environ.get("LPC_LIB") or os.path.join(_HERE, "liblpc.so")   # LPC_LIB: A/B runs of two builds on one box
 
 # lala-core Sig values of the operators PIR accepts (include/lpc.h: enum lpc_sig)
 ADD, MUL, MIN, MAX, TDIV, FDIV, CDIV, EDIV, EQ, LEQ = 2, 4, 6, 7, 25, 27, 29, 31, 46, 48
