@@ -215,7 +215,8 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
     net, table, root, dec, obj = build_c4()
     nbits = sharding.decision_bits(world)
     dec = dec[:nbits]
-    first_id = sharding.shard_first_id(rank, n_stores) if first_id is None else first_id
+    # rank r works on a uniform sample of the world * n_stores subproblem ids (sharding.shard_ids), not on a sub-cube
+    ids = sharding.shard_ids(rank, world, n_stores) if first_id is None else first_id + np.arange(n_stores, dtype=np.int64)
     batch = L.Batch(table, n_stores)
 
     class _Red:   # the 4 x int64 reduction record of the library, viewed as a torch tensor (no copy)
@@ -231,7 +232,7 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
     launches0 = L.launch_count()
     with ClockSampler(rank) as clk:
         for i in range(warmup + steps):
-            batch.init_split(root, dec, first_id)            # untimed: inputs resident in HBM (1 GiB > L2)
+            batch.init_split(root, dec, ids=ids)             # untimed: inputs resident in HBM (1 GiB > L2)
             if dist is not None:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -261,6 +262,7 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
         "config": {"workload": "batched EPS: %d subproblem stores per GPU of a %d-var / %d-propagator PIR model, one "
                                "block per store (BASELINE.json configs[3])" % (n_stores, net.nvars, len(net.records)),
                    "stores_total": n_stores * world, "decision_bits": nbits, "timing": "CUDA events, max over ranks",
+                   "sharding": "consecutive ids" if world == 1 else "each rank a uniform sample of the id space (sharding.shard_ids)",
                    "l2": "inputs larger than L2 (1 GiB of stores per GPU)", "collective":
                    "one NCCL all-reduce pair (SUM, MIN) over the 32-byte reduction record per step" if world > 1 else "none",
                    "seed": net.meta["seed"]},
@@ -277,7 +279,7 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
                                "exceed the HBM copy peak"}
     if e2e:
         pinned = torch.empty((n_stores, net.nvars, 2), dtype=torch.int32).pin_memory()
-        batch.init_split(root, dec, first_id)
+        batch.init_split(root, dec, ids=ids)
         src = torch.from_numpy(batch.read())
         n_e2e = max(1, min(steps, 3))
         t_e2e, d_e2e = 0.0, 0
@@ -439,7 +441,8 @@ def reference_arm(args, rank, world):
         sample = 4096
         secs, ded = [], []
         for i in range(args.warmup + args.steps):
-            stores = W.eps_stores(root, dec[:nbits], i * sample, sample)
+            ids = sharding.shard_ids(0, world, STORES_PER_GPU)[(i * sample) % STORES_PER_GPU:][:sample]
+            stores = W.eps_stores(root, dec[:nbits], 0, len(ids), ids=ids)
             _, _, _, d, sec = O.pir_batch_fixpoint(stores, net.records, threads=cores)
             if i >= args.warmup:
                 secs.append(sec)

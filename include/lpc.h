@@ -150,6 +150,10 @@ int lpc_batch_read(const lpc_batch* b, int32_t first_store, int32_t n, int32_t* 
  * taken on the base domain. */
 int lpc_batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_t* decision_vars, int32_t n_decisions,
                          int64_t first_id);
+/* Same with an explicit subproblem id per store (n_stores ids): lets a multi-GPU driver hand every rank a uniform
+ * sample of the id space instead of a sub-cube of it. */
+int lpc_batch_init_split_ids(lpc_batch* b, const int32_t* base_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                             const int64_t* ids);
 
 typedef struct lpc_batch_result {
   int64_t n_bot;         /* stores that failed */

@@ -117,6 +117,7 @@ SIGNATURES = {
     "lpc_batch_write": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "lpc_batch_read": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "lpc_batch_init_split": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64]),
+    "lpc_batch_init_split_ids": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "lpc_batch_fixpoint": (ctypes.c_int, [_vp, ctypes.POINTER(FixpointOpts), _i32, ctypes.POINTER(BatchResult)]),
     "lpc_batch_fixpoint_async": (ctypes.c_int, [_vp, ctypes.POINTER(FixpointOpts), _i32]),
     "lpc_batch_collect": (ctypes.c_int, [_vp, ctypes.POINTER(BatchResult)]),
@@ -398,10 +399,16 @@ class Batch:
         _check(_L.lpc_batch_read(self._h, first, n, out.ctypes.data))
         return out
 
-    def init_split(self, base, decision_vars, first_id=0):
+    def init_split(self, base, decision_vars, first_id=0, ids=None):
+        """EPS decomposition on the device; `ids` (int64 [n_stores]) overrides the consecutive ids first_id + k."""
         b = np.ascontiguousarray(base, dtype=np.int32).reshape(-1, 2)
         d = np.ascontiguousarray(decision_vars, dtype=np.int32)
-        _check(_L.lpc_batch_init_split(self._h, b.ctypes.data, d.ctypes.data, d.shape[0], first_id))
+        if ids is None:
+            _check(_L.lpc_batch_init_split(self._h, b.ctypes.data, d.ctypes.data, d.shape[0], first_id))
+        else:
+            i = np.ascontiguousarray(ids, dtype=np.int64)
+            assert i.shape == (self.n_stores,)
+            _check(_L.lpc_batch_init_split_ids(self._h, b.ctypes.data, d.ctypes.data, d.shape[0], i.ctypes.data))
 
     def fixpoint(self, objective_var=-1, **kw):
         o, r = _opts(**kw), BatchResult()

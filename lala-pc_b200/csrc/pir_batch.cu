@@ -356,12 +356,12 @@ __global__ void k_pir_search(TableDev t, const int2* roots, int n_stores, int sb
 
 // EPS decomposition: store k := base with decision j halved according to bit j of (first_id + k).
 __global__ void k_batch_init_split(int2* stores, int nvars, int n_stores, const int2* base, const int* dvars, int ndec,
-                                   long long first_id) {
+                                   long long first_id, const long long* ids) {
   for(int k = blockIdx.x; k < n_stores; k += gridDim.x) {
     int2* S = stores + (size_t)k * nvars;
     for(int v = threadIdx.x; v < nvars; v += blockDim.x) S[v] = base[v];
     __syncthreads();
-    const long long id = first_id + k;
+    const long long id = ids ? ids[k] : first_id + k;
     for(int j = threadIdx.x; j < ndec; j += blockDim.x) {
       const int v = dvars[j];
       const int2 d = base[v];
@@ -463,8 +463,22 @@ int lpc_batch_read(const lpc_batch* b, int32_t first, int32_t n, int32_t* lbub) 
   return LPC_OK;
 }
 
+static int batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                            int64_t first_id, const int64_t* ids);
+
 int lpc_batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_t* decision_vars, int32_t n_decisions,
                          int64_t first_id) {
+  return batch_init_split(b, base_lbub, decision_vars, n_decisions, first_id, nullptr);
+}
+
+int lpc_batch_init_split_ids(lpc_batch* b, const int32_t* base_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                             const int64_t* ids) {
+  LPC_REQUIRE(ids != nullptr || (b && b->n_stores == 0), "null ids");
+  return batch_init_split(b, base_lbub, decision_vars, n_decisions, 0, ids);
+}
+
+static int batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                            int64_t first_id, const int64_t* ids) {
   LPC_REQUIRE(b && base_lbub && (n_decisions == 0 || decision_vars), "null argument");
   LPC_REQUIRE(n_decisions >= 0 && n_decisions < 63, "bad n_decisions");
   for(int j = 0; j < n_decisions; ++j) LPC_REQUIRE(decision_vars[j] >= 0 && decision_vars[j] < b->nvars, "decision variable out of range");
@@ -475,12 +489,18 @@ int lpc_batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_t* 
   LPC_CUDA(cudaMalloc((void**)&d_dec, std::max(n_decisions, 1) * sizeof(int)));
   LPC_CUDA(cudaMemcpy(d_base, base_lbub, (size_t)b->nvars * 8, cudaMemcpyHostToDevice));
   if(n_decisions) LPC_CUDA(cudaMemcpy(d_dec, decision_vars, n_decisions * sizeof(int), cudaMemcpyHostToDevice));
-  k_batch_init_split<<<std::min(b->n_stores, 148 * 16), 256>>>(b->d, b->nvars, b->n_stores, d_base, d_dec, n_decisions, first_id);
+  long long* d_ids = nullptr;
+  if(ids) {
+    LPC_CUDA(cudaMalloc((void**)&d_ids, (size_t)b->n_stores * 8));
+    LPC_CUDA(cudaMemcpy(d_ids, ids, (size_t)b->n_stores * 8, cudaMemcpyHostToDevice));
+  }
+  k_batch_init_split<<<std::min(b->n_stores, 148 * 16), 256>>>(b->d, b->nvars, b->n_stores, d_base, d_dec, n_decisions, first_id, d_ids);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   LPC_CUDA(cudaDeviceSynchronize());
   cudaFree(d_base);
   cudaFree(d_dec);
+  cudaFree(d_ids);
   return LPC_OK;
 }
 

@@ -373,10 +373,11 @@ def config5(scale=1.0, seed=SEED_BASE + 5):
     return PcNetwork(props, terms, store, s.astype(np.int32), dict(nvars=nvars, nprops=len(props), nterms=len(terms), seed=seed))
 
 
-def eps_stores(base_store, decision_vars, first_id, n):
-    """Host restatement of lpc_batch_init_split (include/lpc.h): subproblem id bit j halves variable d_j."""
+def eps_stores(base_store, decision_vars, first_id, n, ids=None):
+    """Host restatement of lpc_batch_init_split(_ids) (include/lpc.h): subproblem id bit j halves variable d_j."""
     out = np.repeat(base_store[None, :, :], n, axis=0).copy()
-    ids = first_id + np.arange(n, dtype=np.int64)
+    ids = first_id + np.arange(n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+    assert ids.shape == (n,)
     for j, v in enumerate(decision_vars):
         lb, ub = int(base_store[v, 0]), int(base_store[v, 1])
         mid = lb + ((ub - lb) >> 1)

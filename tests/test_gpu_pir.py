@@ -293,6 +293,21 @@ def test_config4_batched_parity(L, O, W):
     assert np.array_equal(buf[ok], want[ok]) and res2.n_bot == res.n_bot
 
 
+def test_batch_init_split_with_explicit_ids(L, O, W):
+    """lpc_batch_init_split_ids == the host restatement for the scrambled ids a rank of an 8-GPU run gets."""
+    from lala_pc_b200 import sharding
+    net = W.config4_base()
+    root, _ = O.pir_fixpoint(net.store, net.records)
+    dec, obj = W.eps_decisions(net.records, root, n=24)
+    dec = dec[:sharding.decision_bits(8, base_bits=6)]
+    ids = sharding.shard_ids(5, 8, 64)
+    t = L.Table(net.records, net.nvars)
+    b = L.Batch(t, 64)
+    b.init_split(root, dec, ids=ids)
+    assert np.array_equal(b.read(), W.eps_stores(root, dec, 0, 64, ids=ids))
+    b.close()
+
+
 def test_batch_tables_larger_than_shared_memory(L, O, W):
     """A table that does not fit next to the store ring in shared memory is read through L1/L2 instead."""
     net = W.pir_network(4_000, 30_000, W.SEED_BASE + 41, window=512, value_range=1024)

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-N_PER_RANK = 96
+N_PER_RANK = 128
 
 
 def _free_port():
@@ -27,8 +27,8 @@ def _shard_record(rank, world, n_per_rank):
     root, _ = O.pir_fixpoint(net.store, net.records)
     dec, obj = W.eps_decisions(net.records, root, n=24)
     dec = dec[:sharding.decision_bits(world, base_bits=7)]
-    first = sharding.shard_first_id(rank, n_per_rank)
-    stores = W.eps_stores(root, dec, first, n_per_rank)
+    ids = sharding.shard_ids(rank, world, n_per_rank)
+    stores = W.eps_stores(root, dec, 0, n_per_rank, ids=ids)
     out, flags, _, _, _ = O.pir_batch_fixpoint(stores, net.records, threads=2)
     bot = (flags & 1) != 0
     sol = ((flags & 2) != 0) & ~bot
@@ -72,5 +72,13 @@ def test_sharding_helpers():
     from lala_pc_b200 import sharding
     assert [sharding.decision_bits(w) for w in (1, 2, 4, 8)] == [16, 17, 18, 19]
     assert sharding.shard_first_id(3, 65536) == 3 * 65536
+    assert sharding.shard_ids(0, 1, 1000).tolist() == list(range(1000))       # a single rank keeps the id order
+    for world in (2, 4, 8):
+        parts = [sharding.shard_ids(r, world, 4096) for r in range(world)]
+        allids = np.concatenate(parts)
+        assert sorted(allids.tolist()) == list(range(world * 4096))           # a partition of the id space
+        for p in parts:                                                        # ... into uniform samples: no fixed bit
+            for j in range((world * 4096 - 1).bit_length()):
+                assert 0.4 < float(((p >> j) & 1).mean()) < 0.6
     red = torch.tensor([1, 2, 3, 4], dtype=torch.int64)
     assert sharding.allreduce_record(red, None).tolist() == [1, 2, 3, 4]
