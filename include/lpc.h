@@ -155,6 +155,13 @@ int lpc_batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_t* 
 int lpc_batch_init_split_ids(lpc_batch* b, const int32_t* base_lbub, const int32_t* decision_vars, int32_t n_decisions,
                              const int64_t* ids);
 
+/* A promise that makes the change-driven modes incremental: every store of the batch is a fixpoint of the table except
+ * possibly on these `n` variables (e.g. the decision variables of an EPS split of a root fixpoint). The first sweep of
+ * lpc_batch_fixpoint (LPC_MODE_WORKLIST) and the root node of a change-driven lpc_batch_search then only evaluate the
+ * propagators incident to them. n = -1 withdraws the promise (default): the first sweep evaluates every propagator. A false promise gives an
+ * under-propagated store; LPC_MODE_SWEEP ignores it. */
+int lpc_batch_set_seeds(lpc_batch* b, const int32_t* vars, int32_t n);
+
 typedef struct lpc_batch_result {
   int64_t n_bot;         /* stores that failed */
   int64_t n_solution;    /* non-failed stores on which every propagator is entailed (is_extractable) */
@@ -167,7 +174,9 @@ typedef struct lpc_batch_result {
   int32_t reserved;
 } lpc_batch_result;
 
-/* Fixpoint of every store of the batch. objective_var < 0: no objective. */
+/* Fixpoint of every store of the batch. objective_var < 0: no objective. opts.mode: LPC_MODE_SWEEP and LPC_MODE_AUTO =
+ * dense sweeps (every propagator every sweep), LPC_MODE_WORKLIST = change-driven: a 32-record group is re-evaluated only
+ * when a variable of one of its records changed (pays off when changes stay local). Same fixpoints either way. */
 int lpc_batch_fixpoint(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var, lpc_batch_result* r);
 int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var);
 int lpc_batch_collect(lpc_batch* b, lpc_batch_result* r);
@@ -193,6 +202,9 @@ typedef struct lpc_search_opts {
   int32_t max_depth;      /* snapshots per block stack (default 64) */
   int32_t objective_var;  /* < 0: none; else best_bound = min over solutions of lb(objective_var) */
   uint64_t stream;
+  int32_t change_driven;  /* 1 (default): a node's fixpoint starts from the propagators of the branched variable only and
+                             re-evaluates 32-record groups as their variables change; 0: dense sweeps at every node */
+  int32_t reserved;
 } lpc_search_opts;
 
 typedef struct lpc_search_result {

@@ -44,7 +44,7 @@ class FixpointResult(ctypes.Structure):
 
 class SearchOpts(ctypes.Structure):
     _fields_ = [("max_nodes", ctypes.c_int64), ("max_depth", ctypes.c_int32), ("objective_var", ctypes.c_int32),
-                ("stream", ctypes.c_uint64)]
+                ("stream", ctypes.c_uint64), ("change_driven", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class SearchResult(ctypes.Structure):
@@ -118,6 +118,7 @@ SIGNATURES = {
     "lpc_batch_read": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "lpc_batch_init_split": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64]),
     "lpc_batch_init_split_ids": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    "lpc_batch_set_seeds": (ctypes.c_int, [_vp, _vp, _i32]),
     "lpc_batch_fixpoint": (ctypes.c_int, [_vp, ctypes.POINTER(FixpointOpts), _i32, ctypes.POINTER(BatchResult)]),
     "lpc_batch_fixpoint_async": (ctypes.c_int, [_vp, ctypes.POINTER(FixpointOpts), _i32]),
     "lpc_batch_collect": (ctypes.c_int, [_vp, ctypes.POINTER(BatchResult)]),
@@ -439,17 +440,27 @@ class Batch:
     def device_ptr(self):
         return _L.lpc_batch_device_ptr(self._h)
 
+    def set_seeds(self, variables):
+        """Promise that the stores are fixpoints of the table except on `variables` (None withdraws it): include/lpc.h."""
+        if variables is None:
+            _check(_L.lpc_batch_set_seeds(self._h, None, -1))
+        else:
+            v = np.ascontiguousarray(variables, dtype=np.int32)
+            _check(_L.lpc_batch_set_seeds(self._h, v.ctypes.data, v.shape[0]))
+
     @property
     def reduction_device_ptr(self):
         return _L.lpc_batch_reduction_device_ptr(self._h)
 
-    def search(self, branch_vars, objective_var=-1, max_nodes=0, max_depth=64, stream=0, want_per_store=True):
+    def search(self, branch_vars, objective_var=-1, max_nodes=0, max_depth=64, stream=0, want_per_store=True,
+               change_driven=True):
         """Depth-first search from every store of the batch (include/lpc.h: lpc_batch_search).
         Returns (SearchResult, int64 [n_stores, 6] {solutions, nodes, fails, best, incomplete, unknown_leaves} or None)."""
         bv = np.ascontiguousarray(branch_vars, dtype=np.int32)
         o, r = SearchOpts(), SearchResult()
         _L.lpc_search_default_opts(ctypes.byref(o))
         o.max_nodes, o.max_depth, o.objective_var, o.stream = max_nodes, max_depth, objective_var, stream
+        o.change_driven = int(change_driven)
         per = np.zeros((self.n_stores, 6), dtype=np.int64) if want_per_store else None
         _check(_L.lpc_batch_search(self._h, bv.ctypes.data, bv.shape[0], ctypes.byref(o), ctypes.byref(r),
                                    per.ctypes.data if want_per_store else None))

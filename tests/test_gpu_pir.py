@@ -293,6 +293,37 @@ def test_config4_batched_parity(L, O, W):
     assert np.array_equal(buf[ok], want[ok]) and res2.n_bot == res.n_bot
 
 
+def test_config4_batched_modes_and_seeds(L, O, W):
+    """Dense sweeps, change-driven sweeps and change-driven sweeps seeded with the decision variables (the stores are the
+    root fixpoint except there) reach the same flags and the same non-failed stores; the seeded run evaluates the fewest
+    propagators."""
+    net = W.config4_base()
+    root, st = O.pir_fixpoint(net.store, net.records)
+    dec, obj = W.eps_decisions(net.records, root)
+    n = 1024
+    stores = W.eps_stores(root, dec, 777, n)
+    want, wflags, _, _, _ = O.pir_batch_fixpoint(stores, net.records, threads=8)
+    ok = (wflags & 1) == 0
+    t = L.Table(net.records, net.nvars)
+    b = L.Batch(t, n)
+    ded = {}
+    for name, mode, seeds in (("sweep", L.MODE_SWEEP, None), ("auto", L.MODE_WORKLIST, None), ("seeded", L.MODE_WORKLIST, dec)):
+        b.write(stores)
+        b.set_seeds(seeds)
+        res = b.fixpoint(objective_var=obj, mode=mode)
+        assert np.array_equal(b.flags(), wflags), name
+        assert np.array_equal(b.read()[ok], want[ok]), name
+        assert res.best_bound == int(want[ok][:, obj, 0].min()), name
+        ded[name] = res.deductions
+    assert ded["seeded"] < ded["auto"] < ded["sweep"]
+    # the promise is per batch handle and can be withdrawn
+    b.set_seeds(None)
+    b.write(stores)
+    again = b.fixpoint(objective_var=obj, mode=L.MODE_WORKLIST).deductions      # evaluation counts depend on warp timing
+    assert abs(again - ded["auto"]) < 0.1 * ded["auto"] and again > ded["seeded"]
+    b.close()
+
+
 def test_batch_init_split_with_explicit_ids(L, O, W):
     """lpc_batch_init_split_ids == the host restatement for the scrambled ids a rank of an 8-GPU run gets."""
     from lala_pc_b200 import sharding

@@ -81,7 +81,7 @@ def test_device_search_matches_oracle_small_models(L):
         t = L.Table(recs, nvars)
         b = L.Batch(t, 16)
         b.write(roots)
-        r, got = b.search(bv, objective_var=2)
+        r, got = b.search(bv, objective_var=2, change_driven=bool(trial & 1))
         assert np.array_equal(got, want), (trial, got.tolist(), want.tolist())
         assert r.n_solutions == want[:, 0].sum() and r.n_nodes == want[:, 1].sum() and r.n_fails == want[:, 2].sum()
         assert r.best_bound == want[:, 3].min()
@@ -133,7 +133,15 @@ def test_device_search_config4_model_with_node_budget(L):
     t = L.Table(net.records, net.nvars)
     b = L.Batch(t, 256)
     b.write(stores)
-    r, got = b.search(bv, objective_var=obj, max_nodes=40, max_depth=32)
+    r, got = b.search(bv, objective_var=obj, max_nodes=40, max_depth=32, change_driven=False)
     assert np.array_equal(got, want), np.flatnonzero((got != want).any(1))[:8].tolist()
     assert r.n_nodes == want[:, 1].sum() and r.n_nodes > 256
+    # the roots are the root fixpoint except on the decision variables: with that promise the root nodes are incremental too
+    # change-driven nodes: every fixpoint starts from the propagators of the branched variable; with the promise that the
+    # roots are the root fixpoint except on the decision variables the root nodes are incremental too. Same records.
+    r1, got1 = b.search(bv, objective_var=obj, max_nodes=40, max_depth=32, change_driven=True)
+    assert np.array_equal(got1, want) and r1.deductions < r.deductions
+    b.set_seeds(dec)
+    r2, got2 = b.search(bv, objective_var=obj, max_nodes=40, max_depth=32, change_driven=True)
+    assert np.array_equal(got2, want) and r2.deductions < r1.deductions
     b.close()
