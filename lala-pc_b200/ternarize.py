@@ -29,8 +29,8 @@ class Ternarizer:
     """Accumulates records [op, x, y, z] (lala-core Sig codes, include/lpc.h) and the domains of the variables it adds.
 
     `store` is the [nvars, 2] domain array of the formula's own variables; `result()` returns the records and the
-    extended store. Temporaries start at top (the first fixpoint narrows them), constants at their value, reified
-    results at [0, 1]."""
+    extended store. Temporaries start at the interval hull of their definition (see `_hull`), constants at their value,
+    reified results at [0, 1]."""
 
     def __init__(self, store):
         self.doms = [tuple(int(b) for b in d) for d in np.asarray(store).reshape(-1, 2)]
@@ -52,11 +52,40 @@ class Ternarizer:
     def _emit(self, op, x, y, z):
         self.records.append((op, x, y, z))
 
+    def _hull(self, op, y, z):
+        """Initial domain of t = y op z from the operands' domains. Not an optimisation only: a temporary left at top
+        meets rules such as `x = 0 => y >= z.lb + 1` (pir.hpp:750-753) that turn an infinite bound into a finite one next
+        to INT_MIN, after which `+` wraps around (the reference is undefined there, include/lpc.h) and the result
+        depends on the evaluation order. An infinite operand bound keeps the corresponding side infinite."""
+        (yl, yu), (zl, zu) = self.doms[y], self.doms[z]
+        inf = lambda b: b in (INT_MIN, INT_MAX)
+        if op == ADD:
+            lo = INT_MIN if inf(yl) or inf(zl) else yl + zl
+            hi = INT_MAX if inf(yu) or inf(zu) else yu + zu
+        elif op == "sub":
+            lo = INT_MIN if inf(yl) or inf(zu) else yl - zu
+            hi = INT_MAX if inf(yu) or inf(zl) else yu - zl
+        elif op == MUL:
+            if any(inf(b) for b in (yl, yu, zl, zu)):
+                return INT_MIN, INT_MAX
+            p = [yl * zl, yl * zu, yu * zl, yu * zu]
+            lo, hi = min(p), max(p)
+        elif op == MIN:
+            lo, hi = min(yl, zl), min(yu, zu)
+        elif op == MAX:
+            lo, hi = max(yl, zl), max(yu, zu)
+        else:   # divisions: |y / z| <= |y|
+            if inf(yl) or inf(yu):
+                return INT_MIN, INT_MAX
+            m = max(abs(yl), abs(yu))
+            lo, hi = -m, m
+        return max(lo, INT_MIN), min(hi, INT_MAX)
+
     def _def(self, op, y, z, boolean=False):
         """A fresh variable t with t = y op z; identical definitions share one variable."""
         key = (op, y, z)
         if key not in self._cse:
-            t = self._fresh(0, 1) if boolean else self._fresh()
+            t = self._fresh(0, 1) if boolean else self._fresh(*self._hull(op, y, z))
             self._emit(op, t, y, z)
             self._cse[key] = t
         return self._cse[key]
@@ -79,7 +108,7 @@ class Ternarizer:
             a, b = self.term(t[1]), self.term(t[2])
             key = ("sub", a, b)
             if key not in self._cse:
-                d = self._fresh()
+                d = self._fresh(*self._hull("sub", a, b))
                 self._emit(ADD, a, d, b)
                 self._cse[key] = d
             return self._cse[key]
