@@ -180,6 +180,46 @@ def test_random_networks(L, O):
     assert n_ok >= 40
 
 
+def test_fallback_paths_of_the_tile_kernel(L, O):
+    """Propagators the lane tiles cannot take in int32 go through the term-by-term routine inside the same kernel: sums
+    of more than 32 terms, right-hand sides beyond 2^30, term bounds beyond 2^24, infinite and near-infinite domains.
+    Mixed with ordinary propagators in one table so that tiles, wild lanes and the long list all run in one fixpoint."""
+    from lala_pc_b200 import pcflat
+    rng = np.random.default_rng(99)
+    NI, PI = -2**31, 2**31 - 1
+    n_ok = 0
+    for trial in range(60):
+        nvars = 48
+        a = rng.integers(-4, 9, (nvars, 2))
+        store = np.stack([a.min(1), a.max(1)], axis=1).astype(np.int32)
+        store[rng.random(nvars) < 0.3] = (0, 1)
+        sol = rng.integers(store[:, 0], store[:, 1] + 1)             # a planted assignment keeps most networks alive
+
+        def val(ts):
+            return int(sum(c * int(sol[v]) for c, v in ts))
+        vs = rng.permutation(nvars)
+        forms = []
+        # a long sum (40 lanes > 32) and its reified twin
+        ts = [(int(rng.choice([1, 1, 2, -1])), int(v)) for v in vs[:40]]
+        forms.append(pcflat.to_tree(1, ts, val(ts) + int(rng.integers(0, 6)), -1))
+        store[int(vs[41])] = (0, 1)
+        forms.append(pcflat.to_tree(2, ts[:36], val(ts[:36]) + int(rng.integers(-3, 4)), int(vs[41])))
+        # huge right-hand sides (static fallback) and huge coefficients (dynamic fallback)
+        forms.append(pcflat.to_tree(1, [(1, int(vs[0])), (1, int(vs[1]))], int(rng.choice([2**30, 2**30 + 5, PI - 1])), -1))
+        big = [(2**23, int(vs[2])), (3, int(vs[3]))]
+        forms.append(pcflat.to_tree(7, big, val(big) - int(rng.integers(0, 2**24)), -1))
+        eq3 = [(1, int(vs[4])), (-1, int(vs[5])), (1, int(vs[6]))]
+        forms.append(pcflat.to_tree(9, eq3, val(eq3), -1))
+        forms.append(pcflat.to_tree(10, [(1, int(vs[7])), (2, int(vs[8]))], 0, int(vs[9])))
+        store[int(vs[9])] = (NI, PI) if trial % 3 == 0 else (-40, 40)
+        forms += random_pc(rng, nvars)[:2]
+        for v in vs[42:45]:                                          # infinite, half-infinite and large domains
+            store[int(v)] = [(NI, PI), (NI, 7), (-3, PI), (-2**27, 2**27), (2**25, 2**25 + 3)][int(rng.integers(0, 5))]
+        _, r, st = check_parity(L, O, forms, store, f"fallback {trial}")
+        n_ok += not st.is_bot
+    assert n_ok >= 10
+
+
 def test_errors(L):
     with pytest.raises(L.LpcError):
         L.PcTable(np.array([[99, 0, 1, 0, -1]], dtype=np.int32), np.array([[1, 0]], dtype=np.int32), 2)     # bad kind
