@@ -140,6 +140,17 @@ LPC_HD void deduce_regs(int op, Itv& r1, Itv& r2, Itv& r3) {
       break;
     }
     case D_MUL: {
+      // Both factors fixed (and small enough for an exact int32 product): x <- x meet {y*z}, and neither mul_inv can
+      // move a factor - with x = {p} the corner quotients of pir.hpp:711-717 are p/z = y and p/y = z exactly, with
+      // p = 0 they give 0 for the factor that must be 0; an empty x fails the store either way. Multiplication pins
+      // its factors early (config 2: 99.9 % of the MUL records after one sweep), and a warp whose 32 records all take
+      // this branch skips the eight divisions of the general rule.
+      if(yl == yu && zl == zu && (unsigned)(yl + 46340) <= 92680u && (unsigned)(zl + 46340) <= 92680u) {
+        const int p = yl * zl;
+        r1.lb = max(xl, p);
+        r1.ub = min(xu, p);
+        break;
+      }
       if(yl != LPC_MINF && yu != LPC_INF && zl != LPC_MINF && zu != LPC_INF) {
         int t1 = wmul(yl, zl), t2 = wmul(yl, zu), t3 = wmul(yu, zl), t4 = wmul(yu, zu);
         r1.lb = max(xl, min(min(t1, t2), min(t3, t4)));
