@@ -52,4 +52,36 @@ __device__ __forceinline__ GridVote grid_vote_barrier(unsigned long long* words,
   return grid_count_barrier(words, sweep, any_changed ? 1u : 0u, any_bot, smem_slot);
 }
 
+// SM-ordered block ranks. The kernels give block r the r-th contiguous fraction of the (y-sorted) table, so that the
+// gathers of a block fall into one window of the store. Blocks that share an SM share its L1: with ranks handed out in
+// SM order (all blocks of SM 0, then SM 1, ...) the co-resident blocks work on ADJACENT fractions and their windows
+// overlap instead of tripling the SM's L1 footprint. Two steps around a grid barrier the caller already has:
+//   slot = sm_rank_arrive(slots)        before the barrier: this block's arrival number on its SM
+//   r = sm_rank_resolve(slots, slot)    after it: r.below + r.slot is a bijection onto [0, gridDim.x) whatever the
+//                                       block-to-SM placement was; [r.below, r.below + r.here) is the SM's share.
+// `slots`: LPC_SM_SLOTS ints in global memory, zero at launch. Both calls by every thread; the result is block-uniform.
+#define LPC_SM_SLOTS 256
+__device__ __forceinline__ unsigned my_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ __forceinline__ int sm_rank_arrive(int* slots) {
+  __shared__ int s_slot;
+  if(threadIdx.x == 0) s_slot = atomicAdd(&slots[my_smid() & (LPC_SM_SLOTS - 1)], 1);
+  __syncthreads();
+  return s_slot;
+}
+struct SmRank { int below, here, slot; };   // blocks on lower-numbered SMs, blocks on this SM, this block's number among them
+__device__ __forceinline__ SmRank sm_rank_resolve(const int* slots, int slot) {
+  __shared__ int s_below, s_here;
+  if(threadIdx.x < 32) {
+    const int me = (int)(my_smid() & (LPC_SM_SLOTS - 1));
+    int below = 0;
+    for(int j = threadIdx.x; j < me; j += 32) below += reinterpret_cast<const volatile int*>(slots)[j];
+    below = __reduce_add_sync(0xffffffffu, below);
+    if(threadIdx.x == 0) { s_below = below; s_here = reinterpret_cast<const volatile int*>(slots)[me]; }
+  }
+  __syncthreads();
+  SmRank r;
+  r.below = s_below; r.here = s_here; r.slot = slot;
+  return r;
+}
+
 } // namespace lpc

@@ -57,6 +57,7 @@ struct FixCtl {
   int q_len[4];         // rotating queue-length words (3 in use)
   int scratch[4];
   unsigned long long bar[4];   // rotating vote-carrying barrier words (grid_barrier.cuh; 3 in use)
+  int sm_slots[256];    // blocks arrived per SM (sm_rank_arrive / sm_rank_resolve, grid_barrier.cuh)
 };
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

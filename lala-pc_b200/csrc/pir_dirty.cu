@@ -30,7 +30,7 @@ struct DSeg { int nseg; int u[D_MAX_SEG + 1]; };   // opcode segments in units o
 template <bool HAS_DIV>
 __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, DSeg seg, FixCtl* ctl, unsigned char* dmap,
                                                        int n_groups, int map_stride, unsigned switch_groups, int max_sweeps,
-                                                       int stop_on_bot) {
+                                                       int stop_on_bot, int sm_order) {
   __shared__ unsigned long long s_vote;
   __shared__ unsigned s_cnt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -38,12 +38,16 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
   const long long gthreads = (long long)gridDim.x * DTPB;
   int nbar = 0;
   bool bot;
+  const int sm_slot = sm_order ? sm_rank_arrive(ctl->sm_slots) : 0;
   {
     int f = 0;
     for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = store[i]; f |= v.x > v.y; }
     for(long long i = gtid; i < 3LL * map_stride; i += gthreads) dmap[i] = 0;
     bot = grid_vote_barrier(ctl->bar, nbar++, false, f != 0, &s_vote).bot;
   }
+  // this block's fraction of every segment: its rank in SM order (grid_barrier.cuh)
+  long long bid = blockIdx.x;
+  if(sm_order) { const SmRank r = sm_rank_resolve(ctl->sm_slots, sm_slot); bid = r.below + r.slot; }
   int sweeps = 0, dense = 0;
   bool any_changed = false;
   unsigned long long deductions = 0;
@@ -63,9 +67,9 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
     for(int s = 0; s < seg.nseg; ++s) {
       // this block's contiguous share of the segment, cut at group boundaries (32 units = 64 records)
       const long long s0 = seg.u[s], s1 = seg.u[s + 1], len = s1 - s0;
-      long long b0 = s0 + len * blockIdx.x / gridDim.x, b1 = s0 + len * (blockIdx.x + 1) / gridDim.x;
-      b0 = blockIdx.x == 0 ? s0 : max(s0, b0 & ~31LL);
-      b1 = blockIdx.x == gridDim.x - 1 ? s1 : max(s0, b1 & ~31LL);
+      long long b0 = s0 + len * bid / gridDim.x, b1 = s0 + len * (bid + 1) / gridDim.x;
+      b0 = bid == 0 ? s0 : max(s0, b0 & ~31LL);
+      b1 = bid == gridDim.x - 1 ? s1 : max(s0, b1 & ~31LL);
       const int u0 = (int)b0, u1 = (int)b1;
       if(u0 >= u1) continue;
       const int a0 = u0 & ~31;
@@ -179,6 +183,13 @@ int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opt
     s->dirty_cap = 3LL * map_stride;
   }
   if(!t->dirty_ready) {
+    // the kernel's working set is the store window of its SM's table fractions: all of the unified L1 / shared memory
+    // array as L1 (LPC_CARVE=0 leaves the driver's default)
+    const char* ce = getenv("LPC_CARVE");
+    if(!ce || atoi(ce)) {
+      LPC_CUDA(cudaFuncSetAttribute(k_pir_dirty<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+      LPC_CUDA(cudaFuncSetAttribute(k_pir_dirty<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+    }
     for(int d = 0; d < 2; ++d)
       LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->dirty_blocks_per_sm[d], d ? k_pir_dirty<true> : k_pir_dirty<false>, DTPB, 0));
     t->dirty_ready = true;
@@ -202,7 +213,9 @@ int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opt
   FixCtl* ctl = s->d_ctl;
   unsigned char* dmap = s->d_dirty;
   int ng = n_groups, ms = map_stride, max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
-  void* args[] = {&td, &store, &seg, &ctl, &dmap, &ng, &ms, &switch_groups, &max_sweeps, &stop};
+  int sm_order = 1;   // LPC_SMORDER=0: fractions in blockIdx order (A/B runs)
+  if(const char* e = getenv("LPC_SMORDER")) sm_order = atoi(e);
+  void* args[] = {&td, &store, &seg, &ctl, &dmap, &ng, &ms, &switch_groups, &max_sweeps, &stop, &sm_order};
   void* k = t->has_div ? (void*)k_pir_dirty<true> : (void*)k_pir_dirty<false>;
   LPC_CUDA(cudaLaunchCooperativeKernel(k, dim3(grid), dim3(DTPB), args, 0, st));
   g_launches++;

@@ -131,7 +131,7 @@ template <> struct Unit<1> {
 template <bool HAS_DIV, bool TRACK, int RPT, int MINB, bool PIPE>
 __global__ void __launch_bounds__(TPB, MINB) k_pir_fixpoint(TableDev t, int2* store, SegTable seg, FixCtl* ctl,
                                                             WlState w, int max_sweeps, int stop_on_bot,
-                                                            unsigned switch_at, int use_vote) {
+                                                            unsigned switch_at, int use_vote, int sm_order) {
   cg::grid_group grid = cg::this_grid();
   __shared__ unsigned long long s_vote;
   const int tid = threadIdx.x;
@@ -143,12 +143,22 @@ __global__ void __launch_bounds__(TPB, MINB) k_pir_fixpoint(TableDev t, int2* st
   volatile int* vqlen = ctl->q_len;   // 3 rotating queue-length words
 
   // ---- prologue: a store created with an empty variable is at bot before the first sweep ----
+  const int sm_slot = sm_order ? sm_rank_arrive(ctl->sm_slots) : 0;
   {
     int f = 0;
     for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = store[i]; f |= v.x > v.y; }
     if(__syncthreads_or(f) && tid == 0) atomicOr(&ctl->is_bot, 1);
   }
   grid.sync();
+  // which fraction of every segment this block sweeps: its rank in SM order (co-resident blocks get adjacent fractions)
+  // sm_order 1: this block's own fraction; 2: the SM's blocks interleave over the SM's fraction (one moving window)
+  long long bid = blockIdx.x, bspan = 1;
+  int bslot = 0;
+  if(sm_order) {
+    const SmRank r = sm_rank_resolve(ctl->sm_slots, sm_slot);
+    if(sm_order == 2 && !PIPE) { bid = r.below; bspan = r.here; bslot = r.slot; }
+    else bid = r.below + r.slot;
+  }
   int sweeps = 0, dense = 0;
   bool any_changed = false;
   bool bot = *vbot != 0;
@@ -165,8 +175,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_pir_fixpoint(TableDev t, int2* st
     int f = 0, nchg = 0;
     for(int s = 0; s < seg.nseg; ++s) {
       const long long sq0 = seg.q[s], len = seg.q[s + 1] - sq0;
-      const int u0 = (int)((sq0 + len * blockIdx.x / gridDim.x) * UPQ);
-      const int u1 = (int)((sq0 + len * (blockIdx.x + 1) / gridDim.x) * UPQ);
+      const int u0 = (int)((sq0 + len * bid / gridDim.x) * UPQ);
+      const int u1 = (int)((sq0 + len * (bid + bspan) / gridDim.x) * UPQ);
       if constexpr(PIPE) {
         // two-stage software pipeline: while unit i is evaluated, the bounds of unit i + 1 and the records of unit
         // i + 2 are in flight, so a thread waits for memory once per segment instead of twice per unit. Indices past
@@ -201,7 +211,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_pir_fixpoint(TableDev t, int2* st
         }
       }
       else
-      for(int u = u0 + tid; u < u1; u += TPB) {
+      for(int u = u0 + bslot * TPB + tid; u < u1; u += (int)bspan * TPB) {
         Unit<RPT> r;
         r.load(t, u);
         int2 a[RPT], b[RPT], c[RPT];
@@ -342,7 +352,7 @@ __global__ void k_ask_all(TableDev t, const int2* store, unsigned long long* cou
   if((threadIdx.x & 31) == 0 && cnt) atomicAdd(count, (unsigned long long)cnt);
 }
 
-typedef void (*fix_kernel_t)(TableDev, int2*, SegTable, FixCtl*, WlState, int, int, unsigned, int);
+typedef void (*fix_kernel_t)(TableDev, int2*, SegTable, FixCtl*, WlState, int, int, unsigned, int, int);
 
 // The (records per thread, min blocks per SM) variants that are built; LPC_RPT / LPC_MINB select one for tuning.
 struct Variant { int rpt, minb; fix_kernel_t k[2][2]; };
@@ -445,6 +455,10 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
     SegTable sg = build_segments(t);
     t->seg_n = sg.nseg;
     for(int i = 0; i <= sg.nseg; ++i) t->seg_q[i] = sg.q[i];
+    const char* ce = getenv("LPC_CARVE");   // see pir_dirty.cu
+    if(!ce || atoi(ce))
+      for(int tr = 0; tr < 2; ++tr)
+        LPC_CUDA(cudaFuncSetAttribute((const void*)var.k[t->has_div ? 1 : 0][tr], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     for(int tr = 0; tr < 2; ++tr)
       LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[tr], var.k[t->has_div ? 1 : 0][tr], TPB, 0));
     t->plan_ready = true;
@@ -489,7 +503,9 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
   // a table with at most a couple of units per thread is swept as ONE segment: with a handful of records per block the
   // per-segment passes only add dependent memory round trips (config 1: 3 segments x 2 round trips per sweep)
   if(units <= 2LL * grid * TPB) { seg.nseg = 1; seg.q[0] = 0; seg.q[1] = (int)(t->dev.n_pad / 4); }
-  void* args[] = {&td, &store, &seg, &ctl, &w, &max_sweeps, &stop, &switch_at, &use_vote};
+  int sm_order = 2;   // LPC_SMORDER=0: fractions in blockIdx order, 1: in SM order, 2: interleaved per SM (A/B runs)
+  if(const char* e = getenv("LPC_SMORDER")) sm_order = atoi(e);
+  void* args[] = {&td, &store, &seg, &ctl, &w, &max_sweeps, &stop, &switch_at, &use_vote, &sm_order};
   LPC_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(grid), dim3(TPB), args, 0, st));
   g_launches++;
   LPC_CUDA(cudaEventRecord(s->ev1, st));
