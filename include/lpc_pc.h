@@ -2,8 +2,8 @@
  *
  * The reference keeps each PC propagator as a heap-allocated variant tree (pc::Formula / pc::Term,
  * include/lala/formula.hpp, include/lala/terms.hpp) and walks it in PC::deduce(int) (include/lala/pc.hpp:671-680).
- * Here the in-scope shapes are flattened into one 16-byte header + a run of {coef, var} terms, so that a sweep is a
- * streaming read instead of a pointer chase. Each flat kind names the reference tree it stands for; the result of
+ * Here the common shapes are flattened into one 16-byte header + a run of {coef, var} terms, so that a sweep is a
+ * streaming read instead of a pointer chase; every other shape keeps its tree as a prefix-encoded stream (LPC_PC_TREE). Each flat kind names the reference tree it stands for; the result of
  * `deduce` on it is bit-identical to walking that tree (tests/test_gpu_pc.py against oracle/pc_oracle.cpp).
  *
  * Same conventions as lpc.h (status codes, stores as {lb,ub} int32 pairs, one in-flight call per handle).
@@ -40,7 +40,17 @@ enum lpc_pc_kind {
   /* Equality(sum, Constant rhs):        sum = rhs                                           formula.hpp:676-680 */
   LPC_PC_LIN_EQ = 9,
   /* Equality(sum, Variable bvar):       sum = z, z in `bvar`                                formula.hpp:672-681 */
-  LPC_PC_LIN_EQ_VAR = 10
+  LPC_PC_LIN_EQ_VAR = 10,
+  /* Any other pc::Formula (formula.hpp:955-1002) over any pc::Term (terms.hpp:628-652): the tree itself, prefix encoded
+   * as int32 words in the propagator's term slots (n_terms = ceil(words / 2), zero padded; rhs and bvar unused):
+   *   terms     1 k = Constant | 2 v = Variable | 3 t = Neg | 4 t = Abs | 5 a b = Add | 6 a b = Sub | 7 a b = Mul
+   *             | 8 n t1..tn = Nary<Add> | 9 a b = Min | 10 a b = Max
+   *   formulas  20 v = VariableLiteral | 21 v = its negation | 22 l r = (l <= r) | 23 l r = (l > r) | 24 l r = (l = r)
+   *             | 25 l r = (l != r) | 26 f g = and | 27 f g = or | 28 f g = equiv | 29 f g = imply | 30 f g = xor
+   * Walked on the device by one thread per propagator exactly as Formula::deduce / Term::embed walk it
+   * (lala-pc_b200/csrc/pc_tree.cuh); terms up to 5 levels and connectives up to 4 levels deep, deeper streams are
+   * refused with LPC_ERR_UNSUPPORTED. Interval stores only. */
+  LPC_PC_TREE = 11
 };
 
 typedef struct lpc_pc_prop {

@@ -12,8 +12,41 @@
 namespace lpc {
 
 enum PcKind : int { PC_LIN_LE = 1, PC_REIF_LIN_LE = 2, PC_EQ = 3, PC_NEQ = 4, PC_CLAUSE = 5, PC_ABS_EQ = 6,
-                    PC_LIN_GE = 7, PC_LIN_GT = 8, PC_LIN_EQ = 9, PC_LIN_EQ_VAR = 10 };
-__host__ __device__ __forceinline__ bool pc_is_linear(int kind) { return kind == PC_LIN_LE || kind == PC_REIF_LIN_LE || kind >= PC_LIN_GE; }
+                    PC_LIN_GE = 7, PC_LIN_GT = 8, PC_LIN_EQ = 9, PC_LIN_EQ_VAR = 10, PC_TREE = 11 };
+__host__ __device__ __forceinline__ bool pc_is_linear(int kind) { return kind == PC_LIN_LE || kind == PC_REIF_LIN_LE || (kind >= PC_LIN_GE && kind <= PC_LIN_EQ_VAR); }
+// The general tree propagator (pc_tree.cuh); its stream lives in the term array. On the device the interpreter is its
+// own translation unit (pc_tree.cu, built with a register cap so that the kernels can call it through the device ABI
+// whatever their launch bounds are) and is entered through the global-memory accessor below.
+#ifdef LPC_HOST_HARNESS
+template <class Acc> LPC_HD int pc_tree_deduce(Acc& a, const int* words);
+template <class Acc> LPC_HD bool pc_tree_ask(const Acc& a, const int* words);
+#else
+// VStore<Interval<ZLB>> in global memory: gathers + lattice joins at L2.
+struct GlobalAcc {
+  int2* s;
+  mutable int seen_bot;
+  int touched;   // some embed tightened the store: what the fixpoint kernel votes with (a tree propagator's own return
+                 // value can hide a change, formula.hpp:803)
+  __device__ __forceinline__ Itv load(int v) const {
+    const int2 d = __ldcg(&s[v]);
+    seen_bot |= d.x > d.y;
+    return Itv(d.x, d.y);
+  }
+  __device__ __forceinline__ int embed(int v, const Itv& u) {
+    const int2 old = __ldcg(&s[v]);
+    int f = 0;
+    if(u.lb > old.x) { atomicMax(&s[v].x, u.lb); f = 1; }
+    if(u.ub < old.y) { atomicMin(&s[v].y, u.ub); f = 1; }
+    if(f && max(u.lb, old.x) > min(u.ub, old.y)) f |= 2;
+    touched |= f;
+    return f;
+  }
+};
+__device__ int pc_tree_deduce_global(GlobalAcc& a, const int* words);
+__device__ bool pc_tree_ask_global(const GlobalAcc& a, const int* words);
+__device__ __forceinline__ int pc_tree_deduce(GlobalAcc& a, const int* words) { return pc_tree_deduce_global(a, words); }
+__device__ __forceinline__ bool pc_tree_ask(const GlobalAcc& a, const int* words) { return pc_tree_ask_global(a, words); }
+#endif
 __host__ __device__ __forceinline__ bool pc_has_extra_lane(int kind) { return kind == PC_REIF_LIN_LE || kind == PC_LIN_EQ_VAR; }
 
 struct PcTableDev {
@@ -209,6 +242,7 @@ LPC_HD int pc_deduce(Acc& a, const int4 h, const int2* terms) {
       f |= a.embed(x, fjoin(r, Itv(b_neg(r.ub), b_neg(r.lb))));
       return f;
     }
+    case PC_TREE: return pc_tree_deduce(a, reinterpret_cast<const int*>(terms));
     default: return 0;
   }
 }
@@ -255,6 +289,7 @@ LPC_HD bool pc_ask(const Acc& a, const int4 h, const int2* terms) {
       }
       return ((ax.is_bot() && r.is_bot()) || (ax.lb == r.lb && ax.ub == r.ub)) && ax.lb == ax.ub;
     }
+    case PC_TREE: return pc_tree_ask(a, reinterpret_cast<const int*>(terms));
     default: return true;
   }
 }
@@ -371,3 +406,7 @@ LPC_HD bool pc_ask_bits(const BAcc& a, const int4 h, const int2* terms) {
 }
 
 } // namespace lpc
+
+#ifdef LPC_HOST_HARNESS
+#include "pc_tree.cuh"
+#endif

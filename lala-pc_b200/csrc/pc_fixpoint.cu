@@ -15,6 +15,7 @@
 // barrier per sweep.
 #include "lpc_internal.cuh"
 #include "pc_device.cuh"
+#include "pc_tree.cuh"   // tree_check (host) for the table builder
 #include "grid_barrier.cuh"
 
 #include <algorithm>
@@ -29,25 +30,6 @@ constexpr int PC_TPB = 256;
 // tuning runs (tools/pc_probe.py), the default is the fastest measured on config 3 / config 5
 constexpr int PC_NVAR = 5;
 constexpr int PC_VAR_DEFAULT = 0;
-
-// VStore<Interval<ZLB>> in global memory: gathers + lattice joins at L2.
-struct GlobalAcc {
-  int2* s;
-  mutable int seen_bot;
-  __device__ __forceinline__ Itv load(int v) const {
-    const int2 d = __ldcg(&s[v]);
-    seen_bot |= d.x > d.y;
-    return Itv(d.x, d.y);
-  }
-  __device__ __forceinline__ int embed(int v, const Itv& u) {
-    const int2 old = __ldcg(&s[v]);
-    int f = 0;
-    if(u.lb > old.x) { atomicMax(&s[v].x, u.lb); f = 1; }
-    if(u.ub < old.y) { atomicMin(&s[v].y, u.ub); f = 1; }
-    if(f && max(u.lb, old.x) > min(u.ub, old.y)) f |= 2;
-    return f;
-  }
-};
 
 // VStore<NBitset<64>> in global memory: one uint64 per variable, joins by atomicAnd.
 struct GlobalBitAcc {
@@ -74,7 +56,7 @@ template <bool BITS, class Acc> __device__ __noinline__ int pc_step(Acc& acc, co
   if constexpr(BITS) return pc_deduce_bits(acc, h, terms);
   else return pc_deduce(acc, h, terms);
 }
-__device__ __forceinline__ GlobalAcc make_acc(int2* store, GlobalAcc*) { return GlobalAcc{store, 0}; }
+__device__ __forceinline__ GlobalAcc make_acc(int2* store, GlobalAcc*) { return GlobalAcc{store, 0, 0}; }
 __device__ __forceinline__ GlobalBitAcc make_acc(int2* store, GlobalBitAcc*) { return GlobalBitAcc{reinterpret_cast<u64*>(store), 0}; }
 
 // ---- one tile = one warp step ------------------------------------------------------------------------------------------
@@ -311,6 +293,7 @@ __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDe
       f |= pc_step<BITS>(acc, h, t.terms + h.y);
     }
     if(acc.seen_bot) f |= 2;
+    if constexpr(!BITS) f |= acc.touched & 1;
     const GridVote v = grid_vote_barrier(ctl->bar, nbar++, f & 1, f & 2, &s_vote);
     ++sweeps;
     bot |= v.bot;
@@ -392,11 +375,21 @@ int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_
   bool has_linear = false;
   for(int64_t i = 0; i < n_props; ++i) {
     const lpc_pc_prop& p = props[i];
-    if(p.kind < LPC_PC_LIN_LE || p.kind > LPC_PC_LIN_EQ_VAR) { set_error("lpc_pc_table_create: propagator %lld has unsupported kind %d", (long long)i, p.kind); return LPC_ERR_UNSUPPORTED; }
+    if(p.kind < LPC_PC_LIN_LE || p.kind > LPC_PC_TREE) { set_error("lpc_pc_table_create: propagator %lld has unsupported kind %d", (long long)i, p.kind); return LPC_ERR_UNSUPPORTED; }
     if(p.n_terms < 1 || p.n_terms >= (1 << 23) || p.first_term < 0 || (int64_t)p.first_term + p.n_terms > n_terms) { set_error("lpc_pc_table_create: propagator %lld has a bad term range", (long long)i); return LPC_ERR_INVALID; }
+    if(p.kind == LPC_PC_TREE) {   // the term slots hold a prefix-encoded formula (pc_tree.cuh): checked here, walked on the device
+      if(tree_check(reinterpret_cast<const int*>(terms + p.first_term), 2 * p.n_terms, nvars) < 0) {
+        set_error("lpc_pc_table_create: propagator %lld is not a well-formed formula stream within the depth limits (terms %d, connectives %d)",
+                  (long long)i, PC_TREE_TERM_DEPTH, PC_TREE_FORM_DEPTH);
+        return LPC_ERR_UNSUPPORTED;
+      }
+      hdr[i] = make_int4(p.kind | (p.n_terms << 8), p.first_term, p.rhs, p.bvar);
+      has_linear = true;   // interval arithmetic inside: no bitset rule
+      continue;
+    }
     const bool two = p.kind == LPC_PC_EQ || p.kind == LPC_PC_ABS_EQ;
     if((two && p.n_terms != 2) || (p.kind == LPC_PC_NEQ && p.n_terms > 2)) { set_error("lpc_pc_table_create: propagator %lld has the wrong arity for its kind", (long long)i); return LPC_ERR_INVALID; }
-    const bool lin_kind = p.kind == LPC_PC_LIN_LE || p.kind == LPC_PC_REIF_LIN_LE || p.kind >= LPC_PC_LIN_GE;
+    const bool lin_kind = pc_is_linear(p.kind);
     if((p.kind == LPC_PC_REIF_LIN_LE || p.kind == LPC_PC_LIN_EQ_VAR) && (p.bvar < 0 || p.bvar >= nvars)) { set_error("lpc_pc_table_create: propagator %lld has a bad reification / result variable", (long long)i); return LPC_ERR_INVALID; }
     for(int k = 0; k < p.n_terms; ++k) {
       const lpc_pc_term& t = terms[p.first_term + k];
@@ -421,7 +414,7 @@ int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_
       const lpc_pc_prop& p = props[i];
       const int lanes = p.n_terms + (pc_has_extra_lane(p.kind) ? 1 : 0);
       const bool lin_kind = pc_is_linear(p.kind);
-      if(lanes > 32 || (lin_kind && (p.rhs >= (1 << 30) || p.rhs <= -(1 << 30)))) {   // see tile_step: keeps the tile arithmetic in int32
+      if(p.kind == LPC_PC_TREE || lanes > 32 || (lin_kind && (p.rhs >= (1 << 30) || p.rhs <= -(1 << 30)))) {   // see tile_step: keeps the tile arithmetic in int32
         big.push_back((int)i);
         cur = 32;   // close the tile so that tile_prop0 + rank stays a contiguous propagator range
         continue;
@@ -475,7 +468,7 @@ int64_t lpc_pc_table_terms(const lpc_pc_table* t) { return t ? (int64_t)t->dev.n
 
 static int check_bits(const lpc_pc_table* t, bool bits) {
   if(bits && t->has_linear) {
-    set_error("bitset stores support the EQ, NEQ, CLAUSE and ABS_EQ kinds only (NBitset arithmetic is unpinned upstream)");
+    set_error("bitset stores support the EQ, NEQ, CLAUSE and ABS_EQ kinds only (NBitset arithmetic is unpinned upstream; LIN_* and TREE propagators compute on intervals)");
     return LPC_ERR_UNSUPPORTED;
   }
   return LPC_OK;

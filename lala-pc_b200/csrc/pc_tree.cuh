@@ -1,0 +1,407 @@
+// pc_tree.cuh — the general PC propagator: a prefix-encoded formula / term tree interpreted in registers.
+//
+// The flat kinds of pc_device.cuh cover the shapes that make up large models (sums, reified sums, clauses, =, !=, abs).
+// Everything else pc::Formula / pc::Term can hold keeps its tree, here as a prefix-encoded int32 stream that lives in
+// the term array of the table (kind LPC_PC_TREE, include/lpc_pc.h), so PC::deduce(i) and PC::ask(i) have a device rule
+// for EVERY propagator the reference's interpreter can build from these node types (lala-pc include/lala/):
+//   formulas  VariableLiteral<neg>        formula.hpp:80-167      Conjunction            formula.hpp:241-308
+//             Disjunction                 formula.hpp:310-378     Biconditional          formula.hpp:380-451
+//             Implication                 formula.hpp:453-516     ExclusiveDisjunction   formula.hpp:518-587
+//             Equality<neg>               formula.hpp:589-721     Inequality<neg>        formula.hpp:727-845
+//   terms     Constant, Variable          terms.hpp:18-85         Unary<Neg | Abs>       terms.hpp:87-175
+//             Binary<Add|Sub|Mul|Min|Max> terms.hpp:177-262, 301-434                     Nary<Add>  terms.hpp:436-526
+// The walk is the reference's: `project` folds a term bottom-up, `embed` pushes an interval down through the residuals
+// of each group, formulas dispatch ask / nask / deduce / contradeduce with the `negated` flag folded in.
+//
+// No recursion on the device: every function is a template over the REMAINING depth and calls the level below, so the
+// call graph is static and ptxas sizes the stack exactly. The table builder (lpc_pc_table_create) checks a stream
+// against PC_TREE_TERM_DEPTH / PC_TREE_FORM_DEPTH and refuses deeper trees.
+//
+// Bound arithmetic: the same restatement of lala-core's Interval::project as pc_device.cuh (b_add, b_mul, b_ediv ...).
+// Pinned by tests/pc_test.cpp through the CPU checker for what its goldens exercise; MIN / MAX / MUL of two variables
+// by MinConstraint1-3, MaxConstraint1-3 and IntTimes1-6.
+#pragma once
+// (included by pc_tree.cu, by the table builder for tree_check, and - on the host harness - at the end of pc_device.cuh)
+#include "pc_device.cuh"
+namespace lpc {
+
+enum PcTok : int { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8,
+                   T_MIN = 9, T_MAX = 10,
+                   F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27,
+                   F_EQUIV = 28, F_IMPLY = 29, F_XOR = 30 };
+
+constexpr int PC_TREE_TERM_DEPTH = 5;   // height of the tallest term  (x + y = 2, (2*x + y) + 3*z = 4)
+constexpr int PC_TREE_FORM_DEPTH = 4;   // height of the connective nest above a comparison (b <=> (p /\ q) = 3)
+
+#ifdef LPC_HOST_HARNESS
+#define LPC_NI __host__ __device__ __noinline__
+#else
+#define LPC_NI __device__ __noinline__
+#endif
+
+__host__ __device__ inline bool tok_is_term(int k) { return k >= T_CONST && k <= T_MAX; }
+__host__ __device__ inline bool tok_is_binary_term(int k) { return k == T_ADD || k == T_SUB || k == T_MUL || k == T_MIN || k == T_MAX; }
+
+// The first word after the term that starts at p (iterative: `pending` subterms still to be read).
+__host__ __device__ inline const int* tree_skip_term(const int* p) {
+  int pending = 1;
+  while(pending > 0) {
+    const int k = *p++;
+    if(k == T_CONST || k == T_VAR) { ++p; --pending; }
+    else if(k == T_NEG || k == T_ABS) { }
+    else if(k == T_NARY_ADD) { pending += *p++ - 1; }
+    else ++pending;   // binary
+  }
+  return p;
+}
+__host__ __device__ inline const int* tree_skip_formula(const int* p) {
+  int pending = 1;
+  while(pending > 0) {
+    const int k = *p++;
+    if(k == F_VARLIT || k == F_NVARLIT) { ++p; --pending; }
+    else if(k >= F_LEQ && k <= F_NEQ) { p = tree_skip_term(tree_skip_term(p)); --pending; }
+    else ++pending;   // binary connective
+  }
+  return p;
+}
+
+// Host-side check of one stream (table builder): well formed, variables in range, depths within the limits.
+// Returns the number of words the formula occupies, or -1.
+struct TreeCheck {
+  const int* w; int n; int nvars; bool ok;
+  int term(int& i) {   // returns the height
+    if(i >= n) { ok = false; return 0; }
+    const int k = w[i++];
+    if(k == T_CONST) { if(i >= n) { ok = false; return 0; } ++i; return 1; }
+    if(k == T_VAR) { if(i >= n || w[i] < 0 || w[i] >= nvars) { ok = false; return 0; } ++i; return 1; }
+    if(k == T_NEG || k == T_ABS) return 1 + term(i);
+    if(tok_is_binary_term(k)) { const int a = term(i); if(!ok) return 0; const int b = term(i); return 1 + (a > b ? a : b); }
+    if(k == T_NARY_ADD) {
+      if(i >= n || w[i] < 2 || w[i] > n) { ok = false; return 0; }
+      const int m = w[i++];
+      int h = 0;
+      for(int j = 0; j < m && ok; ++j) { const int a = term(i); h = a > h ? a : h; }
+      return 1 + h;
+    }
+    ok = false;
+    return 0;
+  }
+  int formula(int& i) {
+    if(i >= n) { ok = false; return 0; }
+    const int k = w[i++];
+    if(k == F_VARLIT || k == F_NVARLIT) { if(i >= n || w[i] < 0 || w[i] >= nvars) { ok = false; return 0; } ++i; return 1; }
+    if(k >= F_LEQ && k <= F_NEQ) {
+      const int a = term(i); if(!ok) return 0;
+      const int b = term(i);
+      if((a > b ? a : b) > PC_TREE_TERM_DEPTH) ok = false;
+      return 1;
+    }
+    if(k >= F_AND && k <= F_XOR) { const int a = formula(i); if(!ok) return 0; const int b = formula(i); return 1 + (a > b ? a : b); }
+    ok = false;
+    return 0;
+  }
+};
+inline int tree_check(const int* w, int n, int nvars) {
+  TreeCheck c{w, n, nvars, true};
+  int i = 0;
+  const int h = c.formula(i);
+  if(!c.ok || h > PC_TREE_FORM_DEPTH) return -1;
+  for(int j = i; j < n; ++j) if(w[j] != 0) return -1;   // only zero padding after the formula
+  return i;
+}
+
+// ---- interval helpers (lala-core Interval::project(Sig, ...), restated; see the header of pc_device.cuh) -------------
+LPC_HD Itv tr_neg(const Itv& a) { return Itv(b_neg(a.ub), b_neg(a.lb)); }
+LPC_HD Itv tr_add(const Itv& a, const Itv& b) { return Itv(b_add(a.lb, b.lb), b_add(a.ub, b.ub)); }
+LPC_HD Itv tr_sub(const Itv& a, const Itv& b) { return Itv(b_sub(a.lb, b.ub), b_sub(a.ub, b.lb)); }
+LPC_HD Itv tr_abs(const Itv& a) {
+  if(a.is_bot() || a.lb >= 0) return a;
+  if(a.ub <= 0) return tr_neg(a);
+  return Itv(0, max(b_neg(a.lb), a.ub));
+}
+LPC_HD Itv tr_hull4(int t1, int t2, int t3, int t4) { return Itv(min(min(t1, t2), min(t3, t4)), max(max(t1, t2), max(t3, t4))); }
+LPC_HD Itv tr_mul(const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return itv_bot();
+  return tr_hull4(b_mul(a.lb, b.lb), b_mul(a.lb, b.ub), b_mul(a.ub, b.lb), b_mul(a.ub, b.ub));
+}
+LPC_HD int tr_ediv1(int a, int b) {   // Euclidean quotient of two bounds, b != 0
+  if(b_inf(b)) return b_inf(a) ? (((a < 0) != (b < 0)) ? LPC_MINF : LPC_INF) : 0;
+  return b_ediv(a, b);
+}
+// a divisor holding 0 loses it: hull over its negative and its positive part (0 at an endpoint is pinned by IntTimes2,
+// pc_test.cpp:626-636; a straddling divisor and {0} -> empty are not pinned by any reference test)
+LPC_HD Itv tr_ediv(const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return itv_bot();
+  Itv r = itv_bot();
+  if(b.lb < 0) {
+    const int bu = min(b.ub, -1);
+    r = fjoin(r, tr_hull4(tr_ediv1(a.lb, b.lb), tr_ediv1(a.lb, bu), tr_ediv1(a.ub, b.lb), tr_ediv1(a.ub, bu)));
+  }
+  if(b.ub > 0) {
+    const int bl = max(b.lb, 1);
+    r = fjoin(r, tr_hull4(tr_ediv1(a.lb, bl), tr_ediv1(a.lb, b.ub), tr_ediv1(a.ub, bl), tr_ediv1(a.ub, b.ub)));
+  }
+  return r;
+}
+LPC_HD Itv tr_min(const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return itv_bot();
+  return Itv(min(a.lb, b.lb), min(a.ub, b.ub));
+}
+LPC_HD Itv tr_max(const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return itv_bot();
+  return Itv(max(a.lb, b.lb), max(a.ub, b.ub));
+}
+LPC_HD bool tr_same(const Itv& a, const Itv& b) { return (a.is_bot() && b.is_bot()) || (a.lb == b.lb && a.ub == b.ub); }
+
+// G::project (terms.hpp:182, 213, 235, 306)
+LPC_HD Itv tr_group(int k, const Itv& x, const Itv& y) {
+  switch(k) {
+    case T_ADD: return tr_add(x, y);
+    case T_SUB: return tr_sub(x, y);
+    case T_MUL: return tr_mul(x, y);
+    case T_MIN: return tr_min(x, y);
+    default: return tr_max(x, y);
+  }
+}
+// G::left_residual(u, b) / right_residual(u, b) met into top (terms.hpp:196-202, 218-224, 249-257, 310-326)
+LPC_HD Itv tr_residual(int k, bool right, const Itv& u, const Itv& b) {
+  switch(k) {
+    case T_ADD: return tr_sub(u, b);
+    case T_SUB: return right ? tr_sub(b, u) : tr_add(u, b);
+    case T_MUL: return (contains0(u) && contains0(b)) ? itv_top() : tr_ediv(u, b);
+    default: {   // GroupMinMax: disjoint from the other operand -> this operand IS the result; else only one side
+      Itv m = u;
+      m.meet(b);
+      if(m.is_bot()) return u;
+      return k == T_MIN ? Itv(u.lb, LPC_INF) : Itv(LPC_MINF, u.ub);
+    }
+  }
+}
+
+// ---- terms --------------------------------------------------------------------------------------------------------------
+template <int D> struct TreeTerm {
+  // Term::project (terms.hpp:34, 69-71, 148-152, 399-405, 465-478); p is left after the term
+  template <class Acc> static LPC_NI Itv project(const Acc& a, const int*& p) {
+    const int k = *p++;
+    switch(k) {
+      case T_CONST: { const int c = *p++; return Itv(c, c); }
+      case T_VAR: return a.load(*p++);
+      case T_NEG: return tr_neg(TreeTerm<D - 1>::project(a, p));
+      case T_ABS: return tr_abs(TreeTerm<D - 1>::project(a, p));
+      case T_NARY_ADD: {
+        const int n = *p++;
+        Itv accu = TreeTerm<D - 1>::project(a, p);
+        for(int i = 1; i < n; ++i) accu = tr_add(accu, TreeTerm<D - 1>::project(a, p));
+        return accu;
+      }
+      default: {
+        const Itv x = TreeTerm<D - 1>::project(a, p);
+        const Itv y = TreeTerm<D - 1>::project(a, p);
+        return tr_group(k, x, y);
+      }
+    }
+  }
+  // Term::embed(u) (terms.hpp:33, 65-67, 142-146, 376-397, 480-499): bit0 = changed, bit1 = a variable became empty
+  template <class Acc> static LPC_NI int embed(Acc& a, const int*& p, const Itv u) {
+    const int k = *p++;
+    switch(k) {
+      case T_CONST: ++p; return 0;
+      case T_VAR: return a.embed(*p++, u);
+      case T_NEG: return TreeTerm<D - 1>::embed(a, p, tr_neg(u));
+      case T_ABS: return TreeTerm<D - 1>::embed(a, p, fjoin(u, tr_neg(u)));
+      case T_NARY_ADD: {
+        const int n = *p++;
+        const int* q = p - 2;
+        const Itv all = project(a, q);   // once, before any operand moves (terms.hpp:486)
+        int f = 0;
+        for(int i = 0; i < n; ++i) {
+          const int* s = p;
+          const Itv ti = TreeTerm<D - 1>::project(a, s);
+          const Itv others(b_add(all.lb, b_neg(ti.lb)), b_add(all.ub, b_neg(ti.ub)));   // additive_inverse, :190-194
+          f |= TreeTerm<D - 1>::embed(a, p, tr_sub(u, others));
+        }
+        return f;
+      }
+      default: {
+        const int* px = p;
+        const int* py = tree_skip_term(px);
+        int f = 0;
+        if(*px != T_CONST) {
+          const int* s = py;
+          const Itv yt = TreeTerm<D - 1>::project(a, s);
+          s = px;
+          f |= TreeTerm<D - 1>::embed(a, s, tr_residual(k, false, u, yt));
+        }
+        p = tree_skip_term(py);
+        if(*py != T_CONST) {
+          const int* s = px;
+          const Itv xt = TreeTerm<D - 1>::project(a, s);   // re-read: x may just have moved
+          s = py;
+          f |= TreeTerm<D - 1>::embed(a, s, tr_residual(k, true, u, xt));
+        }
+        return f;
+      }
+    }
+  }
+};
+template <> struct TreeTerm<0> {   // below the checked depth: never reached (tree_check)
+  template <class Acc> static LPC_HD Itv project(const Acc&, const int*& p) { p = tree_skip_term(p); return itv_top(); }
+  template <class Acc> static LPC_HD int embed(Acc&, const int*& p, const Itv) { p = tree_skip_term(p); return 0; }
+};
+typedef TreeTerm<PC_TREE_TERM_DEPTH> TreeTop;
+
+// ---- formulas -----------------------------------------------------------------------------------------------------------
+// Equality<true>::deduce, one direction: `other` loses the value of the singleton side (formula.hpp:645-652, 661-668)
+template <class Acc> LPC_HD int tree_shave(Acc& a, const int* other, const Itv& single) {
+  const int* s = other;
+  const Itv o = TreeTop::project(a, s);
+  Itv lo = o, hi = o;
+  lo.meet(Itv(b_add(single.lb, 1), LPC_INF));
+  hi.meet(Itv(LPC_MINF, b_sub(single.ub, 1)));
+  s = other;
+  return TreeTop::embed(a, s, fjoin(lo, hi));
+}
+
+// The comparisons (leaves of the connective nest). `neg` already folds the caller's negation into the node's own.
+template <class Acc> LPC_NI bool tree_cmp_ask(const Acc& a, int k, bool negated, const int*& p) {
+  const Itv x = TreeTop::project(a, p);
+  const Itv y = TreeTop::project(a, p);
+  if(k == F_LEQ || k == F_GT) {   // formula.hpp:757-771
+    const bool neg = (k == F_GT) != negated;
+    return neg ? x.lb > y.ub : x.ub <= y.lb;
+  }
+  const bool neg = (k == F_NEQ) != negated;   // formula.hpp:616-631
+  if(neg) { Itv m = x; m.meet(y); return m.is_bot(); }
+  return tr_same(x, y) && x.lb == x.ub;
+}
+template <class Acc> LPC_NI int tree_cmp_deduce(Acc& a, int k, bool negated, const int*& p) {
+  const int* pl = p;
+  const int* pr = tree_skip_term(pl);
+  p = tree_skip_term(pr);
+  const bool lconst = *pl == T_CONST, rconst = *pr == T_CONST;
+  const int* s;
+  int f = 0;
+  if(k == F_LEQ || k == F_GT) {   // formula.hpp:773-807
+    const bool neg = (k == F_GT) != negated;
+    if(neg) {   // l > r: l >= r.lb + 1, r <= l.ub - 1
+      if(!lconst) { s = pr; const Itv y = TreeTop::project(a, s); s = pl; f = TreeTop::embed(a, s, Itv(b_add(y.lb, 1), LPC_INF)); }
+      if(!rconst) { s = pl; const Itv x = TreeTop::project(a, s); s = pr; f |= TreeTop::embed(a, s, Itv(LPC_MINF, b_sub(x.ub, 1))); }
+    }
+    else {      // l <= r
+      if(!lconst) { s = pr; const Itv y = TreeTop::project(a, s); s = pl; f |= TreeTop::embed(a, s, Itv(LPC_MINF, y.ub)); }
+      if(!rconst) {   // formula.hpp:803 ASSIGNS has_changed here: the left side's change bit is lost, its bot bit is not
+        s = pl; const Itv x = TreeTop::project(a, s); s = pr;
+        f = (f & 2) | TreeTop::embed(a, s, Itv(x.lb, LPC_INF));
+      }
+    }
+    return f;
+  }
+  const bool neg = (k == F_NEQ) != negated;   // formula.hpp:633-683
+  if(neg) {
+    if(!rconst) { s = pl; const Itv x = TreeTop::project(a, s); if(x.lb == x.ub) return tree_shave(a, pr, x); }
+    if(!lconst) { s = pr; const Itv y = TreeTop::project(a, s); if(y.lb == y.ub) return tree_shave(a, pl, y); }
+    return 0;
+  }
+  if(!rconst) { s = pl; const Itv x = TreeTop::project(a, s); s = pr; f = TreeTop::embed(a, s, x); }
+  if(!lconst) { s = pr; const Itv y = TreeTop::project(a, s); s = pl; f |= TreeTop::embed(a, s, y); }
+  return f;
+}
+
+template <int D> struct TreeForm {
+  // ask (negated = false) / nask (negated = true); p is left after the formula
+  template <class Acc> static LPC_NI bool ask(const Acc& a, const int*& p, bool negated) {
+    const int k = *p++;
+    if(k == F_VARLIT || k == F_NVARLIT) {   // formula.hpp:97-110, 126-135
+      const bool neg = (k == F_NVARLIT) != negated;
+      return lit_ask(neg, a.load(*p++));
+    }
+    if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_ask(a, k, negated, p);
+    const int* pf = p;
+    const int* pg = tree_skip_formula(pf);
+    p = tree_skip_formula(pg);
+    const int *s = pf, *t = pg;
+    typedef TreeForm<D - 1> S;
+    switch(k) {
+      case F_AND:     // formula.hpp:268-274
+        if(negated) { if(S::ask(a, s, true)) return true; return S::ask(a, t, true); }
+        if(!S::ask(a, s, false)) return false;
+        return S::ask(a, t, false);
+      case F_OR:      // formula.hpp:338-344
+        if(negated) { if(!S::ask(a, s, true)) return false; return S::ask(a, t, true); }
+        if(S::ask(a, s, false)) return true;
+        return S::ask(a, t, false);
+      case F_IMPLY:   // formula.hpp:479-487: (not f) or g; negated: f and (not g)
+        if(negated) { if(!S::ask(a, s, false)) return false; return S::ask(a, t, true); }
+        if(S::ask(a, s, true)) return true;
+        return S::ask(a, t, false);
+      case F_EQUIV: case F_XOR: {   // formula.hpp:408-419, 541-552
+        const int *s2 = pf, *t2 = pg;
+        const bool fa = S::ask(a, s, false), ga = S::ask(a, t, false), fn = S::ask(a, s2, true), gn = S::ask(a, t2, true);
+        if(k == F_EQUIV) return negated ? ((fa && gn) || (fn && ga)) : ((fa && ga) || (fn && gn));
+        return negated ? ((fa && ga) || (fa && gn))   // as written at formula.hpp:548-552
+                       : ((fa && gn) || (fn && ga));
+      }
+      default: return false;
+    }
+  }
+  // deduce (negated = false) / contradeduce (negated = true)
+  template <class Acc> static LPC_NI int deduce(Acc& a, const int*& p, bool negated) {
+    const int k = *p++;
+    if(k == F_VARLIT || k == F_NVARLIT) {   // formula.hpp:112-120, 140-149
+      const bool neg = (k == F_NVARLIT) != negated;
+      return a.embed(*p++, neg ? Itv(0, 0) : Itv(1, 1));
+    }
+    if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_deduce(a, k, negated, p);
+    const int* pf = p;
+    const int* pg = tree_skip_formula(pf);
+    p = tree_skip_formula(pg);
+    typedef TreeForm<D - 1> S;
+    auto ASK = [&](const int* q, bool n) { return S::ask(a, q, n); };
+    auto DED = [&](const int* q, bool n) { return S::deduce(a, q, n); };
+    switch(k) {
+      case F_AND:     // formula.hpp:276-286
+        if(!negated) { int f = DED(pf, false); f |= DED(pg, false); return f; }
+        if(ASK(pf, false)) return DED(pg, true);
+        if(ASK(pg, false)) return DED(pf, true);
+        return 0;
+      case F_OR:      // formula.hpp:346-356
+        if(negated) { int f = DED(pf, true); f |= DED(pg, true); return f; }
+        if(ASK(pf, true)) return DED(pg, false);
+        if(ASK(pg, true)) return DED(pf, false);
+        return 0;
+      case F_IMPLY:   // formula.hpp:489-499
+        if(ASK(pf, false)) return DED(pg, negated);
+        if(ASK(pg, true)) return DED(pf, !negated);
+        return 0;
+      case F_EQUIV: case F_XOR: {   // formula.hpp:421-435, 554-568: xor is the biconditional with the conclusions swapped
+        const bool flip = (k == F_XOR) != negated;
+        if(ASK(pf, false)) return DED(pg, flip);
+        if(ASK(pf, true)) return DED(pg, !flip);
+        if(ASK(pg, false)) return DED(pf, flip);
+        if(ASK(pg, true)) return DED(pf, !flip);
+        return 0;
+      }
+      default: return 0;
+    }
+  }
+};
+template <> struct TreeForm<0> {
+  template <class Acc> static LPC_HD bool ask(const Acc&, const int*& p, bool) { p = tree_skip_formula(p); return false; }
+  template <class Acc> static LPC_HD int deduce(Acc&, const int*& p, bool) { p = tree_skip_formula(p); return 0; }
+};
+
+// PC::deduce(i) / PC::ask(i) (pc.hpp:661-680) for one LPC_PC_TREE propagator whose stream starts at `words`.
+template <class Acc> LPC_HD int pc_tree_deduce_impl(Acc& a, const int* words) {
+  const int* p = words;
+  return TreeForm<PC_TREE_FORM_DEPTH>::deduce(a, p, false);
+}
+template <class Acc> LPC_HD bool pc_tree_ask_impl(const Acc& a, const int* words) {
+  const int* p = words;
+  return TreeForm<PC_TREE_FORM_DEPTH>::ask(a, p, false);
+}
+#ifdef LPC_HOST_HARNESS
+template <class Acc> LPC_HD int pc_tree_deduce(Acc& a, const int* words) { return pc_tree_deduce_impl(a, words); }
+template <class Acc> LPC_HD bool pc_tree_ask(const Acc& a, const int* words) { return pc_tree_ask_impl(a, words); }
+#endif
+
+} // namespace lpc

@@ -14,9 +14,12 @@
 // tests/pc_bitset_test.cpp:52-55) as one persistent CUDA kernel (lpc_pc_fixpoint / lpc_pc_fixpoint_bits).
 //
 // The store type selects the universe: PC<VStore> runs over Interval<ZLB> cells, PC<BitVStore> over NBitset<64> cells.
-// Only formula shapes with a flat device kind (include/lpc_pc.h) are interpreted; everything else fails interpretation
-// with the reference's message ("The shape of this formula is not supported.") so that a caller can keep such
-// propagators on the reference's tree-walking path. No CPU implementation lives behind this header.
+// Formula shapes with a flat device kind (include/lpc_pc.h) are flattened; every other shape over the node types PC
+// has a device rule for (and / or / equiv / imply / xor nests, comparisons between arbitrary terms, + - * min max neg
+// abs, n-ary sums) keeps its tree as an LPC_PC_TREE propagator and is walked on the device (csrc/pc_tree.cuh). What is
+// left - divisions, n-ary products, `in` over non-bitset stores, trees deeper than the device walks - fails interpretation
+// with the reference's message ("The shape of this formula is not supported."). No CPU implementation lives behind
+// this header.
 #pragma once
 #include <cstdint>
 
@@ -26,7 +29,8 @@
 namespace b200pc {
 
 // Formula signatures PC understands beyond the PIR operators (numeric values are façade-local).
-enum PcSig : int { SUB = 1010, NEG = 1011, ABS = 1012, NOT = 1013, AND = 1014, OR = 1015, EQUIV = 1016, IN = 1017 };
+enum PcSig : int { SUB = 1010, NEG = 1011, ABS = 1012, NOT = 1013, AND = 1014, OR = 1015, EQUIV = 1016, IN = 1017,
+                   IMPLY = 1018, XOR = 1019 };
 
 // NBitset<64, local_memory, unsigned long long> (pc_bitset_test.cpp:23): bit 0 = "<= -1", bit i = value i - 1,
 // bit 63 = ">= 62".
@@ -100,7 +104,7 @@ struct TF {
   bool is_binary() const { return kind == SEQ && args.size() == 2; }
   int sig() const { return sig_; }
   const TF& seq(int i) const { return args[i]; }
-  bool is_logical() const { return kind == SEQ && (sig_ == AND || sig_ == OR || sig_ == EQUIV || sig_ == NOT); }
+  bool is_logical() const { return kind == SEQ && (sig_ == AND || sig_ == OR || sig_ == EQUIV || sig_ == NOT || sig_ == IMPLY || sig_ == XOR); }
   bool is_predicate() const { return kind == SEQ && (sig_ == EQ || sig_ == NEQ || sig_ == LEQ || sig_ == GEQ || sig_ == LT || sig_ == GT || sig_ == IN); }
 };
 
@@ -357,7 +361,106 @@ private:
     return false;
   }
 
+  // ---- the general case: the tree itself as an LPC_PC_TREE stream (include/lpc_pc.h) -------------------------------
+  // Token numbers of the stream; heights are checked against the device interpreter's limits (csrc/pc_tree.cuh).
+  enum { TK_CONST = 1, TK_VAR = 2, TK_NEG = 3, TK_ABS = 4, TK_ADD = 5, TK_SUB = 6, TK_MUL = 7, TK_NARY_ADD = 8, TK_MIN = 9,
+         TK_MAX = 10, FK_LIT = 20, FK_NLIT = 21, FK_LEQ = 22, FK_GT = 23, FK_EQ = 24, FK_NEQ = 25, FK_AND = 26, FK_OR = 27,
+         FK_EQUIV = 28, FK_IMPLY = 29, FK_XOR = 30, TREE_TERM_DEPTH = 5, TREE_FORM_DEPTH = 4 };
+  // interpret_term (pc.hpp:217-296): returns the height (0 = not a term), `len` = Term::length()
+  static int tree_term(const TF& t, const VarEnv& env, std::vector<int>& w, int& len) {
+    AVar v;
+    if(t.is_variable()) { if(!env.interpret(F::var(t.name), v)) return 0; w.push_back(TK_VAR); w.push_back(v.vid()); len = 1; return 1; }
+    if(t.is_constant()) { w.push_back(TK_CONST); w.push_back(t.k); len = 1; return 1; }
+    if(!t.is_seq()) return 0;
+    if((t.sig() == NEG || t.sig() == ABS) && t.args.size() == 1) {
+      w.push_back(t.sig() == NEG ? TK_NEG : TK_ABS);
+      int l = 0; const int h = tree_term(t.seq(0), env, w, l);
+      len = 1 + l;
+      return h ? 1 + h : 0;
+    }
+    int tok = 0;
+    switch(t.sig()) { case ADD: tok = TK_ADD; break; case SUB: tok = TK_SUB; break; case MUL: tok = TK_MUL; break;
+                      case MIN: tok = TK_MIN; break; case MAX: tok = TK_MAX; break; default: return 0; }
+    if(t.args.size() == 2) {
+      w.push_back(tok);
+      int l0 = 0, l1 = 0;
+      const int h0 = tree_term(t.seq(0), env, w, l0), h1 = h0 ? tree_term(t.seq(1), env, w, l1) : 0;
+      len = 1 + l0 + l1;
+      return (h0 && h1) ? 1 + std::max(h0, h1) : 0;
+    }
+    if(tok == TK_ADD && t.args.size() > 2) {   // Nary<Add> (pc.hpp:253)
+      w.push_back(TK_NARY_ADD); w.push_back((int)t.args.size());
+      int h = 0; len = 1;
+      for(auto& a : t.args) { int l = 0; const int ha = tree_term(a, env, w, l); if(!ha) return 0; h = std::max(h, ha); len += l; }
+      return 1 + h;
+    }
+    return 0;
+  }
+  // interpret_formula (pc.hpp:454-572): returns the height of the connective nest (0 = no device rule); `ref_kind` =
+  // index of the pc::Formula alternative the reference builds (formula.hpp:886-899), `len` = its length().
+  static int tree_formula(const TF& f, const VarEnv& env, std::vector<int>& w, int& ref_kind, int& len, bool negate = false) {
+    AVar v;
+    if(f.is_variable()) {
+      if(!env.interpret(F::var(f.name), v)) return 0;
+      w.push_back(negate ? FK_NLIT : FK_LIT); w.push_back(v.vid()); ref_kind = negate ? 1 : 0; len = 1; return 1;
+    }
+    if(!f.is_seq()) return 0;
+    if(f.sig() == NOT && f.args.size() == 1) {   // negation is pushed into a literal or a comparison (pc.hpp:487-520)
+      const TF& g = f.seq(0);
+      if(g.is_variable() || g.is_predicate()) return tree_formula(g, env, w, ref_kind, len, !negate);
+      return 0;
+    }
+    if(f.args.size() > 2 && (f.sig() == AND || f.sig() == OR) && !negate) {   // binarised to the right (pc.hpp:454-463)
+      std::vector<TF> rest(f.args.begin() + 1, f.args.end());
+      return tree_formula(TF::make_binary(f.seq(0), f.sig(), TF::make_nary(f.sig(), rest)), env, w, ref_kind, len);
+    }
+    if(!f.is_binary()) return 0;
+    const TF& a = f.seq(0); const TF& b = f.seq(1);
+    int sig = f.sig();
+    if(sig == EQ && (a.is_predicate() || b.is_predicate() || a.is_logical() || b.is_logical())) sig = EQUIV;   // pc.hpp:553-557
+    if(sig == AND || sig == OR || sig == EQUIV || sig == IMPLY || sig == XOR) {
+      if(negate) return 0;
+      w.push_back(sig == AND ? FK_AND : sig == OR ? FK_OR : sig == EQUIV ? FK_EQUIV : sig == IMPLY ? FK_IMPLY : FK_XOR);
+      ref_kind = sig == AND ? 8 : sig == OR ? 9 : sig == EQUIV ? 10 : sig == IMPLY ? 11 : 12;
+      int k0, k1, l0 = 0, l1 = 0;
+      const int h0 = tree_formula(a, env, w, k0, l0), h1 = h0 ? tree_formula(b, env, w, k1, l1) : 0;
+      len = 1 + l0 + l1;
+      return (h0 && h1) ? 1 + std::max(h0, h1) : 0;
+    }
+    const TF* l = &a; const TF* r = &b;
+    if(sig == GEQ) { sig = LEQ; std::swap(l, r); }        // pc.hpp:565-566
+    else if(sig == LT) { sig = GT; std::swap(l, r); }
+    if(negate) sig = sig == LEQ ? GT : sig == GT ? LEQ : sig == EQ ? NEQ : sig == NEQ ? EQ : 0;
+    int tok = 0;
+    switch(sig) { case LEQ: tok = FK_LEQ; ref_kind = 4; break; case GT: tok = FK_GT; ref_kind = 5; break;
+                  case EQ: tok = FK_EQ; ref_kind = 6; break; case NEQ: tok = FK_NEQ; ref_kind = 7; break; default: return 0; }
+    w.push_back(tok);
+    int l0 = 0, l1 = 0;
+    const int h0 = tree_term(*l, env, w, l0), h1 = h0 ? tree_term(*r, env, w, l1) : 0;
+    len = 1 + l0 + l1;
+    return (h0 && h1 && std::max(h0, h1) <= TREE_TERM_DEPTH) ? 1 : 0;
+  }
+  bool interpret_tree(const TF& f, VarEnv& env, tell_type& out, std::string* why) const {
+    if(bitset) return fail(why, "The shape of this formula is not supported.");   // tree propagators compute on intervals
+    std::vector<int> w;
+    prop_type p;
+    const int h = tree_formula(f, env, w, p.ref_kind, p.length);
+    if(h == 0 || h > TREE_FORM_DEPTH) return fail(why, "The shape of this formula is not supported.");
+    if(w.size() % 2) w.push_back(0);
+    p.kind = LPC_PC_TREE;
+    for(size_t i = 0; i < w.size(); i += 2) p.terms.push_back(lpc_pc_term{w[i], w[i + 1]});
+    out.props.push_back(p);
+    return true;
+  }
+
   bool interpret_formula(const TF& f, VarEnv& env, tell_type& out, std::string* why) const {
+    const size_t n0 = out.props.size();
+    if(interpret_flat(f, env, out, why)) return true;
+    out.props.resize(n0);
+    return interpret_tree(f, env, out, why);   // no flat kind: the tree itself goes to the device
+  }
+
+  bool interpret_flat(const TF& f, VarEnv& env, tell_type& out, std::string* why) const {
     prop_type p;
     lpc_pc_term lit;
     AVar x, y;

@@ -267,16 +267,89 @@ static void UnsupportedShapesAreRefused() {
   IPC ipc(pty, std::make_shared<VStore>(3));
   IPC::tell_type tell;
   std::string why;
-  EXPECT_FALSE(ipc.interpret_tell(bin(V("x"), LEQ, V("y")), m.env, tell, &why));                      // var <= var
+  // shapes without a flat kind keep their tree (LPC_PC_TREE) ...
+  EXPECT_TRUE(ipc.interpret_tell(bin(V("x"), LEQ, V("y")), m.env, tell, &why));                       // var <= var
+  EXPECT_TRUE(ipc.interpret_tell(bin(bin(V("x"), MUL, V("y")), LEQ, K(3)), m.env, tell, &why));        // non-linear
+  EXPECT_TRUE(ipc.interpret_tell(bin(V("x"), AND, V("y")), m.env, tell, &why));                       // conjunction
+  EXPECT_EQ((int)tell.props.size(), 3);
+  for(auto& p : tell.props) EXPECT_EQ(p.kind, (int)LPC_PC_TREE);
+  // ... unless they are deeper than the device interpreter walks, or hold a node PC has no rule for
+  TF deep = V("x");
+  for(int i = 0; i < 6; ++i) deep = bin(deep, ADD, V("y"));
+  EXPECT_FALSE(ipc.interpret_tell(bin(deep, LEQ, K(3)), m.env, tell, &why));
   EXPECT_EQ(why, std::string("The shape of this formula is not supported."));
-  EXPECT_FALSE(ipc.interpret_tell(bin(bin(V("x"), MUL, V("y")), LEQ, K(3)), m.env, tell, &why));       // non-linear
-  EXPECT_FALSE(ipc.interpret_tell(bin(V("x"), AND, V("y")), m.env, tell, &why));                      // conjunction
-  EXPECT_EQ((int)tell.props.size(), 0);
+  EXPECT_FALSE(ipc.interpret_tell(bin(bin(V("x"), TDIV, V("y")), LEQ, K(3)), m.env, tell, &why));      // GroupDiv: unpinned upstream
+  EXPECT_EQ((int)tell.props.size(), 3);
   Model<BitPC> mb;
   mb.var("x").var("y");
   BitPC bpc(pty, std::make_shared<BitVStore>(2));
   BitPC::tell_type btell;
   EXPECT_FALSE(bpc.interpret_tell(bin(bin(V("x"), ADD, V("y")), LEQ, K(3)), mb.env, btell, &why));    // sums over bitsets
+}
+
+// The goldens whose formulas have no flat kind: the tree goes to the device as it is (LPC_PC_TREE).
+static void TreePropagators() {
+  {   // TemporalConstraint10, pc_test.cpp:213-219: x <= -5 + y
+    Model<IPC> m;
+    m.var("x", Itv(0, 10)).var("y", Itv(0, 10)).c(bin(V("x"), LEQ, bin(K(-5), ADD, V("y"))));
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, {Itv(0, 10), Itv(0, 10)}, {Itv(0, 5), Itv(5, 10)}, false);
+  }
+  {   // TernaryAdd2, pc_test.cpp:233-240: (x + y) + z <= 9 as nested binary sums
+    Model<IPC> m;
+    Itv d(3, 10);
+    m.var("x", d).var("y", d).var("z", d).c(bin(bin(bin(V("x"), ADD, V("y")), ADD, V("z")), LEQ, K(9)));
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, {d, d, d}, {Itv(3, 3), Itv(3, 3), Itv(3, 3)}, true);
+  }
+  {   // ResourceConstraint1, pc_test.cpp:360-371: b <=> (x - y <= 0 /\ y - x <= 2)
+    Model<IPC> m;
+    m.var("x", Itv(5, 10)).var("y", Itv(9, 15)).var("b", Itv(0, 1))
+     .c(bin(V("b"), EQUIV, bin(bin(bin(V("x"), SUB, V("y")), LEQ, K(0)), AND, bin(bin(V("y"), SUB, V("x")), LEQ, K(2)))));
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, {Itv(5, 10), Itv(9, 15), Itv(0, 1)}, false);
+    tell_more(ipc, m, bin(V("b"), EQ, K(1)));
+    deduce_and_test(ipc, 1, {Itv(5, 10), Itv(9, 15), Itv(1, 1)}, {Itv(7, 10), Itv(9, 12), Itv(1, 1)}, false);
+  }
+  {   // XorConstraint2, pc_test.cpp:438-447: x = 5 xor y = 5
+    Model<IPC> m;
+    m.var("x", Itv(1, 5)).var("y", Itv(1, 5)).c(bin(bin(V("x"), EQ, K(5)), XOR, bin(V("y"), EQ, K(5))));
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, {Itv(1, 5), Itv(1, 5)}, false);
+    tell_more(ipc, m, bin(V("y"), EQ, K(5)));
+    deduce_and_test(ipc, 1, {Itv(1, 5), Itv(5, 5)}, {Itv(1, 4), Itv(5, 5)}, true);
+  }
+  {   // MinConstraint2, pc_test.cpp:495-507: min(x, y) = z
+    Model<IPC> m;
+    m.var("x", Itv(0, 4)).var("y", Itv(2, 5)).var("z", Itv(0, 10)).c(bin(bin(V("x"), MIN, V("y")), EQ, V("z")));
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, {Itv(0, 4), Itv(2, 5), Itv(0, 10)}, {Itv(0, 4), Itv(2, 5), Itv(0, 4)}, false);
+    tell_more(ipc, m, bin(V("z"), LEQ, K(3)));
+    deduce_and_test(ipc, 1, {Itv(0, 4), Itv(2, 5), Itv(0, 3)}, false);
+    tell_more(ipc, m, bin(V("x"), EQ, K(4)));
+    deduce_and_test(ipc, 1, {Itv(4, 4), Itv(2, 5), Itv(0, 3)}, {Itv(4, 4), Itv(2, 3), Itv(2, 3)}, false);
+  }
+  {   // MaxConstraint2, pc_test.cpp:540-549: max(x, y) = z
+    Model<IPC> m;
+    m.var("x", Itv(0, 4)).var("y", Itv(2, 5)).var("z", Itv(0, 10)).c(bin(bin(V("x"), MAX, V("y")), EQ, V("z")));
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, {Itv(0, 4), Itv(2, 5), Itv(0, 10)}, {Itv(0, 4), Itv(2, 5), Itv(2, 5)}, false);
+    tell_more(ipc, m, bin(V("z"), GEQ, K(5)));
+    deduce_and_test(ipc, 1, {Itv(0, 4), Itv(2, 5), Itv(5, 5)}, {Itv(0, 4), Itv(5, 5), Itv(5, 5)}, true);
+  }
+  {   // IntTimes2 / IntTimes5, pc_test.cpp:626-636, 658-666: x * y = z
+    Model<IPC> m;
+    Itv B(0, 1);
+    m.var("x", B).var("y", B).var("z", B).c(bin(bin(V("x"), MUL, V("y")), EQ, V("z")));
+    IPC ipc = create_and_interpret_and_tell(m);
+    deduce_and_test(ipc, 1, {B, B, B}, false);
+    tell_more(ipc, m, bin(V("z"), EQ, K(1)));
+    deduce_and_test(ipc, 1, {B, B, Itv(1, 1)}, {Itv(1, 1), Itv(1, 1), Itv(1, 1)}, true);
+    Model<IPC> m5;
+    m5.var("x", Itv(1, 2)).var("y", B).var("z", Itv(0, 0)).c(bin(bin(V("x"), MUL, V("y")), EQ, V("z")));
+    IPC ipc5 = create_and_interpret_and_tell(m5);
+    deduce_and_test(ipc5, 1, {Itv(1, 2), B, Itv(0, 0)}, {Itv(1, 2), Itv(0, 0), Itv(0, 0)}, true);
+  }
 }
 
 static void SnapshotRestore() {   // pc.hpp:711-723
@@ -356,6 +429,7 @@ int main() {
   IntAbs1();
   InfiniteDomains();
   UnsupportedShapesAreRefused();
+  TreePropagators();
   SnapshotRestore();
   BitNotEqual();
   BitInConstraint1();

@@ -9,13 +9,20 @@ Formulas are nested tuples (a plain Python stand-in for lala-core's TFormula):
             ('equiv', ('lit', b), ('le', term, ('const', k)))
             ('eq', ('var', x), ('var', y))  ('ne', ('var', x), ('var', y) | ('const', k))
             ('or', lit, ('or', lit, ...)) with lit = ('lit', v) | ('nlit', v)   ('eq', ('abs', ('var', x)), ('var', y))
-Anything else raises `Unsupported` (the reference's "shape of this formula is not supported" interpretation error);
-such formulas stay on the reference's tree-walking path.
+Any other formula over these node types - and ('min' | 'max' | 'mul', t1, t2) terms, ('and' | 'or' | 'equiv' | 'imply' |
+'xor', f, g) connectives, comparisons between two non-constant terms - keeps its tree: `flatten` encodes it as an
+LPC_PC_TREE propagator (the prefix stream of include/lpc_pc.h in the propagator's term slots), which the device walks
+node by node (csrc/pc_tree.cuh). `flatten(..., tree=False)` raises `Unsupported` for those instead (the reference's
+"shape of this formula is not supported" interpretation error); trees deeper than the device limits always do.
 """
 import numpy as np
 
 PC_LIN_LE, PC_REIF_LIN_LE, PC_EQ, PC_NEQ, PC_CLAUSE, PC_ABS_EQ = 1, 2, 3, 4, 5, 6
-PC_LIN_GE, PC_LIN_GT, PC_LIN_EQ, PC_LIN_EQ_VAR = 7, 8, 9, 10
+PC_LIN_GE, PC_LIN_GT, PC_LIN_EQ, PC_LIN_EQ_VAR, PC_TREE = 7, 8, 9, 10, 11
+TREE_TERM_DEPTH, TREE_FORM_DEPTH = 5, 4   # csrc/pc_tree.cuh
+
+_T = {"const": 1, "var": 2, "neg": 3, "abs": 4, "add": 5, "sub": 6, "mul": 7, "sum": 8, "min": 9, "max": 10}
+_F = {"lit": 20, "nlit": 21, "le": 22, "gt": 23, "eq": 24, "ne": 25, "and": 26, "or": 27, "equiv": 28, "imply": 29, "xor": 30}
 
 
 class Unsupported(ValueError):
@@ -102,11 +109,63 @@ def flatten_one(f):
     raise Unsupported(f"formula {op} has no flat kind")
 
 
-def flatten(formulas):
-    """List of formula trees -> (props [n,5] int32, terms [m,2] int32)."""
+def _encode_term(t, out):
+    """Prefix words of a term; returns its height."""
+    op = t[0]
+    if op not in _T:
+        raise Unsupported(f"term {op} has no device rule")
+    if op in ("const", "var"):
+        out += [_T[op], int(t[1])]
+        return 1
+    if op in ("neg", "abs"):
+        out.append(_T[op])
+        return 1 + _encode_term(t[1], out)
+    if op == "sum":
+        if len(t) - 1 < 2:
+            raise Unsupported("an n-ary sum has at least two operands")
+        out += [_T[op], len(t) - 1]
+        return 1 + max(_encode_term(s, out) for s in t[1:])
+    out.append(_T[op])
+    return 1 + max(_encode_term(t[1], out), _encode_term(t[2], out))
+
+
+def _encode_formula(f, out):
+    """Prefix words of a formula; returns the height of its connective nest (a comparison or literal is 1)."""
+    op = f[0]
+    if op not in _F:
+        raise Unsupported(f"formula {op} has no device rule")
+    if op in ("lit", "nlit"):
+        out += [_F[op], int(f[1])]
+        return 1
+    out.append(_F[op])
+    if op in ("le", "gt", "eq", "ne"):
+        if max(_encode_term(f[1], out), _encode_term(f[2], out)) > TREE_TERM_DEPTH:
+            raise Unsupported(f"term deeper than {TREE_TERM_DEPTH} levels")
+        return 1
+    return 1 + max(_encode_formula(f[1], out), _encode_formula(f[2], out))
+
+
+def encode_tree(f):
+    """A formula as an LPC_PC_TREE propagator: (kind, [(w0, w1), ...] word pairs, 0, -1)."""
+    words = []
+    if _encode_formula(f, words) > TREE_FORM_DEPTH:
+        raise Unsupported(f"connectives nested deeper than {TREE_FORM_DEPTH} levels")
+    if len(words) % 2:
+        words.append(0)
+    return PC_TREE, list(zip(words[0::2], words[1::2])), 0, -1
+
+
+def flatten(formulas, tree=True):
+    """List of formula trees -> (props [n,5] int32, terms [m,2] int32). Shapes without a flat kind become LPC_PC_TREE
+    propagators when `tree` is set, else `Unsupported` is raised."""
     props, terms = [], []
     for f in formulas:
-        kind, ts, rhs, bvar = flatten_one(f)
+        try:
+            kind, ts, rhs, bvar = flatten_one(f)
+        except Unsupported:
+            if not tree:
+                raise
+            kind, ts, rhs, bvar = encode_tree(f)
         props.append((kind, len(terms), len(ts), rhs, bvar))
         terms += ts
     return (np.asarray(props, dtype=np.int32).reshape(-1, 5), np.asarray(terms, dtype=np.int32).reshape(-1, 2))

@@ -6,10 +6,12 @@
 //   Formula as term: embed / project                  include/lala/formula.hpp:1090-1102
 //   VariableLiteral<neg>                              include/lala/formula.hpp:80-167
 //   Conjunction / Disjunction / Biconditional         include/lala/formula.hpp:241-451
+//   Implication / ExclusiveDisjunction                include/lala/formula.hpp:453-587
 //   Equality<neg> (=, !=)                             include/lala/formula.hpp:589-724
 //   Inequality<neg> (<=, >)                           include/lala/formula.hpp:727-851
 //   Constant, Variable, Unary<Neg|Abs>                include/lala/terms.hpp:18-175
 //   Binary<GroupAdd|GroupSub|GroupMul<EDIV>>          include/lala/terms.hpp:177-262, 333-434
+//   Binary<GroupMinMax<MIN|MAX>>                      include/lala/terms.hpp:301-331
 //   Nary<Add>                                         include/lala/terms.hpp:436-526
 // The leaf arithmetic, Interval::project(Sig, ...), additive_inverse, fjoin, LB::prev / UB::prev, lives in
 // lala-core v1.2.8 (un-vendored, CMakeLists.txt:33-37) and is restated from its published behaviour:
@@ -102,11 +104,31 @@ inline Itv p_mul(const Itv& a, const Itv& b) {
   if(a.is_bot() || b.is_bot()) return Itv(INF, MINF);
   return hull4(bmul(a.lb, b.lb), bmul(a.lb, b.ub), bmul(a.ub, b.lb), bmul(a.ub, b.ub));
 }
+// EDIV by an interval that holds 0: the quotient is undefined there, so 0 is cut out of the divisor and the result is the
+// hull over its negative and positive parts. Pinned for a 0 endpoint by IntTimes2 (pc_test.cpp:626-636: z = 1, y in [0,1]
+// must give x = 1); a divisor straddling 0 or equal to {0} (-> empty) is UNPINNED.
+inline Itv p_ediv_part(const Itv& a, v_t bl, v_t bu) {
+  return hull4(bediv(a.lb, bl), bediv(a.lb, bu), bediv(a.ub, bl), bediv(a.ub, bu));
+}
 inline Itv p_ediv(const Itv& a, const Itv& b) {
   if(a.is_bot() || b.is_bot()) return Itv(INF, MINF);
-  if(b.contains0()) return Itv();   // unpinned: not exercised by the in-scope shapes (constant non-zero divisors)
-  return hull4(bediv(a.lb, b.lb), bediv(a.lb, b.ub), bediv(a.ub, b.lb), bediv(a.ub, b.ub));
+  Itv r(INF, MINF);
+  if(b.lb < 0) r = fjoin(r, p_ediv_part(a, b.lb, b.ub < -1 ? b.ub : -1));
+  if(b.ub > 0) r = fjoin(r, p_ediv_part(a, b.lb > 1 ? b.lb : 1, b.ub));
+  return r;
 }
+
+// project(MIN / MAX): componentwise on the bounds (pinned by MinConstraint1-3 / MaxConstraint1-3, pc_test.cpp:479-557)
+inline Itv p_min(const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return Itv(INF, MINF);
+  return Itv(a.lb < b.lb ? a.lb : b.lb, a.ub < b.ub ? a.ub : b.ub);
+}
+inline Itv p_max(const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return Itv(INF, MINF);
+  return Itv(a.lb > b.lb ? a.lb : b.lb, a.ub > b.ub ? a.ub : b.ub);
+}
+inline Itv only_lb(const Itv& a) { return Itv(a.lb, INF); }
+inline Itv only_ub(const Itv& a) { return Itv(MINF, a.ub); }
 
 // NBitset<64, local_memory, unsigned long long> (lala-core, un-vendored; see the header).
 struct NBit {
@@ -137,22 +159,28 @@ inline NBit p_neg(const NBit& a) { return a.is_bot() ? a : from_itv(p_neg(a.itv(
 inline NBit additive_inverse(const NBit& a) { return p_neg(a); }   // unpinned; a set has no crossed form
 inline NBit p_abs(const NBit& a) { return a.is_bot() ? a : from_itv(p_abs(a.itv())); }
 inline NBit p_mul(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_mul(a.itv(), b.itv())); }
+inline NBit p_min(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_min(a.itv(), b.itv())); }
+inline NBit p_max(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_max(a.itv(), b.itv())); }
+inline NBit only_lb(const NBit& a) { return from_itv(Itv(a.lo(), INF)); }   // unpinned on bitsets
+inline NBit only_ub(const NBit& a) { return from_itv(Itv(MINF, a.hi())); }
 inline NBit p_ediv(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_ediv(a.itv(), b.itv())); }
 
 template <class U>
 struct Store {
   U* d; int n; bool bot;     // 8-byte cells: {int32 lb, int32 ub} or one uint64 bitset
+  bool touched = false;      // some embed changed a cell since this was last cleared (see fixpoint())
   const U& get(int v) const { return d[v]; }
   void project(int v, U& r) const { r.meet(d[v]); }
   bool embed(int v, const U& u) {                                    // VStore::embed
-    if(d[v].meet(u)) { if(d[v].is_bot()) bot = true; return true; }
+    if(d[v].meet(u)) { touched = true; if(d[v].is_bot()) bot = true; return true; }
     return false;
   }
 };
 static_assert(sizeof(Itv) == 8 && sizeof(NBit) == 8, "8-byte cells");
 
-enum Tok { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8,
-           F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27, F_EQUIV = 28 };
+enum Tok { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8, T_MIN = 9, T_MAX = 10,
+           F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27, F_EQUIV = 28,
+           F_IMPLY = 29, F_XOR = 30 };
 
 template <class U>
 struct Term {
@@ -166,9 +194,10 @@ struct Term {
       case T_VAR: a.project(var, r); break;                          // terms.hpp:69-71
       case T_NEG: { U t; sub[0]->project(a, t); r.meet(p_neg(t)); break; }   // terms.hpp:148-152, 91-93
       case T_ABS: { U t; sub[0]->project(a, t); r.meet(p_abs(t)); break; }
-      case T_ADD: case T_SUB: case T_MUL: {                          // terms.hpp:399-405
+      case T_ADD: case T_SUB: case T_MUL: case T_MIN: case T_MAX: {   // terms.hpp:399-405
         U x, y; sub[0]->project(a, x); sub[1]->project(a, y);
-        r.meet(kind == T_ADD ? p_add(x, y) : kind == T_SUB ? p_sub(x, y) : p_mul(x, y));
+        r.meet(kind == T_ADD ? p_add(x, y) : kind == T_SUB ? p_sub(x, y) : kind == T_MUL ? p_mul(x, y)
+               : kind == T_MIN ? p_min(x, y) : p_max(x, y));
         break;
       }
       case T_NARY_ADD: {                                             // terms.hpp:465-478
@@ -186,7 +215,7 @@ struct Term {
       case T_VAR: return a.embed(var, u);                            // terms.hpp:65-67
       case T_NEG: { U t; t.meet(p_neg(u)); return sub[0]->embed(a, t); }     // terms.hpp:142-146, 95-97
       case T_ABS: { U t; t.meet(fjoin(u, p_neg(u))); return sub[0]->embed(a, t); }   // terms.hpp:112-114
-      case T_ADD: case T_SUB: case T_MUL: {                          // terms.hpp:376-397
+      case T_ADD: case T_SUB: case T_MUL: case T_MIN: case T_MAX: {   // terms.hpp:376-397
         bool ch = false;
         if(!sub[0]->is_const()) {
           U yt, res; sub[1]->project(a, yt);
@@ -218,6 +247,11 @@ struct Term {
   void left_residual(const U& u, const U& b, U& r) const {
     if(kind == T_ADD) r.meet(p_sub(u, b));                           // terms.hpp:196-198
     else if(kind == T_SUB) r.meet(p_add(u, b));                      // terms.hpp:218-220
+    else if(kind == T_MIN || kind == T_MAX) {                        // GroupMinMax, terms.hpp:310-322
+      U m = u; m.meet(b);
+      if(m.is_bot()) r.meet(u);                                      // the other operand cannot be the result
+      else r.meet(kind == T_MIN ? only_lb(u) : only_ub(u));
+    }
     else if(!(u.contains0() && b.contains0())) r.meet(p_ediv(u, b)); // GroupMul, terms.hpp:249-253
   }
   void right_residual(const U& u, const U& b, U& r) const {
@@ -261,6 +295,11 @@ struct Formula {
       case F_EQUIV:                                                  // formula.hpp:408-419
         return negated ? ((f->ask(a) && g->nask(a)) || (f->nask(a) && g->ask(a)))
                        : ((f->ask(a) && g->ask(a)) || (f->nask(a) && g->nask(a)));
+      case F_IMPLY:                                                  // formula.hpp:479-487
+        return negated ? (f->ask(a) && g->nask(a)) : (f->nask(a) || g->ask(a));
+      case F_XOR:                                                    // formula.hpp:541-552 (nask exactly as written there)
+        return negated ? ((f->ask(a) && g->ask(a)) || (f->ask(a) && g->nask(a)))
+                       : ((f->ask(a) && g->nask(a)) || (f->nask(a) && g->ask(a)));
     }
     return false;
   }
@@ -337,6 +376,16 @@ struct Formula {
         else if(g->ask(a)) return f->contradeduce(a);
         else if(g->nask(a)) return f->deduce(a);
         return false;
+      case F_IMPLY:                                                  // formula.hpp:489-499
+        if(f->ask(a)) return negated ? g->contradeduce(a) : g->deduce(a);
+        else if(g->nask(a)) return negated ? f->deduce(a) : f->contradeduce(a);
+        return false;
+      case F_XOR:                                                    // formula.hpp:554-568
+        if(f->ask(a)) return negated ? g->deduce(a) : g->contradeduce(a);
+        else if(f->nask(a)) return negated ? g->contradeduce(a) : g->deduce(a);
+        else if(g->ask(a)) return negated ? f->deduce(a) : f->contradeduce(a);
+        else if(g->nask(a)) return negated ? f->contradeduce(a) : f->deduce(a);
+        return false;
     }
     return false;
   }
@@ -350,7 +399,7 @@ std::unique_ptr<Term<U>> parse_term(const int32_t*& p) {
     case T_CONST: t->k = *p++; break;
     case T_VAR: t->var = *p++; break;
     case T_NEG: case T_ABS: t->sub.push_back(parse_term<U>(p)); break;
-    case T_ADD: case T_SUB: case T_MUL: t->sub.push_back(parse_term<U>(p)); t->sub.push_back(parse_term<U>(p)); break;
+    case T_ADD: case T_SUB: case T_MUL: case T_MIN: case T_MAX: t->sub.push_back(parse_term<U>(p)); t->sub.push_back(parse_term<U>(p)); break;
     case T_NARY_ADD: { int n = *p++; for(int i = 0; i < n; ++i) t->sub.push_back(parse_term<U>(p)); break; }
   }
   return t;
@@ -388,7 +437,13 @@ void fixpoint(const std::vector<std::unique_ptr<Formula<U>>>& props, U* cells, i
   const size_t n = props.size();
   while(changed && !(stop_on_bot && s.bot) && (max_sweeps <= 0 || sweeps < max_sweeps)) {
     changed = false;
+    s.touched = false;
     for(size_t i = 0; i < n; ++i) changed |= props[i]->deduce(s);
+    // Inequality::deduce ASSIGNS its flag on the right-hand side (formula.hpp:803), so `l <= r` with two non-constant
+    // sides can tighten l and return false; a loop driven by the flags alone may then stop short of a fixpoint. The
+    // checker keeps iterating while the store moves - identical on every reference golden (none hits the case), and the
+    // only well-defined target for a parallel schedule. deduce(i)'s own return value stays literal.
+    changed |= s.touched;
     any |= changed;
     ++sweeps;
   }

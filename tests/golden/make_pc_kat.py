@@ -103,6 +103,48 @@ kat("InfiniteDomain2.b", "pc_test.cpp:785-787", [TOP, [0, 0]], [["equiv", ["lit"
 xor = ["equiv", ["eq", v(0), c(5)], ["ne", v(1), c(5)]]
 kat("XorConstraint1.b", "pc_test.cpp:434-435", [[1, 1], TOP], [xor], [[1, 1], [5, 5]], ua=True, changed=True)
 kat("XorConstraint2.b", "pc_test.cpp:445-446", [[1, 5], [5, 5]], [xor], [[1, 4], [5, 5]], ua=True, changed=True)
+# bool_xor builds an ExclusiveDisjunction node (pc.hpp:391-395, formula.hpp:518-587): the same two cases on that node
+xor2 = ["xor", ["eq", v(0), c(5)], ["eq", v(1), c(5)]]
+kat("XorConstraint1.a.xor", "pc_test.cpp:429-432", [TOP, TOP], [xor2], [TOP, TOP], ua=False, changed=False)
+kat("XorConstraint1.b.xor", "pc_test.cpp:434-435", [[1, 1], TOP], [xor2], [[1, 1], [5, 5]], ua=True, changed=True)
+kat("XorConstraint2.a.xor", "pc_test.cpp:440-443", [[1, 5], [1, 5]], [xor2], [[1, 5], [1, 5]], ua=False, changed=False)
+kat("XorConstraint2.b.xor", "pc_test.cpp:445-446", [[1, 5], [5, 5]], [xor2], [[1, 4], [5, 5]], ua=True, changed=True)
+# `var {1, 3}: x` typed into PC is the disjunction x = 1 \/ x = 3 (one propagator, pc_test.cpp:470-472); then x = y
+inx = ["or", ["eq", v(0), c(1)], ["eq", v(0), c(3)]]
+kat("InConstraint1.a", "pc_test.cpp:470-472", [[1, 3], [2, 3]], [inx], [[1, 3], [2, 3]], ua=False, changed=False)
+kat("InConstraint1.b", "pc_test.cpp:474-475", [[1, 3], [2, 3]], [inx, ["eq", v(0), v(1)]], [[3, 3], [3, 3]], ua=True, changed=True)
+# int_min(x, y, z) / int_max(x, y, z): Equality(Binary<GroupMinMax>(x, y), z) (pc.hpp:241-242, terms.hpp:301-331)
+mn, mx = ["eq", ["min", v(0), v(1)], v(2)], ["eq", ["max", v(0), v(1)], v(2)]
+kat("MinConstraint1.a", "pc_test.cpp:479-483", [[0, 4], [2, 5], [0, 10]], [mn], [[0, 4], [2, 5], [0, 4]], ua=False, changed=True)
+kat("MinConstraint1.b", "pc_test.cpp:485-486", [[0, 4], [2, 5], [0, 3]], [mn], [[0, 4], [2, 5], [0, 3]], ua=False, changed=False)
+kat("MinConstraint1.c", "pc_test.cpp:488-489", [[0, 1], [2, 5], [0, 3]], [mn], [[0, 1], [2, 5], [0, 1]], ua=False, changed=True)
+kat("MinConstraint1.d", "pc_test.cpp:491-492", [[0, 0], [2, 5], [0, 1]], [mn], [[0, 0], [2, 5], [0, 0]], ua=True, changed=True)
+kat("MinConstraint2.c", "pc_test.cpp:505-506", [[4, 4], [2, 5], [0, 3]], [mn], [[4, 4], [2, 3], [2, 3]], ua=False, changed=True)
+mn3 = ["eq", ["min", v(1), v(2)], c(1)]
+b1le, b2ge = ["equiv", ["lit", 1], ["le", v(0), c(5)]], ["equiv", ["lit", 2], ["le", c(5), v(0)]]
+kat("MinConstraint3.a", "pc_test.cpp:510-514", [TOP, B, B], [mn3], [TOP, [1, 1], [1, 1]], ua=True, changed=True)
+kat("MinConstraint3.b", "pc_test.cpp:516-517", [TOP, [1, 1], [1, 1]], [mn3, b1le], [[NI, 5], [1, 1], [1, 1]], ua=True, changed=True)
+kat("MinConstraint3.c", "pc_test.cpp:519-520", [[NI, 5], [1, 1], [1, 1]], [mn3, b1le, b2ge], [[5, 5], [1, 1], [1, 1]], ua=True, changed=True)
+kat("MaxConstraint1.a", "pc_test.cpp:524-528", [[0, 4], [2, 5], [0, 10]], [mx], [[0, 4], [2, 5], [2, 5]], ua=False, changed=True)
+kat("MaxConstraint1.b", "pc_test.cpp:530-531", [[0, 4], [2, 5], [2, 3]], [mx], [[0, 3], [2, 3], [2, 3]], ua=False, changed=True)
+kat("MaxConstraint1.c", "pc_test.cpp:533-534", [[0, 1], [2, 3], [2, 3]], [mx], [[0, 1], [2, 3], [2, 3]], ua=False, changed=False)
+kat("MaxConstraint1.d", "pc_test.cpp:536-537", [[0, 1], [2, 2], [2, 3]], [mx], [[0, 1], [2, 2], [2, 2]], ua=True, changed=True)
+kat("MaxConstraint2.b", "pc_test.cpp:547-548", [[0, 4], [2, 5], [5, 5]], [mx], [[0, 4], [5, 5], [5, 5]], ua=True, changed=True)
+mx3 = ["eq", ["max", v(1), v(2)], c(0)]
+b2ge7 = ["equiv", ["lit", 2], ["le", c(7), v(0)]]
+kat("MaxConstraint3.a", "pc_test.cpp:551-555", [TOP, B, B], [mx3], [TOP, [0, 0], [0, 0]], ua=True, changed=True)
+kat("MaxConstraint3.b", "pc_test.cpp:557-558", [TOP, [0, 0], [0, 0]], [mx3, b1le], [[6, PI], [0, 0], [0, 0]], ua=True, changed=True)
+kat("MaxConstraint3.c", "pc_test.cpp:560-561", [[6, PI], [0, 0], [0, 0]], [mx3, b1le, b2ge7], [[6, 6], [0, 0], [0, 0]], ua=True, changed=True)
+# int_times(x, y, z): Equality(Binary<GroupMul<EDIV>>(x, y), z) (pc.hpp:236, terms.hpp:231-262)
+tm = ["eq", ["mul", v(0), v(1)], v(2)]
+kat("IntTimes1.a", "pc_test.cpp:612-619", [B, B, B], [tm], [B, B, B], ua=False, changed=False)
+kat("IntTimes1.b", "pc_test.cpp:620-621", [[1, 1], B, B], [tm], [[1, 1], B, B], ua=False, changed=False)
+kat("IntTimes1.c", "pc_test.cpp:622-623", [[1, 1], [1, 1], B], [tm], [[1, 1], [1, 1], [1, 1]], ua=True, changed=True)
+kat("IntTimes2.b", "pc_test.cpp:634-635", [B, B, [1, 1]], [tm], [[1, 1], [1, 1], [1, 1]], ua=True, changed=True)
+kat("IntTimes3", "pc_test.cpp:638-646", [[0, 0], B, B], [tm], [[0, 0], B, [0, 0]], ua=True, changed=True)
+kat("IntTimes4", "pc_test.cpp:648-656", [B, [0, 0], B], [tm], [B, [0, 0], [0, 0]], ua=True, changed=True)
+kat("IntTimes5", "pc_test.cpp:658-666", [[1, 2], B, [0, 0]], [tm], [[1, 2], [0, 0], [0, 0]], ua=True, changed=True)
+kat("IntTimes6", "pc_test.cpp:668-676", [B, [1, 2], [0, 0]], [tm], [[0, 0], [1, 2], [0, 0]], ua=True, changed=True)
 
 TERM_KATS = [
     dict(name="TermTest.AddTermBinary", source="pc_test.cpp:31-47", store=[D10, D10], term=["add", v(0), v(1)],

@@ -69,12 +69,14 @@ void devhost_exhaustive(int sig, int lo, int hi, int* out) {
 struct HostAcc {
   int* d;
   mutable int seen_bot;
+  int touched;
   Itv load(int v) const { if(d[2 * v] > d[2 * v + 1]) seen_bot = 1; return Itv(d[2 * v], d[2 * v + 1]); }
   int embed(int v, const Itv& u) {
     int f = 0;
     if(u.lb > d[2 * v]) { d[2 * v] = u.lb; f = 1; }
     if(u.ub < d[2 * v + 1]) { d[2 * v + 1] = u.ub; f = 1; }
     if(f && d[2 * v] > d[2 * v + 1]) f |= 2;
+    touched |= f;
     return f;
   }
 };
@@ -88,9 +90,9 @@ int devhost_pc_fixpoint(const int* props, long long n, const int* terms, int* lb
     for(long long i = 0; i < n; ++i) {
       const int* p = props + 5 * i;
       int4 h = make_int4(p[0] | (p[2] << 8), p[1], p[3], p[4]);
-      HostAcc acc{lbub, 0};
+      HostAcc acc{lbub, 0, 0};
       int f = pc_deduce(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
-      changed |= f & 1; bot |= ((f >> 1) & 1) | acc.seen_bot;
+      changed |= (f | acc.touched) & 1; bot |= ((f >> 1) & 1) | acc.seen_bot;
     }
     any |= changed;
     ++sweeps;
@@ -101,7 +103,7 @@ int devhost_pc_fixpoint(const int* props, long long n, const int* terms, int* lb
 int devhost_pc_ask(const int* props, long long i, const int* terms, const int* lbub) {
   const int* p = props + 5 * i;
   int4 h = make_int4(p[0] | (p[2] << 8), p[1], p[3], p[4]);
-  HostAcc acc{const_cast<int*>(lbub), 0};
+  HostAcc acc{const_cast<int*>(lbub), 0, 0};
   return pc_ask(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
 }
 

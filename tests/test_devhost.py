@@ -19,7 +19,7 @@ OPS = dict(ADD=2, MUL=4, MIN=6, MAX=7, TDIV=25, FDIV=27, CDIV=29, EDIV=31, EQ=46
 @pytest.fixture(scope="module")
 def devhost():
     csrc = os.path.join(os.path.dirname(HERE), "lala-pc_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("pir_device.cuh", "pir_div.cuh", "pc_device.cuh")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("pir_device.cuh", "pir_div.cuh", "pc_device.cuh", "pc_tree.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.run(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
                         "-o", LIB, SRC], check=True, capture_output=True)

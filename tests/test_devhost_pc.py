@@ -8,7 +8,7 @@ import pytest
 from conftest import load_golden
 from oracle import oracle as O
 from test_devhost import devhost  # noqa: F401  (fixture: builds tests/native/libdevhost.so)
-from test_gpu_pc import random_pc, to_tree
+from test_gpu_pc import random_pc, random_tree_pc, to_tree
 
 
 def host_fixpoint(D, props, terms, store):
@@ -46,23 +46,39 @@ def compare(D, formulas, store, label):
 
 def test_goldens_and_flattener(devhost):
     from lala_pc_b200 import pcflat
-    ran = 0
+    ran = n_tree = 0
     for k in load_golden("pc_kat.json")["props"]:
         formulas = [to_tree(p) for p in k["props"]]
-        try:
-            pcflat.flatten(formulas)
-        except pcflat.Unsupported:
-            continue
+        props, _ = pcflat.flatten(formulas)      # flat kinds where there is one, LPC_PC_TREE otherwise
+        n_tree += int((props[:, 0] == pcflat.PC_TREE).any())
         ran += 1
         compare(devhost, formulas, np.array(k["store"], dtype=np.int32), k["name"])
-    assert ran >= 38
-    # shapes without a flat kind are refused, not approximated
+    assert ran >= 83 and n_tree >= 40
+    # shapes without a flat kind are never approximated by one: strict flattening refuses them
     for f in (("le", ("add", ("add", ("var", 0), ("var", 1)), ("var", 2)), ("const", 3)),
               ("le", ("var", 0), ("var", 1)), ("gt", ("var", 0), ("var", 1)), ("le", ("var", 0), ("add", ("const", -5), ("var", 1))),
               ("le", ("sub", ("var", 0), ("mul", ("const", 3), ("var", 1))), ("const", 2)),
               ("equiv", ("lit", 0), ("and", ("lit", 1), ("lit", 2)))):
         with pytest.raises(pcflat.Unsupported):
-            pcflat.flatten([f])
+            pcflat.flatten([f], tree=False)
+        assert pcflat.flatten([f])[0][0, 0] == pcflat.PC_TREE
+
+
+def test_random_tree_networks(devhost):
+    """The tree interpreter (pc_tree.cuh) against the tree-walking checker on random formula nests."""
+    rng = np.random.default_rng(17)
+    n_ok = 0
+    for trial in range(400):
+        nvars = int(rng.integers(3, 9))
+        forms = random_tree_pc(rng, nvars)
+        if trial % 3 == 0:
+            forms += random_pc(rng, max(nvars, 4))[:2] if nvars >= 4 else []
+        a = rng.integers(-6, 12, (nvars, 2))
+        store = np.stack([a.min(1), a.max(1)], axis=1).astype(np.int32)
+        store[rng.random(nvars) < 0.4] = (0, 1)   # finite domains only: x > x + y walks an infinite bound one unit per sweep
+        st = compare(devhost, forms, store, f"tree {trial}")
+        n_ok += not st.is_bot
+    assert n_ok >= 100
 
 
 @pytest.mark.parametrize("cfg", ["config3", "config5"])
