@@ -162,6 +162,20 @@ int lpc_table_create(const lpc_bytecode* records, int64_t n, int32_t nvars, lpc_
     if(d >= D_TDIV && d <= D_EDIV) t->has_div = true;
   }
   t->host.assign(records, records + n);
+  {   // opcode runs (OpSegs)
+    OpSegs& sg = t->opsegs;
+    sg.n = 0;
+    bool ok = true;
+    for(int64_t i = 0; i < n && ok; ++i) {
+      if(i == 0 || op[i] != op[i - 1]) {
+        if(sg.n == LPC_MAX_OPSEG) { ok = false; break; }
+        sg.op[sg.n] = op[i];
+        sg.start[sg.n++] = (int)i;
+      }
+    }
+    if(!ok) sg.n = 0;
+    sg.start[sg.n] = (int)n;
+  }
   // var -> records incidence (counting sort)
   std::vector<int> off((size_t)nvars + 1, 0);
   auto each_var = [&](int64_t i, auto f) {

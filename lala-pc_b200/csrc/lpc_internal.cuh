@@ -45,6 +45,16 @@ struct TableDev {
   const int* inc_idx;   // [3 n] (duplicates removed per record)
 };
 
+// Runs of equal opcode in table order (exact record indices, padding excluded). A table built by PIR::deduce(tell) is
+// sorted by (op, y, x, z) (pir.hpp:343-347) and has at most ten runs; n == 0 means "more than LPC_MAX_OPSEG runs", i.e.
+// not sorted by opcode, and the kernels fall back to dispatching per record.
+#define LPC_MAX_OPSEG 16
+struct OpSegs {
+  int n;
+  int start[LPC_MAX_OPSEG + 1];
+  unsigned char op[LPC_MAX_OPSEG];
+};
+
 // Control block of one fixpoint run (device memory, one per store handle).
 struct FixCtl {
   int flags[4];         // rotating per-iteration flag words: bit0 = changed, bit1 = bot
@@ -77,6 +87,7 @@ struct lpc_table {
   void* d_inc_off = nullptr; void* d_inc_idx = nullptr;
   bool has_div = false;
   long long op_count[10] = {0};
+  lpc::OpSegs opsegs{};             // opcode runs for the per-operator loops of the block kernels (pir_batch.cu)
   // launch plan of the dense sweep, computed once on first use (opcode segments in quads, blocks per SM)
   bool plan_ready = false;
   int seg_n = 0;

@@ -28,6 +28,52 @@ struct BatchCtl {
   int next_store;              // dynamic scheduler
 };
 
+
+// ---- one dense sweep of the table over the store at shared address a_S ------------------------------------------------
+// The records of one opcode run, with the opcode a compile-time constant: no per-record opcode load, no dispatch, and the
+// rule is the only code in the loop body (a sorted table has one run per operator, so warps are uniform anyway; what this
+// removes is the ~16 instructions per record of fetching the opcode byte, the jump table and the phi moves after it -
+// a third of the instructions of an `x = y + z` record in a kernel that is bound by instruction issue).
+template <int OP, bool HAS_DIV, bool TABLE_SMEM>
+__device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int* sx, const int* sy, const int* sz,
+                                         const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  int f = 0;
+  for(int i = s0 + tid; i < s1; i += nthr) {
+    int op = OP, xi, yi, zi;
+    if(TABLE_SMEM) { if(OP < 0) op = lds_u8(a_op + i); xi = lds_s32(a_x + 4 * i); yi = lds_s32(a_y + 4 * i); zi = lds_s32(a_z + 4 * i); }
+    else { if(OP < 0) op = sop[i]; xi = sx[i]; yi = sy[i]; zi = sz[i]; }
+    const unsigned ax = a_S + 8u * xi, ay = a_S + 8u * yi, az = a_S + 8u * zi;
+    const int2 a = lds_itv(ax), bb = lds_itv(ay), c = lds_itv(az);
+    Itv r1(a.x, a.y), r2(bb.x, bb.y), r3(c.x, c.y);
+    deduce_regs<HAS_DIV>(op, r1, r2, r3);
+    const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > bb.x) | (r2.ub < bb.y) | (r3.lb > c.x) | (r3.ub < c.y)
+                    | (a.x > a.y) | (bb.x > bb.y) | (c.x > c.y);
+    if(slow) {
+      if((a.x > a.y) | (bb.x > bb.y) | (c.x > c.y)) f |= 2;
+      f |= commit_smem(ax, a, r1) | commit_smem(ay, bb, r2) | commit_smem(az, c, r3);
+    }
+  }
+  return f;
+}
+// OP = -1: opcode read per record (the division operators, and tables that are not sorted by opcode)
+template <bool HAS_DIV, bool TABLE_SMEM>
+__device__ __forceinline__ int sweep_table(const OpSegs& segs, int npad, unsigned a_S, const int* sx, const int* sy, const int* sz,
+                                           const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op) {
+  if(segs.n == 0) return sweep_run<-1, HAS_DIV, TABLE_SMEM>(0, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op);
+  int f = 0;
+  for(int s = 0; s < segs.n; ++s) {
+    const int s0 = segs.start[s], s1 = segs.start[s + 1];
+#define LPC_RUN(O) case O: f |= sweep_run<O, HAS_DIV, TABLE_SMEM>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op); break;
+    switch(segs.op[s]) {
+      LPC_RUN(D_ADD) LPC_RUN(D_MUL) LPC_RUN(D_MIN) LPC_RUN(D_MAX) LPC_RUN(D_EQ) LPC_RUN(D_LEQ)
+      default: f |= sweep_run<-1, HAS_DIV, TABLE_SMEM>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op); break;
+    }
+#undef LPC_RUN
+  }
+  return f;
+}
+
 // ---- change-driven fixpoint of ONE store by its block ---------------------------------------------------------------
 // The loop of k_pir_batch made incremental: records are evaluated in groups of 32 (one warp-iteration) and a group is
 // evaluated in a sweep only if it is flagged; tightening a variable flags, for the next sweep, the groups of its incident
@@ -104,7 +150,7 @@ __device__ __forceinline__ bool block_fixpoint_cd(const TableDev& t, const int2*
 
 // Shared memory carve-up (dynamic): [mbarriers 64 B][store ring 2 x sbytes][table: x | y | z | op][CD: 3 group maps]
 template <bool HAS_DIV, bool TABLE_SMEM, bool CD>
-__global__ void k_pir_batch(TableDev t, int2* stores, int n_stores, int sbytes, uint8_t* flags, int* sweeps_out,
+__global__ void k_pir_batch(TableDev t, OpSegs segs, int2* stores, int n_stores, int sbytes, uint8_t* flags, int* sweeps_out,
                             int* obj_out, BatchCtl* ctl, int objective_var, int max_sweeps, int stop_on_bot,
                             const int* seeds, int nseeds) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -188,22 +234,7 @@ __global__ void k_pir_batch(TableDev t, int2* stores, int n_stores, int sbytes, 
       bot = __syncthreads_or(f0) != 0;
       bool changed = !(bot && stop_on_bot) && t.n > 0;
       while(changed) {
-        int f = 0;
-        for(int i = tid; i < npad; i += nthr) {
-          int op, xi, yi, zi;
-          if(TABLE_SMEM) { op = lds_u8(a_op + i); xi = lds_s32(a_x + 4 * i); yi = lds_s32(a_y + 4 * i); zi = lds_s32(a_z + 4 * i); }
-          else { op = sop[i]; xi = sx[i]; yi = sy[i]; zi = sz[i]; }
-          const unsigned ax = a_S + 8u * xi, ay = a_S + 8u * yi, az = a_S + 8u * zi;
-          const int2 a = lds_itv(ax), bb = lds_itv(ay), c = lds_itv(az);
-          Itv r1(a.x, a.y), r2(bb.x, bb.y), r3(c.x, c.y);
-          deduce_regs<HAS_DIV>(op, r1, r2, r3);
-          const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > bb.x) | (r2.ub < bb.y) | (r3.lb > c.x) | (r3.ub < c.y)
-                          | (a.x > a.y) | (bb.x > bb.y) | (c.x > c.y);
-          if(slow) {
-            if((a.x > a.y) | (bb.x > bb.y) | (c.x > c.y)) f |= 2;
-            f |= commit_smem(ax, a, r1) | commit_smem(ay, bb, r2) | commit_smem(az, c, r3);
-          }
-        }
+        const int f = sweep_table<HAS_DIV, TABLE_SMEM>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op);
         ++sweeps;
         if(f & 2) *s_bot = 1;
         // one barrier per sweep: it publishes the sweep's shared-memory joins, votes has_changed, and orders s_bot
@@ -272,7 +303,7 @@ struct SearchCtl {
 
 // One fixpoint of the store at shared address a_S (the loop of k_pir_batch). Returns bot; adds to sweeps.
 template <bool HAS_DIV, bool TABLE_SMEM>
-__device__ __forceinline__ bool block_fixpoint(const TableDev& t, const int2* S, unsigned a_S, const int* sx, const int* sy,
+__device__ __forceinline__ bool block_fixpoint(const TableDev& t, const OpSegs& segs, const int2* S, unsigned a_S, const int* sx, const int* sy,
                                                const int* sz, const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z,
                                                unsigned a_op, volatile int* s_bot, long long& sweeps_acc) {
   const int tid = threadIdx.x, nthr = blockDim.x, npad = (int)t.n_pad;
@@ -283,22 +314,7 @@ __device__ __forceinline__ bool block_fixpoint(const TableDev& t, const int2* S,
   bool changed = !bot && t.n > 0;
   int sweeps = 0;
   while(changed) {
-    int f = 0;
-    for(int i = tid; i < npad; i += nthr) {
-      int op, xi, yi, zi;
-      if(TABLE_SMEM) { op = lds_u8(a_op + i); xi = lds_s32(a_x + 4 * i); yi = lds_s32(a_y + 4 * i); zi = lds_s32(a_z + 4 * i); }
-      else { op = sop[i]; xi = sx[i]; yi = sy[i]; zi = sz[i]; }
-      const unsigned ax = a_S + 8u * xi, ay = a_S + 8u * yi, az = a_S + 8u * zi;
-      const int2 a = lds_itv(ax), bb = lds_itv(ay), c = lds_itv(az);
-      Itv r1(a.x, a.y), r2(bb.x, bb.y), r3(c.x, c.y);
-      deduce_regs<HAS_DIV>(op, r1, r2, r3);
-      const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > bb.x) | (r2.ub < bb.y) | (r3.lb > c.x) | (r3.ub < c.y)
-                      | (a.x > a.y) | (bb.x > bb.y) | (c.x > c.y);
-      if(slow) {
-        if((a.x > a.y) | (bb.x > bb.y) | (c.x > c.y)) f |= 2;
-        f |= commit_smem(ax, a, r1) | commit_smem(ay, bb, r2) | commit_smem(az, c, r3);
-      }
-    }
+    const int f = sweep_table<HAS_DIV, TABLE_SMEM>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op);
     ++sweeps;
     if(f & 2) *s_bot = 1;
     const int any_chg = __syncthreads_or(f & 1);
@@ -311,7 +327,7 @@ __device__ __forceinline__ bool block_fixpoint(const TableDev& t, const int2* S,
 
 // Shared memory carve-up (dynamic): [mbarriers + scalars 64 B][store sbytes][table: x | y | z | op][CD: 3 group maps]
 template <bool HAS_DIV, bool TABLE_SMEM, bool CD>
-__global__ void __launch_bounds__(HAS_DIV ? 256 : 1024) k_pir_search(TableDev t, const int2* roots, int n_stores, int sbytes, int2* stack, int* vstack, int max_depth,
+__global__ void __launch_bounds__(HAS_DIV ? 256 : 1024) k_pir_search(TableDev t, OpSegs segs, const int2* roots, int n_stores, int sbytes, int2* stack, int* vstack, int max_depth,
                              const int* bvars, int nb, int objective_var, long long max_nodes, long long* per_store,
                              SearchCtl* ctl, const int* root_seeds, int n_root_seeds) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -380,7 +396,7 @@ __global__ void __launch_bounds__(HAS_DIV ? 256 : 1024) k_pir_search(TableDev t,
       }
       else {
         const long long before = sweeps;
-        bot = block_fixpoint<HAS_DIV, TABLE_SMEM>(t, S, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, s_bot, sweeps);
+        bot = block_fixpoint<HAS_DIV, TABLE_SMEM>(t, segs, S, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, s_bot, sweeps);
         evals += (sweeps - before) * ((npad + 31) / 32);
       }
       ++nodes;
@@ -512,7 +528,7 @@ struct lpc_batch {
   lpc::BatchCtl* h_init = nullptr;   // pinned initial control block
 };
 
-typedef void (*batch_kernel_t)(TableDev, int2*, int, int, uint8_t*, int*, int*, BatchCtl*, int, int, int, const int*, int);
+typedef void (*batch_kernel_t)(TableDev, OpSegs, int2*, int, int, uint8_t*, int*, int*, BatchCtl*, int, int, int, const int*, int);
 
 static batch_kernel_t pick_batch_kernel(bool has_div, bool table_smem, bool cd) {
   if(cd) {
@@ -690,7 +706,7 @@ int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t o
   LPC_CUDA(cudaEventRecord(b->ev0, st));
   LPC_CUDA(cudaMemcpyAsync(b->d_ctl, b->h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
   if(b->n_stores > 0) {
-    k<<<grid, threads, smem, st>>>(t->dev, b->d, b->n_stores, b->sbytes, b->d_flags, b->d_sweeps, b->d_obj, b->d_ctl,
+    k<<<grid, threads, smem, st>>>(t->dev, t->opsegs, b->d, b->n_stores, b->sbytes, b->d_flags, b->d_sweeps, b->d_obj, b->d_ctl,
                                   objective_var, o->max_sweeps, o->stop_on_bot, b->d_seeds, b->n_seeds);
     g_launches++;
     LPC_CUDA(cudaGetLastError());
@@ -766,7 +782,7 @@ int lpc_batch_search(lpc_batch* b, const int32_t* branch_vars, int32_t n_branch,
   if(base > (size_t)optin) { set_error("lpc_batch_search: a store of %d variables does not fit shared memory", b->nvars); return LPC_ERR_UNSUPPORTED; }
   const bool table_smem = base + tbl <= (size_t)optin;
   const size_t smem = table_smem ? base + tbl : base;
-  typedef void (*search_kernel_t)(TableDev, const int2*, int, int, int2*, int*, int, const int*, int, int, long long, long long*,
+  typedef void (*search_kernel_t)(TableDev, OpSegs, const int2*, int, int, int2*, int*, int, const int*, int, int, long long, long long*,
                                   SearchCtl*, const int*, int);
   search_kernel_t k;
   if(cd) k = t->has_div ? (table_smem ? k_pir_search<true, true, true> : k_pir_search<true, false, true>)
@@ -794,7 +810,7 @@ int lpc_batch_search(lpc_batch* b, const int32_t* branch_vars, int32_t n_branch,
   LPC_CUDA(cudaMemcpyAsync(d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
   LPC_CUDA(cudaEventRecord(b->ev0, st));
   if(b->n_stores > 0) {
-    k<<<grid, threads, smem, st>>>(t->dev, b->d, b->n_stores, b->sbytes, d_stack, d_vstack, o->max_depth, d_bv, n_branch,
+    k<<<grid, threads, smem, st>>>(t->dev, t->opsegs, b->d, b->n_stores, b->sbytes, d_stack, d_vstack, o->max_depth, d_bv, n_branch,
                                   o->objective_var, (long long)o->max_nodes, d_ps, d_ctl, b->d_seeds, b->n_seeds);
     g_launches++;
     LPC_CUDA(cudaGetLastError());
