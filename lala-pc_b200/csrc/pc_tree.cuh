@@ -9,7 +9,8 @@
 //             Implication                 formula.hpp:453-516     ExclusiveDisjunction   formula.hpp:518-587
 //             Equality<neg>               formula.hpp:589-721     Inequality<neg>        formula.hpp:727-845
 //   terms     Constant, Variable          terms.hpp:18-85         Unary<Neg | Abs>       terms.hpp:87-175
-//             Binary<Add|Sub|Mul|Min|Max> terms.hpp:177-262, 301-434                     Nary<Add>  terms.hpp:436-526
+//             Binary<Add|Sub|Mul|Min|Max> terms.hpp:177-262, 301-434                     Nary<Add|Mul>  terms.hpp:436-526
+//             Binary<TDiv|FDiv|CDiv|EDiv> terms.hpp:264-299       AbstractElement        formula.hpp:14-77
 // The walk is the reference's: `project` folds a term bottom-up, `embed` pushes an interval down through the residuals
 // of each group, formulas dispatch ask / nask / deduce / contradeduce with the `negated` flag folded in.
 //
@@ -26,9 +27,11 @@
 namespace lpc {
 
 enum PcTok : int { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8,
-                   T_MIN = 9, T_MAX = 10,
+                   T_MIN = 9, T_MAX = 10, T_TDIV = 11, T_FDIV = 12, T_CDIV = 13, T_EDIV = 14, T_NARY_MUL = 15,
                    F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27,
-                   F_EQUIV = 28, F_IMPLY = 29, F_XOR = 30 };
+                   F_EQUIV = 28, F_IMPLY = 29, F_XOR = 30, F_AE = 31 };
+// F_AE op var k: AbstractElement over the store, `var op k` with op = 0 <=, 1 >=, 2 =, 3 != (formula.hpp:14-77)
+enum PcAeOp : int { AE_LEQ = 0, AE_GEQ = 1, AE_EQ = 2, AE_NEQ = 3 };
 
 constexpr int PC_TREE_TERM_DEPTH = 5;   // height of the tallest term  (x + y = 2, (2*x + y) + 3*z = 4)
 constexpr int PC_TREE_FORM_DEPTH = 4;   // height of the connective nest above a comparison (b <=> (p /\ q) = 3)
@@ -39,8 +42,8 @@ constexpr int PC_TREE_FORM_DEPTH = 4;   // height of the connective nest above a
 #define LPC_NI __device__ __noinline__
 #endif
 
-__host__ __device__ inline bool tok_is_term(int k) { return k >= T_CONST && k <= T_MAX; }
-__host__ __device__ inline bool tok_is_binary_term(int k) { return k == T_ADD || k == T_SUB || k == T_MUL || k == T_MIN || k == T_MAX; }
+__host__ __device__ inline bool tok_is_div(int k) { return k >= T_TDIV && k <= T_EDIV; }
+__host__ __device__ inline bool tok_is_binary_term(int k) { return k == T_ADD || k == T_SUB || k == T_MUL || k == T_MIN || k == T_MAX || tok_is_div(k); }
 
 // The first word after the term that starts at p (iterative: `pending` subterms still to be read).
 __host__ __device__ inline const int* tree_skip_term(const int* p) {
@@ -49,7 +52,7 @@ __host__ __device__ inline const int* tree_skip_term(const int* p) {
     const int k = *p++;
     if(k == T_CONST || k == T_VAR) { ++p; --pending; }
     else if(k == T_NEG || k == T_ABS) { }
-    else if(k == T_NARY_ADD) { pending += *p++ - 1; }
+    else if(k == T_NARY_ADD || k == T_NARY_MUL) { pending += *p++ - 1; }
     else ++pending;   // binary
   }
   return p;
@@ -59,6 +62,7 @@ __host__ __device__ inline const int* tree_skip_formula(const int* p) {
   while(pending > 0) {
     const int k = *p++;
     if(k == F_VARLIT || k == F_NVARLIT) { ++p; --pending; }
+    else if(k == F_AE) { p += 3; --pending; }
     else if(k >= F_LEQ && k <= F_NEQ) { p = tree_skip_term(tree_skip_term(p)); --pending; }
     else ++pending;   // binary connective
   }
@@ -76,7 +80,7 @@ struct TreeCheck {
     if(k == T_VAR) { if(i >= n || w[i] < 0 || w[i] >= nvars) { ok = false; return 0; } ++i; return 1; }
     if(k == T_NEG || k == T_ABS) return 1 + term(i);
     if(tok_is_binary_term(k)) { const int a = term(i); if(!ok) return 0; const int b = term(i); return 1 + (a > b ? a : b); }
-    if(k == T_NARY_ADD) {
+    if(k == T_NARY_ADD || k == T_NARY_MUL) {
       if(i >= n || w[i] < 2 || w[i] > n) { ok = false; return 0; }
       const int m = w[i++];
       int h = 0;
@@ -90,6 +94,7 @@ struct TreeCheck {
     if(i >= n) { ok = false; return 0; }
     const int k = w[i++];
     if(k == F_VARLIT || k == F_NVARLIT) { if(i >= n || w[i] < 0 || w[i] >= nvars) { ok = false; return 0; } ++i; return 1; }
+    if(k == F_AE) { if(i + 2 >= n || w[i] < AE_LEQ || w[i] > AE_NEQ || w[i + 1] < 0 || w[i + 1] >= nvars) { ok = false; return 0; } i += 3; return 1; }
     if(k >= F_LEQ && k <= F_NEQ) {
       const int a = term(i); if(!ok) return 0;
       const int b = term(i);
@@ -151,6 +156,45 @@ LPC_HD Itv tr_max(const Itv& a, const Itv& b) {
   if(a.is_bot() || b.is_bot()) return itv_bot();
   return Itv(max(a.lb, b.lb), max(a.ub, b.ub));
 }
+// project(TDIV | FDIV | CDIV | EDIV): the corner quotients with the operator's rounding, 0 cut out of the divisor.
+// Pinned on 0/1 domains by IntDiv1-2 (pc_test.cpp:678-698); not pinned by any reference test beyond that.
+LPC_HD int tr_div1(int k, int a, int b) {   // b != 0
+  if(k == T_EDIV) return tr_ediv1(a, b);
+  if(b_inf(a)) return b > 0 ? a : b_neg(a);
+  if(b_inf(b)) return 0;
+  long long q = (long long)a / b;
+  const long long r = (long long)a % b;
+  if(k == T_FDIV && r != 0 && ((r < 0) != (b < 0))) --q;
+  if(k == T_CDIV && r != 0 && ((r < 0) == (b < 0))) ++q;
+  return b_clamp(q);
+}
+LPC_HD Itv tr_div(int k, const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return itv_bot();
+  Itv r = itv_bot();
+  if(b.lb < 0) {
+    const int bu = min(b.ub, -1);
+    r = fjoin(r, tr_hull4(tr_div1(k, a.lb, b.lb), tr_div1(k, a.lb, bu), tr_div1(k, a.ub, b.lb), tr_div1(k, a.ub, bu)));
+  }
+  if(b.ub > 0) {
+    const int bl = max(b.lb, 1);
+    r = fjoin(r, tr_hull4(tr_div1(k, a.lb, bl), tr_div1(k, a.lb, b.ub), tr_div1(k, a.ub, bl), tr_div1(k, a.ub, b.ub)));
+  }
+  return r;
+}
+// GroupDiv::left_residual (terms.hpp:272-277): x in u * y, its upper bound joined with y.ub - 1
+LPC_HD Itv tr_div_left(const Itv& u, const Itv& b) {
+  Itv r = tr_mul(u, b);
+  if(!r.is_bot()) r.ub = max(r.ub, b_sub(b.ub, 1));
+  return r;
+}
+// GroupDiv::right_residual (terms.hpp:279-294) on r = the divisor's current value: 0 leaves its ends, then
+// y in x / u unless x holds 0 or u = {0}
+LPC_HD Itv tr_div_right(int k, const Itv& u, const Itv& b, Itv r) {
+  if(r.lb == 0) r.meet(Itv(1, LPC_INF));
+  if(r.ub == 0) r.meet(Itv(LPC_MINF, -1));
+  if(!contains0(b) && !(u.lb == 0 && u.ub == 0)) r.meet(tr_div(k, b, u));
+  return r;
+}
 LPC_HD bool tr_same(const Itv& a, const Itv& b) { return (a.is_bot() && b.is_bot()) || (a.lb == b.lb && a.ub == b.ub); }
 
 // G::project (terms.hpp:182, 213, 235, 306)
@@ -188,16 +232,19 @@ template <int D> struct TreeTerm {
       case T_VAR: return a.load(*p++);
       case T_NEG: return tr_neg(TreeTerm<D - 1>::project(a, p));
       case T_ABS: return tr_abs(TreeTerm<D - 1>::project(a, p));
-      case T_NARY_ADD: {
+      case T_NARY_ADD: case T_NARY_MUL: {
         const int n = *p++;
         Itv accu = TreeTerm<D - 1>::project(a, p);
-        for(int i = 1; i < n; ++i) accu = tr_add(accu, TreeTerm<D - 1>::project(a, p));
+        for(int i = 1; i < n; ++i) {
+          const Itv ti = TreeTerm<D - 1>::project(a, p);
+          accu = k == T_NARY_ADD ? tr_add(accu, ti) : tr_mul(accu, ti);
+        }
         return accu;
       }
       default: {
         const Itv x = TreeTerm<D - 1>::project(a, p);
         const Itv y = TreeTerm<D - 1>::project(a, p);
-        return tr_group(k, x, y);
+        return tok_is_div(k) ? tr_div(k, x, y) : tr_group(k, x, y);
       }
     }
   }
@@ -209,16 +256,26 @@ template <int D> struct TreeTerm {
       case T_VAR: return a.embed(*p++, u);
       case T_NEG: return TreeTerm<D - 1>::embed(a, p, tr_neg(u));
       case T_ABS: return TreeTerm<D - 1>::embed(a, p, fjoin(u, tr_neg(u)));
-      case T_NARY_ADD: {
+      case T_NARY_ADD: case T_NARY_MUL: {
         const int n = *p++;
         const int* q = p - 2;
         const Itv all = project(a, q);   // once, before any operand moves (terms.hpp:486)
         int f = 0;
+        const bool absorbed = k == T_NARY_MUL && all.lb == 0 && all.ub == 0;   // GroupMul::is_absorbing (:239-241, 487)
         for(int i = 0; i < n; ++i) {
+          if(absorbed) { p = tree_skip_term(p); continue; }
           const int* s = p;
           const Itv ti = TreeTerm<D - 1>::project(a, s);
-          const Itv others(b_add(all.lb, b_neg(ti.lb)), b_add(all.ub, b_neg(ti.ub)));   // additive_inverse, :190-194
-          f |= TreeTerm<D - 1>::embed(a, p, tr_sub(u, others));
+          Itv res;
+          if(k == T_NARY_ADD) {
+            const Itv others(b_add(all.lb, b_neg(ti.lb)), b_add(all.ub, b_neg(ti.ub)));   // additive_inverse, :190-194
+            res = tr_sub(u, others);
+          }
+          else {
+            const Itv others = tr_ediv(all, ti);                                            // rev_op, :244-246
+            res = (contains0(u) && contains0(others)) ? itv_top() : tr_ediv(u, others);     // left_residual, :249-253
+          }
+          f |= TreeTerm<D - 1>::embed(a, p, res);
         }
         return f;
       }
@@ -226,18 +283,22 @@ template <int D> struct TreeTerm {
         const int* px = p;
         const int* py = tree_skip_term(px);
         int f = 0;
+        const bool dv = tok_is_div(k);
         if(*px != T_CONST) {
           const int* s = py;
           const Itv yt = TreeTerm<D - 1>::project(a, s);
           s = px;
-          f |= TreeTerm<D - 1>::embed(a, s, tr_residual(k, false, u, yt));
+          f |= TreeTerm<D - 1>::embed(a, s, dv ? tr_div_left(u, yt) : tr_residual(k, false, u, yt));
         }
         p = tree_skip_term(py);
         if(*py != T_CONST) {
           const int* s = px;
           const Itv xt = TreeTerm<D - 1>::project(a, s);   // re-read: x may just have moved
+          Itv res;
+          if(dv) { s = py; res = tr_div_right(k, u, xt, TreeTerm<D - 1>::project(a, s)); }   // the divisor's own value (:389-392)
+          else res = tr_residual(k, true, u, xt);
           s = py;
-          f |= TreeTerm<D - 1>::embed(a, s, tr_residual(k, true, u, xt));
+          f |= TreeTerm<D - 1>::embed(a, s, res);
         }
         return f;
       }
@@ -307,6 +368,28 @@ template <class Acc> LPC_NI int tree_cmp_deduce(Acc& a, int k, bool negated, con
   return f;
 }
 
+// AbstractElement (formula.hpp:14-77): ask / nask = the store's ask of the element / of its negation, deduce /
+// contradeduce = the store's deduce of them. Over an interval store `v != c` has an ask (c outside the domain) but no
+// tell (AbstractElement3-4, pc_test.cpp:738-764).
+LPC_HD void tree_ae_norm(int& op, int& c, bool negated) {
+  if(!negated) return;
+  if(op == AE_LEQ) { op = AE_GEQ; c = b_add(c, 1); }
+  else if(op == AE_GEQ) { op = AE_LEQ; c = b_sub(c, 1); }
+  else op = op == AE_EQ ? AE_NEQ : AE_EQ;
+}
+LPC_HD Itv tree_ae_itv(int op, int c) { return op == AE_LEQ ? Itv(LPC_MINF, c) : op == AE_GEQ ? Itv(c, LPC_INF) : Itv(c, c); }
+template <class Acc> LPC_HD bool tree_ae_ask(const Acc& a, int op, int v, int c, bool negated) {
+  tree_ae_norm(op, c, negated);
+  const Itv d = a.load(v);
+  if(op == AE_NEQ) return d.is_bot() || c < d.lb || c > d.ub;
+  const Itv want = tree_ae_itv(op, c);
+  return d.is_bot() || (d.lb >= want.lb && d.ub <= want.ub);
+}
+template <class Acc> LPC_HD int tree_ae_tell(Acc& a, int op, int v, int c, bool negated) {
+  tree_ae_norm(op, c, negated);
+  return op == AE_NEQ ? 0 : a.embed(v, tree_ae_itv(op, c));
+}
+
 template <int D> struct TreeForm {
   // ask (negated = false) / nask (negated = true); p is left after the formula
   template <class Acc> static LPC_NI bool ask(const Acc& a, const int*& p, bool negated) {
@@ -315,6 +398,7 @@ template <int D> struct TreeForm {
       const bool neg = (k == F_NVARLIT) != negated;
       return lit_ask(neg, a.load(*p++));
     }
+    if(k == F_AE) { const int op = p[0], v = p[1], c = p[2]; p += 3; return tree_ae_ask(a, op, v, c, negated); }
     if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_ask(a, k, negated, p);
     const int* pf = p;
     const int* pg = tree_skip_formula(pf);
@@ -351,6 +435,7 @@ template <int D> struct TreeForm {
       const bool neg = (k == F_NVARLIT) != negated;
       return a.embed(*p++, neg ? Itv(0, 0) : Itv(1, 1));
     }
+    if(k == F_AE) { const int op = p[0], v = p[1], c = p[2]; p += 3; return tree_ae_tell(a, op, v, c, negated); }
     if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_deduce(a, k, negated, p);
     const int* pf = p;
     const int* pg = tree_skip_formula(pf);

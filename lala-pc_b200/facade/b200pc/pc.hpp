@@ -15,9 +15,9 @@
 //
 // The store type selects the universe: PC<VStore> runs over Interval<ZLB> cells, PC<BitVStore> over NBitset<64> cells.
 // Formula shapes with a flat device kind (include/lpc_pc.h) are flattened; every other shape over the node types PC
-// has a device rule for (and / or / equiv / imply / xor nests, comparisons between arbitrary terms, + - * min max neg
-// abs, n-ary sums) keeps its tree as an LPC_PC_TREE propagator and is walked on the device (csrc/pc_tree.cuh). What is
-// left - divisions, n-ary products, `in` over non-bitset stores, trees deeper than the device walks - fails interpretation
+// has a device rule for (and / or / equiv / imply / xor nests, comparisons between arbitrary terms, + - * / min max neg
+// abs, n-ary sums and products) keeps its tree as an LPC_PC_TREE propagator and is walked on the device (csrc/pc_tree.cuh). What is
+// left - `in` over non-bitset stores, store-typed sub-formulas, trees deeper than the device walks - fails interpretation
 // with the reference's message ("The shape of this formula is not supported."). No CPU implementation lives behind
 // this header.
 #pragma once
@@ -364,7 +364,7 @@ private:
   // ---- the general case: the tree itself as an LPC_PC_TREE stream (include/lpc_pc.h) -------------------------------
   // Token numbers of the stream; heights are checked against the device interpreter's limits (csrc/pc_tree.cuh).
   enum { TK_CONST = 1, TK_VAR = 2, TK_NEG = 3, TK_ABS = 4, TK_ADD = 5, TK_SUB = 6, TK_MUL = 7, TK_NARY_ADD = 8, TK_MIN = 9,
-         TK_MAX = 10, FK_LIT = 20, FK_NLIT = 21, FK_LEQ = 22, FK_GT = 23, FK_EQ = 24, FK_NEQ = 25, FK_AND = 26, FK_OR = 27,
+         TK_MAX = 10, TK_TDIV = 11, TK_FDIV = 12, TK_CDIV = 13, TK_EDIV = 14, TK_NARY_MUL = 15, FK_LIT = 20, FK_NLIT = 21, FK_LEQ = 22, FK_GT = 23, FK_EQ = 24, FK_NEQ = 25, FK_AND = 26, FK_OR = 27,
          FK_EQUIV = 28, FK_IMPLY = 29, FK_XOR = 30, TREE_TERM_DEPTH = 5, TREE_FORM_DEPTH = 4 };
   // interpret_term (pc.hpp:217-296): returns the height (0 = not a term), `len` = Term::length()
   static int tree_term(const TF& t, const VarEnv& env, std::vector<int>& w, int& len) {
@@ -380,7 +380,9 @@ private:
     }
     int tok = 0;
     switch(t.sig()) { case ADD: tok = TK_ADD; break; case SUB: tok = TK_SUB; break; case MUL: tok = TK_MUL; break;
-                      case MIN: tok = TK_MIN; break; case MAX: tok = TK_MAX; break; default: return 0; }
+                      case MIN: tok = TK_MIN; break; case MAX: tok = TK_MAX; break; case TDIV: tok = TK_TDIV; break;
+                      case FDIV: tok = TK_FDIV; break; case CDIV: tok = TK_CDIV; break; case EDIV: tok = TK_EDIV; break;
+                      default: return 0; }
     if(t.args.size() == 2) {
       w.push_back(tok);
       int l0 = 0, l1 = 0;
@@ -388,8 +390,8 @@ private:
       len = 1 + l0 + l1;
       return (h0 && h1) ? 1 + std::max(h0, h1) : 0;
     }
-    if(tok == TK_ADD && t.args.size() > 2) {   // Nary<Add> (pc.hpp:253)
-      w.push_back(TK_NARY_ADD); w.push_back((int)t.args.size());
+    if((tok == TK_ADD || tok == TK_MUL) && t.args.size() > 2) {   // Nary<Add> / Nary<Mul> (pc.hpp:253-254)
+      w.push_back(tok == TK_ADD ? TK_NARY_ADD : TK_NARY_MUL); w.push_back((int)t.args.size());
       int h = 0; len = 1;
       for(auto& a : t.args) { int l = 0; const int ha = tree_term(a, env, w, l); if(!ha) return 0; h = std::max(h, ha); len += l; }
       return 1 + h;

@@ -278,7 +278,7 @@ static void UnsupportedShapesAreRefused() {
   for(int i = 0; i < 6; ++i) deep = bin(deep, ADD, V("y"));
   EXPECT_FALSE(ipc.interpret_tell(bin(deep, LEQ, K(3)), m.env, tell, &why));
   EXPECT_EQ(why, std::string("The shape of this formula is not supported."));
-  EXPECT_FALSE(ipc.interpret_tell(bin(bin(V("x"), TDIV, V("y")), LEQ, K(3)), m.env, tell, &why));      // GroupDiv: unpinned upstream
+  EXPECT_FALSE(ipc.interpret_tell(TF::in(V("x"), {1, 3}), m.env, tell, &why));                         // `in` needs a bitset store
   EXPECT_EQ((int)tell.props.size(), 3);
   Model<BitPC> mb;
   mb.var("x").var("y");
@@ -345,6 +345,14 @@ static void TreePropagators() {
     deduce_and_test(ipc, 1, {B, B, B}, false);
     tell_more(ipc, m, bin(V("z"), EQ, K(1)));
     deduce_and_test(ipc, 1, {B, B, Itv(1, 1)}, {Itv(1, 1), Itv(1, 1), Itv(1, 1)}, true);
+    {   // IntDiv1, pc_test.cpp:678-688: x / y = z
+      Model<IPC> md;
+      md.var("x", B).var("y", B).var("z", B).c(bin(bin(V("x"), TDIV, V("y")), EQ, V("z")));
+      IPC ipd = create_and_interpret_and_tell(md);
+      deduce_and_test(ipd, 1, {B, B, B}, {B, Itv(1, 1), B}, false);
+      tell_more(ipd, md, bin(V("x"), EQ, K(1)));
+      deduce_and_test(ipd, 1, {Itv(1, 1), Itv(1, 1), B}, {Itv(1, 1), Itv(1, 1), Itv(1, 1)}, true);
+    }
     Model<IPC> m5;
     m5.var("x", Itv(1, 2)).var("y", B).var("z", Itv(0, 0)).c(bin(bin(V("x"), MUL, V("y")), EQ, V("z")));
     IPC ipc5 = create_and_interpret_and_tell(m5);

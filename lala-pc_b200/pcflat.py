@@ -9,8 +9,9 @@ Formulas are nested tuples (a plain Python stand-in for lala-core's TFormula):
             ('equiv', ('lit', b), ('le', term, ('const', k)))
             ('eq', ('var', x), ('var', y))  ('ne', ('var', x), ('var', y) | ('const', k))
             ('or', lit, ('or', lit, ...)) with lit = ('lit', v) | ('nlit', v)   ('eq', ('abs', ('var', x)), ('var', y))
-Any other formula over these node types - and ('min' | 'max' | 'mul', t1, t2) terms, ('and' | 'or' | 'equiv' | 'imply' |
-'xor', f, g) connectives, comparisons between two non-constant terms - keeps its tree: `flatten` encodes it as an
+Any other formula over these node types - and ('min' | 'max' | 'mul' | 'tdiv' | 'fdiv' | 'cdiv' | 'ediv', t1, t2) terms,
+('prod', t1, ..., tn) products, ('and' | 'or' | 'equiv' | 'imply' | 'xor', f, g) connectives, ('ae', op, var, k) store
+elements, comparisons between two non-constant terms - keeps its tree: `flatten` encodes it as an
 LPC_PC_TREE propagator (the prefix stream of include/lpc_pc.h in the propagator's term slots), which the device walks
 node by node (csrc/pc_tree.cuh). `flatten(..., tree=False)` raises `Unsupported` for those instead (the reference's
 "shape of this formula is not supported" interpretation error); trees deeper than the device limits always do.
@@ -21,8 +22,11 @@ PC_LIN_LE, PC_REIF_LIN_LE, PC_EQ, PC_NEQ, PC_CLAUSE, PC_ABS_EQ = 1, 2, 3, 4, 5, 
 PC_LIN_GE, PC_LIN_GT, PC_LIN_EQ, PC_LIN_EQ_VAR, PC_TREE = 7, 8, 9, 10, 11
 TREE_TERM_DEPTH, TREE_FORM_DEPTH = 5, 4   # csrc/pc_tree.cuh
 
-_T = {"const": 1, "var": 2, "neg": 3, "abs": 4, "add": 5, "sub": 6, "mul": 7, "sum": 8, "min": 9, "max": 10}
-_F = {"lit": 20, "nlit": 21, "le": 22, "gt": 23, "eq": 24, "ne": 25, "and": 26, "or": 27, "equiv": 28, "imply": 29, "xor": 30}
+_T = {"const": 1, "var": 2, "neg": 3, "abs": 4, "add": 5, "sub": 6, "mul": 7, "sum": 8, "min": 9, "max": 10,
+      "tdiv": 11, "fdiv": 12, "cdiv": 13, "ediv": 14, "prod": 15}
+_F = {"lit": 20, "nlit": 21, "le": 22, "gt": 23, "eq": 24, "ne": 25, "and": 26, "or": 27, "equiv": 28, "imply": 29, "xor": 30,
+      "ae": 31}
+_AE = {"le": 0, "ge": 1, "eq": 2, "ne": 3}
 
 
 class Unsupported(ValueError):
@@ -120,9 +124,9 @@ def _encode_term(t, out):
     if op in ("neg", "abs"):
         out.append(_T[op])
         return 1 + _encode_term(t[1], out)
-    if op == "sum":
+    if op in ("sum", "prod"):
         if len(t) - 1 < 2:
-            raise Unsupported("an n-ary sum has at least two operands")
+            raise Unsupported("an n-ary sum or product has at least two operands")
         out += [_T[op], len(t) - 1]
         return 1 + max(_encode_term(s, out) for s in t[1:])
     out.append(_T[op])
@@ -136,6 +140,9 @@ def _encode_formula(f, out):
         raise Unsupported(f"formula {op} has no device rule")
     if op in ("lit", "nlit"):
         out += [_F[op], int(f[1])]
+        return 1
+    if op == "ae":   # ('ae', 'le' | 'ge' | 'eq' | 'ne', var, k): AbstractElement over the store (formula.hpp:14-77)
+        out += [_F[op], _AE[f[1]], int(f[2]), int(f[3])]
         return 1
     out.append(_F[op])
     if op in ("le", "gt", "eq", "ne"):

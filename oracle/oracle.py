@@ -188,6 +188,8 @@ def pir_exhaustive(op, minval, maxval, complete, threads=0, want_fixpoints=False
 # ---- PC (oracle/pc_oracle.cpp) -------------------------------------------------------------------------------------
 # prefix token codes of the formula stream (enum Tok in pc_oracle.cpp)
 T_CONST, T_VAR, T_NEG, T_ABS, T_ADD, T_SUB, T_MUL, T_NARY_ADD, T_MIN, T_MAX = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+T_TDIV, T_FDIV, T_CDIV, T_EDIV, T_NARY_MUL, F_AE = 11, 12, 13, 14, 15, 31
+AE_OPS = {"le": 0, "ge": 1, "eq": 2, "ne": 3}
 F_VARLIT, F_NVARLIT, F_LEQ, F_GT, F_EQ, F_NEQ, F_AND, F_OR, F_EQUIV, F_IMPLY, F_XOR = 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30
 
 _pc_bound = False
@@ -267,7 +269,8 @@ def flatten(tree):
     ('sum', t1, ..., tn); formulas ('lit', v), ('nlit', v), ('le'|'gt'|'eq'|'ne', a, b), ('and'|'or'|'equiv', f, g)."""
     op = tree[0]
     unary = {"neg": T_NEG, "abs": T_ABS}
-    binary = {"add": T_ADD, "sub": T_SUB, "mul": T_MUL, "min": T_MIN, "max": T_MAX, "le": F_LEQ, "gt": F_GT, "eq": F_EQ,
+    binary = {"add": T_ADD, "sub": T_SUB, "mul": T_MUL, "min": T_MIN, "max": T_MAX, "tdiv": T_TDIV, "fdiv": T_FDIV,
+              "cdiv": T_CDIV, "ediv": T_EDIV, "le": F_LEQ, "gt": F_GT, "eq": F_EQ,
               "ne": F_NEQ, "and": F_AND, "or": F_OR, "equiv": F_EQUIV, "imply": F_IMPLY, "xor": F_XOR}
     if op == "var":
         return [T_VAR, int(tree[1])]
@@ -281,8 +284,10 @@ def flatten(tree):
         return [unary[op]] + flatten(tree[1])
     if op in binary:
         return [binary[op]] + flatten(tree[1]) + flatten(tree[2])
-    if op == "sum":
-        out = [T_NARY_ADD, len(tree) - 1]
+    if op == "ae":   # ('ae', 'le' | 'ge' | 'eq' | 'ne', var, k): a store-level element (AbstractElement)
+        return [F_AE, AE_OPS[tree[1]], int(tree[2]), int(tree[3])]
+    if op in ("sum", "prod"):
+        out = [T_NARY_ADD if op == "sum" else T_NARY_MUL, len(tree) - 1]
         for t in tree[1:]:
             out += flatten(t)
         return out

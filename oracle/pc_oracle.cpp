@@ -12,6 +12,8 @@
 //   Constant, Variable, Unary<Neg|Abs>                include/lala/terms.hpp:18-175
 //   Binary<GroupAdd|GroupSub|GroupMul<EDIV>>          include/lala/terms.hpp:177-262, 333-434
 //   Binary<GroupMinMax<MIN|MAX>>                      include/lala/terms.hpp:301-331
+//   Binary<GroupDiv<TDIV|FDIV|CDIV|EDIV>>, Nary<Mul>  include/lala/terms.hpp:264-299, 436-526
+//   AbstractElement over the store                    include/lala/formula.hpp:14-77
 //   Nary<Add>                                         include/lala/terms.hpp:436-526
 // The leaf arithmetic, Interval::project(Sig, ...), additive_inverse, fjoin, LB::prev / UB::prev, lives in
 // lala-core v1.2.8 (un-vendored, CMakeLists.txt:33-37) and is restated from its published behaviour:
@@ -45,6 +47,11 @@
 namespace {
 
 typedef int32_t v_t;
+enum Tok { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8, T_MIN = 9, T_MAX = 10,
+           T_TDIV = 11, T_FDIV = 12, T_CDIV = 13, T_EDIV = 14, T_NARY_MUL = 15,
+           F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27, F_EQUIV = 28,
+           F_IMPLY = 29, F_XOR = 30, F_AE = 31 };
+enum AeOp { AE_LEQ = 0, AE_GEQ = 1, AE_EQ = 2, AE_NEQ = 3 };   // F_AE op var k: a store-level element `var op k`
 const v_t INF = INT32_MAX, MINF = INT32_MIN;
 
 struct Itv {
@@ -118,6 +125,40 @@ inline Itv p_ediv(const Itv& a, const Itv& b) {
   return r;
 }
 
+// project(TDIV | FDIV | CDIV | EDIV): the same shape with the rounding of the operator (0 cut out of the divisor).
+// Pinned by IntDiv1-2 (pc_test.cpp:678-698) on 0/1 domains only; beyond that UNPINNED.
+inline v_t bdivop(int kind, v_t a, v_t b) {   // b != 0
+  if(kind == T_EDIV) return bediv(a, b);
+  if(inf(a)) return (b > 0) ? a : bneg(a);
+  if(inf(b)) return 0;
+  long long q = (long long)a / b, r = (long long)a % b;
+  if(kind == T_FDIV && r != 0 && ((r < 0) != (b < 0))) --q;
+  if(kind == T_CDIV && r != 0 && ((r < 0) == (b < 0))) ++q;
+  return clamp64(q);
+}
+inline Itv p_div(int kind, const Itv& a, const Itv& b) {
+  if(a.is_bot() || b.is_bot()) return Itv(INF, MINF);
+  Itv r(INF, MINF);
+  if(b.lb < 0) { v_t bu = b.ub < -1 ? b.ub : -1; r = fjoin(r, hull4(bdivop(kind, a.lb, b.lb), bdivop(kind, a.lb, bu), bdivop(kind, a.ub, b.lb), bdivop(kind, a.ub, bu))); }
+  if(b.ub > 0) { v_t bl = b.lb > 1 ? b.lb : 1; r = fjoin(r, hull4(bdivop(kind, a.lb, bl), bdivop(kind, a.lb, b.ub), bdivop(kind, a.ub, bl), bdivop(kind, a.ub, b.ub))); }
+  return r;
+}
+// GroupDiv residuals (terms.hpp:272-296). left: x in u * y, upper bound joined with y.ub - 1 (join_ub(UB::prev(b.ub())));
+// right: 0 leaves the ends of y, then y in x / u unless x holds 0 or u = {0}.
+inline Itv div_left_residual(const Itv& u, const Itv& b) {
+  Itv r = p_mul(u, b);
+  if(r.is_bot()) return r;
+  v_t pb = bsub(b.ub, 1);
+  if(pb > r.ub) r.ub = pb;
+  return r;
+}
+inline Itv div_right_residual(int kind, const Itv& u, const Itv& b, Itv r) {
+  if(r.lb == 0) r.meet(Itv(1, INF));
+  if(r.ub == 0) r.meet(Itv(MINF, -1));
+  if(!b.contains0() && !(u.lb == 0 && u.ub == 0)) r.meet(p_div(kind, b, u));
+  return r;
+}
+
 // project(MIN / MAX): componentwise on the bounds (pinned by MinConstraint1-3 / MaxConstraint1-3, pc_test.cpp:479-557)
 inline Itv p_min(const Itv& a, const Itv& b) {
   if(a.is_bot() || b.is_bot()) return Itv(INF, MINF);
@@ -163,6 +204,9 @@ inline NBit p_min(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot
 inline NBit p_max(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_max(a.itv(), b.itv())); }
 inline NBit only_lb(const NBit& a) { return from_itv(Itv(a.lo(), INF)); }   // unpinned on bitsets
 inline NBit only_ub(const NBit& a) { return from_itv(Itv(MINF, a.hi())); }
+inline NBit p_div(int kind, const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_div(kind, a.itv(), b.itv())); }
+inline NBit div_left_residual(const NBit& u, const NBit& b) { return (u.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(div_left_residual(u.itv(), b.itv())); }
+inline NBit div_right_residual(int kind, const NBit& u, const NBit& b, NBit r) { return r.is_bot() ? r : from_itv(div_right_residual(kind, u.itv(), b.itv(), r.itv())); }
 inline NBit p_ediv(const NBit& a, const NBit& b) { return (a.is_bot() || b.is_bot()) ? NBit::raw(0) : from_itv(p_ediv(a.itv(), b.itv())); }
 
 template <class U>
@@ -178,9 +222,7 @@ struct Store {
 };
 static_assert(sizeof(Itv) == 8 && sizeof(NBit) == 8, "8-byte cells");
 
-enum Tok { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8, T_MIN = 9, T_MAX = 10,
-           F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27, F_EQUIV = 28,
-           F_IMPLY = 29, F_XOR = 30 };
+
 
 template <class U>
 struct Term {
@@ -198,6 +240,17 @@ struct Term {
         U x, y; sub[0]->project(a, x); sub[1]->project(a, y);
         r.meet(kind == T_ADD ? p_add(x, y) : kind == T_SUB ? p_sub(x, y) : kind == T_MUL ? p_mul(x, y)
                : kind == T_MIN ? p_min(x, y) : p_max(x, y));
+        break;
+      }
+      case T_TDIV: case T_FDIV: case T_CDIV: case T_EDIV: {           // GroupDiv::project, terms.hpp:268-270
+        U x, y; sub[0]->project(a, x); sub[1]->project(a, y);
+        r.meet(p_div(kind, x, y));
+        break;
+      }
+      case T_NARY_MUL: {                                             // Nary<Mul>, terms.hpp:465-478
+        U accu; sub[0]->project(a, accu);
+        for(size_t i = 1; i < sub.size(); ++i) { U t; sub[i]->project(a, t); accu = p_mul(accu, t); }
+        r.meet(accu);
         break;
       }
       case T_NARY_ADD: {                                             // terms.hpp:465-478
@@ -226,6 +279,33 @@ struct Term {
           U xt, res; sub[0]->project(a, xt);
           right_residual(u, xt, res);
           ch |= sub[1]->embed(a, res);
+        }
+        return ch;
+      }
+      case T_TDIV: case T_FDIV: case T_CDIV: case T_EDIV: {           // Binary::embed with a division group, terms.hpp:376-397
+        bool ch = false;
+        if(!sub[0]->is_const()) {
+          U yt; sub[1]->project(a, yt);
+          U res; res.meet(div_left_residual(u, yt));
+          ch |= sub[0]->embed(a, res);
+        }
+        if(!sub[1]->is_const()) {
+          U xt; sub[0]->project(a, xt);
+          U cur; sub[1]->project(a, cur);                            // "we read it to potentially remove 0" (:389-392)
+          ch |= sub[1]->embed(a, div_right_residual(kind, u, xt, cur));
+        }
+        return ch;
+      }
+      case T_NARY_MUL: {                                             // Nary<Mul>::embed, terms.hpp:480-499
+        U all; project(a, all);
+        bool ch = false;
+        if(all.same(U(0, 0))) return false;                          // GroupMul::is_absorbing (:239-241)
+        for(size_t i = 0; i < sub.size(); ++i) {
+          U tmp; sub[i]->project(a, tmp);
+          U tmp2; tmp2.meet(p_ediv(all, tmp));                       // rev_op (:244-246)
+          U res;
+          if(!(u.contains0() && tmp2.contains0())) res.meet(p_ediv(u, tmp2));   // left_residual (:249-253)
+          ch |= sub[i]->embed(a, res);
         }
         return ch;
       }
@@ -263,6 +343,7 @@ struct Term {
 template <class U>
 struct Formula {
   int kind = 0; int var = -1;
+  int ae_op = 0; v_t ae_k = 0;     // F_AE
   std::unique_ptr<Term<U>> l, r;
   std::unique_ptr<Formula> f, g;
 
@@ -289,6 +370,17 @@ struct Formula {
         U x, y; l->project(a, x); r->project(a, y);
         if(neg) { U m = x; m.meet(y); return m.is_bot(); }
         return x.same(y) && x.lo() == x.hi();
+      }
+      case F_AE: {   // AbstractElement::ask / nask = the store's ask of the element / of its negation (formula.hpp:43-49)
+        int op = ae_op; v_t k = ae_k;
+        if(negated) { if(op == AE_LEQ) { op = AE_GEQ; k = badd(k, 1); } else if(op == AE_GEQ) { op = AE_LEQ; k = bsub(k, 1); } else op = op == AE_EQ ? AE_NEQ : AE_EQ; }
+        const U& d = a.get(var);
+        switch(op) {
+          case AE_LEQ: return d.sub_of(MINF, k);
+          case AE_GEQ: return d.sub_of(k, INF);
+          case AE_EQ: return d.sub_of(k, k);
+          default: { U m = d; m.meet(U(k, k)); return m.is_bot(); }
+        }
       }
       case F_AND: return negated ? (f->nask(a) || g->nask(a)) : (f->ask(a) && g->ask(a));       // formula.hpp:268-274
       case F_OR: return negated ? (f->nask(a) && g->nask(a)) : (f->ask(a) || g->ask(a));        // formula.hpp:338-344
@@ -353,6 +445,16 @@ struct Formula {
         if(!l->is_const()) { r->project(a, y); ch |= l->embed(a, y); }
         return ch;
       }
+      case F_AE: {   // AbstractElement::deduce / contradeduce = the store's deduce of the element / its negation
+        int op = ae_op; v_t k = ae_k;   // (formula.hpp:51-57); `!=` has no interval (AbstractElement3-4, pc_test.cpp:738-764)
+        if(negated) { if(op == AE_LEQ) { op = AE_GEQ; k = badd(k, 1); } else if(op == AE_GEQ) { op = AE_LEQ; k = bsub(k, 1); } else op = op == AE_EQ ? AE_NEQ : AE_EQ; }
+        switch(op) {
+          case AE_LEQ: return a.embed(var, U(MINF, k));
+          case AE_GEQ: return a.embed(var, U(k, INF));
+          case AE_EQ: return a.embed(var, U(k, k));
+          default: return U::complemented ? a.embed(var, U(k, k).complement()) : false;
+        }
+      }
       case F_AND:                                                    // formula.hpp:276-286
         if(!negated) { bool c = f->deduce(a); c |= g->deduce(a); return c; }
         if(f->ask(a)) return g->contradeduce(a);
@@ -399,8 +501,9 @@ std::unique_ptr<Term<U>> parse_term(const int32_t*& p) {
     case T_CONST: t->k = *p++; break;
     case T_VAR: t->var = *p++; break;
     case T_NEG: case T_ABS: t->sub.push_back(parse_term<U>(p)); break;
-    case T_ADD: case T_SUB: case T_MUL: case T_MIN: case T_MAX: t->sub.push_back(parse_term<U>(p)); t->sub.push_back(parse_term<U>(p)); break;
-    case T_NARY_ADD: { int n = *p++; for(int i = 0; i < n; ++i) t->sub.push_back(parse_term<U>(p)); break; }
+    case T_ADD: case T_SUB: case T_MUL: case T_MIN: case T_MAX: case T_TDIV: case T_FDIV: case T_CDIV: case T_EDIV:
+      t->sub.push_back(parse_term<U>(p)); t->sub.push_back(parse_term<U>(p)); break;
+    case T_NARY_ADD: case T_NARY_MUL: { int n = *p++; for(int i = 0; i < n; ++i) t->sub.push_back(parse_term<U>(p)); break; }
   }
   return t;
 }
@@ -410,6 +513,7 @@ std::unique_ptr<Formula<U>> parse_formula(const int32_t*& p) {
   f->kind = *p++;
   switch(f->kind) {
     case F_VARLIT: case F_NVARLIT: f->var = *p++; break;
+    case F_AE: f->ae_op = *p++; f->var = *p++; f->ae_k = *p++; break;
     case F_LEQ: case F_GT: case F_EQ: case F_NEQ: f->l = parse_term<U>(p); f->r = parse_term<U>(p); break;
     default: f->f = parse_formula<U>(p); f->g = parse_formula<U>(p); break;
   }

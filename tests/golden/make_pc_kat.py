@@ -145,6 +145,22 @@ kat("IntTimes3", "pc_test.cpp:638-646", [[0, 0], B, B], [tm], [[0, 0], B, [0, 0]
 kat("IntTimes4", "pc_test.cpp:648-656", [B, [0, 0], B], [tm], [B, [0, 0], [0, 0]], ua=True, changed=True)
 kat("IntTimes5", "pc_test.cpp:658-666", [[1, 2], B, [0, 0]], [tm], [[1, 2], [0, 0], [0, 0]], ua=True, changed=True)
 kat("IntTimes6", "pc_test.cpp:668-676", [B, [1, 2], [0, 0]], [tm], [[0, 0], [1, 2], [0, 0]], ua=True, changed=True)
+# int_div(x, y, z): Equality(Binary<GroupDiv<TDIV>>(x, y), z) (pc.hpp:237, terms.hpp:264-299)
+dv = ["eq", ["tdiv", v(0), v(1)], v(2)]
+kat("IntDiv1.a", "pc_test.cpp:678-685", [B, B, B], [dv], [B, [1, 1], B], ua=False, changed=True)
+kat("IntDiv1.b", "pc_test.cpp:686-687", [[1, 1], [1, 1], B], [dv], [[1, 1], [1, 1], [1, 1]], ua=True, changed=True)
+dv2 = ["eq", ["tdiv", v(0), c(2)], c(0)]
+kat("IntDiv2.a", "pc_test.cpp:690-695", [B], [dv2], [B], ua=True, changed=False)
+kat("IntDiv2.b", "pc_test.cpp:696-697", [[1, 1]], [dv2], [[1, 1]], ua=True, changed=False)
+# nbool_equiv with both sides typed into the store: Biconditional of two AbstractElements (formula.hpp:14-77)
+ae1 = ["equiv", ["ae", "ge", 0, 5], ["ae", "le", 1, 5]]
+kat("AbstractElement1.a", "pc_test.cpp:714-720", [D10, D10], [ae1], [D10, D10], ua=False, changed=False)
+kat("AbstractElement1.b", "pc_test.cpp:721-722", [[5, 5], D10], [ae1], [[5, 5], [0, 5]], ua=True, changed=True)
+kat("AbstractElement2.b", "pc_test.cpp:733-734", [[4, 4], D10], [ae1], [[4, 4], [6, 10]], ua=True, changed=True)
+ae3 = ["equiv", ["ae", "eq", 0, 5], ["ae", "eq", 1, 5]]
+kat("AbstractElement3.a", "pc_test.cpp:738-744", [D10, D10], [ae3], [D10, D10], ua=False, changed=False)
+kat("AbstractElement3.b", "pc_test.cpp:746-747", [D10, [6, 6]], [ae3], [D10, [6, 6]], ua=False, changed=False)
+kat("AbstractElement4.b", "pc_test.cpp:760-761", [D10, [4, 4]], [ae3], [D10, [4, 4]], ua=False, changed=False)
 
 TERM_KATS = [
     dict(name="TermTest.AddTermBinary", source="pc_test.cpp:31-47", store=[D10, D10], term=["add", v(0), v(1)],

@@ -74,7 +74,7 @@ def test_golden_vectors(L, O):
             continue
         after = np.array(k["after"], dtype=np.int32)
         assert np.array_equal(got[:len(after)], after), (k["name"], got.tolist())
-    assert ran == len(kats) >= 83, ran   # flat kinds + tree propagators: every reference golden runs on the device
+    assert ran == len(kats) >= 93, ran   # flat kinds + tree propagators: every reference golden runs on the device
 
 
 def test_deduce_one_step_by_step(L, O):
@@ -183,17 +183,20 @@ def random_tree_pc(rng, nvars, n_forms=None):
         if depth <= 1 or r < 0.35:
             return leaf()
         if r < 0.85:
-            op = str(rng.choice(["add", "sub", "mul", "min", "max", "add"]))
+            op = str(rng.choice(["add", "sub", "mul", "min", "max", "add", "tdiv", "fdiv", "cdiv", "ediv"]))
             return (op, term(depth - 1), term(depth - 1))
         if r < 0.93:
-            return ("sum",) + tuple(term(depth - 1) for _ in range(int(rng.integers(2, 5))))
+            return (str(rng.choice(["sum", "sum", "prod"])),) + tuple(term(depth - 1) for _ in range(int(rng.integers(2, 5))))
         return (str(rng.choice(["neg", "abs"])), term(depth - 1))
 
     def formula(depth):
         r = rng.random()
         if depth <= 1 or r < 0.3:
-            if rng.random() < 0.2:
+            q = rng.random()
+            if q < 0.2:
                 return (str(rng.choice(["lit", "nlit"])), int(rng.integers(0, nvars)))
+            if q < 0.3:
+                return ("ae", str(rng.choice(["le", "ge", "eq", "ne"])), int(rng.integers(0, nvars)), int(rng.integers(-3, 9)))
             return (str(rng.choice(["le", "gt", "eq", "ne", "le"])), term(3), term(3))
         op = str(rng.choice(["and", "or", "equiv", "imply", "xor"]))
         return (op, formula(depth - 1), formula(depth - 1))
