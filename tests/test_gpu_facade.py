@@ -32,3 +32,13 @@ def test_reference_pc_scenarios_through_the_cpp_facade():
     r = subprocess.run([PC_BIN], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "0 failures" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_flatzinc_models_through_the_cpp_ternariser():
+    """tests/pir_test.cpp's FlatZinc models: b200pc::Ternarizer -> PIR::interpret_tell -> device fixpoint, with the
+    reference's expected intervals and deduction counts."""
+    subprocess.run(["make", "-C", FACADE], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(FACADE, "tests", "ternarize_facade_test")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "0 failures" in r.stdout
