@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace lpc {
 
@@ -36,8 +37,8 @@ struct BatchCtl {
 // a third of the instructions of an `x = y + z` record in a kernel that is bound by instruction issue).
 template <int OP, bool HAS_DIV, bool TABLE_SMEM>
 __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int* sx, const int* sy, const int* sz,
-                                         const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+                                         const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op,
+                                         int tid, int nthr) {
   int f = 0;
   for(int i = s0 + tid; i < s1; i += nthr) {
     int op = OP, xi, yi, zi;
@@ -47,27 +48,33 @@ __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int
     const int2 a = lds_itv(ax), bb = lds_itv(ay), c = lds_itv(az);
     Itv r1(a.x, a.y), r2(bb.x, bb.y), r3(c.x, c.y);
     deduce_regs<HAS_DIV>(op, r1, r2, r3);
-    const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > bb.x) | (r2.ub < bb.y) | (r3.lb > c.x) | (r3.ub < c.y)
-                    | (a.x > a.y) | (bb.x > bb.y) | (c.x > c.y);
-    if(slow) {
-      if((a.x > a.y) | (bb.x > bb.y) | (c.x > c.y)) f |= 2;
-      f |= commit_smem(ax, a, r1) | commit_smem(ay, bb, r2) | commit_smem(az, c, r3);
-    }
+    // Branch-free join. On the batched workloads most warp-iterations tighten something (config 4: 79 % of the `+` ones,
+    // ncu source counters), so the "did anything tighten" test in front of a branchy join path cost more than it saved:
+    // six predicated shared-memory reductions (issued only where the bound moved) and the flags by bit arithmetic.
+    // The rules return the meet with the old domain (lb only grows, ub only shrinks), so "some bound differs" is a
+    // change, and "lb > ub afterwards" covers an operand that was already empty as well as one that just became empty.
+    reds_max_if_gt(ax, r1.lb, a.x);  reds_min_if_lt(ax + 4, r1.ub, a.y);
+    reds_max_if_gt(ay, r2.lb, bb.x); reds_min_if_lt(ay + 4, r2.ub, bb.y);
+    reds_max_if_gt(az, r3.lb, c.x);  reds_min_if_lt(az + 4, r3.ub, c.y);
+    const unsigned moved = (unsigned)((r1.lb ^ a.x) | (r1.ub ^ a.y) | (r2.lb ^ bb.x) | (r2.ub ^ bb.y) | (r3.lb ^ c.x) | (r3.ub ^ c.y));
+    f |= moved != 0u;
+    f |= ((r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub)) ? 2 : 0;
   }
   return f;
 }
 // OP = -1: opcode read per record (the division operators, and tables that are not sorted by opcode)
 template <bool HAS_DIV, bool TABLE_SMEM>
 __device__ __forceinline__ int sweep_table(const OpSegs& segs, int npad, unsigned a_S, const int* sx, const int* sy, const int* sz,
-                                           const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op) {
-  if(segs.n == 0) return sweep_run<-1, HAS_DIV, TABLE_SMEM>(0, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op);
+                                           const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op,
+                                           int tid, int nthr) {
+  if(segs.n == 0) return sweep_run<-1, HAS_DIV, TABLE_SMEM>(0, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
   int f = 0;
   for(int s = 0; s < segs.n; ++s) {
     const int s0 = segs.start[s], s1 = segs.start[s + 1];
-#define LPC_RUN(O) case O: f |= sweep_run<O, HAS_DIV, TABLE_SMEM>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op); break;
+#define LPC_RUN(O) case O: f |= sweep_run<O, HAS_DIV, TABLE_SMEM>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
     switch(segs.op[s]) {
       LPC_RUN(D_ADD) LPC_RUN(D_MUL) LPC_RUN(D_MIN) LPC_RUN(D_MAX) LPC_RUN(D_EQ) LPC_RUN(D_LEQ)
-      default: f |= sweep_run<-1, HAS_DIV, TABLE_SMEM>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op); break;
+      default: f |= sweep_run<-1, HAS_DIV, TABLE_SMEM>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
     }
 #undef LPC_RUN
   }
@@ -234,7 +241,7 @@ __global__ void k_pir_batch(TableDev t, OpSegs segs, int2* stores, int n_stores,
       bot = __syncthreads_or(f0) != 0;
       bool changed = !(bot && stop_on_bot) && t.n > 0;
       while(changed) {
-        const int f = sweep_table<HAS_DIV, TABLE_SMEM>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op);
+        const int f = sweep_table<HAS_DIV, TABLE_SMEM>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
         ++sweeps;
         if(f & 2) *s_bot = 1;
         // one barrier per sweep: it publishes the sweep's shared-memory joins, votes has_changed, and orders s_bot
@@ -286,6 +293,150 @@ __global__ void k_pir_batch(TableDev t, OpSegs segs, int2* stores, int n_stores,
   }
 }
 
+// ---- two stores in flight per block -----------------------------------------------------------------------------------
+// ncu on k_pir_batch (config 4): 15 % of the samples sit at the per-sweep block barrier and a third of the issue slots
+// are empty - with ~10 records per thread between two barriers every divergent warp makes 31 others wait. Here the
+// block's 1024 threads are two independent halves of 512; each half owns a store ring, claims its own stores and
+// synchronises on its own named barrier (bar.sync / bar.red with an id and a thread count), so one half's barrier and
+// copy waits are filled with the other half's instructions. The table stays ONE shared-memory copy per SM.
+// Shared memory: [mbarriers + scalars 128 B][half 0: 2 x sbytes][half 1: 2 x sbytes][table x | y | z | op].
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ int nbar_or(int id, int n, int pred) {
+  int r;
+  asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.or.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
+               : "=r"(r) : "r"(id), "r"(n), "r"(pred) : "memory");
+  return r;
+}
+__device__ __forceinline__ int nbar_and(int id, int n, int pred) {
+  int r;
+  asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.and.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
+               : "=r"(r) : "r"(id), "r"(n), "r"(pred) : "memory");
+  return r;
+}
+
+// G groups of 1024 / G threads, SLOTS ring slots per group (2: the next store is prefetched while this one iterates;
+// 1: load, iterate, write back in turn - the other groups cover the copies). Fewer threads per store also make a sweep
+// more sequential, so a store needs fewer sweeps (config 4: 285 k -> 254 k sweeps in total at G = 2).
+template <bool HAS_DIV, int G, int SLOTS>
+__global__ void __launch_bounds__(1024, 1) k_pir_batch2(TableDev t, OpSegs segs, int2* stores, int n_stores, int sbytes, uint8_t* flags,
+                                                       int* sweeps_out, int* obj_out, BatchCtl* ctl, int objective_var,
+                                                       int max_sweeps, int stop_on_bot) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int nthr = 1024 / G;
+  const int grp = threadIdx.x / nthr, tid = threadIdx.x % nthr, bid = 1 + grp;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);   // [SLOTS * grp + slot]: store rings, [G * SLOTS]: table
+  int* s_next = reinterpret_cast<int*>(smem + 128 + 8 * grp);
+  volatile int* s_bot = reinterpret_cast<volatile int*>(smem + 128 + 8 * grp + 4);
+  unsigned char* ring_base = smem + 256 + (size_t)grp * SLOTS * sbytes;
+  int2* ring[2] = {reinterpret_cast<int2*>(ring_base), reinterpret_cast<int2*>(ring_base + (SLOTS - 1) * (size_t)sbytes)};
+  char* tb = reinterpret_cast<char*>(smem + 256 + (size_t)G * SLOTS * sbytes);
+  const int npad = (int)t.n_pad;
+  const size_t store_stride = (size_t)t.nvars;
+  unsigned long long* tbar = &bars[G * SLOTS];
+
+  if(threadIdx.x == 0) {
+    for(int i = 0; i <= G * SLOTS; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  int cur = G * blockIdx.x + grp < n_stores ? G * blockIdx.x + grp : -1;
+  if(threadIdx.x == 0) {
+    mbar_expect_tx(tbar, (unsigned)(npad * 13));
+    bulk_g2s_chunked(tb, (const char*)t.x, npad * 4, tbar);
+    bulk_g2s_chunked(tb + (size_t)npad * 4, (const char*)t.y, npad * 4, tbar);
+    bulk_g2s_chunked(tb + (size_t)npad * 8, (const char*)t.z, npad * 4, tbar);
+    bulk_g2s_chunked(tb + (size_t)npad * 12, (const char*)t.op, npad, tbar);
+  }
+  if(tid == 0 && cur >= 0) {
+    mbar_expect_tx(&bars[SLOTS * grp], (unsigned)sbytes);
+    bulk_g2s_chunked((char*)ring[0], (const char*)(stores + cur * store_stride), sbytes, &bars[SLOTS * grp]);
+  }
+  const int* sx = reinterpret_cast<const int*>(tb);
+  const int* sy = reinterpret_cast<const int*>(tb + (size_t)npad * 4);
+  const int* sz = reinterpret_cast<const int*>(tb + (size_t)npad * 8);
+  const uint8_t* sop = reinterpret_cast<const uint8_t*>(tb + (size_t)npad * 12);
+  mbar_wait(tbar, 0);
+  const unsigned a_x = smem_u32(sx), a_y = smem_u32(sy), a_z = smem_u32(sz), a_op = smem_u32(sop);
+
+  long long a_sol = 0, a_bot = 0, a_unk = 0, a_sweeps = 0, a_ded = 0;
+  int a_best = LPC_INF, a_maxsw = 0;
+  unsigned phase[2] = {0, 0};
+  int b = 0;
+  while(cur >= 0) {
+    if(tid == 0) {   // claim the next store of this group; with two slots, start fetching it into the other one
+      int nx = atomicAdd(&ctl->next_store, 1);
+      if(nx >= n_stores) nx = -1;
+      *s_next = nx;
+      if(SLOTS == 2 && nx >= 0) {
+        bulk_wait_read0();   // the write-back that last used the other slot has finished reading it
+        mbar_expect_tx(&bars[SLOTS * grp + (b ^ 1)], (unsigned)sbytes);
+        bulk_g2s_chunked((char*)ring[b ^ 1], (const char*)(stores + nx * store_stride), sbytes, &bars[SLOTS * grp + (b ^ 1)]);
+      }
+      *s_bot = 0;
+    }
+    mbar_wait(&bars[SLOTS * grp + b], phase[b]);
+    phase[b] ^= 1;
+    int2* S = ring[b];
+    const unsigned a_S = smem_u32(S);
+    int f0 = 0;
+    for(int v = tid; v < t.nvars; v += nthr) { int2 d = S[v]; f0 |= d.x > d.y; }
+    bool bot = nbar_or(bid, nthr, f0) != 0;   // also orders thread 0's s_bot / s_next writes before their readers
+    int sweeps = 0;
+    bool changed = !(bot && stop_on_bot) && t.n > 0;
+    while(changed) {
+      const int f = sweep_table<HAS_DIV, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+      ++sweeps;
+      if(f & 2) *s_bot = 1;
+      const int any_chg = nbar_or(bid, nthr, f & 1);
+      bot |= *s_bot != 0;
+      changed = any_chg && !(bot && stop_on_bot) && !(max_sweeps && sweeps >= max_sweeps);
+    }
+    int all_ent = 0;
+    if(!bot) {   // entailment: the ask loop of is_extractable
+      int ok = 1;
+      for(int i = tid; i < npad && ok; i += nthr) {
+        const int2 a = S[sx[i]], bb = S[sy[i]], c = S[sz[i]];
+        ok = ask_regs(sop[i], Itv(a.x, a.y), Itv(bb.x, bb.y), Itv(c.x, c.y));
+      }
+      all_ent = nbar_and(bid, nthr, ok);
+    }
+    fence_async_smem();
+    nbar_sync(bid, nthr);
+    const int nxt = *s_next;
+    if(tid == 0) {
+      for(int o = 0; o < sbytes; o += 32768) bulk_s2g((char*)(stores + cur * store_stride) + o, (char*)S + o, min(32768, sbytes - o));
+      bulk_commit();
+      flags[cur] = (uint8_t)((bot ? 1 : 0) | (all_ent ? 2 : 0));
+      sweeps_out[cur] = sweeps;
+      const int olb = objective_var >= 0 ? S[objective_var].x : LPC_INF;
+      if(obj_out) obj_out[cur] = olb;
+      if(bot) ++a_bot; else if(all_ent) ++a_sol; else ++a_unk;
+      if(!bot && objective_var >= 0) a_best = min(a_best, olb);
+      a_sweeps += sweeps;
+      a_ded += (long long)sweeps * t.n;
+      a_maxsw = max(a_maxsw, sweeps);
+      if(SLOTS == 1 && nxt >= 0) {   // one slot: the next store goes into the same image once the write-back has read it
+        bulk_wait_read0();
+        mbar_expect_tx(&bars[grp], (unsigned)sbytes);
+        bulk_g2s_chunked((char*)ring[0], (const char*)(stores + nxt * store_stride), sbytes, &bars[grp]);
+      }
+    }
+    cur = nxt;
+    nbar_sync(bid, nthr);   // everyone of this group has read s_next before its thread 0 overwrites it
+    if(SLOTS == 2) b ^= 1;
+  }
+  if(tid == 0) {
+    bulk_wait0();
+    if(a_sol) atomicAdd((unsigned long long*)&ctl->red[0], (unsigned long long)a_sol);
+    if(a_bot) atomicAdd((unsigned long long*)&ctl->red[1], (unsigned long long)a_bot);
+    if(a_unk) atomicAdd((unsigned long long*)&ctl->red[2], (unsigned long long)a_unk);
+    atomicMin(&ctl->red[3], (long long)a_best);
+    atomicAdd((unsigned long long*)&ctl->sweeps_total, (unsigned long long)a_sweeps);
+    atomicAdd((unsigned long long*)&ctl->deductions, (unsigned long long)a_ded);
+    atomicMax(&ctl->max_sweeps_seen, a_maxsw);
+  }
+}
+
 // ---- in-kernel search: propagate + branch on one store per block ------------------------------------------------------
 // snapshot / restore (pir.hpp:857-870) and branching moved next to the fixpoint, so that a
 // subproblem is SOLVED by its block instead of only propagated once. Depth-first, deterministic: the variable is the
@@ -314,7 +465,7 @@ __device__ __forceinline__ bool block_fixpoint(const TableDev& t, const OpSegs& 
   bool changed = !bot && t.n > 0;
   int sweeps = 0;
   while(changed) {
-    const int f = sweep_table<HAS_DIV, TABLE_SMEM>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op);
+    const int f = sweep_table<HAS_DIV, TABLE_SMEM>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
     ++sweeps;
     if(f & 2) *s_bot = 1;
     const int any_chg = __syncthreads_or(f & 1);
@@ -519,6 +670,9 @@ struct lpc_batch {
   cudaStream_t last_stream = nullptr;
   bool pending = false;
   int sbytes = 0;
+  int dual = -1;                         // two stores in flight per block (k_pir_batch2): -1 = not decided yet
+  size_t dual_smem = 0;
+  int dual_grid = 0;
   bool plan_ready[2] = {false, false};   // [dense, change-driven]
   bool table_smem[2] = {false, false};
   size_t smem[2] = {0, 0};
@@ -530,6 +684,15 @@ struct lpc_batch {
 
 typedef void (*batch_kernel_t)(TableDev, OpSegs, int2*, int, int, uint8_t*, int*, int*, BatchCtl*, int, int, int, const int*, int);
 
+#define LPC_BATCH_G_DEFAULT 4
+static const void* batch2_kernel(bool has_div, int g) {
+  switch(g) {
+    case 2: return has_div ? (const void*)k_pir_batch2<true, 2, 2> : (const void*)k_pir_batch2<false, 2, 2>;
+    case 4: return has_div ? (const void*)k_pir_batch2<true, 4, 1> : (const void*)k_pir_batch2<false, 4, 1>;
+    case 8: return has_div ? (const void*)k_pir_batch2<true, 8, 1> : (const void*)k_pir_batch2<false, 8, 1>;
+    default: return nullptr;
+  }
+}
 static batch_kernel_t pick_batch_kernel(bool has_div, bool table_smem, bool cd) {
   if(cd) {
     if(has_div) return table_smem ? k_pir_batch<true, true, true> : k_pir_batch<true, false, true>;
@@ -697,15 +860,51 @@ int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t o
     b->grid[cd] = std::max(1, std::min(b->n_stores, sms * per_sm));
     b->plan_ready[cd] = true;
   }
+  // dense mode with the table in shared memory and room for the store images of several groups next to it: G stores in
+  // flight per block (k_pir_batch2). LPC_BATCH_DUAL = 0 keeps one store per block, 2 / 4 / 8 force a group count (A/B runs).
+  if(b->dual < 0) {
+    b->dual = 0;
+    const char* e = getenv("LPC_BATCH_DUAL");
+    const int want = e ? atoi(e) : -1;
+    int dev = 0, sms = 0, optin = 0;
+    LPC_CUDA(cudaGetDevice(&dev));
+    LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    LPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t tbl = (size_t)t->dev.n_pad * 13;
+    static const int kG[3] = {LPC_BATCH_G_DEFAULT, 4, 2}, kS[3] = {LPC_BATCH_G_DEFAULT == 2 ? 2 : 1, 1, 2};
+    if(want != 0 && t->dev.n_pad >= 2048 && b->n_stores >= 8 * sms) {
+      for(int c = 0; c < 3 && !b->dual; ++c) {
+        const int g = want > 0 ? want : kG[c], sl = g == 2 ? 2 : (want > 0 ? 1 : kS[c]);
+        const size_t need = 256 + (size_t)g * sl * b->sbytes + tbl;
+        const void* kk = batch2_kernel(t->has_div, g);
+        if(!kk || need > (size_t)optin) { if(want > 0) break; else continue; }
+        LPC_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        int per_sm = 0;
+        LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kk, 1024, need));
+        if(per_sm >= 1) { b->dual = g; b->dual_smem = need; b->dual_grid = std::max(1, std::min((b->n_stores + g - 1) / g, sms)); }
+        if(want > 0) break;
+      }
+    }
+  }
+  const bool dual = !cd && b->dual >= 2;
   batch_kernel_t k = pick_batch_kernel(t->has_div, b->table_smem[cd], cd);
-  const int grid = b->grid[cd], threads = b->threads[cd];
-  const size_t smem = b->smem[cd];
+  const int grid = dual ? b->dual_grid : b->grid[cd], threads = dual ? 1024 : b->threads[cd];
+  const size_t smem = dual ? b->dual_smem : b->smem[cd];
   memset(b->h_init, 0, sizeof(BatchCtl));
   b->h_init->red[3] = LPC_INF;
-  b->h_init->next_store = grid;
+  b->h_init->next_store = dual ? b->dual * grid : grid;
   LPC_CUDA(cudaEventRecord(b->ev0, st));
   LPC_CUDA(cudaMemcpyAsync(b->d_ctl, b->h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
-  if(b->n_stores > 0) {
+  if(b->n_stores > 0 && dual) {
+    const void* kk = batch2_kernel(t->has_div, b->dual);
+    TableDev td = t->dev; OpSegs sg = t->opsegs;
+    int2* dd = b->d; int ns = b->n_stores, sb = b->sbytes; uint8_t* fl = b->d_flags; int* sw = b->d_sweeps; int* ob = b->d_obj;
+    BatchCtl* ct = b->d_ctl; int ov = objective_var, ms = o->max_sweeps, sob = o->stop_on_bot;
+    void* args[] = {&td, &sg, &dd, &ns, &sb, &fl, &sw, &ob, &ct, &ov, &ms, &sob};
+    LPC_CUDA(cudaLaunchKernel(kk, dim3(grid), dim3(threads), args, smem, st));
+    g_launches++;
+  }
+  else if(b->n_stores > 0) {
     k<<<grid, threads, smem, st>>>(t->dev, t->opsegs, b->d, b->n_stores, b->sbytes, b->d_flags, b->d_sweeps, b->d_obj, b->d_ctl,
                                   objective_var, o->max_sweeps, o->stop_on_bot, b->d_seeds, b->n_seeds);
     g_launches++;
