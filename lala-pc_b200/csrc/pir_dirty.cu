@@ -30,7 +30,7 @@ struct DSeg { int nseg; int u[D_MAX_SEG + 1]; };   // opcode segments in units o
 template <bool HAS_DIV>
 __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, DSeg seg, FixCtl* ctl, unsigned char* dmap,
                                                        int n_groups, int map_stride, unsigned switch_groups, int max_sweeps,
-                                                       int stop_on_bot, int sm_order) {
+                                                       int stop_on_bot, int sm_order, int strided) {
   __shared__ unsigned long long s_vote;
   __shared__ unsigned s_cnt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -64,6 +64,86 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
     __syncthreads();
     int f = 0;
     unsigned my_groups = 0, my_evals = 0;
+    // One warp-step: this lane's unit u (2 records) of a 64-record group, evaluated iff `active`; then the group's flags.
+    auto eval_unit = [&](int u, bool active) {
+      int g1 = 0;
+      int cv[6] = {-1, -1, -1, -1, -1, -1};   // variables this lane tightened (2 records x 3 operands)
+      if(active) {
+        const uchar2 o = reinterpret_cast<const uchar2*>(t.op)[u];
+        const int2 X = reinterpret_cast<const int2*>(t.x)[u], Y = reinterpret_cast<const int2*>(t.y)[u],
+                   Z = reinterpret_cast<const int2*>(t.z)[u];
+        const int2 a0v = store[X.x], b0v = store[Y.x], c0v = store[Z.x];
+        const int2 a1v = store[X.y], b1v = store[Y.y], c1v = store[Z.y];
+#pragma unroll
+        for(int h = 0; h < 2; ++h) {
+          const int op = h ? o.y : o.x, xi = h ? X.y : X.x, yi = h ? Y.y : Y.x, zi = h ? Z.y : Z.x;
+          const int2 a = h ? a1v : a0v, b = h ? b1v : b0v, c = h ? c1v : c0v;
+          Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
+          deduce_regs<HAS_DIV>(op, r1, r2, r3);
+          const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > b.x) | (r2.ub < b.y) | (r3.lb > c.x) | (r3.ub < c.y)
+                          | (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
+          if(slow) {
+            if((a.x > a.y) | (b.x > b.y) | (c.x > c.y)) g1 |= 2;
+#pragma unroll
+            for(int w = 0; w < 3; ++w) {
+              const int v = w == 0 ? xi : w == 1 ? yi : zi;
+              const int2 old = w == 0 ? a : w == 1 ? b : c;
+              const Itv nw = w == 0 ? r1 : w == 1 ? r2 : r3;
+              int ch = 0;
+              if(nw.lb > old.x) { atomicMax(&store[v].x, nw.lb); ch = 1; }
+              if(nw.ub < old.y) { atomicMin(&store[v].y, nw.ub); ch = 1; }
+              if(ch) {
+                g1 |= nw.lb > nw.ub ? 3 : 1;
+                cv[h * 3 + w] = v;
+              }
+            }
+          }
+        }
+      }
+      f |= g1;
+      const bool grp_changed = __any_sync(0xffffffffu, g1 & 1);
+      if(grp_changed && dnext) {
+        // flag the groups of the records incident to every tightened variable (var -> records CSR)
+        {
+          // the warp walks each variable's row together (one coalesced load of up to 32 record indices). Letting every
+          // lane walk the rows of its own variables instead was measured slower (0.41-0.43 vs 0.395 ms on config 2,
+          // profiles/r01_ab_strided.txt).
+#pragma unroll
+          for(int q = 0; q < 6; ++q) {
+            unsigned m = __ballot_sync(0xffffffffu, cv[q] >= 0);
+            if(!m) continue;
+            int rb = 0, re = 0;
+            if(cv[q] >= 0) { rb = t.inc_off[cv[q]]; re = t.inc_off[cv[q] + 1]; }
+            while(m) {
+              const int src = __ffs(m) - 1;
+              m &= m - 1;
+              const int bb = __shfl_sync(0xffffffffu, rb, src), ee = __shfl_sync(0xffffffffu, re, src);
+              for(int j = bb + lane; j < ee; j += 32) dnext[t.inc_idx[j] >> 6] = 1;
+            }
+          }
+        }
+      }
+      if(grp_changed) ++my_groups;
+      ++my_evals;
+    };
+    if(phase == 2 && strided) {
+      // Flagged sweeps, groups dealt to the warps of the whole grid round-robin: flagged groups cluster (a change moves
+      // along the sort order), and with contiguous shares a few blocks did all the work of a sparse sweep while the rest
+      // waited at the barrier. A warp reads the flags of its next 32 groups with one strided byte load + ballot.
+      const long long gwarp = gtid >> 5, gwarps = gthreads >> 5;
+      const int n_units = (int)(t.n_pad / 2);
+      for(long long base = gwarp; base < n_groups; base += 32 * gwarps) {
+        const long long g = base + (long long)lane * gwarps;
+        unsigned need = __ballot_sync(0xffffffffu, g < n_groups && dcur[g] != 0);
+        while(need) {
+          const int k = __ffs(need) - 1;
+          need &= need - 1;
+          const int u = (int)(base + (long long)k * gwarps) * 32 + lane;
+          eval_unit(u, u < n_units);
+        }
+      }
+    }
+    else
     for(int s = 0; s < seg.nseg; ++s) {
       // this block's contiguous share of the segment, cut at group boundaries (32 units = 64 records)
       const long long s0 = seg.u[s], s1 = seg.u[s + 1], len = s1 - s0;
@@ -86,61 +166,7 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
         for(int k = kb; k < kend; ++k) {
           if(!((need >> (k - kb)) & 1u)) continue;
           const int u = a0 + tid + k * DTPB;
-          int g1 = 0;
-          int cv[6] = {-1, -1, -1, -1, -1, -1};   // variables this lane tightened (2 records x 3 operands)
-          if(u >= u0 && u < u1) {
-            const uchar2 o = reinterpret_cast<const uchar2*>(t.op)[u];
-            const int2 X = reinterpret_cast<const int2*>(t.x)[u], Y = reinterpret_cast<const int2*>(t.y)[u],
-                       Z = reinterpret_cast<const int2*>(t.z)[u];
-            const int2 a0v = store[X.x], b0v = store[Y.x], c0v = store[Z.x];
-            const int2 a1v = store[X.y], b1v = store[Y.y], c1v = store[Z.y];
-#pragma unroll
-            for(int h = 0; h < 2; ++h) {
-              const int op = h ? o.y : o.x, xi = h ? X.y : X.x, yi = h ? Y.y : Y.x, zi = h ? Z.y : Z.x;
-              const int2 a = h ? a1v : a0v, b = h ? b1v : b0v, c = h ? c1v : c0v;
-              Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
-              deduce_regs<HAS_DIV>(op, r1, r2, r3);
-              const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > b.x) | (r2.ub < b.y) | (r3.lb > c.x) | (r3.ub < c.y)
-                              | (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
-              if(slow) {
-                if((a.x > a.y) | (b.x > b.y) | (c.x > c.y)) g1 |= 2;
-#pragma unroll
-                for(int w = 0; w < 3; ++w) {
-                  const int v = w == 0 ? xi : w == 1 ? yi : zi;
-                  const int2 old = w == 0 ? a : w == 1 ? b : c;
-                  const Itv nw = w == 0 ? r1 : w == 1 ? r2 : r3;
-                  int ch = 0;
-                  if(nw.lb > old.x) { atomicMax(&store[v].x, nw.lb); ch = 1; }
-                  if(nw.ub < old.y) { atomicMin(&store[v].y, nw.ub); ch = 1; }
-                  if(ch) {
-                    g1 |= nw.lb > nw.ub ? 3 : 1;
-                    cv[h * 3 + w] = v;
-                  }
-                }
-              }
-            }
-          }
-          f |= g1;
-          const bool grp_changed = __any_sync(0xffffffffu, g1 & 1);
-          if(grp_changed && dnext) {
-            // flag the groups of the records incident to every tightened variable: the warp walks each variable's CSR
-            // row together (one coalesced load of up to 32 record indices) instead of one lane chasing it alone
-#pragma unroll
-            for(int q = 0; q < 6; ++q) {
-              unsigned m = __ballot_sync(0xffffffffu, cv[q] >= 0);
-              if(!m) continue;
-              int rb = 0, re = 0;
-              if(cv[q] >= 0) { rb = t.inc_off[cv[q]]; re = t.inc_off[cv[q] + 1]; }
-              while(m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const int bb = __shfl_sync(0xffffffffu, rb, src), ee = __shfl_sync(0xffffffffu, re, src);
-                for(int j = bb + lane; j < ee; j += 32) dnext[t.inc_idx[j] >> 6] = 1;
-              }
-            }
-          }
-          if(grp_changed) ++my_groups;
-          ++my_evals;
+          eval_unit(u, u >= u0 && u < u1);
         }
       }
     }
@@ -215,7 +241,9 @@ int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opt
   int ng = n_groups, ms = map_stride, max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
   int sm_order = 1;   // LPC_SMORDER=0: fractions in blockIdx order (A/B runs)
   if(const char* e = getenv("LPC_SMORDER")) sm_order = atoi(e);
-  void* args[] = {&td, &store, &seg, &ctl, &dmap, &ng, &ms, &switch_groups, &max_sweeps, &stop, &sm_order};
+  int strided = 1;    // LPC_DIRTY_STRIDED=0: flagged sweeps keep the contiguous block shares (A/B runs)
+  if(const char* e = getenv("LPC_DIRTY_STRIDED")) strided = atoi(e);
+  void* args[] = {&td, &store, &seg, &ctl, &dmap, &ng, &ms, &switch_groups, &max_sweeps, &stop, &sm_order, &strided};
   void* k = t->has_div ? (void*)k_pir_dirty<true> : (void*)k_pir_dirty<false>;
   LPC_CUDA(cudaLaunchCooperativeKernel(k, dim3(grid), dim3(DTPB), args, 0, st));
   g_launches++;
