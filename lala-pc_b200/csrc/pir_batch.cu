@@ -35,7 +35,7 @@ struct BatchCtl {
 // rule is the only code in the loop body (a sorted table has one run per operator, so warps are uniform anyway; what this
 // removes is the ~16 instructions per record of fetching the opcode byte, the jump table and the phi moves after it -
 // a third of the instructions of an `x = y + z` record in a kernel that is bound by instruction issue).
-template <int OP, bool HAS_DIV, bool TABLE_SMEM>
+template <int OP, bool HAS_DIV, bool TABLE_SMEM, bool BF>
 __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int* sx, const int* sy, const int* sz,
                                          const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op,
                                          int tid, int nthr) {
@@ -48,6 +48,15 @@ __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int
     const int2 a = lds_itv(ax), bb = lds_itv(ay), c = lds_itv(az);
     Itv r1(a.x, a.y), r2(bb.x, bb.y), r3(c.x, c.y);
     deduce_regs<HAS_DIV>(op, r1, r2, r3);
+    if(!BF) {   // few changes expected (the nodes of a search): one test, then the rare join path
+      const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > bb.x) | (r2.ub < bb.y) | (r3.lb > c.x) | (r3.ub < c.y)
+                      | (a.x > a.y) | (bb.x > bb.y) | (c.x > c.y);
+      if(slow) {
+        if((a.x > a.y) | (bb.x > bb.y) | (c.x > c.y)) f |= 2;
+        f |= commit_smem(ax, a, r1) | commit_smem(ay, bb, r2) | commit_smem(az, c, r3);
+      }
+      continue;
+    }
     // Branch-free join. On the batched workloads most warp-iterations tighten something (config 4: 79 % of the `+` ones,
     // ncu source counters), so the "did anything tighten" test in front of a branchy join path cost more than it saved:
     // six predicated shared-memory reductions (issued only where the bound moved) and the flags by bit arithmetic.
@@ -63,18 +72,18 @@ __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int
   return f;
 }
 // OP = -1: opcode read per record (the division operators, and tables that are not sorted by opcode)
-template <bool HAS_DIV, bool TABLE_SMEM>
+template <bool HAS_DIV, bool TABLE_SMEM, bool BF>
 __device__ __forceinline__ int sweep_table(const OpSegs& segs, int npad, unsigned a_S, const int* sx, const int* sy, const int* sz,
                                            const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op,
                                            int tid, int nthr) {
-  if(segs.n == 0) return sweep_run<-1, HAS_DIV, TABLE_SMEM>(0, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+  if(segs.n == 0) return sweep_run<-1, HAS_DIV, TABLE_SMEM, BF>(0, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
   int f = 0;
   for(int s = 0; s < segs.n; ++s) {
     const int s0 = segs.start[s], s1 = segs.start[s + 1];
-#define LPC_RUN(O) case O: f |= sweep_run<O, HAS_DIV, TABLE_SMEM>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
+#define LPC_RUN(O) case O: f |= sweep_run<O, HAS_DIV, TABLE_SMEM, BF>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
     switch(segs.op[s]) {
       LPC_RUN(D_ADD) LPC_RUN(D_MUL) LPC_RUN(D_MIN) LPC_RUN(D_MAX) LPC_RUN(D_EQ) LPC_RUN(D_LEQ)
-      default: f |= sweep_run<-1, HAS_DIV, TABLE_SMEM>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
+      default: f |= sweep_run<-1, HAS_DIV, TABLE_SMEM, BF>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
     }
 #undef LPC_RUN
   }
@@ -241,7 +250,7 @@ __global__ void k_pir_batch(TableDev t, OpSegs segs, int2* stores, int n_stores,
       bot = __syncthreads_or(f0) != 0;
       bool changed = !(bot && stop_on_bot) && t.n > 0;
       while(changed) {
-        const int f = sweep_table<HAS_DIV, TABLE_SMEM>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+        const int f = sweep_table<HAS_DIV, TABLE_SMEM, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
         ++sweeps;
         if(f & 2) *s_bot = 1;
         // one barrier per sweep: it publishes the sweep's shared-memory joins, votes has_changed, and orders s_bot
@@ -384,7 +393,7 @@ __global__ void __launch_bounds__(1024, 1) k_pir_batch2(TableDev t, OpSegs segs,
     int sweeps = 0;
     bool changed = !(bot && stop_on_bot) && t.n > 0;
     while(changed) {
-      const int f = sweep_table<HAS_DIV, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+      const int f = sweep_table<HAS_DIV, true, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
       ++sweeps;
       if(f & 2) *s_bot = 1;
       const int any_chg = nbar_or(bid, nthr, f & 1);
@@ -465,7 +474,7 @@ __device__ __forceinline__ bool block_fixpoint(const TableDev& t, const OpSegs& 
   bool changed = !bot && t.n > 0;
   int sweeps = 0;
   while(changed) {
-    const int f = sweep_table<HAS_DIV, TABLE_SMEM>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+    const int f = sweep_table<HAS_DIV, TABLE_SMEM, false>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
     ++sweeps;
     if(f & 2) *s_bot = 1;
     const int any_chg = __syncthreads_or(f & 1);
