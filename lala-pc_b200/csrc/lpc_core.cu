@@ -205,6 +205,16 @@ int lpc_table_create(const lpc_bytecode* records, int64_t n, int32_t nvars, lpc_
   t->dev.op = (const uint8_t*)t->d_op; t->dev.x = (const int*)t->d_x; t->dev.y = (const int*)t->d_y; t->dev.z = (const int*)t->d_z;
   t->dev.n = n; t->dev.n_pad = n_pad; t->dev.nvars = nvars;
   t->dev.inc_off = (const int*)t->d_inc_off; t->dev.inc_idx = (const int*)t->d_inc_idx;
+  t->dev.x16 = t->dev.y16 = t->dev.z16 = nullptr;
+  if(nvars <= 8191) {   // small enough for 16-bit byte offsets: the shared-memory form of the batch kernels
+    std::vector<unsigned short> x16(n_pad), y16(n_pad), z16(n_pad);
+    for(long long i = 0; i < n_pad; ++i) { x16[i] = (unsigned short)(8 * x[i]); y16[i] = (unsigned short)(8 * y[i]); z16[i] = (unsigned short)(8 * z[i]); }
+    if((rc = up(&t->d_x16, x16.data(), n_pad * 2)) || (rc = up(&t->d_y16, y16.data(), n_pad * 2)) || (rc = up(&t->d_z16, z16.data(), n_pad * 2))) {
+      lpc_table_destroy(t);
+      return rc;
+    }
+    t->dev.x16 = (const unsigned short*)t->d_x16; t->dev.y16 = (const unsigned short*)t->d_y16; t->dev.z16 = (const unsigned short*)t->d_z16;
+  }
   cudaDeviceProp prop;
   LPC_CUDA(cudaGetDeviceProperties(&prop, dev));
   t->sm_count = prop.multiProcessorCount;
@@ -217,6 +227,7 @@ int lpc_table_destroy(lpc_table* t) {
   if(!t) return LPC_OK;
   cudaFree(t->d_op); cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z);
   cudaFree(t->d_inc_off); cudaFree(t->d_inc_idx); cudaFree(t->d_chunk);
+  cudaFree(t->d_x16); cudaFree(t->d_y16); cudaFree(t->d_z16);
   if(t->host_store) lpc_store_destroy(t->host_store);
   lpc_win_plan_free(t->win_plan);
   delete t;

@@ -43,6 +43,11 @@ struct TableDev {
   // var -> records incidence (CSR), for the change-driven worklist
   const int* inc_off;   // [nvars + 1]
   const int* inc_idx;   // [3 n] (duplicates removed per record)
+  // x / y / z as 16-bit byte offsets into a store image (8 * vid), present iff nvars <= 8191: the form the batch kernels
+  // stage in shared memory (7 B per record instead of 13, and the gather address is one add)
+  const unsigned short* x16;
+  const unsigned short* y16;
+  const unsigned short* z16;
 };
 
 // Runs of equal opcode in table order (exact record indices, padding excluded). A table built by PIR::deduce(tell) is
@@ -85,6 +90,7 @@ struct lpc_table {
   lpc::TableDev dev{};
   void* d_op = nullptr; void* d_x = nullptr; void* d_y = nullptr; void* d_z = nullptr;
   void* d_inc_off = nullptr; void* d_inc_idx = nullptr;
+  void* d_x16 = nullptr; void* d_y16 = nullptr; void* d_z16 = nullptr;
   bool has_div = false;
   long long op_count[10] = {0};
   lpc::OpSegs opsegs{};             // opcode runs for the per-operator loops of the block kernels (pir_batch.cu)

@@ -35,16 +35,26 @@ struct BatchCtl {
 // rule is the only code in the loop body (a sorted table has one run per operator, so warps are uniform anyway; what this
 // removes is the ~16 instructions per record of fetching the opcode byte, the jump table and the phi moves after it -
 // a third of the instructions of an `x = y + z` record in a kernel that is bound by instruction issue).
-template <int OP, bool HAS_DIV, bool TABLE_SMEM, bool BF>
+// TAB: where the table is read from - 0 global memory (int32 indices), 1 shared memory (int32 indices), 2 shared memory
+// as 16-bit byte offsets (TableDev::x16; a_x / a_y / a_z then address 2-byte entries)
+template <int OP, bool HAS_DIV, int TAB, bool BF>
 __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int* sx, const int* sy, const int* sz,
                                          const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op,
                                          int tid, int nthr) {
   int f = 0;
   for(int i = s0 + tid; i < s1; i += nthr) {
-    int op = OP, xi, yi, zi;
-    if(TABLE_SMEM) { if(OP < 0) op = lds_u8(a_op + i); xi = lds_s32(a_x + 4 * i); yi = lds_s32(a_y + 4 * i); zi = lds_s32(a_z + 4 * i); }
-    else { if(OP < 0) op = sop[i]; xi = sx[i]; yi = sy[i]; zi = sz[i]; }
-    const unsigned ax = a_S + 8u * xi, ay = a_S + 8u * yi, az = a_S + 8u * zi;
+    int op = OP;
+    unsigned ax, ay, az;
+    if(TAB == 2) {
+      if(OP < 0) op = lds_u8(a_op + i);
+      ax = a_S + lds_u16(a_x + 2 * i); ay = a_S + lds_u16(a_y + 2 * i); az = a_S + lds_u16(a_z + 2 * i);
+    }
+    else {
+      int xi, yi, zi;
+      if(TAB == 1) { if(OP < 0) op = lds_u8(a_op + i); xi = lds_s32(a_x + 4 * i); yi = lds_s32(a_y + 4 * i); zi = lds_s32(a_z + 4 * i); }
+      else { if(OP < 0) op = sop[i]; xi = sx[i]; yi = sy[i]; zi = sz[i]; }
+      ax = a_S + 8u * xi; ay = a_S + 8u * yi; az = a_S + 8u * zi;
+    }
     const int2 a = lds_itv(ax), bb = lds_itv(ay), c = lds_itv(az);
     Itv r1(a.x, a.y), r2(bb.x, bb.y), r3(c.x, c.y);
     deduce_regs<HAS_DIV>(op, r1, r2, r3);
@@ -72,18 +82,18 @@ __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int
   return f;
 }
 // OP = -1: opcode read per record (the division operators, and tables that are not sorted by opcode)
-template <bool HAS_DIV, bool TABLE_SMEM, bool BF>
+template <bool HAS_DIV, int TAB, bool BF>
 __device__ __forceinline__ int sweep_table(const OpSegs& segs, int npad, unsigned a_S, const int* sx, const int* sy, const int* sz,
                                            const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op,
                                            int tid, int nthr) {
-  if(segs.n == 0) return sweep_run<-1, HAS_DIV, TABLE_SMEM, BF>(0, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+  if(segs.n == 0) return sweep_run<-1, HAS_DIV, TAB, BF>(0, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
   int f = 0;
   for(int s = 0; s < segs.n; ++s) {
     const int s0 = segs.start[s], s1 = segs.start[s + 1];
-#define LPC_RUN(O) case O: f |= sweep_run<O, HAS_DIV, TABLE_SMEM, BF>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
+#define LPC_RUN(O) case O: f |= sweep_run<O, HAS_DIV, TAB, BF>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
     switch(segs.op[s]) {
       LPC_RUN(D_ADD) LPC_RUN(D_MUL) LPC_RUN(D_MIN) LPC_RUN(D_MAX) LPC_RUN(D_EQ) LPC_RUN(D_LEQ)
-      default: f |= sweep_run<-1, HAS_DIV, TABLE_SMEM, BF>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
+      default: f |= sweep_run<-1, HAS_DIV, TAB, BF>(s0, s1, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr); break;
     }
 #undef LPC_RUN
   }
@@ -250,7 +260,7 @@ __global__ void k_pir_batch(TableDev t, OpSegs segs, int2* stores, int n_stores,
       bot = __syncthreads_or(f0) != 0;
       bool changed = !(bot && stop_on_bot) && t.n > 0;
       while(changed) {
-        const int f = sweep_table<HAS_DIV, TABLE_SMEM, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+        const int f = sweep_table<HAS_DIV, TABLE_SMEM ? 1 : 0, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
         ++sweeps;
         if(f & 2) *s_bot = 1;
         // one barrier per sweep: it publishes the sweep's shared-memory joins, votes has_changed, and orders s_bot
@@ -325,8 +335,10 @@ __device__ __forceinline__ int nbar_and(int id, int n, int pred) {
 
 // G groups of 1024 / G threads, SLOTS ring slots per group (2: the next store is prefetched while this one iterates;
 // 1: load, iterate, write back in turn - the other groups cover the copies). Fewer threads per store also make a sweep
-// more sequential, so a store needs fewer sweeps (config 4: 285 k -> 254 k sweeps in total at G = 2).
-template <bool HAS_DIV, int G, int SLOTS>
+// more sequential, so a store needs fewer sweeps (config 4: 285 k sweeps in total with one store per block, 254 k at
+// G = 2, 235 k at G = 4, 217 k at G = 8; 9.5 / 7.6 / 6.8 / 6.4 ms per 65,536 stores).
+// IDX16: the table is staged as 16-bit byte offsets (7 B per record), which leaves room for more store slots.
+template <bool HAS_DIV, int G, int SLOTS, bool IDX16>
 __global__ void __launch_bounds__(1024, 1) k_pir_batch2(TableDev t, OpSegs segs, int2* stores, int n_stores, int sbytes, uint8_t* flags,
                                                        int* sweeps_out, int* obj_out, BatchCtl* ctl, int objective_var,
                                                        int max_sweeps, int stop_on_bot) {
@@ -349,21 +361,22 @@ __global__ void __launch_bounds__(1024, 1) k_pir_batch2(TableDev t, OpSegs segs,
   }
   __syncthreads();
   int cur = G * blockIdx.x + grp < n_stores ? G * blockIdx.x + grp : -1;
+  constexpr int IW = IDX16 ? 2 : 4;   // bytes per index entry
   if(threadIdx.x == 0) {
-    mbar_expect_tx(tbar, (unsigned)(npad * 13));
-    bulk_g2s_chunked(tb, (const char*)t.x, npad * 4, tbar);
-    bulk_g2s_chunked(tb + (size_t)npad * 4, (const char*)t.y, npad * 4, tbar);
-    bulk_g2s_chunked(tb + (size_t)npad * 8, (const char*)t.z, npad * 4, tbar);
-    bulk_g2s_chunked(tb + (size_t)npad * 12, (const char*)t.op, npad, tbar);
+    mbar_expect_tx(tbar, (unsigned)(npad * (3 * IW + 1)));
+    bulk_g2s_chunked(tb, IDX16 ? (const char*)t.x16 : (const char*)t.x, npad * IW, tbar);
+    bulk_g2s_chunked(tb + (size_t)npad * IW, IDX16 ? (const char*)t.y16 : (const char*)t.y, npad * IW, tbar);
+    bulk_g2s_chunked(tb + (size_t)npad * 2 * IW, IDX16 ? (const char*)t.z16 : (const char*)t.z, npad * IW, tbar);
+    bulk_g2s_chunked(tb + (size_t)npad * 3 * IW, (const char*)t.op, npad, tbar);
   }
   if(tid == 0 && cur >= 0) {
     mbar_expect_tx(&bars[SLOTS * grp], (unsigned)sbytes);
     bulk_g2s_chunked((char*)ring[0], (const char*)(stores + cur * store_stride), sbytes, &bars[SLOTS * grp]);
   }
   const int* sx = reinterpret_cast<const int*>(tb);
-  const int* sy = reinterpret_cast<const int*>(tb + (size_t)npad * 4);
-  const int* sz = reinterpret_cast<const int*>(tb + (size_t)npad * 8);
-  const uint8_t* sop = reinterpret_cast<const uint8_t*>(tb + (size_t)npad * 12);
+  const int* sy = reinterpret_cast<const int*>(tb + (size_t)npad * IW);
+  const int* sz = reinterpret_cast<const int*>(tb + (size_t)npad * 2 * IW);
+  const uint8_t* sop = reinterpret_cast<const uint8_t*>(tb + (size_t)npad * 3 * IW);
   mbar_wait(tbar, 0);
   const unsigned a_x = smem_u32(sx), a_y = smem_u32(sy), a_z = smem_u32(sz), a_op = smem_u32(sop);
 
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(1024, 1) k_pir_batch2(TableDev t, OpSegs segs,
     int sweeps = 0;
     bool changed = !(bot && stop_on_bot) && t.n > 0;
     while(changed) {
-      const int f = sweep_table<HAS_DIV, true, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+      const int f = sweep_table<HAS_DIV, IDX16 ? 2 : 1, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
       ++sweeps;
       if(f & 2) *s_bot = 1;
       const int any_chg = nbar_or(bid, nthr, f & 1);
@@ -404,7 +417,9 @@ __global__ void __launch_bounds__(1024, 1) k_pir_batch2(TableDev t, OpSegs segs,
     if(!bot) {   // entailment: the ask loop of is_extractable
       int ok = 1;
       for(int i = tid; i < npad && ok; i += nthr) {
-        const int2 a = S[sx[i]], bb = S[sy[i]], c = S[sz[i]];
+        int2 a, bb, c;
+        if(IDX16) { a = lds_itv(a_S + lds_u16(a_x + 2 * i)); bb = lds_itv(a_S + lds_u16(a_y + 2 * i)); c = lds_itv(a_S + lds_u16(a_z + 2 * i)); }
+        else { a = S[sx[i]]; bb = S[sy[i]]; c = S[sz[i]]; }
         ok = ask_regs(sop[i], Itv(a.x, a.y), Itv(bb.x, bb.y), Itv(c.x, c.y));
       }
       all_ent = nbar_and(bid, nthr, ok);
@@ -474,7 +489,7 @@ __device__ __forceinline__ bool block_fixpoint(const TableDev& t, const OpSegs& 
   bool changed = !bot && t.n > 0;
   int sweeps = 0;
   while(changed) {
-    const int f = sweep_table<HAS_DIV, TABLE_SMEM, false>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+    const int f = sweep_table<HAS_DIV, TABLE_SMEM ? 1 : 0, false>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
     ++sweeps;
     if(f & 2) *s_bot = 1;
     const int any_chg = __syncthreads_or(f & 1);
@@ -679,7 +694,8 @@ struct lpc_batch {
   cudaStream_t last_stream = nullptr;
   bool pending = false;
   int sbytes = 0;
-  int dual = -1;                         // two stores in flight per block (k_pir_batch2): -1 = not decided yet
+  bool dual_idx16 = false;               // ... with the table staged as 16-bit byte offsets
+  int dual = -1;                         // groups per block of k_pir_batch2 (0 = one store per block): -1 = not decided yet
   size_t dual_smem = 0;
   int dual_grid = 0;
   bool plan_ready[2] = {false, false};   // [dense, change-driven]
@@ -693,14 +709,16 @@ struct lpc_batch {
 
 typedef void (*batch_kernel_t)(TableDev, OpSegs, int2*, int, int, uint8_t*, int*, int*, BatchCtl*, int, int, int, const int*, int);
 
-#define LPC_BATCH_G_DEFAULT 4
-static const void* batch2_kernel(bool has_div, int g) {
+static const void* batch2_kernel(bool has_div, int g, bool idx16) {
+#define LPC_B2(G, S) (idx16 ? (has_div ? (const void*)k_pir_batch2<true, G, S, true> : (const void*)k_pir_batch2<false, G, S, true>) \
+                            : (has_div ? (const void*)k_pir_batch2<true, G, S, false> : (const void*)k_pir_batch2<false, G, S, false>))
   switch(g) {
-    case 2: return has_div ? (const void*)k_pir_batch2<true, 2, 2> : (const void*)k_pir_batch2<false, 2, 2>;
-    case 4: return has_div ? (const void*)k_pir_batch2<true, 4, 1> : (const void*)k_pir_batch2<false, 4, 1>;
-    case 8: return has_div ? (const void*)k_pir_batch2<true, 8, 1> : (const void*)k_pir_batch2<false, 8, 1>;
+    case 2: return LPC_B2(2, 2);
+    case 4: return LPC_B2(4, 1);
+    case 8: return LPC_B2(8, 1);
     default: return nullptr;
   }
+#undef LPC_B2
 }
 static batch_kernel_t pick_batch_kernel(bool has_div, bool table_smem, bool cd) {
   if(cd) {
@@ -879,13 +897,15 @@ int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t o
     LPC_CUDA(cudaGetDevice(&dev));
     LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     LPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t tbl = (size_t)t->dev.n_pad * 13;
-    static const int kG[3] = {LPC_BATCH_G_DEFAULT, 4, 2}, kS[3] = {LPC_BATCH_G_DEFAULT == 2 ? 2 : 1, 1, 2};
+    const char* e16 = getenv("LPC_BATCH_IDX16");
+    b->dual_idx16 = t->dev.x16 != nullptr && b->nvars <= 8191 && (!e16 || atoi(e16));
+    const size_t tbl = (size_t)t->dev.n_pad * (b->dual_idx16 ? 7 : 13);
+    static const int kG[3] = {8, 4, 2};   // the most groups whose store slots fit next to the table
     if(want != 0 && t->dev.n_pad >= 2048 && b->n_stores >= 8 * sms) {
       for(int c = 0; c < 3 && !b->dual; ++c) {
-        const int g = want > 0 ? want : kG[c], sl = g == 2 ? 2 : (want > 0 ? 1 : kS[c]);
+        const int g = want > 0 ? want : kG[c], sl = g == 2 ? 2 : 1;
         const size_t need = 256 + (size_t)g * sl * b->sbytes + tbl;
-        const void* kk = batch2_kernel(t->has_div, g);
+        const void* kk = batch2_kernel(t->has_div, g, b->dual_idx16);
         if(!kk || need > (size_t)optin) { if(want > 0) break; else continue; }
         LPC_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         int per_sm = 0;
@@ -905,7 +925,7 @@ int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t o
   LPC_CUDA(cudaEventRecord(b->ev0, st));
   LPC_CUDA(cudaMemcpyAsync(b->d_ctl, b->h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
   if(b->n_stores > 0 && dual) {
-    const void* kk = batch2_kernel(t->has_div, b->dual);
+    const void* kk = batch2_kernel(t->has_div, b->dual, b->dual_idx16);
     TableDev td = t->dev; OpSegs sg = t->opsegs;
     int2* dd = b->d; int ns = b->n_stores, sb = b->sbytes; uint8_t* fl = b->d_flags; int* sw = b->d_sweeps; int* ob = b->d_obj;
     BatchCtl* ct = b->d_ctl; int ov = objective_var, ms = o->max_sweeps, sob = o->stop_on_bot;

@@ -54,6 +54,11 @@ __device__ __forceinline__ int lds_s32(unsigned addr) {
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ int lds_u8(unsigned addr) {
   int v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
