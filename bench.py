@@ -318,7 +318,7 @@ def own_batched(args, rank, world, first_id=None, n_stores=STORES_PER_GPU, steps
         sb = n_stores * net.nvars * 8
         out["e2e"] = {"value": float(dd[0]) / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": sb, "d2h_bytes_per_step": sb + 64,
                       "ms_per_step": float(tt[0]) / n_e2e * 1e3, "steps": n_e2e,
-                      "what": "lpc_batch_fixpoint_host: pinned host stores -> device, fixpoints, stores -> host"}
+                      "what": "lpc_batch_fixpoint_host: pinned host stores -> device, fixpoints, stores -> host (8 chunks on three streams)"}
     batch.close()
     return out
 

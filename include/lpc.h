@@ -180,7 +180,9 @@ typedef struct lpc_batch_result {
 int lpc_batch_fixpoint(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var, lpc_batch_result* r);
 int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var);
 int lpc_batch_collect(lpc_batch* b, lpc_batch_result* r);
-/* Same with HOST buffers ([n_stores][nvars] pairs in, fixpoints out). */
+/* Same with HOST buffers ([n_stores][nvars] pairs in, fixpoints out). A large batch (>= 64 MB) goes through in 8 chunks
+ * on three streams, so that copy-in, fixpoints and copy-out overlap on the full-duplex link; give it pinned memory for
+ * that to happen. Synchronous: the buffer holds the results on return. */
 int lpc_batch_fixpoint_host(lpc_batch* b, int32_t* lbub, const lpc_fixpoint_opts* o, int32_t objective_var,
                             lpc_batch_result* r);
 /* Per-store flags to host: bit0 = bot, bit1 = all propagators entailed. */

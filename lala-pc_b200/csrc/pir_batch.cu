@@ -681,6 +681,7 @@ __global__ void k_batch_init_split(int2* stores, int nvars, int n_stores, const 
 
 using namespace lpc;
 
+#define LPC_BATCH_CHUNKS 8
 struct lpc_batch {
   const lpc_table* table = nullptr;
   int n_stores = 0, nvars = 0;
@@ -705,6 +706,12 @@ struct lpc_batch {
   int* d_seeds = nullptr;                // lpc_batch_set_seeds: variables on which the stores differ from a fixpoint
   int n_seeds = -1;
   lpc::BatchCtl* h_init = nullptr;   // pinned initial control block
+  // pipelined host path (lpc_batch_fixpoint_host): copy-in, compute and copy-out streams, per-chunk control blocks
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t e_in[LPC_BATCH_CHUNKS] = {nullptr}, e_k[LPC_BATCH_CHUNKS] = {nullptr};
+  BatchCtl* d_ctl_chunk = nullptr;   // [LPC_BATCH_CHUNKS]
+  BatchCtl* h_ctl_chunk = nullptr;   // pinned, [2 * LPC_BATCH_CHUNKS]: results, then initial values
+  int n_chunks = 0;                  // chunks of the call in flight (0 = one launch, h_ctl holds the result)
 };
 
 typedef void (*batch_kernel_t)(TableDev, OpSegs, int2*, int, int, uint8_t*, int*, int*, BatchCtl*, int, int, int, const int*, int);
@@ -770,6 +777,12 @@ int lpc_batch_destroy(lpc_batch* b) {
   if(b->h_init) cudaFreeHost(b->h_init);
   if(b->ev0) cudaEventDestroy(b->ev0);
   if(b->ev1) cudaEventDestroy(b->ev1);
+  for(int c = 0; c < LPC_BATCH_CHUNKS; ++c) { if(b->e_in[c]) cudaEventDestroy(b->e_in[c]); if(b->e_k[c]) cudaEventDestroy(b->e_k[c]); }
+  if(b->s_in) cudaStreamDestroy(b->s_in);
+  if(b->s_k) cudaStreamDestroy(b->s_k);
+  if(b->s_out) cudaStreamDestroy(b->s_out);
+  cudaFree(b->d_ctl_chunk);
+  if(b->h_ctl_chunk) cudaFreeHost(b->h_ctl_chunk);
   delete b;
   return LPC_OK;
 }
@@ -845,13 +858,10 @@ int lpc_batch_set_seeds(lpc_batch* b, const int32_t* vars, int32_t n) {
   return LPC_OK;
 }
 
-int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var) {
-  LPC_REQUIRE(b != nullptr, "null batch");
-  LPC_REQUIRE(objective_var < b->nvars, "objective variable out of range");
-  lpc_fixpoint_opts def;
-  if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
+// Launch the batch kernel on stores [first, first + count) of the batch with its own control block (plans are per handle).
+static int batch_launch_range(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var, int first, int count,
+                              BatchCtl* d_ctl, BatchCtl* h_init, cudaStream_t st) {
   const lpc_table* t = b->table;
-  cudaStream_t st = (cudaStream_t)o->stream;
   // LPC_MODE_SWEEP / LPC_MODE_AUTO: every sweep evaluates every record; LPC_MODE_WORKLIST: change-driven (block_fixpoint_cd),
   // seeded by lpc_batch_set_seeds when the caller made that promise. AUTO resolves to dense because that is what is faster
   // on the models measured: on config 4 one halved decision variable floods the 10k-record model within two sweeps (the
@@ -917,32 +927,47 @@ int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t o
   }
   const bool dual = !cd && b->dual >= 2;
   batch_kernel_t k = pick_batch_kernel(t->has_div, b->table_smem[cd], cd);
-  const int grid = dual ? b->dual_grid : b->grid[cd], threads = dual ? 1024 : b->threads[cd];
+  const int threads = dual ? 1024 : b->threads[cd];
+  const int grid = dual ? std::max(1, std::min(b->dual_grid, (count + b->dual - 1) / b->dual)) : std::max(1, std::min(b->grid[cd], count));
   const size_t smem = dual ? b->dual_smem : b->smem[cd];
-  memset(b->h_init, 0, sizeof(BatchCtl));
-  b->h_init->red[3] = LPC_INF;
-  b->h_init->next_store = dual ? b->dual * grid : grid;
-  LPC_CUDA(cudaEventRecord(b->ev0, st));
-  LPC_CUDA(cudaMemcpyAsync(b->d_ctl, b->h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
-  if(b->n_stores > 0 && dual) {
+  memset(h_init, 0, sizeof(BatchCtl));
+  h_init->red[3] = LPC_INF;
+  h_init->next_store = dual ? b->dual * grid : grid;
+  LPC_CUDA(cudaMemcpyAsync(d_ctl, h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
+  int2* dd = b->d + (size_t)first * b->nvars;
+  uint8_t* fl = b->d_flags + first; int* sw = b->d_sweeps + first; int* ob = b->d_obj ? b->d_obj + first : nullptr;
+  if(count > 0 && dual) {
     const void* kk = batch2_kernel(t->has_div, b->dual, b->dual_idx16);
     TableDev td = t->dev; OpSegs sg = t->opsegs;
-    int2* dd = b->d; int ns = b->n_stores, sb = b->sbytes; uint8_t* fl = b->d_flags; int* sw = b->d_sweeps; int* ob = b->d_obj;
-    BatchCtl* ct = b->d_ctl; int ov = objective_var, ms = o->max_sweeps, sob = o->stop_on_bot;
+    int ns = count, sb = b->sbytes;
+    BatchCtl* ct = d_ctl; int ov = objective_var, ms = o->max_sweeps, sob = o->stop_on_bot;
     void* args[] = {&td, &sg, &dd, &ns, &sb, &fl, &sw, &ob, &ct, &ov, &ms, &sob};
     LPC_CUDA(cudaLaunchKernel(kk, dim3(grid), dim3(threads), args, smem, st));
     g_launches++;
   }
-  else if(b->n_stores > 0) {
-    k<<<grid, threads, smem, st>>>(t->dev, t->opsegs, b->d, b->n_stores, b->sbytes, b->d_flags, b->d_sweeps, b->d_obj, b->d_ctl,
+  else if(count > 0) {
+    k<<<grid, threads, smem, st>>>(t->dev, t->opsegs, dd, count, b->sbytes, fl, sw, ob, d_ctl,
                                   objective_var, o->max_sweeps, o->stop_on_bot, b->d_seeds, b->n_seeds);
     g_launches++;
     LPC_CUDA(cudaGetLastError());
   }
+  return LPC_OK;
+}
+
+int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var) {
+  LPC_REQUIRE(b != nullptr, "null batch");
+  LPC_REQUIRE(objective_var < b->nvars, "objective variable out of range");
+  lpc_fixpoint_opts def;
+  if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
+  cudaStream_t st = (cudaStream_t)o->stream;
+  LPC_CUDA(cudaEventRecord(b->ev0, st));
+  int rc = batch_launch_range(b, o, objective_var, 0, b->n_stores, b->d_ctl, b->h_init, st);
+  if(rc) return rc;
   LPC_CUDA(cudaEventRecord(b->ev1, st));
   LPC_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
   b->last_stream = st;
   b->pending = true;
+  b->n_chunks = 0;
   return LPC_OK;
 }
 
@@ -950,6 +975,24 @@ int lpc_batch_collect(lpc_batch* b, lpc_batch_result* r) {
   LPC_REQUIRE(b != nullptr, "null batch");
   LPC_REQUIRE(b->pending, "no batch fixpoint in flight");
   LPC_CUDA(cudaStreamSynchronize(b->last_stream));
+  if(b->n_chunks) {   // pipelined host call: the copy-out stream finishes last; fold the chunks' records into h_ctl
+    LPC_CUDA(cudaStreamSynchronize(b->s_out));
+    LPC_CUDA(cudaStreamSynchronize(b->s_k));
+    BatchCtl acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.red[3] = LPC_INF;
+    for(int c = 0; c < b->n_chunks; ++c) {
+      const BatchCtl& h = b->h_ctl_chunk[c];
+      acc.red[0] += h.red[0]; acc.red[1] += h.red[1]; acc.red[2] += h.red[2];
+      acc.red[3] = std::min(acc.red[3], h.red[3]);
+      acc.sweeps_total += h.sweeps_total; acc.deductions += h.deductions;
+      acc.max_sweeps_seen = std::max(acc.max_sweeps_seen, h.max_sweeps_seen);
+    }
+    *b->h_ctl = acc;
+    // the device-side record stays consistent with a one-launch call (lpc_batch_reduction_device_ptr)
+    LPC_CUDA(cudaMemcpy(b->d_ctl, b->h_ctl, sizeof(BatchCtl), cudaMemcpyHostToDevice));
+    b->n_chunks = 0;
+  }
   b->pending = false;
   if(r) {
     memset(r, 0, sizeof(*r));
@@ -976,12 +1019,64 @@ int lpc_batch_fixpoint(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objecti
 int lpc_batch_fixpoint_host(lpc_batch* b, int32_t* lbub, const lpc_fixpoint_opts* o, int32_t objective_var,
                             lpc_batch_result* r) {
   LPC_REQUIRE(b && lbub, "null argument");
-  cudaStream_t st = o ? (cudaStream_t)o->stream : nullptr;
-  size_t bytes = (size_t)b->n_stores * b->nvars * 8;
-  if(bytes) LPC_CUDA(cudaMemcpyAsync(b->d, lbub, bytes, cudaMemcpyHostToDevice, st));
-  int rc = lpc_batch_fixpoint_async(b, o, objective_var);
-  if(rc) return rc;
-  if(bytes) LPC_CUDA(cudaMemcpyAsync(lbub, b->d, bytes, cudaMemcpyDeviceToHost, st));
+  LPC_REQUIRE(objective_var < b->nvars, "objective variable out of range");
+  lpc_fixpoint_opts def;
+  if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
+  cudaStream_t st = (cudaStream_t)o->stream;
+  const size_t store_bytes = (size_t)b->nvars * 8;
+  const size_t bytes = (size_t)b->n_stores * store_bytes;
+  int sms = 148;
+  if(b->table) sms = std::max(1, b->table->sm_count);
+  const char* ep = getenv("LPC_BATCH_PIPE");
+  const bool pipe = (!ep || atoi(ep)) && b->n_stores >= 2 * LPC_BATCH_CHUNKS * 8 * sms && bytes >= (64u << 20);
+  if(!pipe) {
+    if(bytes) LPC_CUDA(cudaMemcpyAsync(b->d, lbub, bytes, cudaMemcpyHostToDevice, st));
+    int rc = lpc_batch_fixpoint_async(b, o, objective_var);
+    if(rc) return rc;
+    if(bytes) LPC_CUDA(cudaMemcpyAsync(lbub, b->d, bytes, cudaMemcpyDeviceToHost, st));
+    return lpc_batch_collect(b, r);
+  }
+  // Large batch from host memory: the link is full duplex and the stores are independent, so the batch goes through in
+  // LPC_BATCH_CHUNKS chunks on three streams - chunk c + 1 is copied in and chunk c - 1 copied out while chunk c iterates.
+  if(!b->s_in) {
+    LPC_CUDA(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
+    LPC_CUDA(cudaStreamCreateWithFlags(&b->s_k, cudaStreamNonBlocking));
+    LPC_CUDA(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+    for(int c = 0; c < LPC_BATCH_CHUNKS; ++c) {
+      LPC_CUDA(cudaEventCreateWithFlags(&b->e_in[c], cudaEventDisableTiming));
+      LPC_CUDA(cudaEventCreateWithFlags(&b->e_k[c], cudaEventDisableTiming));
+    }
+    LPC_CUDA(cudaMalloc((void**)&b->d_ctl_chunk, LPC_BATCH_CHUNKS * sizeof(BatchCtl)));
+    LPC_CUDA(cudaHostAlloc((void**)&b->h_ctl_chunk, 2 * LPC_BATCH_CHUNKS * sizeof(BatchCtl), cudaHostAllocDefault));
+  }
+  // order after whatever the caller queued on its stream
+  LPC_CUDA(cudaEventRecord(b->ev0, st));
+  LPC_CUDA(cudaStreamWaitEvent(b->s_in, b->ev0, 0));
+  LPC_CUDA(cudaStreamWaitEvent(b->s_k, b->ev0, 0));
+  LPC_CUDA(cudaStreamWaitEvent(b->s_out, b->ev0, 0));
+  LPC_CUDA(cudaEventRecord(b->ev0, b->s_k));
+  const int per = (b->n_stores + LPC_BATCH_CHUNKS - 1) / LPC_BATCH_CHUNKS;
+  int nchunks = 0;
+  for(int c = 0; c < LPC_BATCH_CHUNKS; ++c) {
+    const int first = c * per, count = std::min(per, b->n_stores - first);
+    if(count <= 0) break;
+    char* hp = reinterpret_cast<char*>(lbub) + (size_t)first * store_bytes;
+    char* dp = reinterpret_cast<char*>(b->d) + (size_t)first * store_bytes;
+    LPC_CUDA(cudaMemcpyAsync(dp, hp, (size_t)count * store_bytes, cudaMemcpyHostToDevice, b->s_in));
+    LPC_CUDA(cudaEventRecord(b->e_in[c], b->s_in));
+    LPC_CUDA(cudaStreamWaitEvent(b->s_k, b->e_in[c], 0));
+    int rc = batch_launch_range(b, o, objective_var, first, count, b->d_ctl_chunk + c, b->h_ctl_chunk + LPC_BATCH_CHUNKS + c, b->s_k);
+    if(rc) return rc;
+    LPC_CUDA(cudaMemcpyAsync(b->h_ctl_chunk + c, b->d_ctl_chunk + c, sizeof(BatchCtl), cudaMemcpyDeviceToHost, b->s_k));
+    LPC_CUDA(cudaEventRecord(b->e_k[c], b->s_k));
+    LPC_CUDA(cudaStreamWaitEvent(b->s_out, b->e_k[c], 0));
+    LPC_CUDA(cudaMemcpyAsync(hp, dp, (size_t)count * store_bytes, cudaMemcpyDeviceToHost, b->s_out));
+    ++nchunks;
+  }
+  LPC_CUDA(cudaEventRecord(b->ev1, b->s_k));
+  b->n_chunks = nchunks;
+  b->last_stream = b->s_k;
+  b->pending = true;
   return lpc_batch_collect(b, r);
 }
 

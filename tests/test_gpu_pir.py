@@ -293,6 +293,38 @@ def test_config4_batched_parity(L, O, W):
     assert np.array_equal(buf[ok], want[ok]) and res2.n_bot == res.n_bot
 
 
+def test_batched_host_path_pipelined(L, O, W):
+    """A batch large enough for the chunked three-stream host path (copy-in / iterate / copy-out overlapped) gives what
+    the resident path gives: same stores, flags, reduction record; its first stores equal the CPU checker's."""
+    import torch
+    net = W.config4_base()
+    root, _ = O.pir_fixpoint(net.store, net.records)
+    dec, obj = W.eps_decisions(net.records, root)
+    n = 24576
+    t = L.Table(net.records, net.nvars)
+    b = L.Batch(t, n)
+    b.init_split(root, dec, 0)
+    stores = b.read()
+    res = b.fixpoint(objective_var=obj)
+    want, wflags = b.read(), b.flags()
+    pinned = torch.from_numpy(stores.copy()).pin_memory()
+    b2 = L.Batch(t, n)
+    res2 = b2.fixpoint_host(pinned.data_ptr(), objective_var=obj)
+    got = pinned.numpy()
+    flags2 = b2.flags()
+    assert np.array_equal(flags2, wflags)
+    ok = (wflags & 1) == 0
+    assert ok.any() and (~ok).any()
+    assert np.array_equal(got[ok], want[ok])
+    for f in ("n_bot", "n_solution", "n_unknown", "best_bound"):
+        assert getattr(res2, f) == getattr(res, f), f
+    assert res2.deductions > 0 and res2.sweeps_total > 0
+    ref, rflags, _, _, _ = O.pir_batch_fixpoint(stores[:256], net.records, threads=8)
+    assert np.array_equal(rflags, flags2[:256])
+    okr = (rflags & 1) == 0
+    assert np.array_equal(got[:256][okr], ref[okr])
+
+
 def test_config4_batched_modes_and_seeds(L, O, W):
     """Dense sweeps, change-driven sweeps and change-driven sweeps seeded with the decision variables (the stores are the
     root fixpoint except there) reach the same flags and the same non-failed stores; the seeded run evaluates the fewest
