@@ -388,6 +388,74 @@ def test_batch_tables_larger_than_shared_memory(L, O, W):
     assert np.array_equal(got[ok], want[ok])
 
 
+def planted_soup(rng, nvars, nrec, lo=-3, hi=3):
+    """Random records over all ten operators that hold under a hidden assignment (so that stores around it survive),
+    in random order - NOT sorted by operator."""
+    sol = rng.integers(lo, hi + 1, nvars)
+    sol[: nvars // 4] = rng.integers(0, 2, nvars // 4)       # a pool of 0/1 variables for reified results
+    by_val = {}
+    for v, k in enumerate(sol.tolist()):
+        by_val.setdefault(k, []).append(v)
+    names = list(OPS)
+    recs = []
+    while len(recs) < nrec:
+        name = names[int(rng.integers(0, len(names)))]
+        y, z = (int(v) for v in rng.integers(0, nvars, 2))
+        a, b = int(sol[y]), int(sol[z])
+        if name in ("TDIV", "FDIV", "CDIV", "EDIV") and b == 0:
+            continue
+        if name == "ADD": val = a + b
+        elif name == "MUL": val = a * b
+        elif name == "MIN": val = min(a, b)
+        elif name == "MAX": val = max(a, b)
+        elif name == "EQ": val = int(a == b)
+        elif name == "LEQ": val = int(a <= b)
+        elif name == "FDIV": val = a // b
+        elif name == "CDIV": val = -((-a) // b)
+        elif name == "TDIV": val = abs(a) // abs(b) * (1 if (a >= 0) == (b >= 0) else -1)
+        else:   # EDIV: remainder in [0, |b|)
+            r = a % abs(b)
+            val = (a - r) // b
+        cands = by_val.get(val)
+        if not cands:
+            continue
+        recs.append((OPS[name], cands[int(rng.integers(0, len(cands)))], y, z))
+    return np.array(recs, dtype=np.int32), sol
+
+
+def test_batch_unsorted_all_operator_tables(L, O):
+    """Tables that are NOT sorted by operator (more opcode runs than the per-operator loops take) fall back to per-record
+    dispatch; all ten operators, divisions included, in small batches (one store per block) and in batches large enough
+    for the grouped kernel (several stores in flight per block, 16-bit offset table)."""
+    rng = np.random.default_rng(77)
+    ops = list(OPS.values())
+    n_alive = 0
+    for trial, n_stores in enumerate((96, 96, 1600, 1600)):
+        nvars = 300
+        recs, sol = planted_soup(rng, nvars, 2300)            # >= 2048 records so that the grouped kernel is eligible
+        lo = sol[None, :] - rng.integers(0, 4, (n_stores, nvars))
+        hi = sol[None, :] + rng.integers(0, 4, (n_stores, nvars))
+        stores = np.stack([lo, hi], axis=2).astype(np.int32)
+        bad = rng.random(n_stores) < 0.5                         # half of the stores get one domain moved off the assignment
+        for k in np.flatnonzero(bad):
+            v = int(rng.integers(0, nvars))
+            stores[k, v] = (sol[v] + 5, sol[v] + 9)
+        for k in range(n_stores):
+            stores[k] = O.pir_clamp_reified(stores[k], recs)
+        want, wflags, _, _, _ = O.pir_batch_fixpoint(stores, recs, threads=8)
+        t = L.Table(recs, nvars)
+        b = L.Batch(t, n_stores)
+        b.write(stores)
+        b.fixpoint()
+        got, flags = b.read(), b.flags()
+        assert np.array_equal(flags & 1, wflags & 1), trial
+        ok = (wflags & 1) == 0
+        n_alive += int(ok.sum())
+        assert np.array_equal(got[ok], want[ok]), trial
+        assert np.array_equal(flags[ok], wflags[ok]), trial
+    assert n_alive >= 200
+
+
 @pytest.mark.parametrize("name", list(OPS))
 def test_exhaustive_triples_as_one_network(L, O, name):
     """Every NON-failing interval triple of [-5,5]^3 as a disjoint component of one big network (3 variables and one
