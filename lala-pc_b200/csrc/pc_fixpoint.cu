@@ -147,21 +147,26 @@ __device__ __forceinline__ int tile_step(const PcTableDev& t, Acc& acc, int2* st
     // and every term bound is below 2^24 in magnitude: with at most 32 lanes and |rhs| < 2^30 (checked by the table
     // builder) nothing below can leave int32, so plain integer arithmetic gives what the saturating bound arithmetic
     // of pc_device.cuh gives. Infinite bounds fail the test by their size.
-    const long long p0 = (long long)coef * dom.lb, p1 = (long long)coef * dom.ub;
-    const long long tlo = min(p0, p1), thi = max(p0, p1);
-    const bool small_or_inf = (dom.lb == LPC_MINF || dom.lb > -(1 << 30)) && (dom.ub == LPC_INF || dom.ub < (1 << 30));
-    const bool tame = dom.lb <= dom.ub && (term_lane ? (tlo > -(1 << 24) && thi < (1 << 24)) : small_or_inf);
-    const int ti_lb = term_lane ? (int)tlo : 0, ti_ub = term_lane ? (int)thi : 0;
-    const unsigned wildm = __ballot_sync(FULL, active && lin && !tame);
-    const unsigned heads = __ballot_sync(FULL, active && pos == 0);
+    // tiles without a linear propagator (config 5: =, !=, clauses, abs) skip the products, the tameness vote and the scan
     const int maxlen = __reduce_max_sync(FULL, lin ? len : 0);
-    // segmented inclusive sums of the term bounds, then the propagator's total from its last lane
-    int slb = ti_lb, sub_ = ti_ub;
-    for(int off = 1; off < maxlen; off <<= 1) {
-      const int a = __shfl_up_sync(FULL, slb, off), b = __shfl_up_sync(FULL, sub_, off);
-      if(pos >= off) { slb = wadd(slb, a); sub_ = wadd(sub_, b); }
+    int ti_lb = 0, ti_ub = 0, all_lb = 0, all_ub = 0;
+    unsigned wildm = 0, heads = 0;
+    if(maxlen > 0) {
+      const long long p0 = (long long)coef * dom.lb, p1 = (long long)coef * dom.ub;
+      const long long tlo = min(p0, p1), thi = max(p0, p1);
+      const bool small_or_inf = (dom.lb == LPC_MINF || dom.lb > -(1 << 30)) && (dom.ub == LPC_INF || dom.ub < (1 << 30));
+      const bool tame = dom.lb <= dom.ub && (term_lane ? (tlo > -(1 << 24) && thi < (1 << 24)) : small_or_inf);
+      ti_lb = term_lane ? (int)tlo : 0; ti_ub = term_lane ? (int)thi : 0;
+      wildm = __ballot_sync(FULL, active && lin && !tame);
+      heads = __ballot_sync(FULL, active && pos == 0);
+      // segmented inclusive sums of the term bounds, then the propagator's total from its last lane
+      int slb = ti_lb, sub_ = ti_ub;
+      for(int off = 1; off < maxlen; off <<= 1) {
+        const int a = __shfl_up_sync(FULL, slb, off), b = __shfl_up_sync(FULL, sub_, off);
+        if(pos >= off) { slb = wadd(slb, a); sub_ = wadd(sub_, b); }
+      }
+      all_lb = __shfl_sync(FULL, slb, last); all_ub = __shfl_sync(FULL, sub_, last);
     }
-    const int all_lb = __shfl_sync(FULL, slb, last), all_ub = __shfl_sync(FULL, sub_, last);
     const Itv pd(__shfl_sync(FULL, dom.lb, partner), __shfl_sync(FULL, dom.ub, partner));
     const bool refuted = kind == PC_CLAUSE && lit_ask(coef > 0, dom);
     const unsigned open = __ballot_sync(FULL, kind == PC_CLAUSE && !refuted) & segmask;
