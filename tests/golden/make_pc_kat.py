@@ -161,6 +161,13 @@ ae3 = ["equiv", ["ae", "eq", 0, 5], ["ae", "eq", 1, 5]]
 kat("AbstractElement3.a", "pc_test.cpp:738-744", [D10, D10], [ae3], [D10, D10], ua=False, changed=False)
 kat("AbstractElement3.b", "pc_test.cpp:746-747", [D10, [6, 6]], [ae3], [D10, [6, 6]], ua=False, changed=False)
 kat("AbstractElement4.b", "pc_test.cpp:760-761", [D10, [4, 4]], [ae3], [D10, [4, 4]], ua=False, changed=False)
+# array_int_element(b, [10, 11, 12], c): three propagators (pc_test.cpp:404-418). The decomposition happens in the
+# un-vendored FlatZinc front-end; ASSUMED here: one implication per element, b = i => c = a[i] (Implication,
+# formula.hpp:453-516) - it reproduces all three expected steps.
+elem = [["imply", ["eq", v(0), c(i + 1)], ["eq", v(1), c(10 + i)]] for i in range(3)]
+kat("ElementConstraint1.a", "pc_test.cpp:404-411", [[1, 3], [10, 12]], elem, [[1, 3], [10, 12]], ua=False, changed=False)
+kat("ElementConstraint1.b", "pc_test.cpp:413-414", [[1, 3], [10, 11]], elem, [[1, 2], [10, 11]], ua=False, changed=True)
+kat("ElementConstraint1.c", "pc_test.cpp:416-417", [[1, 2], [11, 11]], elem, [[2, 2], [11, 11]], ua=True, changed=True)
 
 TERM_KATS = [
     dict(name="TermTest.AddTermBinary", source="pc_test.cpp:31-47", store=[D10, D10], term=["add", v(0), v(1)],
