@@ -59,6 +59,11 @@ int lpc_device_init(int device);
 int lpc_device_count(int* out);
 /* Number of kernels of this library launched by the calling process so far (bench.py's `gpu_launches`). */
 int64_t lpc_launch_count(void);
+/* Measurement aid (bench.py's roofline): copy bandwidth of a buffer pair that stays resident in L2 (`bytes` each, e.g.
+ * 32 MB), read + written bytes per second in GB/s, from `iters` timed repetitions of a grid-stride 128-bit copy kernel
+ * after two warm-up passes. The driver provides an HBM figure only; working sets like config 2's store and table live in
+ * L2, so the on-chip ceiling is measured by the build itself. */
+int lpc_measure_l2_copy_gbs(int64_t bytes, int iters, double* gbs);
 
 /* ---- propagator table (PIR::deduce(tell) build step, pir.hpp:326-352) ------------------------------------ */
 /* Upload `n` records (host AoS, the order the caller wants `deduce(i)` / `ask(i)` to index — the façade

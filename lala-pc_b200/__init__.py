@@ -85,6 +85,7 @@ SIGNATURES = {
     "lpc_device_init": (ctypes.c_int, [ctypes.c_int]),
     "lpc_device_count": (ctypes.c_int, [_pint]),
     "lpc_launch_count": (_i64, []),
+    "lpc_measure_l2_copy_gbs": (ctypes.c_int, [_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "lpc_table_create": (ctypes.c_int, [_vp, _i64, _i32, _pvp]),
     "lpc_table_destroy": (ctypes.c_int, [_vp]),
     "lpc_table_size": (_i64, [_vp]),
@@ -281,6 +282,13 @@ class Store:
 
     def __del__(self):
         self.close()
+
+
+def measure_l2_copy_gbs(nbytes=32 << 20, iters=20):
+    """Copy bandwidth (read + write, GB/s) of an L2-resident buffer pair: the on-chip ceiling bench.py reports next to HBM."""
+    g = ctypes.c_double(0.0)
+    _check(_L.lpc_measure_l2_copy_gbs(nbytes, iters, ctypes.byref(g)))
+    return g.value
 
 
 def fixpoint(table, store, **kw):

@@ -103,11 +103,44 @@ __global__ void k_clamp_reified(TableDev t, int2* s) {
 
 using namespace lpc;
 
+// grid-stride 128-bit copy (lpc_measure_l2_copy_gbs)
+__global__ void k_copy16(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n) {
+  for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 extern "C" {
 
 const char* lpc_version(void) { return "lpc-b200 0.1 (sm_100a)"; }
 const char* lpc_last_error(void) { return g_err; }
 int64_t lpc_launch_count(void) { return g_launches.load(); }
+
+int lpc_measure_l2_copy_gbs(int64_t bytes, int iters, double* gbs) {
+  LPC_REQUIRE(gbs != nullptr && bytes >= 4096 && iters >= 1, "bad argument");
+  const size_t n16 = (size_t)bytes / 16;
+  uint4 *src = nullptr, *dst = nullptr;
+  LPC_CUDA(cudaMalloc((void**)&src, n16 * 16));
+  LPC_CUDA(cudaMalloc((void**)&dst, n16 * 16));
+  LPC_CUDA(cudaMemset(src, 1, n16 * 16));
+  int dev = 0, sms = 0;
+  LPC_CUDA(cudaGetDevice(&dev));
+  LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaEvent_t e0, e1;
+  LPC_CUDA(cudaEventCreate(&e0));
+  LPC_CUDA(cudaEventCreate(&e1));
+  const int grid = sms * 8;
+  for(int i = 0; i < 2; ++i) k_copy16<<<grid, 512>>>(src, dst, n16);
+  LPC_CUDA(cudaEventRecord(e0));
+  for(int i = 0; i < iters; ++i) k_copy16<<<grid, 512>>>(src, dst, n16);
+  LPC_CUDA(cudaEventRecord(e1));
+  LPC_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  LPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  g_launches += iters + 2;
+  *gbs = 2.0 * (double)(n16 * 16) * iters / ((double)ms * 1e-3) / 1e9;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(src); cudaFree(dst);
+  return LPC_OK;
+}
 
 int lpc_device_count(int* out) {
   int n = 0;
