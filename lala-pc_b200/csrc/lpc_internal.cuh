@@ -84,6 +84,7 @@ struct lpc_win_plan;                                   // pir_window.cu
 void lpc_win_plan_free(lpc_win_plan* p);
 int lpc_win_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, int* used);
 int lpc_dirty_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o);   // pir_dirty.cu
+int lpc_cluster_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, int* used);   // pir_cluster.cu
 struct lpc_table {
   int device = 0;
   std::vector<lpc_bytecode> host;   // the caller's records, caller's order (load_deduce)
@@ -103,6 +104,7 @@ struct lpc_table {
   int sm_count = 0;
   size_t smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin
   lpc_store* host_store = nullptr;  // device staging store of lpc_fixpoint_host
+  bool cluster_ready = false;       // shared-memory attribute of the cluster kernel set (pir_cluster.cu)
   bool dirty_ready = false;         // occupancy of the change-driven kernel (pir_dirty.cu)
   int dirty_blocks_per_sm[2] = {0, 0};
   bool win_plan_tried = false;      // shared-memory window plan of pir_window.cu (built on first dense launch)

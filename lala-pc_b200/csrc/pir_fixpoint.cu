@@ -463,6 +463,11 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
       LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[tr], var.k[t->has_div ? 1 : 0][tr], TPB, 0));
     t->plan_ready = true;
   }
+  if(!track) {   // a small network runs inside one thread-block cluster, replicas of the store in shared memory (pir_cluster.cu)
+    int used = 0;
+    int rc = lpc_cluster_fixpoint_launch(t, s, o, &used);
+    if(rc || used) return rc;
+  }
   if(o->mode == LPC_MODE_AUTO) return lpc_dirty_fixpoint_launch(t, s, o);
   if(!track) {   // dense sweeps: shared-memory windows when the table has the locality for it (pir_window.cu)
     int used = 0;

@@ -118,10 +118,12 @@ def test_config2_parity_tenth(L, O, W, mode_name):
     check_parity(L, O, twin.records, twin.store, mode, "config2@0.1 twin")
 
 
-@pytest.mark.parametrize("env", [{"LPC_WINDOW": "1"}, {"LPC_VOTE": "0"}, {"LPC_RPT": "12", "LPC_MINB": "3"}])
+@pytest.mark.parametrize("env", [{"LPC_WINDOW": "1"}, {"LPC_VOTE": "0"}, {"LPC_RPT": "12", "LPC_MINB": "3"}, {"LPC_CLUSTER": "1"}])
 def test_alternative_dense_kernels_parity(L, O, W, env):
     """The dense-sweep alternatives that are built but not the default - shared-memory store windows (pir_window.cu),
-    the flag-word + grid.sync barrier, the software-pipelined record loop - reach the same fixpoints."""
+    the flag-word + grid.sync barrier, the software-pipelined record loop, the one-cluster kernel with store replicas in
+    distributed shared memory (pir_cluster.cu; takes config 1 and its failing twin, config 2 is too large for it) - reach
+    the same fixpoints."""
     import os
     import subprocess
     import sys
@@ -132,7 +134,7 @@ def test_alternative_dense_kernels_parity(L, O, W, env):
         "from lala_pc_b200 import workloads as W\n"
         "from oracle import oracle as O\n"
         "L.device_init(0)\n"
-        "for net in (W.config1(), W.config2(0.1), W.config2(0.1).failing_twin()):\n"
+        "for net in (W.config1(), W.config1().failing_twin(), W.config2(0.1), W.config2(0.1).failing_twin()):\n"
         "    want, st = O.pir_fixpoint(net.store, net.records)\n"
         "    t = L.Table(net.records, net.nvars)\n"
         "    s = L.Store(values=net.store)\n"
