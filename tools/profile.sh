@@ -13,3 +13,11 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pi
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pc_fixpoint -s 1 -c 3 -f -o gpurun_out/prof_pc \
   python tools/pc_probe.py 2 > gpurun_out/ncu_pc.log 2>&1
 ls -la gpurun_out
+# summaries on the box (the three .ncu-rep files together exceed gpurun's 64 MiB return limit)
+for k in fixpoint batch pc; do
+  python tools/ncu_summary.py gpurun_out/prof_$k.ncu-rep > gpurun_out/r_${k}_ncu.txt 2>&1
+  ncu -i gpurun_out/prof_$k.ncu-rep --page source --csv > /tmp/src_$k.csv 2>/dev/null
+  python tools/sass_hot.py /tmp/src_$k.csv > gpurun_out/r_${k}_sass_hot.txt 2>&1
+done
+rm -f gpurun_out/prof_pc.ncu-rep gpurun_out/prof_fixpoint.ncu-rep   # the batch capture travels back for reference
+ls -la gpurun_out
