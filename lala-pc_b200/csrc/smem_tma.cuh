@@ -67,15 +67,6 @@ __device__ __forceinline__ int lds_u8(unsigned addr) {
 __device__ __forceinline__ void reds_max(unsigned addr, int v) { asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_min(unsigned addr, int v) { asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-// Predicated joins: `red.shared.max [addr], v` iff v > old (resp. min iff v < old), with the predicate formed inside the
-// asm block so that no branch is generated around the reduction. Used by the branch-free sweep of pir_batch.cu.
-__device__ __forceinline__ void reds_max_if_gt(unsigned addr, int v, int old) {
-  asm volatile("{ .reg .pred p; setp.gt.s32 p, %1, %2; @p red.shared.max.s32 [%0], %1; }" ::"r"(addr), "r"(v), "r"(old) : "memory");
-}
-__device__ __forceinline__ void reds_min_if_lt(unsigned addr, int v, int old) {
-  asm volatile("{ .reg .pred p; setp.lt.s32 p, %1, %2; @p red.shared.min.s32 [%0], %1; }" ::"r"(addr), "r"(v), "r"(old) : "memory");
-}
-
 // Join into the shared-memory store (only called when something tightened or an operand was empty).
 __device__ __forceinline__ int commit_smem(unsigned addr, int2 old, const Itv& nw) {
   int f = 0;
