@@ -42,6 +42,8 @@ __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int
                                          const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z, unsigned a_op,
                                          int tid, int nthr) {
   int f = 0;
+  unsigned macc = 0;
+  bool bacc = false;
   for(int i = s0 + tid; i < s1; i += nthr) {
     int op = OP;
     unsigned ax, ay, az;
@@ -80,10 +82,10 @@ __device__ __forceinline__ int sweep_run(int s0, int s1, unsigned a_S, const int
       reds_max(ay, r2.lb); reds_min(ay + 4, r2.ub);
       reds_max(az, r3.lb); reds_min(az + 4, r3.ub);
     }
-    f |= moved != 0u;
-    f |= ((r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub)) ? 2 : 0;
+    macc |= moved;                                                       // flags are assembled once, after the loop
+    bacc |= (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub);
   }
-  return f;
+  return f | (macc != 0u ? 1 : 0) | (bacc ? 2 : 0);
 }
 // OP = -1: opcode read per record (the division operators, and tables that are not sorted by opcode)
 template <bool HAS_DIV, int TAB, bool BF>

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Run under gpurun: the round-end checks in one go - GPU test suite, smoke(), the default bench line and its summary.
 mkdir -p gpurun_out
-(time python -m pytest tests -m gpu -x -q) 2>&1 | tail -4
+(time python -m pytest tests -m gpu -x -q) 2>&1 | tail -6
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python tools/c1_probe.py 2>/dev/null | head -2
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
