@@ -196,6 +196,57 @@ int lpc_batch_flags(const lpc_batch* b, uint8_t* out);
  * lpc_batch_fixpoint: the payload of the one NCCL all-reduce of the multi-GPU driver. */
 void* lpc_batch_reduction_device_ptr(lpc_batch* b);
 
+/* Multi-GPU: tell the batch its position in the job. The kernel that finishes a lpc_batch_fixpoint then also fills the
+ * all-reduce payload (below) - [0..2] the three counters, [3 + rank] this rank's best bound, every other slot 0 - so that
+ * ONE all-reduce (SUM) of 3 + world int64 delivers the counters and every rank's bound (MIN is taken on the host). */
+int lpc_batch_set_rank(lpc_batch* b, int32_t rank, int32_t world);
+void* lpc_batch_payload_device_ptr(lpc_batch* b, int32_t* n_int64);
+
+/* ---- EPS-native call: the batched mode as a solver uses it ---------------------------------------------------------
+ * Embarrassingly parallel search hands the engine ONE root store, a list of decision variables and a set of subproblem
+ * ids (bit j of an id keeps the lower or the upper half of decision variable j, as lpc_batch_init_split). Nothing but
+ * that crosses the host link on the way in; the subproblem stores are generated on the chip, one per thread group, run
+ * to their fixpoint (the loop of tests/pir_test.cpp:60-62 per store, over the shared table of pir.hpp:182-195), and on
+ * the way out come the per-subproblem flags, the reduction record and ONLY the stores that did not fail, compacted -
+ * is_extractable / extract (pir.hpp:873-898) for the whole batch. In LPC_MODE_AUTO (default) the propagators that
+ * PIR::ask (pir.hpp:417-438) already entails on the root are dropped from the table first (what deinterpret's
+ * remove_entailed does, pir.hpp:912-925): every subproblem is a tightening of the root, so they stay entailed and can
+ * never change a store. LPC_MODE_SWEEP keeps them (every sweep evaluates every propagator, the reference's work unit).
+ * The model must fit the shared memory of an SM (<= 8191 variables, table + store slots <= 227 KB). */
+typedef struct lpc_eps lpc_eps;
+typedef struct lpc_eps_result {
+  int64_t n_bot, n_solution, n_unknown;   /* as lpc_batch_result */
+  int32_t best_bound;                     /* min over non-failed stores of lb(objective_var); INT32_MAX if none */
+  int32_t max_sweeps_seen;
+  int64_t sweeps_total;
+  int64_t deductions;                     /* deduce() evaluations executed */
+  int64_t n_survivors;                    /* non-failed stores (may exceed the survivor capacity: then only that many were kept) */
+  int32_t n_live_records;                 /* propagators left in the table after dropping those entailed on the root */
+  float device_ms;
+} lpc_eps_result;
+
+int lpc_eps_create(const lpc_table* t, int32_t max_subproblems, int32_t survivor_cap, lpc_eps** out);
+int lpc_eps_destroy(lpc_eps* e);
+int lpc_eps_set_rank(lpc_eps* e, int32_t rank, int32_t world);
+void* lpc_eps_payload_device_ptr(lpc_eps* e, int32_t* n_int64);
+/* Everything in one call, from and to HOST buffers: root_lbub (nvars pairs), decision_vars, ids (n, or NULL for
+ * first_id + k) in; flags (n bytes: bit0 = bot, bit1 = all propagators entailed), up to max_survivors non-failed stores
+ * (nvars pairs each) with their subproblem index k in [0, n) out (in no particular order; *n_written of them). Any output
+ * pointer may be NULL. Synchronous. */
+int lpc_eps_solve_host(lpc_eps* e, const int32_t* root_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                       const int64_t* ids, int64_t first_id, int32_t n, const lpc_fixpoint_opts* o, int32_t objective_var,
+                       uint8_t* flags, int32_t* survivors_lbub, int32_t* survivor_index, int32_t max_survivors,
+                       int32_t* n_written, lpc_eps_result* r);
+/* The same in steps, for a problem that stays resident on the device between runs (bench.py's device-timed figure). */
+int lpc_eps_upload(lpc_eps* e, const int32_t* root_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                   const int64_t* ids, int64_t first_id, int32_t n);
+int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_var);
+int lpc_eps_collect(lpc_eps* e, lpc_eps_result* r);
+int lpc_eps_download(lpc_eps* e, uint8_t* flags, int32_t* survivors_lbub, int32_t* survivor_index, int32_t max_survivors,
+                     int32_t* n_written);
+/* Sweeps each subproblem took (n ints), informational. */
+int lpc_eps_sweeps(lpc_eps* e, int32_t* out);
+
 /* ---- in-kernel search over the batch (snapshot / restore + branching next to the fixpoint) ---------
  * Every store of the batch is the root of a depth-first search run by ONE thread block: propagate (the fixpoint above),
  * then branch on the first non-singleton variable of `branch_vars` (input order) by bisection, lower half first; the

@@ -67,6 +67,16 @@ class BatchResult(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class EpsResult(ctypes.Structure):
+    _fields_ = [("n_bot", ctypes.c_int64), ("n_solution", ctypes.c_int64), ("n_unknown", ctypes.c_int64),
+                ("best_bound", ctypes.c_int32), ("max_sweeps_seen", ctypes.c_int32), ("sweeps_total", ctypes.c_int64),
+                ("deductions", ctypes.c_int64), ("n_survivors", ctypes.c_int64), ("n_live_records", ctypes.c_int32),
+                ("device_ms", ctypes.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(nvcc, sm_100a). There is no CPU fallback.")
@@ -127,6 +137,19 @@ SIGNATURES = {
                                                ctypes.POINTER(BatchResult)]),
     "lpc_batch_flags": (ctypes.c_int, [_vp, _pu8]),
     "lpc_batch_reduction_device_ptr": (_vp, [_vp]),
+    "lpc_batch_set_rank": (ctypes.c_int, [_vp, _i32, _i32]),
+    "lpc_batch_payload_device_ptr": (_vp, [_vp, _pi32]),
+    "lpc_eps_create": (ctypes.c_int, [_vp, _i32, _i32, _pvp]),
+    "lpc_eps_destroy": (ctypes.c_int, [_vp]),
+    "lpc_eps_set_rank": (ctypes.c_int, [_vp, _i32, _i32]),
+    "lpc_eps_payload_device_ptr": (_vp, [_vp, _pi32]),
+    "lpc_eps_solve_host": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _i32, ctypes.POINTER(FixpointOpts), _i32,
+                                          _vp, _vp, _vp, _i32, _pi32, ctypes.POINTER(EpsResult)]),
+    "lpc_eps_upload": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _i32]),
+    "lpc_eps_run_async": (ctypes.c_int, [_vp, ctypes.POINTER(FixpointOpts), _i32]),
+    "lpc_eps_collect": (ctypes.c_int, [_vp, ctypes.POINTER(EpsResult)]),
+    "lpc_eps_download": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _pi32]),
+    "lpc_eps_sweeps": (ctypes.c_int, [_vp, _vp]),
     "lpc_search_default_opts": (None, [ctypes.POINTER(SearchOpts)]),
     "lpc_batch_search": (ctypes.c_int, [_vp, _vp, _i32, ctypes.POINTER(SearchOpts), ctypes.POINTER(SearchResult), _vp]),
     # include/lpc_pc.h
@@ -460,6 +483,16 @@ class Batch:
     def reduction_device_ptr(self):
         return _L.lpc_batch_reduction_device_ptr(self._h)
 
+    def set_rank(self, rank, world):
+        _check(_L.lpc_batch_set_rank(self._h, rank, world))
+
+    @property
+    def payload(self):
+        """(device address, length) of the int64 all-reduce payload (include/lpc.h: lpc_batch_set_rank)."""
+        n = ctypes.c_int32(0)
+        p = _L.lpc_batch_payload_device_ptr(self._h, ctypes.byref(n))
+        return p, n.value
+
     def search(self, branch_vars, objective_var=-1, max_nodes=0, max_depth=64, stream=0, want_per_store=True,
                change_driven=True):
         """Depth-first search from every store of the batch (include/lpc.h: lpc_batch_search).
@@ -477,6 +510,97 @@ class Batch:
     def close(self):
         if getattr(self, "_h", None):
             _L.lpc_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Eps:
+    """The EPS-native call (include/lpc.h: lpc_eps_*): root store + decision variables + subproblem ids in; flags, the
+    reduction record and the compacted non-failed stores out. `survivor_cap` bounds the stores kept on the device."""
+
+    def __init__(self, table, max_subproblems, survivor_cap=None):
+        self._h = ctypes.c_void_p()
+        self.table, self.nvars, self.max_n = table, table.nvars, max_subproblems
+        self.survivor_cap = max_subproblems if survivor_cap is None else survivor_cap
+        _check(_L.lpc_eps_create(table._h, max_subproblems, self.survivor_cap, ctypes.byref(self._h)))
+        self.n = 0
+
+    def set_rank(self, rank, world):
+        _check(_L.lpc_eps_set_rank(self._h, rank, world))
+
+    @property
+    def payload(self):
+        n = ctypes.c_int32(0)
+        p = _L.lpc_eps_payload_device_ptr(self._h, ctypes.byref(n))
+        return p, n.value
+
+    @staticmethod
+    def _ptr(a):
+        return None if a is None else (a if isinstance(a, int) else a.ctypes.data)
+
+    def solve_host(self, root, decision_vars, ids=None, first_id=0, n=None, objective_var=-1, flags=None, survivors=None,
+                   survivor_index=None, **kw):
+        """One call from host buffers. `root`, `flags`, `survivors`, `survivor_index` may be numpy arrays or raw (pinned)
+        addresses; returns (EpsResult, number of survivor stores written)."""
+        if not isinstance(root, int):
+            root = np.ascontiguousarray(root, dtype=np.int32)
+        d = np.ascontiguousarray(decision_vars, dtype=np.int32)
+        if ids is not None and not isinstance(ids, int):
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            n = len(ids) if n is None else n
+        assert n is not None
+        self.n = n
+        max_surv = 0
+        if survivors is not None:
+            max_surv = self.survivor_cap if isinstance(survivors, int) else len(survivors)
+        o, r, nw = _opts(**kw), EpsResult(), ctypes.c_int32(0)
+        _check(_L.lpc_eps_solve_host(self._h, self._ptr(root), d.ctypes.data, d.shape[0], self._ptr(ids), first_id, n,
+                                     ctypes.byref(o), objective_var, self._ptr(flags), self._ptr(survivors),
+                                     self._ptr(survivor_index), max_surv, ctypes.byref(nw), ctypes.byref(r)))
+        return r, nw.value
+
+    def upload(self, root, decision_vars, ids=None, first_id=0, n=None):
+        root = np.ascontiguousarray(root, dtype=np.int32)
+        d = np.ascontiguousarray(decision_vars, dtype=np.int32)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            n = len(ids) if n is None else n
+        self.n = n
+        _check(_L.lpc_eps_upload(self._h, root.ctypes.data, d.ctypes.data, d.shape[0], self._ptr(ids), first_id, n))
+
+    def run_async(self, objective_var=-1, **kw):
+        o = _opts(**kw)
+        _check(_L.lpc_eps_run_async(self._h, ctypes.byref(o), objective_var))
+
+    def collect(self):
+        r = EpsResult()
+        _check(_L.lpc_eps_collect(self._h, ctypes.byref(r)))
+        return r
+
+    def run(self, objective_var=-1, **kw):
+        self.run_async(objective_var, **kw)
+        return self.collect()
+
+    def download(self, max_survivors=None):
+        """(flags u8 [n], survivors int32 [k, nvars, 2], survivor_index int32 [k]) of the last collected run."""
+        cap = self.survivor_cap if max_survivors is None else max_survivors
+        flags = np.empty(max(self.n, 1), dtype=np.uint8)
+        surv = np.empty((max(cap, 1), self.nvars, 2), dtype=np.int32)
+        idx = np.empty(max(cap, 1), dtype=np.int32)
+        nw = ctypes.c_int32(0)
+        _check(_L.lpc_eps_download(self._h, flags.ctypes.data, surv.ctypes.data, idx.ctypes.data, cap, ctypes.byref(nw)))
+        return flags[:self.n], surv[:nw.value], idx[:nw.value]
+
+    def sweeps(self):
+        out = np.empty(max(self.n, 1), dtype=np.int32)
+        _check(_L.lpc_eps_sweeps(self._h, out.ctypes.data))
+        return out[:self.n]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _L.lpc_eps_destroy(self._h)
             self._h = None
 
     def __del__(self):

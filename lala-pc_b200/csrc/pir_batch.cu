@@ -14,6 +14,7 @@
 //     per batch: 4 x int64 reduction record, the payload of the single NCCL all-reduce of the multi-GPU driver.
 #include "lpc_internal.cuh"
 #include "smem_tma.cuh"
+#include "batch_internal.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -21,13 +22,6 @@
 
 namespace lpc {
 
-struct BatchCtl {
-  long long red[4];            // n_solution, n_bot, n_unknown, best_bound (min)
-  long long sweeps_total;
-  long long deductions;
-  int max_sweeps_seen;
-  int next_store;              // dynamic scheduler
-};
 
 
 // ---- one dense sweep of the table over the store at shared address a_S ------------------------------------------------
@@ -683,42 +677,15 @@ __global__ void k_batch_init_split(int2* stores, int nvars, int n_stores, const 
   }
 }
 
+// BatchCtl::payload from the reduction record (batch_internal.cuh), for the kernels that do not write it themselves.
+__global__ void k_publish_payload(BatchCtl* ctl) {
+  ctl->payload[0] = ctl->red[0]; ctl->payload[1] = ctl->red[1]; ctl->payload[2] = ctl->red[2];
+  ctl->payload[3 + ctl->rank] = ctl->red[3];
+}
+
 } // namespace lpc
 
 using namespace lpc;
-
-#define LPC_BATCH_CHUNKS 8
-struct lpc_batch {
-  const lpc_table* table = nullptr;
-  int n_stores = 0, nvars = 0;
-  int2* d = nullptr;
-  uint8_t* d_flags = nullptr;
-  int* d_sweeps = nullptr;
-  int* d_obj = nullptr;
-  BatchCtl* d_ctl = nullptr;
-  BatchCtl* h_ctl = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaStream_t last_stream = nullptr;
-  bool pending = false;
-  int sbytes = 0;
-  bool dual_idx16 = false;               // ... with the table staged as 16-bit byte offsets
-  int dual = -1;                         // groups per block of k_pir_batch2 (0 = one store per block): -1 = not decided yet
-  size_t dual_smem = 0;
-  int dual_grid = 0;
-  bool plan_ready[2] = {false, false};   // [dense, change-driven]
-  bool table_smem[2] = {false, false};
-  size_t smem[2] = {0, 0};
-  int threads[2] = {0, 0}, grid[2] = {0, 0};
-  int* d_seeds = nullptr;                // lpc_batch_set_seeds: variables on which the stores differ from a fixpoint
-  int n_seeds = -1;
-  lpc::BatchCtl* h_init = nullptr;   // pinned initial control block
-  // pipelined host path (lpc_batch_fixpoint_host): copy-in, compute and copy-out streams, per-chunk control blocks
-  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-  cudaEvent_t e_in[LPC_BATCH_CHUNKS] = {nullptr}, e_k[LPC_BATCH_CHUNKS] = {nullptr};
-  BatchCtl* d_ctl_chunk = nullptr;   // [LPC_BATCH_CHUNKS]
-  BatchCtl* h_ctl_chunk = nullptr;   // pinned, [2 * LPC_BATCH_CHUNKS]: results, then initial values
-  int n_chunks = 0;                  // chunks of the call in flight (0 = one launch, h_ctl holds the result)
-};
 
 typedef void (*batch_kernel_t)(TableDev, OpSegs, int2*, int, int, uint8_t*, int*, int*, BatchCtl*, int, int, int, const int*, int);
 
@@ -789,6 +756,7 @@ int lpc_batch_destroy(lpc_batch* b) {
   if(b->s_out) cudaStreamDestroy(b->s_out);
   cudaFree(b->d_ctl_chunk);
   if(b->h_ctl_chunk) cudaFreeHost(b->h_ctl_chunk);
+  cudaFree(b->d_ptab); cudaFree(b->d_phdr); cudaFree(b->d_root);
   delete b;
   return LPC_OK;
 }
@@ -800,6 +768,7 @@ int lpc_batch_write(lpc_batch* b, int32_t first, int32_t n, const int32_t* lbub)
   LPC_REQUIRE(b && (n == 0 || lbub), "null argument");
   LPC_REQUIRE(first >= 0 && n >= 0 && (long long)first + n <= b->n_stores, "range out of bounds");
   if(n) LPC_CUDA(cudaMemcpy(b->d + (size_t)first * b->nvars, lbub, (size_t)n * b->nvars * 8, cudaMemcpyHostToDevice));
+  b->root_valid = false;   // arbitrary images: no common root is known any more
   return LPC_OK;
 }
 
@@ -844,6 +813,10 @@ static int batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_
   k_batch_init_split<<<std::min(b->n_stores, 148 * 16), 256>>>(b->d, b->nvars, b->n_stores, d_base, d_dec, n_decisions, first_id, d_ids);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
+  // every image of the batch is now a tightening of `base`: LPC_MODE_AUTO may drop the propagators entailed on it
+  if(!b->d_root) LPC_CUDA(cudaMalloc((void**)&b->d_root, std::max<size_t>((size_t)b->nvars * 8, 16)));
+  LPC_CUDA(cudaMemcpy(b->d_root, d_base, (size_t)b->nvars * 8, cudaMemcpyDeviceToDevice));
+  b->root_valid = true;
   LPC_CUDA(cudaDeviceSynchronize());
   cudaFree(d_base);
   cudaFree(d_dec);
@@ -874,6 +847,11 @@ static int batch_launch_range(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
   // seeded change-driven run still evaluates 62 % of the dense run's propagators) and the flagging costs more than it saves
   // (33 vs 15.5 ms per 65,536 stores).
   const int cd = o->mode == LPC_MODE_WORKLIST ? 1 : 0;
+  if(!cd) {   // dense sweeps, large batch, model fits an SM: the grouped kernel over the packed table (pir_eps.cu)
+    int used = 0;
+    int rc = lpc_group_launch_resident(b, o, objective_var, first, count, d_ctl, h_init, st, &used);
+    if(rc || used) return rc;
+  }
   // launch plan: computed once per batch handle and mode (device attribute / occupancy queries are slow driver calls)
   if(!b->plan_ready[cd]) {
     int dev = 0, sms = 0, optin = 0;
@@ -939,6 +917,7 @@ static int batch_launch_range(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
   memset(h_init, 0, sizeof(BatchCtl));
   h_init->red[3] = LPC_INF;
   h_init->next_store = dual ? b->dual * grid : grid;
+  h_init->rank = b->rank; h_init->world = b->world;
   LPC_CUDA(cudaMemcpyAsync(d_ctl, h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
   int2* dd = b->d + (size_t)first * b->nvars;
   uint8_t* fl = b->d_flags + first; int* sw = b->d_sweeps + first; int* ob = b->d_obj ? b->d_obj + first : nullptr;
@@ -957,7 +936,23 @@ static int batch_launch_range(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
     g_launches++;
     LPC_CUDA(cudaGetLastError());
   }
+  // these kernels leave the all-reduce payload to a one-thread epilogue (the grouped kernel's last block writes it itself)
+  k_publish_payload<<<1, 1, 0, st>>>(d_ctl);
+  g_launches++;
+  LPC_CUDA(cudaGetLastError());
   return LPC_OK;
+}
+
+int lpc_batch_set_rank(lpc_batch* b, int32_t rank, int32_t world) {
+  LPC_REQUIRE(b && world >= 1 && world <= LPC_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
+  b->rank = rank; b->world = world;
+  return LPC_OK;
+}
+
+void* lpc_batch_payload_device_ptr(lpc_batch* b, int32_t* n_int64) {
+  if(!b) return nullptr;
+  if(n_int64) *n_int64 = 3 + b->world;
+  return (void*)b->d_ctl->payload;
 }
 
 int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var) {
@@ -1029,6 +1024,7 @@ int lpc_batch_fixpoint_host(lpc_batch* b, int32_t* lbub, const lpc_fixpoint_opts
   lpc_fixpoint_opts def;
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   cudaStream_t st = (cudaStream_t)o->stream;
+  b->root_valid = false;   // the images come from the caller: no common root is known
   const size_t store_bytes = (size_t)b->nvars * 8;
   const size_t bytes = (size_t)b->n_stores * store_bytes;
   int sms = 148;

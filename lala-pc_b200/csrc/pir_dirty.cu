@@ -11,6 +11,13 @@
 //     byte map for the following sweep;
 //   * from then on a warp first reads the flags of its groups (one coalesced byte load per 32 iterations) and only
 //     evaluates flagged groups, marking as it tightens. Three byte maps rotate: read, write, being cleared.
+//   * entailment-driven elimination in EVERY phase: each evaluation also runs PIR::ask
+//     (pir.hpp:417-438) on the bounds it just computed, and a group whose 64 records are all entailed is struck from a
+//     fourth byte map ("live") for the rest of the fixpoint - the use the reference makes of ask() in
+//     deinterpret(env, remove_entailed) (pir.hpp:912-925). An entailed propagator holds on every point of its box, a
+//     sound propagator can then remove nothing from any sub-box, and entailment survives tightening, so a struck group
+//     could never change the store again. Config 2: 99.7 % of the `*` and 99.9 % of the `<=` records are entailed after
+//     one sweep (both factors fixed / relation decided), i.e. half the table is gone from the third sweep on.
 // Invariant: a change of v after the last evaluation of a record on v always flags that record's group for the next
 // sweep (also when the evaluation read a stale L1 copy), so at the sweep that changes nothing every record has been
 // evaluated on the final value of its variables: the store is the common fixpoint, the same as Gauss-Seidel's
@@ -43,6 +50,7 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
     int f = 0;
     for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = store[i]; f |= v.x > v.y; }
     for(long long i = gtid; i < 3LL * map_stride; i += gthreads) dmap[i] = 0;
+    for(long long i = gtid; i < map_stride; i += gthreads) dmap[3LL * map_stride + i] = 1;   // every group live
     bot = grid_vote_barrier(ctl->bar, nbar++, false, f != 0, &s_vote).bot;
   }
   // this block's fraction of every segment: its rank in SM order (grid_barrier.cuh)
@@ -50,7 +58,8 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
   if(sm_order) { const SmRank r = sm_rank_resolve(ctl->sm_slots, sm_slot); bid = r.below + r.slot; }
   int sweeps = 0, dense = 0;
   bool any_changed = false;
-  unsigned long long deductions = 0;
+  unsigned evals_total = 0;             // records this lane evaluated over the whole fixpoint
+  unsigned char* live = dmap + 3 * (size_t)map_stride;
   bool done = (bot && stop_on_bot) || t.n == 0;
   int phase = 0;   // 0: dense, no marking; 1: dense + marking; 2: flagged groups only + marking
   while(!done) {
@@ -67,6 +76,7 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
     // One warp-step: this lane's unit u (2 records) of a 64-record group, evaluated iff `active`; then the group's flags.
     auto eval_unit = [&](int u, bool active) {
       int g1 = 0;
+      bool ent = active;                      // both records of this lane entailed on the bounds just computed
       int cv[6] = {-1, -1, -1, -1, -1, -1};   // variables this lane tightened (2 records x 3 operands)
       if(active) {
         const uchar2 o = reinterpret_cast<const uchar2*>(t.op)[u];
@@ -80,6 +90,7 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
           const int2 a = h ? a1v : a0v, b = h ? b1v : b0v, c = h ? c1v : c0v;
           Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
           deduce_regs<HAS_DIV>(op, r1, r2, r3);
+          ent &= ask_regs(op, r1, r2, r3);
           const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > b.x) | (r2.ub < b.y) | (r3.lb > c.x) | (r3.ub < c.y)
                           | (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
           if(slow) {
@@ -124,7 +135,9 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
         }
       }
       if(grp_changed) ++my_groups;
-      ++my_evals;
+      if(active) my_evals += 2;
+      // all 64 records of a fully covered group entailed: strike it (a group cut by a segment or share boundary stays)
+      if(__all_sync(0xffffffffu, ent) && lane == 0) live[u >> 5] = 0;
     };
     if(phase == 2 && strided) {
       // Flagged sweeps, groups dealt to the warps of the whole grid round-robin: flagged groups cluster (a change moves
@@ -134,7 +147,7 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
       const int n_units = (int)(t.n_pad / 2);
       for(long long base = gwarp; base < n_groups; base += 32 * gwarps) {
         const long long g = base + (long long)lane * gwarps;
-        unsigned need = __ballot_sync(0xffffffffu, g < n_groups && dcur[g] != 0);
+        unsigned need = __ballot_sync(0xffffffffu, g < n_groups && dcur[g] != 0 && live[g] != 0);
         while(need) {
           const int k = __ffs(need) - 1;
           need &= need - 1;
@@ -155,11 +168,12 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
       const int a0 = u0 & ~31;
       const int niter = (u1 - a0 + DTPB - 1) / DTPB;
       for(int kb = 0; kb < niter; kb += 32) {
-        unsigned need = 0xffffffffu;
-        if(phase == 2) {
+        unsigned need;
+        {
           const int k = kb + lane;
           const int g = (a0 + warp * 32 + k * DTPB) >> 5;
-          const int fl = (k < niter && g < n_groups) ? dcur[g] : 0;
+          const bool in = k < niter && g < n_groups;
+          const int fl = in ? (live[g] != 0 && (phase < 2 || dcur[g] != 0)) : 0;
           need = __ballot_sync(0xffffffffu, fl != 0);
         }
         const int kend = min(niter, kb + 32);
@@ -175,20 +189,22 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
     const bool any_bot = __syncthreads_or(f & 2);
     const GridVote v = grid_count_barrier(ctl->bar, nbar++, s_cnt, any_bot, &s_vote);
     ++sweeps;
-    if(phase < 2) { ++dense; deductions += (unsigned long long)t.n; }
-    else if(lane == 0 && my_evals) atomicAdd(&ctl->deductions, 64ull * my_evals);
+    if(phase < 2) ++dense;
+    evals_total += my_evals;
     bot |= v.bot;
     any_changed |= v.changed;
     if(!v.changed || (bot && stop_on_bot) || (max_sweeps && sweeps >= max_sweeps)) done = true;
     else if(phase == 0) { if(v.n_changed <= switch_groups) phase = 1; }
     else phase = 2;
   }
+  // deduce() evaluations executed (one atomic per warp for the whole fixpoint)
+  evals_total = __reduce_add_sync(0xffffffffu, evals_total);
+  if(lane == 0 && evals_total) atomicAdd(&ctl->deductions, (unsigned long long)evals_total);
   if(blockIdx.x == 0 && tid == 0) {
     ctl->sweeps = sweeps;
     ctl->dense_sweeps = dense;
     ctl->has_changed = any_changed;
     ctl->is_bot = bot;
-    atomicAdd(&ctl->deductions, deductions);
   }
 }
 
@@ -202,11 +218,11 @@ int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opt
   const long long n_pad = t->dev.n_pad;
   const int n_groups = (int)((n_pad + 63) / 64);
   const int map_stride = (n_groups + 15) / 16 * 16;
-  if(s->dirty_cap < 3LL * map_stride) {
+  if(s->dirty_cap < 4LL * map_stride) {   // three rotating change maps + the live map
     cudaFree(s->d_dirty);
     s->d_dirty = nullptr; s->dirty_cap = 0;
-    LPC_CUDA(cudaMalloc((void**)&s->d_dirty, 3 * (size_t)map_stride));
-    s->dirty_cap = 3LL * map_stride;
+    LPC_CUDA(cudaMalloc((void**)&s->d_dirty, 4 * (size_t)map_stride));
+    s->dirty_cap = 4LL * map_stride;
   }
   if(!t->dirty_ready) {
     // the kernel's working set is the store window of its SM's table fractions: all of the unified L1 / shared memory

@@ -1,0 +1,651 @@
+// pir_eps.cu — batched mode, second generation: the grouped block kernel over a PACKED table, and the EPS-native call
+// (sm_100a).
+//
+// What a solver does with the batched mode is embarrassingly parallel search (EPS): one root store, a list of decision
+// variables, 2^k subproblem ids; it wants to know which subproblems fail, which are solutions, the best objective bound,
+// and the stores of the few that survive - not 1 GiB of store images in each direction. So here
+//   * the subproblem stores are GENERATED on the chip: a group copies the root image (L2-resident, 16 KB) into its
+//     shared-memory slot with one bulk copy and halves the decision variables according to the bits of its id;
+//   * only the stores that do NOT fail are written out, compacted (an atomic slot counter + one bulk store each), with
+//     their subproblem index - the device-side form of `extract` (pir.hpp:890-898) after `is_extractable`
+//     (pir.hpp:873-884);
+//   * propagators that are already entailed on the ROOT store are dropped from the table before it is staged in shared
+//     memory (`ask`, pir.hpp:417-438, used the way deinterpret(env, remove_entailed) uses it, pir.hpp:912-925): every
+//     subproblem store is a tightening of the root, entailment survives tightening, and an entailed propagator can never
+//     change a store again. The root of an EPS split is usually itself a fixpoint, where every
+//     multiplication with fixed factors and every decided reified comparison is entailed - half of config 4's table.
+// The table is staged as 8-byte packed records {x16 | y16 << 16, z16 | op << 16} (byte offsets into a store image), one
+// run per operator, runs padded to an even length by repeating their last record (evaluating a propagator twice is
+// harmless), so that a thread fetches TWO records with one 128-bit shared-memory load and has six gathers in flight
+// before the first rule. The same kernel serves lpc_batch_fixpoint on resident store images (EPS = false).
+#include "lpc_internal.cuh"
+#include "smem_tma.cuh"
+#include "batch_internal.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+
+namespace lpc {
+
+#define LPC_PK_MAXRUN LPC_MAX_OPSEG
+struct PackedHdr {
+  int np;                          // packed records (even; padding duplicates included)
+  int nruns;
+  int start[LPC_PK_MAXRUN + 1];    // first packed record of each run (even); start[nruns] = np
+  int op[LPC_PK_MAXRUN];           // device opcode of the run; -1 = mixed (opcode taken from each record)
+  int n_live;                      // propagators kept (not entailed on the root)
+  int n_total;                     // propagators of the table
+};
+
+// ---- table packer: one block; keeps table order inside every run ------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, const int2* root, uint2* out, PackedHdr* hdr) {
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nseg = segs.n == 0 ? 1 : segs.n;
+  int base = 0, nruns = 0, n_live = 0;
+  for(int r = 0; r < nseg; ++r) {
+    const int s0 = segs.n == 0 ? 0 : segs.start[r], s1 = segs.n == 0 ? (int)t.n : segs.start[r + 1];
+    const int run_op = segs.n == 0 ? -1 : (int)segs.op[r];
+    const int run_begin = base;
+    for(int i0 = s0; i0 < s1; i0 += 1024) {
+      const int i = i0 + tid;
+      bool live = i < s1;
+      int op = D_NOP, x = 0, y = 0, z = 0;
+      if(live) {
+        op = t.op[i]; x = t.x[i]; y = t.y[i]; z = t.z[i];
+        if(op == D_NOP) live = false;
+        else if(root) {
+          const int2 a = root[x], b = root[y], c = root[z];
+          // an empty operand: keep the record (the store is at bot anyway, nothing is entailed on bot)
+          const bool any_bot = (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
+          if(!any_bot && ask_regs(op, Itv(a.x, a.y), Itv(b.x, b.y), Itv(c.x, c.y))) live = false;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if(lane == 0) s_warp[warp] = __popc(m);
+      __syncthreads();
+      int before = 0, total = 0;
+      for(int w = 0; w < 32; ++w) { const int c = s_warp[w]; if(w < warp) before += c; total += c; }
+      if(live) {
+        const int pos = base + before + __popc(m & ((1u << lane) - 1));
+        out[pos] = make_uint2((unsigned)(8 * x) | ((unsigned)(8 * y) << 16), (unsigned)(8 * z) | ((unsigned)op << 16));
+      }
+      base += total;
+      __syncthreads();
+    }
+    n_live += base - run_begin;
+    if((base - run_begin) & 1) {   // odd run: repeat its last record
+      if(tid == 0) out[base] = out[base - 1];
+      ++base;
+      __syncthreads();
+    }
+    if(base > run_begin) {
+      if(tid == 0) { hdr->start[nruns] = run_begin; hdr->op[nruns] = run_op; }
+      ++nruns;
+    }
+  }
+  if(tid == 0) {
+    hdr->start[nruns] = base;
+    hdr->np = base; hdr->nruns = nruns; hdr->n_live = n_live; hdr->n_total = (int)t.n;
+  }
+}
+
+// ---- the grouped kernel ---------------------------------------------------------------------------------------------
+struct GroupArgs {
+  const uint2* ptab; const PackedHdr* hdr;
+  int2* stores;                    // !EPS: resident images [n_stores][nvars], fixpoints written back in place
+  const int2* root;                // EPS: the root store
+  const int* dvars; int ndec;      // EPS: decision variables (bit j of the id halves dvars[j])
+  const long long* ids;            // EPS: subproblem ids (null: first_id + k)
+  long long first_id;
+  int n_stores, nvars, sbytes;
+  uint8_t* flags; int* sweeps_out; int* obj_out;
+  int2* surv; int* surv_idx; int surv_cap;   // EPS: compacted non-failed stores and their subproblem index k
+  BatchCtl* ctl;
+  int objective_var, max_sweeps, stop_on_bot;
+};
+
+__device__ __forceinline__ uint4 lds_v4(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void gbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ int gbar_or(int id, int n, int pred) {
+  int r;
+  asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.or.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
+               : "=r"(r) : "r"(id), "r"(n), "r"(pred) : "memory");
+  return r;
+}
+__device__ __forceinline__ int gbar_and(int id, int n, int pred) {
+  int r;
+  asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.and.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
+               : "=r"(r) : "r"(id), "r"(n), "r"(pred) : "memory");
+  return r;
+}
+
+// One propagator on gathered bounds. FIN: every bound of the store was finite when it was loaded; bounds only tighten,
+// so the infinity guards of pir.hpp:759-764 can never fire and `x = y + z` is six fused add-min/max.
+// The join: a lane whose record moved anything issues all six shared-memory reductions (the ones of bounds that did not
+// move are no-ops of the lattice join), and looks for an emptied operand there and only there - an operand that was
+// empty before the first sweep is found by the scan at load time, and a bound can only cross its partner by moving.
+template <int OP, bool HAS_DIV, bool FIN>
+__device__ __forceinline__ void pk_rule(int op, int2 a, int2 b, int2 c, unsigned ax, unsigned ay, unsigned az,
+                                        unsigned& macc, int& bacc) {
+  Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
+  if(FIN && OP == D_ADD) {
+    // pir.hpp:759-764; later lines see the bounds the earlier ones just tightened, as in the reference
+    r1.lb = max(r1.lb, wadd(r2.lb, r3.lb)); r1.ub = min(r1.ub, wadd(r2.ub, r3.ub));
+    r2.lb = max(r2.lb, wsub(r1.lb, r3.ub)); r2.ub = min(r2.ub, wsub(r1.ub, r3.lb));
+    r3.lb = max(r3.lb, wsub(r1.lb, r2.ub)); r3.ub = min(r3.ub, wsub(r1.ub, r2.lb));
+  }
+  else deduce_regs<HAS_DIV>(op, r1, r2, r3);
+  const unsigned moved = (unsigned)((r1.lb ^ a.x) | (r1.ub ^ a.y) | (r2.lb ^ b.x) | (r2.ub ^ b.y) | (r3.lb ^ c.x) | (r3.ub ^ c.y));
+  if(moved) {
+    reds_max(ax, r1.lb); reds_min(ax + 4, r1.ub);
+    reds_max(ay, r2.lb); reds_min(ay + 4, r2.ub);
+    reds_max(az, r3.lb); reds_min(az + 4, r3.ub);
+    bacc |= (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub);
+  }
+  macc |= moved;
+}
+
+// The pairs [p0, p1) of one run: two records per thread and iteration.
+template <int OP, bool HAS_DIV, bool FIN>
+__device__ __forceinline__ int pk_sweep_run(int p0, int p1, unsigned a_T, unsigned a_S, int tid, int nthr) {
+  unsigned macc = 0;
+  int bacc = 0;
+  for(int p = p0 + tid; p < p1; p += nthr) {
+    const uint4 q = lds_v4(a_T + 16u * (unsigned)p);
+    const unsigned ax0 = a_S + (q.x & 0xffffu), ay0 = a_S + (q.x >> 16), az0 = a_S + (q.y & 0xffffu);
+    const unsigned ax1 = a_S + (q.z & 0xffffu), ay1 = a_S + (q.z >> 16), az1 = a_S + (q.w & 0xffffu);
+    const int2 a0 = lds_itv(ax0), b0 = lds_itv(ay0), c0 = lds_itv(az0);
+    const int2 a1 = lds_itv(ax1), b1 = lds_itv(ay1), c1 = lds_itv(az1);
+    pk_rule<OP, HAS_DIV, FIN>(OP < 0 ? (int)(q.y >> 16) : OP, a0, b0, c0, ax0, ay0, az0, macc, bacc);
+    pk_rule<OP, HAS_DIV, FIN>(OP < 0 ? (int)(q.w >> 16) : OP, a1, b1, c1, ax1, ay1, az1, macc, bacc);
+  }
+  return (macc != 0u ? 1 : 0) | (bacc ? 2 : 0);
+}
+
+template <bool HAS_DIV>
+__device__ __forceinline__ int pk_sweep(const PackedHdr& h, unsigned a_T, unsigned a_S, int tid, int nthr, bool fin) {
+  int f = 0;
+  for(int r = 0; r < h.nruns; ++r) {
+    const int p0 = h.start[r] >> 1, p1 = h.start[r + 1] >> 1;
+#define LPC_RUN(O) case O: f |= pk_sweep_run<O, HAS_DIV, false>(p0, p1, a_T, a_S, tid, nthr); break;
+    switch(h.op[r]) {
+      case D_ADD: f |= fin ? pk_sweep_run<D_ADD, HAS_DIV, true>(p0, p1, a_T, a_S, tid, nthr)
+                           : pk_sweep_run<D_ADD, HAS_DIV, false>(p0, p1, a_T, a_S, tid, nthr); break;
+      LPC_RUN(D_MUL) LPC_RUN(D_MIN) LPC_RUN(D_MAX) LPC_RUN(D_EQ) LPC_RUN(D_LEQ)
+      default: f |= pk_sweep_run<-1, HAS_DIV, false>(p0, p1, a_T, a_S, tid, nthr); break;
+    }
+#undef LPC_RUN
+  }
+  return f;
+}
+
+// G groups of 1024 / G threads per block, one block per SM; each group owns one shared-memory store slot, claims its
+// own stores from a global counter and synchronises on its own named barrier, so one group's barriers and copy waits are
+// filled with the other groups' instructions. Shared memory: [0, 256) mbarriers + per-group scalars | [256, 512) header
+// | G store slots | packed table.
+template <bool HAS_DIV, int G, bool EPS>
+__global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int nthr = 1024 / G;
+  const int grp = threadIdx.x / nthr, tid = threadIdx.x % nthr, bid = 1 + grp;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);   // [grp]: store slot, [G]: table
+  int* s_next = reinterpret_cast<int*>(smem + 128 + 8 * grp);
+  volatile int* s_bot = reinterpret_cast<volatile int*>(smem + 128 + 8 * grp + 4);
+  PackedHdr* sh = reinterpret_cast<PackedHdr*>(smem + 256);
+  static_assert(sizeof(PackedHdr) <= 256, "header does not fit its shared-memory area");
+  const int sbytes = A.sbytes;
+  int2* S = reinterpret_cast<int2*>(smem + 512 + (size_t)grp * sbytes);
+  char* tb = reinterpret_cast<char*>(smem + 512 + (size_t)G * sbytes);
+  const size_t store_stride = (size_t)A.nvars;
+  unsigned long long* tbar = &bars[G];
+  const int np = A.hdr->np;
+
+  if(threadIdx.x == 0) {
+    for(int i = 0; i <= G; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if(threadIdx.x < (int)(sizeof(PackedHdr) / 4)) reinterpret_cast<int*>(sh)[threadIdx.x] = reinterpret_cast<const int*>(A.hdr)[threadIdx.x];
+  __syncthreads();
+  int cur = G * blockIdx.x + grp < A.n_stores ? G * blockIdx.x + grp : -1;
+  if(threadIdx.x == 0 && np > 0) {
+    mbar_expect_tx(tbar, (unsigned)(np * 8));
+    bulk_g2s_chunked(tb, (const char*)A.ptab, (unsigned)(np * 8), tbar);
+  }
+  if(tid == 0 && cur >= 0) {
+    mbar_expect_tx(&bars[grp], (unsigned)sbytes);
+    bulk_g2s_chunked((char*)S, EPS ? (const char*)A.root : (const char*)(A.stores + cur * store_stride), sbytes, &bars[grp]);
+  }
+  if(np > 0) mbar_wait(tbar, 0);
+  const unsigned a_T = smem_u32(tb), a_S = smem_u32(S);
+  const long long n_live = sh->n_live;
+
+  long long a_sol = 0, a_bot = 0, a_unk = 0, a_sweeps = 0;
+  int a_best = LPC_INF, a_maxsw = 0;
+  unsigned phase = 0;
+  while(cur >= 0) {
+    if(tid == 0) {   // claim the next store of this group
+      int nx = atomicAdd(&A.ctl->next_store, 1);
+      if(nx >= A.n_stores) nx = -1;
+      *s_next = nx;
+      *s_bot = 0;
+    }
+    mbar_wait(&bars[grp], phase);
+    phase ^= 1;
+    if(EPS) {   // the subproblem: bit j of the id keeps the lower (0) or the upper (1) half of decision variable j
+      const long long id = A.ids ? A.ids[cur] : A.first_id + cur;
+      for(int j = tid; j < A.ndec; j += nthr) {
+        const int v = A.dvars[j];
+        const int2 d = S[v];
+        const long long mid = (long long)d.x + (((long long)d.y - (long long)d.x) >> 1);
+        S[v] = ((id >> j) & 1) ? make_int2((int)(mid + 1), d.y) : make_int2(d.x, (int)mid);
+      }
+      gbar_sync(bid, nthr);
+    }
+    int f0 = 0, inf = 0;
+    for(int v = tid; v < A.nvars; v += nthr) { const int2 d = S[v]; f0 |= d.x > d.y; inf |= (d.x == LPC_MINF) | (d.y == LPC_INF); }
+    bool bot = gbar_or(bid, nthr, f0) != 0;   // also orders thread 0's s_bot / s_next writes before their readers
+    const bool fin = gbar_or(bid, nthr, inf) == 0;
+    int sweeps = 0;
+    bool changed = !(bot && A.stop_on_bot) && np > 0;
+    while(changed) {
+      const int f = pk_sweep<HAS_DIV>(*sh, a_T, a_S, tid, nthr, fin);
+      ++sweeps;
+      if(f & 2) *s_bot = 1;
+      const int any_chg = gbar_or(bid, nthr, f & 1);
+      bot |= *s_bot != 0;
+      changed = any_chg && !(bot && A.stop_on_bot) && !(A.max_sweeps && sweeps >= A.max_sweeps);
+    }
+    int all_ent = 0;
+    if(!bot) {   // entailment: the ask loop of is_extractable over the propagators that were not entailed on the root
+      int ok = 1;
+      for(int i = tid; i < np && ok; i += nthr) {
+        const uint2 rc = *reinterpret_cast<const uint2*>(tb + 8 * (size_t)i);
+        const int2 a = lds_itv(a_S + (rc.x & 0xffffu)), bb = lds_itv(a_S + (rc.x >> 16)), c = lds_itv(a_S + (rc.y & 0xffffu));
+        ok = ask_regs((int)(rc.y >> 16), Itv(a.x, a.y), Itv(bb.x, bb.y), Itv(c.x, c.y));
+      }
+      all_ent = gbar_and(bid, nthr, ok);
+    }
+    fence_async_smem();
+    gbar_sync(bid, nthr);
+    const int nxt = *s_next;
+    if(tid == 0) {
+      // write-back: a failed store has no specified contents, so only the others travel
+      if(!bot) {
+        char* dst = nullptr;
+        if(EPS) {
+          const int slot = atomicAdd(&A.ctl->n_surv, 1);
+          if(slot < A.surv_cap) { dst = (char*)(A.surv + (size_t)slot * store_stride); A.surv_idx[slot] = cur; }
+        }
+        else dst = (char*)(A.stores + cur * store_stride);
+        if(dst) {
+          for(int o = 0; o < sbytes; o += 32768) bulk_s2g(dst + o, (char*)S + o, min(32768, sbytes - o));
+          bulk_commit();
+        }
+      }
+      A.flags[cur] = (uint8_t)((bot ? 1 : 0) | (all_ent ? 2 : 0));
+      if(A.sweeps_out) A.sweeps_out[cur] = sweeps;
+      const int olb = A.objective_var >= 0 ? S[A.objective_var].x : LPC_INF;
+      if(A.obj_out) A.obj_out[cur] = olb;
+      if(bot) ++a_bot; else if(all_ent) ++a_sol; else ++a_unk;
+      if(!bot && A.objective_var >= 0) a_best = min(a_best, olb);
+      a_sweeps += sweeps;
+      a_maxsw = max(a_maxsw, sweeps);
+      if(nxt >= 0) {   // the next store goes into the same slot once the write-back has read it
+        bulk_wait_read0();
+        mbar_expect_tx(&bars[grp], (unsigned)sbytes);
+        bulk_g2s_chunked((char*)S, EPS ? (const char*)A.root : (const char*)(A.stores + nxt * store_stride), sbytes, &bars[grp]);
+      }
+    }
+    cur = nxt;
+    gbar_sync(bid, nthr);   // everyone of this group has read s_next before its thread 0 overwrites it
+  }
+  if(tid == 0) {
+    bulk_wait0();
+    if(a_sol) atomicAdd((unsigned long long*)&A.ctl->red[0], (unsigned long long)a_sol);
+    if(a_bot) atomicAdd((unsigned long long*)&A.ctl->red[1], (unsigned long long)a_bot);
+    if(a_unk) atomicAdd((unsigned long long*)&A.ctl->red[2], (unsigned long long)a_unk);
+    atomicMin(&A.ctl->red[3], (long long)a_best);
+    atomicAdd((unsigned long long*)&A.ctl->sweeps_total, (unsigned long long)a_sweeps);
+    atomicAdd((unsigned long long*)&A.ctl->deductions, (unsigned long long)(a_sweeps * n_live));
+    atomicMax(&A.ctl->max_sweeps_seen, a_maxsw);
+    __threadfence();
+  }
+  // the block that finishes last publishes the all-reduce payload (BatchCtl::payload)
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    const int done = atomicAdd(&A.ctl->done_blocks, 1);
+    if(done == (int)gridDim.x - 1) {
+      __threadfence();
+      unsigned long long* red = reinterpret_cast<unsigned long long*>(A.ctl->red);   // read where the atomics landed (L2)
+      for(int i = 0; i < 3; ++i) A.ctl->payload[i] = (long long)atomicAdd(&red[i], 0ull);
+      A.ctl->payload[3 + A.ctl->rank] = (long long)atomicAdd(&red[3], 0ull);
+    }
+  }
+}
+
+} // namespace lpc
+
+using namespace lpc;
+
+// ---- launch plan shared by the resident and the EPS entry points -------------------------------------------------------
+struct GroupPlan { int g = 0; size_t smem = 0; int sms = 0; size_t ptab_bytes = 0; };
+
+template <bool EPS>
+static const void* group_kernel(bool has_div, int g) {
+  switch(g) {
+    case 8: return has_div ? (const void*)k_pir_group<true, 8, EPS> : (const void*)k_pir_group<false, 8, EPS>;
+    case 4: return has_div ? (const void*)k_pir_group<true, 4, EPS> : (const void*)k_pir_group<false, 4, EPS>;
+    case 2: return has_div ? (const void*)k_pir_group<true, 2, EPS> : (const void*)k_pir_group<false, 2, EPS>;
+    default: return nullptr;
+  }
+}
+
+static size_t packed_capacity(const lpc_table* t) {   // records + one padding duplicate per run, rounded to a pair
+  return (size_t)(t->dev.n + LPC_PK_MAXRUN + 2) / 2 * 2;
+}
+
+// The most groups whose store slots fit next to the (full) packed table. plan->g == 0: does not qualify.
+template <bool EPS>
+static int group_plan(const lpc_table* t, int nvars, int sbytes, GroupPlan* plan) {
+  plan->g = 0;
+  if(nvars > 8191 || t->dev.n >= (1 << 24)) return LPC_OK;
+  int dev = 0, sms = 0, optin = 0;
+  LPC_CUDA(cudaGetDevice(&dev));
+  LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  LPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  plan->sms = sms;
+  plan->ptab_bytes = packed_capacity(t) * 8;
+  const char* e = getenv("LPC_BATCH_DUAL");
+  const int want = e ? atoi(e) : -1;
+  static const int kG[3] = {8, 4, 2};
+  for(int c = 0; c < 3; ++c) {
+    const int g = want > 0 ? want : kG[c];
+    const void* k = group_kernel<EPS>(t->has_div, g);
+    const size_t need = 512 + (size_t)g * sbytes + plan->ptab_bytes;
+    if(k && need <= (size_t)optin) {
+      LPC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+      int per_sm = 0;
+      LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 1024, need));
+      if(per_sm >= 1) { plan->g = g; plan->smem = need; return LPC_OK; }
+    }
+    if(want > 0) break;
+  }
+  return LPC_OK;
+}
+
+static void ctl_init(BatchCtl* h, int next_store, int rank, int world) {
+  memset(h, 0, sizeof(BatchCtl));
+  h->red[3] = LPC_INF;
+  h->next_store = next_store;
+  h->rank = rank; h->world = world;
+}
+
+// ---- resident store images: the dense path of lpc_batch_fixpoint --------------------------------------------------------
+int lpc_group_launch_resident(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var, int first, int count,
+                              BatchCtl* d_ctl, BatchCtl* h_init, cudaStream_t st, int* used) {
+  *used = 0;
+  const lpc_table* t = b->table;
+  if(b->grp_g < 0) {
+    GroupPlan p;
+    int rc = group_plan<false>(t, b->nvars, b->sbytes, &p);
+    if(rc) return rc;
+    const char* ev = getenv("LPC_BATCH_V2");
+    if(ev && !atoi(ev)) p.g = 0;
+    b->grp_g = p.g; b->grp_smem = p.smem;
+    if(p.g) {
+      b->grp_grid = std::max(1, std::min((b->n_stores + p.g - 1) / p.g, p.sms));
+      LPC_CUDA(cudaMalloc(&b->d_ptab, p.ptab_bytes));
+      LPC_CUDA(cudaMalloc(&b->d_phdr, sizeof(PackedHdr)));
+    }
+  }
+  // small batches keep the one-store-per-block kernel (more threads per store finish a single store sooner)
+  if(b->grp_g == 0 || t->dev.n_pad < 2048 || b->n_stores < 8 * b->table->sm_count || count <= 0) return LPC_OK;
+  // LPC_MODE_AUTO on a batch whose stores are tightenings of a known root: propagators entailed on the root are dropped
+  const int2* root = (o->mode == LPC_MODE_AUTO && b->root_valid) ? b->d_root : nullptr;
+  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr);
+  g_launches++;
+  LPC_CUDA(cudaGetLastError());
+  const int g = b->grp_g;
+  const int grid = std::max(1, std::min(b->grp_grid, (count + g - 1) / g));
+  ctl_init(h_init, g * grid, b->rank, b->world);
+  LPC_CUDA(cudaMemcpyAsync(d_ctl, h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
+  GroupArgs A{};
+  A.ptab = (const uint2*)b->d_ptab; A.hdr = (const PackedHdr*)b->d_phdr;
+  A.stores = b->d + (size_t)first * b->nvars;
+  A.n_stores = count; A.nvars = b->nvars; A.sbytes = b->sbytes;
+  A.flags = b->d_flags + first; A.sweeps_out = b->d_sweeps + first; A.obj_out = b->d_obj ? b->d_obj + first : nullptr;
+  A.ctl = d_ctl; A.objective_var = objective_var; A.max_sweeps = o->max_sweeps; A.stop_on_bot = o->stop_on_bot;
+  void* args[] = {&A};
+  LPC_CUDA(cudaLaunchKernel(group_kernel<false>(t->has_div, g), dim3(grid), dim3(1024), args, b->grp_smem, st));
+  g_launches++;
+  *used = 1;
+  return LPC_OK;
+}
+
+// ---- the EPS-native handle ----------------------------------------------------------------------------------------------
+struct lpc_eps {
+  const lpc_table* table = nullptr;
+  int device = 0, max_n = 0, nvars = 0, sbytes = 0, surv_cap = 0;
+  int2* d_root = nullptr; int* d_dvars = nullptr; long long* d_ids = nullptr;
+  uint8_t* d_flags = nullptr; int* d_sweeps = nullptr; int* d_obj = nullptr;
+  int2* d_surv = nullptr; int* d_surv_idx = nullptr;
+  BatchCtl* d_ctl = nullptr; BatchCtl* h_ctl = nullptr; BatchCtl* h_init = nullptr;
+  void* d_ptab = nullptr; PackedHdr* d_phdr = nullptr; PackedHdr* h_phdr = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool pending = false, have_ids = false, uploaded = false;
+  long long first_id = 0;
+  int n = 0, ndec = 0;
+  GroupPlan plan;
+  int rank = 0, world = 1;
+};
+
+extern "C" {
+
+int lpc_eps_destroy(lpc_eps* e) {
+  if(!e) return LPC_OK;
+  cudaFree(e->d_root); cudaFree(e->d_dvars); cudaFree(e->d_ids); cudaFree(e->d_flags); cudaFree(e->d_sweeps); cudaFree(e->d_obj);
+  cudaFree(e->d_surv); cudaFree(e->d_surv_idx); cudaFree(e->d_ctl); cudaFree(e->d_ptab); cudaFree(e->d_phdr);
+  if(e->h_ctl) cudaFreeHost(e->h_ctl);
+  if(e->h_init) cudaFreeHost(e->h_init);
+  if(e->h_phdr) cudaFreeHost(e->h_phdr);
+  if(e->ev0) cudaEventDestroy(e->ev0);
+  if(e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+  return LPC_OK;
+}
+
+int lpc_eps_create(const lpc_table* t, int32_t max_subproblems, int32_t survivor_cap, lpc_eps** out) {
+  LPC_REQUIRE(t && out, "null argument");
+  LPC_REQUIRE(max_subproblems >= 0 && survivor_cap >= 0, "bad size");
+  const int nvars = t->dev.nvars;
+  if((nvars * 8) % 16 != 0) {
+    set_error("lpc_eps_create: stores need an even number of variables (got %d); pad the model with one unused variable", nvars);
+    return LPC_ERR_UNSUPPORTED;
+  }
+  lpc_eps* e = new lpc_eps();
+  e->table = t; e->max_n = max_subproblems; e->nvars = nvars; e->sbytes = nvars * 8; e->surv_cap = survivor_cap;
+  int rc = LPC_OK;
+  auto fail = [&](int code) { lpc_eps_destroy(e); return code; };
+#define LPC_TRY(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) return fail(lpc::cuda_fail(e__, #call, __FILE__, __LINE__)); } while(0)
+  LPC_TRY(cudaGetDevice(&e->device));
+  rc = group_plan<true>(t, nvars, e->sbytes, &e->plan);
+  if(rc) return fail(rc);
+  if(e->plan.g == 0) {
+    set_error("lpc_eps_create: the model (%d variables, %lld propagators) does not fit the shared memory of an SM; use "
+              "lpc_batch_* with resident stores", nvars, (long long)t->dev.n);
+    return fail(LPC_ERR_UNSUPPORTED);
+  }
+  const size_t n1 = (size_t)std::max(max_subproblems, 16);
+  LPC_TRY(cudaMalloc((void**)&e->d_root, std::max<size_t>(e->sbytes, 16)));
+  LPC_TRY(cudaMalloc((void**)&e->d_dvars, 64 * sizeof(int)));
+  LPC_TRY(cudaMalloc((void**)&e->d_ids, n1 * 8));
+  LPC_TRY(cudaMalloc((void**)&e->d_flags, n1));
+  LPC_TRY(cudaMalloc((void**)&e->d_sweeps, n1 * 4));
+  LPC_TRY(cudaMalloc((void**)&e->d_obj, n1 * 4));
+  LPC_TRY(cudaMalloc((void**)&e->d_surv, std::max<size_t>((size_t)survivor_cap * e->sbytes, 16)));
+  LPC_TRY(cudaMalloc((void**)&e->d_surv_idx, std::max<size_t>((size_t)survivor_cap * 4, 16)));
+  LPC_TRY(cudaMalloc((void**)&e->d_ctl, sizeof(BatchCtl)));
+  LPC_TRY(cudaMalloc(&e->d_ptab, e->plan.ptab_bytes));
+  LPC_TRY(cudaMalloc((void**)&e->d_phdr, sizeof(PackedHdr)));
+  LPC_TRY(cudaHostAlloc((void**)&e->h_ctl, sizeof(BatchCtl), cudaHostAllocDefault));
+  LPC_TRY(cudaHostAlloc((void**)&e->h_init, sizeof(BatchCtl), cudaHostAllocDefault));
+  LPC_TRY(cudaHostAlloc((void**)&e->h_phdr, sizeof(PackedHdr), cudaHostAllocDefault));
+  LPC_TRY(cudaEventCreate(&e->ev0));
+  LPC_TRY(cudaEventCreate(&e->ev1));
+#undef LPC_TRY
+  memset(e->h_ctl, 0, sizeof(BatchCtl));
+  memset(e->h_phdr, 0, sizeof(PackedHdr));
+  *out = e;
+  return LPC_OK;
+}
+
+int lpc_eps_set_rank(lpc_eps* e, int32_t rank, int32_t world) {
+  LPC_REQUIRE(e && world >= 1 && world <= LPC_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
+  e->rank = rank; e->world = world;
+  return LPC_OK;
+}
+
+void* lpc_eps_payload_device_ptr(lpc_eps* e, int32_t* n_int64) {
+  if(!e) return nullptr;
+  if(n_int64) *n_int64 = 3 + e->world;
+  return (void*)e->d_ctl->payload;
+}
+
+static int eps_check_device(const lpc_eps* e) {
+  int dev = -1;
+  LPC_CUDA(cudaGetDevice(&dev));
+  LPC_REQUIRE(dev == e->device, "the handle lives on another CUDA device than the current one");
+  return LPC_OK;
+}
+
+static int eps_upload(lpc_eps* e, const int32_t* root, const int32_t* dvars, int32_t ndec, const int64_t* ids, int64_t first_id,
+                      int32_t n, cudaStream_t st) {
+  LPC_REQUIRE(e && root && (ndec == 0 || dvars), "null argument");
+  LPC_REQUIRE(!e->pending, "a call is still in flight on this handle (collect it first)");
+  LPC_REQUIRE(n >= 0 && n <= e->max_n, "more subproblems than the handle was created for");
+  LPC_REQUIRE(ndec >= 0 && ndec < 63, "bad n_decisions");
+  for(int j = 0; j < ndec; ++j) {
+    LPC_REQUIRE(dvars[j] >= 0 && dvars[j] < e->nvars, "decision variable out of range");
+    for(int k = 0; k < j; ++k) LPC_REQUIRE(dvars[k] != dvars[j], "decision variables must be distinct");
+  }
+  int rc = eps_check_device(e);
+  if(rc) return rc;
+  if(e->sbytes) LPC_CUDA(cudaMemcpyAsync(e->d_root, root, e->sbytes, cudaMemcpyHostToDevice, st));
+  if(ndec) LPC_CUDA(cudaMemcpyAsync(e->d_dvars, dvars, (size_t)ndec * 4, cudaMemcpyHostToDevice, st));
+  if(ids && n) LPC_CUDA(cudaMemcpyAsync(e->d_ids, ids, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  e->have_ids = ids != nullptr; e->first_id = first_id; e->n = n; e->ndec = ndec; e->uploaded = true;
+  return LPC_OK;
+}
+
+int lpc_eps_upload(lpc_eps* e, const int32_t* root_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                   const int64_t* ids, int64_t first_id, int32_t n) {
+  int rc = eps_upload(e, root_lbub, decision_vars, n_decisions, ids, first_id, n, nullptr);
+  if(rc) return rc;
+  LPC_CUDA(cudaStreamSynchronize(nullptr));
+  return LPC_OK;
+}
+
+int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_var) {
+  LPC_REQUIRE(e != nullptr && e->uploaded, "no problem uploaded");
+  LPC_REQUIRE(!e->pending, "a call is still in flight on this handle (collect it first)");
+  LPC_REQUIRE(objective_var < e->nvars, "objective variable out of range");
+  int rc = eps_check_device(e);
+  if(rc) return rc;
+  lpc_fixpoint_opts def;
+  if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
+  cudaStream_t st = (cudaStream_t)o->stream;
+  const lpc_table* t = e->table;
+  const int g = e->plan.g;
+  const int grid = std::max(1, std::min((e->n + g - 1) / g, e->plan.sms));
+  LPC_CUDA(cudaEventRecord(e->ev0, st));
+  ctl_init(e->h_init, g * grid, e->rank, e->world);
+  LPC_CUDA(cudaMemcpyAsync(e->d_ctl, e->h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
+  // LPC_MODE_SWEEP keeps every propagator (the reference's work unit: each sweep evaluates all of them); the default mode
+  // drops the ones entailed on the root
+  const int2* elim_root = o->mode == LPC_MODE_SWEEP ? nullptr : e->d_root;
+  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr);
+  g_launches++;
+  LPC_CUDA(cudaGetLastError());
+  if(e->n > 0) {
+    GroupArgs A{};
+    A.ptab = (const uint2*)e->d_ptab; A.hdr = e->d_phdr;
+    A.root = e->d_root; A.dvars = e->d_dvars; A.ndec = e->ndec; A.ids = e->have_ids ? e->d_ids : nullptr; A.first_id = e->first_id;
+    A.n_stores = e->n; A.nvars = e->nvars; A.sbytes = e->sbytes;
+    A.flags = e->d_flags; A.sweeps_out = e->d_sweeps; A.obj_out = e->d_obj;
+    A.surv = e->d_surv; A.surv_idx = e->d_surv_idx; A.surv_cap = e->surv_cap;
+    A.ctl = e->d_ctl; A.objective_var = objective_var; A.max_sweeps = o->max_sweeps; A.stop_on_bot = o->stop_on_bot;
+    void* args[] = {&A};
+    LPC_CUDA(cudaLaunchKernel(group_kernel<true>(t->has_div, g), dim3(grid), dim3(1024), args, e->plan.smem, st));
+    g_launches++;
+  }
+  LPC_CUDA(cudaEventRecord(e->ev1, st));
+  LPC_CUDA(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
+  LPC_CUDA(cudaMemcpyAsync(e->h_phdr, e->d_phdr, sizeof(PackedHdr), cudaMemcpyDeviceToHost, st));
+  e->last_stream = st;
+  e->pending = true;
+  return LPC_OK;
+}
+
+int lpc_eps_collect(lpc_eps* e, lpc_eps_result* r) {
+  LPC_REQUIRE(e != nullptr, "null handle");
+  LPC_REQUIRE(e->pending, "no call in flight on this handle");
+  LPC_CUDA(cudaStreamSynchronize(e->last_stream));
+  e->pending = false;
+  if(r) {
+    memset(r, 0, sizeof(*r));
+    const BatchCtl& h = *e->h_ctl;
+    r->n_solution = h.red[0]; r->n_bot = h.red[1]; r->n_unknown = h.red[2];
+    r->best_bound = (int32_t)h.red[3];
+    r->max_sweeps_seen = h.max_sweeps_seen;
+    r->sweeps_total = h.sweeps_total; r->deductions = h.deductions;
+    r->n_survivors = h.n_surv;
+    r->n_live_records = e->h_phdr->n_live;
+    float ms = 0;
+    LPC_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    r->device_ms = ms;
+  }
+  return LPC_OK;
+}
+
+int lpc_eps_download(lpc_eps* e, uint8_t* flags, int32_t* survivors_lbub, int32_t* survivor_index, int32_t max_survivors,
+                     int32_t* n_written) {
+  LPC_REQUIRE(e != nullptr && !e->pending, "collect the call first");
+  LPC_REQUIRE(max_survivors >= 0, "bad max_survivors");
+  cudaStream_t st = e->last_stream;
+  const int ns = std::min(std::min(e->h_ctl->n_surv, e->surv_cap), max_survivors);
+  if(flags && e->n) LPC_CUDA(cudaMemcpyAsync(flags, e->d_flags, e->n, cudaMemcpyDeviceToHost, st));
+  if(survivors_lbub && ns) LPC_CUDA(cudaMemcpyAsync(survivors_lbub, e->d_surv, (size_t)ns * e->sbytes, cudaMemcpyDeviceToHost, st));
+  if(survivor_index && ns) LPC_CUDA(cudaMemcpyAsync(survivor_index, e->d_surv_idx, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+  LPC_CUDA(cudaStreamSynchronize(st));
+  if(n_written) *n_written = ns;
+  return LPC_OK;
+}
+
+int lpc_eps_solve_host(lpc_eps* e, const int32_t* root_lbub, const int32_t* decision_vars, int32_t n_decisions,
+                       const int64_t* ids, int64_t first_id, int32_t n, const lpc_fixpoint_opts* o, int32_t objective_var,
+                       uint8_t* flags, int32_t* survivors_lbub, int32_t* survivor_index, int32_t max_survivors,
+                       int32_t* n_written, lpc_eps_result* r) {
+  cudaStream_t st = o ? (cudaStream_t)o->stream : nullptr;
+  int rc = eps_upload(e, root_lbub, decision_vars, n_decisions, ids, first_id, n, st);
+  if(rc) return rc;
+  if((rc = lpc_eps_run_async(e, o, objective_var))) return rc;
+  // the flags do not depend on the survivor count: queue their copy behind the kernel, before the first synchronisation
+  if(flags && n) LPC_CUDA(cudaMemcpyAsync(flags, e->d_flags, n, cudaMemcpyDeviceToHost, st));
+  if((rc = lpc_eps_collect(e, r))) return rc;
+  return lpc_eps_download(e, nullptr, survivors_lbub, survivor_index, max_survivors, n_written);
+}
+
+int lpc_eps_sweeps(lpc_eps* e, int32_t* out) {
+  LPC_REQUIRE(e && (out || e->n == 0) && !e->pending, "bad argument");
+  if(e->n) LPC_CUDA(cudaMemcpy(out, e->d_sweeps, (size_t)e->n * 4, cudaMemcpyDeviceToHost));
+  return LPC_OK;
+}
+
+} // extern "C"

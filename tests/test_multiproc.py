@@ -41,8 +41,15 @@ def _worker(rank, world, port, n_per_rank, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from lala_pc_b200 import sharding
-    red = torch.tensor(_shard_record(rank, world, n_per_rank), dtype=torch.int64)
+    rec = _shard_record(rank, world, n_per_rank)
+    red = torch.tensor(rec, dtype=torch.int64)
     sharding.allreduce_record(red, dist)
+    # the packed form the kernels fill (include/lpc.h: lpc_eps_set_rank): ONE SUM all-reduce, MIN folded on the host
+    payload = torch.zeros(3 + world, dtype=torch.int64)
+    payload[:3] = torch.tensor(rec[:3])
+    payload[3 + rank] = rec[3]
+    sharding.allreduce_payload(payload, dist)
+    assert sharding.fold_payload(payload.tolist()) == red.tolist()
     q.put((rank, red.tolist()))
     dist.barrier()
     dist.destroy_process_group()
@@ -80,5 +87,10 @@ def test_sharding_helpers():
         for p in parts:                                                        # ... into uniform samples: no fixed bit
             for j in range((world * 4096 - 1).bit_length()):
                 assert 0.4 < float(((p >> j) & 1).mean()) < 0.6
+    for world in (1, 2, 8):                                                   # strong scaling: ONE batch of 65,536 dealt out
+        parts = [sharding.strong_shard_ids(r, world) for r in range(world)]
+        assert all(len(p) == 65536 // world for p in parts)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(65536))
+    assert sharding.fold_payload([5, 6, 7, 40, 30, 50]) == [5, 6, 7, 30]
     red = torch.tensor([1, 2, 3, 4], dtype=torch.int64)
     assert sharding.allreduce_record(red, None).tolist() == [1, 2, 3, 4]
