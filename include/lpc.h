@@ -10,7 +10,12 @@
  *     top = [INT32_MIN, INT32_MAX]; an interval with lb > ub is empty (bot).
  *   - a *table* is the immutable propagator table `battery::vector<bytecode_type>` (pir.hpp:104, 115-118).
  *   - arithmetic is 32-bit two's-complement with wrap-around (the reference has UB on overflow,
- *     pir.hpp:759-772; generators keep magnitudes small so that the question never arises).
+ *     pir.hpp:759-772; generators keep magnitudes small so that the question never arises). The rules are monotone
+ *     over the integers, not over wrapped int32: once a FINITE bound sits next to INT32_MIN / INT32_MAX (it gets there
+ *     from an exactly infinite one, e.g. `x = 0 => y >= z.lb + 1`, pir.hpp:750-753) a later `+` or `*` may wrap and the
+ *     result then depends on the evaluation order - on the reference's side it is undefined behaviour. The engine
+ *     reports that situation instead of hiding it: `overflow_hazard` in the result records is set when a finite bound
+ *     within 2^24 of the int32 limits was present in the initial store or written during the fixpoint.
  *   - one in-flight call per handle; distinct handles are independent. Handles live on the CUDA device that
  *     was current when they were created.
  */
@@ -105,7 +110,7 @@ int lpc_store_is_top(const lpc_store* s, int* out);
 #define LPC_MODE_AUTO 0      /* change-driven: dense sweeps that skip 64-record groups none of whose variables changed, once
                                 a sweep changes at most 1/d of the groups (d = opts.reserved, default 8) */
 #define LPC_MODE_SWEEP 1     /* dense: every sweep evaluates every propagator */
-#define LPC_MODE_WORKLIST 2  /* record-granular worklist from the second iteration on */
+#define LPC_MODE_WORKLIST 2  /* change-driven from the second sweep on (the same kernel as AUTO, handing over at once) */
 
 typedef struct lpc_fixpoint_opts {
   int32_t mode;          /* LPC_MODE_* */
@@ -122,7 +127,7 @@ typedef struct lpc_fixpoint_result {
   int32_t dense_sweeps;  /* how many of them were dense */
   int64_t deductions;    /* deduce() evaluations executed (informational: schedule dependent) */
   float device_ms;       /* device time of the fixpoint kernel(s), CUDA events on `stream` */
-  int32_t reserved;
+  int32_t overflow_hazard; /* 1: a finite bound next to the int32 limits was seen (see "arithmetic" above) */
 } lpc_fixpoint_result;
 
 void lpc_fixpoint_default_opts(lpc_fixpoint_opts* o);
@@ -176,7 +181,7 @@ typedef struct lpc_batch_result {
   int64_t sweeps_total;  /* sum over stores */
   int64_t deductions;    /* deduce() evaluations executed over the whole batch */
   float device_ms;
-  int32_t reserved;
+  int32_t overflow_hazard; /* 1: some store held a finite bound next to the int32 limits before or after its fixpoint */
 } lpc_batch_result;
 
 /* Fixpoint of every store of the batch. objective_var < 0: no objective. opts.mode: LPC_MODE_SWEEP and LPC_MODE_AUTO =
@@ -223,6 +228,8 @@ typedef struct lpc_eps_result {
   int64_t n_survivors;                    /* non-failed stores (may exceed the survivor capacity: then only that many were kept) */
   int32_t n_live_records;                 /* propagators left in the table after dropping those entailed on the root */
   float device_ms;
+  int32_t overflow_hazard;                /* as lpc_batch_result */
+  int32_t reserved;
 } lpc_eps_result;
 
 int lpc_eps_create(const lpc_table* t, int32_t max_subproblems, int32_t survivor_cap, lpc_eps** out);

@@ -36,10 +36,10 @@ class FixpointOpts(ctypes.Structure):
 class FixpointResult(ctypes.Structure):
     _fields_ = [("has_changed", ctypes.c_int32), ("is_bot", ctypes.c_int32), ("sweeps", ctypes.c_int32),
                 ("dense_sweeps", ctypes.c_int32), ("deductions", ctypes.c_int64), ("device_ms", ctypes.c_float),
-                ("reserved", ctypes.c_int32)]
+                ("overflow_hazard", ctypes.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class SearchOpts(ctypes.Structure):
@@ -61,20 +61,20 @@ class BatchResult(ctypes.Structure):
     _fields_ = [("n_bot", ctypes.c_int64), ("n_solution", ctypes.c_int64), ("n_unknown", ctypes.c_int64),
                 ("best_bound", ctypes.c_int32), ("max_sweeps_seen", ctypes.c_int32),
                 ("sweeps_total", ctypes.c_int64), ("deductions", ctypes.c_int64), ("device_ms", ctypes.c_float),
-                ("reserved", ctypes.c_int32)]
+                ("overflow_hazard", ctypes.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class EpsResult(ctypes.Structure):
     _fields_ = [("n_bot", ctypes.c_int64), ("n_solution", ctypes.c_int64), ("n_unknown", ctypes.c_int64),
                 ("best_bound", ctypes.c_int32), ("max_sweeps_seen", ctypes.c_int32), ("sweeps_total", ctypes.c_int64),
                 ("deductions", ctypes.c_int64), ("n_survivors", ctypes.c_int64), ("n_live_records", ctypes.c_int32),
-                ("device_ms", ctypes.c_float)]
+                ("device_ms", ctypes.c_float), ("overflow_hazard", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
 if not os.path.exists(LIB_PATH):

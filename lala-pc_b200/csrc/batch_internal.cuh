@@ -13,6 +13,7 @@ struct BatchCtl {
   int next_store;              // dynamic scheduler
   int n_surv;                  // EPS: non-failed stores written to the survivor buffer so far (pir_eps.cu)
   int done_blocks;             // blocks that have finished (the last one writes the all-reduce payload)
+  int hazard;                  // a store held a finite bound next to the int32 limits (lpc.h: overflow_hazard)
   int rank, world;             // position of this GPU in the multi-GPU job (lpc_batch_set_rank / lpc_eps_set_rank)
   // The payload of the ONE all-reduce (SUM) of the multi-GPU driver: [0..2] = the three counters, [3 + rank] = this
   // rank's best bound (every other slot 0), so that SUM delivers every rank's bound and MIN is taken on the host.

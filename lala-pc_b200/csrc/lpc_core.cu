@@ -262,7 +262,6 @@ int lpc_table_destroy(lpc_table* t) {
   cudaFree(t->d_inc_off); cudaFree(t->d_inc_idx); cudaFree(t->d_chunk);
   cudaFree(t->d_x16); cudaFree(t->d_y16); cudaFree(t->d_z16);
   if(t->host_store) lpc_store_destroy(t->host_store);
-  lpc_win_plan_free(t->win_plan);
   delete t;
   return LPC_OK;
 }
@@ -339,7 +338,7 @@ int lpc_store_wrap_device(void* device_ptr, int32_t nvars, lpc_store** out) {
 int lpc_store_destroy(lpc_store* s) {
   if(!s) return LPC_OK;
   if(s->owning) cudaFree(s->d);
-  cudaFree(s->wl_stamp); cudaFree(s->wl_q0); cudaFree(s->wl_q1); cudaFree(s->wl_vmark); cudaFree(s->d_dirty);
+  cudaFree(s->d_dirty);
   cudaFree(s->d_ctl);
   if(s->h_ctl) cudaFreeHost(s->h_ctl);
   if(s->ev0) cudaEventDestroy(s->ev0);

@@ -68,8 +68,8 @@ struct FixCtl {
   int has_changed;
   int is_bot;
   unsigned long long deductions;
-  // worklist state
-  int q_len[4];         // rotating queue-length words (3 in use)
+  int hazard;           // a finite bound next to the int32 limits was seen (lpc.h: overflow_hazard)
+  int pad_[3];
   int scratch[4];
   unsigned long long bar[4];   // rotating vote-carrying barrier words (grid_barrier.cuh; 3 in use)
   int sm_slots[256];    // blocks arrived per SM (sm_rank_arrive / sm_rank_resolve, grid_barrier.cuh)
@@ -80,11 +80,8 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 } // namespace lpc
 
 struct lpc_store;
-struct lpc_win_plan;                                   // pir_window.cu
-void lpc_win_plan_free(lpc_win_plan* p);
-int lpc_win_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, int* used);
 int lpc_dirty_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o);   // pir_dirty.cu
-int lpc_cluster_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, int* used);   // pir_cluster.cu
+int lpc_check_device(int handle_device, const char* what);                                       // pir_fixpoint.cu
 struct lpc_table {
   int device = 0;
   std::vector<lpc_bytecode> host;   // the caller's records, caller's order (load_deduce)
@@ -104,11 +101,8 @@ struct lpc_table {
   int sm_count = 0;
   size_t smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin
   lpc_store* host_store = nullptr;  // device staging store of lpc_fixpoint_host
-  bool cluster_ready = false;       // shared-memory attribute of the cluster kernel set (pir_cluster.cu)
   bool dirty_ready = false;         // occupancy of the change-driven kernel (pir_dirty.cu)
   int dirty_blocks_per_sm[2] = {0, 0};
-  bool win_plan_tried = false;      // shared-memory window plan of pir_window.cu (built on first dense launch)
-  lpc_win_plan* win_plan = nullptr;
 };
 
 struct lpc_store {
@@ -121,9 +115,6 @@ struct lpc_store {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t last_stream = nullptr;
   bool pending = false;
-  // worklist scratch (allocated on first use): enqueue stamps, two record queues, changed-variable marks
-  int* wl_stamp = nullptr; int* wl_q0 = nullptr; int* wl_q1 = nullptr; int* wl_vmark = nullptr;
-  long long wl_n = 0; int wl_nvars = 0;
   // group byte maps of the change-driven kernel (pir_dirty.cu)
   unsigned char* d_dirty = nullptr; long long dirty_cap = 0;
 };

@@ -988,6 +988,7 @@ int lpc_batch_collect(lpc_batch* b, lpc_batch_result* r) {
       acc.red[3] = std::min(acc.red[3], h.red[3]);
       acc.sweeps_total += h.sweeps_total; acc.deductions += h.deductions;
       acc.max_sweeps_seen = std::max(acc.max_sweeps_seen, h.max_sweeps_seen);
+      acc.hazard |= h.hazard;
     }
     *b->h_ctl = acc;
     // the device-side record stays consistent with a one-launch call (lpc_batch_reduction_device_ptr)
@@ -1004,6 +1005,7 @@ int lpc_batch_collect(lpc_batch* b, lpc_batch_result* r) {
     r->max_sweeps_seen = b->h_ctl->max_sweeps_seen;
     r->sweeps_total = b->h_ctl->sweeps_total;
     r->deductions = b->h_ctl->deductions;
+    r->overflow_hazard = b->h_ctl->hazard;
     float ms = 0;
     LPC_CUDA(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
     r->device_ms = ms;

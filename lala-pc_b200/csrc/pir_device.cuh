@@ -35,6 +35,10 @@ struct Itv {
   __host__ __device__ __forceinline__ void meet(const Itv& o) { lb = lb > o.lb ? lb : o.lb; ub = ub < o.ub ? ub : o.ub; }
 };
 
+// A FINITE bound within 2^24 of the int32 limits (lpc.h, "arithmetic"): from there on `+` and `*` may wrap.
+LPC_HD bool near_inf_lo(int b) { return (unsigned)b - 0x80000001u < (1u << 24); }
+LPC_HD bool near_inf_hi(int b) { return 0x7ffffffeu - (unsigned)b < (1u << 24); }
+
 LPC_HD Itv itv_top() { return Itv(LPC_MINF, LPC_INF); }
 LPC_HD Itv itv_bot() { return Itv(LPC_INF, LPC_MINF); }
 // hull ignoring empty operands (lala-core Interval::join / fjoin)

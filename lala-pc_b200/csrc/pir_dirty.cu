@@ -1,10 +1,12 @@
-// pir_dirty.cu — the change-driven single-store fixpoint (LPC_MODE_AUTO): dense sweeps that learn to skip (sm_100a).
+// pir_dirty.cu — the change-driven single-store fixpoint (LPC_MODE_AUTO, LPC_MODE_WORKLIST): dense sweeps that learn
+// to skip (sm_100a).
 //
 // BASELINE.json's north_star asks for "an optional change-driven worklist so only propagators touching changed
-// variables are re-run". A record-granular queue (LPC_MODE_WORKLIST, pir_fixpoint.cu) pays an atomicExch per enqueued
-// record and gives up the streaming table scan; on config 2 it runs 4x fewer deductions and is still slower than dense
-// sweeps. This kernel keeps the dense sweep's shape - same partition, same coalesced record loads, same rules - and
-// makes whole 64-record GROUPS skippable:
+// variables are re-run". A record-granular queue (round 1's LPC_MODE_WORKLIST) paid an atomicExch per enqueued record and
+// gave up the streaming table scan: on config 2 it ran 4x fewer deductions and took 6.0 ms against 0.44 ms for dense
+// sweeps, and was removed. This kernel keeps the dense sweep's shape - same partition, same coalesced record loads, same
+// rules - and makes whole 64-record GROUPS the unit of the worklist (LPC_MODE_WORKLIST = hand over to flagged sweeps
+// right after the first sweep, LPC_MODE_AUTO = once few groups change):
 //   * while many groups change per sweep (the first sweeps) it is the dense kernel: no bookkeeping at all;
 //   * once a sweep changes at most 1/8 of the groups, the next sweep still evaluates everything but every tightening of
 //     a variable v also marks the groups of v's incident records (var -> records CSR, built by lpc_table_create) in a
@@ -44,11 +46,12 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
   const long long gtid = blockIdx.x * (long long)DTPB + tid;
   const long long gthreads = (long long)gridDim.x * DTPB;
   int nbar = 0;
+  int hazard = 0;
   bool bot;
   const int sm_slot = sm_order ? sm_rank_arrive(ctl->sm_slots) : 0;
   {
     int f = 0;
-    for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = store[i]; f |= v.x > v.y; }
+    for(long long i = gtid; i < t.nvars; i += gthreads) { int2 v = store[i]; f |= v.x > v.y; hazard |= near_inf_lo(v.x) | near_inf_hi(v.y); }
     for(long long i = gtid; i < 3LL * map_stride; i += gthreads) dmap[i] = 0;
     for(long long i = gtid; i < map_stride; i += gthreads) dmap[3LL * map_stride + i] = 1;   // every group live
     bot = grid_vote_barrier(ctl->bar, nbar++, false, f != 0, &s_vote).bot;
@@ -101,8 +104,8 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
               const int2 old = w == 0 ? a : w == 1 ? b : c;
               const Itv nw = w == 0 ? r1 : w == 1 ? r2 : r3;
               int ch = 0;
-              if(nw.lb > old.x) { atomicMax(&store[v].x, nw.lb); ch = 1; }
-              if(nw.ub < old.y) { atomicMin(&store[v].y, nw.ub); ch = 1; }
+              if(nw.lb > old.x) { atomicMax(&store[v].x, nw.lb); ch = 1; hazard |= near_inf_lo(nw.lb); }
+              if(nw.ub < old.y) { atomicMin(&store[v].y, nw.ub); ch = 1; hazard |= near_inf_hi(nw.ub); }
               if(ch) {
                 g1 |= nw.lb > nw.ub ? 3 : 1;
                 cv[h * 3 + w] = v;
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
     else phase = 2;
   }
   // deduce() evaluations executed (one atomic per warp for the whole fixpoint)
+  if(__syncthreads_or(hazard) && tid == 0) atomicOr(&ctl->hazard, 1);
   evals_total = __reduce_add_sync(0xffffffffu, evals_total);
   if(lane == 0 && evals_total) atomicAdd(&ctl->deductions, (unsigned long long)evals_total);
   if(blockIdx.x == 0 && tid == 0) {
@@ -245,9 +249,10 @@ int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opt
   seg.nseg = t->seg_n;
   for(int i = 0; i <= t->seg_n; ++i) seg.u[i] = t->seg_q[i] * 2;
   if(units <= 2LL * grid * DTPB) { seg.nseg = 1; seg.u[0] = 0; seg.u[1] = (int)units; }   // small table: one pass (see pir_fixpoint.cu)
-  // hand over to flagged sweeps once a sweep changes at most 1/d of the groups (opts.reserved = d, default 8)
+  // hand over to flagged sweeps once a sweep changes at most 1/d of the groups (opts.reserved = d, default 8);
+  // LPC_MODE_WORKLIST: after the first sweep whatever it changed
   const int div = o->reserved > 0 ? o->reserved : 8;
-  unsigned switch_groups = (unsigned)std::max(1, n_groups / div);
+  unsigned switch_groups = o->mode == LPC_MODE_WORKLIST ? 0xffffffffu : (unsigned)std::max(1, n_groups / div);
   LPC_CUDA(cudaEventRecord(s->ev0, st));
   LPC_CUDA(cudaMemsetAsync(s->d_ctl, 0, sizeof(FixCtl), st));
   TableDev td = t->dev;

@@ -247,8 +247,13 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
       }
       gbar_sync(bid, nthr);
     }
-    int f0 = 0, inf = 0;
-    for(int v = tid; v < A.nvars; v += nthr) { const int2 d = S[v]; f0 |= d.x > d.y; inf |= (d.x == LPC_MINF) | (d.y == LPC_INF); }
+    int f0 = 0, inf = 0, hz = 0;
+    for(int v = tid; v < A.nvars; v += nthr) {
+      const int2 d = S[v];
+      f0 |= d.x > d.y;
+      inf |= (d.x == LPC_MINF) | (d.y == LPC_INF);
+      hz |= near_inf_lo(d.x) | near_inf_hi(d.y);
+    }
     bool bot = gbar_or(bid, nthr, f0) != 0;   // also orders thread 0's s_bot / s_next writes before their readers
     const bool fin = gbar_or(bid, nthr, inf) == 0;
     int sweeps = 0;
@@ -270,7 +275,10 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
         ok = ask_regs((int)(rc.y >> 16), Itv(a.x, a.y), Itv(bb.x, bb.y), Itv(c.x, c.y));
       }
       all_ent = gbar_and(bid, nthr, ok);
+      // overflow hazard (lpc.h): a finite bound next to the int32 limits in a store that is handed back
+      for(int v = tid; v < A.nvars; v += nthr) { const int2 d = S[v]; hz |= near_inf_lo(d.x) | near_inf_hi(d.y); }
     }
+    if(hz) atomicOr(&A.ctl->hazard, 1);
     fence_async_smem();
     gbar_sync(bid, nthr);
     const int nxt = *s_next;
@@ -607,6 +615,7 @@ int lpc_eps_collect(lpc_eps* e, lpc_eps_result* r) {
     r->sweeps_total = h.sweeps_total; r->deductions = h.deductions;
     r->n_survivors = h.n_surv;
     r->n_live_records = e->h_phdr->n_live;
+    r->overflow_hazard = h.hazard;
     float ms = 0;
     LPC_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     r->device_ms = ms;

@@ -31,7 +31,8 @@ def W():
 
 
 def modes(L):
-    """Fixpoint options under test: dense sweeps, dense -> worklist hand-over, worklist after the first sweep."""
+    """Fixpoint options under test: dense sweeps, change-driven sweeps handing over once few groups change (AUTO) and
+    right after the first sweep (WORKLIST)."""
     return [("sweep", dict(mode=L.MODE_SWEEP)), ("auto", dict(mode=L.MODE_AUTO, switch_div=8)),
             ("worklist", dict(mode=L.MODE_WORKLIST))]
 
@@ -118,12 +119,11 @@ def test_config2_parity_tenth(L, O, W, mode_name):
     check_parity(L, O, twin.records, twin.store, mode, "config2@0.1 twin")
 
 
-@pytest.mark.parametrize("env", [{"LPC_WINDOW": "1"}, {"LPC_VOTE": "0"}, {"LPC_RPT": "12", "LPC_MINB": "3"}, {"LPC_CLUSTER": "1"}])
+@pytest.mark.parametrize("env", [{"LPC_RPT": "4", "LPC_MINB": "3"}, {"LPC_RPT": "1", "LPC_MINB": "4"}, {"LPC_SMORDER": "0"},
+                                 {"LPC_BATCH_DUAL": "4"}])
 def test_alternative_dense_kernels_parity(L, O, W, env):
-    """The dense-sweep alternatives that are built but not the default - shared-memory store windows (pir_window.cu),
-    the flag-word + grid.sync barrier, the software-pipelined record loop, the one-cluster kernel with store replicas in
-    distributed shared memory (pir_cluster.cu; takes config 1 and its failing twin, config 2 is too large for it) - reach
-    the same fixpoints."""
+    """The tuning variants of the dense kernel that are built but not the default (records per thread / blocks per SM,
+    table fractions in blockIdx order) reach the same fixpoints."""
     import os
     import subprocess
     import sys

@@ -29,7 +29,8 @@ def main():
         s = L.Store(values=net.store)
         L.fixpoint(table, s)
         root = s.read()
-        dec, obj = W.eps_decisions(net.records, root, n=16)
+        dec, obj = W.eps_decisions(net.records, root, n=24)   # bench.py's decision list
+        dec = dec[:16]
         mode = L.MODE_AUTO if what.endswith("auto") else L.MODE_SWEEP
         if what.startswith("eps"):
             e = L.Eps(table, 65536, survivor_cap=8192)
