@@ -130,7 +130,33 @@ __device__ __forceinline__ int gbar_and(int id, int n, int pred) {
 // The join: a lane whose record moved anything issues all six shared-memory reductions (the ones of bounds that did not
 // move are no-ops of the lattice join), and looks for an emptied operand there and only there - an operand that was
 // empty before the first sweep is found by the scan at load time, and a bound can only cross its partner by moving.
-template <int OP, bool HAS_DIV, bool FIN>
+// JOIN = 1 (default) / 2: every reduction individually guarded by "this bound moved", inside the moved-region (1) or
+// without a region at all (2). ptxas turns the guard into a branch around the ATOMS (a shared-memory atomic cannot be
+// predicated), so this costs instructions - but the kernel is bound by the shared-memory pipe (ncu: l1tex throughput 94 %,
+// half of the wavefronts bank conflicts, issue slots 49 % busy), and a no-op reduction occupies its banks like a real one.
+__device__ __forceinline__ void reds_max_if_gt(unsigned addr, int nw, int old) {
+  asm volatile("{ .reg .pred q; setp.gt.s32 q, %1, %2; @q red.shared.max.s32 [%0], %1; }" ::"r"(addr), "r"(nw), "r"(old) : "memory");
+}
+__device__ __forceinline__ void reds_min_if_lt(unsigned addr, int nw, int old) {
+  asm volatile("{ .reg .pred q; setp.lt.s32 q, %1, %2; @q red.shared.min.s32 [%0], %1; }" ::"r"(addr), "r"(nw), "r"(old) : "memory");
+}
+
+// JOIN = 3: no atomics at all - a bound that moved is written with a plain predicated store. Two lanes that tighten the
+// same bound in the same sweep may overwrite each other (the weaker value can win, a bound can even step back within a
+// sweep), which the fixpoint tolerates: every value ever written is the result of a sound rule on values that contain the
+// greatest fixpoint G, so it contains G; a written value is strictly tighter than a value read in the same sweep, hence
+// (induction over the writes of a sweep) than the bound at the sweep's start, so every sweep that writes makes strict
+// progress and the loop ends; and the sweep that ends it wrote nothing, i.e. every propagator was evaluated on the
+// final store and moved nothing: a common fixpoint inside the initial store, which is below G. So the result is G, bit
+// for bit, as with atomic joins - without the shared-memory atomics' bank and same-address serialisation.
+__device__ __forceinline__ void sts_if_gt(unsigned addr, int nw, int old) {
+  asm volatile("{ .reg .pred q; setp.gt.s32 q, %1, %2; @q st.shared.s32 [%0], %1; }" ::"r"(addr), "r"(nw), "r"(old) : "memory");
+}
+__device__ __forceinline__ void sts_if_lt(unsigned addr, int nw, int old) {
+  asm volatile("{ .reg .pred q; setp.lt.s32 q, %1, %2; @q st.shared.s32 [%0], %1; }" ::"r"(addr), "r"(nw), "r"(old) : "memory");
+}
+
+template <int OP, bool HAS_DIV, bool FIN, int JOIN>
 __device__ __forceinline__ void pk_rule(int op, int2 a, int2 b, int2 c, unsigned ax, unsigned ay, unsigned az,
                                         unsigned& macc, int& bacc) {
   Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
@@ -142,17 +168,36 @@ __device__ __forceinline__ void pk_rule(int op, int2 a, int2 b, int2 c, unsigned
   }
   else deduce_regs<HAS_DIV>(op, r1, r2, r3);
   const unsigned moved = (unsigned)((r1.lb ^ a.x) | (r1.ub ^ a.y) | (r2.lb ^ b.x) | (r2.ub ^ b.y) | (r3.lb ^ c.x) | (r3.ub ^ c.y));
-  if(moved) {
-    reds_max(ax, r1.lb); reds_min(ax + 4, r1.ub);
-    reds_max(ay, r2.lb); reds_min(ay + 4, r2.ub);
-    reds_max(az, r3.lb); reds_min(az + 4, r3.ub);
+  if(JOIN == 3) {
+    sts_if_gt(ax, r1.lb, a.x); sts_if_lt(ax + 4, r1.ub, a.y);
+    sts_if_gt(ay, r2.lb, b.x); sts_if_lt(ay + 4, r2.ub, b.y);
+    sts_if_gt(az, r3.lb, c.x); sts_if_lt(az + 4, r3.ub, c.y);
+    bacc |= (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub);
+  }
+  else if(JOIN == 2) {
+    reds_max_if_gt(ax, r1.lb, a.x); reds_min_if_lt(ax + 4, r1.ub, a.y);
+    reds_max_if_gt(ay, r2.lb, b.x); reds_min_if_lt(ay + 4, r2.ub, b.y);
+    reds_max_if_gt(az, r3.lb, c.x); reds_min_if_lt(az + 4, r3.ub, c.y);
+    bacc |= (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub);
+  }
+  else if(moved) {
+    if(JOIN == 1) {
+      reds_max_if_gt(ax, r1.lb, a.x); reds_min_if_lt(ax + 4, r1.ub, a.y);
+      reds_max_if_gt(ay, r2.lb, b.x); reds_min_if_lt(ay + 4, r2.ub, b.y);
+      reds_max_if_gt(az, r3.lb, c.x); reds_min_if_lt(az + 4, r3.ub, c.y);
+    }
+    else {
+      reds_max(ax, r1.lb); reds_min(ax + 4, r1.ub);
+      reds_max(ay, r2.lb); reds_min(ay + 4, r2.ub);
+      reds_max(az, r3.lb); reds_min(az + 4, r3.ub);
+    }
     bacc |= (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub);
   }
   macc |= moved;
 }
 
 // The pairs [p0, p1) of one run: two records per thread and iteration.
-template <int OP, bool HAS_DIV, bool FIN>
+template <int OP, bool HAS_DIV, bool FIN, int JOIN>
 __device__ __forceinline__ int pk_sweep_run(int p0, int p1, unsigned a_T, unsigned a_S, int tid, int nthr) {
   unsigned macc = 0;
   int bacc = 0;
@@ -162,23 +207,23 @@ __device__ __forceinline__ int pk_sweep_run(int p0, int p1, unsigned a_T, unsign
     const unsigned ax1 = a_S + (q.z & 0xffffu), ay1 = a_S + (q.z >> 16), az1 = a_S + (q.w & 0xffffu);
     const int2 a0 = lds_itv(ax0), b0 = lds_itv(ay0), c0 = lds_itv(az0);
     const int2 a1 = lds_itv(ax1), b1 = lds_itv(ay1), c1 = lds_itv(az1);
-    pk_rule<OP, HAS_DIV, FIN>(OP < 0 ? (int)(q.y >> 16) : OP, a0, b0, c0, ax0, ay0, az0, macc, bacc);
-    pk_rule<OP, HAS_DIV, FIN>(OP < 0 ? (int)(q.w >> 16) : OP, a1, b1, c1, ax1, ay1, az1, macc, bacc);
+    pk_rule<OP, HAS_DIV, FIN, JOIN>(OP < 0 ? (int)(q.y >> 16) : OP, a0, b0, c0, ax0, ay0, az0, macc, bacc);
+    pk_rule<OP, HAS_DIV, FIN, JOIN>(OP < 0 ? (int)(q.w >> 16) : OP, a1, b1, c1, ax1, ay1, az1, macc, bacc);
   }
   return (macc != 0u ? 1 : 0) | (bacc ? 2 : 0);
 }
 
-template <bool HAS_DIV>
+template <bool HAS_DIV, int JOIN>
 __device__ __forceinline__ int pk_sweep(const PackedHdr& h, unsigned a_T, unsigned a_S, int tid, int nthr, bool fin) {
   int f = 0;
   for(int r = 0; r < h.nruns; ++r) {
     const int p0 = h.start[r] >> 1, p1 = h.start[r + 1] >> 1;
-#define LPC_RUN(O) case O: f |= pk_sweep_run<O, HAS_DIV, false>(p0, p1, a_T, a_S, tid, nthr); break;
+#define LPC_RUN(O) case O: f |= pk_sweep_run<O, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr); break;
     switch(h.op[r]) {
-      case D_ADD: f |= fin ? pk_sweep_run<D_ADD, HAS_DIV, true>(p0, p1, a_T, a_S, tid, nthr)
-                           : pk_sweep_run<D_ADD, HAS_DIV, false>(p0, p1, a_T, a_S, tid, nthr); break;
+      case D_ADD: f |= fin ? pk_sweep_run<D_ADD, HAS_DIV, true, JOIN>(p0, p1, a_T, a_S, tid, nthr)
+                           : pk_sweep_run<D_ADD, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr); break;
       LPC_RUN(D_MUL) LPC_RUN(D_MIN) LPC_RUN(D_MAX) LPC_RUN(D_EQ) LPC_RUN(D_LEQ)
-      default: f |= pk_sweep_run<-1, HAS_DIV, false>(p0, p1, a_T, a_S, tid, nthr); break;
+      default: f |= pk_sweep_run<-1, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr); break;
     }
 #undef LPC_RUN
   }
@@ -189,7 +234,7 @@ __device__ __forceinline__ int pk_sweep(const PackedHdr& h, unsigned a_T, unsign
 // own stores from a global counter and synchronises on its own named barrier, so one group's barriers and copy waits are
 // filled with the other groups' instructions. Shared memory: [0, 256) mbarriers + per-group scalars | [256, 512) header
 // | G store slots | packed table.
-template <bool HAS_DIV, int G, bool EPS>
+template <bool HAS_DIV, int G, bool EPS, int JOIN = 1>
 __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int nthr = 1024 / G;
@@ -259,7 +304,7 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
     int sweeps = 0;
     bool changed = !(bot && A.stop_on_bot) && np > 0;
     while(changed) {
-      const int f = pk_sweep<HAS_DIV>(*sh, a_T, a_S, tid, nthr, fin);
+      const int f = pk_sweep<HAS_DIV, JOIN>(*sh, a_T, a_S, tid, nthr, fin);
       ++sweeps;
       if(f & 2) *s_bot = 1;
       const int any_chg = gbar_or(bid, nthr, f & 1);
@@ -346,6 +391,14 @@ struct GroupPlan { int g = 0; size_t smem = 0; int sms = 0; size_t ptab_bytes = 
 
 template <bool EPS>
 static const void* group_kernel(bool has_div, int g) {
+  // LPC_JOIN picks another join variant for A/B runs (built for the 8-group kernel without divisions only). Measured on
+  // config 4, dense / AUTO (profiles/r02_ab_join.txt): 0 = 6.02 / 3.84 ms, 1 = 5.29 / 3.66 ms (default), 2 = 6.10 / 3.86 ms,
+  // 3 = 6.33 / 3.60 ms.
+  static int join = -1;
+  if(join < 0) { const char* e = getenv("LPC_JOIN"); join = e ? atoi(e) : 1; }
+  if(!has_div && g == 8 && join == 0) return (const void*)k_pir_group<false, 8, EPS, 0>;
+  if(!has_div && g == 8 && join == 2) return (const void*)k_pir_group<false, 8, EPS, 2>;
+  if(!has_div && g == 8 && join == 3) return (const void*)k_pir_group<false, 8, EPS, 3>;
   switch(g) {
     case 8: return has_div ? (const void*)k_pir_group<true, 8, EPS> : (const void*)k_pir_group<false, 8, EPS>;
     case 4: return has_div ? (const void*)k_pir_group<true, 4, EPS> : (const void*)k_pir_group<false, 4, EPS>;
