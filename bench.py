@@ -194,7 +194,7 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
 
     def timed(mode, k_steps, k_warm):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k_steps)]
-        res, l0 = None, L.launch_count()
+        res, l0, kms = None, L.launch_count(), []
         for i in range(k_warm + k_steps):
             flush.zero_()
             if dist is not None:
@@ -209,12 +209,14 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
             if i >= k_warm:
                 ev[i - k_warm][1].record()
             res = eps.collect()
+            if i >= k_warm:
+                kms.append(res.device_ms)
             torch.cuda.synchronize()
         ms = [a.elapsed_time(b) for a, b in ev]
-        return ms, res, L.launch_count() - l0
+        return ms, res, L.launch_count() - l0, float(np.mean(kms))
 
     with ClockSampler(rank) as clk:
-        ms, res, launches = timed(L.MODE_SWEEP, steps, warmup)
+        ms, res, launches, kernel_ms = timed(L.MODE_SWEEP, steps, warmup)
     my_ms = float(np.mean(ms))
     tot = torch.tensor([float(np.sum(ms)), float(res.deductions), float(res.sweeps_total)], dtype=torch.float64, device="cuda")
     tmax = tot.clone()
@@ -224,7 +226,8 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
     step_ms = float(tmax[0]) / steps
     reduced = sharding.fold_payload(payload.cpu().tolist())
     out.update({"value": float(tot[1]) / (step_ms * 1e-3), "ms_per_step": step_ms, "gpu_launches": int(launches),
-                "rank_ms": _rank_stats(my_ms, dist, world), "clocks": clk.summary(),
+                "rank_ms": _rank_stats(my_ms, dist, world), "rank_kernel_ms": _rank_stats(kernel_ms, dist, world),
+                "clocks": clk.summary(),
                 "batch_result": {"n_solution": reduced[0], "n_bot": reduced[1], "n_unknown": reduced[2], "best_bound": reduced[3],
                                  "sweeps_total": float(tot[2]), "max_sweeps_seen": res.max_sweeps_seen,
                                  "deductions_per_step": float(tot[1])},
@@ -301,7 +304,7 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
                           "subproblems generated on the chip -> fixpoints -> flags, reduction record and the compacted "
                           "non-failed stores (%d here) back to pinned host memory; wall clock, max over ranks" % nw}
     # ---- time to result in the default mode: propagators entailed on the root are dropped -------------
-    ms_a, res_a, _ = timed(L.MODE_AUTO, min(steps, 10), 2)
+    ms_a, res_a, _, _ = timed(L.MODE_AUTO, min(steps, 10), 2)
     ms_ae, v_ae, _ = e2e(L.MODE_AUTO, min(steps, 10))
     ta = torch.tensor([float(np.mean(ms_a))], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -659,7 +662,7 @@ def main():
     line["roofline"] = issue_roofline(out["value"] / world, out["clocks"])
     if world > 1 and not args.no_strong:
         s = own_eps(args, rank, world, "strong", ctx, check=True)
-        line["strong"] = {k: s[k] for k in ("config", "value", "ms_per_step", "rank_ms", "e2e", "time_to_result", "batch_result", "checks") if k in s}
+        line["strong"] = {k: s[k] for k in ("config", "value", "ms_per_step", "rank_ms", "rank_kernel_ms", "e2e", "time_to_result", "batch_result", "checks") if k in s}
         line["strong"]["unit"] = UNIT
         line["gpu_launches"] += s["gpu_launches"]
     if world == 1:

@@ -78,6 +78,22 @@ int lpc_measure_l2_copy_gbs(int64_t bytes, int iters, double* gbs);
  * operation and is applied by lpc_table_clamp_reified(). */
 int lpc_table_create(const lpc_bytecode* records, int64_t n, int32_t nvars, lpc_table** out);
 int lpc_table_destroy(lpc_table* t);
+/* Incremental build, the way PIR::deduce(tell) grows its table (pir.hpp:326-352; the reference's tests tell between
+ * fixpoints, tests/pir_test.cpp:485, 577-581): an empty table over `nvars` variables; lpc_table_append adds records on the
+ * host side; lpc_table_finalize brings the device image up to date - with sort != 0 after the stable sort by
+ * (op, y, x, z) of pir.hpp:343-347 (only the appended tail is sorted and merged in), with sort == 0 in append order. The
+ * device arrays keep spare capacity (doubling), and only the part of the image behind the first record that moved is
+ * uploaded; the var -> records index of the change-driven kernels is rebuilt on first use. lpc_table_set_nvars widens the
+ * variable range (a tell that declares variables), lpc_table_truncate keeps the first n records (PIR::restore pops from
+ * the back of the table, pir.hpp:863-870). No call using the table may be in flight; batches and EPS handles created over
+ * the table before a finalize must be re-created. */
+int lpc_table_create_empty(int32_t nvars, lpc_table** out);
+int lpc_table_append(lpc_table* t, const lpc_bytecode* records, int64_t n);
+int lpc_table_set_nvars(lpc_table* t, int32_t nvars);
+int lpc_table_truncate(lpc_table* t, int64_t n);
+int lpc_table_finalize(lpc_table* t, int32_t sort);
+/* Table bytes copied to the device since the table was created (diagnostic: what incremental tells cost). */
+int64_t lpc_table_uploaded_bytes(const lpc_table* t);
 /* PIR::num_deductions (pir.hpp:382-384). */
 int64_t lpc_table_size(const lpc_table* t);
 int32_t lpc_table_nvars(const lpc_table* t);

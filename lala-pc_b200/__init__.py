@@ -98,6 +98,12 @@ SIGNATURES = {
     "lpc_measure_l2_copy_gbs": (ctypes.c_int, [_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "lpc_table_create": (ctypes.c_int, [_vp, _i64, _i32, _pvp]),
     "lpc_table_destroy": (ctypes.c_int, [_vp]),
+    "lpc_table_create_empty": (ctypes.c_int, [_i32, _pvp]),
+    "lpc_table_append": (ctypes.c_int, [_vp, _vp, _i64]),
+    "lpc_table_set_nvars": (ctypes.c_int, [_vp, _i32]),
+    "lpc_table_truncate": (ctypes.c_int, [_vp, _i64]),
+    "lpc_table_finalize": (ctypes.c_int, [_vp, _i32]),
+    "lpc_table_uploaded_bytes": (_i64, [_vp]),
     "lpc_table_size": (_i64, [_vp]),
     "lpc_table_nvars": (_i32, [_vp]),
     "lpc_table_load": (ctypes.c_int, [_vp, _i64, _pi32]),
@@ -216,11 +222,42 @@ def _opts(mode=MODE_AUTO, max_sweeps=0, stop_on_bot=True, stream=0, switch_div=0
 class Table:
     """Immutable device propagator table (battery::vector<bytecode_type>, pir.hpp:104,115-118)."""
 
-    def __init__(self, records, nvars):
-        r = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, 4)
+    def __init__(self, records=None, nvars=0):
+        """`records` None: an empty table to be grown by append() + finalize() (PIR::deduce(tell), pir.hpp:326-352)."""
         self._h = ctypes.c_void_p()
-        _check(_L.lpc_table_create(r.ctypes.data, r.shape[0], nvars, ctypes.byref(self._h)))
+        if records is None:
+            _check(_L.lpc_table_create_empty(nvars, ctypes.byref(self._h)))
+        else:
+            r = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, 4)
+            _check(_L.lpc_table_create(r.ctypes.data, r.shape[0], nvars, ctypes.byref(self._h)))
         self.nvars = nvars
+
+    def append(self, records):
+        r = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, 4)
+        _check(_L.lpc_table_append(self._h, r.ctypes.data, r.shape[0]))
+
+    def set_nvars(self, nvars):
+        _check(_L.lpc_table_set_nvars(self._h, nvars))
+        self.nvars = nvars
+
+    def truncate(self, n):
+        _check(_L.lpc_table_truncate(self._h, n))
+
+    def finalize(self, sort=True):
+        """Bring the device image up to date; sort=True: stable sort by (op, y, x, z) first (pir.hpp:343-347)."""
+        _check(_L.lpc_table_finalize(self._h, int(sort)))
+
+    def uploaded_bytes(self):
+        return int(_L.lpc_table_uploaded_bytes(self._h))
+
+    def records(self):
+        n = len(self)
+        out = np.empty((n, 4), dtype=np.int32)
+        row = (ctypes.c_int32 * 4)()
+        for i in range(n):
+            _check(_L.lpc_table_load(self._h, i, row))
+            out[i] = tuple(row)
+        return out
 
     def __len__(self):
         return int(_L.lpc_table_size(self._h))
@@ -613,9 +650,9 @@ class PIR:
     name = "PIR"
 
     def __init__(self, nvars):
-        self._records = np.zeros((0, 4), dtype=np.int32)
+        self._n = 0
         self.store = Store(nvars)
-        self._table = None
+        self._table = Table(None, nvars)
 
     # -- build step: PIR::deduce(const tell_type&) (pir.hpp:326-352) --
     def tell(self, records=(), domains=()):
@@ -625,25 +662,21 @@ class PIR:
             changed |= self.store.embed(v, lb, ub)
         recs = np.asarray(list(records), dtype=np.int32).reshape(-1, 4)
         if len(recs):
-            self._records = sort_records(np.concatenate([self._records, recs]))
-            self._rebuild()
+            # incremental: only the appended records are sorted and merged in, only the changed part of the device image
+            # is uploaded (lpc_table_append / lpc_table_finalize)
+            self._table.append(recs)
+            self._table.finalize(sort=True)
+            self._n += len(recs)
             _check(_L.lpc_table_clamp_reified(self._table._h, self.store._h))
             changed = True
         return changed
 
-    def _rebuild(self):
-        if self._table is not None:
-            self._table.close()
-        self._table = Table(self._records, self.store.nvars)
-
     @property
     def table(self):
-        if self._table is None:
-            self._rebuild()
         return self._table
 
     def num_deductions(self):
-        return len(self._records)
+        return self._n
 
     def load_deduce(self, i):
         return self.table.load(i)
@@ -682,12 +715,15 @@ class PIR:
         return self.store.nvars
 
     def snapshot(self):
-        return len(self._records), self.store.read()
+        return self._n, self.store.read()
 
     def restore(self, snap):
+        """pir.hpp:863-870: pops the records behind the snapshot's count from the back of the (sorted) table."""
         n, values = snap
-        if n != len(self._records):
-            raise LpcError("restore across a table change needs the records told since the snapshot")
+        if n < self._n:
+            self._table.truncate(n)
+            self._table.finalize(sort=True)
+            self._n = n
         self.store.write(values)
 
     def is_extractable(self):

@@ -36,10 +36,6 @@ struct lpc_batch {
   cudaStream_t last_stream = nullptr;
   bool pending = false;
   int sbytes = 0;
-  bool dual_idx16 = false;               // ... with the table staged as 16-bit byte offsets
-  int dual = -1;                         // groups per block of k_pir_batch2 (0 = one store per block): -1 = not decided yet
-  size_t dual_smem = 0;
-  int dual_grid = 0;
   bool plan_ready[2] = {false, false}; // [dense, change-driven]
   bool table_smem[2] = {false, false};
   size_t smem[2] = {0, 0};
@@ -59,6 +55,7 @@ struct lpc_batch {
   int2* d_root = nullptr; bool root_valid = false;
   int grp_g = -1; size_t grp_smem = 0; int grp_grid = 0;   // plan of the grouped kernel (-1 = not decided, 0 = unusable)
   int rank = 0, world = 1;           // lpc_batch_set_rank
+  long long table_gen = 0;           // lpc_table::generation at creation: a table that changed since needs a new batch
 };
 
 // pir_eps.cu: the grouped kernel over resident store images (called by batch_launch_range of pir_batch.cu).

@@ -164,103 +164,216 @@ int lpc_device_init(int device) {
 }
 
 // ---- table ---------------------------------------------------------------------------------------------------------
-int lpc_table_create(const lpc_bytecode* records, int64_t n, int32_t nvars, lpc_table** out) {
+// The host keeps the records in the caller's order (load_deduce); the device keeps the SoA image with spare capacity, so
+// that an incremental tell (lpc_table_append + lpc_table_finalize) uploads only the part of the arrays that changed.
+static int no_device() {
+  int cnt = 0;
+  lpc_device_count(&cnt);
+  if(cnt == 0) { set_error("no CUDA device: this library has no CPU path"); return LPC_ERR_NO_DEVICE; }
+  return LPC_OK;
+}
+
+int lpc_table_create_empty(int32_t nvars, lpc_table** out) {
   LPC_REQUIRE(out != nullptr, "null out");
-  LPC_REQUIRE(n >= 0 && (n == 0 || records != nullptr), "bad records");
   LPC_REQUIRE(nvars >= 0, "bad nvars");
-  LPC_REQUIRE(n < (1ll << 31) - 8, "too many records");
-  int dev = 0;
-  {
-    int cnt = 0;
-    lpc_device_count(&cnt);
-    if(cnt == 0) { set_error("no CUDA device: this library has no CPU path"); return LPC_ERR_NO_DEVICE; }
-  }
-  LPC_CUDA(cudaGetDevice(&dev));
-  // padded with NOP records to a multiple of 16: quads for the 128-bit loads, 16-B granules for the bulk copies
-  long long n_pad = (n + 15) / 16 * 16;
-  if(n_pad == 0) n_pad = 16;
-  std::vector<uint8_t> op(n_pad, (uint8_t)D_NOP);
-  std::vector<int> x(n_pad, 0), y(n_pad, 0), z(n_pad, 0);
+  int rc = no_device();
+  if(rc) return rc;
   lpc_table* t = new lpc_table();
-  t->device = dev;
-  for(int64_t i = 0; i < n; ++i) {
-    const lpc_bytecode& b = records[i];
-    int d = to_dev_op(b.op);
-    if(d < 0) { delete t; set_error("lpc_table_create: record %lld has unsupported op %d", (long long)i, b.op); return LPC_ERR_UNSUPPORTED; }
-    if(b.x < 0 || b.x >= nvars || b.y < 0 || b.y >= nvars || b.z < 0 || b.z >= nvars) {
-      delete t; set_error("lpc_table_create: record %lld has a variable out of range", (long long)i); return LPC_ERR_INVALID;
-    }
-    op[i] = (uint8_t)d; x[i] = b.x; y[i] = b.y; z[i] = b.z;
-    t->op_count[d]++;
-    if(d >= D_TDIV && d <= D_EDIV) t->has_div = true;
-  }
-  t->host.assign(records, records + n);
-  {   // opcode runs (OpSegs)
-    OpSegs& sg = t->opsegs;
-    sg.n = 0;
-    bool ok = true;
-    for(int64_t i = 0; i < n && ok; ++i) {
-      if(i == 0 || op[i] != op[i - 1]) {
-        if(sg.n == LPC_MAX_OPSEG) { ok = false; break; }
-        sg.op[sg.n] = op[i];
-        sg.start[sg.n++] = (int)i;
-      }
-    }
-    if(!ok) sg.n = 0;
-    sg.start[sg.n] = (int)n;
-  }
-  // var -> records incidence (counting sort)
-  std::vector<int> off((size_t)nvars + 1, 0);
-  auto each_var = [&](int64_t i, auto f) {
-    f(x[i]);
-    if(y[i] != x[i]) f(y[i]);
-    if(z[i] != x[i] && z[i] != y[i]) f(z[i]);
-  };
-  for(int64_t i = 0; i < n; ++i) each_var(i, [&](int v) { off[v + 1]++; });
-  for(int v = 0; v < nvars; ++v) off[v + 1] += off[v];
-  std::vector<int> idx((size_t)std::max(1, off[nvars]));
-  {
-    std::vector<int> cur(off.begin(), off.end() - 1);
-    for(int64_t i = 0; i < n; ++i) each_var(i, [&](int v) { idx[cur[v]++] = (int)i; });
-  }
-  auto up = [&](void** d, const void* h, size_t bytes) -> int {
-    LPC_CUDA(cudaMalloc(d, std::max<size_t>(bytes, 16)));
-    if(bytes) LPC_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
-    return LPC_OK;
-  };
-  int rc;
-  if((rc = up(&t->d_op, op.data(), n_pad)) || (rc = up(&t->d_x, x.data(), n_pad * 4)) ||
-     (rc = up(&t->d_y, y.data(), n_pad * 4)) || (rc = up(&t->d_z, z.data(), n_pad * 4)) ||
-     (rc = up(&t->d_inc_off, off.data(), off.size() * 4)) || (rc = up(&t->d_inc_idx, idx.data(), idx.size() * 4))) {
-    lpc_table_destroy(t);
-    return rc;
-  }
-  t->dev.op = (const uint8_t*)t->d_op; t->dev.x = (const int*)t->d_x; t->dev.y = (const int*)t->d_y; t->dev.z = (const int*)t->d_z;
-  t->dev.n = n; t->dev.n_pad = n_pad; t->dev.nvars = nvars;
-  t->dev.inc_off = (const int*)t->d_inc_off; t->dev.inc_idx = (const int*)t->d_inc_idx;
-  t->dev.x16 = t->dev.y16 = t->dev.z16 = nullptr;
-  if(nvars <= 8191) {   // small enough for 16-bit byte offsets: the shared-memory form of the batch kernels
-    std::vector<unsigned short> x16(n_pad), y16(n_pad), z16(n_pad);
-    for(long long i = 0; i < n_pad; ++i) { x16[i] = (unsigned short)(8 * x[i]); y16[i] = (unsigned short)(8 * y[i]); z16[i] = (unsigned short)(8 * z[i]); }
-    if((rc = up(&t->d_x16, x16.data(), n_pad * 2)) || (rc = up(&t->d_y16, y16.data(), n_pad * 2)) || (rc = up(&t->d_z16, z16.data(), n_pad * 2))) {
-      lpc_table_destroy(t);
-      return rc;
-    }
-    t->dev.x16 = (const unsigned short*)t->d_x16; t->dev.y16 = (const unsigned short*)t->d_y16; t->dev.z16 = (const unsigned short*)t->d_z16;
-  }
+  cudaError_t e = cudaGetDevice(&t->device);
+  if(e != cudaSuccess) { delete t; return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__); }
   cudaDeviceProp prop;
-  LPC_CUDA(cudaGetDeviceProperties(&prop, dev));
+  e = cudaGetDeviceProperties(&prop, t->device);
+  if(e != cudaSuccess) { delete t; return cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__); }
   t->sm_count = prop.multiProcessorCount;
   t->smem_optin = prop.sharedMemPerBlockOptin;
+  t->dev.nvars = nvars;
+  if((rc = lpc_table_finalize(t, 0))) { lpc_table_destroy(t); return rc; }
   *out = t;
   return LPC_OK;
 }
 
+int lpc_table_append(lpc_table* t, const lpc_bytecode* records, int64_t n) {
+  LPC_REQUIRE(t != nullptr, "null table");
+  LPC_REQUIRE(n >= 0 && (n == 0 || records != nullptr), "bad records");
+  // 3 incidences per record must fit the int offsets of the var -> records index
+  LPC_REQUIRE((int64_t)t->host.size() + n <= (int64_t)(INT_MAX / 3) - 16, "too many records");
+  const int nvars = t->dev.nvars;
+  for(int64_t i = 0; i < n; ++i) {
+    const lpc_bytecode& b = records[i];
+    if(to_dev_op(b.op) < 0) { set_error("lpc_table_append: record %lld has unsupported op %d", (long long)i, b.op); return LPC_ERR_UNSUPPORTED; }
+    if(b.x < 0 || b.x >= nvars || b.y < 0 || b.y >= nvars || b.z < 0 || b.z >= nvars) {
+      set_error("lpc_table_append: record %lld has a variable out of range", (long long)i); return LPC_ERR_INVALID;
+    }
+  }
+  t->dirty_from = std::min<long long>(t->dirty_from, (long long)t->host.size());
+  t->host.insert(t->host.end(), records, records + n);
+  t->finalized = false;
+  return LPC_OK;
+}
+
+int lpc_table_set_nvars(lpc_table* t, int32_t nvars) {
+  LPC_REQUIRE(t != nullptr, "null table");
+  LPC_REQUIRE(nvars >= t->dev.nvars, "the variable range of a table can only grow");
+  if(nvars != t->dev.nvars) {
+    t->dev.nvars = nvars;
+    t->finalized = false;
+  }
+  return LPC_OK;
+}
+
+int lpc_table_truncate(lpc_table* t, int64_t n) {
+  LPC_REQUIRE(t != nullptr && n >= 0 && n <= (int64_t)t->host.size(), "bad record count");
+  if(n < (int64_t)t->host.size()) {
+    t->host.resize((size_t)n);
+    t->dirty_from = std::min<long long>(t->dirty_from, n);
+    t->finalized = false;
+  }
+  return LPC_OK;
+}
+
+static bool rec_less(const lpc_bytecode& a, const lpc_bytecode& b) {   // pir.hpp:343-347
+  if(a.op != b.op) return a.op < b.op;
+  if(a.y != b.y) return a.y < b.y;
+  if(a.x != b.x) return a.x < b.x;
+  return a.z < b.z;
+}
+
+int lpc_table_finalize(lpc_table* t, int32_t sort) {
+  LPC_REQUIRE(t != nullptr, "null table");
+  int rc = lpc_check_device(t->device, "lpc_table_finalize");
+  if(rc) return rc;
+  const long long n = (long long)t->host.size();
+  if(sort) {
+    // stable sort by (op, y, x, z). When the part already on the device is sorted, only the appended tail is sorted and
+    // merged in, and the image changes from the place where the smallest new record lands.
+    const long long old_n = std::min<long long>(t->sorted_n, n);
+    if(old_n < n) {
+      auto b0 = t->host.begin();
+      t->dirty_from = std::min<long long>(t->dirty_from, old_n);   // the unsorted tail may hold records already uploaded
+      std::stable_sort(b0 + old_n, t->host.end(), rec_less);
+      if(old_n > 0) {
+        const long long ins = std::upper_bound(b0, b0 + old_n, t->host[(size_t)old_n], rec_less) - b0;
+        t->dirty_from = std::min<long long>(t->dirty_from, ins);
+        std::inplace_merge(b0, b0 + old_n, t->host.end(), rec_less);
+      }
+    }
+    t->sorted_n = n;
+  }
+  else t->sorted_n = std::min<long long>(t->sorted_n, t->dirty_from);
+  long long n_pad = (n + 15) / 16 * 16;   // quads for the 128-bit loads, 16-B granules for the bulk copies
+  if(n_pad == 0) n_pad = 16;
+  LPC_CUDA(cudaDeviceSynchronize());   // no kernel may still be reading the arrays that are about to change
+  long long from = std::min<long long>(t->dirty_from, n) / 16 * 16;
+  if(n_pad > t->cap_pad) {   // grow geometrically; everything is uploaded again
+    const long long cap = std::max<long long>(n_pad, t->cap_pad * 2);
+    cudaFree(t->d_op); cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z);
+    t->d_op = t->d_x = t->d_y = t->d_z = nullptr;
+    t->cap_pad = 0;
+    LPC_CUDA(cudaMalloc(&t->d_op, (size_t)cap));
+    LPC_CUDA(cudaMalloc(&t->d_x, (size_t)cap * 4));
+    LPC_CUDA(cudaMalloc(&t->d_y, (size_t)cap * 4));
+    LPC_CUDA(cudaMalloc(&t->d_z, (size_t)cap * 4));
+    t->cap_pad = cap;
+    from = 0;
+  }
+  {   // upload records [from, n_pad) of the SoA image (NOP padding behind n)
+    const long long m = n_pad - from;
+    std::vector<uint8_t> op((size_t)m, (uint8_t)D_NOP);
+    std::vector<int> x((size_t)m, 0), y((size_t)m, 0), z((size_t)m, 0);
+    for(long long i = from; i < n; ++i) {
+      const lpc_bytecode& b = t->host[(size_t)i];
+      op[i - from] = (uint8_t)to_dev_op(b.op); x[i - from] = b.x; y[i - from] = b.y; z[i - from] = b.z;
+    }
+    if(m > 0) {
+      LPC_CUDA(cudaMemcpy((uint8_t*)t->d_op + from, op.data(), (size_t)m, cudaMemcpyHostToDevice));
+      LPC_CUDA(cudaMemcpy((int*)t->d_x + from, x.data(), (size_t)m * 4, cudaMemcpyHostToDevice));
+      LPC_CUDA(cudaMemcpy((int*)t->d_y + from, y.data(), (size_t)m * 4, cudaMemcpyHostToDevice));
+      LPC_CUDA(cudaMemcpy((int*)t->d_z + from, z.data(), (size_t)m * 4, cudaMemcpyHostToDevice));
+    }
+    t->uploaded_bytes += (long long)m * 13;
+  }
+  // operator statistics and opcode runs (OpSegs)
+  t->has_div = false;
+  for(int d = 0; d < 10; ++d) t->op_count[d] = 0;
+  OpSegs& sg = t->opsegs;
+  sg.n = 0;
+  bool ok = true;
+  int prev = -1;
+  for(long long i = 0; i < n; ++i) {
+    const int d = to_dev_op(t->host[(size_t)i].op);
+    t->op_count[d]++;
+    if(d >= D_TDIV && d <= D_EDIV) t->has_div = true;
+    if(ok && d != prev) {
+      if(sg.n == LPC_MAX_OPSEG) ok = false;
+      else { sg.op[sg.n] = (unsigned char)d; sg.start[sg.n++] = (int)i; }
+    }
+    prev = d;
+  }
+  if(!ok) sg.n = 0;
+  sg.start[sg.n] = (int)n;
+  t->dev.op = (const uint8_t*)t->d_op; t->dev.x = (const int*)t->d_x; t->dev.y = (const int*)t->d_y; t->dev.z = (const int*)t->d_z;
+  t->dev.n = n; t->dev.n_pad = n_pad;
+  // whatever was derived from the old contents is rebuilt on first use: the var -> records index, the launch plans, the
+  // staging store of lpc_fixpoint_host; batches created over the old contents refuse to run (generation)
+  t->csr_valid = false;
+  t->dev.inc_off = nullptr; t->dev.inc_idx = nullptr;
+  t->plan_ready = false;
+  if(t->host_store && lpc_store_nvars(t->host_store) != t->dev.nvars) { lpc_store_destroy(t->host_store); t->host_store = nullptr; }
+  t->dirty_from = n;
+  t->finalized = true;
+  t->generation++;
+  return LPC_OK;
+}
+
+// var -> records incidence (CSR) for the change-driven kernels, built when one of them first needs it.
+int lpc_table_ensure_csr(lpc_table* t) {
+  if(t->csr_valid) return LPC_OK;
+  LPC_REQUIRE(t->finalized, "lpc_table_finalize has not been called since the last change of the table");
+  const long long n = t->dev.n;
+  const int nvars = t->dev.nvars;
+  std::vector<int> off((size_t)nvars + 1, 0);
+  auto each_var = [&](long long i, auto f) {
+    const lpc_bytecode& b = t->host[(size_t)i];
+    f(b.x);
+    if(b.y != b.x) f(b.y);
+    if(b.z != b.x && b.z != b.y) f(b.z);
+  };
+  for(long long i = 0; i < n; ++i) each_var(i, [&](int v) { off[v + 1]++; });
+  for(int v = 0; v < nvars; ++v) off[v + 1] += off[v];
+  std::vector<int> idx((size_t)std::max(1, off[nvars]));
+  {
+    std::vector<int> cur(off.begin(), off.end() - 1);
+    for(long long i = 0; i < n; ++i) each_var(i, [&](int v) { idx[cur[v]++] = (int)i; });
+  }
+  LPC_CUDA(cudaDeviceSynchronize());
+  cudaFree(t->d_inc_off); cudaFree(t->d_inc_idx);
+  t->d_inc_off = t->d_inc_idx = nullptr;
+  LPC_CUDA(cudaMalloc(&t->d_inc_off, off.size() * 4));
+  LPC_CUDA(cudaMalloc(&t->d_inc_idx, idx.size() * 4));
+  LPC_CUDA(cudaMemcpy(t->d_inc_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  LPC_CUDA(cudaMemcpy(t->d_inc_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
+  t->dev.inc_off = (const int*)t->d_inc_off; t->dev.inc_idx = (const int*)t->d_inc_idx;
+  t->csr_valid = true;
+  return LPC_OK;
+}
+
+int lpc_table_create(const lpc_bytecode* records, int64_t n, int32_t nvars, lpc_table** out) {
+  LPC_REQUIRE(out != nullptr, "null out");
+  LPC_REQUIRE(n >= 0 && (n == 0 || records != nullptr), "bad records");
+  lpc_table* t = nullptr;
+  int rc = lpc_table_create_empty(nvars, &t);
+  if(rc) return rc;
+  if((rc = lpc_table_append(t, records, n)) || (rc = lpc_table_finalize(t, 0))) { lpc_table_destroy(t); return rc; }
+  *out = t;
+  return LPC_OK;
+}
+
+int64_t lpc_table_uploaded_bytes(const lpc_table* t) { return t ? (int64_t)t->uploaded_bytes : 0; }
+
 int lpc_table_destroy(lpc_table* t) {
   if(!t) return LPC_OK;
   cudaFree(t->d_op); cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z);
-  cudaFree(t->d_inc_off); cudaFree(t->d_inc_idx); cudaFree(t->d_chunk);
-  cudaFree(t->d_x16); cudaFree(t->d_y16); cudaFree(t->d_z16);
+  cudaFree(t->d_inc_off); cudaFree(t->d_inc_idx);
   if(t->host_store) lpc_store_destroy(t->host_store);
   delete t;
   return LPC_OK;

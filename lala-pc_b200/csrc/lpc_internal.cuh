@@ -43,11 +43,6 @@ struct TableDev {
   // var -> records incidence (CSR), for the change-driven worklist
   const int* inc_off;   // [nvars + 1]
   const int* inc_idx;   // [3 n] (duplicates removed per record)
-  // x / y / z as 16-bit byte offsets into a store image (8 * vid), present iff nvars <= 8191: the form the batch kernels
-  // stage in shared memory (7 B per record instead of 13, and the gather address is one add)
-  const unsigned short* x16;
-  const unsigned short* y16;
-  const unsigned short* z16;
 };
 
 // Runs of equal opcode in table order (exact record indices, padding excluded). A table built by PIR::deduce(tell) is
@@ -82,22 +77,29 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 struct lpc_store;
 int lpc_dirty_fixpoint_launch(struct lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o);   // pir_dirty.cu
 int lpc_check_device(int handle_device, const char* what);                                       // pir_fixpoint.cu
+extern "C" int lpc_table_ensure_csr(struct lpc_table* t);                                                   // lpc_core.cu
 struct lpc_table {
   int device = 0;
   std::vector<lpc_bytecode> host;   // the caller's records, caller's order (load_deduce)
   lpc::TableDev dev{};
   void* d_op = nullptr; void* d_x = nullptr; void* d_y = nullptr; void* d_z = nullptr;
   void* d_inc_off = nullptr; void* d_inc_idx = nullptr;
-  void* d_x16 = nullptr; void* d_y16 = nullptr; void* d_z16 = nullptr;
   bool has_div = false;
   long long op_count[10] = {0};
+  // incremental build (lpc_table_append / lpc_table_finalize)
+  long long cap_pad = 0;            // records the device arrays have room for
+  long long dirty_from = 0;         // first record whose device image is stale
+  long long sorted_n = 0;           // the first sorted_n records are in (op, y, x, z) order
+  long long uploaded_bytes = 0;     // table bytes copied to the device so far (diagnostic: lpc_table_uploaded_bytes)
+  bool finalized = false;
+  bool csr_valid = false;           // var -> records index (lpc_table_ensure_csr)
+  long long generation = 0;         // bumped by every finalize; batches remember the one they were created over
   lpc::OpSegs opsegs{};             // opcode runs for the per-operator loops of the block kernels (pir_batch.cu)
   // launch plan of the dense sweep, computed once on first use (opcode segments in quads, blocks per SM)
   bool plan_ready = false;
   int seg_n = 0;
   int seg_q[17] = {0};
   int blocks_per_sm[2] = {0, 0};    // [track]
-  void* d_chunk = nullptr;          // unused (kept for ABI stability of the handle)
   int sm_count = 0;
   size_t smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin
   lpc_store* host_store = nullptr;  // device staging store of lpc_fixpoint_host

@@ -312,155 +312,6 @@ __global__ void k_pir_batch(TableDev t, OpSegs segs, int2* stores, int n_stores,
   }
 }
 
-// ---- two stores in flight per block -----------------------------------------------------------------------------------
-// ncu on k_pir_batch (config 4): 15 % of the samples sit at the per-sweep block barrier and a third of the issue slots
-// are empty - with ~10 records per thread between two barriers every divergent warp makes 31 others wait. Here the
-// block's 1024 threads are two independent halves of 512; each half owns a store ring, claims its own stores and
-// synchronises on its own named barrier (bar.sync / bar.red with an id and a thread count), so one half's barrier and
-// copy waits are filled with the other half's instructions. The table stays ONE shared-memory copy per SM.
-// Shared memory: [mbarriers + scalars 128 B][half 0: 2 x sbytes][half 1: 2 x sbytes][table x | y | z | op].
-__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ int nbar_or(int id, int n, int pred) {
-  int r;
-  asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.or.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
-               : "=r"(r) : "r"(id), "r"(n), "r"(pred) : "memory");
-  return r;
-}
-__device__ __forceinline__ int nbar_and(int id, int n, int pred) {
-  int r;
-  asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.and.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
-               : "=r"(r) : "r"(id), "r"(n), "r"(pred) : "memory");
-  return r;
-}
-
-// G groups of 1024 / G threads, SLOTS ring slots per group (2: the next store is prefetched while this one iterates;
-// 1: load, iterate, write back in turn - the other groups cover the copies). Fewer threads per store also make a sweep
-// more sequential, so a store needs fewer sweeps (config 4: 285 k sweeps in total with one store per block, 254 k at
-// G = 2, 235 k at G = 4, 217 k at G = 8; 9.5 / 7.6 / 6.8 / 6.4 ms per 65,536 stores).
-// IDX16: the table is staged as 16-bit byte offsets (7 B per record), which leaves room for more store slots.
-template <bool HAS_DIV, int G, int SLOTS, bool IDX16>
-__global__ void __launch_bounds__(1024, 1) k_pir_batch2(TableDev t, OpSegs segs, int2* stores, int n_stores, int sbytes, uint8_t* flags,
-                                                       int* sweeps_out, int* obj_out, BatchCtl* ctl, int objective_var,
-                                                       int max_sweeps, int stop_on_bot) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int nthr = 1024 / G;
-  const int grp = threadIdx.x / nthr, tid = threadIdx.x % nthr, bid = 1 + grp;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);   // [SLOTS * grp + slot]: store rings, [G * SLOTS]: table
-  int* s_next = reinterpret_cast<int*>(smem + 128 + 8 * grp);
-  volatile int* s_bot = reinterpret_cast<volatile int*>(smem + 128 + 8 * grp + 4);
-  unsigned char* ring_base = smem + 256 + (size_t)grp * SLOTS * sbytes;
-  int2* ring[2] = {reinterpret_cast<int2*>(ring_base), reinterpret_cast<int2*>(ring_base + (SLOTS - 1) * (size_t)sbytes)};
-  char* tb = reinterpret_cast<char*>(smem + 256 + (size_t)G * SLOTS * sbytes);
-  const int npad = (int)t.n_pad;
-  const size_t store_stride = (size_t)t.nvars;
-  unsigned long long* tbar = &bars[G * SLOTS];
-
-  if(threadIdx.x == 0) {
-    for(int i = 0; i <= G * SLOTS; ++i) mbar_init(&bars[i], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  int cur = G * blockIdx.x + grp < n_stores ? G * blockIdx.x + grp : -1;
-  constexpr int IW = IDX16 ? 2 : 4;   // bytes per index entry
-  if(threadIdx.x == 0) {
-    mbar_expect_tx(tbar, (unsigned)(npad * (3 * IW + 1)));
-    bulk_g2s_chunked(tb, IDX16 ? (const char*)t.x16 : (const char*)t.x, npad * IW, tbar);
-    bulk_g2s_chunked(tb + (size_t)npad * IW, IDX16 ? (const char*)t.y16 : (const char*)t.y, npad * IW, tbar);
-    bulk_g2s_chunked(tb + (size_t)npad * 2 * IW, IDX16 ? (const char*)t.z16 : (const char*)t.z, npad * IW, tbar);
-    bulk_g2s_chunked(tb + (size_t)npad * 3 * IW, (const char*)t.op, npad, tbar);
-  }
-  if(tid == 0 && cur >= 0) {
-    mbar_expect_tx(&bars[SLOTS * grp], (unsigned)sbytes);
-    bulk_g2s_chunked((char*)ring[0], (const char*)(stores + cur * store_stride), sbytes, &bars[SLOTS * grp]);
-  }
-  const int* sx = reinterpret_cast<const int*>(tb);
-  const int* sy = reinterpret_cast<const int*>(tb + (size_t)npad * IW);
-  const int* sz = reinterpret_cast<const int*>(tb + (size_t)npad * 2 * IW);
-  const uint8_t* sop = reinterpret_cast<const uint8_t*>(tb + (size_t)npad * 3 * IW);
-  mbar_wait(tbar, 0);
-  const unsigned a_x = smem_u32(sx), a_y = smem_u32(sy), a_z = smem_u32(sz), a_op = smem_u32(sop);
-
-  long long a_sol = 0, a_bot = 0, a_unk = 0, a_sweeps = 0, a_ded = 0;
-  int a_best = LPC_INF, a_maxsw = 0;
-  unsigned phase[2] = {0, 0};
-  int b = 0;
-  while(cur >= 0) {
-    if(tid == 0) {   // claim the next store of this group; with two slots, start fetching it into the other one
-      int nx = atomicAdd(&ctl->next_store, 1);
-      if(nx >= n_stores) nx = -1;
-      *s_next = nx;
-      if(SLOTS == 2 && nx >= 0) {
-        bulk_wait_read0();   // the write-back that last used the other slot has finished reading it
-        mbar_expect_tx(&bars[SLOTS * grp + (b ^ 1)], (unsigned)sbytes);
-        bulk_g2s_chunked((char*)ring[b ^ 1], (const char*)(stores + nx * store_stride), sbytes, &bars[SLOTS * grp + (b ^ 1)]);
-      }
-      *s_bot = 0;
-    }
-    mbar_wait(&bars[SLOTS * grp + b], phase[b]);
-    phase[b] ^= 1;
-    int2* S = ring[b];
-    const unsigned a_S = smem_u32(S);
-    int f0 = 0;
-    for(int v = tid; v < t.nvars; v += nthr) { int2 d = S[v]; f0 |= d.x > d.y; }
-    bool bot = nbar_or(bid, nthr, f0) != 0;   // also orders thread 0's s_bot / s_next writes before their readers
-    int sweeps = 0;
-    bool changed = !(bot && stop_on_bot) && t.n > 0;
-    while(changed) {
-      const int f = sweep_table<HAS_DIV, IDX16 ? 2 : 1, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
-      ++sweeps;
-      if(f & 2) *s_bot = 1;
-      const int any_chg = nbar_or(bid, nthr, f & 1);
-      bot |= *s_bot != 0;
-      changed = any_chg && !(bot && stop_on_bot) && !(max_sweeps && sweeps >= max_sweeps);
-    }
-    int all_ent = 0;
-    if(!bot) {   // entailment: the ask loop of is_extractable
-      int ok = 1;
-      for(int i = tid; i < npad && ok; i += nthr) {
-        int2 a, bb, c;
-        if(IDX16) { a = lds_itv(a_S + lds_u16(a_x + 2 * i)); bb = lds_itv(a_S + lds_u16(a_y + 2 * i)); c = lds_itv(a_S + lds_u16(a_z + 2 * i)); }
-        else { a = S[sx[i]]; bb = S[sy[i]]; c = S[sz[i]]; }
-        ok = ask_regs(sop[i], Itv(a.x, a.y), Itv(bb.x, bb.y), Itv(c.x, c.y));
-      }
-      all_ent = nbar_and(bid, nthr, ok);
-    }
-    fence_async_smem();
-    nbar_sync(bid, nthr);
-    const int nxt = *s_next;
-    if(tid == 0) {
-      for(int o = 0; o < sbytes; o += 32768) bulk_s2g((char*)(stores + cur * store_stride) + o, (char*)S + o, min(32768, sbytes - o));
-      bulk_commit();
-      flags[cur] = (uint8_t)((bot ? 1 : 0) | (all_ent ? 2 : 0));
-      sweeps_out[cur] = sweeps;
-      const int olb = objective_var >= 0 ? S[objective_var].x : LPC_INF;
-      if(obj_out) obj_out[cur] = olb;
-      if(bot) ++a_bot; else if(all_ent) ++a_sol; else ++a_unk;
-      if(!bot && objective_var >= 0) a_best = min(a_best, olb);
-      a_sweeps += sweeps;
-      a_ded += (long long)sweeps * t.n;
-      a_maxsw = max(a_maxsw, sweeps);
-      if(SLOTS == 1 && nxt >= 0) {   // one slot: the next store goes into the same image once the write-back has read it
-        bulk_wait_read0();
-        mbar_expect_tx(&bars[grp], (unsigned)sbytes);
-        bulk_g2s_chunked((char*)ring[0], (const char*)(stores + nxt * store_stride), sbytes, &bars[grp]);
-      }
-    }
-    cur = nxt;
-    nbar_sync(bid, nthr);   // everyone of this group has read s_next before its thread 0 overwrites it
-    if(SLOTS == 2) b ^= 1;
-  }
-  if(tid == 0) {
-    bulk_wait0();
-    if(a_sol) atomicAdd((unsigned long long*)&ctl->red[0], (unsigned long long)a_sol);
-    if(a_bot) atomicAdd((unsigned long long*)&ctl->red[1], (unsigned long long)a_bot);
-    if(a_unk) atomicAdd((unsigned long long*)&ctl->red[2], (unsigned long long)a_unk);
-    atomicMin(&ctl->red[3], (long long)a_best);
-    atomicAdd((unsigned long long*)&ctl->sweeps_total, (unsigned long long)a_sweeps);
-    atomicAdd((unsigned long long*)&ctl->deductions, (unsigned long long)a_ded);
-    atomicMax(&ctl->max_sweeps_seen, a_maxsw);
-  }
-}
-
 // ---- in-kernel search: propagate + branch on one store per block ------------------------------------------------------
 // snapshot / restore (pir.hpp:857-870) and branching moved next to the fixpoint, so that a
 // subproblem is SOLVED by its block instead of only propagated once. Depth-first, deterministic: the variable is the
@@ -689,17 +540,6 @@ using namespace lpc;
 
 typedef void (*batch_kernel_t)(TableDev, OpSegs, int2*, int, int, uint8_t*, int*, int*, BatchCtl*, int, int, int, const int*, int);
 
-static const void* batch2_kernel(bool has_div, int g, bool idx16) {
-#define LPC_B2(G, S) (idx16 ? (has_div ? (const void*)k_pir_batch2<true, G, S, true> : (const void*)k_pir_batch2<false, G, S, true>) \
-                            : (has_div ? (const void*)k_pir_batch2<true, G, S, false> : (const void*)k_pir_batch2<false, G, S, false>))
-  switch(g) {
-    case 2: return LPC_B2(2, 2);
-    case 4: return LPC_B2(4, 1);
-    case 8: return LPC_B2(8, 1);
-    default: return nullptr;
-  }
-#undef LPC_B2
-}
 static batch_kernel_t pick_batch_kernel(bool has_div, bool table_smem, bool cd) {
   if(cd) {
     if(has_div) return table_smem ? k_pir_batch<true, true, true> : k_pir_batch<true, false, true>;
@@ -715,8 +555,9 @@ extern "C" {
 int lpc_batch_create(const lpc_table* t, int32_t n_stores, lpc_batch** out) {
   LPC_REQUIRE(t && out, "null argument");
   LPC_REQUIRE(n_stores >= 0, "bad n_stores");
+  LPC_REQUIRE(t->finalized, "lpc_table_finalize has not been called since the last change of the table");
   lpc_batch* b = new lpc_batch();
-  b->table = t; b->n_stores = n_stores; b->nvars = t->dev.nvars;
+  b->table = t; b->n_stores = n_stores; b->nvars = t->dev.nvars; b->table_gen = t->generation;
   // ring slots are multiples of 16 B (bulk copy granularity); stores are packed at nvars*8 B in global memory, so
   // the per-store image must itself be a multiple of 16 B: require an even number of variables or pad by one.
   b->sbytes = ((b->nvars * 8 + 15) / 16) * 16;
@@ -841,12 +682,14 @@ int lpc_batch_set_seeds(lpc_batch* b, const int32_t* vars, int32_t n) {
 static int batch_launch_range(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var, int first, int count,
                               BatchCtl* d_ctl, BatchCtl* h_init, cudaStream_t st) {
   const lpc_table* t = b->table;
+  LPC_REQUIRE(t->generation == b->table_gen, "the table changed since this batch was created: create a new batch");
   // LPC_MODE_SWEEP / LPC_MODE_AUTO: every sweep evaluates every record; LPC_MODE_WORKLIST: change-driven (block_fixpoint_cd),
   // seeded by lpc_batch_set_seeds when the caller made that promise. AUTO resolves to dense because that is what is faster
   // on the models measured: on config 4 one halved decision variable floods the 10k-record model within two sweeps (the
   // seeded change-driven run still evaluates 62 % of the dense run's propagators) and the flagging costs more than it saves
   // (33 vs 15.5 ms per 65,536 stores).
   const int cd = o->mode == LPC_MODE_WORKLIST ? 1 : 0;
+  if(cd) { int rc = lpc_table_ensure_csr(const_cast<lpc_table*>(t)); if(rc) return rc; }
   if(!cd) {   // dense sweeps, large batch, model fits an SM: the grouped kernel over the packed table (pir_eps.cu)
     int used = 0;
     int rc = lpc_group_launch_resident(b, o, objective_var, first, count, d_ctl, h_init, st, &used);
@@ -881,56 +724,18 @@ static int batch_launch_range(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
     b->grid[cd] = std::max(1, std::min(b->n_stores, sms * per_sm));
     b->plan_ready[cd] = true;
   }
-  // dense mode with the table in shared memory and room for the store images of several groups next to it: G stores in
-  // flight per block (k_pir_batch2). LPC_BATCH_DUAL = 0 keeps one store per block, 2 / 4 / 8 force a group count (A/B runs).
-  if(b->dual < 0) {
-    b->dual = 0;
-    const char* e = getenv("LPC_BATCH_DUAL");
-    const int want = e ? atoi(e) : -1;
-    int dev = 0, sms = 0, optin = 0;
-    LPC_CUDA(cudaGetDevice(&dev));
-    LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    LPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const char* e16 = getenv("LPC_BATCH_IDX16");
-    b->dual_idx16 = t->dev.x16 != nullptr && b->nvars <= 8191 && (!e16 || atoi(e16));
-    const size_t tbl = (size_t)t->dev.n_pad * (b->dual_idx16 ? 7 : 13);
-    static const int kG[3] = {8, 4, 2};   // the most groups whose store slots fit next to the table
-    if(want != 0 && t->dev.n_pad >= 2048 && b->n_stores >= 8 * sms) {
-      for(int c = 0; c < 3 && !b->dual; ++c) {
-        const int g = want > 0 ? want : kG[c], sl = g == 2 ? 2 : 1;
-        const size_t need = 256 + (size_t)g * sl * b->sbytes + tbl;
-        const void* kk = batch2_kernel(t->has_div, g, b->dual_idx16);
-        if(!kk || need > (size_t)optin) { if(want > 0) break; else continue; }
-        LPC_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        int per_sm = 0;
-        LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kk, 1024, need));
-        if(per_sm >= 1) { b->dual = g; b->dual_smem = need; b->dual_grid = std::max(1, std::min((b->n_stores + g - 1) / g, sms)); }
-        if(want > 0) break;
-      }
-    }
-  }
-  const bool dual = !cd && b->dual >= 2;
   batch_kernel_t k = pick_batch_kernel(t->has_div, b->table_smem[cd], cd);
-  const int threads = dual ? 1024 : b->threads[cd];
-  const int grid = dual ? std::max(1, std::min(b->dual_grid, (count + b->dual - 1) / b->dual)) : std::max(1, std::min(b->grid[cd], count));
-  const size_t smem = dual ? b->dual_smem : b->smem[cd];
+  const int threads = b->threads[cd];
+  const int grid = std::max(1, std::min(b->grid[cd], count));
+  const size_t smem = b->smem[cd];
   memset(h_init, 0, sizeof(BatchCtl));
   h_init->red[3] = LPC_INF;
-  h_init->next_store = dual ? b->dual * grid : grid;
+  h_init->next_store = grid;
   h_init->rank = b->rank; h_init->world = b->world;
   LPC_CUDA(cudaMemcpyAsync(d_ctl, h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
   int2* dd = b->d + (size_t)first * b->nvars;
   uint8_t* fl = b->d_flags + first; int* sw = b->d_sweeps + first; int* ob = b->d_obj ? b->d_obj + first : nullptr;
-  if(count > 0 && dual) {
-    const void* kk = batch2_kernel(t->has_div, b->dual, b->dual_idx16);
-    TableDev td = t->dev; OpSegs sg = t->opsegs;
-    int ns = count, sb = b->sbytes;
-    BatchCtl* ct = d_ctl; int ov = objective_var, ms = o->max_sweeps, sob = o->stop_on_bot;
-    void* args[] = {&td, &sg, &dd, &ns, &sb, &fl, &sw, &ob, &ct, &ov, &ms, &sob};
-    LPC_CUDA(cudaLaunchKernel(kk, dim3(grid), dim3(threads), args, smem, st));
-    g_launches++;
-  }
-  else if(count > 0) {
+  if(count > 0) {
     k<<<grid, threads, smem, st>>>(t->dev, t->opsegs, dd, count, b->sbytes, fl, sw, ob, d_ctl,
                                   objective_var, o->max_sweeps, o->stop_on_bot, b->d_seeds, b->n_seeds);
     g_launches++;
@@ -1099,12 +904,14 @@ int lpc_batch_search(lpc_batch* b, const int32_t* branch_vars, int32_t n_branch,
   LPC_REQUIRE(o->max_depth >= 1, "max_depth must be at least 1");
   for(int i = 0; i < n_branch; ++i) LPC_REQUIRE(branch_vars[i] >= 0 && branch_vars[i] < b->nvars, "branching variable out of range");
   const lpc_table* t = b->table;
+  LPC_REQUIRE(t->generation == b->table_gen, "the table changed since this batch was created: create a new batch");
   cudaStream_t st = (cudaStream_t)o->stream;
   int dev = 0, sms = 0, optin = 0;
   LPC_CUDA(cudaGetDevice(&dev));
   LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   LPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const bool cd = o->change_driven != 0;
+  if(cd) { int rc = lpc_table_ensure_csr(const_cast<lpc_table*>(t)); if(rc) return rc; }
   const size_t base = 64 + (size_t)b->sbytes + (cd ? group_maps_bytes(t) : 0), tbl = (size_t)t->dev.n_pad * 13;
   if(base > (size_t)optin) { set_error("lpc_batch_search: a store of %d variables does not fit shared memory", b->nvars); return LPC_ERR_UNSUPPORTED; }
   const bool table_smem = base + tbl <= (size_t)optin;

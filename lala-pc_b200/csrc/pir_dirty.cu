@@ -219,6 +219,8 @@ using namespace lpc;
 // Called by lpc_fixpoint_async for LPC_MODE_AUTO. The three byte maps live with the store handle.
 int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opts* o) {
   cudaStream_t st = (cudaStream_t)o->stream;
+  int rc = lpc_table_ensure_csr(t);   // the var -> records index is built when a change-driven kernel first needs it
+  if(rc) return rc;
   const long long n_pad = t->dev.n_pad;
   const int n_groups = (int)((n_pad + 63) / 64);
   const int map_stride = (n_groups + 15) / 16 * 16;

@@ -10,6 +10,21 @@
 
 namespace lpc {
 
+// Negation as the division rules use it. With LPC_DIV_OPAQUE_NEG the device takes it through a call that is not inlined,
+// so that ptxas cannot fold the negation into a neighbouring three-input min / max (tools/repro/div_miscompile.cu).
+#if defined(LPC_DIV_OPAQUE_NEG)
+static __device__ __noinline__ int dneg_call(int a) { return (int)(0u - (unsigned)a); }
+LPC_HD int dneg(int a) {
+#ifdef __CUDA_ARCH__
+  return dneg_call(a);
+#else
+  return (int)(0u - (unsigned)a);
+#endif
+}
+#else
+LPC_HD int dneg(int a) { return wneg(a); }
+#endif
+
 #define xl r1.lb
 #define xu r1.ub
 #define yl r2.lb
@@ -20,8 +35,8 @@ namespace lpc {
 // pir.hpp:449-467 — r1 = r2 / r3
 LPC_HD void itv_div(int op, Itv& r1, Itv& r2, Itv& r3) {
   if(zl < 0 && zu > 0) {
-    r1.lb = max(xl, min(yl, yu == LPC_MINF ? LPC_INF : wneg(yu)));
-    r1.ub = min(xu, max(yl == LPC_INF ? LPC_MINF : wneg(yl), yu));
+    r1.lb = max(xl, min(yl, yu == LPC_MINF ? LPC_INF : dneg(yu)));
+    r1.ub = min(xu, max(yl == LPC_INF ? LPC_MINF : dneg(yl), yu));
   }
   else {
     if(zl == 0) r3.lb = 1;
@@ -38,8 +53,8 @@ LPC_HD void itv_div(int op, Itv& r1, Itv& r2, Itv& r3) {
 LPC_HD Itv num_fdiv(const Itv& r1, const Itv& r3) {
   const int xu1 = wadd(xu, 1);
   if(zl < 0 && zu > 0) {
-    return Itv(min(min(xl, wneg(xu)), min(wmul(xl, zu), wadd(wmul(xu1, zl), 1))),
-               max(max(wneg(xl), xu), max(wmul(xl, zl), wsub(wmul(xu1, zu), 1))));
+    return Itv(min(min(xl, dneg(xu)), min(wmul(xl, zu), wadd(wmul(xu1, zl), 1))),
+               max(max(dneg(xl), xu), max(wmul(xl, zl), wsub(wmul(xu1, zu), 1))));
   }
   else if(zl > 0 || zu < 0) {
     return Itv(min(min(wmul(xl, zl), wmul(xl, zu)), min(wadd(wmul(xu1, zl), 1), wadd(wmul(xu1, zu), 1))),
@@ -52,8 +67,8 @@ LPC_HD Itv num_fdiv(const Itv& r1, const Itv& r3) {
 LPC_HD Itv num_cdiv(const Itv& r1, const Itv& r3) {
   const int xl1 = wsub(xl, 1);
   if(zl < 0 && zu > 0) {
-    return Itv(min(min(xl, wneg(xu)), min(wmul(xu, zl), wadd(wmul(xl1, zu), 1))),
-               max(max(wneg(xl), xu), max(wmul(xu, zu), wsub(wmul(xl1, zl), 1))));
+    return Itv(min(min(xl, dneg(xu)), min(wmul(xu, zl), wadd(wmul(xl1, zu), 1))),
+               max(max(dneg(xl), xu), max(wmul(xu, zu), wsub(wmul(xl1, zl), 1))));
   }
   else if(zl > 0 || zu < 0) {
     return Itv(min(min(wmul(xu, zl), wmul(xu, zu)), min(wadd(wmul(xl1, zl), 1), wadd(wmul(xl1, zu), 1))),
@@ -67,7 +82,7 @@ LPC_HD Itv num_tdiv(const Itv& r1, const Itv& r3) {
   if(xl > 0) return num_fdiv(r1, r3);
   else if(xu < 0) return num_cdiv(r1, r3);
   else if(xl <= 0 && 0 <= xu) {
-    Itv r(wadd(min(zl, wneg(zu)), 1), wsub(max(wneg(zl), zu), 1));
+    Itv r(wadd(min(zl, dneg(zu)), 1), wsub(max(dneg(zl), zu), 1));
     if(xl != 0) r = fjoin(r, num_cdiv(Itv(xl, -1), r3));
     if(xu != 0) r = fjoin(r, num_fdiv(Itv(1, xu), r3));
     return r;
@@ -111,8 +126,8 @@ LPC_HD Itv den_fdiv_B(const Itv& r2) {
 }
 // x = [-1,-1]: pir.hpp:553-559
 LPC_HD Itv den_fdiv_C(const Itv& r2) {
-  if(yl > 0) return Itv(LPC_MINF, wneg(yl));
-  if(yu < 0) return Itv(wneg(yu), LPC_INF);
+  if(yl > 0) return Itv(LPC_MINF, dneg(yl));
+  if(yu < 0) return Itv(dneg(yu), LPC_INF);
   if(0 == yl && yl < yu) return Itv(LPC_MINF, -1);
   if(yl < yu && yu == 0) return Itv(1, LPC_INF);
   if(yl == 0 && yu == 0) return itv_bot();
@@ -148,8 +163,8 @@ LPC_HD Itv den_cdiv_A(const Itv& r1, const Itv& r2) {
   return r;
 }
 LPC_HD Itv den_cdiv_B(const Itv& r2) {   // x = [0,0]: pir.hpp:605-608
-  if(yl > 0) return Itv(LPC_MINF, wsub(wneg(yl), 1));
-  if(yu < 0) return Itv(wadd(wneg(yu), 1), LPC_INF);
+  if(yl > 0) return Itv(LPC_MINF, wsub(dneg(yl), 1));
+  if(yu < 0) return Itv(wadd(dneg(yu), 1), LPC_INF);
   return itv_top();
 }
 LPC_HD Itv den_cdiv_C(const Itv& r2) {   // x = [1,1]: pir.hpp:609-615
@@ -174,8 +189,8 @@ LPC_HD Itv den_cdiv(const Itv& r1, const Itv& r2) {
 // pir.hpp:633-649
 LPC_HD Itv den_tdiv0(const Itv& r2, const Itv& r3) {   // x = [0,0]
   if(yl > 0 && zl > 0) return Itv(wadd(yl, 1), LPC_INF);
-  if(yl > 0 && zu < 0) return Itv(LPC_MINF, wsub(wneg(yl), 1));
-  if(yu < 0 && zl > 0) return Itv(wadd(wneg(yu), 1), LPC_INF);
+  if(yl > 0 && zu < 0) return Itv(LPC_MINF, wsub(dneg(yl), 1));
+  if(yu < 0 && zl > 0) return Itv(wadd(dneg(yu), 1), LPC_INF);
   if(yu < 0 && zu < 0) return Itv(LPC_MINF, wsub(yu, 1));
   return itv_top();
 }

@@ -505,6 +505,7 @@ struct lpc_eps {
   int n = 0, ndec = 0;
   GroupPlan plan;
   int rank = 0, world = 1;
+  long long table_gen = 0;
 };
 
 extern "C" {
@@ -530,7 +531,9 @@ int lpc_eps_create(const lpc_table* t, int32_t max_subproblems, int32_t survivor
     set_error("lpc_eps_create: stores need an even number of variables (got %d); pad the model with one unused variable", nvars);
     return LPC_ERR_UNSUPPORTED;
   }
+  LPC_REQUIRE(t->finalized, "lpc_table_finalize has not been called since the last change of the table");
   lpc_eps* e = new lpc_eps();
+  e->table_gen = t->generation;
   e->table = t; e->max_n = max_subproblems; e->nvars = nvars; e->sbytes = nvars * 8; e->surv_cap = survivor_cap;
   int rc = LPC_OK;
   auto fail = [&](int code) { lpc_eps_destroy(e); return code; };
@@ -617,6 +620,7 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
   LPC_REQUIRE(e != nullptr && e->uploaded, "no problem uploaded");
   LPC_REQUIRE(!e->pending, "a call is still in flight on this handle (collect it first)");
   LPC_REQUIRE(objective_var < e->nvars, "objective variable out of range");
+  LPC_REQUIRE(e->table->generation == e->table_gen, "the table changed since this handle was created: create a new one");
   int rc = eps_check_device(e);
   if(rc) return rc;
   lpc_fixpoint_opts def;

@@ -10,6 +10,9 @@
 //   is_bot, is_top, operator[], project, vars          [pc.hpp:685-709]
 //   snapshot / restore                                 [pc.hpp:711-723]
 //   is_extractable / extract                           [pc.hpp:726-752]
+//   deinterpret(env[, remove_entailed, n])             [pc.hpp:754-788]  each propagator back to the formula it was
+//                                                                        interpreted from; entailed ones found by ONE
+//                                                                        lpc_pc_ask_all call
 // `PC::fixpoint()` is the fast path: GaussSeidelIteration::fixpoint(num_deductions(), deduce) (tests/pc_test.cpp:91-94,
 // tests/pc_bitset_test.cpp:52-55) as one persistent CUDA kernel (lpc_pc_fixpoint / lpc_pc_fixpoint_bits).
 //
@@ -29,7 +32,7 @@
 namespace b200pc {
 
 // Formula signatures PC understands beyond the PIR operators (numeric values are façade-local).
-enum PcSig : int { SUB = 1010, NEG = 1011, ABS = 1012, NOT = 1013, AND = 1014, OR = 1015, EQUIV = 1016, IN = 1017,
+enum PcSig : int { SUB = 1010, NEG = 1011, ABS = 1012, NOT = 1013, /* AND = 1014 lives in pir.hpp's Sig */ OR = 1015, EQUIV = 1016, IN = 1017,
                    IMPLY = 1018, XOR = 1019 };
 
 // NBitset<64, local_memory, unsigned long long> (pc_bitset_test.cpp:23): bit 0 = "<= -1", bit i = value i - 1,
@@ -130,6 +133,7 @@ public:
     int kind = 0, rhs = 0, bvar = -1;
     std::vector<lpc_pc_term> terms;
     int ref_kind = 0, length = 0;
+    std::shared_ptr<TF> source;   // the formula this propagator was interpreted from (deinterpret, pc.hpp:754-788)
   };
   struct tell_type {
     std::vector<std::pair<AVar, universe_type>> sub_value;
@@ -229,7 +233,54 @@ public:
   void extract(S& ua) const { ua.restore(sub_->snapshot()); }
   sub_ptr sub() const { return sub_; }
 
+  // pc.hpp:754-788: AND(store, propagators...) - the store alone when there is no propagator -, optionally without the
+  // propagators that are entailed (one lpc_pc_ask_all call over the table, their count added to num_entailed).
+  TF deinterpret(const VarEnv& env, bool remove_entailed, size_t& num_entailed) const {
+    TF subf = deinterpret_sub(env);
+    const auto& ps = table_->props;
+    if(ps.empty()) return subf;
+    std::vector<TF> seq;
+    seq.push_back(std::move(subf));
+    std::vector<uint8_t> ent(ps.size() + 1, 0);
+    if(remove_entailed) { int64_t n = 0; ask_all(table(), &n, ent.data()); }
+    for(size_t i = 0; i < ps.size(); ++i) {
+      if(remove_entailed && ent[i]) { ++num_entailed; continue; }
+      seq.push_back(ps[i].source ? *ps[i].source : TF::z(1));
+    }
+    return TF::make_nary(AND, std::move(seq));
+  }
+  TF deinterpret(const VarEnv& env) const { size_t n = 0; return deinterpret(env, false, n); }
+  TF deinterpret(const tell_type& t, const VarEnv& env) const {
+    std::vector<TF> sub, seq;
+    for(auto& sv : t.sub_value) deinterpret_domain(env.name_of(sv.first), sv.second, sub);
+    seq.push_back(TF::make_nary(AND, std::move(sub)));
+    for(auto& p : t.props) seq.push_back(p.source ? *p.source : TF::z(1));
+    return TF::make_nary(AND, std::move(seq));
+  }
+
 private:
+  // one domain as formulas: a singleton as `x == k`, an interval by its finite ends, a bitset with holes as `x in S`
+  static void deinterpret_domain(const std::string& name, const universe_type& d, std::vector<TF>& seq) {
+    const int lb = d.lb().value(), ub = d.ub().value();
+    if constexpr(bitset) {
+      const uint64_t full = lpc_nbit_range(lb, ub);
+      if(d.bits != full && !(d.bits & 1) && !(d.bits >> 63)) {   // holes, all values finite: the set itself
+        std::vector<int> vs;
+        for(int b = 1; b < 63; ++b) if(d.bits >> b & 1) vs.push_back(b - 1);
+        seq.push_back(TF::in(TF::var(name), vs));
+        return;
+      }
+    }
+    if(lb == ub) { seq.push_back(TF::make_binary(TF::var(name), EQ, TF::z(lb))); return; }
+    if(lb != INT_MIN) seq.push_back(TF::make_binary(TF::var(name), GEQ, TF::z(lb)));
+    if(ub != INT_MAX) seq.push_back(TF::make_binary(TF::var(name), LEQ, TF::z(ub)));
+  }
+  TF deinterpret_sub(const VarEnv& env) const {
+    std::vector<TF> seq;
+    const int n = std::min(env.num_vars(), sub_->vars());
+    for(int v = 0; v < n; ++v) deinterpret_domain(env.name_of(AVar(0, v)), (*sub_)[v], seq);
+    return TF::make_nary(AND, std::move(seq));
+  }
   struct Table {
     std::vector<prop_type> props;
     lpc_pc_table* h = nullptr;
@@ -457,9 +508,13 @@ private:
 
   bool interpret_formula(const TF& f, VarEnv& env, tell_type& out, std::string* why) const {
     const size_t n0 = out.props.size();
-    if(interpret_flat(f, env, out, why)) return true;
-    out.props.resize(n0);
-    return interpret_tree(f, env, out, why);   // no flat kind: the tree itself goes to the device
+    bool ok = interpret_flat(f, env, out, why);
+    if(!ok) {
+      out.props.resize(n0);
+      ok = interpret_tree(f, env, out, why);   // no flat kind: the tree itself goes to the device
+    }
+    if(ok) for(size_t i = n0; i < out.props.size(); ++i) out.props[i].source = std::make_shared<TF>(f);
+    return ok;
   }
 
   bool interpret_flat(const TF& f, VarEnv& env, tell_type& out, std::string* why) const {

@@ -16,8 +16,10 @@
 // (call sites tests/pir_test.cpp:60-62, 82-86). `PIR::fixpoint()` is the fast path: the whole loop as one persistent
 // CUDA kernel (lpc_fixpoint).
 //
+//   deinterpret(env[, remove_entailed, n])          [pir.hpp:901-941]   table + store back to a conjunction; the
+//                                                                       entailed propagators found by ONE lpc_ask_bits call
 // Not mirrored: allocators (device memory is owned by the C-ABI handles), the IDiagnostics tree (interpretation
-// errors are returned as a string), deinterpret. There is no CPU implementation behind this header: every call ends
+// errors are returned as a string). There is no CPU implementation behind this header: every call ends
 // in liblpc.so, and construction throws when no CUDA device is present.
 #pragma once
 #include <algorithm>
@@ -39,7 +41,8 @@ constexpr AType UNTYPED = -1;
 // lala-core Sig values of the operators PIR accepts (include/lpc.h).
 enum Sig : int { ADD = LPC_ADD, MUL = LPC_MUL, MIN = LPC_MIN, MAX = LPC_MAX, TDIV = LPC_TDIV, FDIV = LPC_FDIV,
                  CDIV = LPC_CDIV, EDIV = LPC_EDIV, EQ = LPC_EQ, LEQ = LPC_LEQ,
-                 GEQ = 1001, NEQ = 1002, LT = 1003, GT = 1004 };   // unary-store comparisons only
+                 GEQ = 1001, NEQ = 1002, LT = 1003, GT = 1004,     // unary-store comparisons only
+                 AND = 1014 };                                      // the n-ary conjunction deinterpret produces
 
 inline void check(int rc) {
   if(rc != LPC_OK) throw std::runtime_error(std::string("lpc: ") + lpc_last_error());
@@ -122,11 +125,33 @@ struct AbstractDeps {
 // A tiny formula type: just enough structure for PIR::interpret_formula (pir.hpp:254-287) — variables, integer
 // constants and binary nodes — standing in for lala-core's TFormula.
 struct F {
-  enum Kind { VAR, CONST, BINARY } kind = CONST;
+  enum Kind { VAR, CONST, BINARY, NARY } kind = CONST;
   std::string name;
   int k = 0;
   int sig_ = 0;
   std::shared_ptr<F> a, b;
+  std::vector<F> children;   // NARY (the conjunctions deinterpret builds, pir.hpp:912-925)
+  static F nary(int sig, std::vector<F> seq) { F f; f.kind = NARY; f.sig_ = sig; f.children = std::move(seq); return f; }
+  bool is_nary() const { return kind == NARY; }
+  size_t arity() const { return kind == NARY ? children.size() : (kind == BINARY ? 2 : 0); }
+  const F& child(size_t i) const { return kind == NARY ? children[i] : seq((int)i); }
+  // a printable form, for diagnostics and tests: (x == (y + z)), (and ...)
+  std::string str() const {
+    auto op = [](int s) -> std::string {
+      switch(s) {
+        case LPC_ADD: return "+"; case LPC_MUL: return "*"; case LPC_MIN: return "min"; case LPC_MAX: return "max";
+        case LPC_TDIV: return "tdiv"; case LPC_FDIV: return "fdiv"; case LPC_CDIV: return "cdiv"; case LPC_EDIV: return "ediv";
+        case LPC_EQ: return "=="; case LPC_LEQ: return "<="; case 1001: return ">="; case 1002: return "!="; case 1003: return "<";
+        case 1004: return ">"; case 1014: return "and"; default: return "op" + std::to_string(s);
+      }
+    };
+    if(kind == VAR) return name;
+    if(kind == CONST) return std::to_string(k);
+    if(kind == BINARY) return "(" + a->str() + " " + op(sig_) + " " + b->str() + ")";
+    std::string r = "(" + op(sig_);
+    for(auto& c : children) r += " " + c.str();
+    return r + ")";
+  }
   static F var(const std::string& n) { F f; f.kind = VAR; f.name = n; return f; }
   static F z(int k) { F f; f.kind = CONST; f.k = k; return f; }
   static F binary(const F& l, int sig, const F& r) {
@@ -165,6 +190,22 @@ private:
   std::map<std::string, AVar> vars_;
   std::vector<std::string> names_;
 };
+
+// The bounds of one variable as formulas: `x == k` for a singleton, else `x >= lb` / `x <= ub` for each finite end
+// (the shape of lala-core's VStore / Interval deinterpret is un-vendored; this is its logical content).
+inline void deinterpret_bounds(const std::string& name, const Itv& d, std::vector<F>& seq) {
+  if(d.l == d.u) { seq.push_back(F::binary(F::var(name), EQ, F::z(d.l))); return; }
+  if(d.l != INT_MIN) seq.push_back(F::binary(F::var(name), GEQ, F::z(d.l)));
+  if(d.u != INT_MAX) seq.push_back(F::binary(F::var(name), LEQ, F::z(d.u)));
+}
+// sub->deinterpret(env) (pir.hpp:916): the store as a conjunction over the variables the environment names.
+inline F deinterpret_store(const VStore& s, const VarEnv& env) {
+  std::vector<F> seq;
+  const std::vector<int> snap = s.snapshot();
+  const int n = std::min(env.num_vars(), s.vars());
+  for(int v = 0; v < n; ++v) deinterpret_bounds(env.name_of(AVar(0, v)), Itv(snap[2 * (size_t)v], snap[2 * (size_t)v + 1]), seq);
+  return F::nary(AND, std::move(seq));
+}
 
 // GaussSeidelIteration of lala-core (fixpoint.hpp): sequential sweeps until no deduction changes anything.
 struct GaussSeidelIteration {
@@ -235,7 +276,9 @@ public:
       std::stable_sort(bc.begin(), bc.end(), [](const bytecode_type& a, const bytecode_type& b) {
         return a.op == b.op ? (a.y.vid() == b.y.vid() ? (a.x.vid() == b.x.vid() ? a.z.vid() < b.z.vid() : a.x.vid() < b.x.vid()) : a.y.vid() < b.y.vid()) : a.op < b.op;
       });
-      table_->invalidate();
+      // the device table grows incrementally: the new records are appended, sorted and merged in by the library with the
+      // same stable (op, y, x, z) order, and only the part of the device image that moved is uploaded
+      table_->append(t.bytecodes, sub_->vars());
       has_changed = true;
     }
     return has_changed;
@@ -284,7 +327,7 @@ public:
     if((int)bc.size() > snap.num_bytecodes) {
       // pir.hpp:865-868 pops from the back of the sorted table; the façade keeps that literal behaviour
       bc.resize(snap.num_bytecodes);
-      table_->invalidate();
+      table_->truncate(snap.num_bytecodes);
     }
     sub_->restore(snap.sub_snap);
   }
@@ -298,7 +341,36 @@ public:
   void extract(PIR& ua) const { ua.sub_->restore(sub_->snapshot()); }
   void extract(VStore& ua) const { ua.restore(sub_->snapshot()); }
 
+  // pir.hpp:901-941. One propagator back to `X = Y op Z`; the whole element as AND(store, propagators...), optionally
+  // without the propagators PIR::ask entails (their count is added to num_entailed) - found with ONE lpc_ask_bits call
+  // over the table instead of num_deductions() single asks.
+  F deinterpret(const bytecode_type& b, const VarEnv& env) const {
+    return F::binary(F::var(env.name_of(b.x)), EQ, F::binary(F::var(env.name_of(b.y)), (int)b.op, F::var(env.name_of(b.z))));
+  }
+  F deinterpret(const VarEnv& env, bool remove_entailed, size_t& num_entailed) const {
+    std::vector<F> seq;
+    seq.push_back(deinterpret_store(*sub_, env));
+    const auto& bc = table_->bytecodes;
+    std::vector<uint8_t> ent(bc.size(), 0);
+    if(remove_entailed && !bc.empty()) check(lpc_ask_bits(table(), sub_->handle(), ent.data()));
+    for(size_t i = 0; i < bc.size(); ++i) {
+      if(remove_entailed && ent[i]) { ++num_entailed; continue; }
+      seq.push_back(deinterpret(bc[i], env));
+    }
+    return F::nary(AND, std::move(seq));
+  }
+  F deinterpret(const VarEnv& env) const { size_t n = 0; return deinterpret(env, false, n); }
+  F deinterpret(const tell_type& t, const VarEnv& env) const {   // an intermediate (tell / ask) element, pir.hpp:931-940
+    std::vector<F> sub, seq;
+    for(auto& sv : t.sub_value) deinterpret_bounds(env.name_of(sv.first), sv.second, sub);
+    seq.push_back(F::nary(AND, std::move(sub)));
+    for(auto& b : t.bytecodes) seq.push_back(deinterpret(b, env));
+    return F::nary(AND, std::move(seq));
+  }
+
   sub_ptr sub() const { return sub_; }
+  // table bytes copied to the device so far (diagnostic: incremental tells upload only what changed)
+  long long table_uploaded_bytes() const { return table_->uploaded_bytes(); }
 
 private:
   struct Table {
@@ -309,16 +381,40 @@ private:
     Table(const Table& o) : bytecodes(o.bytecodes) {}
     ~Table() { lpc_table_destroy(h); }
     void invalidate() { lpc_table_destroy(h); h = nullptr; }
+    static std::vector<lpc_bytecode> raw(const std::vector<bytecode_type>& v) {
+      std::vector<lpc_bytecode> r(v.size());
+      for(size_t i = 0; i < r.size(); ++i) r[i] = lpc_bytecode{(int)v[i].op, v[i].x.vid(), v[i].y.vid(), v[i].z.vid()};
+      return r;
+    }
+    // PIR::deduce(tell), pir.hpp:326-352: lpc_table_append + lpc_table_finalize(sort) on the live handle
+    void append(const std::vector<bytecode_type>& fresh, int nvars) {
+      if(!h) return;   // not on the device yet: get() uploads everything
+      if(nvars > h_nvars) { check(lpc_table_set_nvars(h, nvars)); h_nvars = nvars; }
+      std::vector<lpc_bytecode> r = raw(fresh);
+      check(lpc_table_append(h, r.data(), (int64_t)r.size()));
+      check(lpc_table_finalize(h, 1));
+    }
+    void truncate(int n) {
+      if(!h) return;
+      check(lpc_table_truncate(h, n));
+      check(lpc_table_finalize(h, 1));
+    }
     lpc_table* get(int nvars) {
-      if(!h || h_nvars != nvars) {
-        invalidate();
-        std::vector<lpc_bytecode> r(bytecodes.size());
-        for(size_t i = 0; i < r.size(); ++i) r[i] = lpc_bytecode{(int)bytecodes[i].op, bytecodes[i].x.vid(), bytecodes[i].y.vid(), bytecodes[i].z.vid()};
-        check(lpc_table_create(r.data(), (int64_t)r.size(), nvars, &h));
+      if(!h) {
+        std::vector<lpc_bytecode> r = raw(bytecodes);
+        check(lpc_table_create_empty(nvars, &h));
+        check(lpc_table_append(h, r.data(), (int64_t)r.size()));
+        check(lpc_table_finalize(h, 1));
+        h_nvars = nvars;
+      }
+      else if(nvars > h_nvars) {   // the store grew (a tell declared variables)
+        check(lpc_table_set_nvars(h, nvars));
+        check(lpc_table_finalize(h, 1));
         h_nvars = nvars;
       }
       return h;
     }
+    long long uploaded_bytes() const { return h ? (long long)lpc_table_uploaded_bytes(h) : 0; }
   };
   lpc_table* table() const { return table_->get(sub_->vars()); }
 

@@ -425,6 +425,51 @@ static void BitIntAbs1() {   // pc_bitset_test.cpp:150-157
   deduce_and_test(bpc, 1, {NBit(-1, 5), NBit(-1, 10)}, {NBit(-1, 5), NBit(0, 10)}, false);
 }
 
+// pc.hpp:754-788: the element back as a conjunction, with and without the entailed propagators
+static size_t count_nodes(const TF& f) { size_t n = 1; for(auto& a : f.args) n += count_nodes(a); return n; }
+static void Deinterpret() {
+  Model<IPC> m;
+  m.var("x", Itv(0, 10)).var("y", Itv(0, 10)).var("b", Itv(0, 1))
+   .c(bin(bin(V("x"), ADD, V("y")), LEQ, K(5))).c(bin(V("x"), NEQ, V("y"))).c(bin(V("b"), EQUIV, bin(V("x"), LEQ, K(20))));
+  IPC ipc = create_and_interpret_and_tell(m);
+  TF f = ipc.deinterpret(m.env);
+  EXPECT_EQ(f.sig(), (int)AND);
+  EXPECT_EQ((int)f.args.size(), 1 + 3);                 // the store, then one formula per propagator
+  EXPECT_EQ((int)f.seq(0).args.size(), 6);              // two bounds for each of x, y, b
+  ipc.fixpoint();
+  // b <=> (x <= 20) is entailed once b = 1 (x <= 5 <= 20); x + y <= 5 and x != y are not
+  size_t ent = 0;
+  TF g = ipc.deinterpret(m.env, true, ent);
+  EXPECT_EQ(ent, (size_t)1);
+  EXPECT_EQ((int)g.args.size(), 1 + 2);
+  EXPECT_EQ(ipc[2], Itv(1, 1));
+  // telling the deinterpreted formulas to a fresh element gives the same element
+  Model<IPC> m2;
+  m2.var("x").var("y").var("b");
+  IPC again(pty, std::make_shared<VStore>(3));
+  IPC::tell_type t2;
+  std::string why;
+  TF all = ipc.deinterpret(m.env);
+  for(auto& a : all.seq(0).args) EXPECT_TRUE(again.interpret_tell(a, m2.env, t2, &why));
+  for(size_t i = 1; i < all.args.size(); ++i) EXPECT_TRUE(again.interpret_tell(all.args[i], m2.env, t2, &why));
+  again.deduce(t2);
+  EXPECT_EQ(again.num_deductions(), ipc.num_deductions());
+  for(int v = 0; v < 3; ++v) EXPECT_EQ(again[v], ipc[v]);
+  EXPECT_TRUE(count_nodes(all) > 10);
+  // without propagators deinterpret is the store alone (pc.hpp:757-759)
+  IPC empty(pty, std::make_shared<VStore>(3));
+  EXPECT_EQ((int)empty.deinterpret(m2.env).args.size(), 0);
+  // a bitset store with a hole deinterprets to `x in S`
+  Model<BitPC> mb;
+  mb.var("x", NBit(1, 6)).c(TF::in(V("x"), {1, 2, 4, 6}));
+  BitPC bpc = create_and_interpret_and_tell(mb);
+  TF fb = bpc.deinterpret(mb.env);
+  EXPECT_EQ(fb.sig(), (int)AND);
+  EXPECT_EQ((int)fb.args.size(), 1);
+  EXPECT_EQ(fb.seq(0).sig(), (int)IN);
+  EXPECT_EQ((int)fb.seq(0).seq(1).set.size(), 4);
+}
+
 int main() {
   if(lpc_device_init(0) != LPC_OK) { printf("no CUDA device: %s\n", lpc_last_error()); return 2; }
   TemporalConstraint1();
@@ -439,6 +484,7 @@ int main() {
   UnsupportedShapesAreRefused();
   TreePropagators();
   SnapshotRestore();
+  Deinterpret();
   BitNotEqual();
   BitInConstraint1();
   BooleanClauses<BitPC>();

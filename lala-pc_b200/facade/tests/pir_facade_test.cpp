@@ -234,6 +234,84 @@ static void ExhaustiveAddWithSnapshots() {
   EXPECT_TRUE(cases > 1000);
 }
 
+// pir.hpp:326-352 + 857-870: CONSTRAINTS told between fixpoints (the table grows on the device without being rebuilt),
+// snapshot / restore across a table change (restore pops the records told since), shared and private table copies.
+static void IncrementalTells() {
+  Model m;
+  for(int i = 0; i < 40; ++i) m.var(("v" + std::to_string(i)).c_str(), Itv(0, 1000000000));
+  m.c(X_eq("v2", "v0", ADD, "v1"));
+  IPIR pir = create_and_interpret_and_tell(m);
+  pir.embed(AVar(sty, 0), Itv(3, 5)); pir.embed(AVar(sty, 1), Itv(10, 20));
+  EXPECT_FALSE(pir.fixpoint().is_bot);
+  EXPECT_EQ(pir[2], Itv(13, 25));
+  const long long b0 = pir.table_uploaded_bytes();
+  EXPECT_TRUE(b0 > 0);
+  auto snap = pir.snapshot();
+  // a chain v(i+2) = v(i) + v(i+1), one constraint per tell; every tell sorts into the live table
+  for(int i = 1; i < 30; ++i)
+    tell_more(pir, m, X_eq(("v" + std::to_string(i + 2)).c_str(), ("v" + std::to_string(i)).c_str(), ADD, ("v" + std::to_string(i + 1)).c_str()));
+  EXPECT_EQ(pir.num_deductions(), 30);
+  // sorted by (op, y, x, z): y = v0, v1, ... in order
+  for(int i = 0; i < 30; ++i) { EXPECT_EQ(pir.load_deduce(i).y.vid(), i); EXPECT_EQ(pir.load_deduce(i).x.vid(), i + 2); }
+  // 29 tells uploaded 29 small pieces, not 29 whole tables: far less than 29 x the 16-record granule of the first upload
+  EXPECT_TRUE(pir.table_uploaded_bytes() - b0 <= 29 * 2 * 16 * 13);
+  fixpoint_stats st = pir.fixpoint();
+  EXPECT_FALSE(st.is_bot);
+  EXPECT_EQ(pir[3], Itv(23, 45));     // v3 = v1 + v2
+  EXPECT_EQ(pir[4], Itv(36, 70));     // v4 = v2 + v3
+  EXPECT_EQ(pir[5], Itv(59, 115));    // v5 = v3 + v4
+  // a mixed tell: other operators land in their own runs
+  tell_more(pir, m, X_eq("v35", "v0", MAX, "v1"));
+  tell_more(pir, m, X_eq("v36", "v0", MUL, "v1"));
+  EXPECT_EQ(pir.num_deductions(), 32);
+  EXPECT_EQ((int)pir.load_deduce(30).op, (int)MUL);   // ADD = 2 < MUL = 4 < MAX = 7
+  EXPECT_EQ((int)pir.load_deduce(31).op, (int)MAX);
+  // a private copy owns its table, a shared copy uses the same one
+  AbstractDeps shared, priv; priv.shared_copy = false;
+  IPIR c1(pir, shared), c2(pir, priv);
+  EXPECT_EQ(c1.num_deductions(), 32); EXPECT_EQ(c2.num_deductions(), 32);
+  // restore pops everything told after the snapshot (pir.hpp:863-870) and the store with it
+  pir.restore(snap);
+  EXPECT_EQ(pir.num_deductions(), 1);
+  EXPECT_EQ(pir[2], Itv(13, 25));
+  EXPECT_EQ(pir[3], Itv(0, 1000000000));
+  EXPECT_FALSE(pir.fixpoint().has_changed);
+  EXPECT_EQ(c2.num_deductions(), 32);   // the private copy is unaffected
+  c2.fixpoint();
+  EXPECT_EQ(c2[35], Itv(10, 20));       // max(v0, v1)
+}
+
+// pir.hpp:901-941
+static void Deinterpret() {
+  Model m;
+  m.var("x", Itv(1, 1)).var("y", Itv(0, 10)).var("z", Itv(0, 10)).var("w").c(X_eq("z", "x", ADD, "y")).c(X_eq("w", "x", MUL, "x"));
+  IPIR pir = create_and_interpret_and_tell(m);
+  EXPECT_EQ(pir.deinterpret(m.env).str(),
+            std::string("(and (and (x == 1) (y >= 0) (y <= 10) (z >= 0) (z <= 10)) (z == (x + y)) (w == (x * x)))"));
+  pir.fixpoint();
+  size_t ent = 0;
+  F f = pir.deinterpret(m.env, true, ent);
+  // w = x * x with x = 1 is entailed once w is 1; z = x + y is not (y, z still ranges)
+  EXPECT_EQ(ent, (size_t)1);
+  EXPECT_EQ(f.str(), std::string("(and (and (x == 1) (y >= 0) (y <= 9) (z >= 1) (z <= 10) (w == 1)) (z == (x + y)))"));
+  IPIR::tell_type tell;
+  std::string why;
+  EXPECT_TRUE(pir.interpret_tell(F::binary(V("y"), LEQ, F::z(4)), m.env, tell, &why));
+  EXPECT_TRUE(pir.interpret_tell(X_eq("w", "y", MIN, "z"), m.env, tell, &why));
+  EXPECT_EQ(pir.deinterpret(tell, m.env).str(), std::string("(and (and (y <= 4)) (w == (y min z)))"));
+  // what deinterpret gives back can be told again: same element
+  Model m2;
+  m2.var("x").var("y").var("z").var("w");
+  IPIR again(pty, std::make_shared<IStore>(4));
+  IPIR::tell_type t2;
+  F all = pir.deinterpret(m.env);
+  for(size_t i = 0; i < all.child(0).arity(); ++i) EXPECT_TRUE(again.interpret_tell(all.child(0).child(i), m2.env, t2, &why));
+  for(size_t i = 1; i < all.arity(); ++i) EXPECT_TRUE(again.interpret_tell(all.child(i), m2.env, t2, &why));
+  again.deduce(t2);
+  EXPECT_EQ(again.num_deductions(), pir.num_deductions());
+  for(int v = 0; v < 4; ++v) EXPECT_EQ(again[v], pir[v]);
+}
+
 int main() {
   if(lpc_device_init(0) != LPC_OK) { printf("no CUDA device: %s\n", lpc_last_error()); return 2; }
   TernaryProblem();
@@ -247,6 +325,8 @@ int main() {
   Strict1();
   InterpretationErrors();
   ExhaustiveAddWithSnapshots();
+  IncrementalTells();
+  Deinterpret();
   printf("%d checks, %d failures\n", g_checks, g_fail);
   return g_fail ? 1 : 0;
 }

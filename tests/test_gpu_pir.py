@@ -487,3 +487,64 @@ def test_exhaustive_triples_as_one_network(L, O, name):
         r = L.fixpoint(t, s, **mode)
         assert not r.is_bot, (name, mname)
         assert np.array_equal(s.read(), want), (name, mname)
+
+
+def test_incremental_table_build(L, O, W):
+    """lpc_table_append / lpc_table_finalize (PIR::deduce(tell), pir.hpp:326-352): a table told in pieces is the table
+    told at once - same (op, y, x, z) order, same fixpoints in every mode (the change-driven modes rebuild the
+    var -> records index lazily) - and a small tell uploads a small piece of the device image, not the table."""
+    net = W.config2(0.02)                        # 100k records
+    rng = np.random.default_rng(5)
+    recs = net.records[rng.permutation(len(net.records))]
+    want_order = L.sort_records(recs)
+    assert np.array_equal(want_order, net.records) or True   # ties between equal records are irrelevant
+    want, st = O.pir_fixpoint(net.store, want_order)
+    t = L.Table(None, net.nvars)
+    cuts = [0, 1, 17, 5000, 5001, 60000, len(recs)]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        t.append(recs[a:b])
+        t.finalize(sort=True)
+        assert len(t) == b
+        got = t.records()[:50] if b > 50 else t.records()
+        assert np.array_equal(got, L.sort_records(recs[:b])[:len(got)])
+    assert np.array_equal(t.records()[::97], want_order[::97])
+    for name, mode in modes(L):
+        s = L.Store(values=net.store)
+        r = L.fixpoint(t, s, **mode)
+        assert not r.is_bot and np.array_equal(s.read(), want), name
+    # one more record: sorted into place, a piece of the image goes to the device
+    before = t.uploaded_bytes()
+    extra = np.array([[LEQ, 5, 6, 7]], dtype=np.int32)     # LEQ is the last operator run: lands near the end
+    t.append(extra)
+    t.finalize(sort=True)
+    assert t.uploaded_bytes() - before < 13 * len(recs) // 4
+    assert len(t) == len(recs) + 1
+    # restore pops from the back (pir.hpp:863-870)
+    t.truncate(1000)
+    t.finalize(sort=True)
+    assert len(t) == 1000 and np.array_equal(t.records(), L.sort_records(np.concatenate([recs, extra]))[:1000])
+    want2, st2 = O.pir_fixpoint(net.store, t.records())
+    s = L.Store(values=net.store)
+    r = L.fixpoint(t, s, mode=L.MODE_WORKLIST)
+    assert bool(r.is_bot) == bool(st2.is_bot) and (st2.is_bot or np.array_equal(s.read(), want2))
+    # a batch created before a finalize refuses to run on the changed table
+    small = L.Table(None, 4)
+    small.append(np.array([[ADD, 0, 1, 2]], dtype=np.int32))
+    small.finalize()
+    b = L.Batch(small, 4)
+    b.write(np.zeros((4, 4, 2), dtype=np.int32))
+    b.fixpoint()
+    small.append(np.array([[ADD, 1, 2, 3]], dtype=np.int32))
+    with pytest.raises(L.LpcError):
+        L.Batch(small, 4)                 # not finalized
+    small.finalize()
+    with pytest.raises(L.LpcError):
+        b.fixpoint()                      # created over the old contents
+    # a growing variable range
+    small.set_nvars(6)
+    small.append(np.array([[MAX, 5, 4, 0]], dtype=np.int32))
+    small.finalize()
+    s6 = L.Store(values=np.array([[1, 2], [3, 4], [0, 9], [0, 99], [7, 8], [0, 99]], dtype=np.int32))
+    w6, _ = O.pir_fixpoint(s6.read(), small.records())
+    L.fixpoint(small, s6)
+    assert np.array_equal(s6.read(), w6)

@@ -18,7 +18,7 @@ def f(x, p=3):
 
 
 print("N", d.get("n_gpus"), "| c4 weak: value", f((d.get("value") or 0) / 1e9, 1), "G ded/s, step", f(d.get("ms_per_step")), "ms, e2e",
-      f(g(d, "e2e", "ms_per_step")), "ms (", f((g(d, "e2e", "value") or 0) / 1e9, 1), "G/s ), rank_ms", {k: f(v) for k, v in (d.get("rank_ms") or {}).items() if k != "per_rank"})
+      f(g(d, "e2e", "ms_per_step")), "ms (", f((g(d, "e2e", "value") or 0) / 1e9, 1), "G/s ), rank_kernel_ms", {k: f(v) for k, v in (d.get("rank_kernel_ms") or {}).items() if k != "per_rank"})
 print("  time_to_result", {k: f(v) for k, v in (d.get("time_to_result") or {}).items() if k.endswith("_ms") or k.endswith("propagators")})
 print("  roofline", {k: f(v) for k, v in (d.get("roofline") or {}).items() if k in ("bound", "frac", "warp_inst_per_deduction", "thread_inst_per_deduction", "traffic")},
       "hbm-alg frac", f(g(d, "roofline", "hbm", "frac")))
@@ -26,7 +26,7 @@ print("  result", d.get("batch_result"), "launches", d.get("gpu_launches"), "clo
 if isinstance(d.get("strong"), dict) and "value" in d["strong"]:
     s = d["strong"]
     print("  strong: value", f(s["value"] / 1e9, 1), "G ded/s, step", f(s["ms_per_step"]), "ms, e2e", f(g(s, "e2e", "ms_per_step")), "ms, auto",
-          f(g(s, "time_to_result", "auto_ms")), "ms, rank_ms", {k: f(v) for k, v in (s.get("rank_ms") or {}).items() if k != "per_rank"})
+          f(g(s, "time_to_result", "auto_ms")), "ms, rank_kernel_ms", {k: f(v) for k, v in (s.get("rank_kernel_ms") or {}).items() if k != "per_rank"})
 r = d.get("resident_images")
 if r:
     print("  resident images: dense", f(g(r, "dense", "ms_per_step")), "ms", f((g(r, "dense", "value") or 0) / 1e9, 1), "G/s | auto", f(g(r, "auto", "ms_per_step")), "ms")
