@@ -25,6 +25,19 @@ LPC_HD int dneg(int a) {
 LPC_HD int dneg(int a) { return wneg(a); }
 #endif
 
+// LPC_DIV_FIX (tools/repro/div_miscompile.cu): 0 = the code as it was, 1 = num_tdiv / den_tdiv out of line on the device,
+// 2 = 1 + the zero-straddling numerator written with one maximum.
+#ifndef LPC_DIV_FIX
+#define LPC_DIV_FIX 0
+#endif
+#if LPC_DIV_FIX >= 1 && !defined(LPC_HOST_HARNESS)
+#define LPC_DIV_TDIV_ATTR __device__ __noinline__
+#elif LPC_DIV_FIX >= 1
+#define LPC_DIV_TDIV_ATTR __host__ __device__ __noinline__
+#else
+#define LPC_DIV_TDIV_ATTR LPC_HD
+#endif
+
 #define xl r1.lb
 #define xu r1.ub
 #define yl r2.lb
@@ -78,11 +91,18 @@ LPC_HD Itv num_cdiv(const Itv& r1, const Itv& r3) {
 }
 
 // pir.hpp:493-507
-LPC_HD Itv num_tdiv(const Itv& r1, const Itv& r3) {
+LPC_DIV_TDIV_ATTR Itv num_tdiv(const Itv& r1, const Itv& r3) {
   if(xl > 0) return num_fdiv(r1, r3);
   else if(xu < 0) return num_cdiv(r1, r3);
   else if(xl <= 0 && 0 <= xu) {
+#if LPC_DIV_FIX >= 2
+    // the same interval as the reference's (min(zl, -zu) + 1, max(-zl, zu) - 1), written with ONE maximum:
+    // min(zl, -zu) = -max(-zl, zu)
+    const int m = max(dneg(zl), zu);
+    Itv r(wadd(dneg(m), 1), wsub(m, 1));
+#else
     Itv r(wadd(min(zl, dneg(zu)), 1), wsub(max(dneg(zl), zu), 1));
+#endif
     if(xl != 0) r = fjoin(r, num_cdiv(Itv(xl, -1), r3));
     if(xu != 0) r = fjoin(r, num_fdiv(Itv(1, xu), r3));
     return r;
@@ -194,7 +214,7 @@ LPC_HD Itv den_tdiv0(const Itv& r2, const Itv& r3) {   // x = [0,0]
   if(yu < 0 && zu < 0) return Itv(LPC_MINF, wsub(yu, 1));
   return itv_top();
 }
-LPC_HD Itv den_tdiv(const Itv& r1, const Itv& r2, const Itv& r3) {
+LPC_DIV_TDIV_ATTR Itv den_tdiv(const Itv& r1, const Itv& r2, const Itv& r3) {
   if(xl > 0) return den_fdiv(r1, r2);
   else if(xu < 0) return den_cdiv(r1, r2);
   else if(xl == 0 && xu == 0) return den_tdiv0(r2, r3);

@@ -514,11 +514,16 @@ def test_incremental_table_build(L, O, W):
         assert not r.is_bot and np.array_equal(s.read(), want), name
     # one more record: sorted into place, a piece of the image goes to the device
     before = t.uploaded_bytes()
-    extra = np.array([[LEQ, 5, 6, 7]], dtype=np.int32)     # LEQ is the last operator run: lands near the end
+    extra = np.array([[LEQ, 5, net.nvars - 1, 7]], dtype=np.int32)     # the last operator run, the largest y: lands at the end
     t.append(extra)
     t.finalize(sort=True)
-    assert t.uploaded_bytes() - before < 13 * len(recs) // 4
-    assert len(t) == len(recs) + 1
+    assert t.uploaded_bytes() - before <= 13 * 32, "a one-record tell at the end uploads one or two 16-record granules"
+    mid = np.array([[MUL, 5, 6, 7]], dtype=np.int32)                   # lands at the start of the `*` run: the image behind it moves
+    t.append(mid)
+    t.finalize(sort=True)
+    assert 13 * 1000 < t.uploaded_bytes() - before < 13 * (len(recs) + 64)
+    extra = np.concatenate([extra, mid])
+    assert len(t) == len(recs) + 2
     # restore pops from the back (pir.hpp:863-870)
     t.truncate(1000)
     t.finalize(sort=True)
