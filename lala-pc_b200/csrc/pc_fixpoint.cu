@@ -159,13 +159,25 @@ __device__ __forceinline__ int tile_step(const PcTableDev& t, Acc& acc, int2* st
       ti_lb = term_lane ? (int)tlo : 0; ti_ub = term_lane ? (int)thi : 0;
       wildm = __ballot_sync(FULL, active && lin && !tame);
       heads = __ballot_sync(FULL, active && pos == 0);
-      // The propagator's totals: every lane only needs the SUM of the term bounds of its propagator (the residual of a
-      // term is total - own term), so one masked warp reduction per bound (REDUX) over the propagator's own lanes
-      // replaces the segmented shuffle scan (two shuffles and a dozen instructions per doubling step: 113 of the 300
-      // instructions of a tile step in the round-1 profile). Lanes outside any propagator reduce over themselves.
-      const unsigned rmask = active ? segmask : (1u << lane);
-      all_lb = __reduce_add_sync(rmask, ti_lb);
-      all_ub = __reduce_add_sync(rmask, ti_ub);
+      // Segmented inclusive sums of the term bounds, then the propagator's total from its last lane. Four doubling steps,
+      // unrolled, cover propagators of up to 16 lanes (the loop over a run-time step count cost 113 of the 300
+      // instructions of a tile step in the profile: shuffles, selects, loop control and a convergence check per shuffle);
+      // a fifth step runs only for tiles that hold a longer propagator. (A masked warp reduction per propagator,
+      // __reduce_add_sync, was tried: REDUX delivers ONE result per warp, so lane-varying masks fall back to a loop over
+      // the distinct masks - slower, 119 vs 97 us on config 3.)
+      int slb = ti_lb, sub_ = ti_ub;
+#pragma unroll
+      for(int off = 1; off <= 8; off <<= 1) {
+        const int a = __shfl_up_sync(FULL, slb, off), b = __shfl_up_sync(FULL, sub_, off);
+        const bool in = pos >= off;
+        slb = wadd(slb, in ? a : 0); sub_ = wadd(sub_, in ? b : 0);
+      }
+      if(maxlen > 16) {
+        const int a = __shfl_up_sync(FULL, slb, 16), b = __shfl_up_sync(FULL, sub_, 16);
+        const bool in = pos >= 16;
+        slb = wadd(slb, in ? a : 0); sub_ = wadd(sub_, in ? b : 0);
+      }
+      all_lb = __shfl_sync(FULL, slb, last); all_ub = __shfl_sync(FULL, sub_, last);
     }
     const Itv pd(__shfl_sync(FULL, dom.lb, partner), __shfl_sync(FULL, dom.ub, partner));
     const bool refuted = kind == PC_CLAUSE && lit_ask(coef > 0, dom);

@@ -30,6 +30,10 @@ LPC_HD int dneg(int a) { return wneg(a); }
 #ifndef LPC_DIV_FIX
 #define LPC_DIV_FIX 0
 #endif
+#if LPC_DIV_FIX >= 3
+#undef LPC_HD
+#define LPC_HD __host__ __device__ __noinline__
+#endif
 #if LPC_DIV_FIX >= 1 && !defined(LPC_HOST_HARNESS)
 #define LPC_DIV_TDIV_ATTR __device__ __noinline__
 #elif LPC_DIV_FIX >= 1

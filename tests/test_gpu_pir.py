@@ -549,7 +549,8 @@ def test_incremental_table_build(L, O, W):
     small.set_nvars(6)
     small.append(np.array([[MAX, 5, 4, 0]], dtype=np.int32))
     small.finalize()
-    s6 = L.Store(values=np.array([[1, 2], [3, 4], [0, 9], [0, 99], [7, 8], [0, 99]], dtype=np.int32))
-    w6, _ = O.pir_fixpoint(s6.read(), small.records())
-    L.fixpoint(small, s6)
-    assert np.array_equal(s6.read(), w6)
+    s6 = L.Store(values=np.array([[1, 20], [3, 4], [0, 9], [0, 99], [7, 8], [0, 99]], dtype=np.int32))
+    w6, st6 = O.pir_fixpoint(s6.read(), small.records())
+    r6 = L.fixpoint(small, s6)
+    assert not st6.is_bot and not r6.is_bot and np.array_equal(s6.read(), w6)
+    assert tuple(w6[5]) == (7, 8) and tuple(w6[0]) == (3, 8)

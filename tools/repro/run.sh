@@ -9,4 +9,7 @@ build O1 -Xptxas -O1
 build O3_opaque -DLPC_DIV_OPAQUE_NEG
 build O3_fix1 -DLPC_DIV_FIX=1
 build O3_fix2 -DLPC_DIV_FIX=2
-for v in O3 O0 O1 O3_opaque O3_fix1 O3_fix2; do echo "== variant $v"; /tmp/div_$v ${1:-6}; echo "exit $?"; done
+build cicc0_ptxas3 -Xcicc -O0
+build O3_fix3 -DLPC_DIV_FIX=3
+build O3_nofma -Xptxas --fmad=false
+for v in O3 O0 cicc0_ptxas3 O3_fix3 O3_nofma; do echo "== variant $v"; /tmp/div_$v ${1:-6}; echo "exit $?"; done
