@@ -29,7 +29,9 @@ namespace lpc {
 enum PcTok : int { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8,
                    T_MIN = 9, T_MAX = 10, T_TDIV = 11, T_FDIV = 12, T_CDIV = 13, T_EDIV = 14, T_NARY_MUL = 15,
                    F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27,
-                   F_EQUIV = 28, F_IMPLY = 29, F_XOR = 30, F_AE = 31 };
+                   F_EQUIV = 28, F_IMPLY = 29, F_XOR = 30, F_AE = 31, F_TRUE = 32, F_FALSE = 33 };
+// F_TRUE / F_FALSE: the constant formulas (formula.hpp:169-239), no operand; False::deduce / True::contradeduce send the
+// store to bot (a.meet_bot()), here by emptying variable 0.
 // F_AE op var k: AbstractElement over the store, `var op k` with op = 0 <=, 1 >=, 2 =, 3 != (formula.hpp:14-77)
 enum PcAeOp : int { AE_LEQ = 0, AE_GEQ = 1, AE_EQ = 2, AE_NEQ = 3 };
 
@@ -63,6 +65,7 @@ __host__ __device__ inline const int* tree_skip_formula(const int* p) {
     const int k = *p++;
     if(k == F_VARLIT || k == F_NVARLIT) { ++p; --pending; }
     else if(k == F_AE) { p += 3; --pending; }
+    else if(k == F_TRUE || k == F_FALSE) { --pending; }
     else if(k >= F_LEQ && k <= F_NEQ) { p = tree_skip_term(tree_skip_term(p)); --pending; }
     else ++pending;   // binary connective
   }
@@ -73,35 +76,46 @@ __host__ __device__ inline const int* tree_skip_formula(const int* p) {
 // Returns the number of words the formula occupies, or -1.
 struct TreeCheck {
   const int* w; int n; int nvars; bool ok;
-  int term(int& i) {   // returns the height
-    if(i >= n) { ok = false; return 0; }
+  // `left` = levels this subtree may still use: the recursion stops where the device interpreter's static depth does,
+  // so a hostile stream (a long chain of negations) cannot overflow the host stack.
+  int term(int& i, int left) {   // returns the height
+    if(i >= n || left <= 0) { ok = false; return 0; }
     const int k = w[i++];
     if(k == T_CONST) { if(i >= n) { ok = false; return 0; } ++i; return 1; }
     if(k == T_VAR) { if(i >= n || w[i] < 0 || w[i] >= nvars) { ok = false; return 0; } ++i; return 1; }
-    if(k == T_NEG || k == T_ABS) return 1 + term(i);
-    if(tok_is_binary_term(k)) { const int a = term(i); if(!ok) return 0; const int b = term(i); return 1 + (a > b ? a : b); }
+    if(k == T_NEG || k == T_ABS) { const int a = term(i, left - 1); return ok ? 1 + a : 0; }
+    if(tok_is_binary_term(k)) {
+      const int a = term(i, left - 1); if(!ok) return 0;
+      const int b = term(i, left - 1); if(!ok) return 0;
+      return 1 + (a > b ? a : b);
+    }
     if(k == T_NARY_ADD || k == T_NARY_MUL) {
       if(i >= n || w[i] < 2 || w[i] > n) { ok = false; return 0; }
       const int m = w[i++];
       int h = 0;
-      for(int j = 0; j < m && ok; ++j) { const int a = term(i); h = a > h ? a : h; }
-      return 1 + h;
+      for(int j = 0; j < m && ok; ++j) { const int a = term(i, left - 1); h = a > h ? a : h; }
+      return ok ? 1 + h : 0;
     }
     ok = false;
     return 0;
   }
-  int formula(int& i) {
-    if(i >= n) { ok = false; return 0; }
+  int formula(int& i, int left) {
+    if(i >= n || left <= 0) { ok = false; return 0; }
     const int k = w[i++];
     if(k == F_VARLIT || k == F_NVARLIT) { if(i >= n || w[i] < 0 || w[i] >= nvars) { ok = false; return 0; } ++i; return 1; }
+    if(k == F_TRUE) return 1;
+    if(k == F_FALSE) { if(nvars < 1) ok = false; return 1; }   // needs a variable to empty
     if(k == F_AE) { if(i + 2 >= n || w[i] < AE_LEQ || w[i] > AE_NEQ || w[i + 1] < 0 || w[i + 1] >= nvars) { ok = false; return 0; } i += 3; return 1; }
     if(k >= F_LEQ && k <= F_NEQ) {
-      const int a = term(i); if(!ok) return 0;
-      const int b = term(i);
-      if((a > b ? a : b) > PC_TREE_TERM_DEPTH) ok = false;
+      term(i, PC_TREE_TERM_DEPTH); if(!ok) return 0;
+      term(i, PC_TREE_TERM_DEPTH); if(!ok) return 0;
       return 1;
     }
-    if(k >= F_AND && k <= F_XOR) { const int a = formula(i); if(!ok) return 0; const int b = formula(i); return 1 + (a > b ? a : b); }
+    if(k >= F_AND && k <= F_XOR) {
+      const int a = formula(i, left - 1); if(!ok) return 0;
+      const int b = formula(i, left - 1); if(!ok) return 0;
+      return 1 + (a > b ? a : b);
+    }
     ok = false;
     return 0;
   }
@@ -109,7 +123,7 @@ struct TreeCheck {
 inline int tree_check(const int* w, int n, int nvars) {
   TreeCheck c{w, n, nvars, true};
   int i = 0;
-  const int h = c.formula(i);
+  const int h = c.formula(i, PC_TREE_FORM_DEPTH);
   if(!c.ok || h > PC_TREE_FORM_DEPTH) return -1;
   for(int j = i; j < n; ++j) if(w[j] != 0) return -1;   // only zero padding after the formula
   return i;
@@ -399,6 +413,9 @@ template <int D> struct TreeForm {
       return lit_ask(neg, a.load(*p++));
     }
     if(k == F_AE) { const int op = p[0], v = p[1], c = p[2]; p += 3; return tree_ae_ask(a, op, v, c, negated); }
+    // formula.hpp:182-183, 220-221: true is entailed, false is refuted (their a.is_bot() halves only hold on a failed
+    // store, where the fixpoint has stopped)
+    if(k == F_TRUE || k == F_FALSE) return (k == F_TRUE) != negated;
     if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_ask(a, k, negated, p);
     const int* pf = p;
     const int* pg = tree_skip_formula(pf);
@@ -436,6 +453,8 @@ template <int D> struct TreeForm {
       return a.embed(*p++, neg ? Itv(0, 0) : Itv(1, 1));
     }
     if(k == F_AE) { const int op = p[0], v = p[1], c = p[2]; p += 3; return tree_ae_tell(a, op, v, c, negated); }
+    // formula.hpp:185-193, 222-228: deducing false / contradeducing true is a.meet_bot()
+    if(k == F_TRUE || k == F_FALSE) return ((k == F_FALSE) != negated) ? a.embed(0, itv_bot()) : 0;
     if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_deduce(a, k, negated, p);
     const int* pf = p;
     const int* pg = tree_skip_formula(pf);

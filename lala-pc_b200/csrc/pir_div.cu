@@ -1,4 +1,4 @@
-// pir_div.cu — out-of-line definition of the division propagators; built with `-Xptxas -O0` (see pir_div.cuh).
+// pir_div.cu — out-of-line definition of the division propagators; built with -DLPC_DIV_FIX=3 (see pir_div.cuh).
 #include "pir_div.cuh"
 
 namespace lpc {

@@ -1,10 +1,12 @@
 // pir_div.cuh — the four integer-division propagators (x = y tdiv|fdiv|cdiv|ediv z) on registers.
 //
 // Device counterpart of pir.hpp:449-699 and :780-792. Kept apart from pir_device.cuh because it is compiled in its
-// own translation unit (pir_div.cu) with `-Xptxas -O0`: ptxas 12.9 mis-allocates a register in this branchy code at
-// -O1..-O3 for sm_100a (an operand of a fused VIMNMX3 is replaced by the un-negated value; found by the exhaustive
-// TDIV parity test, see DESIGN.md "toolchain notes"). Divisions are rare in real models, so the cold path trades
-// speed for a correct binary; the hot operators stay fully optimised and are guarded by the exhaustive GPU tests.
+// own translation unit (pir_div.cu) with LPC_DIV_FIX=3, which keeps every helper below out of line: with the helpers
+// inlined into one function, CUDA 12.9 miscompiles the TDIV rules for sm_100a at -O1..-O3 (found by the exhaustive TDIV
+// parity test; minimal repro and the variants tried in tools/repro/div_miscompile.cu - `-Xcicc -O0 -Xptxas -O3` is
+// correct, so the fault is in the NVVM optimiser, not in ptxas as first thought; round 1 worked around it with
+// `-Xptxas -O0` for the whole unit). Divisions are rare in real models and the calls cost little; the hot operators stay
+// inlined and are guarded by the exhaustive GPU tests.
 #pragma once
 #include "pir_device.cuh"
 
@@ -32,7 +34,11 @@ LPC_HD int dneg(int a) { return wneg(a); }
 #endif
 #if LPC_DIV_FIX >= 3
 #undef LPC_HD
+#ifdef LPC_HOST_HARNESS
 #define LPC_HD __host__ __device__ __noinline__
+#else
+#define LPC_HD __device__ __noinline__
+#endif
 #endif
 #if LPC_DIV_FIX >= 1 && !defined(LPC_HOST_HARNESS)
 #define LPC_DIV_TDIV_ATTR __device__ __noinline__

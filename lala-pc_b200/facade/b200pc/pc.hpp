@@ -89,7 +89,7 @@ private:
 // An n-ary formula / term tree: a stand-in for lala-core's TFormula with just the structure PC::interpret reads
 // (is_variable / is_constant / is(Seq) / sig / seq(i), pc.hpp:300-604).
 struct TF {
-  enum Kind { VAR, CONST, SEQ, SET } kind = CONST;
+  enum Kind { VAR, CONST, SEQ, SET, BOOL } kind = CONST;   // BOOL: the formulas true (k = 1) / false (k = 0)
   std::string name;
   int k = 0;
   int sig_ = 0;
@@ -97,6 +97,10 @@ struct TF {
   std::vector<int> set;   // the S of `x in S`
   static TF var(const std::string& n) { TF f; f.kind = VAR; f.name = n; return f; }
   static TF z(int k) { TF f; f.kind = CONST; f.k = k; return f; }
+  static TF make_true() { TF f; f.kind = BOOL; f.k = 1; return f; }
+  static TF make_false() { TF f; f.kind = BOOL; f.k = 0; return f; }
+  bool is_true() const { return kind == BOOL && k != 0; }
+  bool is_false() const { return kind == BOOL && k == 0; }
   static TF make_nary(int sig, std::vector<TF> a) { TF f; f.kind = SEQ; f.sig_ = sig; f.args = std::move(a); return f; }
   static TF make_unary(int sig, const TF& a) { return make_nary(sig, {a}); }
   static TF make_binary(const TF& l, int sig, const TF& r) { return make_nary(sig, {l, r}); }
@@ -416,7 +420,7 @@ private:
   // Token numbers of the stream; heights are checked against the device interpreter's limits (csrc/pc_tree.cuh).
   enum { TK_CONST = 1, TK_VAR = 2, TK_NEG = 3, TK_ABS = 4, TK_ADD = 5, TK_SUB = 6, TK_MUL = 7, TK_NARY_ADD = 8, TK_MIN = 9,
          TK_MAX = 10, TK_TDIV = 11, TK_FDIV = 12, TK_CDIV = 13, TK_EDIV = 14, TK_NARY_MUL = 15, FK_LIT = 20, FK_NLIT = 21, FK_LEQ = 22, FK_GT = 23, FK_EQ = 24, FK_NEQ = 25, FK_AND = 26, FK_OR = 27,
-         FK_EQUIV = 28, FK_IMPLY = 29, FK_XOR = 30, TREE_TERM_DEPTH = 5, TREE_FORM_DEPTH = 4 };
+         FK_EQUIV = 28, FK_IMPLY = 29, FK_XOR = 30, FK_TRUE = 32, FK_FALSE = 33, TREE_TERM_DEPTH = 5, TREE_FORM_DEPTH = 4 };
   // interpret_term (pc.hpp:217-296): returns the height (0 = not a term), `len` = Term::length()
   static int tree_term(const TF& t, const VarEnv& env, std::vector<int>& w, int& len) {
     AVar v;
@@ -453,6 +457,10 @@ private:
   // index of the pc::Formula alternative the reference builds (formula.hpp:886-899), `len` = its length().
   static int tree_formula(const TF& f, const VarEnv& env, std::vector<int>& w, int& ref_kind, int& len, bool negate = false) {
     AVar v;
+    if(f.is_true() || f.is_false()) {   // pc.hpp:515-522: Formula::make_false / make_true (formula.hpp:169-239)
+      const bool t = f.is_true() != negate;
+      w.push_back(t ? FK_TRUE : FK_FALSE); ref_kind = t ? 2 : 3; len = 1; return 1;
+    }
     if(f.is_variable()) {
       if(!env.interpret(F::var(f.name), v)) return 0;
       w.push_back(negate ? FK_NLIT : FK_LIT); w.push_back(v.vid()); ref_kind = negate ? 1 : 0; len = 1; return 1;
@@ -460,7 +468,7 @@ private:
     if(!f.is_seq()) return 0;
     if(f.sig() == NOT && f.args.size() == 1) {   // negation is pushed into a literal or a comparison (pc.hpp:487-520)
       const TF& g = f.seq(0);
-      if(g.is_variable() || g.is_predicate()) return tree_formula(g, env, w, ref_kind, len, !negate);
+      if(g.is_variable() || g.is_predicate() || g.kind == TF::BOOL) return tree_formula(g, env, w, ref_kind, len, !negate);
       return 0;
     }
     if(f.args.size() > 2 && (f.sig() == AND || f.sig() == OR) && !negate) {   // binarised to the right (pc.hpp:454-463)

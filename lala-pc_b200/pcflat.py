@@ -10,7 +10,7 @@ Formulas are nested tuples (a plain Python stand-in for lala-core's TFormula):
             ('eq', ('var', x), ('var', y))  ('ne', ('var', x), ('var', y) | ('const', k))
             ('or', lit, ('or', lit, ...)) with lit = ('lit', v) | ('nlit', v)   ('eq', ('abs', ('var', x)), ('var', y))
 Any other formula over these node types - and ('min' | 'max' | 'mul' | 'tdiv' | 'fdiv' | 'cdiv' | 'ediv', t1, t2) terms,
-('prod', t1, ..., tn) products, ('and' | 'or' | 'equiv' | 'imply' | 'xor', f, g) connectives, ('ae', op, var, k) store
+('prod', t1, ..., tn) products, ('and' | 'or' | 'equiv' | 'imply' | 'xor', f, g) connectives, ('true',) / ('false',), ('ae', op, var, k) store
 elements, comparisons between two non-constant terms - keeps its tree: `flatten` encodes it as an
 LPC_PC_TREE propagator (the prefix stream of include/lpc_pc.h in the propagator's term slots), which the device walks
 node by node (csrc/pc_tree.cuh). `flatten(..., tree=False)` raises `Unsupported` for those instead (the reference's
@@ -25,7 +25,7 @@ TREE_TERM_DEPTH, TREE_FORM_DEPTH = 5, 4   # csrc/pc_tree.cuh
 _T = {"const": 1, "var": 2, "neg": 3, "abs": 4, "add": 5, "sub": 6, "mul": 7, "sum": 8, "min": 9, "max": 10,
       "tdiv": 11, "fdiv": 12, "cdiv": 13, "ediv": 14, "prod": 15}
 _F = {"lit": 20, "nlit": 21, "le": 22, "gt": 23, "eq": 24, "ne": 25, "and": 26, "or": 27, "equiv": 28, "imply": 29, "xor": 30,
-      "ae": 31}
+      "ae": 31, "true": 32, "false": 33}
 _AE = {"le": 0, "ge": 1, "eq": 2, "ne": 3}
 
 
@@ -143,6 +143,9 @@ def _encode_formula(f, out):
         return 1
     if op == "ae":   # ('ae', 'le' | 'ge' | 'eq' | 'ne', var, k): AbstractElement over the store (formula.hpp:14-77)
         out += [_F[op], _AE[f[1]], int(f[2]), int(f[3])]
+        return 1
+    if op in ("true", "false"):   # ('true',) / ('false',): the constant formulas (formula.hpp:169-239)
+        out.append(_F[op])
         return 1
     out.append(_F[op])
     if op in ("le", "gt", "eq", "ne"):

@@ -286,6 +286,8 @@ def flatten(tree):
         return [binary[op]] + flatten(tree[1]) + flatten(tree[2])
     if op == "ae":   # ('ae', 'le' | 'ge' | 'eq' | 'ne', var, k): a store-level element (AbstractElement)
         return [F_AE, AE_OPS[tree[1]], int(tree[2]), int(tree[3])]
+    if op in ("true", "false"):   # the constant formulas (formula.hpp:169-239)
+        return [32 if op == "true" else 33]
     if op in ("sum", "prod"):
         out = [T_NARY_ADD if op == "sum" else T_NARY_MUL, len(tree) - 1]
         for t in tree[1:]:

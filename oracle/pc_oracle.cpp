@@ -50,7 +50,7 @@ typedef int32_t v_t;
 enum Tok { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8, T_MIN = 9, T_MAX = 10,
            T_TDIV = 11, T_FDIV = 12, T_CDIV = 13, T_EDIV = 14, T_NARY_MUL = 15,
            F_VARLIT = 20, F_NVARLIT = 21, F_LEQ = 22, F_GT = 23, F_EQ = 24, F_NEQ = 25, F_AND = 26, F_OR = 27, F_EQUIV = 28,
-           F_IMPLY = 29, F_XOR = 30, F_AE = 31 };
+           F_IMPLY = 29, F_XOR = 30, F_AE = 31, F_TRUE = 32, F_FALSE = 33 };   // True / False: formula.hpp:169-239
 enum AeOp { AE_LEQ = 0, AE_GEQ = 1, AE_EQ = 2, AE_NEQ = 3 };   // F_AE op var k: a store-level element `var op k`
 const v_t INF = INT32_MAX, MINF = INT32_MIN;
 
@@ -67,6 +67,7 @@ struct Itv {
   bool sub_of(v_t l, v_t u) const { return is_bot() || (lb >= l && ub <= u); }   // `*this <= [l,u]`
   bool same(const Itv& o) const { return (is_bot() && o.is_bot()) || (lb == o.lb && ub == o.ub); }
   Itv complement() const { return Itv(); }                        // never called (complemented == false)
+  static Itv empty() { return Itv(INF, MINF); }
 };
 inline Itv fjoin(const Itv& a, const Itv& b) {
   if(a.is_bot()) return b;
@@ -190,6 +191,7 @@ struct NBit {
   bool sub_of(v_t l, v_t u) const { return (bits & ~NBit(l, u).bits) == 0; }
   bool same(const NBit& o) const { return bits == o.bits; }
   NBit complement() const { return raw(~bits); }
+  static NBit empty() { return raw(0); }
   Itv itv() const { return Itv(lo(), hi()); }
 };
 inline NBit from_itv(const Itv& i) { return NBit(i.lb, i.ub); }
@@ -218,6 +220,15 @@ struct Store {
   bool embed(int v, const U& u) {                                    // VStore::embed
     if(d[v].meet(u)) { touched = true; if(d[v].is_bot()) bot = true; return true; }
     return false;
+  }
+  bool is_bot() const { return bot; }
+  // a.meet_bot() (formula.hpp:185-193): the whole element fails. VStore keeps a flag; the device has no flag and empties
+  // variable 0 - stores of failed elements are not compared (only that they failed).
+  bool meet_bot() {
+    if(bot) return false;
+    bot = true; touched = true;
+    if(n > 0) d[0] = U::empty();
+    return true;
   }
 };
 static_assert(sizeof(Itv) == 8 && sizeof(NBit) == 8, "8-byte cells");
@@ -371,6 +382,8 @@ struct Formula {
         if(neg) { U m = x; m.meet(y); return m.is_bot(); }
         return x.same(y) && x.lo() == x.hi();
       }
+      case F_TRUE: return negated ? a.is_bot() : true;              // formula.hpp:220-221
+      case F_FALSE: return negated ? true : a.is_bot();             // formula.hpp:182-183
       case F_AE: {   // AbstractElement::ask / nask = the store's ask of the element / of its negation (formula.hpp:43-49)
         int op = ae_op; v_t k = ae_k;
         if(negated) { if(op == AE_LEQ) { op = AE_GEQ; k = badd(k, 1); } else if(op == AE_GEQ) { op = AE_LEQ; k = bsub(k, 1); } else op = op == AE_EQ ? AE_NEQ : AE_EQ; }
@@ -445,6 +458,8 @@ struct Formula {
         if(!l->is_const()) { r->project(a, y); ch |= l->embed(a, y); }
         return ch;
       }
+      case F_TRUE: return negated ? a.meet_bot() : false;           // formula.hpp:222-228
+      case F_FALSE: return negated ? false : a.meet_bot();          // formula.hpp:185-193
       case F_AE: {   // AbstractElement::deduce / contradeduce = the store's deduce of the element / its negation
         int op = ae_op; v_t k = ae_k;   // (formula.hpp:51-57); `!=` has no interval (AbstractElement3-4, pc_test.cpp:738-764)
         if(negated) { if(op == AE_LEQ) { op = AE_GEQ; k = badd(k, 1); } else if(op == AE_GEQ) { op = AE_LEQ; k = bsub(k, 1); } else op = op == AE_EQ ? AE_NEQ : AE_EQ; }
@@ -514,6 +529,7 @@ std::unique_ptr<Formula<U>> parse_formula(const int32_t*& p) {
   switch(f->kind) {
     case F_VARLIT: case F_NVARLIT: f->var = *p++; break;
     case F_AE: f->ae_op = *p++; f->var = *p++; f->ae_k = *p++; break;
+    case F_TRUE: case F_FALSE: break;
     case F_LEQ: case F_GT: case F_EQ: case F_NEQ: f->l = parse_term<U>(p); f->r = parse_term<U>(p); break;
     default: f->f = parse_formula<U>(p); f->g = parse_formula<U>(p); break;
   }

@@ -193,6 +193,8 @@ def random_tree_pc(rng, nvars, n_forms=None):
         r = rng.random()
         if depth <= 1 or r < 0.3:
             q = rng.random()
+            if q < 0.05:   # the constant formulas (formula.hpp:169-239)
+                return ("true",) if rng.random() < 0.6 else ("false",)
             if q < 0.2:
                 return (str(rng.choice(["lit", "nlit"])), int(rng.integers(0, nvars)))
             if q < 0.3:

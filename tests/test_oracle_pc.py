@@ -88,3 +88,21 @@ def test_bitset_refines_interval():
     assert (sb != hull).any()        # != punches holes an interval cannot hold
     sol = np.array([O.nbit(v, v) for v in net.solution.tolist()], dtype=np.uint64)
     assert ((sb & sol) == sol).all()  # the planted solution survives
+
+
+def test_true_false_nodes():
+    """formula.hpp:169-239: True is entailed and does nothing, False fails the element; under connectives they act as
+    the constants they are (b <=> true fixes b, false \\/ c enforces c, b => false refutes b)."""
+    from oracle import oracle as O
+    store = np.array([[0, 1], [0, 10], [0, 1]], dtype=np.int32)
+    forms = [("equiv", ("lit", 0), ("true",)), ("or", ("false",), ("le", ("var", 1), ("const", 4))),
+             ("imply", ("lit", 2), ("false",)), ("true",)]
+    m = O.PCModel(forms)
+    out, st = m.fixpoint(store)
+    assert not st.is_bot and out.tolist() == [[1, 1], [0, 4], [0, 0]]
+    n, bits = m.ask_all(out, want_bits=True)
+    assert bits.tolist() == [1, 1, 1, 1]
+    _, st = O.PCModel([("false",)]).fixpoint(store)
+    assert st.is_bot
+    _, st = O.PCModel([("and", ("true",), ("equiv", ("lit", 0), ("false",))), ("lit", 0)]).fixpoint(store)
+    assert st.is_bot

@@ -11,5 +11,5 @@ build O3_fix1 -DLPC_DIV_FIX=1
 build O3_fix2 -DLPC_DIV_FIX=2
 build cicc0_ptxas3 -Xcicc -O0
 build O3_fix3 -DLPC_DIV_FIX=3
-build O3_nofma -Xptxas --fmad=false
-for v in O3 O0 cicc0_ptxas3 O3_fix3 O3_nofma; do echo "== variant $v"; /tmp/div_$v ${1:-6}; echo "exit $?"; done
+build O3_fix3_r64 -DLPC_DIV_FIX=3 -maxrregcount=64
+for v in O3 O0 cicc0_ptxas3 O3_fix3 O3_fix3_r64; do echo "== variant $v"; /tmp/div_$v ${1:-6}; echo "exit $?"; done
