@@ -414,22 +414,26 @@ static int store_init_common(lpc_store* s) {
 
 int lpc_store_create(int32_t nvars, lpc_store** out) {
   LPC_REQUIRE(out != nullptr && nvars >= 0, "bad argument");
-  int cnt = 0;
-  lpc_device_count(&cnt);
-  if(cnt == 0) { set_error("no CUDA device: this library has no CPU path"); return LPC_ERR_NO_DEVICE; }
+  int rc = no_device();
+  if(rc) return rc;
   lpc_store* s = new lpc_store();
-  LPC_CUDA(cudaGetDevice(&s->device));
   s->nvars = nvars;
   s->owning = true;
-  cudaError_t e = cudaMalloc((void**)&s->d, std::max<size_t>((size_t)nvars * 8, 16));
-  if(e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(store)", __FILE__, __LINE__); }
-  if(nvars) {
-    k_store_fill_top<<<ceil_div(nvars, 256), 256>>>(s->d, nvars);
-    g_launches++;
-  }
-  int rc = store_init_common(s);
-  if(rc) { lpc_store_destroy(s); return rc; }
-  LPC_CUDA(cudaDeviceSynchronize());
+  // every failure below destroys the half-built handle (and what it already allocated) before returning
+  auto body = [&]() -> int {
+    LPC_CUDA(cudaGetDevice(&s->device));
+    LPC_CUDA(cudaMalloc((void**)&s->d, std::max<size_t>((size_t)nvars * 8, 16)));
+    if(nvars) {
+      k_store_fill_top<<<ceil_div(nvars, 256), 256>>>(s->d, nvars);
+      g_launches++;
+      LPC_CUDA(cudaGetLastError());
+    }
+    int rc2 = store_init_common(s);
+    if(rc2) return rc2;
+    LPC_CUDA(cudaDeviceSynchronize());
+    return LPC_OK;
+  };
+  if((rc = body())) { lpc_store_destroy(s); return rc; }
   *out = s;
   return LPC_OK;
 }
@@ -438,10 +442,11 @@ int lpc_store_wrap_device(void* device_ptr, int32_t nvars, lpc_store** out) {
   LPC_REQUIRE(out != nullptr && nvars >= 0 && device_ptr != nullptr, "bad argument");
   LPC_REQUIRE(((uintptr_t)device_ptr & 7) == 0, "device pointer must be 8-byte aligned");
   lpc_store* s = new lpc_store();
-  LPC_CUDA(cudaGetDevice(&s->device));
   s->nvars = nvars;
   s->owning = false;
   s->d = (int2*)device_ptr;
+  cudaError_t e = cudaGetDevice(&s->device);
+  if(e != cudaSuccess) { lpc_store_destroy(s); return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__); }
   int rc = store_init_common(s);
   if(rc) { lpc_store_destroy(s); return rc; }
   *out = s;

@@ -560,26 +560,31 @@ int lpc_batch_create(const lpc_table* t, int32_t n_stores, lpc_batch** out) {
   b->table = t; b->n_stores = n_stores; b->nvars = t->dev.nvars; b->table_gen = t->generation;
   // ring slots are multiples of 16 B (bulk copy granularity); stores are packed at nvars*8 B in global memory, so
   // the per-store image must itself be a multiple of 16 B: require an even number of variables or pad by one.
-  b->sbytes = ((b->nvars * 8 + 15) / 16) * 16;
-  if(b->sbytes != b->nvars * 8) {
+  b->sbytes = (int)((((size_t)b->nvars * 8 + 15) / 16) * 16);
+  if((size_t)b->sbytes != (size_t)b->nvars * 8) {
     delete b;
     set_error("lpc_batch_create: batched stores need an even number of variables (got %d); pad the model with one unused variable", t->dev.nvars);
     return LPC_ERR_UNSUPPORTED;
   }
-  size_t bytes = std::max<size_t>((size_t)n_stores * b->nvars * 8, 16);
-  cudaError_t e = cudaMalloc((void**)&b->d, bytes);
-  if(e != cudaSuccess) { delete b; return cuda_fail(e, "cudaMalloc(batch)", __FILE__, __LINE__); }
-  LPC_CUDA(cudaMalloc((void**)&b->d_flags, std::max(n_stores, 16)));
-  LPC_CUDA(cudaMalloc((void**)&b->d_sweeps, std::max(n_stores, 4) * sizeof(int)));
-  LPC_CUDA(cudaMalloc((void**)&b->d_obj, std::max(n_stores, 4) * sizeof(int)));
-  LPC_CUDA(cudaMalloc((void**)&b->d_ctl, sizeof(BatchCtl)));
-  LPC_CUDA(cudaMemset(b->d_ctl, 0, sizeof(BatchCtl)));
-  LPC_CUDA(cudaMemset(b->d_flags, 0, std::max(n_stores, 16)));
-  LPC_CUDA(cudaHostAlloc((void**)&b->h_ctl, sizeof(BatchCtl), cudaHostAllocDefault));
-  memset(b->h_ctl, 0, sizeof(BatchCtl));
-  LPC_CUDA(cudaHostAlloc((void**)&b->h_init, sizeof(BatchCtl), cudaHostAllocDefault));
-  LPC_CUDA(cudaEventCreate(&b->ev0));
-  LPC_CUDA(cudaEventCreate(&b->ev1));
+  // every failure below destroys the half-built handle (and what it already allocated) before returning
+  auto body = [&]() -> int {
+    const size_t bytes = std::max<size_t>((size_t)n_stores * (size_t)b->nvars * 8, 16);
+    LPC_CUDA(cudaMalloc((void**)&b->d, bytes));
+    LPC_CUDA(cudaMalloc((void**)&b->d_flags, std::max(n_stores, 16)));
+    LPC_CUDA(cudaMalloc((void**)&b->d_sweeps, std::max(n_stores, 4) * sizeof(int)));
+    LPC_CUDA(cudaMalloc((void**)&b->d_obj, std::max(n_stores, 4) * sizeof(int)));
+    LPC_CUDA(cudaMalloc((void**)&b->d_ctl, sizeof(BatchCtl)));
+    LPC_CUDA(cudaMemset(b->d_ctl, 0, sizeof(BatchCtl)));
+    LPC_CUDA(cudaMemset(b->d_flags, 0, std::max(n_stores, 16)));
+    LPC_CUDA(cudaHostAlloc((void**)&b->h_ctl, sizeof(BatchCtl), cudaHostAllocDefault));
+    memset(b->h_ctl, 0, sizeof(BatchCtl));
+    LPC_CUDA(cudaHostAlloc((void**)&b->h_init, sizeof(BatchCtl), cudaHostAllocDefault));
+    LPC_CUDA(cudaEventCreate(&b->ev0));
+    LPC_CUDA(cudaEventCreate(&b->ev1));
+    return LPC_OK;
+  };
+  const int rc_body = body();
+  if(rc_body) { lpc_batch_destroy(b); return rc_body; }
   *out = b;
   return LPC_OK;
 }
@@ -642,27 +647,31 @@ static int batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_
   if(b->n_stores == 0) return LPC_OK;
   int2* d_base = nullptr;
   int* d_dec = nullptr;
-  LPC_CUDA(cudaMalloc((void**)&d_base, std::max<size_t>((size_t)b->nvars * 8, 16)));
-  LPC_CUDA(cudaMalloc((void**)&d_dec, std::max(n_decisions, 1) * sizeof(int)));
-  LPC_CUDA(cudaMemcpy(d_base, base_lbub, (size_t)b->nvars * 8, cudaMemcpyHostToDevice));
-  if(n_decisions) LPC_CUDA(cudaMemcpy(d_dec, decision_vars, n_decisions * sizeof(int), cudaMemcpyHostToDevice));
   long long* d_ids = nullptr;
-  if(ids) {
-    LPC_CUDA(cudaMalloc((void**)&d_ids, (size_t)b->n_stores * 8));
-    LPC_CUDA(cudaMemcpy(d_ids, ids, (size_t)b->n_stores * 8, cudaMemcpyHostToDevice));
-  }
-  k_batch_init_split<<<std::min(b->n_stores, 148 * 16), 256>>>(b->d, b->nvars, b->n_stores, d_base, d_dec, n_decisions, first_id, d_ids);
-  g_launches++;
-  LPC_CUDA(cudaGetLastError());
-  // every image of the batch is now a tightening of `base`: LPC_MODE_AUTO may drop the propagators entailed on it
-  if(!b->d_root) LPC_CUDA(cudaMalloc((void**)&b->d_root, std::max<size_t>((size_t)b->nvars * 8, 16)));
-  LPC_CUDA(cudaMemcpy(b->d_root, d_base, (size_t)b->nvars * 8, cudaMemcpyDeviceToDevice));
-  b->root_valid = true;
-  LPC_CUDA(cudaDeviceSynchronize());
-  cudaFree(d_base);
+  auto body = [&]() -> int {
+    LPC_CUDA(cudaMalloc((void**)&d_base, std::max<size_t>((size_t)b->nvars * 8, 16)));
+    LPC_CUDA(cudaMalloc((void**)&d_dec, std::max(n_decisions, 1) * sizeof(int)));
+    LPC_CUDA(cudaMemcpy(d_base, base_lbub, (size_t)b->nvars * 8, cudaMemcpyHostToDevice));
+    if(n_decisions) LPC_CUDA(cudaMemcpy(d_dec, decision_vars, n_decisions * sizeof(int), cudaMemcpyHostToDevice));
+    if(ids) {
+      LPC_CUDA(cudaMalloc((void**)&d_ids, (size_t)b->n_stores * 8));
+      LPC_CUDA(cudaMemcpy(d_ids, ids, (size_t)b->n_stores * 8, cudaMemcpyHostToDevice));
+    }
+    k_batch_init_split<<<std::min(b->n_stores, 148 * 16), 256>>>(b->d, b->nvars, b->n_stores, d_base, d_dec, n_decisions, first_id, d_ids);
+    g_launches++;
+    LPC_CUDA(cudaGetLastError());
+    // every image of the batch is now a tightening of `base`: LPC_MODE_AUTO may drop the propagators entailed on it
+    if(!b->d_root) LPC_CUDA(cudaMalloc((void**)&b->d_root, std::max<size_t>((size_t)b->nvars * 8, 16)));
+    LPC_CUDA(cudaMemcpy(b->d_root, d_base, (size_t)b->nvars * 8, cudaMemcpyDeviceToDevice));
+    b->root_valid = true;
+    LPC_CUDA(cudaDeviceSynchronize());
+    return LPC_OK;
+  };
+  const int rc = body();
+  cudaFree(d_base);   // the scratch goes whether or not a step failed
   cudaFree(d_dec);
   cudaFree(d_ids);
-  return LPC_OK;
+  return rc;
 }
 
 int lpc_batch_set_seeds(lpc_batch* b, const int32_t* vars, int32_t n) {
@@ -763,6 +772,8 @@ void* lpc_batch_payload_device_ptr(lpc_batch* b, int32_t* n_int64) {
 int lpc_batch_fixpoint_async(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t objective_var) {
   LPC_REQUIRE(b != nullptr, "null batch");
   LPC_REQUIRE(objective_var < b->nvars, "objective variable out of range");
+  LPC_REQUIRE(!b->pending, "a call is still in flight on this batch (collect it first)");
+  { int rc = lpc_check_device(b->table->device, "lpc_batch_fixpoint"); if(rc) return rc; }
   lpc_fixpoint_opts def;
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   cudaStream_t st = (cudaStream_t)o->stream;
@@ -932,29 +943,33 @@ int lpc_batch_search(lpc_batch* b, const int32_t* branch_vars, int32_t n_branch,
   const int grid = std::max(1, std::min(b->n_stores, sms * per_sm));
   // scratch: snapshot stacks, branching order, per-store records, control block
   int2* d_stack = nullptr; int* d_bv = nullptr; long long* d_ps = nullptr; SearchCtl* d_ctl = nullptr; int* d_vstack = nullptr;
-  LPC_CUDA(cudaMalloc((void**)&d_stack, std::max<size_t>((size_t)grid * o->max_depth * b->nvars * 8, 16)));
-  LPC_CUDA(cudaMalloc((void**)&d_vstack, std::max<size_t>((size_t)grid * o->max_depth * 4, 16)));
-  LPC_CUDA(cudaMalloc((void**)&d_bv, std::max<size_t>((size_t)n_branch * 4, 16)));
-  LPC_CUDA(cudaMalloc((void**)&d_ps, std::max<size_t>((size_t)b->n_stores * 6 * 8, 16)));
-  LPC_CUDA(cudaMalloc((void**)&d_ctl, sizeof(SearchCtl)));
   SearchCtl h;
   memset(&h, 0, sizeof(h));
   h.best = LPC_INF; h.next_store = grid;
-  if(n_branch) LPC_CUDA(cudaMemcpyAsync(d_bv, branch_vars, (size_t)n_branch * 4, cudaMemcpyHostToDevice, st));
-  LPC_CUDA(cudaMemcpyAsync(d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-  LPC_CUDA(cudaEventRecord(b->ev0, st));
-  if(b->n_stores > 0) {
-    k<<<grid, threads, smem, st>>>(t->dev, t->opsegs, b->d, b->n_stores, b->sbytes, d_stack, d_vstack, o->max_depth, d_bv, n_branch,
-                                  o->objective_var, (long long)o->max_nodes, d_ps, d_ctl, b->d_seeds, b->n_seeds);
-    g_launches++;
-    LPC_CUDA(cudaGetLastError());
-  }
-  LPC_CUDA(cudaEventRecord(b->ev1, st));
-  LPC_CUDA(cudaMemcpyAsync(&h, d_ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
-  if(per_store && b->n_stores) LPC_CUDA(cudaMemcpyAsync(per_store, d_ps, (size_t)b->n_stores * 6 * 8, cudaMemcpyDeviceToHost, st));
-  cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(d_stack); cudaFree(d_vstack); cudaFree(d_bv); cudaFree(d_ps); cudaFree(d_ctl);
-  LPC_CUDA(e);
+  auto body = [&]() -> int {
+    LPC_CUDA(cudaMalloc((void**)&d_stack, std::max<size_t>((size_t)grid * o->max_depth * b->nvars * 8, 16)));
+    LPC_CUDA(cudaMalloc((void**)&d_vstack, std::max<size_t>((size_t)grid * o->max_depth * 4, 16)));
+    LPC_CUDA(cudaMalloc((void**)&d_bv, std::max<size_t>((size_t)n_branch * 4, 16)));
+    LPC_CUDA(cudaMalloc((void**)&d_ps, std::max<size_t>((size_t)b->n_stores * 6 * 8, 16)));
+    LPC_CUDA(cudaMalloc((void**)&d_ctl, sizeof(SearchCtl)));
+    if(n_branch) LPC_CUDA(cudaMemcpyAsync(d_bv, branch_vars, (size_t)n_branch * 4, cudaMemcpyHostToDevice, st));
+    LPC_CUDA(cudaMemcpyAsync(d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    LPC_CUDA(cudaEventRecord(b->ev0, st));
+    if(b->n_stores > 0) {
+      k<<<grid, threads, smem, st>>>(t->dev, t->opsegs, b->d, b->n_stores, b->sbytes, d_stack, d_vstack, o->max_depth, d_bv, n_branch,
+                                    o->objective_var, (long long)o->max_nodes, d_ps, d_ctl, b->d_seeds, b->n_seeds);
+      g_launches++;
+      LPC_CUDA(cudaGetLastError());
+    }
+    LPC_CUDA(cudaEventRecord(b->ev1, st));
+    LPC_CUDA(cudaMemcpyAsync(&h, d_ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    if(per_store && b->n_stores) LPC_CUDA(cudaMemcpyAsync(per_store, d_ps, (size_t)b->n_stores * 6 * 8, cudaMemcpyDeviceToHost, st));
+    LPC_CUDA(cudaStreamSynchronize(st));
+    return LPC_OK;
+  };
+  const int rc_body = body();
+  cudaFree(d_stack); cudaFree(d_vstack); cudaFree(d_bv); cudaFree(d_ps); cudaFree(d_ctl);   // also when a step failed
+  if(rc_body) return rc_body;
   if(r) {
     memset(r, 0, sizeof(*r));
     r->n_solutions = h.n_solutions; r->n_nodes = h.n_nodes; r->n_fails = h.n_fails; r->n_unknown_leaves = h.n_unknown_leaves;

@@ -125,6 +125,12 @@ __device__ __forceinline__ int gbar_and(int id, int n, int pred) {
   return r;
 }
 
+// An emptied variable is signalled to the whole group at once (a predicated store to the group's bot word), so that the
+// other threads can abandon the rest of the sweep: the store has failed, whatever else the sweep computes is moot.
+__device__ __forceinline__ void signal_bot(unsigned a_bot, int bn) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q st.shared.s32 [%0], %1; }" ::"r"(a_bot), "r"(bn) : "memory");
+}
+
 // One propagator on gathered bounds. FIN: every bound of the store was finite when it was loaded; bounds only tighten,
 // so the infinity guards of pir.hpp:759-764 can never fire and `x = y + z` is six fused add-min/max.
 // The join: a lane whose record moved anything issues all six shared-memory reductions (the ones of bounds that did not
@@ -158,7 +164,7 @@ __device__ __forceinline__ void sts_if_lt(unsigned addr, int nw, int old) {
 
 template <int OP, bool HAS_DIV, bool FIN, int JOIN>
 __device__ __forceinline__ void pk_rule(int op, int2 a, int2 b, int2 c, unsigned ax, unsigned ay, unsigned az,
-                                        unsigned& macc, int& bacc) {
+                                        unsigned& macc, int& bacc, unsigned a_bot) {
   Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
   if(FIN && OP == D_ADD) {
     // pir.hpp:759-764; later lines see the bounds the earlier ones just tightened, as in the reference
@@ -172,13 +178,13 @@ __device__ __forceinline__ void pk_rule(int op, int2 a, int2 b, int2 c, unsigned
     sts_if_gt(ax, r1.lb, a.x); sts_if_lt(ax + 4, r1.ub, a.y);
     sts_if_gt(ay, r2.lb, b.x); sts_if_lt(ay + 4, r2.ub, b.y);
     sts_if_gt(az, r3.lb, c.x); sts_if_lt(az + 4, r3.ub, c.y);
-    bacc |= (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub);
+    { const int bn = (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub); signal_bot(a_bot, bn); bacc |= bn; }
   }
   else if(JOIN == 2) {
     reds_max_if_gt(ax, r1.lb, a.x); reds_min_if_lt(ax + 4, r1.ub, a.y);
     reds_max_if_gt(ay, r2.lb, b.x); reds_min_if_lt(ay + 4, r2.ub, b.y);
     reds_max_if_gt(az, r3.lb, c.x); reds_min_if_lt(az + 4, r3.ub, c.y);
-    bacc |= (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub);
+    { const int bn = (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub); signal_bot(a_bot, bn); bacc |= bn; }
   }
   else if(moved) {
     if(JOIN == 1) {
@@ -191,39 +197,49 @@ __device__ __forceinline__ void pk_rule(int op, int2 a, int2 b, int2 c, unsigned
       reds_max(ay, r2.lb); reds_min(ay + 4, r2.ub);
       reds_max(az, r3.lb); reds_min(az + 4, r3.ub);
     }
-    bacc |= (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub);
+    { const int bn = (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub); signal_bot(a_bot, bn); bacc |= bn; }
   }
   macc |= moved;
 }
 
-// The pairs [p0, p1) of one run: two records per thread and iteration.
+// The pairs [p0, p1) of one run: two records per thread and iteration, in chunks of four iterations after each of which
+// the group's bot word is looked at (stop_on_bot): most EPS subproblems fail, and a failed store's sweep is cut short as
+// soon as any thread has emptied a variable. `nev` counts the records this thread evaluated.
 template <int OP, bool HAS_DIV, bool FIN, int JOIN>
-__device__ __forceinline__ int pk_sweep_run(int p0, int p1, unsigned a_T, unsigned a_S, int tid, int nthr) {
+__device__ __forceinline__ int pk_sweep_run(int p0, int p1, unsigned a_T, unsigned a_S, int tid, int nthr, unsigned a_bot, int stop,
+                                            unsigned& nev) {
   unsigned macc = 0;
   int bacc = 0;
-  for(int p = p0 + tid; p < p1; p += nthr) {
-    const uint4 q = lds_v4(a_T + 16u * (unsigned)p);
-    const unsigned ax0 = a_S + (q.x & 0xffffu), ay0 = a_S + (q.x >> 16), az0 = a_S + (q.y & 0xffffu);
-    const unsigned ax1 = a_S + (q.z & 0xffffu), ay1 = a_S + (q.z >> 16), az1 = a_S + (q.w & 0xffffu);
-    const int2 a0 = lds_itv(ax0), b0 = lds_itv(ay0), c0 = lds_itv(az0);
-    const int2 a1 = lds_itv(ax1), b1 = lds_itv(ay1), c1 = lds_itv(az1);
-    pk_rule<OP, HAS_DIV, FIN, JOIN>(OP < 0 ? (int)(q.y >> 16) : OP, a0, b0, c0, ax0, ay0, az0, macc, bacc);
-    pk_rule<OP, HAS_DIV, FIN, JOIN>(OP < 0 ? (int)(q.w >> 16) : OP, a1, b1, c1, ax1, ay1, az1, macc, bacc);
+  for(int c0 = p0; c0 < p1; c0 += 4 * nthr) {
+    const int c1 = min(c0 + 4 * nthr, p1);
+    for(int p = c0 + tid; p < c1; p += nthr) {
+      const uint4 q = lds_v4(a_T + 16u * (unsigned)p);
+      const unsigned ax0 = a_S + (q.x & 0xffffu), ay0 = a_S + (q.x >> 16), az0 = a_S + (q.y & 0xffffu);
+      const unsigned ax1 = a_S + (q.z & 0xffffu), ay1 = a_S + (q.z >> 16), az1 = a_S + (q.w & 0xffffu);
+      const int2 a0 = lds_itv(ax0), b0 = lds_itv(ay0), c0v = lds_itv(az0);
+      const int2 a1 = lds_itv(ax1), b1 = lds_itv(ay1), c1v = lds_itv(az1);
+      pk_rule<OP, HAS_DIV, FIN, JOIN>(OP < 0 ? (int)(q.y >> 16) : OP, a0, b0, c0v, ax0, ay0, az0, macc, bacc, a_bot);
+      pk_rule<OP, HAS_DIV, FIN, JOIN>(OP < 0 ? (int)(q.w >> 16) : OP, a1, b1, c1v, ax1, ay1, az1, macc, bacc, a_bot);
+    }
+    nev += 2u * (unsigned)max(0, (c1 - c0 - tid + nthr - 1) / nthr);
+    if(stop && lds_s32(a_bot)) break;
   }
   return (macc != 0u ? 1 : 0) | (bacc ? 2 : 0);
 }
 
 template <bool HAS_DIV, int JOIN>
-__device__ __forceinline__ int pk_sweep(const PackedHdr& h, unsigned a_T, unsigned a_S, int tid, int nthr, bool fin) {
+__device__ __forceinline__ int pk_sweep(const PackedHdr& h, unsigned a_T, unsigned a_S, int tid, int nthr, bool fin, unsigned a_bot,
+                                        int stop, unsigned& nev) {
   int f = 0;
   for(int r = 0; r < h.nruns; ++r) {
+    if(r && stop && lds_s32(a_bot)) break;
     const int p0 = h.start[r] >> 1, p1 = h.start[r + 1] >> 1;
-#define LPC_RUN(O) case O: f |= pk_sweep_run<O, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr); break;
+#define LPC_RUN(O) case O: f |= pk_sweep_run<O, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr, a_bot, stop, nev); break;
     switch(h.op[r]) {
-      case D_ADD: f |= fin ? pk_sweep_run<D_ADD, HAS_DIV, true, JOIN>(p0, p1, a_T, a_S, tid, nthr)
-                           : pk_sweep_run<D_ADD, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr); break;
+      case D_ADD: f |= fin ? pk_sweep_run<D_ADD, HAS_DIV, true, JOIN>(p0, p1, a_T, a_S, tid, nthr, a_bot, stop, nev)
+                           : pk_sweep_run<D_ADD, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr, a_bot, stop, nev); break;
       LPC_RUN(D_MUL) LPC_RUN(D_MIN) LPC_RUN(D_MAX) LPC_RUN(D_EQ) LPC_RUN(D_LEQ)
-      default: f |= pk_sweep_run<-1, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr); break;
+      default: f |= pk_sweep_run<-1, HAS_DIV, false, JOIN>(p0, p1, a_T, a_S, tid, nthr, a_bot, stop, nev); break;
     }
 #undef LPC_RUN
   }
@@ -232,21 +248,27 @@ __device__ __forceinline__ int pk_sweep(const PackedHdr& h, unsigned a_T, unsign
 
 // G groups of 1024 / G threads per block, one block per SM; each group owns one shared-memory store slot, claims its
 // own stores from a global counter and synchronises on its own named barrier, so one group's barriers and copy waits are
-// filled with the other groups' instructions. Shared memory: [0, 256) mbarriers + per-group scalars | [256, 512) header
-// | G store slots | packed table.
+// filled with the other groups' instructions. Shared memory: [0, 128) mbarriers | [128, 640) per-group scalars |
+// [640, 1024) header | G store slots | packed table.
 template <bool HAS_DIV, int G, bool EPS, int JOIN = 1>
 __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int nthr = 1024 / G;
   const int grp = threadIdx.x / nthr, tid = threadIdx.x % nthr, bid = 1 + grp;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);   // [grp]: store slot, [G]: table
-  int* s_next = reinterpret_cast<int*>(smem + 128 + 8 * grp);
-  volatile int* s_bot = reinterpret_cast<volatile int*>(smem + 128 + 8 * grp + 4);
-  PackedHdr* sh = reinterpret_cast<PackedHdr*>(smem + 256);
+  // per group 64 B of scalars: the scheduler's next store, the bot word, the records evaluated on the current store, and
+  // the group's running totals (kept here rather than in thread 0's registers: they would be live in every thread)
+  struct GroupAcc { int next; int bot; unsigned nev; int best; long long sol, nbot, unk, sweeps, ded; int maxsw; int pad; };
+  static_assert(sizeof(GroupAcc) <= 64, "group scalars");
+  GroupAcc* ga = reinterpret_cast<GroupAcc*>(smem + 128 + 64 * grp);
+  int* s_next = &ga->next;
+  volatile int* s_bot = &ga->bot;
+  unsigned* s_nev = &ga->nev;
+  PackedHdr* sh = reinterpret_cast<PackedHdr*>(smem + 640);
   static_assert(sizeof(PackedHdr) <= 256, "header does not fit its shared-memory area");
   const int sbytes = A.sbytes;
-  int2* S = reinterpret_cast<int2*>(smem + 512 + (size_t)grp * sbytes);
-  char* tb = reinterpret_cast<char*>(smem + 512 + (size_t)G * sbytes);
+  int2* S = reinterpret_cast<int2*>(smem + 1024 + (size_t)grp * sbytes);
+  char* tb = reinterpret_cast<char*>(smem + 1024 + (size_t)G * sbytes);
   const size_t store_stride = (size_t)A.nvars;
   unsigned long long* tbar = &bars[G];
   const int np = A.hdr->np;
@@ -268,17 +290,17 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   }
   if(np > 0) mbar_wait(tbar, 0);
   const unsigned a_T = smem_u32(tb), a_S = smem_u32(S);
-  const long long n_live = sh->n_live;
 
-  long long a_sol = 0, a_bot = 0, a_unk = 0, a_sweeps = 0;
-  int a_best = LPC_INF, a_maxsw = 0;
+  if(tid == 0) { ga->best = LPC_INF; ga->sol = ga->nbot = ga->unk = ga->sweeps = ga->ded = 0; ga->maxsw = 0; }
   unsigned phase = 0;
+  const unsigned a_sbot = smem_u32(const_cast<int*>(s_bot));
   while(cur >= 0) {
     if(tid == 0) {   // claim the next store of this group
       int nx = atomicAdd(&A.ctl->next_store, 1);
       if(nx >= A.n_stores) nx = -1;
       *s_next = nx;
       *s_bot = 0;
+      *s_nev = 0;
     }
     mbar_wait(&bars[grp], phase);
     phase ^= 1;
@@ -302,15 +324,17 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
     bool bot = gbar_or(bid, nthr, f0) != 0;   // also orders thread 0's s_bot / s_next writes before their readers
     const bool fin = gbar_or(bid, nthr, inf) == 0;
     int sweeps = 0;
+    unsigned nev = 0;
     bool changed = !(bot && A.stop_on_bot) && np > 0;
     while(changed) {
-      const int f = pk_sweep<HAS_DIV, JOIN>(*sh, a_T, a_S, tid, nthr, fin);
+      const int f = pk_sweep<HAS_DIV, JOIN>(*sh, a_T, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev);
       ++sweeps;
-      if(f & 2) *s_bot = 1;
-      const int any_chg = gbar_or(bid, nthr, f & 1);
+      const int any_chg = gbar_or(bid, nthr, f & 1);   // the bot word was written where the variable was emptied
       bot |= *s_bot != 0;
       changed = any_chg && !(bot && A.stop_on_bot) && !(A.max_sweeps && sweeps >= A.max_sweeps);
     }
+    nev = __reduce_add_sync(0xffffffffu, nev);
+    if((tid & 31) == 0 && nev) atomicAdd(s_nev, nev);
     int all_ent = 0;
     if(!bot) {   // entailment: the ask loop of is_extractable over the propagators that were not entailed on the root
       int ok = 1;
@@ -345,10 +369,11 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
       if(A.sweeps_out) A.sweeps_out[cur] = sweeps;
       const int olb = A.objective_var >= 0 ? S[A.objective_var].x : LPC_INF;
       if(A.obj_out) A.obj_out[cur] = olb;
-      if(bot) ++a_bot; else if(all_ent) ++a_sol; else ++a_unk;
-      if(!bot && A.objective_var >= 0) a_best = min(a_best, olb);
-      a_sweeps += sweeps;
-      a_maxsw = max(a_maxsw, sweeps);
+      if(bot) ++ga->nbot; else if(all_ent) ++ga->sol; else ++ga->unk;
+      if(!bot && A.objective_var >= 0) ga->best = min(ga->best, olb);
+      ga->sweeps += sweeps;
+      ga->ded += *s_nev;   // complete after the barrier above: every warp has added its share
+      ga->maxsw = max(ga->maxsw, sweeps);
       if(nxt >= 0) {   // the next store goes into the same slot once the write-back has read it
         bulk_wait_read0();
         mbar_expect_tx(&bars[grp], (unsigned)sbytes);
@@ -360,13 +385,13 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   }
   if(tid == 0) {
     bulk_wait0();
-    if(a_sol) atomicAdd((unsigned long long*)&A.ctl->red[0], (unsigned long long)a_sol);
-    if(a_bot) atomicAdd((unsigned long long*)&A.ctl->red[1], (unsigned long long)a_bot);
-    if(a_unk) atomicAdd((unsigned long long*)&A.ctl->red[2], (unsigned long long)a_unk);
-    atomicMin(&A.ctl->red[3], (long long)a_best);
-    atomicAdd((unsigned long long*)&A.ctl->sweeps_total, (unsigned long long)a_sweeps);
-    atomicAdd((unsigned long long*)&A.ctl->deductions, (unsigned long long)(a_sweeps * n_live));
-    atomicMax(&A.ctl->max_sweeps_seen, a_maxsw);
+    if(ga->sol) atomicAdd((unsigned long long*)&A.ctl->red[0], (unsigned long long)ga->sol);
+    if(ga->nbot) atomicAdd((unsigned long long*)&A.ctl->red[1], (unsigned long long)ga->nbot);
+    if(ga->unk) atomicAdd((unsigned long long*)&A.ctl->red[2], (unsigned long long)ga->unk);
+    atomicMin(&A.ctl->red[3], (long long)ga->best);
+    atomicAdd((unsigned long long*)&A.ctl->sweeps_total, (unsigned long long)ga->sweeps);
+    atomicAdd((unsigned long long*)&A.ctl->deductions, (unsigned long long)ga->ded);
+    atomicMax(&A.ctl->max_sweeps_seen, ga->maxsw);
     __threadfence();
   }
   // the block that finishes last publishes the all-reduce payload (BatchCtl::payload)
@@ -428,7 +453,7 @@ static int group_plan(const lpc_table* t, int nvars, int sbytes, GroupPlan* plan
   for(int c = 0; c < 3; ++c) {
     const int g = want > 0 ? want : kG[c];
     const void* k = group_kernel<EPS>(t->has_div, g);
-    const size_t need = 512 + (size_t)g * sbytes + plan->ptab_bytes;
+    const size_t need = 1024 + (size_t)g * sbytes + plan->ptab_bytes;
     if(k && need <= (size_t)optin) {
       LPC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
       int per_sm = 0;

@@ -385,20 +385,25 @@ static int ask_impl(const lpc_table* t, const lpc_store* s, int64_t* n_entailed,
   LPC_REQUIRE(s->nvars >= t->dev.nvars, "store smaller than the table's variable range");
   unsigned long long* d_cnt = nullptr;
   uint8_t* d_bits = nullptr;
-  LPC_CUDA(cudaMalloc((void**)&d_cnt, 8));
-  LPC_CUDA(cudaMemset(d_cnt, 0, 8));
-  if(host_bits && t->dev.n) LPC_CUDA(cudaMalloc((void**)&d_bits, t->dev.n));
-  if(t->dev.n) {
-    int blocks = (int)std::min<long long>(ceil_div(t->dev.n, 256), 148 * 8);
-    k_ask_all<<<blocks, 256>>>(t->dev, s->d, d_cnt, d_bits);
-    g_launches++;
-    LPC_CUDA(cudaGetLastError());
-  }
   unsigned long long c = 0;
-  LPC_CUDA(cudaMemcpy(&c, d_cnt, 8, cudaMemcpyDeviceToHost));
-  if(host_bits && t->dev.n) LPC_CUDA(cudaMemcpy(host_bits, d_bits, t->dev.n, cudaMemcpyDeviceToHost));
-  cudaFree(d_cnt);
+  auto body = [&]() -> int {
+    LPC_CUDA(cudaMalloc((void**)&d_cnt, 8));
+    LPC_CUDA(cudaMemset(d_cnt, 0, 8));
+    if(host_bits && t->dev.n) LPC_CUDA(cudaMalloc((void**)&d_bits, t->dev.n));
+    if(t->dev.n) {
+      int blocks = (int)std::min<long long>(ceil_div(t->dev.n, 256), 148 * 8);
+      k_ask_all<<<blocks, 256>>>(t->dev, s->d, d_cnt, d_bits);
+      g_launches++;
+      LPC_CUDA(cudaGetLastError());
+    }
+    LPC_CUDA(cudaMemcpy(&c, d_cnt, 8, cudaMemcpyDeviceToHost));
+    if(host_bits && t->dev.n) LPC_CUDA(cudaMemcpy(host_bits, d_bits, t->dev.n, cudaMemcpyDeviceToHost));
+    return LPC_OK;
+  };
+  const int rc = body();
+  cudaFree(d_cnt);   // the scratch goes whether or not a step failed
   cudaFree(d_bits);
+  if(rc) return rc;
   if(n_entailed) *n_entailed = (int64_t)c;
   return LPC_OK;
 }

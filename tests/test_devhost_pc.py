@@ -8,7 +8,7 @@ import pytest
 from conftest import load_golden
 from oracle import oracle as O
 from test_devhost import devhost  # noqa: F401  (fixture: builds tests/native/libdevhost.so)
-from test_gpu_pc import random_pc, random_tree_pc, to_tree
+from test_gpu_pc import booleanize, random_pc, random_tree_pc, to_tree
 
 
 def host_fixpoint(D, props, terms, store):
@@ -76,6 +76,7 @@ def test_random_tree_networks(devhost):
         a = rng.integers(-6, 12, (nvars, 2))
         store = np.stack([a.min(1), a.max(1)], axis=1).astype(np.int32)
         store[rng.random(nvars) < 0.4] = (0, 1)   # finite domains only: x > x + y walks an infinite bound one unit per sweep
+        booleanize(forms, store)
         st = compare(devhost, forms, store, f"tree {trial}")
         n_ok += not st.is_bot
     assert n_ok >= 100

@@ -206,6 +206,32 @@ def random_tree_pc(rng, nvars, n_forms=None):
     return [formula(int(rng.integers(1, 4))) for _ in range(n_forms or int(rng.integers(1, 6)))]
 
 
+def literal_vars(forms):
+    """Variables used as Boolean literals somewhere in the formulas."""
+    out = set()
+
+    def walk(f):
+        if f[0] in ("lit", "nlit"):
+            out.add(int(f[1]))
+        elif f[0] in ("and", "or", "equiv", "imply", "xor"):
+            walk(f[1])
+            walk(f[2])
+    for f in forms:
+        if isinstance(f, tuple):
+            walk(f)
+    return sorted(out)
+
+
+def booleanize(forms, store):
+    """A variable used as a literal gets a 0/1 domain. VariableLiteral reads `b does not contain 0` as true but deduces
+    b = 1 (formula.hpp:100-120): on a wider domain ask and deduce disagree ([2,2] is "true" yet meets [1,1] to nothing),
+    the propagator is not monotone and the fixpoint depends on the evaluation order - an ill-typed model, not a parity
+    case (the reference's interpreter only builds literals over Boolean variables)."""
+    for v in literal_vars(forms):
+        store[v] = (max(int(store[v, 0]), 0), min(int(store[v, 1]), 1)) if store[v, 0] <= 1 and store[v, 1] >= 0 else (0, 1)
+    return store
+
+
 def test_tree_propagators(L, O):
     """Every pc::Formula / pc::Term shape without a flat kind keeps its tree (LPC_PC_TREE) and is walked on the device:
     random formula nests, alone and mixed with flat propagators in one table (tiles + tree list in one fixpoint), plus
@@ -223,6 +249,7 @@ def test_tree_propagators(L, O):
         a = rng.integers(-6, 12, (nvars, 2))
         store = np.stack([a.min(1), a.max(1)], axis=1).astype(np.int32)
         store[rng.random(nvars) < 0.4] = (0, 1)   # finite domains only: x > x + y walks an infinite bound one unit per sweep
+        booleanize(forms, store)
         _, r, st = check_parity(L, O, forms, store, f"tree {trial}")
         n_ok += not st.is_bot
         if trial < 40:   # deduce(i) in index order == the tree walker's own steps (return value included)
