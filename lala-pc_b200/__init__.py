@@ -578,7 +578,7 @@ class Eps:
         return None if a is None else (a if isinstance(a, int) else a.ctypes.data)
 
     def solve_host(self, root, decision_vars, ids=None, first_id=0, n=None, objective_var=-1, flags=None, survivors=None,
-                   survivor_index=None, **kw):
+                   survivor_index=None, max_survivors=None, **kw):
         """One call from host buffers. `root`, `flags`, `survivors`, `survivor_index` may be numpy arrays or raw (pinned)
         addresses; returns (EpsResult, number of survivor stores written)."""
         if not isinstance(root, int):
@@ -591,7 +591,7 @@ class Eps:
         self.n = n
         max_surv = 0
         if survivors is not None:
-            max_surv = self.survivor_cap if isinstance(survivors, int) else len(survivors)
+            max_surv = (self.survivor_cap if isinstance(survivors, int) else len(survivors)) if max_survivors is None else max_survivors
         o, r, nw = _opts(**kw), EpsResult(), ctypes.c_int32(0)
         _check(_L.lpc_eps_solve_host(self._h, self._ptr(root), d.ctypes.data, d.shape[0], self._ptr(ids), first_id, n,
                                      ctypes.byref(o), objective_var, self._ptr(flags), self._ptr(survivors),

@@ -531,6 +531,9 @@ struct lpc_eps {
   GroupPlan plan;
   int rank = 0, world = 1;
   long long table_gen = 0;
+  // lpc_eps_solve_host with pinned, device-accessible output buffers: the kernel writes the surviving stores straight
+  // into the caller's host memory (zero copy), so that their trip over the link overlaps the fixpoints
+  int2* direct_surv = nullptr; int* direct_idx = nullptr; int direct_cap = 0;
 };
 
 extern "C" {
@@ -670,6 +673,7 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
     A.n_stores = e->n; A.nvars = e->nvars; A.sbytes = e->sbytes;
     A.flags = e->d_flags; A.sweeps_out = e->d_sweeps; A.obj_out = e->d_obj;
     A.surv = e->d_surv; A.surv_idx = e->d_surv_idx; A.surv_cap = e->surv_cap;
+    if(e->direct_surv) { A.surv = e->direct_surv; A.surv_idx = e->direct_idx; A.surv_cap = e->direct_cap; }
     A.ctl = e->d_ctl; A.objective_var = objective_var; A.max_sweeps = o->max_sweeps; A.stop_on_bot = o->stop_on_bot;
     void* args[] = {&A};
     LPC_CUDA(cudaLaunchKernel(group_kernel<true>(t->has_div, g), dim3(grid), dim3(1024), args, e->plan.smem, st));
@@ -719,17 +723,40 @@ int lpc_eps_download(lpc_eps* e, uint8_t* flags, int32_t* survivors_lbub, int32_
   return LPC_OK;
 }
 
+// The device address of a host buffer the GPU can write directly (pinned and mapped), or null.
+static void* device_view_of_pinned(const void* p) {
+  if(!p) return nullptr;
+  cudaPointerAttributes at;
+  if(cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if(at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return at.devicePointer;
+}
+
 int lpc_eps_solve_host(lpc_eps* e, const int32_t* root_lbub, const int32_t* decision_vars, int32_t n_decisions,
                        const int64_t* ids, int64_t first_id, int32_t n, const lpc_fixpoint_opts* o, int32_t objective_var,
                        uint8_t* flags, int32_t* survivors_lbub, int32_t* survivor_index, int32_t max_survivors,
                        int32_t* n_written, lpc_eps_result* r) {
+  LPC_REQUIRE(max_survivors >= 0, "bad max_survivors");
   cudaStream_t st = o ? (cudaStream_t)o->stream : nullptr;
   int rc = eps_upload(e, root_lbub, decision_vars, n_decisions, ids, first_id, n, st);
   if(rc) return rc;
-  if((rc = lpc_eps_run_async(e, o, objective_var))) return rc;
+  // Pinned output buffers: the kernel stores the survivors into them directly (one bulk store each, over the link while
+  // the other stores are still being propagated) instead of compacting them in device memory for a copy afterwards.
+  const char* ez = getenv("LPC_EPS_ZEROCOPY");
+  void* dv_surv = (!ez || atoi(ez)) ? device_view_of_pinned(survivors_lbub) : nullptr;
+  void* dv_idx = dv_surv ? device_view_of_pinned(survivor_index) : nullptr;
+  const bool direct = dv_surv && dv_idx && max_survivors > 0;
+  if(direct) { e->direct_surv = (int2*)dv_surv; e->direct_idx = (int*)dv_idx; e->direct_cap = max_survivors; }
+  rc = lpc_eps_run_async(e, o, objective_var);
+  e->direct_surv = nullptr; e->direct_idx = nullptr; e->direct_cap = 0;
+  if(rc) return rc;
   // the flags do not depend on the survivor count: queue their copy behind the kernel, before the first synchronisation
   if(flags && n) LPC_CUDA(cudaMemcpyAsync(flags, e->d_flags, n, cudaMemcpyDeviceToHost, st));
   if((rc = lpc_eps_collect(e, r))) return rc;
+  if(direct) {
+    if(n_written) *n_written = std::min(e->h_ctl->n_surv, max_survivors);
+    return LPC_OK;
+  }
   return lpc_eps_download(e, nullptr, survivors_lbub, survivor_index, max_survivors, n_written);
 }
 

@@ -256,3 +256,33 @@ def test_batch_payload_matches_the_record(L, O, W):
             assert p[:3] == [res.n_solution, res.n_bot, res.n_unknown], (n, handle)
             assert p[3:] == [0, 0, res.best_bound, 0], (n, handle)
             h.close()
+
+
+def test_eps_zero_copy_outputs(L, O, W):
+    """Pinned (device-accessible) survivor buffers are written by the kernel itself, over the link while the other
+    subproblems are still being propagated; the result is what the staged path (pageable buffers) delivers."""
+    import torch
+    net = W.config4_base()
+    root, _ = O.pir_fixpoint(net.store, net.records)
+    dec, obj = W.eps_decisions(net.records, root, n=13)
+    n = 8192
+    want, wflags = oracle_eps(O, W, net.records, root, dec, np.arange(n, dtype=np.int64))
+    ok = (wflags & 1) == 0
+    t = L.Table(net.records, net.nvars)
+    e = L.Eps(t, n, survivor_cap=n)
+    cap = int(ok.sum()) + 7
+    surv = torch.zeros((cap, net.nvars, 2), dtype=torch.int32).pin_memory()
+    idx = torch.full((cap,), -1, dtype=torch.int32).pin_memory()
+    flags = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    for rep in range(2):
+        surv.zero_()
+        idx.fill_(-1)
+        res, nw = e.solve_host(root, dec, first_id=0, n=n, objective_var=obj, flags=flags.data_ptr(), survivors=surv.data_ptr(),
+                               survivor_index=idx.data_ptr(), max_survivors=cap)
+        assert np.array_equal(flags.numpy(), wflags)
+        assert nw == res.n_survivors == int(ok.sum())
+        got_idx = idx.numpy()[:nw]
+        assert sorted(got_idx.tolist()) == np.flatnonzero(ok).tolist()
+        assert np.array_equal(surv.numpy()[:nw], want[got_idx])
+        assert (idx.numpy()[nw:] == -1).all()
+    e.close()
