@@ -18,7 +18,8 @@ M = {"duration_ns": "gpu__time_duration.sum", "dram_read": "dram__bytes_read.sum
      "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts_bytes": "lts__t_bytes.sum",
      "l1_hit_pct": "l1tex__t_sector_hit_rate.pct", "lts_hit_pct": "lts__t_sector_hit_rate.pct",
      "registers": "launch__registers_per_thread", "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active"}
-SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1, "usecond": 1e3, "msecond": 1e6, "second": 1e9}
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1, "usecond": 1e3, "msecond": 1e6, "second": 1e9,
+         "ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}
 
 
 def num(s):
