@@ -187,6 +187,21 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
         import torch.distributed as dist
     eps = L.Eps(table, n, survivor_cap=SURVIVOR_CAP)
     eps.set_rank(rank, world)
+    # The record exchange: fused into the batch kernel over NVLink peer memory when the GPUs can reach each other (CUDA IPC
+    # handles gathered once through torch.distributed), else one NCCL all-reduce per step. LPC_P2P=0 forces NCCL.
+    p2p = False
+    if dist is not None and os.environ.get("LPC_P2P", "1") != "0":
+        handles = [None] * world
+        dist.all_gather_object(handles, eps.peer_export())
+        try:
+            eps.peer_connect(rank, world, handles)
+            ok = 1
+        except L.LpcError:
+            ok = 0
+        agree = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        p2p = bool(int(agree[0]))
+        assert p2p or not ok, "peer access on some ranks only"
     payload = torch.as_tensor(_DevView(*eps.payload), device="cuda")
     flush = ctx_flush()
     eps.upload(root, dec, ids=ids)
@@ -204,8 +219,9 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
                 l0 = L.launch_count()
             if i >= k_warm:
                 ev[i - k_warm][0].record()
-            eps.run_async(objective_var=obj, mode=mode)
-            sharding.allreduce_payload(payload, dist)
+            eps.run_async(objective_var=obj, mode=mode)     # with peers connected the exchange is part of the call
+            if not p2p:
+                sharding.allreduce_payload(payload, dist)
             if i >= k_warm:
                 ev[i - k_warm][1].record()
             res = eps.collect()
@@ -235,7 +251,11 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
                                 "l2": "flushed between steps (512 MiB write); the kernel's inputs are the 16 KB root store, the "
                                       "subproblem ids and the 80 KB table",
                                 "sharding": "consecutive ids" if world == 1 else "each rank a uniform sample of the id space (sharding.py)",
-                                "collective": "one NCCL all-reduce (SUM) of the %d x int64 payload per step" % (3 + world) if world > 1 else "none",
+                                "collective": "none" if world == 1 else
+                                              ("fused into the batch kernel: its last block writes the rank's 32-byte record into every "
+                                               "peer's inbox over NVLink (CUDA IPC peer memory), a one-thread kernel folds the inbox; no "
+                                               "collective library call per step" if p2p else
+                                               "one NCCL all-reduce (SUM) of the %d x int64 payload per step" % (3 + world)),
                                 "seed": net.meta["seed"]}})
     # ---- run-time checks (outside the timed region) -----------------------------------------------------------------------
     if check:
@@ -283,7 +303,7 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
             t0 = time.perf_counter()
             r, nw = eps.solve_host(root_p.data_ptr(), dec, ids=ids_p.data_ptr(), n=n, objective_var=obj, flags=flags_p.data_ptr(),
                                    survivors=surv_p.data_ptr(), survivor_index=sidx_p.data_ptr(), mode=mode)
-            if dist is not None:
+            if dist is not None and not p2p:
                 sharding.allreduce_payload(payload, dist)
                 torch.cuda.synchronize()
             t1 = time.perf_counter()
@@ -314,6 +334,9 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
                              "auto_live_propagators": int(res_a.n_live_records), "propagators": len(net.records),
                              "auto_value": float(res_a.deductions) * world / (float(ta[0]) * 1e-3), "auto_e2e_value": v_ae,
                              "what": "LPC_MODE_AUTO: same flags, stores and record (tests/test_gpu_eps.py), fewer deductions"}
+    if p2p:   # nobody may still have an inbox mapped when its owner frees it
+        eps.peer_disconnect()
+        dist.barrier()
     eps.close()
     return out
 

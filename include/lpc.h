@@ -267,6 +267,19 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
 int lpc_eps_collect(lpc_eps* e, lpc_eps_result* r);
 int lpc_eps_download(lpc_eps* e, uint8_t* flags, int32_t* survivors_lbub, int32_t* survivor_index, int32_t max_survivors,
                      int32_t* n_written);
+/* Multi-GPU, one process per GPU of one node: the exchange of the reduction record fused into the batch kernel. Every rank
+ * exports the CUDA IPC handle of its inbox (LPC_PEER_HANDLE_BYTES bytes), the handles are gathered by whatever plumbing the
+ * processes share (torch.distributed in bench.py) and connected; from then on the kernel that finishes a rank's batch
+ * writes the rank's record into every peer's inbox over NVLink, and every lpc_eps_run_async / lpc_eps_solve_host queues a
+ * one-thread kernel behind it that waits for the peers' records and leaves the payload of lpc_eps_payload_device_ptr as an
+ * all-reduce would - without a collective library call per step. Every rank must make the same sequence of calls (a call
+ * only returns its payload once every peer has made it too). lpc_eps_peer_connect fails with LPC_ERR_CUDA when two devices
+ * have no peer access; the caller then keeps its all-reduce. */
+#define LPC_PEER_HANDLE_BYTES 64
+int lpc_eps_peer_export(lpc_eps* e, void* handle_out);
+int lpc_eps_peer_connect(lpc_eps* e, int32_t rank, int32_t world, const void* handles);
+/* Unmap the peers' inboxes (before the ranks destroy their handles: synchronise the ranks between the two). */
+int lpc_eps_peer_disconnect(lpc_eps* e);
 /* Sweeps each subproblem took (n ints), informational. */
 int lpc_eps_sweeps(lpc_eps* e, int32_t* out);
 

@@ -156,6 +156,9 @@ SIGNATURES = {
     "lpc_eps_collect": (ctypes.c_int, [_vp, ctypes.POINTER(EpsResult)]),
     "lpc_eps_download": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _pi32]),
     "lpc_eps_sweeps": (ctypes.c_int, [_vp, _vp]),
+    "lpc_eps_peer_export": (ctypes.c_int, [_vp, _vp]),
+    "lpc_eps_peer_connect": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
+    "lpc_eps_peer_disconnect": (ctypes.c_int, [_vp]),
     "lpc_search_default_opts": (None, [ctypes.POINTER(SearchOpts)]),
     "lpc_batch_search": (ctypes.c_int, [_vp, _vp, _i32, ctypes.POINTER(SearchOpts), ctypes.POINTER(SearchResult), _vp]),
     # include/lpc_pc.h
@@ -634,6 +637,23 @@ class Eps:
         out = np.empty(max(self.n, 1), dtype=np.int32)
         _check(_L.lpc_eps_sweeps(self._h, out.ctypes.data))
         return out[:self.n]
+
+    def peer_disconnect(self):
+        _check(_L.lpc_eps_peer_disconnect(self._h))
+
+    # -- record exchange over peer memory (include/lpc.h: lpc_eps_peer_*) --
+    PEER_HANDLE_BYTES = 64
+
+    def peer_export(self):
+        buf = ctypes.create_string_buffer(self.PEER_HANDLE_BYTES)
+        _check(_L.lpc_eps_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, rank, world, handles):
+        """`handles`: the ranks' exported handles in rank order (list of bytes)."""
+        blob = b"".join(handles)
+        assert len(blob) == world * self.PEER_HANDLE_BYTES
+        _check(_L.lpc_eps_peer_connect(self._h, rank, world, blob))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -91,6 +91,42 @@ __global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, co
   }
 }
 
+// ---- the exchange of the reduction record between the GPUs of one node, fused into the batch kernel ------------------------
+// Every rank owns an inbox of 2 x LPC_MAX_RANKS slots in its device memory, opened by every peer through CUDA IPC
+// (lpc_eps_peer_export / _connect). The block that finishes a rank's batch last writes the rank's record into slot
+// [epoch & 1][my rank] of EVERY inbox (its own included) - 40 bytes per peer over NVLink, straight from the kernel -, then
+// releases the slot's epoch word at system scope. k_eps_fold, a one-thread kernel queued behind the batch kernel, acquires
+// the epoch words of its own inbox and folds the records into the payload. No collective library call on the path. Two
+// slot sets alternate: a rank can run at most one step ahead of a peer (its fold of step k needs every peer's record of
+// step k), so the records of step k + 1 never land on records of step k that are still unread.
+struct PeerSlot { long long rec[4]; long long epoch; long long pad[3]; };
+static_assert(sizeof(PeerSlot) == 64, "one slot per 64-byte line");
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// payload[0..2] = sum of the ranks' counters, payload[3 + r] = rank r's best bound: the layout the all-reduce produces.
+// A peer that never arrives (2^28 polls, a few seconds) leaves payload[0] = -1 instead of hanging the GPU.
+__global__ void k_eps_fold(const PeerSlot* inbox, int world, long long epoch, BatchCtl* ctl) {
+  long long sum[3] = {0, 0, 0};
+  bool ok = true;
+  for(int r = 0; r < world && ok; ++r) {
+    const PeerSlot* s = inbox + (epoch & 1) * LPC_MAX_RANKS + r;
+    long long polls = 0;
+    while(ld_acquire_sys(&s->epoch) != epoch) { if(++polls > (1ll << 28)) { ok = false; break; } }
+    if(!ok) break;
+    for(int i = 0; i < 3; ++i) sum[i] += s->rec[i];
+    ctl->payload[3 + r] = s->rec[3];
+  }
+  for(int i = 0; i < 3; ++i) ctl->payload[i] = ok ? sum[i] : -1;
+}
+
 // ---- the grouped kernel ---------------------------------------------------------------------------------------------
 struct GroupArgs {
   const uint2* ptab; const PackedHdr* hdr;
@@ -104,6 +140,9 @@ struct GroupArgs {
   int2* surv; int* surv_idx; int surv_cap;   // EPS: compacted non-failed stores and their subproblem index k
   BatchCtl* ctl;
   int objective_var, max_sweeps, stop_on_bot;
+  PeerSlot* const* peers;          // multi-GPU: the inboxes of all ranks (device array of `world` pointers), or null
+  int my_rank, world;
+  long long epoch;
 };
 
 __device__ __forceinline__ uint4 lds_v4(unsigned addr) {
@@ -401,8 +440,18 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
     if(done == (int)gridDim.x - 1) {
       __threadfence();
       unsigned long long* red = reinterpret_cast<unsigned long long*>(A.ctl->red);   // read where the atomics landed (L2)
-      for(int i = 0; i < 3; ++i) A.ctl->payload[i] = (long long)atomicAdd(&red[i], 0ull);
-      A.ctl->payload[3 + A.ctl->rank] = (long long)atomicAdd(&red[3], 0ull);
+      long long rec[4];
+      for(int i = 0; i < 4; ++i) rec[i] = (long long)atomicAdd(&red[i], 0ull);
+      for(int i = 0; i < 3; ++i) A.ctl->payload[i] = rec[i];
+      A.ctl->payload[3 + A.ctl->rank] = rec[3];
+      if(A.peers) {   // the record goes into every rank's inbox (PeerSlot above)
+        for(int r = 0; r < A.world; ++r) {
+          PeerSlot* dst = A.peers[r] + (A.epoch & 1) * LPC_MAX_RANKS + A.my_rank;
+          for(int i = 0; i < 4; ++i) dst->rec[i] = rec[i];
+        }
+        __threadfence_system();
+        for(int r = 0; r < A.world; ++r) st_release_sys(&(A.peers[r] + (A.epoch & 1) * LPC_MAX_RANKS + A.my_rank)->epoch, A.epoch);
+      }
     }
   }
 }
@@ -534,6 +583,12 @@ struct lpc_eps {
   // lpc_eps_solve_host with pinned, device-accessible output buffers: the kernel writes the surviving stores straight
   // into the caller's host memory (zero copy), so that their trip over the link overlaps the fixpoints
   int2* direct_surv = nullptr; int* direct_idx = nullptr; int direct_cap = 0;
+  // record exchange over peer memory (PeerSlot): this rank's inbox, the peers' inboxes as mapped here, the step counter
+  PeerSlot* d_inbox = nullptr;
+  PeerSlot** d_peer_ptrs = nullptr;
+  void* peer_mapped[LPC_MAX_RANKS] = {nullptr};
+  bool peers_ok = false;
+  long long epoch = 0;
 };
 
 extern "C" {
@@ -542,6 +597,8 @@ int lpc_eps_destroy(lpc_eps* e) {
   if(!e) return LPC_OK;
   cudaFree(e->d_root); cudaFree(e->d_dvars); cudaFree(e->d_ids); cudaFree(e->d_flags); cudaFree(e->d_sweeps); cudaFree(e->d_obj);
   cudaFree(e->d_surv); cudaFree(e->d_surv_idx); cudaFree(e->d_ctl); cudaFree(e->d_ptab); cudaFree(e->d_phdr);
+  for(int r = 0; r < LPC_MAX_RANKS; ++r) if(e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
+  cudaFree(e->d_inbox); cudaFree(e->d_peer_ptrs);
   if(e->h_ctl) cudaFreeHost(e->h_ctl);
   if(e->h_init) cudaFreeHost(e->h_init);
   if(e->h_phdr) cudaFreeHost(e->h_phdr);
@@ -675,11 +732,18 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
     A.surv = e->d_surv; A.surv_idx = e->d_surv_idx; A.surv_cap = e->surv_cap;
     if(e->direct_surv) { A.surv = e->direct_surv; A.surv_idx = e->direct_idx; A.surv_cap = e->direct_cap; }
     A.ctl = e->d_ctl; A.objective_var = objective_var; A.max_sweeps = o->max_sweeps; A.stop_on_bot = o->stop_on_bot;
+    ++e->epoch;
+    if(e->peers_ok) { A.peers = e->d_peer_ptrs; A.my_rank = e->rank; A.world = e->world; A.epoch = e->epoch; }
     void* args[] = {&A};
     LPC_CUDA(cudaLaunchKernel(group_kernel<true>(t->has_div, g), dim3(grid), dim3(1024), args, e->plan.smem, st));
     g_launches++;
   }
   LPC_CUDA(cudaEventRecord(e->ev1, st));
+  if(e->peers_ok && e->n > 0) {   // wait for the peers' records and fold them into the payload (PeerSlot)
+    k_eps_fold<<<1, 1, 0, st>>>(e->d_inbox, e->world, e->epoch, e->d_ctl);
+    g_launches++;
+    LPC_CUDA(cudaGetLastError());
+  }
   LPC_CUDA(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
   LPC_CUDA(cudaMemcpyAsync(e->h_phdr, e->d_phdr, sizeof(PackedHdr), cudaMemcpyDeviceToHost, st));
   e->last_stream = st;
@@ -758,6 +822,59 @@ int lpc_eps_solve_host(lpc_eps* e, const int32_t* root_lbub, const int32_t* deci
     return LPC_OK;
   }
   return lpc_eps_download(e, nullptr, survivors_lbub, survivor_index, max_survivors, n_written);
+}
+
+int lpc_eps_peer_export(lpc_eps* e, void* handle_out) {
+  LPC_REQUIRE(e && handle_out, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= LPC_PEER_HANDLE_BYTES, "IPC handle size");
+  int rc = eps_check_device(e);
+  if(rc) return rc;
+  if(!e->d_inbox) {
+    LPC_CUDA(cudaMalloc((void**)&e->d_inbox, 2 * LPC_MAX_RANKS * sizeof(PeerSlot)));
+    LPC_CUDA(cudaMemset(e->d_inbox, 0, 2 * LPC_MAX_RANKS * sizeof(PeerSlot)));
+    LPC_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  LPC_CUDA(cudaIpcGetMemHandle(&h, e->d_inbox));
+  memset(handle_out, 0, LPC_PEER_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof(h));
+  return LPC_OK;
+}
+
+int lpc_eps_peer_connect(lpc_eps* e, int32_t rank, int32_t world, const void* handles) {
+  LPC_REQUIRE(e && handles, "null argument");
+  LPC_REQUIRE(world >= 1 && world <= LPC_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
+  LPC_REQUIRE(e->d_inbox != nullptr, "call lpc_eps_peer_export first");
+  LPC_REQUIRE(!e->pending, "a call is still in flight on this handle");
+  int rc = eps_check_device(e);
+  if(rc) return rc;
+  PeerSlot* ptrs[LPC_MAX_RANKS];
+  for(int r = 0; r < world; ++r) {
+    if(r == rank) { ptrs[r] = e->d_inbox; continue; }
+    if(e->peer_mapped[r]) { cudaIpcCloseMemHandle(e->peer_mapped[r]); e->peer_mapped[r] = nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * LPC_PEER_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if(err != cudaSuccess) {   // no peer access between the two devices: the caller keeps its all-reduce
+      e->peers_ok = false;
+      return cuda_fail(err, "cudaIpcOpenMemHandle", __FILE__, __LINE__);
+    }
+    e->peer_mapped[r] = p;
+    ptrs[r] = (PeerSlot*)p;
+  }
+  if(!e->d_peer_ptrs) LPC_CUDA(cudaMalloc((void**)&e->d_peer_ptrs, LPC_MAX_RANKS * sizeof(PeerSlot*)));
+  LPC_CUDA(cudaMemcpy(e->d_peer_ptrs, ptrs, world * sizeof(PeerSlot*), cudaMemcpyHostToDevice));
+  e->rank = rank; e->world = world;
+  e->peers_ok = true;
+  return LPC_OK;
+}
+
+int lpc_eps_peer_disconnect(lpc_eps* e) {
+  LPC_REQUIRE(e != nullptr && !e->pending, "null handle or a call in flight");
+  for(int r = 0; r < LPC_MAX_RANKS; ++r) if(e->peer_mapped[r]) { cudaIpcCloseMemHandle(e->peer_mapped[r]); e->peer_mapped[r] = nullptr; }
+  e->peers_ok = false;
+  return LPC_OK;
 }
 
 int lpc_eps_sweeps(lpc_eps* e, int32_t* out) {

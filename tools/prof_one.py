@@ -47,9 +47,10 @@ def main():
         net = W.config2() if what.startswith("c2") else W.config1()
         table = L.Table(net.records, net.nvars)
         mode = L.MODE_AUTO if what.endswith("auto") else L.MODE_SWEEP
+        ms = 1 if what.endswith("first") else 0      # c2_first: the first sweep alone
         for _ in range(warm + 1):
             s = L.Store(values=net.store)
-            r = L.fixpoint(table, s, mode=mode)
+            r = L.fixpoint(table, s, mode=mode, max_sweeps=ms)
         rec.update(r.as_dict())
     else:
         net = W.config3() if what == "pc_c3" else W.config5()
