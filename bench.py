@@ -7,7 +7,8 @@ One "step" = one pass of the hot path over one batch of synthetic input. The lin
 the same workload at EVERY N, so that v_N / (N * v_1) means something) is BASELINE.json configs[3], the one configuration
 the metric quotes at 1/2/4/8 GPUs: batched EPS, 65,536 subproblem stores of the 2k-variable / 10k-propagator PIR model
 PER GPU (weak scaling; each rank a uniform sample of the subproblem ids), one thread group per store, no inter-GPU
-traffic inside the fixpoints and ONE NCCL all-reduce (3 + N int64) per step. Next to it, in the same line:
+traffic inside the fixpoints; the ranks' reduction records (32 B each) are exchanged by the kernel itself over NVLink
+peer memory (fallback: ONE NCCL all-reduce of 3 + N int64) per step. Next to it, in the same line:
   strong            the 65,536 subproblems of configs[3] in total, 65,536 / N per rank
   single_fixpoint   (N = 1) BASELINE.json configs[1]: one fixpoint of the 1M-variable / 5M-propagator network - dense
                     sweeps with their HBM roofline fraction, time to fixpoint of the change-driven mode with
@@ -511,23 +512,32 @@ def own_pc(args, cpu=True):
         prev = net
         t = L.PcTable(net.props, net.terms, net.nvars)
         cells = L.nbit_from_intervals(net.store) if bitset else None
-        ms, res = [], None
         n_steps = max(3, min(args.steps, 10))
-        for i in range(3 + n_steps):
-            s = L.Store(values=net.store)
-            if bitset:
-                s.write_bits(cells)
-            flush.zero_()
-            torch.cuda.synchronize()
-            res = t.fixpoint(s, bitset=bitset)
-            if i >= 3:
-                ms.append(res.device_ms)
+        runs = {}
+        for mode in (L.MODE_SWEEP, L.MODE_AUTO):
+            ms, res = [], None
+            for i in range(3 + n_steps):
+                s = L.Store(values=net.store)
+                if bitset:
+                    s.write_bits(cells)
+                flush.zero_()
+                torch.cuda.synchronize()
+                res = t.fixpoint(s, bitset=bitset, mode=mode)
+                if i >= 3:
+                    ms.append(res.device_ms)
+            runs[mode] = (float(np.mean(ms)), res, s.read())
         P, T = len(net.props), len(net.terms)
         bytes_per_sweep = 16 * P + 16 * T + (8 * int((net.props[:, 0] == 2).sum()))
-        m = float(np.mean(ms))
+        m, res, final = runs[L.MODE_SWEEP]
+        ma, resa, finala = runs[L.MODE_AUTO]
+        assert np.array_equal(final, finala), "PC: the two modes disagree"
         achieved = bytes_per_sweep * res.sweeps / (m * 1e-3) / 1e9
         e = {"ms_per_fixpoint": m, "sweeps": int(res.sweeps), "propagators": P, "terms": T, "vars": net.nvars,
              "value": res.deductions / (m * 1e-3), "unit": UNIT,
+             "time_to_fixpoint": {"dense_ms": m, "auto_ms": ma, "dense_deductions": int(res.deductions),
+                                  "auto_deductions": int(resa.deductions),
+                                  "what": "LPC_MODE_AUTO skips the lane tiles whose operands have not moved since their "
+                                          "last evaluation: same store", "auto_sweeps": int(resa.sweeps)},
              "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                           "kernel": "k_pc_fixpoint<%s>" % ("true" if bitset else "false"),
                           "algorithmic_bytes_per_launch": bytes_per_sweep * res.sweeps}}

@@ -48,7 +48,7 @@ enum lpc_pc_kind {
    *   formulas  20 v = VariableLiteral | 21 v = its negation | 22 l r = (l <= r) | 23 l r = (l > r) | 24 l r = (l = r)
    *             | 25 l r = (l != r) | 26 f g = and | 27 f g = or | 28 f g = equiv | 29 f g = imply | 30 f g = xor
    * Walked on the device by one thread per propagator exactly as Formula::deduce / Term::embed walk it
-   * (lala-pc_b200/csrc/pc_tree.cuh); terms up to 5 levels and connectives up to 4 levels deep, deeper streams are
+   * (lala-pc_b200/csrc/pc_tree.cuh); terms up to 8 levels and connectives up to 6 levels deep, deeper streams are
    * refused with LPC_ERR_UNSUPPORTED. Interval stores only. */
   LPC_PC_TREE = 11
 };

@@ -457,6 +457,7 @@ int lpc_store_destroy(lpc_store* s) {
   if(!s) return LPC_OK;
   if(s->owning) cudaFree(s->d);
   cudaFree(s->d_dirty);
+  cudaFree(s->d_pc_seen);
   cudaFree(s->d_ctl);
   if(s->h_ctl) cudaFreeHost(s->h_ctl);
   if(s->ev0) cudaEventDestroy(s->ev0);

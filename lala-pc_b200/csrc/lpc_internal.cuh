@@ -119,4 +119,6 @@ struct lpc_store {
   bool pending = false;
   // group byte maps of the change-driven kernel (pir_dirty.cu)
   unsigned char* d_dirty = nullptr; long long dirty_cap = 0;
+  // the operand cells each lane tile of the PC kernel saw at its last evaluation (pc_fixpoint.cu, LPC_MODE_AUTO)
+  int2* d_pc_seen = nullptr; long long pc_seen_cap = 0;
 };

@@ -254,9 +254,37 @@ __device__ __forceinline__ int tile_step(const PcTableDev& t, Acc& acc, int2* st
   }
 }
 
+// One tile of one sweep under LPC_MODE_AUTO: skipped when `was` (what its lanes loaded at its last evaluation) equals what
+// they load now (see the kernel).
+template <bool BITS, class Acc>
+__device__ __forceinline__ int tile_visit(const PcTableDev& t, Acc& acc, int2* store, long long tile, int lane, const int4 L,
+                                          const int2 raw, int2* seen, bool have_was, const int2 was, unsigned& nprops) {
+  if(seen != nullptr) {
+    if(have_was && __all_sync(0xffffffffu, was.x == raw.x && was.y == raw.y)) return 0;
+    __stcg(seen + tile * 32 + lane, raw);
+    const int meta = L.z;
+    nprops += __popc(__ballot_sync(0xffffffffu, PC_META_KIND(meta) != 0 && (meta & 31) == lane));
+  }
+  return tile_step<BITS>(t, acc, store, tile, lane, L, raw);
+}
+
+// The schedule (lpc_fixpoint_opts.mode), never the result:
+//  * LPC_MODE_SWEEP (`seen` == nullptr): every sweep evaluates every tile.
+//  * LPC_MODE_AUTO: `seen` holds the cells each lane of a tile loaded at the tile's last evaluation. A tile whose 32 cells
+//    are what they were then is skipped, and exactly so: its evaluation is a function of those cells (cells only shrink,
+//    so whatever it re-read in between had the same value), its result has been joined into the store already, and had it
+//    moved one of its own cells that cell would differ now. A sweep that skips every tile moves nothing and ends the loop,
+//    as in the dense schedule, on a store every propagator has been evaluated on: the same greatest common fixpoint. A
+//    skipped tile costs two coalesced loads, a gather and a vote instead of ~300 instructions (config 3: 0.37 of the dense
+//    schedule's propagator evaluations, 73 against 91 us; a sweep of tiles at rest still costs 8 us of L2 traffic).
+//    Propagators outside the tiles (more than 32 lanes, trees) run every sweep.
+//    Tried on top and dropped: flag bytes per tile, set through a var -> tiles index by whoever tightens a variable, so
+//    that a sweep of tiles at rest reads one byte per tile. The late sweeps fall to 2-6 us, but walking the index inside
+//    the divergent join costs more than it saves while many variables still move (first sweep of config 3: 42 against
+//    32 us; of config 5, 13 tiles per variable: 174 against 35 us): tools/pc_sweep_probe.py, profiles/r02_pc_skip.txt.
 template <bool BITS, int PC_UNROLL, int PC_MIN_BLOCKS>
 __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDev t, int2* store, FixCtl* ctl, int max_sweeps,
-                                                        int stop_on_bot) {
+                                                        int stop_on_bot, int2* seen) {
   typedef typename PcAcc<BITS>::type Acc;
   __shared__ unsigned long long s_vote;
   const int tid = threadIdx.x;
@@ -274,9 +302,11 @@ __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDe
   int sweeps = 0;
   bool any_changed = false;
   bool done = (bot && stop_on_bot) || t.n == 0;
+  unsigned nprops = 0;   // propagators this warp evaluated (lane-uniform)
   while(!done) {
     Acc acc = make_acc(store, (Acc*)nullptr);
     int f = 0;
+    const bool hw = seen != nullptr && sweeps > 0;
     if constexpr(PC_UNROLL == 0) {
       // two-stage software pipeline: while tile i is evaluated, the domains of tile i + 1 and the records of tile i + 2
       // are in flight, so a warp waits for memory once per sweep instead of twice per tile
@@ -288,7 +318,8 @@ __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDe
       while(cur < t.n_tiles) {
         const int4 L2 = cur + 2 * gwarps < t.n_tiles ? __ldg(&t.tiles[(cur + 2 * gwarps) * 32 + lane]) : Z;
         const int2 r1 = PC_META_KIND(L1.z) ? __ldcg(&store[L1.y]) : make_int2(0, 0);
-        f |= tile_step<BITS>(t, acc, store, cur, lane, L0, r0);
+        const int2 was = hw ? __ldcg(seen + cur * 32 + lane) : make_int2(0, 0);
+        f |= tile_visit<BITS>(t, acc, store, cur, lane, L0, r0, seen, hw, was, nprops);
         L0 = L1; L1 = L2; r0 = r1;
         cur += gwarps;
       }
@@ -296,14 +327,17 @@ __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDe
     else
     for(long long base = gwarp * PC_UNROLL; base < t.n_tiles; base += gwarps * PC_UNROLL) {
       int4 L[PC_UNROLL ? PC_UNROLL : 1];
-      int2 raw[PC_UNROLL ? PC_UNROLL : 1];
+      int2 raw[PC_UNROLL ? PC_UNROLL : 1], was[PC_UNROLL ? PC_UNROLL : 1];
 #pragma unroll
-      for(int u = 0; u < PC_UNROLL; ++u)
+      for(int u = 0; u < PC_UNROLL; ++u) {
         L[u] = base + u < t.n_tiles ? __ldg(&t.tiles[(base + u) * 32 + lane]) : make_int4(0, 0, 0, 0);
+        was[u] = hw && base + u < t.n_tiles ? __ldcg(seen + (base + u) * 32 + lane) : make_int2(0, 0);
+      }
 #pragma unroll
       for(int u = 0; u < PC_UNROLL; ++u) raw[u] = PC_META_KIND(L[u].z) ? __ldcg(&store[L[u].y]) : make_int2(0, 0);
 #pragma unroll
-      for(int u = 0; u < PC_UNROLL; ++u) f |= tile_step<BITS>(t, acc, store, base + u, lane, L[u], raw[u]);
+      for(int u = 0; u < PC_UNROLL; ++u)
+        if(base + u < t.n_tiles) f |= tile_visit<BITS>(t, acc, store, base + u, lane, L[u], raw[u], seen, hw, was[u], nprops);
     }
     for(long long b = gtid; b < t.n_big; b += gthreads) {
       const int4 h = t.hdr[t.big[b]];
@@ -322,7 +356,12 @@ __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDe
     ctl->dense_sweeps = sweeps;
     ctl->has_changed = any_changed;
     ctl->is_bot = bot;
-    ctl->deductions = (unsigned long long)sweeps * (unsigned long long)t.n;
+  }
+  // deductions: every propagator every sweep (dense), or the propagators of the tiles actually evaluated + the untiled ones
+  if(seen == nullptr) { if(blockIdx.x == 0 && tid == 0) ctl->deductions = (unsigned long long)sweeps * (unsigned long long)t.n; }
+  else {
+    if(lane == 0 && nprops) atomicAdd(&ctl->deductions, (unsigned long long)nprops);
+    if(blockIdx.x == 0 && tid == 0) atomicAdd(&ctl->deductions, (unsigned long long)sweeps * (unsigned long long)t.n_big);
   }
 }
 
@@ -502,13 +541,24 @@ static int pc_fixpoint_async(const lpc_pc_table* t, lpc_store* s, const lpc_fixp
   int grid = t->sm_count * t->blocks_per_sm[bits];
   long long want = std::max<long long>(1, std::max<long long>((t->dev.n_tiles * 32 + PC_TPB - 1) / PC_TPB, (t->dev.n_big + PC_TPB - 1) / PC_TPB));
   if(want < grid) grid = (int)want;
+  int2* seen = nullptr;
+  if(o->mode != LPC_MODE_SWEEP && t->dev.n_tiles > 0) {   // per tile: the 32 cells last seen
+    const long long cells = t->dev.n_tiles * 32;
+    if(s->pc_seen_cap < cells) {
+      cudaFree(s->d_pc_seen);
+      s->d_pc_seen = nullptr; s->pc_seen_cap = 0;
+      LPC_CUDA(cudaMalloc((void**)&s->d_pc_seen, (size_t)cells * sizeof(int2)));
+      s->pc_seen_cap = cells;
+    }
+    seen = s->d_pc_seen;
+  }
   LPC_CUDA(cudaEventRecord(s->ev0, st));
   LPC_CUDA(cudaMemsetAsync(s->d_ctl, 0, sizeof(FixCtl), st));
   PcTableDev td = t->dev;
   int2* store = s->d;
   FixCtl* ctl = s->d_ctl;
   int max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
-  void* args[] = {&td, &store, &ctl, &max_sweeps, &stop};
+  void* args[] = {&td, &store, &ctl, &max_sweeps, &stop, &seen};
   LPC_CUDA(cudaLaunchCooperativeKernel(pc_kernel(bits, t->variant), dim3(grid), dim3(PC_TPB), args, 0, st));
   g_launches++;
   LPC_CUDA(cudaEventRecord(s->ev1, st));

@@ -35,8 +35,8 @@ enum PcTok : int { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SU
 // F_AE op var k: AbstractElement over the store, `var op k` with op = 0 <=, 1 >=, 2 =, 3 != (formula.hpp:14-77)
 enum PcAeOp : int { AE_LEQ = 0, AE_GEQ = 1, AE_EQ = 2, AE_NEQ = 3 };
 
-constexpr int PC_TREE_TERM_DEPTH = 5;   // height of the tallest term  (x + y = 2, (2*x + y) + 3*z = 4)
-constexpr int PC_TREE_FORM_DEPTH = 4;   // height of the connective nest above a comparison (b <=> (p /\ q) = 3)
+constexpr int PC_TREE_TERM_DEPTH = 8;   // height of the tallest term  (x + y = 2, (2*x + y) + 3*z = 4)
+constexpr int PC_TREE_FORM_DEPTH = 6;   // height of the connective nest above a comparison (b <=> (p /\ q) = 3)
 
 #ifdef LPC_HOST_HARNESS
 #define LPC_NI __host__ __device__ __noinline__

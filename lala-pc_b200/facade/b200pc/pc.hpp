@@ -420,7 +420,7 @@ private:
   // Token numbers of the stream; heights are checked against the device interpreter's limits (csrc/pc_tree.cuh).
   enum { TK_CONST = 1, TK_VAR = 2, TK_NEG = 3, TK_ABS = 4, TK_ADD = 5, TK_SUB = 6, TK_MUL = 7, TK_NARY_ADD = 8, TK_MIN = 9,
          TK_MAX = 10, TK_TDIV = 11, TK_FDIV = 12, TK_CDIV = 13, TK_EDIV = 14, TK_NARY_MUL = 15, FK_LIT = 20, FK_NLIT = 21, FK_LEQ = 22, FK_GT = 23, FK_EQ = 24, FK_NEQ = 25, FK_AND = 26, FK_OR = 27,
-         FK_EQUIV = 28, FK_IMPLY = 29, FK_XOR = 30, FK_TRUE = 32, FK_FALSE = 33, TREE_TERM_DEPTH = 5, TREE_FORM_DEPTH = 4 };
+         FK_EQUIV = 28, FK_IMPLY = 29, FK_XOR = 30, FK_TRUE = 32, FK_FALSE = 33, TREE_TERM_DEPTH = 8, TREE_FORM_DEPTH = 6 };
   // interpret_term (pc.hpp:217-296): returns the height (0 = not a term), `len` = Term::length()
   static int tree_term(const TF& t, const VarEnv& env, std::vector<int>& w, int& len) {
     AVar v;

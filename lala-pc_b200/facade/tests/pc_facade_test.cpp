@@ -275,7 +275,7 @@ static void UnsupportedShapesAreRefused() {
   for(auto& p : tell.props) EXPECT_EQ(p.kind, (int)LPC_PC_TREE);
   // ... unless they are deeper than the device interpreter walks, or hold a node PC has no rule for
   TF deep = V("x");
-  for(int i = 0; i < 6; ++i) deep = bin(deep, ADD, V("y"));
+  for(int i = 0; i < 9; ++i) deep = bin(deep, ADD, V("y"));
   EXPECT_FALSE(ipc.interpret_tell(bin(deep, LEQ, K(3)), m.env, tell, &why));
   EXPECT_EQ(why, std::string("The shape of this formula is not supported."));
   EXPECT_FALSE(ipc.interpret_tell(TF::in(V("x"), {1, 3}), m.env, tell, &why));                         // `in` needs a bitset store

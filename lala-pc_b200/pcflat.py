@@ -20,7 +20,7 @@ import numpy as np
 
 PC_LIN_LE, PC_REIF_LIN_LE, PC_EQ, PC_NEQ, PC_CLAUSE, PC_ABS_EQ = 1, 2, 3, 4, 5, 6
 PC_LIN_GE, PC_LIN_GT, PC_LIN_EQ, PC_LIN_EQ_VAR, PC_TREE = 7, 8, 9, 10, 11
-TREE_TERM_DEPTH, TREE_FORM_DEPTH = 5, 4   # csrc/pc_tree.cuh
+TREE_TERM_DEPTH, TREE_FORM_DEPTH = 8, 6   # csrc/pc_tree.cuh
 
 _T = {"const": 1, "var": 2, "neg": 3, "abs": 4, "add": 5, "sub": 6, "mul": 7, "sum": 8, "min": 9, "max": 10,
       "tdiv": 11, "fdiv": 12, "cdiv": 13, "ediv": 14, "prod": 15}

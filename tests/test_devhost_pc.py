@@ -80,6 +80,20 @@ def test_random_tree_networks(devhost):
         st = compare(devhost, forms, store, f"tree {trial}")
         n_ok += not st.is_bot
     assert n_ok >= 100
+    # the deepest trees the interpreter takes (8 term levels under 6 connective levels), and one level more: refused
+    from lala_pc_b200 import pcflat
+    comb = ("var", 0)
+    for k in range(7):
+        comb = (("add", "max", "sub")[k % 3], comb, ("var", 1 + k % 3))
+    nest = ("le", comb, ("const", 9))
+    for k in range(5):
+        nest = (("and", "or", "imply", "equiv", "and")[k], nest, ("gt", ("var", k % 4), ("const", k - 2)))
+    store = np.array([[0, 5], [-1, 4], [0, 3], [1, 2]], dtype=np.int32)
+    compare(devhost, [nest, ("le", comb, ("const", 4))], store, "deepest")
+    with pytest.raises(pcflat.Unsupported):
+        pcflat.flatten([("le", ("add", comb, ("var", 1)), ("const", 4))])
+    with pytest.raises(pcflat.Unsupported):
+        pcflat.flatten([("and", nest, ("lit", 3))])
 
 
 @pytest.mark.parametrize("cfg", ["config3", "config5"])

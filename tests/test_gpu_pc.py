@@ -46,9 +46,15 @@ def check_parity(L, O, formulas, store, label=""):
     want, st = m.fixpoint(store)
     t = L.PcTable(props, terms, len(store))
     s = L.Store(values=store)
-    r = t.fixpoint(s)
+    r = t.fixpoint(s)                      # default mode: lane tiles whose operands did not move are skipped
     got = s.read()
     assert bool(r.is_bot) == bool(st.is_bot), (label, "bot flag")
+    sd = L.Store(values=store)
+    rd = t.fixpoint(sd, mode=L.MODE_SWEEP)  # every propagator in every sweep
+    assert bool(rd.is_bot) == bool(st.is_bot), (label, "bot flag, dense")
+    assert rd.deductions == rd.sweeps * len(formulas) and r.deductions <= r.sweeps * len(formulas), (label, "deductions")
+    if not st.is_bot:
+        assert np.array_equal(sd.read(), got), (label, "dense vs tile-skipping store")
     if not st.is_bot:
         assert np.array_equal(got, want), (label, "store", np.flatnonzero((got != want).any(1))[:5].tolist())
         n_ent, bits = m.ask_all(want, want_bits=True)
@@ -123,8 +129,12 @@ def test_config3_full_size(L, O, W):
     s = L.Store(values=net.store)
     r = t.fixpoint(s)
     assert not r.is_bot and np.array_equal(s.read(), want)
+    sd = L.Store(values=net.store)
+    rd = t.fixpoint(sd, mode=L.MODE_SWEEP)
+    assert np.array_equal(sd.read(), want) and rd.deductions == rd.sweeps * len(net.props)
+    assert len(net.props) <= r.deductions < rd.deductions, (r.deductions, rd.deductions)   # tiles at rest were skipped
     r2 = t.fixpoint(s)
-    assert not r2.has_changed and r2.sweeps == 1
+    assert not r2.has_changed and r2.sweeps == 1 and r2.deductions == len(net.props)
     buf = net.store.copy()
     t.fixpoint_host(buf)
     assert np.array_equal(buf, want)
@@ -263,9 +273,18 @@ def test_tree_propagators(L, O):
                 if not bot:
                     assert np.array_equal(s.read(), cur), (trial, i, forms[i])
     assert n_ok >= 40 and n_tree >= 150
+    # the deepest trees the interpreter takes: a left comb of 8 term levels under 6 connective levels
+    comb = ("var", 0)
+    for k in range(7):
+        comb = (("add", "max", "sub")[k % 3], comb, ("var", 1 + k % 3))
+    nest = ("le", comb, ("const", 9))
+    for k in range(5):
+        nest = (("and", "or", "imply", "equiv", "and")[k], nest, ("gt", ("var", k % 4), ("const", k - 2)))
+    store = np.array([[0, 5], [-1, 4], [0, 3], [1, 2]], dtype=np.int32)
+    check_parity(L, O, [nest, ("le", comb, ("const", 4))], store, "deepest")
     # too deep for the device interpreter: refused, not approximated
     deep = ("var", 0)
-    for _ in range(6):
+    for _ in range(9):
         deep = ("add", deep, ("var", 1))
     with pytest.raises(pcflat.Unsupported):
         pcflat.flatten([("le", deep, ("const", 3))])
@@ -421,6 +440,10 @@ def test_config5_interval_vs_bitset(L, O, W, scale):
     rb = t.fixpoint(sb, bitset=True)
     got_b = sb.read_bits()
     assert not rb.is_bot and not st_b.is_bot and np.array_equal(got_b, want_b)
+    sbd = L.Store(nvars=net.nvars)
+    sbd.write_bits(cells)
+    rbd = t.fixpoint(sbd, bitset=True, mode=L.MODE_SWEEP)
+    assert np.array_equal(sbd.read_bits(), want_b) and rb.deductions <= rbd.deductions == rbd.sweeps * len(net.props)
     assert ((got_b & ~L.nbit_from_intervals(want_i)) == 0).all()
     sol = L.nbit_range(net.solution, net.solution)
     assert ((got_b & sol) == sol).all()

@@ -2,7 +2,7 @@
 wraps in tools/profile_r02.sh (`-k regex:<kernel> -s <warm-ups> -c 1` captures exactly that final launch), so that the
 counters of the capture can be divided by the deductions of the very launch they belong to.
 
-  python tools/prof_one.py <eps_dense|eps_auto|resident_dense|c2_dense|c2_auto|c1_dense|pc_c3|pc_c5|pc_c5_bits> [warmups] [out.json]
+  python tools/prof_one.py <eps_dense|eps_auto|resident_dense|c2_dense|c2_auto|c1_dense|pc_c3[_dense]|pc_c5[_dense]|pc_c5_bits[_dense]> [warmups] [out.json]
 """
 import json
 import os
@@ -53,6 +53,8 @@ def main():
             r = L.fixpoint(table, s, mode=mode, max_sweeps=ms)
         rec.update(r.as_dict())
     else:
+        dense = what.endswith("_dense")
+        what = what[:-6] if dense else what
         net = W.config3() if what == "pc_c3" else W.config5()
         bits = what.endswith("bits")
         t = L.PcTable(net.props, net.terms, net.nvars)
@@ -60,7 +62,7 @@ def main():
             s = L.Store(values=net.store)
             if bits:
                 s.write_bits(L.nbit_from_intervals(net.store))
-            r = t.fixpoint(s, bitset=bits)
+            r = t.fixpoint(s, bitset=bits, mode=L.MODE_SWEEP if dense else L.MODE_AUTO)
         rec.update(r.as_dict())
         rec["propagators"], rec["terms"] = len(net.props), len(net.terms)
     with open(out, "w") as f:
