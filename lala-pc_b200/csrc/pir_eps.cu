@@ -226,7 +226,12 @@ __device__ __forceinline__ void pk_rule(int op, int2 a, int2 b, int2 c, unsigned
     { const int bn = (r1.lb > r1.ub) | (r2.lb > r2.ub) | (r3.lb > r3.ub); signal_bot(a_bot, bn); bacc |= bn; }
   }
   else if(moved) {
-    if(JOIN == 1) {
+    if(JOIN == 4) {   // the plain stores of JOIN = 3, inside the moved-region
+      sts_if_gt(ax, r1.lb, a.x); sts_if_lt(ax + 4, r1.ub, a.y);
+      sts_if_gt(ay, r2.lb, b.x); sts_if_lt(ay + 4, r2.ub, b.y);
+      sts_if_gt(az, r3.lb, c.x); sts_if_lt(az + 4, r3.ub, c.y);
+    }
+    else if(JOIN == 1) {
       reds_max_if_gt(ax, r1.lb, a.x); reds_min_if_lt(ax + 4, r1.ub, a.y);
       reds_max_if_gt(ay, r2.lb, b.x); reds_min_if_lt(ay + 4, r2.ub, b.y);
       reds_max_if_gt(az, r3.lb, c.x); reds_min_if_lt(az + 4, r3.ub, c.y);
@@ -463,16 +468,24 @@ using namespace lpc;
 // ---- launch plan shared by the resident and the EPS entry points -------------------------------------------------------
 struct GroupPlan { int g = 0; size_t smem = 0; int sms = 0; size_t ptab_bytes = 0; };
 
+// The join variant (pk_rule) goes with the schedule. Dense sweeps (LPC_MODE_SWEEP) join with guarded atomics (JOIN = 1);
+// the default mode, which evaluates only the propagators not entailed on the root and so moves a bound in a larger share
+// of its evaluations, joins with plain predicated stores inside the moved-region (JOIN = 4): 2-4 % more sweeps, each of
+// them cheaper. Measured on config 4, dense / AUTO, ms (profiles/r02_ab_join.txt): JOIN 0 = 4.63 / 3.24, 1 = 4.36 / 3.20,
+// 2 = 5.12 / 3.35, 3 = 5.37 / 3.18, 4 = 4.45 / 3.06. LPC_JOIN forces one variant for A/B runs (0, 2, 3 are built for the
+// 8-group kernel without divisions only).
+static int join_of_mode(int mode) {
+  static int forced = -2;
+  if(forced == -2) { const char* e = getenv("LPC_JOIN"); forced = e ? atoi(e) : -1; }
+  return forced >= 0 ? forced : (mode == LPC_MODE_SWEEP ? 1 : 4);
+}
+
 template <bool EPS>
-static const void* group_kernel(bool has_div, int g) {
-  // LPC_JOIN picks another join variant for A/B runs (built for the 8-group kernel without divisions only). Measured on
-  // config 4, dense / AUTO (profiles/r02_ab_join.txt): 0 = 6.02 / 3.84 ms, 1 = 5.29 / 3.66 ms (default), 2 = 6.10 / 3.86 ms,
-  // 3 = 6.33 / 3.60 ms.
-  static int join = -1;
-  if(join < 0) { const char* e = getenv("LPC_JOIN"); join = e ? atoi(e) : 1; }
+static const void* group_kernel(bool has_div, int g, int join) {
   if(!has_div && g == 8 && join == 0) return (const void*)k_pir_group<false, 8, EPS, 0>;
   if(!has_div && g == 8 && join == 2) return (const void*)k_pir_group<false, 8, EPS, 2>;
   if(!has_div && g == 8 && join == 3) return (const void*)k_pir_group<false, 8, EPS, 3>;
+  if(g == 8 && join == 4) return has_div ? (const void*)k_pir_group<true, 8, EPS, 4> : (const void*)k_pir_group<false, 8, EPS, 4>;
   switch(g) {
     case 8: return has_div ? (const void*)k_pir_group<true, 8, EPS> : (const void*)k_pir_group<false, 8, EPS>;
     case 4: return has_div ? (const void*)k_pir_group<true, 4, EPS> : (const void*)k_pir_group<false, 4, EPS>;
@@ -501,10 +514,12 @@ static int group_plan(const lpc_table* t, int nvars, int sbytes, GroupPlan* plan
   static const int kG[3] = {8, 4, 2};
   for(int c = 0; c < 3; ++c) {
     const int g = want > 0 ? want : kG[c];
-    const void* k = group_kernel<EPS>(t->has_div, g);
+    const void* k = group_kernel<EPS>(t->has_div, g, join_of_mode(LPC_MODE_SWEEP));
+    const void* k2 = group_kernel<EPS>(t->has_div, g, join_of_mode(LPC_MODE_AUTO));
     const size_t need = 1024 + (size_t)g * sbytes + plan->ptab_bytes;
     if(k && need <= (size_t)optin) {
       LPC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+      if(k2 != k) LPC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
       int per_sm = 0;
       LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 1024, need));
       if(per_sm >= 1) { plan->g = g; plan->smem = need; return LPC_OK; }
@@ -557,7 +572,7 @@ int lpc_group_launch_resident(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
   A.flags = b->d_flags + first; A.sweeps_out = b->d_sweeps + first; A.obj_out = b->d_obj ? b->d_obj + first : nullptr;
   A.ctl = d_ctl; A.objective_var = objective_var; A.max_sweeps = o->max_sweeps; A.stop_on_bot = o->stop_on_bot;
   void* args[] = {&A};
-  LPC_CUDA(cudaLaunchKernel(group_kernel<false>(t->has_div, g), dim3(grid), dim3(1024), args, b->grp_smem, st));
+  LPC_CUDA(cudaLaunchKernel(group_kernel<false>(t->has_div, g, join_of_mode(o->mode)), dim3(grid), dim3(1024), args, b->grp_smem, st));
   g_launches++;
   *used = 1;
   return LPC_OK;
@@ -735,7 +750,7 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
     ++e->epoch;
     if(e->peers_ok) { A.peers = e->d_peer_ptrs; A.my_rank = e->rank; A.world = e->world; A.epoch = e->epoch; }
     void* args[] = {&A};
-    LPC_CUDA(cudaLaunchKernel(group_kernel<true>(t->has_div, g), dim3(grid), dim3(1024), args, e->plan.smem, st));
+    LPC_CUDA(cudaLaunchKernel(group_kernel<true>(t->has_div, g, join_of_mode(o->mode)), dim3(grid), dim3(1024), args, e->plan.smem, st));
     g_launches++;
   }
   LPC_CUDA(cudaEventRecord(e->ev1, st));
