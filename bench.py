@@ -594,6 +594,55 @@ def own_search(args, cpu=True, n_split=16384, max_nodes=64):
         out["cpu_baseline"] = {"nodes_per_s": float(want[:, 1].sum()) / dt, "cores": cores, "kind": "port",
                                "sample": "%d of the %d subproblems" % (sample, len(alive))}
     batch.close()
+    out["backtracking"] = own_search_complete(cpu)
+    return out
+
+
+def own_search_complete(cpu=True, nbits=12, max_nodes=2048):
+    """A search that runs to the bottom: a 200-variable / 500-propagator planted-solution model with narrow domains,
+    4,096 EPS subproblems, depth-first until every leaf is a solution or a failure (restore on every failure). The
+    per-subproblem records of a sample are compared with the CPU restatement at run time."""
+    import lala_pc_b200 as L
+    from lala_pc_b200 import workloads as W
+    net = W.pir_network(200, 500, seed=77, width=6)
+    table = L.Table(net.records, net.nvars)
+    s = L.Store(values=net.store)
+    L.fixpoint(table, s)
+    root = s.read()
+    dec, obj = W.eps_decisions(net.records, root, n=nbits, min_degree=2)
+    stores = W.eps_stores(root, dec, 0, 1 << len(dec))
+    width = root[:, 1].astype(np.int64) - root[:, 0]
+    bv = [int(v) for v in np.argsort(-width, kind="stable")]
+    batch = L.Batch(table, len(stores))
+    runs = {}
+    for cd in (False, True, None):   # dense nodes, change-driven nodes, the library's default (by table size)
+        for _ in range(3):
+            batch.write(stores)
+            r, per = batch.search(bv, objective_var=obj, max_nodes=max_nodes, max_depth=96, change_driven=cd)
+            if cd not in runs or r.device_ms < runs[cd][0].device_ms:
+                runs[cd] = (r, per)
+    (best, got), dense, chd = runs[None], runs[False][0], runs[True][0]
+    out = {"workload": "200-var / 500-propagator model, %d EPS subproblems, DFS to the leaves (budget %d nodes each)"
+                       % (len(stores), max_nodes),
+           "ms": best.device_ms, "nodes": int(best.n_nodes), "solutions": int(best.n_solutions), "fails": int(best.n_fails),
+           "incomplete": int(best.n_incomplete), "best_bound": int(best.best_bound), "max_depth": int(best.max_depth_seen),
+           "nodes_per_s": best.n_nodes / (best.device_ms * 1e-3), "deductions": int(best.deductions),
+           "dense_nodes_ms": dense.device_ms, "dense_nodes_deductions": int(dense.deductions),
+           "change_driven_nodes_ms": chd.device_ms, "change_driven_nodes_deductions": int(chd.deductions)}
+    assert best.n_fails > 0 and best.n_solutions > 0, "the backtracking workload neither failed nor solved anything"
+    assert (dense.n_nodes, dense.n_solutions, dense.n_fails) == (chd.n_nodes, chd.n_solutions, chd.n_fails)
+    if cpu:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        sample = min(len(stores), 512)
+        t0 = time.perf_counter()
+        want = O.pir_search(stores[:sample], net.records, bv, objective_var=obj, max_nodes=max_nodes, max_depth=96, threads=cores)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(got[:sample], want), "search records differ from the CPU restatement"
+        out["cpu_baseline"] = {"nodes_per_s": float(want[:, 1].sum()) / dt, "cores": cores, "kind": "port",
+                               "sample": "%d of the %d subproblems" % (sample, len(stores))}
+        out["checked"] = "per-subproblem {solutions, nodes, fails, best, incomplete} of %d subproblems == CPU restatement" % sample
+    batch.close()
     return out
 
 

@@ -296,8 +296,9 @@ typedef struct lpc_search_opts {
   int32_t max_depth;      /* snapshots per block stack (default 64) */
   int32_t objective_var;  /* < 0: none; else best_bound = min over solutions of lb(objective_var) */
   uint64_t stream;
-  int32_t change_driven;  /* 1 (default): a node's fixpoint starts from the propagators of the branched variable only and
-                             re-evaluates 32-record groups as their variables change; 0: dense sweeps at every node */
+  int32_t change_driven;  /* 1: a node's fixpoint starts from the propagators of the branched variable only and
+                             re-evaluates 32-record groups as their variables change; 0: dense sweeps at every node;
+                             -1 (default): change-driven for tables of 2,048 propagators or more, dense below */
   int32_t reserved;
 } lpc_search_opts;
 

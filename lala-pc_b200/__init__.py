@@ -534,14 +534,14 @@ class Batch:
         return p, n.value
 
     def search(self, branch_vars, objective_var=-1, max_nodes=0, max_depth=64, stream=0, want_per_store=True,
-               change_driven=True):
+               change_driven=None):
         """Depth-first search from every store of the batch (include/lpc.h: lpc_batch_search).
         Returns (SearchResult, int64 [n_stores, 6] {solutions, nodes, fails, best, incomplete, unknown_leaves} or None)."""
         bv = np.ascontiguousarray(branch_vars, dtype=np.int32)
         o, r = SearchOpts(), SearchResult()
         _L.lpc_search_default_opts(ctypes.byref(o))
         o.max_nodes, o.max_depth, o.objective_var, o.stream = max_nodes, max_depth, objective_var, stream
-        o.change_driven = int(change_driven)
+        o.change_driven = -1 if change_driven is None else int(change_driven)   # None: by table size
         per = np.zeros((self.n_stores, 6), dtype=np.int64) if want_per_store else None
         _check(_L.lpc_batch_search(self._h, bv.ctypes.data, bv.shape[0], ctypes.byref(o), ctypes.byref(r),
                                    per.ctypes.data if want_per_store else None))

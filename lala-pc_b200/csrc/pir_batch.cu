@@ -921,7 +921,9 @@ int lpc_batch_search(lpc_batch* b, const int32_t* branch_vars, int32_t n_branch,
   LPC_CUDA(cudaGetDevice(&dev));
   LPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   LPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const bool cd = o->change_driven != 0;
+  // change-driven nodes pay for their group maps on every node: a win on the 10,000-propagator model of config 4 (0.60 vs
+  // 0.82 ms for 15.8 k nodes), a loss on a 500-propagator one (39 vs 18 ms for 1.1 M nodes), so the default goes by size
+  const bool cd = o->change_driven < 0 ? t->dev.n >= 2048 : o->change_driven != 0;
   if(cd) { int rc = lpc_table_ensure_csr(const_cast<lpc_table*>(t)); if(rc) return rc; }
   const size_t base = 64 + (size_t)b->sbytes + (cd ? group_maps_bytes(t) : 0), tbl = (size_t)t->dev.n_pad * 13;
   if(base > (size_t)optin) { set_error("lpc_batch_search: a store of %d variables does not fit shared memory", b->nvars); return LPC_ERR_UNSUPPORTED; }
@@ -986,7 +988,7 @@ void lpc_search_default_opts(lpc_search_opts* o) {
   if(!o) return;
   memset(o, 0, sizeof(*o));
   o->max_nodes = 0; o->max_depth = 64; o->objective_var = -1;
-  o->change_driven = 1;   // measured on the config-4 model: 0.61 vs 1.25 ms for 15.8 k nodes, 40x fewer deductions
+  o->change_driven = -1;  // by table size (lpc_batch_search)
 }
 
 } // extern "C"

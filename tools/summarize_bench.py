@@ -37,7 +37,13 @@ if s:
     print("  time_to_fixpoint", {k: f(v, 4) for k, v in s["time_to_fixpoint"].items() if k != "what"})
     print("  cpu", f(g(s, "cpu_baseline", "fixpoint_ms"), 1), "ms")
 if d.get("pc"):
-    print("pc:", {k: (f(v["ms_per_fixpoint"], 4), v["sweeps"], f(g(v, "roofline", "frac"))) for k, v in d["pc"].items()})
-if d.get("search"):
-    print("search:", f(d["search"]["ms"]), "ms", d["search"]["nodes"], "nodes; fails", d["search"].get("fails"), "solutions", d["search"].get("solutions"))
+    print("pc (dense ms, sweeps, hbm frac, default-mode ms):", {k: (f(v["ms_per_fixpoint"], 4), v["sweeps"], f(g(v, "roofline", "frac")), f(g(v, "time_to_fixpoint", "auto_ms"), 4)) for k, v in d["pc"].items()})
 print("cpu_baseline", d.get("cpu_baseline"))
+if d.get("search"):
+    s = d["search"]
+    print("search:", f(s.get("ms")), "ms", s.get("nodes"), "nodes; fails", s.get("fails"), "solutions", s.get("solutions"))
+    b = s.get("backtracking")
+    if b:
+        print("  backtracking:", f(b.get("ms")), "ms (dense", f(b.get("dense_nodes_ms")), "cd", f(b.get("change_driven_nodes_ms")), ")", b.get("nodes"), "nodes; fails",
+              b.get("fails"), "solutions", b.get("solutions"), "incomplete", b.get("incomplete"), "| cpu nodes/s", f(g(b, "cpu_baseline", "nodes_per_s"), 0),
+              "gpu nodes/s", f(b.get("nodes_per_s"), 0))
