@@ -49,7 +49,8 @@ enum lpc_pc_kind {
    *             | 25 l r = (l != r) | 26 f g = and | 27 f g = or | 28 f g = equiv | 29 f g = imply | 30 f g = xor
    * Walked on the device by one thread per propagator exactly as Formula::deduce / Term::embed walk it
    * (lala-pc_b200/csrc/pc_tree.cuh); terms up to 8 levels and connectives up to 6 levels deep, deeper streams are
-   * refused with LPC_ERR_UNSUPPORTED. Interval stores only. */
+   * refused with LPC_ERR_UNSUPPORTED. Both store universes: over a bitset store the same walk runs on NBitset values
+   * (see below). */
   LPC_PC_TREE = 11
 };
 
@@ -91,9 +92,15 @@ int lpc_pc_ask_all(const lpc_pc_table* t, const lpc_store* s, int64_t* n_entaile
  * The same 8-byte cells of an lpc_store read as ONE uint64 per variable: bit 0 = "some value <= -1", bit i (1..62) =
  * value i - 1, bit 63 = "some value >= 62" (so [0, 61] is exact); meet = AND, bot = 0, top = all ones. A store handle
  * carries no domain tag: the caller picks the `_bits` entry points for stores it filled with lpc_store_write_bits.
- * Kinds with a bitset rule: EQ, NEQ (by complement, formula.hpp:642-644), CLAUSE, ABS_EQ - the shapes the reference
- * pins in tests/pc_bitset_test.cpp. Tables holding LIN_LE / REIF_LIN_LE return LPC_ERR_UNSUPPORTED from the `_bits`
- * calls: NBitset arithmetic on sums lives in lala-core (un-vendored) and no reference test pins it. */
+ * Kinds with a lane-tile rule on bitsets: EQ, NEQ (by complement, formula.hpp:642-644), CLAUSE, ABS_EQ - the shapes the
+ * reference pins in tests/pc_bitset_test.cpp. Every other kind - the LIN_* sums and LPC_PC_TREE - is walked as a formula
+ * tree over the NBitset universe, one thread per propagator (the `_bits` calls rewrite the linear kinds of a table as
+ * streams on first use): set operations (meet, join, complement, inclusion) are bitwise, every arithmetic operation goes
+ * through the interval hull of its operands and back into the universe, so values beyond [-1, 62] fold into the two
+ * open-ended bits. lala-core's NBitset::project is un-vendored and no reference test pins it beyond IntAbs1: this
+ * reading is the one the CPU checker of the test-suite carries, PARITY UNPINNED upstream.
+ * In that universe -x and (-1) * x differ (the constant -1 is the open-ended bit), so a front end that targets bitset
+ * stores must keep Unary<Neg> / Binary<Sub> as trees instead of folding them into a coefficient of -1. */
 int lpc_store_write_bits(lpc_store* s, int32_t first, int32_t n, const uint64_t* cells);
 int lpc_store_read_bits(const lpc_store* s, int32_t first, int32_t n, uint64_t* cells);
 /* VStore::embed / is_bot / is_top on bitset cells (pc.hpp:647-649, 685-692). */

@@ -17,12 +17,15 @@ __host__ __device__ __forceinline__ bool pc_is_linear(int kind) { return kind ==
 // The general tree propagator (pc_tree.cuh); its stream lives in the term array. On the device the interpreter is its
 // own translation unit (pc_tree.cu, built with a register cap so that the kernels can call it through the device ABI
 // whatever their launch bounds are) and is entered through the global-memory accessor below.
+struct UItv;   // the universes of the tree interpreter (pc_tree.cuh); an accessor names its own as Acc::Univ
+struct UNb;
 #ifdef LPC_HOST_HARNESS
 template <class Acc> LPC_HD int pc_tree_deduce(Acc& a, const int* words);
 template <class Acc> LPC_HD bool pc_tree_ask(const Acc& a, const int* words);
 #else
 // VStore<Interval<ZLB>> in global memory: gathers + lattice joins at L2.
 struct GlobalAcc {
+  typedef UItv Univ;
   int2* s;
   mutable int seen_bot;
   int touched;   // some embed tightened the store: what the fixpoint kernel votes with (a tree propagator's own return
@@ -297,8 +300,8 @@ LPC_HD bool pc_ask(const Acc& a, const int4 h, const int2* terms) {
 // ---- the same propagators over a VStore<NBitset<64>> (tests/pc_bitset_test.cpp:23-25) ----------------------------
 // One uint64 per variable: bit 0 = "some value <= -1", bit i (1..62) = value i - 1, bit 63 = "some value >= 62"; meet =
 // AND, join = OR, bot = 0, complement = NOT (lala-core nbitset.hpp, un-vendored; pinned by pc_bitset_test.cpp). Only the
-// four shapes those tests pin have a bitset rule (EQ, NEQ, CLAUSE, ABS_EQ); the table builder refuses the linear kinds
-// on a bitset store because NBitset's arithmetic is unpinned. `BAcc`: `load(v)` -> bits, `embed(v, bits)` -> bit0 =
+// four shapes those tests pin have a flat bitset rule (EQ, NEQ, CLAUSE, ABS_EQ); everything else runs through the tree
+// interpreter over the NBitset universe (pc_tree.cuh: arithmetic through the interval hull, unpinned upstream). `BAcc`: `load(v)` -> bits, `embed(v, bits)` -> bit0 =
 // changed, bit1 = became empty.
 typedef unsigned long long u64;
 LPC_HD int nb_ctz(u64 b) {
@@ -340,6 +343,34 @@ LPC_HD u64 nb_neg(u64 b) {   // project_fun(NEG)
   return nb_range(b_neg(x.ub), b_neg(x.lb));
 }
 LPC_HD bool nb_lit_ask(bool neg, u64 b) { return neg ? (b & ~2ull) == 0 : !((b >> 1) & 1); }   // formula.hpp:100-110
+
+#ifndef LPC_HOST_HARNESS
+// VStore<NBitset<64>> in global memory: one uint64 per variable, joins by atomicAnd.
+struct GlobalBitAcc {
+  typedef UNb Univ;
+  u64* s;
+  mutable int seen_bot;
+  int touched;   // as in GlobalAcc
+  __device__ __forceinline__ u64 load(int v) const {
+    const u64 d = __ldcg(&s[v]);
+    seen_bot |= d == 0;
+    return d;
+  }
+  __device__ __forceinline__ int embed(int v, u64 u) {
+    const u64 old = __ldcg(&s[v]);
+    if(old == 0) return 2;
+    const u64 nw = old & u;
+    if(nw == old) return 0;
+    atomicAnd(&s[v], u);
+    touched |= 1;
+    return nw == 0 ? 3 : 1;
+  }
+};
+__device__ int pc_tree_deduce_global_bits(GlobalBitAcc& a, const int* words);
+__device__ bool pc_tree_ask_global_bits(const GlobalBitAcc& a, const int* words);
+__device__ __forceinline__ int pc_tree_deduce(GlobalBitAcc& a, const int* words) { return pc_tree_deduce_global_bits(a, words); }
+__device__ __forceinline__ bool pc_tree_ask(const GlobalBitAcc& a, const int* words) { return pc_tree_ask_global_bits(a, words); }
+#endif
 
 template <class BAcc>
 LPC_HD int pc_deduce_bits(BAcc& a, const int4 h, const int2* terms) {
@@ -385,6 +416,9 @@ LPC_HD int pc_deduce_bits(BAcc& a, const int4 h, const int2* terms) {
       f |= a.embed(x, r | nb_neg(r));
       return f;
     }
+    // every other shape - sums included - is walked as a tree over the NBitset universe (pc_tree.cuh, struct UNb); the table
+    // builder hands the linear kinds over in that form (pc_linear_tree_words)
+    case PC_TREE: return pc_tree_deduce(a, reinterpret_cast<const int*>(terms));
     default: return 0;
   }
 }
@@ -401,6 +435,7 @@ LPC_HD bool pc_ask_bits(const BAcc& a, const int4 h, const int2* terms) {
       return any;
     }
     case PC_ABS_EQ: { const u64 ax = nb_abs(a.load(terms[0].y)), r = a.load(terms[1].y); return ax == r && nb_singleton(ax); }
+    case PC_TREE: return pc_tree_ask(a, reinterpret_cast<const int*>(terms));
     default: return true;
   }
 }

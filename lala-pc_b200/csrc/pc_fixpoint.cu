@@ -31,25 +31,6 @@ constexpr int PC_TPB = 256;
 constexpr int PC_NVAR = 5;
 constexpr int PC_VAR_DEFAULT = 0;
 
-// VStore<NBitset<64>> in global memory: one uint64 per variable, joins by atomicAnd.
-struct GlobalBitAcc {
-  u64* s;
-  mutable int seen_bot;
-  __device__ __forceinline__ u64 load(int v) const {
-    const u64 d = __ldcg(&s[v]);
-    seen_bot |= d == 0;
-    return d;
-  }
-  __device__ __forceinline__ int embed(int v, u64 u) {
-    const u64 old = __ldcg(&s[v]);
-    if(old == 0) return 2;
-    const u64 nw = old & u;
-    if(nw == old) return 0;
-    atomicAnd(&s[v], u);
-    return nw == 0 ? 3 : 1;
-  }
-};
-
 template <bool BITS> struct PcAcc { typedef GlobalAcc type; };
 template <> struct PcAcc<true> { typedef GlobalBitAcc type; };
 template <bool BITS, class Acc> __device__ __noinline__ int pc_step(Acc& acc, const int4 h, const int2* terms) {
@@ -57,7 +38,7 @@ template <bool BITS, class Acc> __device__ __noinline__ int pc_step(Acc& acc, co
   else return pc_deduce(acc, h, terms);
 }
 __device__ __forceinline__ GlobalAcc make_acc(int2* store, GlobalAcc*) { return GlobalAcc{store, 0, 0}; }
-__device__ __forceinline__ GlobalBitAcc make_acc(int2* store, GlobalBitAcc*) { return GlobalBitAcc{reinterpret_cast<u64*>(store), 0}; }
+__device__ __forceinline__ GlobalBitAcc make_acc(int2* store, GlobalBitAcc*) { return GlobalBitAcc{reinterpret_cast<u64*>(store), 0, 0}; }
 
 // ---- one tile = one warp step ------------------------------------------------------------------------------------------
 // Join of one variable given the domain this lane read (VStore::embed): bit0 = tightened, bit1 = became empty.
@@ -344,7 +325,7 @@ __global__ void __launch_bounds__(PC_TPB, PC_MIN_BLOCKS) k_pc_fixpoint(PcTableDe
       f |= pc_step<BITS>(acc, h, t.terms + h.y);
     }
     if(acc.seen_bot) f |= 2;
-    if constexpr(!BITS) f |= acc.touched & 1;
+    f |= acc.touched & 1;
     const GridVote v = grid_vote_barrier(ctl->bar, nbar++, f & 1, f & 2, &s_vote);
     ++sweeps;
     bot |= v.bot;
@@ -394,17 +375,33 @@ __global__ void k_pc_ask_all(PcTableDev t, const int2* store, unsigned long long
 
 using namespace lpc;
 
-struct lpc_pc_table {
+// The device arrays of one view of a table.
+struct PcArrays {
   PcTableDev dev{};
   void* d_hdr = nullptr;
   void* d_terms = nullptr;
   void* d_tiles = nullptr;
   void* d_tile_prop0 = nullptr;
   void* d_big = nullptr;
+  void release() {
+    cudaFree(d_hdr); cudaFree(d_terms); cudaFree(d_tiles); cudaFree(d_tile_prop0); cudaFree(d_big);
+    d_hdr = d_terms = d_tiles = d_tile_prop0 = d_big = nullptr;
+  }
+};
+
+struct lpc_pc_table {
+  PcTableDev dev{};                 // the table as an interval store sees it (= main.dev)
+  PcArrays main;
+  // the table as an NBitset store sees it: linear kinds rewritten as formula streams (pc_bits_view). Built on the first
+  // bitset call of a table that holds a linear kind; tables without one use `main` on both stores.
+  PcArrays bits;
+  bool bits_built = false;
+  bool has_linear = false;          // a flat linear kind is present
+  std::vector<int> h_props;         // the caller's arrays, kept for the bitset view (5 ints per propagator)
+  std::vector<int2> h_terms;
   int sm_count = 0;
   int blocks_per_sm[2] = {0, 0};   // [interval store, bitset store]
   int variant = 0;
-  bool has_linear = false;          // LIN_LE / REIF_LIN_LE present: no bitset rule (see lpc_pc.h)
   lpc_store* host_store = nullptr;
 };
 
@@ -417,16 +414,10 @@ static const void* pc_kernel(bool bits, int variant) {
   return k[bits][variant];
 }
 
-extern "C" {
-
-int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_term* terms, int64_t n_terms,
-                        int32_t nvars, lpc_pc_table** out) {
-  LPC_REQUIRE(out != nullptr, "null out");
-  LPC_REQUIRE(n_props >= 0 && n_terms >= 0 && nvars >= 0, "negative size");
-  LPC_REQUIRE((n_props == 0 || props) && (n_terms == 0 || terms), "null array");
-  int cnt = 0;
-  lpc_device_count(&cnt);
-  if(cnt == 0) { set_error("no CUDA device: this library has no CPU path"); return LPC_ERR_NO_DEVICE; }
+// Check + upload one view: headers, terms, lane tiles (whole propagators packed into 32-lane tiles, in table order; see the
+// header of this file), the list of untiled propagators.
+static int pc_build_arrays(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_term* terms, int64_t n_terms, int32_t nvars,
+                           PcArrays* A, bool* has_linear_out) {
   std::vector<int4> hdr((size_t)std::max<int64_t>(n_props, 1));
   bool has_linear = false;
   for(int64_t i = 0; i < n_props; ++i) {
@@ -440,7 +431,6 @@ int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_
         return LPC_ERR_UNSUPPORTED;
       }
       hdr[i] = make_int4(p.kind | (p.n_terms << 8), p.first_term, p.rhs, p.bvar);
-      has_linear = true;   // interval arithmetic inside: no bitset rule
       continue;
     }
     const bool two = p.kind == LPC_PC_EQ || p.kind == LPC_PC_ABS_EQ;
@@ -455,65 +445,106 @@ int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_
     hdr[i] = make_int4(p.kind | (p.n_terms << 8), p.first_term, p.rhs, p.bvar);
     has_linear |= lin_kind;
   }
-  lpc_pc_table* t = new lpc_pc_table();
-  t->has_linear = has_linear;
-  LPC_CUDA(cudaMalloc(&t->d_hdr, hdr.size() * sizeof(int4)));
-  LPC_CUDA(cudaMalloc(&t->d_terms, std::max<size_t>((size_t)n_terms * sizeof(int2), 16)));
-  if(n_props) LPC_CUDA(cudaMemcpy(t->d_hdr, hdr.data(), (size_t)n_props * sizeof(int4), cudaMemcpyHostToDevice));
-  if(n_terms) LPC_CUDA(cudaMemcpy(t->d_terms, terms, (size_t)n_terms * sizeof(int2), cudaMemcpyHostToDevice));
-  // lane tiles: whole propagators packed into 32-lane tiles, in table order (see the header of this file)
-  {
-    std::vector<int4> tiles;
-    std::vector<int> prop0, big;
-    int cur = 32;   // lanes used in the open tile (32 = none open)
-    for(int64_t i = 0; i < n_props; ++i) {
-      const lpc_pc_prop& p = props[i];
-      const int lanes = p.n_terms + (pc_has_extra_lane(p.kind) ? 1 : 0);
-      const bool lin_kind = pc_is_linear(p.kind);
-      if(p.kind == LPC_PC_TREE || lanes > 32 || (lin_kind && (p.rhs >= (1 << 30) || p.rhs <= -(1 << 30)))) {   // see tile_step: keeps the tile arithmetic in int32
-        big.push_back((int)i);
-        cur = 32;   // close the tile so that tile_prop0 + rank stays a contiguous propagator range
-        continue;
-      }
-      if(cur + lanes > 32) {
-        tiles.resize(tiles.size() + 32, make_int4(0, 0, 0, 0));
-        prop0.push_back((int)i);
-        cur = 0;
-      }
-      int4* lane = tiles.data() + tiles.size() - 32 + cur;
-      for(int k = 0; k < p.n_terms; ++k) {
-        const lpc_pc_term& tm = terms[p.first_term + k];
-        lane[k] = make_int4(tm.coef, tm.var, PC_META(cur, lanes, p.kind, 0), p.rhs);
-      }
-      if(lanes > p.n_terms) lane[p.n_terms] = make_int4(0, p.bvar, PC_META(cur, lanes, p.kind, 1), p.rhs);
-      cur += lanes;
+  if(has_linear_out) *has_linear_out = has_linear;
+  LPC_CUDA(cudaMalloc(&A->d_hdr, hdr.size() * sizeof(int4)));
+  LPC_CUDA(cudaMalloc(&A->d_terms, std::max<size_t>((size_t)n_terms * sizeof(int2), 16)));
+  if(n_props) LPC_CUDA(cudaMemcpy(A->d_hdr, hdr.data(), (size_t)n_props * sizeof(int4), cudaMemcpyHostToDevice));
+  if(n_terms) LPC_CUDA(cudaMemcpy(A->d_terms, terms, (size_t)n_terms * sizeof(int2), cudaMemcpyHostToDevice));
+  std::vector<int4> tiles;
+  std::vector<int> prop0, big;
+  int cur = 32;   // lanes used in the open tile (32 = none open)
+  for(int64_t i = 0; i < n_props; ++i) {
+    const lpc_pc_prop& p = props[i];
+    const int lanes = p.n_terms + (pc_has_extra_lane(p.kind) ? 1 : 0);
+    const bool lin_kind = pc_is_linear(p.kind);
+    if(p.kind == LPC_PC_TREE || lanes > 32 || (lin_kind && (p.rhs >= (1 << 30) || p.rhs <= -(1 << 30)))) {   // see tile_step: keeps the tile arithmetic in int32
+      big.push_back((int)i);
+      cur = 32;   // close the tile so that tile_prop0 + rank stays a contiguous propagator range
+      continue;
     }
-    t->dev.n_tiles = (long long)prop0.size();
-    t->dev.n_big = (int)big.size();
-    LPC_CUDA(cudaMalloc(&t->d_tiles, std::max<size_t>(tiles.size() * sizeof(int4), 16)));
-    LPC_CUDA(cudaMalloc(&t->d_tile_prop0, std::max<size_t>(prop0.size() * sizeof(int), 16)));
-    LPC_CUDA(cudaMalloc(&t->d_big, std::max<size_t>(big.size() * sizeof(int), 16)));
-    if(!tiles.empty()) LPC_CUDA(cudaMemcpy(t->d_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    if(!prop0.empty()) LPC_CUDA(cudaMemcpy(t->d_tile_prop0, prop0.data(), prop0.size() * sizeof(int), cudaMemcpyHostToDevice));
-    if(!big.empty()) LPC_CUDA(cudaMemcpy(t->d_big, big.data(), big.size() * sizeof(int), cudaMemcpyHostToDevice));
-    t->dev.tiles = (const int4*)t->d_tiles; t->dev.tile_prop0 = (const int*)t->d_tile_prop0; t->dev.big = (const int*)t->d_big;
+    if(cur + lanes > 32) {
+      tiles.resize(tiles.size() + 32, make_int4(0, 0, 0, 0));
+      prop0.push_back((int)i);
+      cur = 0;
+    }
+    int4* lane = tiles.data() + tiles.size() - 32 + cur;
+    for(int k = 0; k < p.n_terms; ++k) {
+      const lpc_pc_term& tm = terms[p.first_term + k];
+      lane[k] = make_int4(tm.coef, tm.var, PC_META(cur, lanes, p.kind, 0), p.rhs);
+    }
+    if(lanes > p.n_terms) lane[p.n_terms] = make_int4(0, p.bvar, PC_META(cur, lanes, p.kind, 1), p.rhs);
+    cur += lanes;
   }
-  t->dev.hdr = (const int4*)t->d_hdr; t->dev.terms = (const int2*)t->d_terms;
-  t->dev.n = n_props; t->dev.n_terms = n_terms; t->dev.nvars = nvars;
-  int dev = 0;
-  LPC_CUDA(cudaGetDevice(&dev));
-  LPC_CUDA(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
-  t->variant = PC_VAR_DEFAULT;
-  if(const char* e = getenv("LPC_PC_VARIANT")) { int v = atoi(e); if(v >= 0 && v < PC_NVAR) t->variant = v; }
-  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[0], pc_kernel(false, t->variant), PC_TPB, 0));
-  LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[1], pc_kernel(true, t->variant), PC_TPB, 0));
+  A->dev.n_tiles = (long long)prop0.size();
+  A->dev.n_big = (int)big.size();
+  LPC_CUDA(cudaMalloc(&A->d_tiles, std::max<size_t>(tiles.size() * sizeof(int4), 16)));
+  LPC_CUDA(cudaMalloc(&A->d_tile_prop0, std::max<size_t>(prop0.size() * sizeof(int), 16)));
+  LPC_CUDA(cudaMalloc(&A->d_big, std::max<size_t>(big.size() * sizeof(int), 16)));
+  if(!tiles.empty()) LPC_CUDA(cudaMemcpy(A->d_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if(!prop0.empty()) LPC_CUDA(cudaMemcpy(A->d_tile_prop0, prop0.data(), prop0.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if(!big.empty()) LPC_CUDA(cudaMemcpy(A->d_big, big.data(), big.size() * sizeof(int), cudaMemcpyHostToDevice));
+  A->dev.tiles = (const int4*)A->d_tiles; A->dev.tile_prop0 = (const int*)A->d_tile_prop0; A->dev.big = (const int*)A->d_big;
+  A->dev.hdr = (const int4*)A->d_hdr; A->dev.terms = (const int2*)A->d_terms;
+  A->dev.n = n_props; A->dev.n_terms = n_terms; A->dev.nvars = nvars;
+  return LPC_OK;
+}
+
+// The view a store of the given universe runs on (the bitset view is built on first use).
+static int pc_view(const lpc_pc_table* tc, bool bits, const PcTableDev** out) {
+  lpc_pc_table* t = const_cast<lpc_pc_table*>(tc);
+  if(!bits || !t->has_linear) { *out = &t->main.dev; return LPC_OK; }
+  if(!t->bits_built) {
+    std::vector<int> vp;
+    std::vector<int2> vt;
+    pc_bits_view(t->h_props.data(), (long long)t->h_props.size() / 5, t->h_terms.data(), (long long)t->h_terms.size(), vp, vt);
+    static_assert(sizeof(lpc_pc_prop) == 5 * sizeof(int) && sizeof(lpc_pc_term) == sizeof(int2), "flat layouts");
+    int rc = pc_build_arrays(reinterpret_cast<const lpc_pc_prop*>(vp.data()), (int64_t)vp.size() / 5,
+                             reinterpret_cast<const lpc_pc_term*>(vt.data()), (int64_t)vt.size(), t->dev.nvars, &t->bits, nullptr);
+    if(rc) { t->bits.release(); return rc; }
+    t->bits_built = true;
+  }
+  *out = &t->bits.dev;
+  return LPC_OK;
+}
+
+extern "C" {
+
+int lpc_pc_table_create(const lpc_pc_prop* props, int64_t n_props, const lpc_pc_term* terms, int64_t n_terms,
+                        int32_t nvars, lpc_pc_table** out) {
+  LPC_REQUIRE(out != nullptr, "null out");
+  LPC_REQUIRE(n_props >= 0 && n_terms >= 0 && nvars >= 0, "negative size");
+  LPC_REQUIRE((n_props == 0 || props) && (n_terms == 0 || terms), "null array");
+  int cnt = 0;
+  lpc_device_count(&cnt);
+  if(cnt == 0) { set_error("no CUDA device: this library has no CPU path"); return LPC_ERR_NO_DEVICE; }
+  lpc_pc_table* t = new lpc_pc_table();
+  auto body = [&]() -> int {
+    int rc = pc_build_arrays(props, n_props, terms, n_terms, nvars, &t->main, &t->has_linear);
+    if(rc) return rc;
+    t->dev = t->main.dev;
+    if(t->has_linear) {   // kept for the bitset view
+      t->h_props.assign(reinterpret_cast<const int*>(props), reinterpret_cast<const int*>(props) + 5 * n_props);
+      t->h_terms.assign(reinterpret_cast<const int2*>(terms), reinterpret_cast<const int2*>(terms) + n_terms);
+    }
+    int dev = 0;
+    LPC_CUDA(cudaGetDevice(&dev));
+    LPC_CUDA(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    t->variant = PC_VAR_DEFAULT;
+    if(const char* e = getenv("LPC_PC_VARIANT")) { int v = atoi(e); if(v >= 0 && v < PC_NVAR) t->variant = v; }
+    LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[0], pc_kernel(false, t->variant), PC_TPB, 0));
+    LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->blocks_per_sm[1], pc_kernel(true, t->variant), PC_TPB, 0));
+    return LPC_OK;
+  };
+  const int rc = body();
+  if(rc) { lpc_pc_table_destroy(t); return rc; }
   *out = t;
   return LPC_OK;
 }
 
 int lpc_pc_table_destroy(lpc_pc_table* t) {
   if(!t) return LPC_OK;
-  cudaFree(t->d_hdr); cudaFree(t->d_terms); cudaFree(t->d_tiles); cudaFree(t->d_tile_prop0); cudaFree(t->d_big);
+  t->main.release();
+  t->bits.release();
   if(t->host_store) lpc_store_destroy(t->host_store);
   delete t;
   return LPC_OK;
@@ -522,28 +553,21 @@ int lpc_pc_table_destroy(lpc_pc_table* t) {
 int64_t lpc_pc_table_size(const lpc_pc_table* t) { return t ? (int64_t)t->dev.n : 0; }
 int64_t lpc_pc_table_terms(const lpc_pc_table* t) { return t ? (int64_t)t->dev.n_terms : 0; }
 
-static int check_bits(const lpc_pc_table* t, bool bits) {
-  if(bits && t->has_linear) {
-    set_error("bitset stores support the EQ, NEQ, CLAUSE and ABS_EQ kinds only (NBitset arithmetic is unpinned upstream; LIN_* and TREE propagators compute on intervals)");
-    return LPC_ERR_UNSUPPORTED;
-  }
-  return LPC_OK;
-}
-
 static int pc_fixpoint_async(const lpc_pc_table* t, lpc_store* s, const lpc_fixpoint_opts* o, bool bits) {
   LPC_REQUIRE(t && s, "null argument");
   LPC_REQUIRE(s->nvars >= t->dev.nvars, "store smaller than the table's variable range");
   LPC_REQUIRE(t->blocks_per_sm[bits] > 0, "kernel does not fit on an SM");
-  if(int rc = check_bits(t, bits)) return rc;
+  const PcTableDev* view = nullptr;
+  if(int rc = pc_view(t, bits, &view)) return rc;
   lpc_fixpoint_opts def;
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   cudaStream_t st = (cudaStream_t)o->stream;
   int grid = t->sm_count * t->blocks_per_sm[bits];
-  long long want = std::max<long long>(1, std::max<long long>((t->dev.n_tiles * 32 + PC_TPB - 1) / PC_TPB, (t->dev.n_big + PC_TPB - 1) / PC_TPB));
+  long long want = std::max<long long>(1, std::max<long long>((view->n_tiles * 32 + PC_TPB - 1) / PC_TPB, (view->n_big + PC_TPB - 1) / PC_TPB));
   if(want < grid) grid = (int)want;
   int2* seen = nullptr;
-  if(o->mode != LPC_MODE_SWEEP && t->dev.n_tiles > 0) {   // per tile: the 32 cells last seen
-    const long long cells = t->dev.n_tiles * 32;
+  if(o->mode != LPC_MODE_SWEEP && view->n_tiles > 0) {   // per tile: the 32 cells last seen
+    const long long cells = view->n_tiles * 32;
     if(s->pc_seen_cap < cells) {
       cudaFree(s->d_pc_seen);
       s->d_pc_seen = nullptr; s->pc_seen_cap = 0;
@@ -554,7 +578,7 @@ static int pc_fixpoint_async(const lpc_pc_table* t, lpc_store* s, const lpc_fixp
   }
   LPC_CUDA(cudaEventRecord(s->ev0, st));
   LPC_CUDA(cudaMemsetAsync(s->d_ctl, 0, sizeof(FixCtl), st));
-  PcTableDev td = t->dev;
+  PcTableDev td = *view;
   int2* store = s->d;
   FixCtl* ctl = s->d_ctl;
   int max_sweeps = o->max_sweeps, stop = o->stop_on_bot;
@@ -589,9 +613,10 @@ static int pc_deduce_one(const lpc_pc_table* t, lpc_store* s, int64_t i, int* ch
   LPC_REQUIRE(t && s, "null argument");
   LPC_REQUIRE(i >= 0 && i < t->dev.n, "propagator index out of range");
   LPC_REQUIRE(s->nvars >= t->dev.nvars, "store smaller than the table's variable range");
-  if(int rc = check_bits(t, bits)) return rc;
-  if(bits) k_pc_deduce_one<true><<<1, 1>>>(t->dev, s->d, i, &s->d_ctl->scratch[0]);
-  else k_pc_deduce_one<false><<<1, 1>>>(t->dev, s->d, i, &s->d_ctl->scratch[0]);
+  const PcTableDev* view = nullptr;
+  if(int rc = pc_view(t, bits, &view)) return rc;
+  if(bits) k_pc_deduce_one<true><<<1, 1>>>(*view, s->d, i, &s->d_ctl->scratch[0]);
+  else k_pc_deduce_one<false><<<1, 1>>>(*view, s->d, i, &s->d_ctl->scratch[0]);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   int c = 0;
@@ -603,7 +628,8 @@ static int pc_deduce_one(const lpc_pc_table* t, lpc_store* s, int64_t i, int* ch
 static int pc_ask_all(const lpc_pc_table* t, const lpc_store* s, int64_t* n_entailed, uint8_t* bits_out, bool bits) {
   LPC_REQUIRE(t && s, "null argument");
   LPC_REQUIRE(s->nvars >= t->dev.nvars, "store smaller than the table's variable range");
-  if(int rc = check_bits(t, bits)) return rc;
+  const PcTableDev* view = nullptr;
+  if(int rc = pc_view(t, bits, &view)) return rc;
   unsigned long long* d_cnt = nullptr;
   uint8_t* d_bits = nullptr;
   LPC_CUDA(cudaMalloc((void**)&d_cnt, 8));
@@ -611,8 +637,8 @@ static int pc_ask_all(const lpc_pc_table* t, const lpc_store* s, int64_t* n_enta
   if(bits_out && t->dev.n) LPC_CUDA(cudaMalloc((void**)&d_bits, t->dev.n));
   if(t->dev.n) {
     int blocks = (int)std::min<long long>(ceil_div(t->dev.n, 256), 148 * 8);
-    if(bits) k_pc_ask_all<true><<<blocks, 256>>>(t->dev, s->d, d_cnt, d_bits);
-    else k_pc_ask_all<false><<<blocks, 256>>>(t->dev, s->d, d_cnt, d_bits);
+    if(bits) k_pc_ask_all<true><<<blocks, 256>>>(*view, s->d, d_cnt, d_bits);
+    else k_pc_ask_all<false><<<blocks, 256>>>(*view, s->d, d_cnt, d_bits);
     g_launches++;
     LPC_CUDA(cudaGetLastError());
   }

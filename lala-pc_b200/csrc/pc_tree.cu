@@ -6,4 +6,6 @@
 namespace lpc {
 __device__ __noinline__ int pc_tree_deduce_global(GlobalAcc& a, const int* words) { return pc_tree_deduce_impl(a, words); }
 __device__ __noinline__ bool pc_tree_ask_global(const GlobalAcc& a, const int* words) { return pc_tree_ask_impl(a, words); }
+__device__ __noinline__ int pc_tree_deduce_global_bits(GlobalBitAcc& a, const int* words) { return pc_tree_deduce_impl(a, words); }
+__device__ __noinline__ bool pc_tree_ask_global_bits(const GlobalBitAcc& a, const int* words) { return pc_tree_ask_impl(a, words); }
 } // namespace lpc

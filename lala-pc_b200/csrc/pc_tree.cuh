@@ -24,6 +24,7 @@
 #pragma once
 // (included by pc_tree.cu, by the table builder for tree_check, and - on the host harness - at the end of pc_device.cuh)
 #include "pc_device.cuh"
+#include <vector>
 namespace lpc {
 
 enum PcTok : int { T_CONST = 1, T_VAR = 2, T_NEG = 3, T_ABS = 4, T_ADD = 5, T_SUB = 6, T_MUL = 7, T_NARY_ADD = 8,
@@ -129,6 +130,48 @@ inline int tree_check(const int* w, int n, int nvars) {
   return i;
 }
 
+// A flat linear propagator (include/lpc_pc.h) as the formula stream of the tree it stands for - the shape the
+// reference's interpreter builds (pc.hpp:277-296): a coefficient 1 is the bare variable, any other c * x is
+// Binary<Mul>(Constant, Variable); one term stands alone, two are Binary<Add>, three or more Nary<Add>. Used by the table
+// builder for stores whose universe has no lane-tile rule for sums (NBitset).
+inline void pc_linear_tree_words(int kind, const int2* terms, int n, int rhs, int bvar, std::vector<int>& w) {
+  auto lhs = [&]() {
+    if(n == 2) w.push_back(T_ADD);
+    else if(n > 2) { w.push_back(T_NARY_ADD); w.push_back(n); }
+    for(int i = 0; i < n; ++i) {
+      if(terms[i].x != 1) { w.push_back(T_MUL); w.push_back(T_CONST); w.push_back(terms[i].x); }
+      w.push_back(T_VAR); w.push_back(terms[i].y);
+    }
+  };
+  auto cst = [&]() { w.push_back(T_CONST); w.push_back(rhs); };
+  switch(kind) {
+    case PC_LIN_LE: w.push_back(F_LEQ); lhs(); cst(); break;
+    case PC_LIN_GE: w.push_back(F_LEQ); cst(); lhs(); break;
+    case PC_LIN_GT: w.push_back(F_GT); lhs(); cst(); break;
+    case PC_LIN_EQ: w.push_back(F_EQ); lhs(); cst(); break;
+    case PC_LIN_EQ_VAR: w.push_back(F_EQ); lhs(); w.push_back(T_VAR); w.push_back(bvar); break;
+    default: w.push_back(F_EQUIV); w.push_back(F_VARLIT); w.push_back(bvar); w.push_back(F_LEQ); lhs(); cst(); break;   // PC_REIF_LIN_LE
+  }
+  if(w.size() % 2) w.push_back(0);
+}
+
+// The table as a bitset store sees it: the four flat kinds with a bitset rule stay, every linear propagator becomes an
+// LPC_PC_TREE propagator whose stream is appended to the term array. props: n x {kind, first_term, n_terms, rhs, bvar}.
+inline void pc_bits_view(const int* props, long long n, const int2* terms, long long n_terms, std::vector<int>& oprops,
+                         std::vector<int2>& oterms) {
+  oprops.assign(props, props + 5 * n);
+  oterms.assign(terms, terms + n_terms);
+  std::vector<int> w;
+  for(long long i = 0; i < n; ++i) {
+    int* p = oprops.data() + 5 * i;
+    if(!pc_is_linear(p[0])) continue;
+    w.clear();
+    pc_linear_tree_words(p[0], terms + p[1], p[2], p[3], p[4], w);
+    p[0] = PC_TREE; p[1] = (int)oterms.size(); p[2] = (int)(w.size() / 2); p[3] = 0; p[4] = -1;
+    for(size_t k = 0; k < w.size(); k += 2) oterms.push_back(make_int2(w[k], w[k + 1]));
+  }
+}
+
 // ---- interval helpers (lala-core Interval::project(Sig, ...), restated; see the header of pc_device.cuh) -------------
 LPC_HD Itv tr_neg(const Itv& a) { return Itv(b_neg(a.ub), b_neg(a.lb)); }
 LPC_HD Itv tr_add(const Itv& a, const Itv& b) { return Itv(b_add(a.lb, b.lb), b_add(a.ub, b.ub)); }
@@ -211,85 +254,160 @@ LPC_HD Itv tr_div_right(int k, const Itv& u, const Itv& b, Itv r) {
 }
 LPC_HD bool tr_same(const Itv& a, const Itv& b) { return (a.is_bot() && b.is_bot()) || (a.lb == b.lb && a.ub == b.ub); }
 
+// ---- universes ----------------------------------------------------------------------------------------------------------
+// The walk below is written once over a universe U (the reference's template parameter of pc::Term / pc::Formula): the
+// value type V of a variable's domain and of every intermediate result, with the operations Interval / NBitset offer.
+// An accessor names its universe (Acc::Univ); load(v) returns a V, embed(v, V) joins one.
+//  * UItv: Interval<ZLB>, the operations above.
+//  * UNb: NBitset<64> as one uint64 (pc_device.cuh). lala-core's NBitset::project is un-vendored and no reference test
+//    pins it beyond IntAbs1: every arithmetic operation goes through the interval hull of its operands and
+//    back into the universe (so results beyond [-1, 62] fold into the two open-ended bits), the set operations - meet,
+//    join, complement, inclusion - are bitwise. The CPU checker of the test-suite carries the same
+//    reading; PARITY UNPINNED against upstream for anything but =, !=, clauses and abs.
+struct UItv {
+  typedef Itv V;
+  static constexpr bool complemented = false;
+  static LPC_HD V range(int l, int u) { return Itv(l, u); }
+  static LPC_HD V top() { return itv_top(); }
+  static LPC_HD V bot() { return itv_bot(); }
+  static LPC_HD int lo(const V& a) { return a.lb; }
+  static LPC_HD int hi(const V& a) { return a.ub; }
+  static LPC_HD bool is_bot(const V& a) { return a.is_bot(); }
+  static LPC_HD void meet(V& a, const V& b) { a.meet(b); }
+  static LPC_HD V join(const V& a, const V& b) { return fjoin(a, b); }
+  static LPC_HD V complement(const V& a) { return a; }   // never called: complemented == false
+  static LPC_HD bool same(const V& a, const V& b) { return tr_same(a, b); }
+  static LPC_HD bool has0(const V& a) { return contains0(a); }
+  static LPC_HD bool sub_of(const V& a, int l, int u) { return a.is_bot() || (a.lb >= l && a.ub <= u); }
+  static LPC_HD V neg(const V& a) { return tr_neg(a); }
+  static LPC_HD V abs(const V& a) { return tr_abs(a); }
+  static LPC_HD V add(const V& a, const V& b) { return tr_add(a, b); }
+  static LPC_HD V sub(const V& a, const V& b) { return tr_sub(a, b); }
+  static LPC_HD V mul(const V& a, const V& b) { return tr_mul(a, b); }
+  static LPC_HD V ediv(const V& a, const V& b) { return tr_ediv(a, b); }
+  static LPC_HD V vmin(const V& a, const V& b) { return tr_min(a, b); }
+  static LPC_HD V vmax(const V& a, const V& b) { return tr_max(a, b); }
+  static LPC_HD V div(int k, const V& a, const V& b) { return tr_div(k, a, b); }
+  static LPC_HD V div_left(const V& u, const V& b) { return tr_div_left(u, b); }
+  static LPC_HD V div_right(int k, const V& u, const V& b, const V& r) { return tr_div_right(k, u, b, r); }
+  static LPC_HD V only_lb(const V& a) { return Itv(a.lb, LPC_INF); }
+  static LPC_HD V only_ub(const V& a) { return Itv(LPC_MINF, a.ub); }
+  // GroupAdd::rev_op's operand (terms.hpp:190-194): the crossed interval [-lb, -ub], so that all + it = all - t bound by bound
+  static LPC_HD V additive_inverse(const V& t) { return Itv(b_neg(t.lb), b_neg(t.ub)); }
+};
+struct UNb {
+  typedef u64 V;
+  static constexpr bool complemented = true;
+  static LPC_HD V from(const Itv& i) { return nb_range(i.lb, i.ub); }
+  static LPC_HD Itv itv(V a) { return nb_itv(a); }
+  static LPC_HD V range(int l, int u) { return nb_range(l, u); }
+  static LPC_HD V top() { return ~0ull; }
+  static LPC_HD V bot() { return 0ull; }
+  static LPC_HD int lo(V a) { return nb_itv(a).lb; }
+  static LPC_HD int hi(V a) { return nb_itv(a).ub; }
+  static LPC_HD bool is_bot(V a) { return a == 0; }
+  static LPC_HD void meet(V& a, V b) { a &= b; }
+  static LPC_HD V join(V a, V b) { return a | b; }
+  static LPC_HD V complement(V a) { return ~a; }
+  static LPC_HD bool same(V a, V b) { return a == b; }
+  static LPC_HD bool has0(V a) { return (a >> 1) & 1; }
+  static LPC_HD bool sub_of(V a, int l, int u) { return (a & ~nb_range(l, u)) == 0; }
+  static LPC_HD V neg(V a) { return a == 0 ? a : from(tr_neg(itv(a))); }
+  static LPC_HD V abs(V a) { return a == 0 ? a : from(tr_abs(itv(a))); }
+  static LPC_HD V add(V a, V b) { return (a == 0 || b == 0) ? 0 : from(tr_add(itv(a), itv(b))); }
+  static LPC_HD V sub(V a, V b) { return (a == 0 || b == 0) ? 0 : from(tr_sub(itv(a), itv(b))); }
+  static LPC_HD V mul(V a, V b) { return (a == 0 || b == 0) ? 0 : from(tr_mul(itv(a), itv(b))); }
+  static LPC_HD V ediv(V a, V b) { return (a == 0 || b == 0) ? 0 : from(tr_ediv(itv(a), itv(b))); }
+  static LPC_HD V vmin(V a, V b) { return (a == 0 || b == 0) ? 0 : from(tr_min(itv(a), itv(b))); }
+  static LPC_HD V vmax(V a, V b) { return (a == 0 || b == 0) ? 0 : from(tr_max(itv(a), itv(b))); }
+  static LPC_HD V div(int k, V a, V b) { return (a == 0 || b == 0) ? 0 : from(tr_div(k, itv(a), itv(b))); }
+  static LPC_HD V div_left(V u, V b) { return (u == 0 || b == 0) ? 0 : from(tr_div_left(itv(u), itv(b))); }
+  static LPC_HD V div_right(int k, V u, V b, V r) { return r == 0 ? r : from(tr_div_right(k, itv(u), itv(b), itv(r))); }
+  static LPC_HD V only_lb(V a) { return nb_range(lo(a), LPC_INF); }
+  static LPC_HD V only_ub(V a) { return nb_range(LPC_MINF, hi(a)); }
+  static LPC_HD V additive_inverse(V t) { return neg(t); }   // a set has no crossed form
+};
+
 // G::project (terms.hpp:182, 213, 235, 306)
-LPC_HD Itv tr_group(int k, const Itv& x, const Itv& y) {
+template <class U> LPC_HD typename U::V tr_group_u(int k, const typename U::V& x, const typename U::V& y) {
   switch(k) {
-    case T_ADD: return tr_add(x, y);
-    case T_SUB: return tr_sub(x, y);
-    case T_MUL: return tr_mul(x, y);
-    case T_MIN: return tr_min(x, y);
-    default: return tr_max(x, y);
+    case T_ADD: return U::add(x, y);
+    case T_SUB: return U::sub(x, y);
+    case T_MUL: return U::mul(x, y);
+    case T_MIN: return U::vmin(x, y);
+    default: return U::vmax(x, y);
   }
 }
 // G::left_residual(u, b) / right_residual(u, b) met into top (terms.hpp:196-202, 218-224, 249-257, 310-326)
-LPC_HD Itv tr_residual(int k, bool right, const Itv& u, const Itv& b) {
+template <class U> LPC_HD typename U::V tr_residual_u(int k, bool right, const typename U::V& u, const typename U::V& b) {
   switch(k) {
-    case T_ADD: return tr_sub(u, b);
-    case T_SUB: return right ? tr_sub(b, u) : tr_add(u, b);
-    case T_MUL: return (contains0(u) && contains0(b)) ? itv_top() : tr_ediv(u, b);
+    case T_ADD: return U::sub(u, b);
+    case T_SUB: return right ? U::sub(b, u) : U::add(u, b);
+    case T_MUL: return (U::has0(u) && U::has0(b)) ? U::top() : U::ediv(u, b);
     default: {   // GroupMinMax: disjoint from the other operand -> this operand IS the result; else only one side
-      Itv m = u;
-      m.meet(b);
-      if(m.is_bot()) return u;
-      return k == T_MIN ? Itv(u.lb, LPC_INF) : Itv(LPC_MINF, u.ub);
+      typename U::V m = u;
+      U::meet(m, b);
+      if(U::is_bot(m)) return u;
+      return k == T_MIN ? U::only_lb(u) : U::only_ub(u);
     }
   }
 }
 
 // ---- terms --------------------------------------------------------------------------------------------------------------
-template <int D> struct TreeTerm {
+template <class U, int D> struct TreeTerm {
+  typedef typename U::V V;
   // Term::project (terms.hpp:34, 69-71, 148-152, 399-405, 465-478); p is left after the term
-  template <class Acc> static LPC_NI Itv project(const Acc& a, const int*& p) {
+  template <class Acc> static LPC_NI V project(const Acc& a, const int*& p) {
     const int k = *p++;
     switch(k) {
-      case T_CONST: { const int c = *p++; return Itv(c, c); }
+      case T_CONST: { const int c = *p++; return U::range(c, c); }
       case T_VAR: return a.load(*p++);
-      case T_NEG: return tr_neg(TreeTerm<D - 1>::project(a, p));
-      case T_ABS: return tr_abs(TreeTerm<D - 1>::project(a, p));
+      case T_NEG: return U::neg(TreeTerm<U, D - 1>::project(a, p));
+      case T_ABS: return U::abs(TreeTerm<U, D - 1>::project(a, p));
       case T_NARY_ADD: case T_NARY_MUL: {
         const int n = *p++;
-        Itv accu = TreeTerm<D - 1>::project(a, p);
+        V accu = TreeTerm<U, D - 1>::project(a, p);
         for(int i = 1; i < n; ++i) {
-          const Itv ti = TreeTerm<D - 1>::project(a, p);
-          accu = k == T_NARY_ADD ? tr_add(accu, ti) : tr_mul(accu, ti);
+          const V ti = TreeTerm<U, D - 1>::project(a, p);
+          accu = k == T_NARY_ADD ? U::add(accu, ti) : U::mul(accu, ti);
         }
         return accu;
       }
       default: {
-        const Itv x = TreeTerm<D - 1>::project(a, p);
-        const Itv y = TreeTerm<D - 1>::project(a, p);
-        return tok_is_div(k) ? tr_div(k, x, y) : tr_group(k, x, y);
+        const V x = TreeTerm<U, D - 1>::project(a, p);
+        const V y = TreeTerm<U, D - 1>::project(a, p);
+        return tok_is_div(k) ? U::div(k, x, y) : tr_group_u<U>(k, x, y);
       }
     }
   }
   // Term::embed(u) (terms.hpp:33, 65-67, 142-146, 376-397, 480-499): bit0 = changed, bit1 = a variable became empty
-  template <class Acc> static LPC_NI int embed(Acc& a, const int*& p, const Itv u) {
+  template <class Acc> static LPC_NI int embed(Acc& a, const int*& p, const V u) {
     const int k = *p++;
     switch(k) {
       case T_CONST: ++p; return 0;
       case T_VAR: return a.embed(*p++, u);
-      case T_NEG: return TreeTerm<D - 1>::embed(a, p, tr_neg(u));
-      case T_ABS: return TreeTerm<D - 1>::embed(a, p, fjoin(u, tr_neg(u)));
+      case T_NEG: return TreeTerm<U, D - 1>::embed(a, p, U::neg(u));
+      case T_ABS: return TreeTerm<U, D - 1>::embed(a, p, U::join(u, U::neg(u)));
       case T_NARY_ADD: case T_NARY_MUL: {
         const int n = *p++;
         const int* q = p - 2;
-        const Itv all = project(a, q);   // once, before any operand moves (terms.hpp:486)
+        const V all = project(a, q);   // once, before any operand moves (terms.hpp:486)
         int f = 0;
-        const bool absorbed = k == T_NARY_MUL && all.lb == 0 && all.ub == 0;   // GroupMul::is_absorbing (:239-241, 487)
+        const bool absorbed = k == T_NARY_MUL && U::same(all, U::range(0, 0));   // GroupMul::is_absorbing (:239-241, 487)
         for(int i = 0; i < n; ++i) {
           if(absorbed) { p = tree_skip_term(p); continue; }
           const int* s = p;
-          const Itv ti = TreeTerm<D - 1>::project(a, s);
-          Itv res;
+          const V ti = TreeTerm<U, D - 1>::project(a, s);
+          V res;
           if(k == T_NARY_ADD) {
-            const Itv others(b_add(all.lb, b_neg(ti.lb)), b_add(all.ub, b_neg(ti.ub)));   // additive_inverse, :190-194
-            res = tr_sub(u, others);
+            const V others = U::add(all, U::additive_inverse(ti));   // GroupAdd::rev_op, :190-194
+            res = U::sub(u, others);                                 // left_residual, :196-198
           }
           else {
-            const Itv others = tr_ediv(all, ti);                                            // rev_op, :244-246
-            res = (contains0(u) && contains0(others)) ? itv_top() : tr_ediv(u, others);     // left_residual, :249-253
+            const V others = U::ediv(all, ti);                                              // rev_op, :244-246
+            res = (U::has0(u) && U::has0(others)) ? U::top() : U::ediv(u, others);          // left_residual, :249-253
           }
-          f |= TreeTerm<D - 1>::embed(a, p, res);
+          f |= TreeTerm<U, D - 1>::embed(a, p, res);
         }
         return f;
       }
@@ -300,56 +418,63 @@ template <int D> struct TreeTerm {
         const bool dv = tok_is_div(k);
         if(*px != T_CONST) {
           const int* s = py;
-          const Itv yt = TreeTerm<D - 1>::project(a, s);
+          const V yt = TreeTerm<U, D - 1>::project(a, s);
           s = px;
-          f |= TreeTerm<D - 1>::embed(a, s, dv ? tr_div_left(u, yt) : tr_residual(k, false, u, yt));
+          f |= TreeTerm<U, D - 1>::embed(a, s, dv ? U::div_left(u, yt) : tr_residual_u<U>(k, false, u, yt));
         }
         p = tree_skip_term(py);
         if(*py != T_CONST) {
           const int* s = px;
-          const Itv xt = TreeTerm<D - 1>::project(a, s);   // re-read: x may just have moved
-          Itv res;
-          if(dv) { s = py; res = tr_div_right(k, u, xt, TreeTerm<D - 1>::project(a, s)); }   // the divisor's own value (:389-392)
-          else res = tr_residual(k, true, u, xt);
+          const V xt = TreeTerm<U, D - 1>::project(a, s);   // re-read: x may just have moved
+          V res;
+          if(dv) { s = py; res = U::div_right(k, u, xt, TreeTerm<U, D - 1>::project(a, s)); }   // the divisor's own value (:389-392)
+          else res = tr_residual_u<U>(k, true, u, xt);
           s = py;
-          f |= TreeTerm<D - 1>::embed(a, s, res);
+          f |= TreeTerm<U, D - 1>::embed(a, s, res);
         }
         return f;
       }
     }
   }
 };
-template <> struct TreeTerm<0> {   // below the checked depth: never reached (tree_check)
-  template <class Acc> static LPC_HD Itv project(const Acc&, const int*& p) { p = tree_skip_term(p); return itv_top(); }
-  template <class Acc> static LPC_HD int embed(Acc&, const int*& p, const Itv) { p = tree_skip_term(p); return 0; }
+template <class U> struct TreeTerm<U, 0> {   // below the checked depth: never reached (tree_check)
+  typedef typename U::V V;
+  template <class Acc> static LPC_HD V project(const Acc&, const int*& p) { p = tree_skip_term(p); return U::top(); }
+  template <class Acc> static LPC_HD int embed(Acc&, const int*& p, const V) { p = tree_skip_term(p); return 0; }
 };
-typedef TreeTerm<PC_TREE_TERM_DEPTH> TreeTop;
 
 // ---- formulas -----------------------------------------------------------------------------------------------------------
-// Equality<true>::deduce, one direction: `other` loses the value of the singleton side (formula.hpp:645-652, 661-668)
-template <class Acc> LPC_HD int tree_shave(Acc& a, const int* other, const Itv& single) {
+// Equality<true>::deduce, one direction: `other` loses the value of the singleton side (formula.hpp:645-652, 661-668);
+// a complemented universe embeds the complement of the singleton (:640-644, 656-660)
+template <class U, class Acc> LPC_HD int tree_shave(Acc& a, const int* other, const typename U::V& single) {
+  typedef TreeTerm<U, PC_TREE_TERM_DEPTH> TreeTop;
   const int* s = other;
-  const Itv o = TreeTop::project(a, s);
-  Itv lo = o, hi = o;
-  lo.meet(Itv(b_add(single.lb, 1), LPC_INF));
-  hi.meet(Itv(LPC_MINF, b_sub(single.ub, 1)));
+  if(U::complemented) return TreeTop::embed(a, s, U::complement(single));
+  const typename U::V o = TreeTop::project(a, s);
+  typename U::V lo = o, hi = o;
+  U::meet(lo, U::range(b_add(U::lo(single), 1), LPC_INF));
+  U::meet(hi, U::range(LPC_MINF, b_sub(U::hi(single), 1)));
   s = other;
-  return TreeTop::embed(a, s, fjoin(lo, hi));
+  return TreeTop::embed(a, s, U::join(lo, hi));
 }
 
 // The comparisons (leaves of the connective nest). `neg` already folds the caller's negation into the node's own.
-template <class Acc> LPC_NI bool tree_cmp_ask(const Acc& a, int k, bool negated, const int*& p) {
-  const Itv x = TreeTop::project(a, p);
-  const Itv y = TreeTop::project(a, p);
+template <class U, class Acc> LPC_NI bool tree_cmp_ask(const Acc& a, int k, bool negated, const int*& p) {
+  typedef TreeTerm<U, PC_TREE_TERM_DEPTH> TreeTop;
+  typedef typename U::V V;
+  const V x = TreeTop::project(a, p);
+  const V y = TreeTop::project(a, p);
   if(k == F_LEQ || k == F_GT) {   // formula.hpp:757-771
     const bool neg = (k == F_GT) != negated;
-    return neg ? x.lb > y.ub : x.ub <= y.lb;
+    return neg ? U::lo(x) > U::hi(y) : U::hi(x) <= U::lo(y);
   }
   const bool neg = (k == F_NEQ) != negated;   // formula.hpp:616-631
-  if(neg) { Itv m = x; m.meet(y); return m.is_bot(); }
-  return tr_same(x, y) && x.lb == x.ub;
+  if(neg) { V m = x; U::meet(m, y); return U::is_bot(m); }
+  return U::same(x, y) && U::lo(x) == U::hi(x);
 }
-template <class Acc> LPC_NI int tree_cmp_deduce(Acc& a, int k, bool negated, const int*& p) {
+template <class U, class Acc> LPC_NI int tree_cmp_deduce(Acc& a, int k, bool negated, const int*& p) {
+  typedef TreeTerm<U, PC_TREE_TERM_DEPTH> TreeTop;
+  typedef typename U::V V;
   const int* pl = p;
   const int* pr = tree_skip_term(pl);
   p = tree_skip_term(pr);
@@ -358,70 +483,70 @@ template <class Acc> LPC_NI int tree_cmp_deduce(Acc& a, int k, bool negated, con
   int f = 0;
   if(k == F_LEQ || k == F_GT) {   // formula.hpp:773-807
     const bool neg = (k == F_GT) != negated;
-    if(neg) {   // l > r: l >= r.lb + 1, r <= l.ub - 1
-      if(!lconst) { s = pr; const Itv y = TreeTop::project(a, s); s = pl; f = TreeTop::embed(a, s, Itv(b_add(y.lb, 1), LPC_INF)); }
-      if(!rconst) { s = pl; const Itv x = TreeTop::project(a, s); s = pr; f |= TreeTop::embed(a, s, Itv(LPC_MINF, b_sub(x.ub, 1))); }
+    if(neg) {   // l > r: l >= (what is left of r above its lower bound).lb, r <= (what is left of l below its upper bound).ub
+      if(!lconst) { s = pr; V y = TreeTop::project(a, s); U::meet(y, U::range(b_add(U::lo(y), 1), LPC_INF)); s = pl; f = TreeTop::embed(a, s, U::range(U::lo(y), LPC_INF)); }
+      if(!rconst) { s = pl; V x = TreeTop::project(a, s); U::meet(x, U::range(LPC_MINF, b_sub(U::hi(x), 1))); s = pr; f |= TreeTop::embed(a, s, U::range(LPC_MINF, U::hi(x))); }
     }
     else {      // l <= r
-      if(!lconst) { s = pr; const Itv y = TreeTop::project(a, s); s = pl; f |= TreeTop::embed(a, s, Itv(LPC_MINF, y.ub)); }
+      if(!lconst) { s = pr; const V y = TreeTop::project(a, s); s = pl; f |= TreeTop::embed(a, s, U::range(LPC_MINF, U::hi(y))); }
       if(!rconst) {   // formula.hpp:803 ASSIGNS has_changed here: the left side's change bit is lost, its bot bit is not
-        s = pl; const Itv x = TreeTop::project(a, s); s = pr;
-        f = (f & 2) | TreeTop::embed(a, s, Itv(x.lb, LPC_INF));
+        s = pl; const V x = TreeTop::project(a, s); s = pr;
+        f = (f & 2) | TreeTop::embed(a, s, U::range(U::lo(x), LPC_INF));
       }
     }
     return f;
   }
   const bool neg = (k == F_NEQ) != negated;   // formula.hpp:633-683
   if(neg) {
-    if(!rconst) { s = pl; const Itv x = TreeTop::project(a, s); if(x.lb == x.ub) return tree_shave(a, pr, x); }
-    if(!lconst) { s = pr; const Itv y = TreeTop::project(a, s); if(y.lb == y.ub) return tree_shave(a, pl, y); }
+    if(!rconst) { s = pl; const V x = TreeTop::project(a, s); if(U::lo(x) == U::hi(x)) return tree_shave<U>(a, pr, x); }
+    if(!lconst) { s = pr; const V y = TreeTop::project(a, s); if(U::lo(y) == U::hi(y)) return tree_shave<U>(a, pl, y); }
     return 0;
   }
-  if(!rconst) { s = pl; const Itv x = TreeTop::project(a, s); s = pr; f = TreeTop::embed(a, s, x); }
-  if(!lconst) { s = pr; const Itv y = TreeTop::project(a, s); s = pl; f |= TreeTop::embed(a, s, y); }
+  if(!rconst) { s = pl; const V x = TreeTop::project(a, s); s = pr; f = TreeTop::embed(a, s, x); }
+  if(!lconst) { s = pr; const V y = TreeTop::project(a, s); s = pl; f |= TreeTop::embed(a, s, y); }
   return f;
 }
 
 // AbstractElement (formula.hpp:14-77): ask / nask = the store's ask of the element / of its negation, deduce /
 // contradeduce = the store's deduce of them. Over an interval store `v != c` has an ask (c outside the domain) but no
-// tell (AbstractElement3-4, pc_test.cpp:738-764).
+// tell (AbstractElement3-4, pc_test.cpp:738-764); a complemented universe tells the complement of {c}.
 LPC_HD void tree_ae_norm(int& op, int& c, bool negated) {
   if(!negated) return;
   if(op == AE_LEQ) { op = AE_GEQ; c = b_add(c, 1); }
   else if(op == AE_GEQ) { op = AE_LEQ; c = b_sub(c, 1); }
   else op = op == AE_EQ ? AE_NEQ : AE_EQ;
 }
-LPC_HD Itv tree_ae_itv(int op, int c) { return op == AE_LEQ ? Itv(LPC_MINF, c) : op == AE_GEQ ? Itv(c, LPC_INF) : Itv(c, c); }
-template <class Acc> LPC_HD bool tree_ae_ask(const Acc& a, int op, int v, int c, bool negated) {
+template <class U, class Acc> LPC_HD bool tree_ae_ask(const Acc& a, int op, int v, int c, bool negated) {
   tree_ae_norm(op, c, negated);
-  const Itv d = a.load(v);
-  if(op == AE_NEQ) return d.is_bot() || c < d.lb || c > d.ub;
-  const Itv want = tree_ae_itv(op, c);
-  return d.is_bot() || (d.lb >= want.lb && d.ub <= want.ub);
+  const typename U::V d = a.load(v);
+  if(op == AE_NEQ) { typename U::V m = d; U::meet(m, U::range(c, c)); return U::is_bot(m); }
+  return op == AE_LEQ ? U::sub_of(d, LPC_MINF, c) : op == AE_GEQ ? U::sub_of(d, c, LPC_INF) : U::sub_of(d, c, c);
 }
-template <class Acc> LPC_HD int tree_ae_tell(Acc& a, int op, int v, int c, bool negated) {
+template <class U, class Acc> LPC_HD int tree_ae_tell(Acc& a, int op, int v, int c, bool negated) {
   tree_ae_norm(op, c, negated);
-  return op == AE_NEQ ? 0 : a.embed(v, tree_ae_itv(op, c));
+  if(op == AE_NEQ) return U::complemented ? a.embed(v, U::complement(U::range(c, c))) : 0;
+  return a.embed(v, op == AE_LEQ ? U::range(LPC_MINF, c) : op == AE_GEQ ? U::range(c, LPC_INF) : U::range(c, c));
 }
 
-template <int D> struct TreeForm {
+template <class U, int D> struct TreeForm {
   // ask (negated = false) / nask (negated = true); p is left after the formula
   template <class Acc> static LPC_NI bool ask(const Acc& a, const int*& p, bool negated) {
     const int k = *p++;
     if(k == F_VARLIT || k == F_NVARLIT) {   // formula.hpp:97-110, 126-135
       const bool neg = (k == F_NVARLIT) != negated;
-      return lit_ask(neg, a.load(*p++));
+      const typename U::V t = a.load(*p++);
+      return neg ? U::sub_of(t, 0, 0) : !U::has0(t);
     }
-    if(k == F_AE) { const int op = p[0], v = p[1], c = p[2]; p += 3; return tree_ae_ask(a, op, v, c, negated); }
+    if(k == F_AE) { const int op = p[0], v = p[1], c = p[2]; p += 3; return tree_ae_ask<U>(a, op, v, c, negated); }
     // formula.hpp:182-183, 220-221: true is entailed, false is refuted (their a.is_bot() halves only hold on a failed
     // store, where the fixpoint has stopped)
     if(k == F_TRUE || k == F_FALSE) return (k == F_TRUE) != negated;
-    if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_ask(a, k, negated, p);
+    if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_ask<U>(a, k, negated, p);
     const int* pf = p;
     const int* pg = tree_skip_formula(pf);
     p = tree_skip_formula(pg);
     const int *s = pf, *t = pg;
-    typedef TreeForm<D - 1> S;
+    typedef TreeForm<U, D - 1> S;
     switch(k) {
       case F_AND:     // formula.hpp:268-274
         if(negated) { if(S::ask(a, s, true)) return true; return S::ask(a, t, true); }
@@ -450,16 +575,16 @@ template <int D> struct TreeForm {
     const int k = *p++;
     if(k == F_VARLIT || k == F_NVARLIT) {   // formula.hpp:112-120, 140-149
       const bool neg = (k == F_NVARLIT) != negated;
-      return a.embed(*p++, neg ? Itv(0, 0) : Itv(1, 1));
+      return a.embed(*p++, neg ? U::range(0, 0) : U::range(1, 1));
     }
-    if(k == F_AE) { const int op = p[0], v = p[1], c = p[2]; p += 3; return tree_ae_tell(a, op, v, c, negated); }
+    if(k == F_AE) { const int op = p[0], v = p[1], c = p[2]; p += 3; return tree_ae_tell<U>(a, op, v, c, negated); }
     // formula.hpp:185-193, 222-228: deducing false / contradeducing true is a.meet_bot()
-    if(k == F_TRUE || k == F_FALSE) return ((k == F_FALSE) != negated) ? a.embed(0, itv_bot()) : 0;
-    if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_deduce(a, k, negated, p);
+    if(k == F_TRUE || k == F_FALSE) return ((k == F_FALSE) != negated) ? a.embed(0, U::bot()) : 0;
+    if(k >= F_LEQ && k <= F_NEQ) return tree_cmp_deduce<U>(a, k, negated, p);
     const int* pf = p;
     const int* pg = tree_skip_formula(pf);
     p = tree_skip_formula(pg);
-    typedef TreeForm<D - 1> S;
+    typedef TreeForm<U, D - 1> S;
     auto ASK = [&](const int* q, bool n) { return S::ask(a, q, n); };
     auto DED = [&](const int* q, bool n) { return S::deduce(a, q, n); };
     switch(k) {
@@ -489,19 +614,20 @@ template <int D> struct TreeForm {
     }
   }
 };
-template <> struct TreeForm<0> {
+template <class U> struct TreeForm<U, 0> {
   template <class Acc> static LPC_HD bool ask(const Acc&, const int*& p, bool) { p = tree_skip_formula(p); return false; }
   template <class Acc> static LPC_HD int deduce(Acc&, const int*& p, bool) { p = tree_skip_formula(p); return 0; }
 };
 
-// PC::deduce(i) / PC::ask(i) (pc.hpp:661-680) for one LPC_PC_TREE propagator whose stream starts at `words`.
+// PC::deduce(i) / PC::ask(i) (pc.hpp:661-680) for one LPC_PC_TREE propagator whose stream starts at `words`, over the
+// universe of the accessor.
 template <class Acc> LPC_HD int pc_tree_deduce_impl(Acc& a, const int* words) {
   const int* p = words;
-  return TreeForm<PC_TREE_FORM_DEPTH>::deduce(a, p, false);
+  return TreeForm<typename Acc::Univ, PC_TREE_FORM_DEPTH>::deduce(a, p, false);
 }
 template <class Acc> LPC_HD bool pc_tree_ask_impl(const Acc& a, const int* words) {
   const int* p = words;
-  return TreeForm<PC_TREE_FORM_DEPTH>::ask(a, p, false);
+  return TreeForm<typename Acc::Univ, PC_TREE_FORM_DEPTH>::ask(a, p, false);
 }
 #ifdef LPC_HOST_HARNESS
 template <class Acc> LPC_HD int pc_tree_deduce(Acc& a, const int* words) { return pc_tree_deduce_impl(a, words); }

@@ -502,7 +502,6 @@ private:
     return (h0 && h1 && std::max(h0, h1) <= TREE_TERM_DEPTH) ? 1 : 0;
   }
   bool interpret_tree(const TF& f, VarEnv& env, tell_type& out, std::string* why) const {
-    if(bitset) return fail(why, "The shape of this formula is not supported.");   // tree propagators compute on intervals
     std::vector<int> w;
     prop_type p;
     const int h = tree_formula(f, env, w, p.ref_kind, p.length);
@@ -583,7 +582,7 @@ private:
       return fail(why, "The shape of this formula is not supported.");
     }
     if(lin_cmp(f, env, p)) {
-      if(bitset) return fail(why, "Linear sums over a bitset store are not supported (NBitset arithmetic is unpinned).");
+      if(bitset) return fail(why, "kept as a tree over a bitset store");   // interpret_formula falls back to interpret_tree
       out.props.push_back(p); return true;
     }
     return fail(why, "The shape of this formula is not supported.");

@@ -280,11 +280,11 @@ static void UnsupportedShapesAreRefused() {
   EXPECT_EQ(why, std::string("The shape of this formula is not supported."));
   EXPECT_FALSE(ipc.interpret_tell(TF::in(V("x"), {1, 3}), m.env, tell, &why));                         // `in` needs a bitset store
   EXPECT_EQ((int)tell.props.size(), 3);
+  // sums over a bitset store are walked as trees over the NBitset universe (arithmetic through the interval hull)
   Model<BitPC> mb;
-  mb.var("x").var("y");
-  BitPC bpc(pty, std::make_shared<BitVStore>(2));
-  BitPC::tell_type btell;
-  EXPECT_FALSE(bpc.interpret_tell(bin(bin(V("x"), ADD, V("y")), LEQ, K(3)), mb.env, btell, &why));    // sums over bitsets
+  mb.var("x", NBit(0, 5)).var("y", NBit::from_set({0, 2, 5})).c(bin(bin(V("x"), ADD, V("y")), LEQ, K(3)));
+  BitPC bpc = create_and_interpret_and_tell(mb);
+  deduce_and_test(bpc, 1, {NBit(0, 5), NBit::from_set({0, 2, 5})}, {NBit(0, 3), NBit::from_set({0, 2})}, false);
 }
 
 // The goldens whose formulas have no flat kind: the tree goes to the device as it is (LPC_PC_TREE).

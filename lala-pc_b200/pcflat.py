@@ -33,9 +33,14 @@ class Unsupported(ValueError):
     pass
 
 
-def _linear_terms(t):
-    """A term that is a variable, coef * variable, or an n-ary sum of those -> [(coef, var)]."""
+def _linear_terms(t, nb=False):
+    """A term that is a variable, coef * variable, or an n-ary sum of those -> [(coef, var)].
+    nb: the table is for NBitset stores. There -x and (-1) * x are different sets (the product goes through the constant's
+    image in the universe, which folds every negative value into one bit), so Unary<Neg> and Binary<Sub> are not folded
+    into a coefficient of -1: such formulas keep their tree."""
     op = t[0]
+    if nb and op in ("neg", "sub"):
+        raise Unsupported("Unary<Neg> / Binary<Sub> keep their tree over NBitset stores")
     if op == "var":
         return [(1, int(t[1]))]
     if op == "neg" and t[1][0] == "var":   # Unary<Neg>(Variable): the bounds of -1 * x (terms.hpp:87-102)
@@ -43,12 +48,12 @@ def _linear_terms(t):
     if op == "mul" and t[1][0] == "const" and t[2][0] == "var" and int(t[1][1]) != 0:
         return [(int(t[1][1]), int(t[2][1]))]
     if op == "sub":   # Binary<GroupSub>(leaf, Variable): same residuals as leaf + (-1) * y (terms.hpp:209-229)
-        a = _linear_terms(t[1])
+        a = _linear_terms(t[1], nb)
         if len(a) != 1 or t[1][0] in ("add", "sum", "sub") or t[2][0] != "var":
             raise Unsupported("only leaf - variable differences are flattened (a scaled right operand rounds differently)")
         return a + [(-1, int(t[2][1]))]
     if op == "add":   # Binary<GroupAdd> of two leaf terms
-        a, b = _linear_terms(t[1]), _linear_terms(t[2])
+        a, b = _linear_terms(t[1], nb), _linear_terms(t[2], nb)
         if len(a) != 1 or len(b) != 1 or t[1][0] in ("add", "sum", "sub") or t[2][0] in ("add", "sum", "sub"):
             raise Unsupported("nested binary sums are not flattened (their residuals differ from a flat sum)")
         return a + b
@@ -59,14 +64,14 @@ def _linear_terms(t):
         for s in t[1:]:
             if s[0] in ("sum", "add", "sub"):
                 raise Unsupported("nested n-ary sums are not flattened (their residuals differ from a flat sum)")
-            out += _linear_terms(s)
+            out += _linear_terms(s, nb)
         return out
     raise Unsupported(f"term {op} is not linear")
 
 
-def _lin_le(f):
+def _lin_le(f, nb=False):
     if f[0] == "le" and f[2][0] == "const":
-        return _linear_terms(f[1]), int(f[2][1])
+        return _linear_terms(f[1], nb), int(f[2][1])
     raise Unsupported("not a linear inequality with a constant right-hand side")
 
 
@@ -83,22 +88,22 @@ def _clause_literals(f):
             raise Unsupported("not a right-nested clause of literals")
 
 
-def flatten_one(f):
-    """-> (kind, [(coef, var)], rhs, bvar)"""
+def flatten_one(f, nb=False):
+    """-> (kind, [(coef, var)], rhs, bvar); nb: for NBitset stores (see _linear_terms)"""
     op = f[0]
     if op == "le" and f[1][0] == "const" and f[2][0] != "const":   # k <= term
-        return PC_LIN_GE, _linear_terms(f[2]), int(f[1][1]), -1
+        return PC_LIN_GE, _linear_terms(f[2], nb), int(f[1][1]), -1
     if op == "le":
-        terms, k = _lin_le(f)
+        terms, k = _lin_le(f, nb)
         return PC_LIN_LE, terms, k, -1
     if op == "gt" and f[2][0] == "const":
-        return PC_LIN_GT, _linear_terms(f[1]), int(f[2][1]), -1
+        return PC_LIN_GT, _linear_terms(f[1], nb), int(f[2][1]), -1
     if op == "eq" and f[2][0] == "const" and f[1][0] != "abs":
-        return PC_LIN_EQ, _linear_terms(f[1]), int(f[2][1]), -1
+        return PC_LIN_EQ, _linear_terms(f[1], nb), int(f[2][1]), -1
     if op == "eq" and f[2][0] == "var" and f[1][0] in ("add", "sub", "sum", "mul", "neg"):
-        return PC_LIN_EQ_VAR, _linear_terms(f[1]), 0, int(f[2][1])
+        return PC_LIN_EQ_VAR, _linear_terms(f[1], nb), 0, int(f[2][1])
     if op == "equiv" and f[1][0] == "lit" and f[2][0] == "le":
-        terms, k = _lin_le(f[2])
+        terms, k = _lin_le(f[2], nb)
         return PC_REIF_LIN_LE, terms, k, int(f[1][1])
     if op == "eq" and f[1][0] == "var" and f[2][0] == "var":
         return PC_EQ, [(1, int(f[1][1])), (1, int(f[2][1]))], 0, -1
@@ -165,13 +170,14 @@ def encode_tree(f):
     return PC_TREE, list(zip(words[0::2], words[1::2])), 0, -1
 
 
-def flatten(formulas, tree=True):
+def flatten(formulas, tree=True, bitset=False):
     """List of formula trees -> (props [n,5] int32, terms [m,2] int32). Shapes without a flat kind become LPC_PC_TREE
-    propagators when `tree` is set, else `Unsupported` is raised."""
+    propagators when `tree` is set, else `Unsupported` is raised. bitset: the table is for NBitset stores (Unary<Neg> and
+    Binary<Sub> are not folded into coefficients, see _linear_terms)."""
     props, terms = [], []
     for f in formulas:
         try:
-            kind, ts, rhs, bvar = flatten_one(f)
+            kind, ts, rhs, bvar = flatten_one(f, bitset)
         except Unsupported:
             if not tree:
                 raise

@@ -67,6 +67,7 @@ void devhost_exhaustive(int sig, int lo, int hi, int* out) {
 
 // ---- PC: the flat propagators of pc_device.cuh on the host --------------------------------------------------------
 struct HostAcc {
+  typedef lpc::UItv Univ;
   int* d;
   mutable int seen_bot;
   int touched;
@@ -109,8 +110,10 @@ int devhost_pc_ask(const int* props, long long i, const int* terms, const int* l
 
 // ---- the same over NBitset<64> cells ---------------------------------------------------------------------------------
 struct HostBitAcc {
+  typedef lpc::UNb Univ;
   unsigned long long* d;
   mutable int seen_bot;
+  int touched;
   u64 load(int v) const { if(d[v] == 0) seen_bot = 1; return d[v]; }
   int embed(int v, u64 u) {
     const u64 old = d[v];
@@ -118,11 +121,17 @@ struct HostBitAcc {
     const u64 nw = old & u;
     if(nw == old) return 0;
     d[v] = nw;
+    touched |= 1;
     return nw == 0 ? 3 : 1;
   }
 };
-int devhost_pc_fixpoint_bits(const int* props, long long n, const int* terms, unsigned long long* cells, int nvars, int* is_bot,
-                             int* has_changed) {
+// linear kinds are handed to the tree interpreter exactly as the library's table builder does (pc_bits_view)
+int devhost_pc_fixpoint_bits(const int* props_in, long long n, const int* terms_in, long long n_terms, unsigned long long* cells, int nvars,
+                             int* is_bot, int* has_changed) {
+  std::vector<int> vp; std::vector<int2> vt;
+  lpc::pc_bits_view(props_in, n, reinterpret_cast<const int2*>(terms_in), n_terms, vp, vt);
+  const int* props = vp.data();
+  const int* terms = reinterpret_cast<const int*>(vt.data());
   int bot = 0, any = 0;
   for(int v = 0; v < nvars; ++v) bot |= cells[v] == 0;
   int sweeps = 0, changed = 1;
@@ -131,9 +140,9 @@ int devhost_pc_fixpoint_bits(const int* props, long long n, const int* terms, un
     for(long long i = 0; i < n; ++i) {
       const int* p = props + 5 * i;
       int4 h = make_int4(p[0] | (p[2] << 8), p[1], p[3], p[4]);
-      HostBitAcc acc{cells, 0};
+      HostBitAcc acc{cells, 0, 0};
       int f = pc_deduce_bits(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
-      changed |= f & 1; bot |= ((f >> 1) & 1) | acc.seen_bot;
+      changed |= (f | acc.touched) & 1; bot |= ((f >> 1) & 1) | acc.seen_bot;
     }
     any |= changed;
     ++sweeps;
@@ -141,10 +150,21 @@ int devhost_pc_fixpoint_bits(const int* props, long long n, const int* terms, un
   *is_bot = bot; *has_changed = any;
   return sweeps;
 }
-int devhost_pc_ask_bits(const int* props, long long i, const int* terms, const unsigned long long* cells) {
-  const int* p = props + 5 * i;
+int devhost_pc_ask_bits(const int* props_in, long long n, long long i, const int* terms_in, long long n_terms, const unsigned long long* cells) {
+  std::vector<int> vp; std::vector<int2> vt;
+  lpc::pc_bits_view(props_in, n, reinterpret_cast<const int2*>(terms_in), n_terms, vp, vt);
+  const int* terms = reinterpret_cast<const int*>(vt.data());
+  const int* p = vp.data() + 5 * i;
   int4 h = make_int4(p[0] | (p[2] << 8), p[1], p[3], p[4]);
-  HostBitAcc acc{const_cast<unsigned long long*>(cells), 0};
+  HostBitAcc acc{const_cast<unsigned long long*>(cells), 0, 0};
   return pc_ask_bits(acc, h, reinterpret_cast<const int2*>(terms) + p[1]);
+}
+// The table builder's rewriting of a flat linear propagator as a formula stream (bitset stores): words out, count returned.
+int devhost_linear_tree_words(int kind, const int* terms, int n, int rhs, int bvar, int* out, int cap) {
+  std::vector<int> w;
+  lpc::pc_linear_tree_words(kind, reinterpret_cast<const int2*>(terms), n, rhs, bvar, w);
+  if((int)w.size() > cap) return -1;
+  for(size_t i = 0; i < w.size(); ++i) out[i] = w[i];
+  return (int)w.size();
 }
 }

@@ -8,7 +8,7 @@ import pytest
 from conftest import load_golden
 from oracle import oracle as O
 from test_devhost import devhost  # noqa: F401  (fixture: builds tests/native/libdevhost.so)
-from test_gpu_pc import booleanize, random_pc, random_tree_pc, to_tree
+from test_gpu_pc import booleanize, literal_vars, random_pc, random_tree_pc, to_tree
 
 
 def host_fixpoint(D, props, terms, store):
@@ -127,13 +127,14 @@ def host_fixpoint_bits(D, props, terms, cells):
     t = np.ascontiguousarray(terms if len(terms) else np.zeros((1, 2)), dtype=np.int32)
     bot, ch = ctypes.c_int(0), ctypes.c_int(0)
     D.devhost_pc_fixpoint_bits(p.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(len(props)), t.ctypes.data_as(ctypes.c_void_p),
-                               s.ctypes.data_as(ctypes.c_void_p), len(s), ctypes.byref(bot), ctypes.byref(ch))
+                               ctypes.c_longlong(len(terms)), s.ctypes.data_as(ctypes.c_void_p), len(s), ctypes.byref(bot),
+                               ctypes.byref(ch))
     return s, bool(bot.value), bool(ch.value)
 
 
 def compare_bits(D, formulas, cells, label):
     from lala_pc_b200 import pcflat
-    props, terms = pcflat.flatten(formulas)
+    props, terms = pcflat.flatten(formulas, bitset=True)
     m = O.PCModel(formulas)
     want, st = m.fixpoint_bits(cells)
     got, bot, ch = host_fixpoint_bits(D, props, terms, cells)
@@ -145,7 +146,8 @@ def compare_bits(D, formulas, cells, label):
         p = np.ascontiguousarray(props, dtype=np.int32)
         t = np.ascontiguousarray(terms if len(terms) else np.zeros((1, 2)), dtype=np.int32)
         w = np.ascontiguousarray(want)
-        gb = [D.devhost_pc_ask_bits(p.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(i), t.ctypes.data_as(ctypes.c_void_p),
+        gb = [D.devhost_pc_ask_bits(p.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(len(p)), ctypes.c_longlong(i),
+                                    t.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(len(terms)),
                                     w.ctypes.data_as(ctypes.c_void_p)) for i in range(len(p))]
         assert gb == bits.tolist(), label
     return got, st
@@ -199,3 +201,60 @@ def test_bitset_config5_and_random(devhost):
         _, st = compare_bits(devhost, random_bits_pc(rng, nvars), random_cells(rng, nvars), f"random bits {trial}")
         n_ok += not st.is_bot
     assert n_ok >= 100
+
+
+# ---- NBitset arithmetic: sums and general trees over bitset cells (PARITY UNPINNED upstream, see oracle/pc_oracle.cpp) -----
+def test_linear_props_as_tree_streams(devhost):
+    """The table builder's rewriting of a flat linear propagator (pc_linear_tree_words) == the stream of the formula tree
+    the propagator stands for (pcflat.to_tree -> encode_tree)."""
+    from lala_pc_b200 import pcflat
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        kind = int(rng.choice([1, 2, 7, 8, 9, 10]))
+        n = int(rng.integers(1, 7))
+        ts = [(int(rng.choice([1, 1, 2, 3, -1, -4])), int(rng.integers(0, 9))) for _ in range(n)]
+        if kind == 10 and n == 1 and ts[0][0] == 1:
+            ts = [(2, ts[0][1])]
+        rhs, bvar = int(rng.integers(-20, 60)), int(rng.integers(0, 9))
+        _, pairs, _, _ = pcflat.encode_tree(pcflat.to_tree(kind, ts, rhs, bvar))
+        want = [w for pr in pairs for w in pr]
+        t = np.array(ts, dtype=np.int32)
+        out = np.zeros(64, dtype=np.int32)
+        k = devhost.devhost_linear_tree_words(kind, t.ctypes.data_as(ctypes.c_void_p), n, rhs, bvar, out.ctypes.data_as(ctypes.c_void_p), 64)
+        assert out[:k].tolist() == want, (kind, ts, rhs, bvar)
+
+
+def small_cells(rng, nvars):
+    """Domains inside the exact range of the universe, some with holes."""
+    cells = np.zeros(nvars, dtype=np.uint64)
+    for i in range(nvars):
+        r = rng.random()
+        if r < 0.3:
+            cells[i] = O.nbit(0, 1)
+        elif r < 0.75:
+            a, b = sorted(int(x) for x in rng.integers(-1, 20, 2))
+            cells[i] = O.nbit(a, b)
+        else:
+            cells[i] = O.nbit_from_set(int(x) for x in rng.integers(0, 24, int(rng.integers(1, 5))))
+    return cells
+
+
+def test_bitset_linear_and_tree_networks(devhost):
+    """Sums (every linear kind), general trees and the four flat shapes mixed, over NBitset cells: the device rules on the
+    host against the tree-walking checker's NBitset universe."""
+    rng = np.random.default_rng(23)
+    n_ok = n_lin = 0
+    for trial in range(500):
+        nvars = int(rng.integers(4, 9))
+        forms = random_pc(rng, nvars)
+        if trial % 2:
+            forms += random_tree_pc(rng, nvars)[:2]
+        if trial % 5 == 0:
+            forms += random_bits_pc(rng, nvars)[:2]
+        cells = small_cells(rng, nvars) if trial % 3 else random_cells(rng, nvars)
+        for v in literal_vars(forms):
+            cells[v] = O.nbit(0, 1)
+        n_lin += sum(1 for f in forms if f[0] in ("le", "gt", "eq", "equiv"))
+        _, st = compare_bits(devhost, forms, cells, f"bits linear/tree {trial}")
+        n_ok += not st.is_bot
+    assert n_ok >= 100 and n_lin >= 500, (n_ok, n_lin)

@@ -369,7 +369,7 @@ def test_errors(L):
 # ---- bitset stores (VStore<NBitset<64>>, tests/pc_bitset_test.cpp) -------------------------------------------------
 def check_parity_bits(L, O, formulas, cells, nvars, label=""):
     from lala_pc_b200 import pcflat
-    props, terms = pcflat.flatten(formulas)
+    props, terms = pcflat.flatten(formulas, bitset=True)
     m = O.PCModel(formulas)
     want, st = m.fixpoint_bits(cells)
     t = L.PcTable(props, terms, nvars)
@@ -406,7 +406,7 @@ def test_bitset_deduce_one_and_random(L, O):
         _, r, st = check_parity_bits(L, O, forms, cells, nvars, f"random bits {trial}")
         n_ok += not st.is_bot
         if trial < 25:   # PC::deduce(i) step by step
-            props, terms = pcflat.flatten(forms)
+            props, terms = pcflat.flatten(forms, bitset=True)
             m = O.PCModel(forms)
             t = L.PcTable(props, terms, nvars)
             s = L.Store(nvars=nvars)
@@ -463,9 +463,67 @@ def test_config5_interval_vs_bitset(L, O, W, scale):
     assert bool(rt.is_bot) == bool(stt.is_bot)
 
 
-def test_bitset_refuses_linear_kinds(L):
-    t = L.PcTable(np.array([[1, 0, 2, 5, -1]], dtype=np.int32), np.array([[1, 0], [1, 1]], dtype=np.int32), 2)
-    s = L.Store(nvars=2)
-    s.write_bits(np.array([7, 7], dtype=np.uint64))
-    with pytest.raises(L.LpcError):
-        t.fixpoint(s, bitset=True)
+def test_bitset_linear_and_tree_networks(L, O):
+    """NBitset arithmetic: sums of every linear kind, general trees and the four flat shapes in one
+    table over a bitset store - the table builder hands the linear kinds to the tree interpreter over the NBitset universe
+    (pc_tree.cuh, UNb). Compared with the tree-walking checker's NBitset universe (parity unpinned upstream beyond the
+    pc_bitset_test.cpp goldens); fixpoint, ask bits and PC::deduce(i) step by step. The same table still runs on an
+    interval store."""
+    from lala_pc_b200 import pcflat
+    from test_devhost_pc import random_bits_pc, random_cells, small_cells
+    rng = np.random.default_rng(29)
+    n_ok = n_lin = 0
+    for trial in range(160):
+        nvars = int(rng.integers(4, 9))
+        forms = random_pc(rng, nvars)
+        if trial % 2:
+            forms += random_tree_pc(rng, nvars)[:2]
+        if trial % 5 == 0:
+            forms += random_bits_pc(rng, nvars)[:2]
+        cells = small_cells(rng, nvars) if trial % 3 else random_cells(rng, nvars)
+        for v in literal_vars(forms):
+            cells[v] = O.nbit(0, 1)
+        props, terms = pcflat.flatten(forms, bitset=True)
+        n_lin += int(np.isin(props[:, 0], (1, 2, 7, 8, 9, 10)).sum())
+        _, r, st = check_parity_bits(L, O, forms, cells, nvars, f"bits linear/tree {trial}")
+        n_ok += not st.is_bot
+        if trial < 30:
+            m = O.PCModel(forms)
+            t = L.PcTable(props, terms, nvars)
+            s = L.Store(nvars=nvars)
+            s.write_bits(cells)
+            cur, bot = cells, False
+            for i in range(len(forms)):
+                was_bot = bot
+                cur, changed, bot = m.deduce_bits(i, cur, bot)
+                got = t.deduce(s, i, bitset=True)
+                if not was_bot:   # on a failed store the reference's `false` node reports no change (its flag is set already)
+                    assert got == changed, (trial, i, forms[i])
+                if not bot:
+                    assert np.array_equal(s.read_bits(), cur), (trial, i, forms[i])
+    assert n_ok >= 30 and n_lin >= 150, (n_ok, n_lin)
+    # one table, both universes
+    forms = [("le", ("sum", ("var", 0), ("mul", ("const", 2), ("var", 1)), ("var", 2)), ("const", 9)), ("ne", ("var", 0), ("var", 1))]
+    props, terms = pcflat.flatten(forms, bitset=True)
+    t = L.PcTable(props, terms, 3)
+    store = np.array([[0, 9], [3, 3], [2, 8]], dtype=np.int32)
+    si = L.Store(values=store)
+    t.fixpoint(si)
+    want_i, _ = O.PCModel(forms).fixpoint(store)
+    assert np.array_equal(si.read(), want_i)
+    sb = L.Store(nvars=3)
+    sb.write_bits(L.nbit_from_intervals(store))
+    t.fixpoint(sb, bitset=True)
+    want_b, _ = O.PCModel(forms).fixpoint_bits(L.nbit_from_intervals(store))
+    assert np.array_equal(sb.read_bits(), want_b)
+
+
+def test_bitset_config3_shape(L, O, W):
+    """BASELINE.json config 3's propagators (sums and reified sums) over a bitset store, domains inside the universe."""
+    net = W.config3(0.02)
+    store = np.stack([np.clip(net.store[:, 0], 0, 40), np.clip(net.store[:, 1], 0, 40)], axis=1).astype(np.int32)
+    store[store[:, 0] > store[:, 1]] = (0, 40)
+    cells = L.nbit_from_intervals(store)
+    forms = net.formulas()
+    _, r, st = check_parity_bits(L, O, forms, cells, net.nvars, "config3 over bitsets")
+    assert r.sweeps >= 1
