@@ -232,7 +232,9 @@ void* lpc_batch_payload_device_ptr(lpc_batch* b, int32_t* n_int64);
  * is_extractable / extract (pir.hpp:873-898) for the whole batch. In LPC_MODE_AUTO (default) the propagators that
  * PIR::ask (pir.hpp:417-438) already entails on the root are dropped from the table first (what deinterpret's
  * remove_entailed does, pir.hpp:912-925): every subproblem is a tightening of the root, so they stay entailed and can
- * never change a store. LPC_MODE_SWEEP keeps them (every sweep evaluates every propagator, the reference's work unit).
+ * never change a store; and when the root is itself a common fixpoint of the table, the first sweep of a subproblem
+ * evaluates only the propagators that mention a decision variable (nothing else can move: every other operand is as in
+ * the root). LPC_MODE_SWEEP does neither (every sweep evaluates every propagator, the reference's work unit).
  * The model must fit the shared memory of an SM (<= 8191 variables, table + store slots <= 227 KB). */
 typedef struct lpc_eps lpc_eps;
 typedef struct lpc_eps_result {
@@ -245,7 +247,8 @@ typedef struct lpc_eps_result {
   int32_t n_live_records;                 /* propagators left in the table after dropping those entailed on the root */
   float device_ms;
   int32_t overflow_hazard;                /* as lpc_batch_result */
-  int32_t reserved;
+  int32_t n_first_sweep_records;          /* > 0: the root was a common fixpoint of the table, and the first sweep of every
+                                             subproblem ran on these records only (those that mention a decision variable) */
 } lpc_eps_result;
 
 int lpc_eps_create(const lpc_table* t, int32_t max_subproblems, int32_t survivor_cap, lpc_eps** out);

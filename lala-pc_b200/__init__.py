@@ -71,7 +71,7 @@ class EpsResult(ctypes.Structure):
     _fields_ = [("n_bot", ctypes.c_int64), ("n_solution", ctypes.c_int64), ("n_unknown", ctypes.c_int64),
                 ("best_bound", ctypes.c_int32), ("max_sweeps_seen", ctypes.c_int32), ("sweeps_total", ctypes.c_int64),
                 ("deductions", ctypes.c_int64), ("n_survivors", ctypes.c_int64), ("n_live_records", ctypes.c_int32),
-                ("device_ms", ctypes.c_float), ("overflow_hazard", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("device_ms", ctypes.c_float), ("overflow_hazard", ctypes.c_int32), ("n_first_sweep_records", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -39,18 +39,35 @@ struct PackedHdr {
 };
 
 // ---- table packer: one block; keeps table order inside every run ------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, const int2* root, uint2* out, PackedHdr* hdr) {
-  __shared__ int s_warp[32];
+// hdr[0] / out: the packed table. hdr[1] / out1 (EPS, default mode): the records among those that mention a decision
+// variable - the only propagators that can move anything in the FIRST sweep of a subproblem when the root is a common
+// fixpoint of the table (checked here: no kept record moves a bound on the root). hdr[1].np = 0 when that does not hold,
+// when there are more than cap1 such records, or when no decision list is given: the first sweep is then a full one.
+struct PackOut { uint2* out; PackedHdr* hdr; int base, nruns, run_begin; };
+__global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, const int2* root, uint2* out, PackedHdr* hdr,
+                                                     const int* dvars, int ndec, uint2* out1, int cap1) {
+  __shared__ int s_warp[2][32];
+  __shared__ unsigned s_dmap[256];   // bit v: variable v is a decision variable (the grouped kernel takes nvars <= 8191)
+  __shared__ int s_moves;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool want1 = dvars != nullptr && root != nullptr && out1 != nullptr && cap1 >= 2 && t.nvars <= 8192;
+  if(tid < 256) s_dmap[tid] = 0;
+  if(tid == 0) s_moves = 0;
+  __syncthreads();
+  if(want1) for(int j = tid; j < ndec; j += 1024) atomicOr(&s_dmap[dvars[j] >> 5], 1u << (dvars[j] & 31));
+  __syncthreads();
   const int nseg = segs.n == 0 ? 1 : segs.n;
   int base = 0, nruns = 0, n_live = 0;
+  int base1 = 0, nruns1 = 0;
+  bool over1 = false;
+  int moves = 0;
   for(int r = 0; r < nseg; ++r) {
     const int s0 = segs.n == 0 ? 0 : segs.start[r], s1 = segs.n == 0 ? (int)t.n : segs.start[r + 1];
     const int run_op = segs.n == 0 ? -1 : (int)segs.op[r];
-    const int run_begin = base;
+    const int run_begin = base, run_begin1 = base1;
     for(int i0 = s0; i0 < s1; i0 += 1024) {
       const int i = i0 + tid;
-      bool live = i < s1;
+      bool live = i < s1, inc = false;
       int op = D_NOP, x = 0, y = 0, z = 0;
       if(live) {
         op = t.op[i]; x = t.x[i]; y = t.y[i]; z = t.z[i];
@@ -60,34 +77,58 @@ __global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, co
           // an empty operand: keep the record (the store is at bot anyway, nothing is entailed on bot)
           const bool any_bot = (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
           if(!any_bot && ask_regs(op, Itv(a.x, a.y), Itv(b.x, b.y), Itv(c.x, c.y))) live = false;
+          else if(want1) {
+            Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
+            deduce_regs<true>(op, r1, r2, r3);
+            moves |= any_bot | (r1.lb != a.x) | (r1.ub != a.y) | (r2.lb != b.x) | (r2.ub != b.y) | (r3.lb != c.x) | (r3.ub != c.y);
+            inc = ((s_dmap[x >> 5] >> (x & 31)) | (s_dmap[y >> 5] >> (y & 31)) | (s_dmap[z >> 5] >> (z & 31))) & 1;
+          }
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, live);
-      if(lane == 0) s_warp[warp] = __popc(m);
+      const unsigned m = __ballot_sync(0xffffffffu, live), m1 = __ballot_sync(0xffffffffu, inc);
+      if(lane == 0) { s_warp[0][warp] = __popc(m); s_warp[1][warp] = __popc(m1); }
       __syncthreads();
-      int before = 0, total = 0;
-      for(int w = 0; w < 32; ++w) { const int c = s_warp[w]; if(w < warp) before += c; total += c; }
-      if(live) {
-        const int pos = base + before + __popc(m & ((1u << lane) - 1));
-        out[pos] = make_uint2((unsigned)(8 * x) | ((unsigned)(8 * y) << 16), (unsigned)(8 * z) | ((unsigned)op << 16));
+      int before = 0, total = 0, before1 = 0, total1 = 0;
+      for(int w = 0; w < 32; ++w) {
+        const int c = s_warp[0][w], c1 = s_warp[1][w];
+        if(w < warp) { before += c; before1 += c1; }
+        total += c; total1 += c1;
       }
+      const uint2 rec = make_uint2((unsigned)(8 * x) | ((unsigned)(8 * y) << 16), (unsigned)(8 * z) | ((unsigned)op << 16));
+      if(live) out[base + before + __popc(m & ((1u << lane) - 1))] = rec;
+      if(base1 + total1 + 1 > cap1) over1 |= total1 > 0;
+      else if(inc) out1[base1 + before1 + __popc(m1 & ((1u << lane) - 1))] = rec;
       base += total;
+      if(!over1) base1 += total1;
       __syncthreads();
     }
     n_live += base - run_begin;
     if((base - run_begin) & 1) {   // odd run: repeat its last record
       if(tid == 0) out[base] = out[base - 1];
       ++base;
-      __syncthreads();
     }
+    if(!over1 && ((base1 - run_begin1) & 1)) {
+      if(tid == 0) out1[base1] = out1[base1 - 1];
+      ++base1;
+    }
+    __syncthreads();
     if(base > run_begin) {
-      if(tid == 0) { hdr->start[nruns] = run_begin; hdr->op[nruns] = run_op; }
+      if(tid == 0) { hdr[0].start[nruns] = run_begin; hdr[0].op[nruns] = run_op; }
       ++nruns;
     }
+    if(want1 && !over1 && base1 > run_begin1) {
+      if(tid == 0) { hdr[1].start[nruns1] = run_begin1; hdr[1].op[nruns1] = run_op; }
+      ++nruns1;
+    }
   }
+  if(moves) s_moves = 1;
+  __syncthreads();
   if(tid == 0) {
-    hdr->start[nruns] = base;
-    hdr->np = base; hdr->nruns = nruns; hdr->n_live = n_live; hdr->n_total = (int)t.n;
+    hdr[0].start[nruns] = base;
+    hdr[0].np = base; hdr[0].nruns = nruns; hdr[0].n_live = n_live; hdr[0].n_total = (int)t.n;
+    const bool ok1 = want1 && !over1 && s_moves == 0;
+    hdr[1].start[ok1 ? nruns1 : 0] = ok1 ? base1 : 0;
+    hdr[1].np = ok1 ? base1 : 0; hdr[1].nruns = ok1 ? nruns1 : 0; hdr[1].n_live = ok1 ? base1 : 0; hdr[1].n_total = (int)t.n;
   }
 }
 
@@ -129,7 +170,8 @@ __global__ void k_eps_fold(const PeerSlot* inbox, int world, long long epoch, Ba
 
 // ---- the grouped kernel ---------------------------------------------------------------------------------------------
 struct GroupArgs {
-  const uint2* ptab; const PackedHdr* hdr;
+  const uint2* ptab; const PackedHdr* hdr;   // hdr[0]: the packed table; hdr[1] / ptab1: the first-sweep table (k_pack_table)
+  const uint2* ptab1;              // null: every sweep is a full one
   int2* stores;                    // !EPS: resident images [n_stores][nvars], fixpoints written back in place
   const int2* root;                // EPS: the root store
   const int* dvars; int ndec;      // EPS: decision variables (bit j of the id halves dvars[j])
@@ -309,31 +351,37 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   volatile int* s_bot = &ga->bot;
   unsigned* s_nev = &ga->nev;
   PackedHdr* sh = reinterpret_cast<PackedHdr*>(smem + 640);
-  static_assert(sizeof(PackedHdr) <= 256, "header does not fit its shared-memory area");
+  PackedHdr* sh1 = reinterpret_cast<PackedHdr*>(smem + 640 + 192);
+  static_assert(sizeof(PackedHdr) <= 192, "two headers share the 384-byte header area");
   const int sbytes = A.sbytes;
   int2* S = reinterpret_cast<int2*>(smem + 1024 + (size_t)grp * sbytes);
   char* tb = reinterpret_cast<char*>(smem + 1024 + (size_t)G * sbytes);
   const size_t store_stride = (size_t)A.nvars;
   unsigned long long* tbar = &bars[G];
   const int np = A.hdr->np;
+  const int np1 = (EPS && A.ptab1) ? A.hdr[1].np : 0;   // > 0: sweep 1 of every subproblem runs on the first-sweep table
 
   if(threadIdx.x == 0) {
     for(int i = 0; i <= G; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
-  if(threadIdx.x < (int)(sizeof(PackedHdr) / 4)) reinterpret_cast<int*>(sh)[threadIdx.x] = reinterpret_cast<const int*>(A.hdr)[threadIdx.x];
+  if(threadIdx.x < (int)(sizeof(PackedHdr) / 4)) {
+    reinterpret_cast<int*>(sh)[threadIdx.x] = reinterpret_cast<const int*>(A.hdr)[threadIdx.x];
+    if(np1 > 0) reinterpret_cast<int*>(sh1)[threadIdx.x] = reinterpret_cast<const int*>(A.hdr + 1)[threadIdx.x];
+  }
   __syncthreads();
   int cur = G * blockIdx.x + grp < A.n_stores ? G * blockIdx.x + grp : -1;
   if(threadIdx.x == 0 && np > 0) {
-    mbar_expect_tx(tbar, (unsigned)(np * 8));
+    mbar_expect_tx(tbar, (unsigned)((np + np1) * 8));
     bulk_g2s_chunked(tb, (const char*)A.ptab, (unsigned)(np * 8), tbar);
+    if(np1 > 0) bulk_g2s_chunked(tb + (size_t)np * 8, (const char*)A.ptab1, (unsigned)(np1 * 8), tbar);
   }
   if(tid == 0 && cur >= 0) {
     mbar_expect_tx(&bars[grp], (unsigned)sbytes);
     bulk_g2s_chunked((char*)S, EPS ? (const char*)A.root : (const char*)(A.stores + cur * store_stride), sbytes, &bars[grp]);
   }
   if(np > 0) mbar_wait(tbar, 0);
-  const unsigned a_T = smem_u32(tb), a_S = smem_u32(S);
+  const unsigned a_T = smem_u32(tb), a_S = smem_u32(S), a_T1 = a_T + 8u * (unsigned)np;
 
   if(tid == 0) { ga->best = LPC_INF; ga->sol = ga->nbot = ga->unk = ga->sweeps = ga->ded = 0; ga->maxsw = 0; }
   unsigned phase = 0;
@@ -371,7 +419,10 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
     unsigned nev = 0;
     bool changed = !(bot && A.stop_on_bot) && np > 0;
     while(changed) {
-      const int f = pk_sweep<HAS_DIV, JOIN>(*sh, a_T, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev);
+      // The root is a common fixpoint of the table (k_pack_table checked), so in the first sweep of a subproblem only the
+      // propagators that mention a halved decision variable can move anything: a few hundred records instead of all.
+      const int f = (EPS && np1 > 0 && sweeps == 0) ? pk_sweep<HAS_DIV, JOIN>(*sh1, a_T1, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev)
+                                                    : pk_sweep<HAS_DIV, JOIN>(*sh, a_T, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev);
       ++sweeps;
       const int any_chg = gbar_or(bid, nthr, f & 1);   // the bot word was written where the variable was emptied
       bot |= *s_bot != 0;
@@ -466,7 +517,7 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
 using namespace lpc;
 
 // ---- launch plan shared by the resident and the EPS entry points -------------------------------------------------------
-struct GroupPlan { int g = 0; size_t smem = 0; int sms = 0; size_t ptab_bytes = 0; };
+struct GroupPlan { int g = 0; size_t smem = 0; int sms = 0; size_t ptab_bytes = 0; int cap1 = 0; };   // cap1: records of the first-sweep table
 
 // The join variant (pk_rule) goes with the schedule. Dense sweeps (LPC_MODE_SWEEP) join with guarded atomics (JOIN = 1);
 // the default mode, which evaluates only the propagators not entailed on the root and so moves a bound in a larger share
@@ -522,7 +573,21 @@ static int group_plan(const lpc_table* t, int nvars, int sbytes, GroupPlan* plan
       if(k2 != k) LPC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
       int per_sm = 0;
       LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 1024, need));
-      if(per_sm >= 1) { plan->g = g; plan->smem = need; return LPC_OK; }
+      if(per_sm >= 1) {
+        plan->g = g; plan->smem = need;
+        if(EPS) {   // what is left of the SM's shared memory takes the first-sweep table (up to 2,048 records)
+          const size_t room = ((size_t)optin - need) / 16 * 16;
+          const int cap1 = (int)std::min<size_t>(room / 8, 2048);
+          if(cap1 >= 64) {
+            plan->cap1 = cap1; plan->smem = need + (size_t)cap1 * 8;
+            LPC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
+            if(k2 != k) LPC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
+            LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 1024, plan->smem));
+            if(per_sm < 1) { plan->cap1 = 0; plan->smem = need; }
+          }
+        }
+        return LPC_OK;
+      }
     }
     if(want > 0) break;
   }
@@ -551,14 +616,14 @@ int lpc_group_launch_resident(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
     if(p.g) {
       b->grp_grid = std::max(1, std::min((b->n_stores + p.g - 1) / p.g, p.sms));
       LPC_CUDA(cudaMalloc(&b->d_ptab, p.ptab_bytes));
-      LPC_CUDA(cudaMalloc(&b->d_phdr, sizeof(PackedHdr)));
+      LPC_CUDA(cudaMalloc(&b->d_phdr, 2 * sizeof(PackedHdr)));
     }
   }
   // small batches keep the one-store-per-block kernel (more threads per store finish a single store sooner)
   if(b->grp_g == 0 || t->dev.n_pad < 2048 || b->n_stores < 8 * b->table->sm_count || count <= 0) return LPC_OK;
   // LPC_MODE_AUTO on a batch whose stores are tightenings of a known root: propagators entailed on the root are dropped
   const int2* root = (o->mode == LPC_MODE_AUTO && b->root_valid) ? b->d_root : nullptr;
-  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr);
+  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr, nullptr, 0, nullptr, 0);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   const int g = b->grp_g;
@@ -656,16 +721,16 @@ int lpc_eps_create(const lpc_table* t, int32_t max_subproblems, int32_t survivor
   LPC_TRY(cudaMalloc((void**)&e->d_surv, std::max<size_t>((size_t)survivor_cap * e->sbytes, 16)));
   LPC_TRY(cudaMalloc((void**)&e->d_surv_idx, std::max<size_t>((size_t)survivor_cap * 4, 16)));
   LPC_TRY(cudaMalloc((void**)&e->d_ctl, sizeof(BatchCtl)));
-  LPC_TRY(cudaMalloc(&e->d_ptab, e->plan.ptab_bytes));
-  LPC_TRY(cudaMalloc((void**)&e->d_phdr, sizeof(PackedHdr)));
+  LPC_TRY(cudaMalloc(&e->d_ptab, e->plan.ptab_bytes + (size_t)e->plan.cap1 * 8));
+  LPC_TRY(cudaMalloc((void**)&e->d_phdr, 2 * sizeof(PackedHdr)));
   LPC_TRY(cudaHostAlloc((void**)&e->h_ctl, sizeof(BatchCtl), cudaHostAllocDefault));
   LPC_TRY(cudaHostAlloc((void**)&e->h_init, sizeof(BatchCtl), cudaHostAllocDefault));
-  LPC_TRY(cudaHostAlloc((void**)&e->h_phdr, sizeof(PackedHdr), cudaHostAllocDefault));
+  LPC_TRY(cudaHostAlloc((void**)&e->h_phdr, 2 * sizeof(PackedHdr), cudaHostAllocDefault));
   LPC_TRY(cudaEventCreate(&e->ev0));
   LPC_TRY(cudaEventCreate(&e->ev1));
 #undef LPC_TRY
   memset(e->h_ctl, 0, sizeof(BatchCtl));
-  memset(e->h_phdr, 0, sizeof(PackedHdr));
+  memset(e->h_phdr, 0, 2 * sizeof(PackedHdr));
   *out = e;
   return LPC_OK;
 }
@@ -735,12 +800,13 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
   // LPC_MODE_SWEEP keeps every propagator (the reference's work unit: each sweep evaluates all of them); the default mode
   // drops the ones entailed on the root
   const int2* elim_root = o->mode == LPC_MODE_SWEEP ? nullptr : e->d_root;
-  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr);
+  uint2* ptab1 = (elim_root && e->plan.cap1 > 0 && e->ndec > 0) ? (uint2*)((char*)e->d_ptab + e->plan.ptab_bytes) : nullptr;
+  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr, e->d_dvars, e->ndec, ptab1, e->plan.cap1);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   if(e->n > 0) {
     GroupArgs A{};
-    A.ptab = (const uint2*)e->d_ptab; A.hdr = e->d_phdr;
+    A.ptab = (const uint2*)e->d_ptab; A.hdr = e->d_phdr; A.ptab1 = ptab1;
     A.root = e->d_root; A.dvars = e->d_dvars; A.ndec = e->ndec; A.ids = e->have_ids ? e->d_ids : nullptr; A.first_id = e->first_id;
     A.n_stores = e->n; A.nvars = e->nvars; A.sbytes = e->sbytes;
     A.flags = e->d_flags; A.sweeps_out = e->d_sweeps; A.obj_out = e->d_obj;
@@ -760,7 +826,7 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
     LPC_CUDA(cudaGetLastError());
   }
   LPC_CUDA(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, st));
-  LPC_CUDA(cudaMemcpyAsync(e->h_phdr, e->d_phdr, sizeof(PackedHdr), cudaMemcpyDeviceToHost, st));
+  LPC_CUDA(cudaMemcpyAsync(e->h_phdr, e->d_phdr, 2 * sizeof(PackedHdr), cudaMemcpyDeviceToHost, st));
   e->last_stream = st;
   e->pending = true;
   return LPC_OK;
@@ -779,7 +845,8 @@ int lpc_eps_collect(lpc_eps* e, lpc_eps_result* r) {
     r->max_sweeps_seen = h.max_sweeps_seen;
     r->sweeps_total = h.sweeps_total; r->deductions = h.deductions;
     r->n_survivors = h.n_surv;
-    r->n_live_records = e->h_phdr->n_live;
+    r->n_live_records = e->h_phdr[0].n_live;
+    r->n_first_sweep_records = e->h_phdr[1].np;
     r->overflow_hazard = h.hazard;
     float ms = 0;
     LPC_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));

@@ -96,10 +96,38 @@ def test_config4_full_size_eps(L, c4, mode_name):
     assert np.array_equal(surv[:nw][order], c4["want_alive"])
     if mode_name == "auto":
         assert 0 < res.n_live_records < len(net.records)
+        # the root is a fixpoint: the first sweep of every subproblem ran on the records that mention a decision variable
+        assert 0 < res.n_first_sweep_records < res.n_live_records // 4
     else:
-        assert res.n_live_records == len(net.records)
+        assert res.n_live_records == len(net.records) and res.n_first_sweep_records == 0
     assert 0 < res.deductions <= res.sweeps_total * (res.n_live_records + 16)
     e.close()
+
+
+def test_eps_root_that_is_not_a_fixpoint(L, O, W):
+    """The first-sweep shortcut needs a root that is a common fixpoint of the table; a root that is not one (here: the
+    initial store of the model, never propagated) must turn it off and still give the exact fixpoints."""
+    net = W.pir_network(600, 2400, seed=91, width=10)
+    raw = net.store.copy()
+    fix, st = O.pir_fixpoint(raw, net.records)
+    assert not st.is_bot and not np.array_equal(fix, raw)
+    dec, obj = W.eps_decisions(net.records, fix, n=10, min_degree=2)
+    ids = np.arange(1 << len(dec), dtype=np.int64)
+    for root, expect_first in ((raw, False), (fix, True)):
+        want, wflags = oracle_eps(O, W, net.records, root, dec, ids)
+        t = L.Table(net.records, net.nvars)
+        e = L.Eps(t, len(ids), survivor_cap=len(ids))
+        flags = np.zeros(len(ids), dtype=np.uint8)
+        surv = np.zeros((len(ids), net.nvars, 2), dtype=np.int32)
+        idx = np.zeros(len(ids), dtype=np.int32)
+        res, nw = e.solve_host(root, dec, ids=ids, objective_var=obj, flags=flags, survivors=surv, survivor_index=idx)
+        assert (res.n_first_sweep_records > 0) == expect_first, (expect_first, res.n_first_sweep_records)
+        assert np.array_equal(flags, wflags)
+        ok = (wflags & 1) == 0
+        assert nw == int(ok.sum())
+        assert np.array_equal(surv[:nw], want[idx[:nw]])
+        e.close()
+        t.close()
 
 
 def oracle_eps(O, W, records, root, dec, ids):

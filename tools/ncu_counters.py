@@ -11,7 +11,7 @@ import sys
 
 # capture name -> (key in the json, prof_one workload)
 CAPS = {"eps_dense": "k_pir_group", "eps_auto": "k_pir_group_auto", "c2_dense": "k_pir_fixpoint", "c2_auto": "k_pir_dirty",
-        "pc_c3": "k_pc_fixpoint", "pc_c5": "k_pc_fixpoint_c5", "pc_c5_bits": "k_pc_fixpoint_c5_bits"}
+        "pc_c3": "k_pc_fixpoint_auto", "pc_c3_dense": "k_pc_fixpoint", "pc_c5": "k_pc_fixpoint_c5", "pc_c5_bits": "k_pc_fixpoint_c5_bits"}
 M = {"duration_ns": "gpu__time_duration.sum", "dram_read": "dram__bytes_read.sum", "dram_write": "dram__bytes_write.sum",
      "inst_executed": "smsp__inst_executed.sum", "thread_inst_ratio": "smsp__thread_inst_executed_per_inst_executed.ratio",
      "smem_wavefronts": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_bank_conflicts": "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",

@@ -10,7 +10,7 @@ cap() {  # name kernel-regex
   ncu -i gpurun_out/prof_$1.ncu-rep --page source --csv > /tmp/src_$1.csv 2>/dev/null
   python tools/sass_hot.py /tmp/src_$1.csv > gpurun_out/r02_$1_sass_hot.txt 2>&1
 }
-for spec in ${PROFILE_CAPS:-eps_dense:k_pir_group eps_auto:k_pir_group c2_dense:k_pir_fixpoint c2_auto:k_pir_dirty pc_c3:k_pc_fixpoint}; do
+for spec in ${PROFILE_CAPS:-eps_dense:k_pir_group eps_auto:k_pir_group c2_dense:k_pir_fixpoint c2_auto:k_pir_dirty pc_c3:k_pc_fixpoint pc_c3_dense:k_pc_fixpoint}; do
   cap ${spec%%:*} ${spec##*:}
 done
 python tools/ncu_counters.py gpurun_out > gpurun_out/ncu_counters.json
