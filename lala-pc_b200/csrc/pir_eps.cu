@@ -36,6 +36,8 @@ struct PackedHdr {
   int op[LPC_PK_MAXRUN];           // device opcode of the run; -1 = mixed (opcode taken from each record)
   int n_live;                      // propagators kept (not entailed on the root)
   int n_total;                     // propagators of the table
+  int root_flags;                  // EPS: bit0 = the root has an empty variable, bit1 = an infinite bound, bit2 = a finite
+                                   // bound next to the int32 limits (lpc.h: overflow hazard); -1 = no root was scanned
 };
 
 // ---- table packer: one block; keeps table order inside every run ------------------------------------------------------
@@ -45,15 +47,24 @@ struct PackedHdr {
 // when there are more than cap1 such records, or when no decision list is given: the first sweep is then a full one.
 struct PackOut { uint2* out; PackedHdr* hdr; int base, nruns, run_begin; };
 __global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, const int2* root, uint2* out, PackedHdr* hdr,
-                                                     const int* dvars, int ndec, uint2* out1, int cap1) {
+                                                     const int* dvars, int ndec, uint2* out1, int cap1, const int2* scan_root) {
   __shared__ int s_warp[2][32];
+  __shared__ int s_rflags;
   __shared__ unsigned s_dmap[256];   // bit v: variable v is a decision variable (the grouped kernel takes nvars <= 8191)
   __shared__ int s_moves;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool want1 = dvars != nullptr && root != nullptr && out1 != nullptr && cap1 >= 2 && t.nvars <= 8192;
   if(tid < 256) s_dmap[tid] = 0;
-  if(tid == 0) s_moves = 0;
+  if(tid == 0) { s_moves = 0; s_rflags = 0; }
   __syncthreads();
+  if(scan_root) {   // what every subproblem store inherits from the root (halving a variable keeps its bounds inside the old ones)
+    int rf = 0;
+    for(int v = tid; v < t.nvars; v += 1024) {
+      const int2 d = scan_root[v];
+      rf |= (d.x > d.y ? 1 : 0) | ((d.x == LPC_MINF || d.y == LPC_INF) ? 2 : 0) | ((near_inf_lo(d.x) | near_inf_hi(d.y)) ? 4 : 0);
+    }
+    if(rf) atomicOr(&s_rflags, rf);
+  }
   if(want1) for(int j = tid; j < ndec; j += 1024) atomicOr(&s_dmap[dvars[j] >> 5], 1u << (dvars[j] & 31));
   __syncthreads();
   const int nseg = segs.n == 0 ? 1 : segs.n;
@@ -126,9 +137,11 @@ __global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, co
   if(tid == 0) {
     hdr[0].start[nruns] = base;
     hdr[0].np = base; hdr[0].nruns = nruns; hdr[0].n_live = n_live; hdr[0].n_total = (int)t.n;
+    hdr[0].root_flags = scan_root ? s_rflags : -1;
     const bool ok1 = want1 && !over1 && s_moves == 0;
     hdr[1].start[ok1 ? nruns1 : 0] = ok1 ? base1 : 0;
     hdr[1].np = ok1 ? base1 : 0; hdr[1].nruns = ok1 ? nruns1 : 0; hdr[1].n_live = ok1 ? base1 : 0; hdr[1].n_total = (int)t.n;
+    hdr[1].root_flags = -1;
   }
 }
 
@@ -396,25 +409,39 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
     }
     mbar_wait(&bars[grp], phase);
     phase ^= 1;
+    int f0 = 0, inf = 0, hz = 0;
+    bool bot, fin;
+    const int rflags = EPS ? sh->root_flags : -1;
     if(EPS) {   // the subproblem: bit j of the id keeps the lower (0) or the upper (1) half of decision variable j
       const long long id = A.ids ? A.ids[cur] : A.first_id + cur;
       for(int j = tid; j < A.ndec; j += nthr) {
         const int v = A.dvars[j];
         const int2 d = S[v];
         const long long mid = (long long)d.x + (((long long)d.y - (long long)d.x) >> 1);
-        S[v] = ((id >> j) & 1) ? make_int2((int)(mid + 1), d.y) : make_int2(d.x, (int)mid);
+        const int2 h = ((id >> j) & 1) ? make_int2((int)(mid + 1), d.y) : make_int2(d.x, (int)mid);
+        S[v] = h;
+        f0 |= h.x > h.y;   // the upper half of a singleton is empty
       }
-      gbar_sync(bid, nthr);
     }
-    int f0 = 0, inf = 0, hz = 0;
-    for(int v = tid; v < A.nvars; v += nthr) {
-      const int2 d = S[v];
-      f0 |= d.x > d.y;
-      inf |= (d.x == LPC_MINF) | (d.y == LPC_INF);
-      hz |= near_inf_lo(d.x) | near_inf_hi(d.y);
+    if(EPS && rflags >= 0) {
+      // Everything but the halved variables is the root, whose emptiness / finiteness / overflow hazard k_pack_table has
+      // scanned once for the whole batch; a half of a variable lies inside its old bounds, so it adds neither an infinite
+      // bound nor a hazard - only, for a singleton, an empty upper half.
+      bot = (gbar_or(bid, nthr, f0) != 0) | ((rflags & 1) != 0);   // also orders thread 0's s_bot / s_next writes before their readers
+      fin = (rflags & 2) == 0;
+      hz = (rflags & 4) != 0 && tid == 0;   // one thread reports it
     }
-    bool bot = gbar_or(bid, nthr, f0) != 0;   // also orders thread 0's s_bot / s_next writes before their readers
-    const bool fin = gbar_or(bid, nthr, inf) == 0;
+    else {
+      if(EPS) gbar_sync(bid, nthr);
+      for(int v = tid; v < A.nvars; v += nthr) {
+        const int2 d = S[v];
+        f0 |= d.x > d.y;
+        inf |= (d.x == LPC_MINF) | (d.y == LPC_INF);
+        hz |= near_inf_lo(d.x) | near_inf_hi(d.y);
+      }
+      bot = gbar_or(bid, nthr, f0) != 0;   // also orders thread 0's s_bot / s_next writes before their readers
+      fin = gbar_or(bid, nthr, inf) == 0;
+    }
     int sweeps = 0;
     unsigned nev = 0;
     bool changed = !(bot && A.stop_on_bot) && np > 0;
@@ -439,8 +466,10 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
         ok = ask_regs((int)(rc.y >> 16), Itv(a.x, a.y), Itv(bb.x, bb.y), Itv(c.x, c.y));
       }
       all_ent = gbar_and(bid, nthr, ok);
-      // overflow hazard (lpc.h): a finite bound next to the int32 limits in a store that is handed back
-      for(int v = tid; v < A.nvars; v += nthr) { const int2 d = S[v]; hz |= near_inf_lo(d.x) | near_inf_hi(d.y); }
+      // overflow hazard (lpc.h): a finite bound next to the int32 limits in a store that is handed back (bounds only
+      // tighten: a root without a bound in that band cannot grow one)
+      if(!(EPS && rflags >= 0 && !(rflags & 4)))
+        for(int v = tid; v < A.nvars; v += nthr) { const int2 d = S[v]; hz |= near_inf_lo(d.x) | near_inf_hi(d.y); }
     }
     if(hz) atomicOr(&A.ctl->hazard, 1);
     fence_async_smem();
@@ -623,7 +652,7 @@ int lpc_group_launch_resident(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
   if(b->grp_g == 0 || t->dev.n_pad < 2048 || b->n_stores < 8 * b->table->sm_count || count <= 0) return LPC_OK;
   // LPC_MODE_AUTO on a batch whose stores are tightenings of a known root: propagators entailed on the root are dropped
   const int2* root = (o->mode == LPC_MODE_AUTO && b->root_valid) ? b->d_root : nullptr;
-  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr, nullptr, 0, nullptr, 0);
+  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr, nullptr, 0, nullptr, 0, nullptr);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   const int g = b->grp_g;
@@ -801,7 +830,7 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
   // drops the ones entailed on the root
   const int2* elim_root = o->mode == LPC_MODE_SWEEP ? nullptr : e->d_root;
   uint2* ptab1 = (elim_root && e->plan.cap1 > 0 && e->ndec > 0) ? (uint2*)((char*)e->d_ptab + e->plan.ptab_bytes) : nullptr;
-  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr, e->d_dvars, e->ndec, ptab1, e->plan.cap1);
+  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr, e->d_dvars, e->ndec, ptab1, e->plan.cap1, e->d_root);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   if(e->n > 0) {
