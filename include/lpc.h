@@ -276,7 +276,9 @@ int lpc_eps_download(lpc_eps* e, uint8_t* flags, int32_t* survivors_lbub, int32_
  * writes the rank's record into every peer's inbox over NVLink, and every lpc_eps_run_async / lpc_eps_solve_host queues a
  * one-thread kernel behind it that waits for the peers' records and leaves the payload of lpc_eps_payload_device_ptr as an
  * all-reduce would - without a collective library call per step. Every rank must make the same sequence of calls (a call
- * only returns its payload once every peer has made it too). lpc_eps_peer_connect fails with LPC_ERR_CUDA when two devices
+ * only returns its payload once every peer has made it too), counted from lpc_eps_peer_connect on, and the ranks must be
+ * synchronised once between the last connect and the first call (a barrier of the launching plumbing). A peer that never
+ * arrives leaves payload[0] = -1 after a few seconds instead of hanging the GPU. lpc_eps_peer_connect fails with LPC_ERR_CUDA when two devices
  * have no peer access; the caller then keeps its all-reduce. */
 #define LPC_PEER_HANDLE_BYTES 64
 int lpc_eps_peer_export(lpc_eps* e, void* handle_out);

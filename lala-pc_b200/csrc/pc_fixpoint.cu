@@ -22,6 +22,7 @@
 #include <cstring>
 
 #include "../../include/lpc_pc.h"
+#include <mutex>
 
 namespace lpc {
 
@@ -396,6 +397,7 @@ struct lpc_pc_table {
   // bitset call of a table that holds a linear kind; tables without one use `main` on both stores.
   PcArrays bits;
   bool bits_built = false;
+  std::mutex bits_mu;               // a table is shared by the stores that run on it: the lazy build is serialised
   bool has_linear = false;          // a flat linear kind is present
   std::vector<int> h_props;         // the caller's arrays, kept for the bitset view (5 ints per propagator)
   std::vector<int2> h_terms;
@@ -493,6 +495,7 @@ static int pc_build_arrays(const lpc_pc_prop* props, int64_t n_props, const lpc_
 static int pc_view(const lpc_pc_table* tc, bool bits, const PcTableDev** out) {
   lpc_pc_table* t = const_cast<lpc_pc_table*>(tc);
   if(!bits || !t->has_linear) { *out = &t->main.dev; return LPC_OK; }
+  std::lock_guard<std::mutex> lock(t->bits_mu);
   if(!t->bits_built) {
     std::vector<int> vp;
     std::vector<int2> vt;

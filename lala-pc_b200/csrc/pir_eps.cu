@@ -977,6 +977,7 @@ int lpc_eps_peer_connect(lpc_eps* e, int32_t rank, int32_t world, const void* ha
   if(!e->d_peer_ptrs) LPC_CUDA(cudaMalloc((void**)&e->d_peer_ptrs, LPC_MAX_RANKS * sizeof(PeerSlot*)));
   LPC_CUDA(cudaMemcpy(e->d_peer_ptrs, ptrs, world * sizeof(PeerSlot*), cudaMemcpyHostToDevice));
   e->rank = rank; e->world = world;
+  e->epoch = 0;   // the ranks count their calls from here on: they must make the same calls in the same order
   e->peers_ok = true;
   return LPC_OK;
 }
