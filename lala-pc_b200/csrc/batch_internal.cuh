@@ -53,6 +53,10 @@ struct lpc_batch {
   // the batch is a tightening of, when known (lpc_batch_init_split establishes it, lpc_batch_write withdraws it)
   void* d_ptab = nullptr; void* d_phdr = nullptr;
   int2* d_root = nullptr; bool root_valid = false;
+  // the decision variables of the last lpc_batch_init_split, while every image still IS the root outside them (until the
+  // first fixpoint / write): the first sweep of the grouped kernel may then run on their records only (pir_eps.cu)
+  int* d_split_vars = nullptr; int n_split_vars = 0; bool split_fresh = false;
+  size_t grp_ptab_bytes = 0; int grp_cap1 = 0;
   int grp_g = -1; size_t grp_smem = 0; int grp_grid = 0;   // plan of the grouped kernel (-1 = not decided, 0 = unusable)
   int rank = 0, world = 1;           // lpc_batch_set_rank
   long long table_gen = 0;           // lpc_table::generation at creation: a table that changed since needs a new batch

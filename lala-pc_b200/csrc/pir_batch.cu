@@ -602,7 +602,7 @@ int lpc_batch_destroy(lpc_batch* b) {
   if(b->s_out) cudaStreamDestroy(b->s_out);
   cudaFree(b->d_ctl_chunk);
   if(b->h_ctl_chunk) cudaFreeHost(b->h_ctl_chunk);
-  cudaFree(b->d_ptab); cudaFree(b->d_phdr); cudaFree(b->d_root);
+  cudaFree(b->d_ptab); cudaFree(b->d_phdr); cudaFree(b->d_root); cudaFree(b->d_split_vars);
   delete b;
   return LPC_OK;
 }
@@ -615,6 +615,7 @@ int lpc_batch_write(lpc_batch* b, int32_t first, int32_t n, const int32_t* lbub)
   LPC_REQUIRE(first >= 0 && n >= 0 && (long long)first + n <= b->n_stores, "range out of bounds");
   if(n) LPC_CUDA(cudaMemcpy(b->d + (size_t)first * b->nvars, lbub, (size_t)n * b->nvars * 8, cudaMemcpyHostToDevice));
   b->root_valid = false;   // arbitrary images: no common root is known any more
+  b->split_fresh = false;
   return LPC_OK;
 }
 
@@ -665,6 +666,9 @@ static int batch_init_split(lpc_batch* b, const int32_t* base_lbub, const int32_
     LPC_CUDA(cudaMemcpy(b->d_root, d_base, (size_t)b->nvars * 8, cudaMemcpyDeviceToDevice));
     b->root_valid = true;
     LPC_CUDA(cudaDeviceSynchronize());
+    cudaFree(b->d_split_vars);   // the batch keeps the decision list
+    b->d_split_vars = d_dec; d_dec = nullptr;
+    b->n_split_vars = n_decisions; b->split_fresh = true;
     return LPC_OK;
   };
   const int rc = body();
@@ -704,6 +708,7 @@ static int batch_launch_range(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
     int rc = lpc_group_launch_resident(b, o, objective_var, first, count, d_ctl, h_init, st, &used);
     if(rc || used) return rc;
   }
+  b->split_fresh = false;   // any fixpoint moves the images off the root of the split
   // launch plan: computed once per batch handle and mode (device attribute / occupancy queries are slow driver calls)
   if(!b->plan_ready[cd]) {
     int dev = 0, sms = 0, optin = 0;
@@ -843,6 +848,7 @@ int lpc_batch_fixpoint_host(lpc_batch* b, int32_t* lbub, const lpc_fixpoint_opts
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   cudaStream_t st = (cudaStream_t)o->stream;
   b->root_valid = false;   // the images come from the caller: no common root is known
+  b->split_fresh = false;
   const size_t store_bytes = (size_t)b->nvars * 8;
   const size_t bytes = (size_t)b->n_stores * store_bytes;
   int sms = 148;

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   const size_t store_stride = (size_t)A.nvars;
   unsigned long long* tbar = &bars[G];
   const int np = A.hdr->np;
-  const int np1 = (EPS && A.ptab1) ? A.hdr[1].np : 0;   // > 0: sweep 1 of every subproblem runs on the first-sweep table
+  const int np1 = A.ptab1 ? A.hdr[1].np : 0;   // > 0: sweep 1 of every store runs on the first-sweep table
 
   if(threadIdx.x == 0) {
     for(int i = 0; i <= G; ++i) mbar_init(&bars[i], 1);
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
     while(changed) {
       // The root is a common fixpoint of the table (k_pack_table checked), so in the first sweep of a subproblem only the
       // propagators that mention a halved decision variable can move anything: a few hundred records instead of all.
-      const int f = (EPS && np1 > 0 && sweeps == 0) ? pk_sweep<HAS_DIV, JOIN>(*sh1, a_T1, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev)
+      const int f = (np1 > 0 && sweeps == 0) ? pk_sweep<HAS_DIV, JOIN>(*sh1, a_T1, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev)
                                                     : pk_sweep<HAS_DIV, JOIN>(*sh, a_T, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev);
       ++sweeps;
       const int any_chg = gbar_or(bid, nthr, f & 1);   // the bot word was written where the variable was emptied
@@ -604,7 +604,7 @@ static int group_plan(const lpc_table* t, int nvars, int sbytes, GroupPlan* plan
       LPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 1024, need));
       if(per_sm >= 1) {
         plan->g = g; plan->smem = need;
-        if(EPS) {   // what is left of the SM's shared memory takes the first-sweep table (up to 2,048 records)
+        {   // what is left of the SM's shared memory takes the first-sweep table (up to 2,048 records)
           const size_t room = ((size_t)optin - need) / 16 * 16;
           const int cap1 = (int)std::min<size_t>(room / 8, 2048);
           if(cap1 >= 64) {
@@ -641,10 +641,10 @@ int lpc_group_launch_resident(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
     if(rc) return rc;
     const char* ev = getenv("LPC_BATCH_V2");
     if(ev && !atoi(ev)) p.g = 0;
-    b->grp_g = p.g; b->grp_smem = p.smem;
+    b->grp_g = p.g; b->grp_smem = p.smem; b->grp_ptab_bytes = p.ptab_bytes; b->grp_cap1 = p.cap1;
     if(p.g) {
       b->grp_grid = std::max(1, std::min((b->n_stores + p.g - 1) / p.g, p.sms));
-      LPC_CUDA(cudaMalloc(&b->d_ptab, p.ptab_bytes));
+      LPC_CUDA(cudaMalloc(&b->d_ptab, p.ptab_bytes + (size_t)p.cap1 * 8));
       LPC_CUDA(cudaMalloc(&b->d_phdr, 2 * sizeof(PackedHdr)));
     }
   }
@@ -652,7 +652,13 @@ int lpc_group_launch_resident(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
   if(b->grp_g == 0 || t->dev.n_pad < 2048 || b->n_stores < 8 * b->table->sm_count || count <= 0) return LPC_OK;
   // LPC_MODE_AUTO on a batch whose stores are tightenings of a known root: propagators entailed on the root are dropped
   const int2* root = (o->mode == LPC_MODE_AUTO && b->root_valid) ? b->d_root : nullptr;
-  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr, nullptr, 0, nullptr, 0, nullptr);
+  // ... and while every image still is the root outside the decision variables of the split (no fixpoint, no write since),
+  // the first sweep may run on the records of those variables only (k_pack_table checks that the root is a fixpoint)
+  const bool fresh = root && b->split_fresh && b->n_split_vars > 0 && b->grp_cap1 > 0;
+  uint2* ptab1 = fresh ? (uint2*)((char*)b->d_ptab + b->grp_ptab_bytes) : nullptr;
+  b->split_fresh = false;   // whatever mode this call runs in, it moves the images off the root
+  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr, b->d_split_vars, b->n_split_vars,
+                                   ptab1, b->grp_cap1, nullptr);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   const int g = b->grp_g;
@@ -660,7 +666,7 @@ int lpc_group_launch_resident(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
   ctl_init(h_init, g * grid, b->rank, b->world);
   LPC_CUDA(cudaMemcpyAsync(d_ctl, h_init, sizeof(BatchCtl), cudaMemcpyHostToDevice, st));
   GroupArgs A{};
-  A.ptab = (const uint2*)b->d_ptab; A.hdr = (const PackedHdr*)b->d_phdr;
+  A.ptab = (const uint2*)b->d_ptab; A.hdr = (const PackedHdr*)b->d_phdr; A.ptab1 = ptab1;
   A.stores = b->d + (size_t)first * b->nvars;
   A.n_stores = count; A.nvars = b->nvars; A.sbytes = b->sbytes;
   A.flags = b->d_flags + first; A.sweeps_out = b->d_sweeps + first; A.obj_out = b->d_obj ? b->d_obj + first : nullptr;

@@ -74,6 +74,17 @@ def test_config4_full_size_resident(L, c4, mode_name):
     assert 0 < res.deductions <= res.sweeps_total * (len(net.records) + 16)
     if mode_name == "auto":
         assert res.deductions < res.sweeps_total * len(net.records) * 0.7   # entailed propagators were dropped
+        # a second fixpoint on the same images (no longer the root of the split outside the decision variables: the
+        # first-sweep shortcut must be off) finds the surviving stores at rest (failed images are not written back: they
+        # fail again)
+        res2 = b.fixpoint(objective_var=c4["obj"], mode=L.MODE_AUTO)
+        assert np.array_equal(b.flags(), c4["wflags"]) and np.array_equal(b.read()[c4["alive"]], c4["want_alive"])
+        assert res2.sweeps_total < res.sweeps_total
+        # and a fresh split after it turns it on again
+        b.init_split(c4["root"], c4["dec"], 0)
+        res3 = b.fixpoint(objective_var=c4["obj"], mode=L.MODE_AUTO)
+        assert np.array_equal(b.flags(), c4["wflags"]) and np.array_equal(b.read()[c4["alive"]], c4["want_alive"])
+        assert abs(res3.deductions - res.deductions) < 0.02 * res.deductions
     b.close()
 
 
