@@ -45,10 +45,11 @@ struct PackedHdr {
 // variable - the only propagators that can move anything in the FIRST sweep of a subproblem when the root is a common
 // fixpoint of the table (checked here: no kept record moves a bound on the root). hdr[1].np = 0 when that does not hold,
 // when there are more than cap1 such records, or when no decision list is given: the first sweep is then a full one.
-struct PackOut { uint2* out; PackedHdr* hdr; int base, nruns, run_begin; };
-__global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, const int2* root, uint2* out, PackedHdr* hdr,
+constexpr int PK_K = 4;   // consecutive records per thread and iteration: their loads are in flight together
+constexpr int PK_T = 512; // threads of the one block (4 x 512 records per iteration without spilling at 128 registers)
+__global__ void __launch_bounds__(PK_T) k_pack_table(TableDev t, OpSegs segs, const int2* root, uint2* out, PackedHdr* hdr,
                                                      const int* dvars, int ndec, uint2* out1, int cap1, const int2* scan_root) {
-  __shared__ int s_warp[2][32];
+  __shared__ unsigned s_warp[PK_T / 32];    // per warp: kept records | first-sweep records << 16
   __shared__ int s_rflags;
   __shared__ unsigned s_dmap[256];   // bit v: variable v is a decision variable (the grouped kernel takes nvars <= 8191)
   __shared__ int s_moves;
@@ -59,13 +60,13 @@ __global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, co
   __syncthreads();
   if(scan_root) {   // what every subproblem store inherits from the root (halving a variable keeps its bounds inside the old ones)
     int rf = 0;
-    for(int v = tid; v < t.nvars; v += 1024) {
+    for(int v = tid; v < t.nvars; v += PK_T) {
       const int2 d = scan_root[v];
       rf |= (d.x > d.y ? 1 : 0) | ((d.x == LPC_MINF || d.y == LPC_INF) ? 2 : 0) | ((near_inf_lo(d.x) | near_inf_hi(d.y)) ? 4 : 0);
     }
     if(rf) atomicOr(&s_rflags, rf);
   }
-  if(want1) for(int j = tid; j < ndec; j += 1024) atomicOr(&s_dmap[dvars[j] >> 5], 1u << (dvars[j] & 31));
+  if(want1) for(int j = tid; j < ndec; j += PK_T) atomicOr(&s_dmap[dvars[j] >> 5], 1u << (dvars[j] & 31));
   __syncthreads();
   const int nseg = segs.n == 0 ? 1 : segs.n;
   int base = 0, nruns = 0, n_live = 0;
@@ -76,40 +77,58 @@ __global__ void __launch_bounds__(1024) k_pack_table(TableDev t, OpSegs segs, co
     const int s0 = segs.n == 0 ? 0 : segs.start[r], s1 = segs.n == 0 ? (int)t.n : segs.start[r + 1];
     const int run_op = segs.n == 0 ? -1 : (int)segs.op[r];
     const int run_begin = base, run_begin1 = base1;
-    for(int i0 = s0; i0 < s1; i0 += 1024) {
-      const int i = i0 + tid;
-      bool live = i < s1, inc = false;
-      int op = D_NOP, x = 0, y = 0, z = 0;
-      if(live) {
-        op = t.op[i]; x = t.x[i]; y = t.y[i]; z = t.z[i];
-        if(op == D_NOP) live = false;
-        else if(root) {
-          const int2 a = root[x], b = root[y], c = root[z];
+    for(int i0 = s0; i0 < s1; i0 += PK_T * PK_K) {
+      int op[PK_K], x[PK_K], y[PK_K], z[PK_K];
+      int2 a[PK_K], b[PK_K], c[PK_K];
+#pragma unroll
+      for(int k = 0; k < PK_K; ++k) {
+        const int i = i0 + PK_K * tid + k;
+        const bool in = i < s1;
+        op[k] = in ? (int)t.op[i] : D_NOP; x[k] = in ? t.x[i] : 0; y[k] = in ? t.y[i] : 0; z[k] = in ? t.z[i] : 0;
+      }
+      if(root) {
+#pragma unroll
+        for(int k = 0; k < PK_K; ++k) { a[k] = root[x[k]]; b[k] = root[y[k]]; c[k] = root[z[k]]; }
+      }
+      unsigned livem = 0, incm = 0;
+#pragma unroll
+      for(int k = 0; k < PK_K; ++k) {
+        if(op[k] == D_NOP) continue;
+        bool live = true, inc = false;
+        if(root) {
           // an empty operand: keep the record (the store is at bot anyway, nothing is entailed on bot)
-          const bool any_bot = (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
-          if(!any_bot && ask_regs(op, Itv(a.x, a.y), Itv(b.x, b.y), Itv(c.x, c.y))) live = false;
+          const bool any_bot = (a[k].x > a[k].y) | (b[k].x > b[k].y) | (c[k].x > c[k].y);
+          if(!any_bot && ask_regs(op[k], Itv(a[k].x, a[k].y), Itv(b[k].x, b[k].y), Itv(c[k].x, c[k].y))) live = false;
           else if(want1) {
-            Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
-            deduce_regs<true>(op, r1, r2, r3);
-            moves |= any_bot | (r1.lb != a.x) | (r1.ub != a.y) | (r2.lb != b.x) | (r2.ub != b.y) | (r3.lb != c.x) | (r3.ub != c.y);
-            inc = ((s_dmap[x >> 5] >> (x & 31)) | (s_dmap[y >> 5] >> (y & 31)) | (s_dmap[z >> 5] >> (z & 31))) & 1;
+            Itv r1(a[k].x, a[k].y), r2(b[k].x, b[k].y), r3(c[k].x, c[k].y);
+            deduce_regs<true>(op[k], r1, r2, r3);
+            moves |= any_bot | (r1.lb != a[k].x) | (r1.ub != a[k].y) | (r2.lb != b[k].x) | (r2.ub != b[k].y) | (r3.lb != c[k].x) | (r3.ub != c[k].y);
+            inc = ((s_dmap[x[k] >> 5] >> (x[k] & 31)) | (s_dmap[y[k] >> 5] >> (y[k] & 31)) | (s_dmap[z[k] >> 5] >> (z[k] & 31))) & 1;
           }
         }
+        livem |= (live ? 1u : 0u) << k;
+        incm |= (inc ? 1u : 0u) << k;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, live), m1 = __ballot_sync(0xffffffffu, inc);
-      if(lane == 0) { s_warp[0][warp] = __popc(m); s_warp[1][warp] = __popc(m1); }
+      // exclusive positions: inclusive scan over the warp of (kept | first-sweep << 16), then over the warps
+      const unsigned mine = (unsigned)__popc(livem) | ((unsigned)__popc(incm) << 16);
+      unsigned incl = mine;
+#pragma unroll
+      for(int off = 1; off < 32; off <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, off); if(lane >= off) incl += u; }
+      if(lane == 31) s_warp[warp] = incl;
       __syncthreads();
-      int before = 0, total = 0, before1 = 0, total1 = 0;
-      for(int w = 0; w < 32; ++w) {
-        const int c = s_warp[0][w], c1 = s_warp[1][w];
-        if(w < warp) { before += c; before1 += c1; }
-        total += c; total1 += c1;
+      unsigned before = 0, total = 0;
+      for(int w = 0; w < PK_T / 32; ++w) { const unsigned cw = s_warp[w]; if(w < warp) before += cw; total += cw; }
+      const int total0 = (int)(total & 0xffffu), total1 = (int)(total >> 16);
+      int pos = base + (int)((before + incl - mine) & 0xffffu), pos1 = base1 + (int)((before + incl - mine) >> 16);
+      const bool fits1 = !over1 && base1 + total1 + 1 <= cap1;
+#pragma unroll
+      for(int k = 0; k < PK_K; ++k) {
+        const uint2 rec = make_uint2((unsigned)(8 * x[k]) | ((unsigned)(8 * y[k]) << 16), (unsigned)(8 * z[k]) | ((unsigned)op[k] << 16));
+        if((livem >> k) & 1) out[pos++] = rec;
+        if(fits1 && ((incm >> k) & 1)) out1[pos1++] = rec;
       }
-      const uint2 rec = make_uint2((unsigned)(8 * x) | ((unsigned)(8 * y) << 16), (unsigned)(8 * z) | ((unsigned)op << 16));
-      if(live) out[base + before + __popc(m & ((1u << lane) - 1))] = rec;
-      if(base1 + total1 + 1 > cap1) over1 |= total1 > 0;
-      else if(inc) out1[base1 + before1 + __popc(m1 & ((1u << lane) - 1))] = rec;
-      base += total;
+      if(!fits1 && total1 > 0) over1 = true;
+      base += total0;
       if(!over1) base1 += total1;
       __syncthreads();
     }
@@ -657,7 +676,7 @@ int lpc_group_launch_resident(lpc_batch* b, const lpc_fixpoint_opts* o, int32_t 
   const bool fresh = root && b->split_fresh && b->n_split_vars > 0 && b->grp_cap1 > 0;
   uint2* ptab1 = fresh ? (uint2*)((char*)b->d_ptab + b->grp_ptab_bytes) : nullptr;
   b->split_fresh = false;   // whatever mode this call runs in, it moves the images off the root
-  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr, b->d_split_vars, b->n_split_vars,
+  k_pack_table<<<1, PK_T, 0, st>>>(t->dev, t->opsegs, root, (uint2*)b->d_ptab, (PackedHdr*)b->d_phdr, b->d_split_vars, b->n_split_vars,
                                    ptab1, b->grp_cap1, nullptr);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
@@ -836,7 +855,7 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
   // drops the ones entailed on the root
   const int2* elim_root = o->mode == LPC_MODE_SWEEP ? nullptr : e->d_root;
   uint2* ptab1 = (elim_root && e->plan.cap1 > 0 && e->ndec > 0) ? (uint2*)((char*)e->d_ptab + e->plan.ptab_bytes) : nullptr;
-  k_pack_table<<<1, 1024, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr, e->d_dvars, e->ndec, ptab1, e->plan.cap1, e->d_root);
+  k_pack_table<<<1, PK_T, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr, e->d_dvars, e->ndec, ptab1, e->plan.cap1, e->d_root);
   g_launches++;
   LPC_CUDA(cudaGetLastError());
   if(e->n > 0) {
