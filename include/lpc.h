@@ -165,7 +165,9 @@ int lpc_ask_all(const lpc_table* t, const lpc_store* s, int64_t* n_entailed);
 int lpc_ask_bits(const lpc_table* t, const lpc_store* s, uint8_t* out);
 
 /* ---- batched mode: one store per subproblem, one thread block per store ---------------------------------- */
-/* The table is shared by all stores (the `deps.is_shared_copy()` design of pir.hpp:182-195). */
+/* The table is shared by all stores (the `deps.is_shared_copy()` design of pir.hpp:182-195). A store image travels as one
+ * bulk copy, whose size must be a multiple of 16 bytes: the table must count an EVEN number of variables
+ * (lpc_table_set_nvars adds an unused one), else LPC_ERR_UNSUPPORTED. The same holds for lpc_eps_create. */
 int lpc_batch_create(const lpc_table* t, int32_t n_stores, lpc_batch** out);
 int lpc_batch_destroy(lpc_batch* b);
 void* lpc_batch_device_ptr(lpc_batch* b);                 /* [n_stores][nvars] pairs */
