@@ -566,7 +566,8 @@ static int pc_fixpoint_async(const lpc_pc_table* t, lpc_store* s, const lpc_fixp
   if(!o) { lpc_fixpoint_default_opts(&def); o = &def; }
   cudaStream_t st = (cudaStream_t)o->stream;
   int grid = t->sm_count * t->blocks_per_sm[bits];
-  long long want = std::max<long long>(1, std::max<long long>((view->n_tiles * 32 + PC_TPB - 1) / PC_TPB, (view->n_big + PC_TPB - 1) / PC_TPB));
+  long long want = std::max<long long>({1, (view->n_tiles * 32 + PC_TPB - 1) / PC_TPB, ((long long)view->n_big + PC_TPB - 1) / PC_TPB,
+                                        ((long long)s->nvars + 16 * PC_TPB - 1) / (16 * PC_TPB)});   // the last: the prologue's store scan
   if(want < grid) grid = (int)want;
   int2* seen = nullptr;
   if(o->mode != LPC_MODE_SWEEP && view->n_tiles > 0) {   // per tile: the 32 cells last seen

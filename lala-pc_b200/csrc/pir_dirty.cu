@@ -246,7 +246,7 @@ int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opt
   LPC_REQUIRE(per_sm > 0, "kernel does not fit on an SM");
   int grid = t->sm_count * per_sm;
   const long long units = n_pad / 2;
-  grid = (int)std::max<long long>(1, std::min<long long>(grid, (units + DTPB - 1) / DTPB));
+  grid = (int)std::max<long long>(1, std::min<long long>(grid, std::max<long long>((units + DTPB - 1) / DTPB, ((long long)s->nvars + 16 * DTPB - 1) / (16 * DTPB))));
   DSeg seg;
   seg.nseg = t->seg_n;
   for(int i = 0; i <= t->seg_n; ++i) seg.u[i] = t->seg_q[i] * 2;

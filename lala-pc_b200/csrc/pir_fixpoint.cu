@@ -297,7 +297,9 @@ int lpc_fixpoint_async(const lpc_table* tc, lpc_store* s, const lpc_fixpoint_opt
   // enough blocks to fill the chip, no more than there are thread-loads of work
   const long long units = t->dev.n_pad / var.rpt;
   int grid = t->sm_count * per_sm;
-  long long want = std::max<long long>(1, (units + TPB - 1) / TPB);
+  // enough blocks for the records - and for the prologue's scan of the store (a handful of records over a million
+  // variables would otherwise leave that scan to one block: 400 us)
+  long long want = std::max<long long>({1, (units + TPB - 1) / TPB, ((long long)s->nvars + 16 * TPB - 1) / (16 * TPB)});
   if(want < grid) grid = (int)want;
   SegTable seg;
   seg.nseg = t->seg_n;
