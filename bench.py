@@ -136,7 +136,9 @@ def c4_config(world, scaling):
     return {"workload": "batched EPS: %d subproblem stores %s of a 2000-var / 10000-propagator PIR model, one thread "
                         "group per store (BASELINE.json configs[3])" % (STORES, "per GPU" if scaling == "weak" else "in total"),
             "scaling": scaling, "stores_per_gpu": per, "stores_total": per * world, "decision_bits": nbits,
-            "mode": "every sweep evaluates every propagator (the reference's work unit)"}
+            "mode": "every sweep evaluates every propagator (the reference's work unit)",
+            "l2": "GPU arm: L2 flushed between timed steps (a 512 MiB write); the step's inputs are the 16 KB root store, the "
+                  "subproblem ids and the 80 KB table"}
 
 
 def build_c4():
