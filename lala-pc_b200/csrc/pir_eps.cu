@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   const size_t store_stride = (size_t)A.nvars;
   unsigned long long* tbar = &bars[G];
   const int np = A.hdr->np;
-  const int np1 = A.ptab1 ? A.hdr[1].np : 0;   // > 0: sweep 1 of every store runs on the first-sweep table
+  // > 0: sweep 1 of every store runs on the first-sweep table (not under a sweep budget: a caller who asks for k sweeps gets
+  // k full ones)
+  const int np1 = (A.ptab1 && A.max_sweeps == 0) ? A.hdr[1].np : 0;
 
   if(threadIdx.x == 0) {
     for(int i = 0; i <= G; ++i) mbar_init(&bars[i], 1);
