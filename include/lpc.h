@@ -265,7 +265,9 @@ int lpc_eps_solve_host(lpc_eps* e, const int32_t* root_lbub, const int32_t* deci
                        const int64_t* ids, int64_t first_id, int32_t n, const lpc_fixpoint_opts* o, int32_t objective_var,
                        uint8_t* flags, int32_t* survivors_lbub, int32_t* survivor_index, int32_t max_survivors,
                        int32_t* n_written, lpc_eps_result* r);
-/* The same in steps, for a problem that stays resident on the device between runs (bench.py's device-timed figure). */
+/* The same in steps, for a problem that stays resident on the device between runs (bench.py's device-timed figure). What
+ * is derived from the table, the root and the decision list alone - the packed table without the propagators entailed on
+ * the root, the first-sweep table - is built by the first run after an upload and kept until the next upload. */
 int lpc_eps_upload(lpc_eps* e, const int32_t* root_lbub, const int32_t* decision_vars, int32_t n_decisions,
                    const int64_t* ids, int64_t first_id, int32_t n);
 int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_var);

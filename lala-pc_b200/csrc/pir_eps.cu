@@ -711,6 +711,9 @@ struct lpc_eps {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t last_stream = nullptr;
   bool pending = false, have_ids = false, uploaded = false;
+  // The packed tables (k_pack_table) are a function of the table, the root, the decision list and the mode: they are kept
+  // from one run to the next until lpc_eps_upload brings a new problem (-1: none packed yet)
+  int packed_mode = -1;
   long long first_id = 0;
   int n = 0, ndec = 0;
   GroupPlan plan;
@@ -826,6 +829,7 @@ static int eps_upload(lpc_eps* e, const int32_t* root, const int32_t* dvars, int
   if(ndec) LPC_CUDA(cudaMemcpyAsync(e->d_dvars, dvars, (size_t)ndec * 4, cudaMemcpyHostToDevice, st));
   if(ids && n) LPC_CUDA(cudaMemcpyAsync(e->d_ids, ids, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   e->have_ids = ids != nullptr; e->first_id = first_id; e->n = n; e->ndec = ndec; e->uploaded = true;
+  e->packed_mode = -1;
   return LPC_OK;
 }
 
@@ -857,8 +861,12 @@ int lpc_eps_run_async(lpc_eps* e, const lpc_fixpoint_opts* o, int32_t objective_
   // drops the ones entailed on the root
   const int2* elim_root = o->mode == LPC_MODE_SWEEP ? nullptr : e->d_root;
   uint2* ptab1 = (elim_root && e->plan.cap1 > 0 && e->ndec > 0) ? (uint2*)((char*)e->d_ptab + e->plan.ptab_bytes) : nullptr;
-  k_pack_table<<<1, PK_T, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr, e->d_dvars, e->ndec, ptab1, e->plan.cap1, e->d_root);
-  g_launches++;
+  const int pack_mode = o->mode == LPC_MODE_SWEEP ? 1 : 0;
+  if(e->packed_mode != pack_mode) {
+    k_pack_table<<<1, PK_T, 0, st>>>(t->dev, t->opsegs, elim_root, (uint2*)e->d_ptab, e->d_phdr, e->d_dvars, e->ndec, ptab1, e->plan.cap1, e->d_root);
+    g_launches++;
+    e->packed_mode = pack_mode;
+  }
   LPC_CUDA(cudaGetLastError());
   if(e->n > 0) {
     GroupArgs A{};
