@@ -251,6 +251,9 @@ def own_eps(args, rank, world, scaling, ctx, steps=None, warmup=None, check=True
                                  "sweeps_total": float(tot[2]), "max_sweeps_seen": res.max_sweeps_seen,
                                  "deductions_per_step": float(tot[1])},
                 "measurement": {"timing": "CUDA events on the launching stream around lpc_eps_run_async + the all-reduce, max over ranks",
+                                "resident": "root, decision list, ids, the record table and what is derived from them alone (the packed "
+                                            "table, built by the first warm-up run after the upload) stay in HBM across steps; every "
+                                            "step generates and solves all subproblems anew; the e2e figure uploads and packs per call",
                                 "l2": "flushed between steps (512 MiB write); the kernel's inputs are the 16 KB root store, the "
                                       "subproblem ids and the 80 KB table",
                                 "sharding": "consecutive ids" if world == 1 else "each rank a uniform sample of the id space (sharding.py)",
