@@ -39,7 +39,7 @@ struct DSeg { int nseg; int u[D_MAX_SEG + 1]; };   // opcode segments in units o
 template <bool HAS_DIV>
 __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, DSeg seg, FixCtl* ctl, unsigned char* dmap,
                                                        int n_groups, int map_stride, unsigned switch_groups, int max_sweeps,
-                                                       int stop_on_bot, int sm_order, int strided) {
+                                                       int stop_on_bot, int sm_order, int strided, int ask_every) {
   __shared__ unsigned long long s_vote;
   __shared__ unsigned s_cnt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -77,9 +77,12 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
     int f = 0;
     unsigned my_groups = 0, my_evals = 0;
     // One warp-step: this lane's unit u (2 records) of a 64-record group, evaluated iff `active`; then the group's flags.
+    // entailment is looked for in the first sweeps, where it is found (config 2: the `*` and `<=` records decided by the
+    // first sweep), and every fourth sweep afterwards: striking a group is an optimisation, never a need
+    const bool do_ask = ask_every <= 1 || sweeps < 3 || (sweeps % ask_every) == 0;
     auto eval_unit = [&](int u, bool active) {
       int g1 = 0;
-      bool ent = active;                      // both records of this lane entailed on the bounds just computed
+      bool ent = active && do_ask;                      // both records of this lane entailed on the bounds just computed
       int cv[6] = {-1, -1, -1, -1, -1, -1};   // variables this lane tightened (2 records x 3 operands)
       if(active) {
         const uchar2 o = reinterpret_cast<const uchar2*>(t.op)[u];
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(DTPB, 3) k_pir_dirty(TableDev t, int2* store, 
           const int2 a = h ? a1v : a0v, b = h ? b1v : b0v, c = h ? c1v : c0v;
           Itv r1(a.x, a.y), r2(b.x, b.y), r3(c.x, c.y);
           deduce_regs<HAS_DIV>(op, r1, r2, r3);
-          ent &= ask_regs(op, r1, r2, r3);
+          if(do_ask) ent &= ask_regs(op, r1, r2, r3);
           const bool slow = (r1.lb > a.x) | (r1.ub < a.y) | (r2.lb > b.x) | (r2.ub < b.y) | (r3.lb > c.x) | (r3.ub < c.y)
                           | (a.x > a.y) | (b.x > b.y) | (c.x > c.y);
           if(slow) {
@@ -266,7 +269,9 @@ int lpc_dirty_fixpoint_launch(lpc_table* t, lpc_store* s, const lpc_fixpoint_opt
   if(const char* e = getenv("LPC_SMORDER")) sm_order = atoi(e);
   int strided = 1;    // LPC_DIRTY_STRIDED=0: flagged sweeps keep the contiguous block shares (A/B runs)
   if(const char* e = getenv("LPC_DIRTY_STRIDED")) strided = atoi(e);
-  void* args[] = {&td, &store, &seg, &ctl, &dmap, &ng, &ms, &switch_groups, &max_sweeps, &stop, &sm_order, &strided};
+  int ask_every = 4;
+  if(const char* e = getenv("LPC_ASK_EVERY")) ask_every = atoi(e);
+  void* args[] = {&td, &store, &seg, &ctl, &dmap, &ng, &ms, &switch_groups, &max_sweeps, &stop, &sm_order, &strided, &ask_every};
   void* k = t->has_div ? (void*)k_pir_dirty<true> : (void*)k_pir_dirty<false>;
   LPC_CUDA(cudaLaunchCooperativeKernel(k, dim3(grid), dim3(DTPB), args, 0, st));
   g_launches++;
