@@ -117,7 +117,7 @@ __device__ __forceinline__ bool block_fixpoint_cd(const TableDev& t, const int2*
                                                   int stop_on_bot, int& sweeps_out) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
   const int npad = (int)t.n_pad;
-  if(tid == 0) { *s_bot = 0; *s_evals = 0; }
+  if(tid == 0) { s_bot[0] = 0; s_bot[4] = 0; *s_evals = 0; }   // two bot words, one per sweep parity (see k_pir_batch)
   for(int i = tid; i < 3 * ngp; i += nthr) dmap[i] = (seed_mode == 0 && i < ng) ? 1 : 0;
   int f0 = 0;
   for(int v = tid; v < t.nvars; v += nthr) { int2 d = S[v]; f0 |= d.x > d.y; }
@@ -162,10 +162,11 @@ __device__ __forceinline__ bool block_fixpoint_cd(const TableDev& t, const int2*
         }
       }
     }
+    volatile int* sb = s_bot + 4 * (sweeps & 1);
     ++sweeps;
-    if(f & 2) *s_bot = 1;
+    if(f & 2) *sb = 1;
     const int any_chg = __syncthreads_or(f & 1);
-    bot |= *s_bot != 0;
+    bot |= *sb != 0;
     changed = any_chg && !(bot && stop_on_bot) && !(max_sweeps && sweeps >= max_sweeps);
   }
   if(lane == 0 && evals) atomicAdd(s_evals, evals);
@@ -254,18 +255,22 @@ __global__ void k_pir_batch(TableDev t, OpSegs segs, int2* stores, int n_stores,
     }
     else {
       // bot before the first sweep?
-      if(tid == 0) *s_bot = 0;
+      // Two bot words (smem + 36 and + 52), one per sweep parity: a thread that has left the sweep-ending barrier and runs
+      // ahead into the next sweep must not change what a slower thread is about to read as the outcome of the sweep
+      // just ended - else the two disagree on whether the store has failed and meet different barriers.
+      if(tid == 0) { s_bot[0] = 0; s_bot[4] = 0; }
       int f0 = 0;
       for(int v = tid; v < t.nvars; v += nthr) { int2 d = S[v]; f0 |= d.x > d.y; }
       bot = __syncthreads_or(f0) != 0;
       bool changed = !(bot && stop_on_bot) && t.n > 0;
       while(changed) {
         const int f = sweep_table<HAS_DIV, TABLE_SMEM ? 1 : 0, true>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+        volatile int* sb = s_bot + 4 * (sweeps & 1);
         ++sweeps;
-        if(f & 2) *s_bot = 1;
-        // one barrier per sweep: it publishes the sweep's shared-memory joins, votes has_changed, and orders s_bot
+        if(f & 2) *sb = 1;
+        // one barrier per sweep: it publishes the sweep's shared-memory joins, votes has_changed, and orders the bot word
         const int any_chg = __syncthreads_or(f & 1);
-        bot |= *s_bot != 0;
+        bot |= *sb != 0;
         changed = any_chg && !(bot && stop_on_bot) && !(max_sweeps && sweeps >= max_sweeps);
       }
       ded_store = (long long)sweeps * t.n;
@@ -333,7 +338,7 @@ __device__ __forceinline__ bool block_fixpoint(const TableDev& t, const OpSegs& 
                                                const int* sz, const uint8_t* sop, unsigned a_x, unsigned a_y, unsigned a_z,
                                                unsigned a_op, volatile int* s_bot, long long& sweeps_acc) {
   const int tid = threadIdx.x, nthr = blockDim.x, npad = (int)t.n_pad;
-  if(tid == 0) *s_bot = 0;
+  if(tid == 0) { s_bot[0] = 0; s_bot[4] = 0; }   // two bot words, one per sweep parity (see k_pir_batch)
   int f0 = 0;
   for(int v = tid; v < t.nvars; v += nthr) { int2 d = S[v]; f0 |= d.x > d.y; }
   bool bot = __syncthreads_or(f0) != 0;
@@ -341,10 +346,11 @@ __device__ __forceinline__ bool block_fixpoint(const TableDev& t, const OpSegs& 
   int sweeps = 0;
   while(changed) {
     const int f = sweep_table<HAS_DIV, TABLE_SMEM ? 1 : 0, false>(segs, npad, a_S, sx, sy, sz, sop, a_x, a_y, a_z, a_op, tid, nthr);
+    volatile int* sb = s_bot + 4 * (sweeps & 1);
     ++sweeps;
-    if(f & 2) *s_bot = 1;
+    if(f & 2) *sb = 1;
     const int any_chg = __syncthreads_or(f & 1);
-    bot |= *s_bot != 0;
+    bot |= *sb != 0;
     changed = any_chg && !bot;
   }
   sweeps_acc += sweeps;

@@ -224,15 +224,23 @@ __device__ __forceinline__ uint4 lds_v4(unsigned addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void gbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// Named barriers of a thread group. `bar.sync` / `bar.red` are the .aligned forms: every thread of a warp must execute them
+// together, so a warp that may still be split by an earlier data-dependent branch (the per-lane exit of the ask loop, a
+// predicated atomic) is brought back together first (compute-sanitizer synccheck flags it otherwise).
+__device__ __forceinline__ void gbar_sync(int id, int n) {
+  __syncwarp();
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
 __device__ __forceinline__ int gbar_or(int id, int n, int pred) {
   int r;
+  __syncwarp();
   asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.or.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
                : "=r"(r) : "r"(id), "r"(n), "r"(pred) : "memory");
   return r;
 }
 __device__ __forceinline__ int gbar_and(int id, int n, int pred) {
   int r;
+  __syncwarp();
   asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.and.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
                : "=r"(r) : "r"(id), "r"(n), "r"(pred) : "memory");
   return r;
@@ -376,11 +384,15 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);   // [grp]: store slot, [G]: table
   // per group 64 B of scalars: the scheduler's next store, the bot word, the records evaluated on the current store, and
   // the group's running totals (kept here rather than in thread 0's registers: they would be live in every thread)
-  struct GroupAcc { int next; int bot; unsigned nev; int best; long long sol, nbot, unk, sweeps, ded; int maxsw; int pad; };
+  struct GroupAcc { int next; int bot; unsigned nev; int best; long long sol, nbot, unk, sweeps, ded; int maxsw; int bot1; };
   static_assert(sizeof(GroupAcc) <= 64, "group scalars");
   GroupAcc* ga = reinterpret_cast<GroupAcc*>(smem + 128 + 64 * grp);
   int* s_next = &ga->next;
+  // Two bot words, one per sweep parity: a thread that has left the sweep-ending barrier and runs ahead into the next
+  // sweep must not change what a slower thread is about to read as the outcome of the sweep just ended (else the two
+  // disagree on whether the store has failed and part ways on the group's barrier)
   volatile int* s_bot = &ga->bot;
+  volatile int* s_bot1 = &ga->bot1;
   unsigned* s_nev = &ga->nev;
   PackedHdr* sh = reinterpret_cast<PackedHdr*>(smem + 640);
   PackedHdr* sh1 = reinterpret_cast<PackedHdr*>(smem + 640 + 192);
@@ -395,9 +407,12 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
   // k full ones)
   const int np1 = (A.ptab1 && A.max_sweeps == 0) ? A.hdr[1].np : 0;
 
+  int* s_groups_done = reinterpret_cast<int*>(smem + 96);   // behind the G + 1 mbarriers of the first 128 bytes
+  static_assert((G + 1) * 8 <= 96, "mbarriers overlap the group counter");
   if(threadIdx.x == 0) {
     for(int i = 0; i <= G; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
+    *s_groups_done = 0;
   }
   if(threadIdx.x < (int)(sizeof(PackedHdr) / 4)) {
     reinterpret_cast<int*>(sh)[threadIdx.x] = reinterpret_cast<const int*>(A.hdr)[threadIdx.x];
@@ -419,13 +434,14 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
 
   if(tid == 0) { ga->best = LPC_INF; ga->sol = ga->nbot = ga->unk = ga->sweeps = ga->ded = 0; ga->maxsw = 0; }
   unsigned phase = 0;
-  const unsigned a_sbot = smem_u32(const_cast<int*>(s_bot));
+  const unsigned a_sbot0 = smem_u32(const_cast<int*>(s_bot)), a_sbot1 = smem_u32(const_cast<int*>(s_bot1));
   while(cur >= 0) {
     if(tid == 0) {   // claim the next store of this group
       int nx = atomicAdd(&A.ctl->next_store, 1);
       if(nx >= A.n_stores) nx = -1;
       *s_next = nx;
       *s_bot = 0;
+      *s_bot1 = 0;
       *s_nev = 0;
     }
     mbar_wait(&bars[grp], phase);
@@ -469,11 +485,12 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
     while(changed) {
       // The root is a common fixpoint of the table (k_pack_table checked), so in the first sweep of a subproblem only the
       // propagators that mention a halved decision variable can move anything: a few hundred records instead of all.
+      const unsigned a_sbot = (sweeps & 1) ? a_sbot1 : a_sbot0;   // this sweep's bot word
       const int f = (np1 > 0 && sweeps == 0) ? pk_sweep<HAS_DIV, JOIN>(*sh1, a_T1, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev)
                                                     : pk_sweep<HAS_DIV, JOIN>(*sh, a_T, a_S, tid, nthr, fin, a_sbot, A.stop_on_bot, nev);
       ++sweeps;
       const int any_chg = gbar_or(bid, nthr, f & 1);   // the bot word was written where the variable was emptied
-      bot |= *s_bot != 0;
+      bot |= lds_s32(a_sbot) != 0;   // complete: every thread of the group has finished the sweep that wrote it
       changed = any_chg && !(bot && A.stop_on_bot) && !(A.max_sweeps && sweeps >= A.max_sweeps);
     }
     nev = __reduce_add_sync(0xffffffffu, nev);
@@ -538,11 +555,10 @@ __global__ void __launch_bounds__(1024, 1) k_pir_group(GroupArgs A) {
     atomicAdd((unsigned long long*)&A.ctl->deductions, (unsigned long long)ga->ded);
     atomicMax(&A.ctl->max_sweeps_seen, ga->maxsw);
     __threadfence();
-  }
-  // the block that finishes last publishes the all-reduce payload (BatchCtl::payload)
-  __syncthreads();
-  if(threadIdx.x == 0) {
-    const int done = atomicAdd(&A.ctl->done_blocks, 1);
+    // The group that finishes last in its block reports the block, and the block that finishes last publishes the
+    // all-reduce payload (BatchCtl::payload). No block-wide barrier here: the other groups are still on their named ones.
+    const bool last_group = atomicAdd(s_groups_done, 1) == G - 1;
+    const int done = last_group ? atomicAdd(&A.ctl->done_blocks, 1) : -1;
     if(done == (int)gridDim.x - 1) {
       __threadfence();
       unsigned long long* red = reinterpret_cast<unsigned long long*>(A.ctl->red);   // read where the atomics landed (L2)
