@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(PK_T) k_pack_table(TableDev t, OpSegs segs, co
   const bool want1 = dvars != nullptr && root != nullptr && out1 != nullptr && cap1 >= 2 && t.nvars <= 8192;
   if(tid < 256) s_dmap[tid] = 0;
   if(tid == 0) { s_moves = 0; s_rflags = 0; }
+  // both headers travel to shared memory as whole structs: the entries behind the last run are zero, not whatever the
+  // allocation held
+  for(int i = tid; i < (int)(2 * sizeof(PackedHdr) / 4); i += PK_T) reinterpret_cast<int*>(hdr)[i] = 0;
   __syncthreads();
   if(scan_root) {   // what every subproblem store inherits from the root (halving a variable keeps its bounds inside the old ones)
     int rf = 0;
